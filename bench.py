@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native CartPole MPPI rollout path.
+
+Workload (BASELINE.json configs[1]): open-loop batched cartpole_ode explicit-Euler rollouts, 1M cartpoles x 500
+integrator substeps (T = 50 control steps x n = 10 substeps of 2 ms, the predictor_ODE_v0 operating point), random
+controls, full trajectory materialised as predictor.predict_core returns it.  One "step" = one pass over the batch
+= B*T*n state-steps.  N > 1: every rank runs its own batch (weak scaling, no data-path collective).
+
+  python bench.py --gpus N --steps K --warmup W            # ours (CUDA through the C ABI)
+  python bench.py --impl reference --gpus N ...            # the reference algorithm's CPU port on the host cores
+
+Prints ONE JSON line on rank 0.  Also measured inside the same run and attached to the line:
+  e2e           same pass through cps_rollout_host with pinned HOST buffers (H2D of s0+Q, D2H of the trajectory)
+  roofline      algorithmic FLOPs (32 per state-step) / CUDA-event kernel time vs the FP32 peak
+                measured in place by cps_measure_peaks; MUFU and HBM views beside it
+  cpu_baseline  the oracle (C restatement of the reference, OpenMP over rollouts) on a bounded sample, host cores
+  mppi_solve    MPPI solve latency at K=2000, T=50 (BASELINE.json configs[0]/metric second half)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+FLOP_PER_STATE_STEP = 32.0   # 24 (ODE rhs) + 8 (integrator), FMA = 2
+MUFU_PER_STATE_STEP = 3.0    # rcp + sin + cos when the MUFU path is used; 1 (rcp) with the accurate sincosf
+B_DEFAULT, T_DEFAULT, N_SUB, DT = 1 << 20, 50, 10, 0.02
+METRIC = "rollout_state_steps_per_sec"
+UNIT = "state-steps/s"
+
+
+def workload_name(B, T):
+    return (f"open-loop cartpole_ode explicit-Euler rollouts (predictor_ODE_v0), {B} cartpoles x {T * N_SUB} substeps "
+            f"(T={T} x n={N_SUB}, dt={DT}), random controls, trajectory [T+1,6,B] materialised")
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index=0, period=0.05):
+        super().__init__(daemon=True)
+        self.period, self.stop_flag, self.samples, self.reasons = period, False, [], set()
+        self.max_mhz = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+                 nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake"}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def make_inputs(B, T, seed):
+    """Synthetic inputs of SURVEY.md 8(d) C2: per-cartpole random state, Q ~ U(-1, 1)."""
+    rng = np.random.default_rng(seed)
+    ang = rng.uniform(-np.pi, np.pi, B).astype(np.float32)
+    s0 = np.stack([ang, rng.uniform(-5, 5, B), np.cos(ang), np.sin(ang), rng.uniform(-0.8 * 0.198, 0.8 * 0.198, B),
+                   rng.uniform(-0.5 * 0.198, 0.5 * 0.198, B)], 1).astype(np.float32)
+    Q = rng.uniform(-1, 1, (T, B)).astype(np.float32)  # time-major
+    return s0, Q
+
+
+def cpu_port_rate(B_sample, T, threads=None, repeats=1, seed=0):
+    """state-steps/s of the oracle port (cps_oracle_rollout_v0, OpenMP) on this host."""
+    from oracle import oracle as O
+    if threads:
+        O.lib().cps_oracle_set_num_threads(int(threads))
+    s0, Q = make_inputs(B_sample, T, seed)
+    Qr = np.ascontiguousarray(Q.T)
+    O.rollout("ODE_v0", s0[:64], Qr[:64], n=N_SUB, dt=DT)  # warm up (thread pool, page faults)
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        O.rollout("ODE_v0", s0, Qr, n=N_SUB, dt=DT)
+        dt_ = time.perf_counter() - t0
+        best = dt_ if best is None else min(best, dt_)
+    return B_sample * T * N_SUB / best, best, O.lib().cps_oracle_num_threads()
+
+
+def run_reference(args):
+    """--impl reference: the reference's algorithm on the host cores.  The reference is pure Python (numba + numpy)
+    and cannot travel to the GPU box, so this is the oracle port (kind "port"), OpenMP over all host threads; each
+    step is a bounded sample of the workload (B_sample cartpoles of the 1M)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    T = args.horizon
+    cores = os.cpu_count() or 1
+    # size the sample for ~2 s per step
+    rate, _, threads = cpu_port_rate(4096, T)
+    B_sample = int(min(args.batch, max(4096, rate * 2.0 / (T * N_SUB))))
+    from oracle import oracle as O
+    s0, Q = make_inputs(B_sample, T, 0)
+    Qr = np.ascontiguousarray(Q.T)
+    for _ in range(args.warmup):
+        O.rollout("ODE_v0", s0, Qr, n=N_SUB, dt=DT)
+    times = []
+    for _ in range(args.steps):
+        t1 = time.perf_counter()
+        O.rollout("ODE_v0", s0, Qr, n=N_SUB, dt=DT)
+        times.append(time.perf_counter() - t1)
+    total = float(np.sum(times))
+    value = B_sample * T * N_SUB * args.steps / total
+    sample = f"{B_sample} of {args.batch} cartpoles x {T * N_SUB} substeps per step"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (f64 inside a control step)",
+            "data": "synthetic", "config": {"workload": workload_name(args.batch, T), "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                             "host_cores": cores},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def mppi_latency(device, n_calls=1000):
+    """MPPI solve latency at K=2000, T=50 through the reference-facing optimizer.step(s): numpy state in, numpy
+    control out (the reference's Q_update_time analogue, CartPole/__init__.py:494,521)."""
+    import torch
+    import cartpolesimulation_b200 as cps
+    from cartpolesimulation_b200.optimizer_mppi_b200 import optimizer_mppi_b200
+    K, T = 2000, 50
+    vp = cps.VariableParameters(target_position=0.0, target_equilibrium=1.0, L=0.395, m_pole=0.087)
+    out = {}
+    for pred in ("ODE_v0", "ODE"):
+        opt = optimizer_mppi_b200(predictor=pred, cost_function=cps.CostFunctionWrapper(),
+                                  control_limits=([-1.0], [1.0]), seed=1, mpc_horizon=T, num_rollouts=K)
+        opt.cost_function.configure(batch_size=K, horizon=T, variable_parameters=vp,
+                                    cost_function_specification="quadratic_boundary_grad_minimal")
+        opt.configure(num_states=6, num_control_inputs=1, dt=DT, predictor_specification=pred)
+        a = np.pi - 1e-3
+        s = np.array([a, 0.0, np.cos(a), np.sin(a), 0.0, 0.0], dtype=np.float32)
+        for _ in range(50):
+            opt.step(s)
+        lat = np.empty(n_calls)
+        for i in range(n_calls):
+            t0 = time.perf_counter()
+            opt.step(s)
+            lat[i] = time.perf_counter() - t0
+        # kernel-only time with CUDA events on the launching stream
+        eng = opt.engine
+        noise = torch.randn((eng.n_ind, K), device=eng.device)
+        s_dev = torch.from_numpy(s).to(eng.device)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ks = []
+        for i in range(60):
+            e0.record()
+            eng.mppi_step(s_dev, noise, 1, 0.0)
+            e1.record()
+            e1.synchronize()
+            if i >= 10:
+                ks.append(e0.elapsed_time(e1))
+        out[pred] = {"latency_ms_median": float(np.median(lat) * 1e3), "latency_ms_p99": float(np.percentile(lat, 99) * 1e3),
+                     "kernel_ms_median": float(np.median(ks)), "calls": n_calls,
+                     "state_steps_per_solve": K * T * N_SUB}
+    out["config"] = "K=2000, T=50, n=10, cost quadratic_boundary_grad_minimal, optimizer_mppi_b200.step(numpy s) -> numpy u"
+    return out
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from cartpolesimulation_b200.core import Engine
+    from cartpolesimulation_b200 import _lib as L
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, T = args.batch, args.horizon
+    eng = Engine(B, T, dt=DT, substeps=N_SUB, integrator="ODE_v0", cost=None, device=local_rank,
+                 fast_sincos=args.fast_sincos)
+    s0_np, Q_np = make_inputs(B, T, seed=1234 + rank)
+    s0 = torch.from_numpy(s0_np).to(dev)
+    Q = torch.from_numpy(Q_np).to(dev)           # [T, B] time-major, 200 MB > L2 (126 MB): no L2 flush needed
+    traj = torch.empty((T + 1, 6, B), device=dev)  # 1.22 GB, written every step
+
+    def one_pass():
+        eng.rollout(s0, Q, q_layout=L.TIME_MAJOR, traj_layout=L.TIME_MAJOR, traj_out=traj)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        one_pass()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = eng.launch_count()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    t_all0 = torch.cuda.Event(enable_timing=True)
+    t_all1 = torch.cuda.Event(enable_timing=True)
+    t_all0.record()
+    for e0, e1 in evs:
+        e0.record()
+        one_pass()
+        e1.record()
+    t_all1.record()
+    barrier()
+    launches = eng.launch_count() - launches0
+    total_ms = t_all0.elapsed_time(t_all1)
+    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+    sampler.stop_flag = True
+    sampler.join(timeout=1.0)
+    if world > 1:
+        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    steps_per_pass = float(B) * T * N_SUB
+    value = steps_per_pass * args.steps * world / (total_ms * 1e-3)
+
+    # ---- e2e: host buffers through cps_rollout_host (pinned), H2D + kernel + D2H inside the timed region --------
+    s0_pin = torch.from_numpy(s0_np).pin_memory()
+    Q_pin = torch.from_numpy(Q_np).pin_memory()
+    traj_pin = torch.empty((T + 1, 6, B), pin_memory=True)
+    e2e_steps = max(2, min(args.steps, 5))
+    for _ in range(2):
+        eng.rollout_host(s0_pin.numpy(), Q_pin.numpy(), L.TIME_MAJOR, L.TIME_MAJOR, traj_out=traj_pin.numpy())
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        eng.rollout_host(s0_pin.numpy(), Q_pin.numpy(), L.TIME_MAJOR, L.TIME_MAJOR, traj_out=traj_pin.numpy())
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = steps_per_pass * e2e_steps * world / e2e_s
+    h2d = s0_pin.numel() * 4 + Q_pin.numel() * 4
+    d2h = traj_pin.numel() * 4
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (rollout_kernel) ------------------------------------------------------
+    fp32_peak, mufu_peak = eng.measure_peaks()
+    rate_1gpu = steps_per_pass / (kern_ms * 1e-3)
+    achieved_tflops = rate_1gpu * FLOP_PER_STATE_STEP / 1e12
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    alg_bytes = 4.0 * B * T + 24.0 * B * (T + 1) + 24.0 * B   # Q in, trajectory out, s0 in
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(REPO, "profiles", "roofline_traffic.json"))).get("rollout_kernel_dram_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = {"bound": "fp32", "kernel": "rollout_kernel<ODE_v0>", "achieved": achieved_tflops, "peak": fp32_peak,
+                "unit": "TFLOP/s", "frac": achieved_tflops / fp32_peak if fp32_peak else None, "traffic": traffic,
+                "peak_source": "cps_measure_peaks FFMA microbenchmark, this run (not in MEASURED_PEAKS.json)",
+                "flop_per_state_step": FLOP_PER_STATE_STEP, "kernel_ms": kern_ms,
+                "mufu": {"achieved_gops": rate_1gpu * (MUFU_PER_STATE_STEP if args.fast_sincos else 1.0) / 1e9,
+                         "peak_gops": mufu_peak},
+                "hbm": {"achieved_gbs": alg_bytes / (kern_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
+                        "frac": alg_bytes / (kern_ms * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes": alg_bytes,
+                        "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}}
+
+    # ---- cpu baseline: oracle port on a bounded sample ---------------------------------------------------------
+    rate0, _, threads = cpu_port_rate(4096, T)
+    B_sample = int(min(B, max(4096, rate0 * 10.0 / (T * N_SUB))))   # ~10 s of CPU work
+    cpu_rate, cpu_s, threads = cpu_port_rate(B_sample, T)
+    cpu_baseline = {"value": cpu_rate, "unit": UNIT, "cores": threads, "kind": "port",
+                    "sample": f"{B_sample} of {B} cartpoles x {T * N_SUB} substeps, {cpu_s:.1f} s",
+                    "host_cores": os.cpu_count()}
+
+    mppi = None
+    if not args.no_mppi:
+        try:
+            mppi = mppi_latency(local_rank, n_calls=args.mppi_calls)
+        except Exception as ex:  # never lose the headline line because of the secondary measurement
+            mppi = {"error": repr(ex)}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(B, T), "per_gpu_batch": B, "l2": "inputs larger than L2 (Q = %d MB)" % (Q.numel() * 4 >> 20),
+                       "sincos": "MUFU" if args.fast_sincos else "sincosf (1 ulp)"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": 1e3 * e2e_s / e2e_steps, "api": "cps_rollout_host (pinned host buffers)"},
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "clocks": sampler.summary(), "mppi_solve": mppi}
+    print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=B_DEFAULT, help="cartpoles per GPU")
+    ap.add_argument("--horizon", type=int, default=T_DEFAULT)
+    ap.add_argument("--fast-sincos", action="store_true", help="MUFU sin/cos variant (parity-checked separately)")
+    ap.add_argument("--no-mppi", action="store_true")
+    ap.add_argument("--mppi-calls", type=int, default=1000)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

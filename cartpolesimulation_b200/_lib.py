@@ -1,0 +1,119 @@
+"""ctypes loader of libcps_b200.so (the C ABI declared in include/cps.h).
+
+There is no CPU fallback: if the library has not been built, or it cannot be loaded, importing callers get
+a RuntimeError that says how to build it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_PKG, "libcps_b200.so")
+_CSRC = os.path.join(_PKG, "csrc")
+
+CPS_OK = 0
+STATUS_NAMES = {0: "CPS_OK", 1: "CPS_ERR_INVALID", 2: "CPS_ERR_CUDA", 3: "CPS_ERR_UNSUPPORTED",
+                4: "CPS_ERR_NOT_CONFIGURED"}
+
+EULER_V0, EULER_CROMER = 0, 1
+COST_NONE, COST_DEFAULT, COST_QUADRATIC_BOUNDARY, COST_QB_GRAD_MINIMAL, COST_QB_GRAD = -1, 0, 1, 2, 3
+NOISE_INDUCING, NOISE_DIRECT = 0, 1
+ROLLOUT_MAJOR, TIME_MAJOR = 0, 1
+FLAG_FAST_SINCOS, FLAG_EXACT_ATAN2, FLAG_FAST_DIV = 0x1, 0x2, 0x4
+PH_COUNT = 9
+
+
+class cps_config(C.Structure):
+    _fields_ = [("struct_size", C.c_int), ("device", C.c_int), ("num_rollouts", C.c_int), ("horizon", C.c_int),
+                ("substeps", C.c_int), ("dt", C.c_float), ("integrator", C.c_int), ("cost_id", C.c_int),
+                ("noise_mode", C.c_int), ("interp_period", C.c_int), ("flags", C.c_uint)]
+
+
+# name -> (restype, argtypes); every symbol include/cps.h declares
+_FP = C.POINTER(C.c_float)
+_VP = C.c_void_p
+SYMBOLS = {
+    "cps_create": (C.c_int, [C.POINTER(cps_config), C.POINTER(_VP)]),
+    "cps_destroy": (None, [_VP]),
+    "cps_last_error": (C.c_char_p, [_VP]),
+    "cps_abi_version": (C.c_int, []),
+    "cps_num_inducing_points": (C.c_int, [C.c_int, C.c_int]),
+    "cps_set_stream": (C.c_int, [_VP, _VP]),
+    "cps_set_physics": (C.c_int, [_VP, _FP, C.c_int]),
+    "cps_set_cost_params": (C.c_int, [_VP, _FP, C.c_int]),
+    "cps_set_mppi_params": (C.c_int, [_VP] + [C.c_float] * 7),
+    "cps_set_variable_parameters": (C.c_int, [_VP] + [C.c_float] * 4),
+    "cps_mppi_step": (C.c_int, [_VP, _VP, _VP, C.c_int, C.c_float, _VP, _VP, _VP, _VP, C.c_int, _VP]),
+    "cps_mppi_step_host": (C.c_int, [_VP, _FP, _VP, C.c_int, C.c_float, _FP]),
+    "cps_mppi_reset": (C.c_int, [_VP, C.c_float]),
+    "cps_mppi_get_u_nom": (C.c_int, [_VP, _FP]),
+    "cps_mppi_set_u_nom": (C.c_int, [_VP, _FP]),
+    "cps_mppi_u_nom_dev": (_VP, [_VP]),
+    "cps_mppi_set_shard": (C.c_int, [_VP, C.c_int, _VP]),
+    "cps_mppi_partial_size": (C.c_int, [_VP]),
+    "cps_mppi_finalize": (C.c_int, [_VP, _VP, C.c_int, _VP, _VP]),
+    "cps_rollout": (C.c_int, [_VP, _VP, C.c_int, _VP, C.c_int, C.c_int, C.c_int, _VP, C.c_int, _VP]),
+    "cps_rollout_host": (C.c_int, [_VP, _VP, C.c_int, _VP, C.c_int, C.c_int, C.c_int, _VP, C.c_int, _VP]),
+    "cps_trajectory_cost": (C.c_int, [_VP, _VP, _VP, C.c_float, C.c_int, C.c_int, _VP]),
+    "cps_stage_cost": (C.c_int, [_VP, _VP, C.c_int, _VP, C.c_float, C.c_int, C.c_int, C.c_int, _VP]),
+    "cps_terminal_cost": (C.c_int, [_VP, _VP, C.c_int, _VP]),
+    "cps_measure_peaks": (C.c_int, [_VP, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "cps_launch_count": (C.c_longlong, [_VP]),
+    "cps_nonfinite_costs": (C.c_int, [_VP, C.POINTER(C.c_int)]),
+}
+
+
+def library_path() -> str:
+    return _SO
+
+
+def build(verbose: bool = False) -> str:
+    """Compile csrc/*.cu for sm_100a into the in-tree libcps_b200.so (nvcc cross-compiles without a GPU)."""
+    out = subprocess.run(["make", "-C", _CSRC], capture_output=True, text=True)
+    if verbose or out.returncode != 0:
+        print(out.stdout[-4000:])
+        print(out.stderr[-4000:])
+    if out.returncode != 0:
+        raise RuntimeError("building libcps_b200.so failed")
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            raise RuntimeError(
+                f"{_SO} is missing: the CUDA extension has not been built.  Build it with "
+                "`python -c 'import __graft_entry__ as g; g.build()'` (or `make -C cartpolesimulation_b200/csrc`). "
+                "cartpolesimulation_b200 has no CPU fallback.")
+        L = C.CDLL(_SO)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(L, name)  # AttributeError if the library does not export a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        if L.cps_abi_version() != 1:
+            raise RuntimeError("libcps_b200.so ABI version mismatch")
+        _lib = L
+    return _lib
+
+
+class CpsError(RuntimeError):
+    pass
+
+
+def check(rc: int, handle=None):
+    if rc == CPS_OK:
+        return
+    msg = lib().cps_last_error(handle)
+    msg = msg.decode() if msg else ""
+    name = STATUS_NAMES.get(rc, str(rc))
+    if rc == 1:
+        raise ValueError(f"{name}: {msg}")
+    if rc == 3:
+        raise NotImplementedError(f"{name}: {msg}")
+    raise CpsError(f"{name}: {msg}")

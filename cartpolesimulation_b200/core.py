@@ -1,0 +1,278 @@
+"""Thin Python object around one cps_handle (include/cps.h).  Device memory, streams and pointers come
+from torch (plumbing); all arithmetic happens in libcps_b200.so.  No CPU fallback."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from . import config as cfgmod
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    return C.c_void_p(t.data_ptr())
+
+
+def _check_dev(t, name, device, dtype=torch.float32):
+    if not isinstance(t, torch.Tensor) or t.device != device:
+        raise ValueError(f"{name} must be a torch tensor on {device}")
+    if t.dtype != dtype:
+        raise ValueError(f"{name} must be {dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+    return t
+
+
+INTEGRATORS = {"ODE_v0": L.EULER_V0, "ODE": L.EULER_CROMER}
+COSTS = {None: L.COST_NONE, "none": L.COST_NONE, "default": L.COST_DEFAULT,
+         "quadratic_boundary": L.COST_QUADRATIC_BOUNDARY,
+         "quadratic_boundary_grad_minimal": L.COST_QB_GRAD_MINIMAL,
+         "quadratic_boundary_grad": L.COST_QB_GRAD}
+
+
+class Engine:
+    """One configured rollout engine = one cps_handle.
+
+    Parameters mirror what controller_mpc.configure wires together
+    (Control_Toolkit/Controllers/controller_mpc.py:42-92): K rollouts, horizon T, n substeps, dt,
+    integrator ('ODE_v0' | 'ODE'), cost plugin name, noise mode.
+    """
+
+    def __init__(self, num_rollouts: int, horizon: int, dt: float = 0.02, substeps: int = 10,
+                 integrator: str = "ODE", cost: str | None = "quadratic_boundary_grad_minimal",
+                 noise_mode: str = "inducing", interp_period: int = 10, device: int | None = None,
+                 fast_sincos: bool = False, exact_atan2: bool = False, fast_div: bool = False):
+        if integrator not in INTEGRATORS:
+            raise ValueError(f"unknown integrator {integrator!r}; expected one of {list(INTEGRATORS)}")
+        if cost not in COSTS:
+            raise ValueError(f"unknown cost function {cost!r}; expected one of {list(COSTS)}")
+        if not torch.cuda.is_available():
+            raise RuntimeError("cartpolesimulation_b200 needs a CUDA device (no CPU fallback)")
+        self.lib = L.lib()
+        dev = torch.cuda.current_device() if device is None else int(device)
+        self.device = torch.device("cuda", dev)
+        flags = (L.FLAG_FAST_SINCOS if fast_sincos else 0) | (L.FLAG_EXACT_ATAN2 if exact_atan2 else 0) \
+            | (L.FLAG_FAST_DIV if fast_div else 0)
+        self.K, self.T, self.n, self.dt, self.p = int(num_rollouts), int(horizon), int(substeps), float(dt), int(interp_period)
+        self.integrator, self.cost_name = integrator, cost
+        self.noise_mode = {"inducing": L.NOISE_INDUCING, "direct": L.NOISE_DIRECT}[noise_mode]
+        c = L.cps_config(C.sizeof(L.cps_config), dev, self.K, self.T, self.n, self.dt, INTEGRATORS[integrator],
+                         COSTS[cost], self.noise_mode, self.p, flags)
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            torch.cuda.init()
+            L.check(self.lib.cps_create(C.byref(c), C.byref(h)), None)
+        self._h = h
+        self.n_ind = self.lib.cps_num_inducing_points(self.T, self.p)
+        self.n_noise = self.n_ind if self.noise_mode == L.NOISE_INDUCING else self.T
+        self._stream = None
+        self._u_dev = torch.zeros(1, device=self.device)
+        self._s_dev = torch.zeros(6, device=self.device)
+        self._u_host = (C.c_float * 1)()
+        self._s_host = (C.c_float * 6)()
+
+    # -- lifetime -------------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.cps_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc):
+        L.check(rc, self._h)
+
+    def use_current_stream(self):
+        s = torch.cuda.current_stream(self.device).cuda_stream
+        if s != self._stream:
+            self._chk(self.lib.cps_set_stream(self._h, C.c_void_p(s)))
+            self._stream = s
+
+    # -- parameters -----------------------------------------------------------------------------------
+    def set_physics(self, **params):
+        v = cfgmod.physics_vector(**params)
+        self._chk(self.lib.cps_set_physics(self._h, v.ctypes.data_as(L._FP), len(v)))
+
+    def set_cost_params(self, vec):
+        v = np.ascontiguousarray(vec, dtype=np.float32)
+        self._chk(self.lib.cps_set_cost_params(self._h, v.ctypes.data_as(L._FP), len(v)))
+
+    def set_cost_config(self, cfg: dict | None = None):
+        self.set_cost_params(cfgmod.cost_vector(self.cost_name, cfg))
+
+    def set_mppi_params(self, cc_weight=1.0, R=1.0, LBD=100.0, NU=1000.0, SQRTRHOINV=0.03, lo=-1.0, hi=1.0):
+        sigma = np.float32(np.array(SQRTRHOINV) * (1 / np.sqrt(self.dt)))  # optimizer_mppi.py:130
+        self._chk(self.lib.cps_set_mppi_params(self._h, cc_weight, R, LBD, NU, float(sigma), lo, hi))
+
+    def set_variable_parameters(self, target_position=0.0, target_equilibrium=1.0, L=0.395, m_pole=0.087):
+        self._chk(self.lib.cps_set_variable_parameters(self._h, float(target_position), float(target_equilibrium),
+                                                        float(np.float32(L)), float(np.float32(m_pole))))
+
+    # -- MPPI -----------------------------------------------------------------------------------------
+    def noise_shape(self, layout=L.TIME_MAJOR):
+        return (self.n_noise, self.K) if layout == L.TIME_MAJOR else (self.K, self.n_noise)
+
+    def mppi_step(self, s, noise, noise_layout=L.TIME_MAJOR, u_prev=0.0, u_nom=None, J_out=None, traj_out=None,
+                  traj_layout=L.ROLLOUT_MAJOR, u_run_out=None):
+        """Device-pointer form (cps_mppi_step).  s: cuda tensor [6]; noise: cuda tensor of noise_shape(layout);
+        u_nom: cuda tensor [T] updated in place (default: the handle's own).  Returns the cuda tensor [1]
+        holding u (no synchronisation)."""
+        self.use_current_stream()
+        _check_dev(s, "s", self.device)
+        _check_dev(noise, "noise", self.device)
+        if tuple(noise.shape[:2]) != self.noise_shape(noise_layout) or noise.numel() != self.n_noise * self.K:
+            raise ValueError(f"noise has shape {tuple(noise.shape)}, expected {self.noise_shape(noise_layout)}")
+        unom_ptr = self.lib.cps_mppi_u_nom_dev(self._h) if u_nom is None else _check_dev(u_nom, "u_nom", self.device).data_ptr()
+        for t, name, numel in ((J_out, "J_out", self.K), (traj_out, "traj_out", self.K * (self.T + 1) * 6),
+                               (u_run_out, "u_run_out", self.K * self.T)):
+            if t is not None:
+                _check_dev(t, name, self.device)
+                if t.numel() != numel:
+                    raise ValueError(f"{name} has {t.numel()} elements, expected {numel}")
+        self._chk(self.lib.cps_mppi_step(self._h, _ptr(s), _ptr(noise), noise_layout, float(u_prev),
+                                         C.c_void_p(unom_ptr), _ptr(self._u_dev), _ptr(J_out), _ptr(traj_out),
+                                         traj_layout, _ptr(u_run_out)))
+        return self._u_dev
+
+    def mppi_step_host(self, s_np, noise, noise_layout=L.TIME_MAJOR, u_prev=0.0) -> float:
+        """Host form (cps_mppi_step_host): numpy state in, python float control out; synchronises."""
+        self.use_current_stream()
+        _check_dev(noise, "noise", self.device)
+        if noise.numel() != self.n_noise * self.K:
+            raise ValueError(f"noise has {noise.numel()} elements, expected {self.n_noise * self.K}")
+        for i in range(6):
+            self._s_host[i] = s_np[i]
+        self._chk(self.lib.cps_mppi_step_host(self._h, self._s_host, _ptr(noise), noise_layout, float(u_prev),
+                                              self._u_host))
+        return self._u_host[0]
+
+    def mppi_reset(self, value=0.0):
+        self.use_current_stream()
+        self._chk(self.lib.cps_mppi_reset(self._h, float(value)))
+
+    def get_u_nom(self) -> np.ndarray:
+        self.use_current_stream()
+        out = np.zeros(self.T, dtype=np.float32)
+        self._chk(self.lib.cps_mppi_get_u_nom(self._h, out.ctypes.data_as(L._FP)))
+        return out
+
+    def set_u_nom(self, u_nom):
+        self.use_current_stream()
+        v = np.ascontiguousarray(np.asarray(u_nom, dtype=np.float32).reshape(-1))
+        if v.shape[0] != self.T:
+            raise ValueError(f"u_nom has {v.shape[0]} entries, expected {self.T}")
+        self._chk(self.lib.cps_mppi_set_u_nom(self._h, v.ctypes.data_as(L._FP)))
+
+    def partial_size(self):
+        return self.lib.cps_mppi_partial_size(self._h)
+
+    def set_shard(self, partial_out):
+        if partial_out is None:
+            self._chk(self.lib.cps_mppi_set_shard(self._h, 0, None))
+        else:
+            _check_dev(partial_out, "partial_out", self.device)
+            if partial_out.numel() < self.partial_size():
+                raise ValueError("partial_out too small")
+            self._chk(self.lib.cps_mppi_set_shard(self._h, 1, _ptr(partial_out)))
+        self._shard_buf = partial_out
+
+    def mppi_finalize(self, partials, u_nom=None):
+        self.use_current_stream()
+        _check_dev(partials, "partials", self.device)
+        n = partials.numel() // self.partial_size()
+        unom_ptr = self.lib.cps_mppi_u_nom_dev(self._h) if u_nom is None else u_nom.data_ptr()
+        self._chk(self.lib.cps_mppi_finalize(self._h, _ptr(partials), n, C.c_void_p(unom_ptr), _ptr(self._u_dev)))
+        return self._u_dev
+
+    # -- rollouts -------------------------------------------------------------------------------------
+    def rollout(self, s0, Q, q_layout=L.ROLLOUT_MAJOR, traj_layout=L.ROLLOUT_MAJOR, want_traj=True,
+                want_final=False, traj_out=None, final_out=None):
+        """cps_rollout on device tensors.  s0: [6] or [B,6]; Q: [B,T] (ROLLOUT_MAJOR) or [T,B] (TIME_MAJOR).
+        Returns (traj, final): traj is [B,T+1,6] (ROLLOUT_MAJOR) or [T+1,6,B] (TIME_MAJOR)."""
+        self.use_current_stream()
+        _check_dev(s0, "s0", self.device)
+        _check_dev(Q, "Q", self.device)
+        Q2 = Q.reshape(Q.shape[0], Q.shape[1])
+        B, T = (Q2.shape if q_layout == L.ROLLOUT_MAJOR else Q2.shape[::-1])
+        if s0.numel() == 6:
+            batched = 0
+        elif s0.shape[0] == B and s0.numel() == 6 * B:
+            batched = 1
+        else:
+            raise ValueError("Batch size of control input contradict batch size of initial state")
+        if want_traj and traj_out is None:
+            shape = (B, T + 1, 6) if traj_layout == L.ROLLOUT_MAJOR else (T + 1, 6, B)
+            traj_out = torch.empty(shape, device=self.device, dtype=torch.float32)
+        if want_final and final_out is None:
+            final_out = torch.empty((B, 6), device=self.device, dtype=torch.float32)
+        self._chk(self.lib.cps_rollout(self._h, _ptr(s0), batched, _ptr(Q2), q_layout, B, T, _ptr(traj_out),
+                                       traj_layout, _ptr(final_out)))
+        return traj_out, final_out
+
+    def rollout_host(self, s0_np, Q_np, q_layout=L.ROLLOUT_MAJOR, traj_layout=L.ROLLOUT_MAJOR, traj_out=None,
+                     final_out=None):
+        """cps_rollout_host on host (numpy) buffers; synchronises.  Outputs are written into the given arrays."""
+        self.use_current_stream()
+        s0_np = np.ascontiguousarray(s0_np, dtype=np.float32)
+        Q_np = np.ascontiguousarray(Q_np, dtype=np.float32)
+        Q2 = Q_np.reshape(Q_np.shape[0], Q_np.shape[1])
+        B, T = (Q2.shape if q_layout == L.ROLLOUT_MAJOR else Q2.shape[::-1])
+        batched = 0 if s0_np.size == 6 else 1
+        if batched and s0_np.shape[0] != B:
+            raise ValueError("Batch size of control input contradict batch size of initial state")
+        vp = lambda a: None if a is None else C.c_void_p(a.ctypes.data)
+        self._chk(self.lib.cps_rollout_host(self._h, vp(s0_np), batched, vp(Q2), q_layout, B, T, vp(traj_out),
+                                            traj_layout, vp(final_out)))
+        return traj_out, final_out
+
+    # -- standalone costs -----------------------------------------------------------------------------
+    def trajectory_cost(self, traj, Q, u_prev=0.0):
+        self.use_current_stream()
+        _check_dev(traj, "traj", self.device)
+        _check_dev(Q, "Q", self.device)
+        K, T = traj.shape[0], traj.shape[1] - 1
+        J = torch.empty((K,), device=self.device, dtype=torch.float32)
+        self._chk(self.lib.cps_trajectory_cost(self._h, _ptr(traj), _ptr(Q), float(u_prev), K, T, _ptr(J)))
+        return J
+
+    def stage_cost(self, traj, Q, u_prev=0.0, unshifted=False):
+        self.use_current_stream()
+        _check_dev(traj, "traj", self.device)
+        _check_dev(Q, "Q", self.device)
+        K, rows, T = traj.shape[0], traj.shape[1], Q.shape[1]
+        st = torch.empty((K, T), device=self.device, dtype=torch.float32)
+        self._chk(self.lib.cps_stage_cost(self._h, _ptr(traj), rows, _ptr(Q), float(u_prev), K, T, int(unshifted),
+                                          _ptr(st)))
+        return st
+
+    def terminal_cost(self, states):
+        self.use_current_stream()
+        _check_dev(states, "states", self.device)
+        K = states.shape[0]
+        out = torch.empty((K,), device=self.device, dtype=torch.float32)
+        self._chk(self.lib.cps_terminal_cost(self._h, _ptr(states), K, _ptr(out)))
+        return out
+
+    def measure_peaks(self):
+        """(FP32 TFLOP/s, MUFU Gop/s) measured on this device by two microbenchmark kernels."""
+        self.use_current_stream()
+        f, m = C.c_double(0), C.c_double(0)
+        self._chk(self.lib.cps_measure_peaks(self._h, C.byref(f), C.byref(m)))
+        return f.value, m.value
+
+    # -- diagnostics ----------------------------------------------------------------------------------
+    def launch_count(self) -> int:
+        return int(self.lib.cps_launch_count(self._h))
+
+    def nonfinite_costs(self) -> int:
+        n = C.c_int(0)
+        self._chk(self.lib.cps_nonfinite_costs(self._h, C.byref(n)))
+        return n.value

@@ -1,0 +1,197 @@
+/*
+ * cps.h -- C ABI of the B200-native CartPole MPPI rollout path (libcps_b200.so).
+ *
+ * This is the drop-in boundary: plain C, opaque handle, raw pointers and sizes, no torch / numpy types.
+ * The Python host side (cartpolesimulation_b200/) binds it with ctypes and mirrors the reference's plugin
+ * interface (optimizer / predictor / cost-function objects) on top.  Citations are file:line relative to
+ * the reference root (SensorsINI/CartPoleSimulation @ a5169e85 with its pinned submodules).
+ *
+ * Conventions
+ *   - "dev" pointers are device pointers on the handle's device; "host" pointers are host memory (pinned
+ *     memory makes the copies asynchronous; pageable memory is accepted and merely slower).
+ *   - All calls are stream-ordered on the handle's stream (cps_set_stream; default: the legacy default
+ *     stream).  *_host entry points synchronise the stream before returning; the others do not.
+ *   - One in-flight call per handle (the reference is single-threaded per controller; its GUI may call
+ *     step() from a worker thread, GUI/_CartPoleGUI_GuiActions.py:195-209).
+ *   - Every function returns CPS_OK (0) or a cps_status error code; cps_last_error() gives the text.
+ *     There is no CPU fallback anywhere: without a CUDA device cps_create fails with CPS_ERR_CUDA.
+ *   - State vector layout (CartPole/state_utilities.py:5-23):
+ *       [0] angle [1] angleD [2] angle_cos [3] angle_sin [4] position [5] positionD
+ */
+#ifndef CPS_H_
+#define CPS_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CPS_ABI_VERSION 1
+#define CPS_STATE_DIM 6
+
+typedef struct cps_handle cps_handle;
+
+typedef enum cps_status {
+    CPS_OK = 0,
+    CPS_ERR_INVALID = 1,        /* bad argument / inconsistent configuration (reference: ValueError) */
+    CPS_ERR_CUDA = 2,           /* CUDA runtime error, or no device (reference: n/a) */
+    CPS_ERR_UNSUPPORTED = 3,    /* valid in the reference but not implemented here (NotImplementedError) */
+    CPS_ERR_NOT_CONFIGURED = 4  /* e.g. cps_net_rollout before cps_net_load */
+} cps_status;
+
+/* Integrator variants:
+ *  CPS_EULER_V0     predictor_ODE_v0: explicit Euler + edge bounce + fmod wrap
+ *                   (CartPole/cartpole_numba.py:56-78, CartPole/cartpole_equations.py:341-364)
+ *  CPS_EULER_CROMER predictor_ODE: semi-implicit Euler + atan2 wrap, no bounce
+ *                   (CartPole/cartpole_equations.py:214-261,292-308) */
+typedef enum cps_integrator { CPS_EULER_V0 = 0, CPS_EULER_CROMER = 1 } cps_integrator;
+
+/* Cost plugins (Control_Toolkit_ASF/Cost_Functions/CartPole/<name>.py) */
+typedef enum cps_cost {
+    CPS_COST_NONE = -1,
+    CPS_COST_DEFAULT = 0,             /* default.py:19-88 */
+    CPS_COST_QUADRATIC_BOUNDARY = 1,  /* quadratic_boundary.py:22-87 */
+    CPS_COST_QB_GRAD_MINIMAL = 2,     /* quadratic_boundary_grad_minimal.py:17-140 */
+    CPS_COST_QB_GRAD = 3              /* quadratic_boundary_grad.py:17-268 */
+} cps_cost;
+
+/* Where the MPPI perturbations come from (Control_Toolkit/Optimizers/optimizer_mppi.py:169-178):
+ *  CPS_NOISE_INDUCING  standard-normal draws at the n_ind inducing points; the kernel scales them by
+ *                      SQRTRHODTINV and interpolates linearly in registers (Interpolator.py:53-106)
+ *  CPS_NOISE_DIRECT    delta_u for every horizon step is supplied as is (post-interpolation injection) */
+typedef enum cps_noise_mode { CPS_NOISE_INDUCING = 0, CPS_NOISE_DIRECT = 1 } cps_noise_mode;
+
+/* Memory order of per-rollout arrays.
+ *  *_ROLLOUT_MAJOR is the reference's order ([K][n_ind] noise, [B][T] controls, [B][T+1][6] trajectories);
+ *  *_TIME_MAJOR is the coalesced order the kernels prefer ([n_ind][K], [T][B], [T+1][6][B]). */
+typedef enum cps_layout { CPS_ROLLOUT_MAJOR = 0, CPS_TIME_MAJOR = 1 } cps_layout;
+
+/* cps_config.flags */
+#define CPS_FLAG_FAST_SINCOS 0x1u   /* MUFU.SIN/COS (__sincosf) instead of the 1-ulp sincosf */
+#define CPS_FLAG_EXACT_ATAN2 0x2u   /* Euler-Cromer wrap by atan2f(sin, cos) as the reference writes it, instead of
+                                       the mathematically identical +-2*pi fold */
+#define CPS_FLAG_FAST_DIV 0x4u      /* MUFU.RCP without the Newton step in the ODE right-hand side */
+
+typedef struct cps_config {
+    int struct_size;      /* = sizeof(cps_config), ABI check */
+    int device;           /* CUDA device ordinal */
+    int num_rollouts;     /* K, optimizer_mppi num_rollouts (config_optimizers.yml:91) */
+    int horizon;          /* T, mpc_horizon (:89) */
+    int substeps;         /* n, intermediate_steps (SI_Toolkit_ASF/config_predictors.yml:21,25) */
+    float dt;             /* mpc_timestep (config_optimizers.yml:90); substep h = dt / n */
+    int integrator;       /* cps_integrator */
+    int cost_id;          /* cps_cost */
+    int noise_mode;       /* cps_noise_mode */
+    int interp_period;    /* p, period_interpolation_inducing_points (config_optimizers.yml:97) */
+    unsigned flags;       /* CPS_FLAG_* */
+} cps_config;
+
+/* Physical parameters, fp32-rounded by the caller as CartPole/cartpole_parameters.py:27-29 does.
+ * Index order of the p[] vector given to cps_set_physics: */
+enum {
+    CPS_PH_K = 0, CPS_PH_M_CART, CPS_PH_M_POLE, CPS_PH_G, CPS_PH_J_FRIC, CPS_PH_M_FRIC, CPS_PH_L, CPS_PH_U_MAX,
+    CPS_PH_TRACK_HALF_LENGTH, CPS_PH_COUNT
+};
+
+/* ---- lifetime -------------------------------------------------------------------------------------- */
+/* Replaces the construction done by controller_mpc.configure (Control_Toolkit/Controllers/controller_mpc.py:42-92):
+ * optimizer + predictor + cost wrapper for one (K, T, n, integrator, cost) configuration.  Physics defaults to
+ * cartpole_physical_parameters.yml:6-17,33-42, cost weights to config_cost_function.yml:5-58 and MPPI parameters
+ * to config_optimizers.yml:87-97 until the cps_set_* calls override them.  The handle owns all scratch
+ * (block partials, ticket, staging buffers); no allocation happens in the step / rollout calls. */
+int cps_create(const cps_config *cfg, cps_handle **out);
+void cps_destroy(cps_handle *h);
+/* Text of the last error on this handle (h == NULL: last cps_create failure on the calling thread). */
+const char *cps_last_error(const cps_handle *h);
+int cps_abi_version(void);
+/* Number of inducing points ceil((T-1)/p)+1 (Control_Toolkit/others/Interpolator.py:79-84). */
+int cps_num_inducing_points(int horizon, int period);
+int cps_set_stream(cps_handle *h, void *cuda_stream /* cudaStream_t */);
+
+/* ---- parameters (cheap; may be called between any two steps) ------------------------------------------- */
+/* CartPoleParameters (CartPole/cartpole_parameters.py:8-31). */
+int cps_set_physics(cps_handle *h, const float *p, int n /* = CPS_PH_COUNT */);
+/* Cost weights in the per-plugin order documented in DESIGN.md "cost parameter vectors"; the hot-reload hook of
+ * cost_function_wrapper.update_cost_parameters_from_config (cost_function_wrapper.py:71-74). */
+int cps_set_cost_params(cps_handle *h, const float *w, int n);
+/* optimizer_mppi.__init__/configure (optimizer_mppi.py:16-138): sqrt_rho_dt_inv = SQRTRHOINV / sqrt(dt) (:130). */
+int cps_set_mppi_params(cps_handle *h, float cc_weight, float R, float LBD, float NU, float sqrt_rho_dt_inv,
+                        float action_low, float action_high);
+/* variable_parameters that may change every control tick (CartPole/__init__.py:512-519):
+ * target_position, target_equilibrium for the cost; L and m_pole for the ODE (m_pole is ignored by
+ * CPS_EULER_V0, predictors_customization_v0.py:47-54 reads only L). */
+int cps_set_variable_parameters(cps_handle *h, float target_position, float target_equilibrium, float L,
+                                float m_pole);
+
+/* ---- the hot path: one MPPI solve ------------------------------------------------------------------- */
+/* optimizer_mppi._predict_and_cost (optimizer_mppi.py:180-192) as ONE kernel launch: warm-start shift, noise
+ * interpolation, clip, K rollouts over T x n substeps, stage + terminal + MPPI-correction cost, exp-weighted update,
+ * clip.  s_dev [6]; noise_dev: INDUCING -> n_ind x K standard-normal draws, DIRECT -> T x K delta_u, in
+ * `noise_layout` order; u_prev = the last returned control (optimizer_mppi.py:210; 0.0 initially,
+ * Optimizers/__init__.py:35); u_nom_dev [T] in/out (the reference's self.u_nom: NOT pre-shifted; the shift
+ * happens at the start of the next solve, :183); u_out_dev [1] = u_nom[0] after the update.
+ * Optional logging outputs (NULL to skip; optimizer_logging, :205-217): J_out_dev [K],
+ * traj_out_dev (K x (T+1) x 6 in traj_layout order), u_run_out_dev ([K][T]). */
+int cps_mppi_step(cps_handle *h, const float *s_dev, const float *noise_dev, int noise_layout, float u_prev,
+                  float *u_nom_dev, float *u_out_dev, float *J_out_dev, float *traj_out_dev, int traj_layout,
+                  float *u_run_out_dev);
+
+/* Host-buffer form of the same call, the one the reference-facing optimizer.step(s) makes: s_host [6] is copied
+ * up, the control comes back in *u_out_host; u_nom lives in the handle (cps_mppi_reset zeroes it like
+ * optimizer_reset, optimizer_mppi.py:226-230).  noise_dev stays a DEVICE pointer: the draws are produced on the
+ * device (the reference draws them inside step() too, :169-175).  Synchronises. */
+int cps_mppi_step_host(cps_handle *h, const float *s_host, const float *noise_dev, int noise_layout, float u_prev,
+                       float *u_out_host);
+int cps_mppi_reset(cps_handle *h, float u_nom_init);
+int cps_mppi_get_u_nom(cps_handle *h, float *u_nom_host /* [T] */);
+int cps_mppi_set_u_nom(cps_handle *h, const float *u_nom_host /* [T] */);
+float *cps_mppi_u_nom_dev(cps_handle *h);
+
+/* K sharded over several GPUs: with cps_mppi_set_shard(h, 1) cps_mppi_step stops after the local
+ * reduction and writes the rank's partial (min J, sum w, sum w*noise[.]) = cps_mppi_partial_size() floats to
+ * partial_out_dev; the ranks exchange them (all-gather) and each calls cps_mppi_finalize on the gathered
+ * [n_ranks][size] array to obtain the identical u_nom / u. */
+int cps_mppi_set_shard(cps_handle *h, int enabled, float *partial_out_dev);
+int cps_mppi_partial_size(const cps_handle *h);
+int cps_mppi_finalize(cps_handle *h, const float *partials_dev, int n_ranks, float *u_nom_dev, float *u_out_dev);
+
+/* ---- open-loop batched rollouts (the predictor interface) ------------------------------------------------ */
+/* predictor.predict_core(s, Q) (SI_Toolkit/src/SI_Toolkit/Predictors/predictor_ODE.py:86-97,
+ * predictor_ODE_v0.py:42-74): B rollouts of T control steps x n substeps.  s0_dev: [B][6] if s0_batched else [6]
+ * (tiled, predictor_ODE_v0.py:59-60); Q_dev: B x T in q_layout order; traj_out_dev: B x (T+1) x 6 in traj_layout
+ * order, row 0 = s0 (may be NULL); final_out_dev: [B][6] last state (may be NULL).  B and T are free per call
+ * (B is not tied to cfg.num_rollouts). */
+int cps_rollout(cps_handle *h, const float *s0_dev, int s0_batched, const float *Q_dev, int q_layout, int B, int T,
+                float *traj_out_dev, int traj_layout, float *final_out_dev);
+/* Host-buffer form: copies s0 and Q up, runs, copies the requested outputs back, synchronises.  Uses handle-owned
+ * device buffers that grow on demand (the only *_host call that may allocate, on first use / growth). */
+int cps_rollout_host(cps_handle *h, const float *s0_host, int s0_batched, const float *Q_host, int q_layout, int B,
+                     int T, float *traj_out_host, int traj_layout, float *final_out_host);
+
+/* ---- standalone cost plugin (for the other optimizers; CostFunctionWrapper interface) ---------------------- */
+/* get_trajectory_cost (Control_Toolkit/Cost_Functions/__init__.py:74-93): traj_dev [K][T+1][6], Q_dev [K][T]
+ * (reference order) -> J_dev [K] = mean over the T+1 entries (stage - MAX_COST ..., terminal). */
+int cps_trajectory_cost(cps_handle *h, const float *traj_dev, const float *Q_dev, float u_prev, int K, int T,
+                        float *J_dev);
+/* get_stage_cost (:49-64): states_dev [K][rows][6] with rows = T (the reference passes state_horizon[:, :-1, :]) or
+ * T+1 (a whole trajectory, last row ignored) -> stage_dev [K][T]; unshifted != 0 gives _get_stage_cost (no MAX_COST). */
+int cps_stage_cost(cps_handle *h, const float *states_dev, int rows, const float *Q_dev, float u_prev, int K, int T,
+                   int unshifted, float *stage_dev);
+
+/* get_terminal_cost (default.py:44-68 etc.): states_dev [K][6] -> out_dev [K]. */
+int cps_terminal_cost(cps_handle *h, const float *states_dev, int K, float *out_dev);
+
+/* Roofline denominators for the compute-bound rollout kernels, measured on this device with two microbenchmarks
+ * (dense FFMA chains; MUFU.EX2 chains): FP32 TFLOP/s (FMA = 2 flops) and MUFU Gop/s.  Synchronises. */
+int cps_measure_peaks(cps_handle *h, double *fp32_tflops, double *mufu_gops);
+
+/* ---- diagnostics ------------------------------------------------------------------------------------- */
+/* Number of kernels this handle has launched so far (bench.py's gpu_launches claim). */
+long long cps_launch_count(const cps_handle *h);
+/* Cumulative count of non-finite trajectory costs seen by cps_mppi_step since cps_create (the reference propagates
+ * NaN silently into exp(); this library does the same arithmetic but counts it).  Synchronises. */
+int cps_nonfinite_costs(cps_handle *h, int *count_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CPS_H_ */

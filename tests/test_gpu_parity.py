@@ -1,0 +1,279 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via cartpolesimulation_b200.core.Engine) against
+(a) the CPU oracle on seeded inputs, (b) the golden vectors frozen from the live reference.
+
+Tolerances (north_star): rollout trajectories and costs within 1e-5 relative (norm-wise per channel, angle modulo
+2*pi -- tests/parity.py) at T <= 50 in fp32 on the MPPI operating point; selected control within 1e-4.  For
+uniformly random high-energy states the dynamics amplify 1-ulp differences by ~e^6 over a 1 s horizon, so those
+cases carry the looser, measured bound that two IEEE restatements of the same formulas (oracle vs torch) also show
+(tests/test_oracle_golden.py uses the same numbers).
+"""
+import numpy as np
+import pytest
+
+from tests.parity import load_golden, traj_err, vec_err
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+def _engine(*a, **k):
+    from cartpolesimulation_b200.core import Engine
+    return Engine(*a, **k)
+
+
+def _L():
+    from cartpolesimulation_b200 import _lib
+    return _lib
+
+
+def cuda(x):
+    return torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).cuda()
+
+
+ROLL_CASES = ["known", "random", "edge", "wrap", "upright", "tiled", "varL", "T100", "n1"]
+CHAOTIC = ("random", "edge", "wrap", "varL", "T100")
+
+
+@pytest.mark.parametrize("case", ROLL_CASES)
+@pytest.mark.parametrize("integ,fname", [("ODE_v0", "rollout_ode_v0"), ("ODE", "rollout_ode")])
+def test_rollout_vs_reference_golden(integ, fname, case):
+    z, meta = load_golden(fname)
+    s0, Q, ref = z[f"{case}__s0"], z[f"{case}__Q"], z[f"{case}__traj"]
+    Lv, m_pole, n = z[f"{case}__var"]
+    B, T = Q.shape
+    eng = _engine(B, T, dt=meta["dt"], substeps=int(n), integrator=integ, cost=None)
+    eng.set_variable_parameters(L=Lv, m_pole=m_pole)
+    s_in = s0[0] if s0.shape[0] == 1 else s0
+    traj, fin = eng.rollout(cuda(s_in), cuda(Q), want_final=True)
+    got = traj.cpu().numpy()
+    assert got.shape == ref.shape
+    np.testing.assert_array_equal(got[:, 0], np.broadcast_to(s0, (B, 6)) if s0.shape[0] == 1 else s0)
+    np.testing.assert_array_equal(fin.cpu().numpy(), got[:, -1])
+    e1 = traj_err(got[:, :2], ref[:, :2])
+    assert max(e1.values()) < 3e-6, e1
+    e = traj_err(got, ref)
+    tol = 3e-4 if case in CHAOTIC else 1e-5
+    assert max(e.values()) < tol, e
+
+
+@pytest.mark.parametrize("integ", ["ODE_v0", "ODE"])
+def test_rollout_vs_oracle_layouts_and_flags(integ):
+    from oracle import oracle as O
+    L = _L()
+    rng = np.random.default_rng(3)
+    B, T = 1000, 50  # not a multiple of the block size
+    a = np.pi - 1e-3
+    s = np.array([a, 0, np.cos(a), np.sin(a), 0, 0], dtype=np.float32)
+    Q = np.clip(rng.normal(0, 0.2121, (B, T)), -1, 1).astype(np.float32)
+    ref = O.rollout(integ, s, Q)
+    eng = _engine(B, T, integrator=integ, cost=None)
+    t_rm, _ = eng.rollout(cuda(s), cuda(Q))
+    e = traj_err(t_rm.cpu().numpy(), ref)
+    assert max(e.values()) < 1e-5, e
+    # time-major (coalesced) layout of controls and trajectories must give bit-identical numbers
+    t_tm, _ = eng.rollout(cuda(s), cuda(Q.T), q_layout=L.TIME_MAJOR, traj_layout=L.TIME_MAJOR)
+    np.testing.assert_array_equal(t_tm.permute(2, 0, 1).cpu().numpy(), t_rm.cpu().numpy())
+    # exact atan2 / fast-math variants stay within the tolerance of the MPPI operating point
+    for kw, tol in ((dict(exact_atan2=True), 1e-5), (dict(fast_sincos=True), 5e-5), (dict(fast_div=True), 2e-5)):
+        e2 = _engine(B, T, integrator=integ, cost=None, **kw)
+        t2, _ = e2.rollout(cuda(s), cuda(Q))
+        err = traj_err(t2.cpu().numpy(), ref)
+        assert max(err.values()) < tol, (kw, err)
+
+
+@pytest.mark.parametrize("name", ["default", "quadratic_boundary", "quadratic_boundary_grad_minimal",
+                                  "quadratic_boundary_grad"])
+def test_cost_kernels_vs_reference_golden(name):
+    z, meta = load_golden("costs")
+    traj, Q = z["traj"], z["Q"]
+    K, T = Q.shape
+    eng = _engine(K, T, cost=name)
+    for i, (tp, te, up) in enumerate(z["settings"]):
+        eng.set_variable_parameters(target_position=tp, target_equilibrium=te)
+        ref_stage, ref_J, ref_term = z[f"{name}__{i}__stage"], z[f"{name}__{i}__J"], z[f"{name}__{i}__terminal"]
+        st = eng.stage_cost(cuda(traj), cuda(Q), up).cpu().numpy()
+        st_T = eng.stage_cost(cuda(traj[:, :-1]), cuda(Q), up).cpu().numpy()  # the reference passes T rows
+        np.testing.assert_array_equal(st, st_T)
+        J = eng.trajectory_cost(cuda(traj), cuda(Q), up).cpu().numpy()
+        term = eng.terminal_cost(cuda(traj[:, -1])).cpu().numpy()
+        np.testing.assert_array_equal(term, ref_term)
+        if name in ("default", "quadratic_boundary"):
+            np.testing.assert_allclose(st, ref_stage, rtol=0, atol=512.0)  # one fp32 ulp at MAX_COST ~ 6e9
+            un = eng.stage_cost(cuda(traj), cuda(Q), up, unshifted=True).cpu().numpy()
+            ref_un = ref_stage.astype(np.float64) + float(z[f"{name}__max_cost"])
+            big = np.abs(un) > 1e5
+            if big.any():
+                assert np.abs(un[big] - ref_un[big]).max() / np.abs(ref_un[big]).max() < 2e-6
+            assert np.abs(un[~big] - ref_un[~big]).max() <= 512.0
+            assert vec_err(J, ref_J) < 1e-6
+        else:
+            assert vec_err(st, ref_stage) < 2e-6
+            assert vec_err(J, ref_J) < 2e-6
+
+
+MPPI_RUNS = ["ode_gradmin", "v0_gradmin", "ode_gradmin_K2000", "ode_grad", "ode_grad_down", "ode_qb", "ode_default",
+             "ode_gradmin_T100", "ode_gradmin_T51"]
+
+
+@pytest.mark.parametrize("run", MPPI_RUNS)
+def test_mppi_step_vs_reference_golden(run):
+    """Identical injected noise, identical u_nom, identical s: u / u_nom / J of every solve against the reference."""
+    L = _L()
+    z, m = load_golden("mppi_" + run)
+    T, K = m["T"], m["K"]
+    eng = _engine(K, T, dt=m["dt"], substeps=m["n"], integrator=m["predictor"], cost=m["cost"], interp_period=m["p"])
+    eng.set_variable_parameters(target_position=m["target_position"], target_equilibrium=m["target_equilibrium"])
+    J = torch.empty(K, device="cuda")
+    traj = torch.empty((K, T + 1, 6), device="cuda")
+    u_run = torch.empty((K, T), device="cuda")
+    u_nom_prev = np.zeros(T, dtype=np.float32)
+    for i in range(m["steps"]):
+        eng.set_u_nom(u_nom_prev)
+        # reference noise layout [K, n_ind] as is (rollout-major) on even steps, transposed on odd ones
+        if i % 2 == 0:
+            noise, layout = cuda(z["eps"][i]), L.ROLLOUT_MAJOR
+        else:
+            noise, layout = cuda(z["eps"][i].T), L.TIME_MAJOR
+        u = eng.mppi_step(cuda(z["s"][i]), noise, layout, float(z["u_prev"][i]), None, J, traj, L.ROLLOUT_MAJOR, u_run)
+        u = float(u.cpu()[0])
+        u_nom = eng.get_u_nom()
+        if i == 0:
+            np.testing.assert_allclose(u_run.cpu().numpy(), z["u_run0"], rtol=0, atol=3e-7)
+            assert max(traj_err(traj[:32].cpu().numpy(), z["traj0"]).values()) < 1e-5
+        if m["cost"] in ("default", "quadratic_boundary"):
+            assert vec_err(J.cpu().numpy(), z["J"][i]) < 1e-6
+        else:
+            assert vec_err(J.cpu().numpy(), z["J"][i]) < 1e-5
+            assert abs(u - float(z["u"][i])) < 1e-4
+            np.testing.assert_allclose(u_nom, z["u_nom"][i], rtol=0, atol=1e-4)
+        assert eng.nonfinite_costs() == 0
+        u_nom_prev = z["u_nom"][i].copy()
+
+
+@pytest.mark.parametrize("integ,cost,K,T,p", [("ODE", "quadratic_boundary_grad_minimal", 2000, 50, 10),
+                                             ("ODE_v0", "quadratic_boundary_grad", 777, 35, 10),
+                                             ("ODE", "quadratic_boundary_grad_minimal", 1, 7, 10),
+                                             ("ODE", "quadratic_boundary_grad_minimal", 33, 1, 10),
+                                             ("ODE_v0", "quadratic_boundary_grad_minimal", 5000, 20, 1),
+                                             ("ODE", "quadratic_boundary_grad_minimal", 40000, 12, 5)])
+def test_mppi_step_vs_oracle(integ, cost, K, T, p):
+    """Seeded inputs at sizes the oracle finishes in seconds, incl. ragged K, T=1, T<p, p=1 and the multi-warp
+    block geometry (K=40000 -> 64-thread blocks)."""
+    from oracle import oracle as O
+    L = _L()
+    rng = np.random.default_rng(K + T)
+    n_ind = O.num_inducing(T, p)
+    eps = rng.standard_normal((K, n_ind)).astype(np.float32)
+    s = np.array([2.9, 0.5, np.cos(2.9), np.sin(2.9), 0.05, -0.1], dtype=np.float32)
+    u_nom0 = rng.uniform(-0.3, 0.3, T).astype(np.float32)
+    ref = O.mppi_step(integ, cost, s, u_nom0, eps=eps, u_prev=0.1, target_position=0.03, p=p, want=("delta_u",))
+    eng = _engine(K, T, integrator=integ, cost=cost, interp_period=p)
+    eng.set_variable_parameters(target_position=0.03)
+    eng.set_u_nom(u_nom0)
+    J = torch.empty(K, device="cuda")
+    u = eng.mppi_step(cuda(s), cuda(eps.T), L.TIME_MAJOR, 0.1, None, J)
+    assert vec_err(J.cpu().numpy(), ref["J"]) < 1e-5
+    assert abs(float(u.cpu()[0]) - float(ref["u"])) < 1e-4
+    np.testing.assert_allclose(eng.get_u_nom(), ref["u_nom"], rtol=0, atol=1e-4)
+    # DIRECT noise mode fed with the oracle's interpolated perturbations must agree with the INDUCING mode
+    eng_d = _engine(K, T, integrator=integ, cost=cost, interp_period=p, noise_mode="direct")
+    eng_d.set_variable_parameters(target_position=0.03)
+    eng_d.set_u_nom(u_nom0)
+    J2 = torch.empty(K, device="cuda")
+    u2 = eng_d.mppi_step(cuda(s), cuda(ref["delta_u"]), L.ROLLOUT_MAJOR, 0.1, None, J2)
+    assert vec_err(J2.cpu().numpy(), ref["J"]) < 1e-5
+    assert abs(float(u2.cpu()[0]) - float(ref["u"])) < 1e-4
+    np.testing.assert_allclose(eng_d.get_u_nom(), ref["u_nom"], rtol=0, atol=1e-4)
+
+
+def test_mppi_full_size_properties():
+    """BASELINE config 4 size (K=65536, T=100), where the oracle is too slow to be the checker: size-independent
+    properties.  (1) fused cost == standalone cost kernel on the materialised trajectories + correction term;
+    (2) bitwise run-to-run determinism; (3) permuting the rollouts leaves the update unchanged (to fp32 summation
+    noise); (4) cos^2 + sin^2 = 1 and |angle| <= pi on every stored state; (5) u_nom stays inside the limits."""
+    L = _L()
+    K, T = 65536, 100
+    eng = _engine(K, T, integrator="ODE", cost="quadratic_boundary_grad_minimal")
+    g = torch.Generator(device="cuda").manual_seed(5)
+    noise = torch.randn((eng.n_ind, K), generator=g, device="cuda")
+    s = cuda(np.array([3.0, 0.0, np.cos(3.0), np.sin(3.0), 0.0, 0.0]))
+    J = torch.empty(K, device="cuda")
+    traj = torch.empty((K, T + 1, 6), device="cuda")
+    u_run = torch.empty((K, T), device="cuda")
+    eng.mppi_reset(0.0)
+    u1 = eng.mppi_step(s, noise, L.TIME_MAJOR, 0.0, None, J, traj, L.ROLLOUT_MAJOR, u_run).clone()
+    un1 = eng.get_u_nom()
+    J1 = J.clone()
+    # (1)
+    Jc = eng.trajectory_cost(traj, u_run, 0.0)
+    # u_nom = 0 on this first solve, so delta_u == u_run wherever no clipping happened; mppi_correction_cost
+    # (optimizer_mppi.py:153-154) then reduces to (0.5 (1 - 1/NU) + 1 + 0.5) * delta_u^2 summed over the horizon
+    unclipped = (u_run.abs() < 1.0).all(dim=1)
+    d = u_run.double()
+    corr = ((0.5 * (1 - 1 / 1000.0) + 1.5) * d * d).sum(1).float()
+    rel = ((Jc + corr - J1)[unclipped].abs().max() / J1.abs().max()).item()
+    assert unclipped.float().mean().item() > 0.5
+    assert rel < 2e-6, rel
+    # (2)
+    eng.mppi_reset(0.0)
+    u2 = eng.mppi_step(s, noise, L.TIME_MAJOR, 0.0, None, J).clone()
+    assert torch.equal(u1, u2) and torch.equal(J, J1)
+    np.testing.assert_array_equal(eng.get_u_nom(), un1)
+    # (3)
+    perm = torch.randperm(K, generator=g, device="cuda")
+    eng.mppi_reset(0.0)
+    u3 = eng.mppi_step(s, noise[:, perm].contiguous(), L.TIME_MAJOR, 0.0, None, J)
+    assert abs(float(u3.cpu()[0]) - float(u1.cpu()[0])) < 1e-5
+    np.testing.assert_allclose(eng.get_u_nom(), un1, rtol=0, atol=1e-5)
+    assert torch.equal(J, J1[perm])  # a rollout's cost does not depend on which thread computed it
+    # (4) (5)
+    c, sn, ang = traj[..., 2], traj[..., 3], traj[..., 0]
+    assert ((c * c + sn * sn - 1).abs().max().item()) < 1e-6
+    assert ang.abs().max().item() <= np.pi + 1e-6
+    assert np.abs(un1).max() <= 1.0
+    assert eng.nonfinite_costs() == 0
+
+
+def test_rollout_full_size_properties():
+    """1M cartpoles (BASELINE config 2 size, shortened horizon to bound test time): tiling invariance -- the same
+    (state, controls) pair must produce bit-identical trajectories wherever it sits in the batch -- and agreement
+    of a random sample of rows with the oracle."""
+    from oracle import oracle as O
+    B, T = 1 << 20, 20
+    rng = np.random.default_rng(11)
+    base_s = np.stack([rng.uniform(-3, 3, 4096), rng.uniform(-3, 3, 4096), np.zeros(4096), np.zeros(4096),
+                       rng.uniform(-0.15, 0.15, 4096), rng.uniform(-0.3, 0.3, 4096)], 1).astype(np.float32)
+    base_s[:, 2], base_s[:, 3] = np.cos(base_s[:, 0]), np.sin(base_s[:, 0])
+    base_Q = rng.uniform(-1, 1, (4096, T)).astype(np.float32)
+    s0 = cuda(np.tile(base_s, (B // 4096, 1)))
+    Q = cuda(np.tile(base_Q, (B // 4096, 1)))
+    for integ in ("ODE", "ODE_v0"):
+        eng = _engine(B, T, integrator=integ, cost=None)
+        _, fin = eng.rollout(s0, Q, want_traj=False, want_final=True)
+        fin = fin.reshape(B // 4096, 4096, 6)
+        assert torch.equal(fin[0], fin[-1]) and torch.equal(fin[0], fin[B // 8192])
+        ref = O.rollout(integ, base_s[:512], base_Q[:512], want_traj=False)
+        e = traj_err(fin[0, :512].cpu().numpy(), ref)
+        assert max(e.values()) < 5e-5, e
+
+
+def test_error_behaviour():
+    """ValueError / NotImplementedError where the reference raises them; no silent fallback."""
+    from cartpolesimulation_b200.core import Engine
+    with pytest.raises(ValueError):
+        Engine(16, 10, integrator="RK4")
+    with pytest.raises(ValueError):
+        Engine(16, 10, cost="quadratic_boundary_nonconvex")
+    with pytest.raises(ValueError):
+        Engine(0, 10)
+    eng = Engine(16, 10, cost=None)
+    with pytest.raises(ValueError):  # batch mismatch, predictor_ODE_v0.py:63-64
+        eng.rollout(torch.zeros((3, 6), device="cuda"), torch.zeros((16, 10), device="cuda"))
+    with pytest.raises(ValueError):
+        eng.rollout(torch.zeros(6), torch.zeros((16, 10), device="cuda"))  # CPU tensor at the device API
+    with pytest.raises(Exception):
+        eng.trajectory_cost(torch.zeros((16, 11, 6), device="cuda"), torch.zeros((16, 10), device="cuda"))
+    # empty batch is a no-op, not an error
+    t, _ = eng.rollout(torch.zeros(6, device="cuda"), torch.zeros((0, 10), device="cuda"))
+    assert t.shape == (0, 11, 6)

@@ -1,0 +1,189 @@
+"""GPU tests of the reference-facing plugin objects (optimizer / predictor / cost wrappers): same names, argument
+meaning and error behaviour as the reference's own classes, results against the golden vectors frozen from it."""
+import numpy as np
+import pytest
+
+from tests.parity import load_golden, traj_err, vec_err
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+class InjectedNormal:
+    """Same hook as in the reference harness: replaces optimizer.rng (optimizer_mppi.py:172-174)."""
+
+    def __init__(self, draws):
+        self.draws, self.i = list(draws), 0
+
+    def normal(self, shape, dtype=None):
+        d = self.draws[self.i]
+        self.i += 1
+        assert list(d.shape) == list(shape)
+        return d
+
+
+def _make_optimizer(m, logging=False, **kw):
+    import cartpolesimulation_b200 as cps
+    from cartpolesimulation_b200.optimizer_mppi_b200 import optimizer_mppi_b200
+    vp = cps.VariableParameters(target_position=m["target_position"], target_equilibrium=m["target_equilibrium"],
+                                L=0.395, m_pole=0.087)
+    cost = cps.CostFunctionWrapper()
+    predictor = cps.PredictorWrapper()
+    opt = optimizer_mppi_b200(predictor=predictor, cost_function=cost,
+                              control_limits=(np.array([-1.0], np.float32), np.array([1.0], np.float32)),
+                              computation_library=None, seed=1, cc_weight=m["cc_weight"], R=m["R"], LBD=m["LBD"],
+                              mpc_horizon=m["T"], num_rollouts=m["K"], NU=m["NU"], SQRTRHOINV=m["SQRTRHOINV"],
+                              period_interpolation_inducing_points=m["p"], optimizer_logging=logging,
+                              calculate_optimal_trajectory=False, **kw)
+    predictor.configure(batch_size=m["K"], horizon=m["T"], dt=m["dt"], variable_parameters=vp,
+                        predictor_specification=m["predictor"])
+    cost.configure(batch_size=m["K"], horizon=m["T"], variable_parameters=vp, environment_name="CartPole",
+                   computation_library=None, cost_function_specification=m["cost"])
+    opt.configure(dt=m["dt"], predictor_specification=m["predictor"], num_states=predictor.num_states,
+                  num_control_inputs=predictor.num_control_inputs)
+    return opt, vp
+
+
+@pytest.mark.parametrize("run", ["ode_gradmin", "v0_gradmin", "ode_grad_down", "ode_gradmin_T100"])
+@pytest.mark.parametrize("logging", [False, True])
+def test_optimizer_step_sequence_matches_reference(run, logging):
+    """controller_mpc-style use: consecutive optimizer.step(s) calls with the reference's injected draws; the
+    optimizer carries u_nom and u_prev itself (warm-start shift, last returned control)."""
+    z, m = load_golden("mppi_" + run)
+    opt, _ = _make_optimizer(m, logging=logging)
+    opt.rng = InjectedNormal([torch.from_numpy(e[:, :, None].copy()) for e in z["eps"]])
+    for i in range(m["steps"]):
+        u = opt.step(z["s"][i].copy())
+        assert isinstance(u, np.ndarray) and u.dtype == np.float32 and u.shape == ()
+        assert abs(float(u) - float(z["u"][i])) < 1e-4, (i, float(u), float(z["u"][i]))
+        np.testing.assert_allclose(opt.u_nom.numpy().reshape(-1), z["u_nom"][i], rtol=0, atol=1e-4)
+        assert opt.u_nom.shape == (1, m["T"], 1)
+        if logging:
+            lv = opt.logging_values
+            assert lv["Q_logged"].shape == (m["K"], m["T"], 1)
+            assert lv["rollout_trajectories_logged"].shape == (m["K"], m["T"] + 1, 6)
+            assert vec_err(lv["J_logged"], z["J"][i]) < 1e-5
+            np.testing.assert_array_equal(lv["s_logged"], z["s"][i])
+            if i == 0:
+                np.testing.assert_allclose(lv["Q_logged"][:, :, 0], z["u_run0"], rtol=0, atol=3e-7)
+    assert opt.optimizer_name == "mppi-b200"
+    opt.optimizer_reset()
+    np.testing.assert_array_equal(opt.u_nom.numpy().reshape(-1), np.zeros(m["T"], np.float32))
+
+
+def test_optimizer_own_rng_is_seeded_and_variable_parameters_are_reread():
+    z, m = load_golden("mppi_ode_gradmin")
+    m = dict(m, K=512)
+    a, vp_a = _make_optimizer(m)
+    b, vp_b = _make_optimizer(m)
+    s = z["s"][0]
+    ua = [float(a.step(s)) for _ in range(3)]
+    ub = [float(b.step(s)) for _ in range(3)]
+    assert ua == ub  # same seed -> same device draws -> bitwise same controls
+    assert all(abs(x) <= 1.0 for x in ua)
+    # target change is picked up on the next step without reconfiguring (CartPole/__init__.py:512-519)
+    vp_b.update_attributes({"target_position": 0.15, "target_equilibrium": -1.0})
+    vp_a.update_attributes({"target_position": 0.15, "target_equilibrium": -1.0})
+    assert float(a.step(s)) == float(b.step(s))
+    c, _ = _make_optimizer(m)
+    for _ in range(3):
+        c.step(s)
+    assert float(c.step(s)) != float(a.u)  # c still tracks the old target
+
+
+def test_optimal_trajectory_and_errors():
+    z, m = load_golden("mppi_ode_gradmin")
+    import cartpolesimulation_b200 as cps
+    from cartpolesimulation_b200.optimizer_mppi_b200 import optimizer_mppi_b200
+    opt, _ = _make_optimizer(dict(m, K=256))
+    opt.calculate_optimal_trajectory = True
+    opt.step(z["s"][0])
+    assert opt.optimal_trajectory.shape == (1, m["T"] + 1, 6)
+    np.testing.assert_array_equal(opt.optimal_trajectory[0, 0], z["s"][0])
+    assert opt.optimal_control_sequence.shape == (1, m["T"], 1)
+    with pytest.raises(ValueError):
+        opt.step(np.zeros(5, np.float32))
+    bad = optimizer_mppi_b200(predictor="GP", cost_function="default", control_limits=([-1.0], [1.0]),
+                              mpc_horizon=10, num_rollouts=32)
+    with pytest.raises(ValueError):
+        bad.configure(num_states=6, num_control_inputs=1, dt=0.02, predictor_specification="GP")
+    with pytest.raises(ValueError):
+        bad.configure(num_states=4, num_control_inputs=2, dt=0.02, predictor_specification="ODE")
+    with pytest.raises(RuntimeError):
+        optimizer_mppi_b200(predictor="ODE", cost_function="default", control_limits=([-1.0], [1.0])).step(z["s"][0])
+
+
+@pytest.mark.parametrize("integ,fname", [("ODE_v0", "rollout_ode_v0"), ("ODE", "rollout_ode")])
+def test_predictor_wrapper_interface(integ, fname):
+    import cartpolesimulation_b200 as cps
+    z, meta = load_golden(fname)
+    s0, Q, ref = z["tiled__s0"], z["tiled__Q"], z["tiled__traj"]
+    B, T = Q.shape
+    pw = cps.PredictorWrapper()
+    pw.configure(batch_size=B, horizon=T, dt=meta["dt"], predictor_specification=integ)
+    assert pw.num_states == 6 and pw.num_control_inputs == 1 and pw.predictor_type == integ
+    # predict_core: torch cuda in -> torch cuda out, numpy in -> numpy out, torch cpu in -> torch cpu out
+    out_np = pw.predict_core(np.tile(s0, (B, 1)), Q[:, :, None])
+    assert isinstance(out_np, np.ndarray) and out_np.shape == (B, T + 1, 6)
+    assert max(traj_err(out_np, ref).values()) < 1e-5
+    out_t = pw.predict_core(torch.from_numpy(s0).cuda(), torch.from_numpy(Q[:, :, None]).cuda())
+    assert out_t.is_cuda
+    np.testing.assert_array_equal(out_t.cpu().numpy(), out_np)
+    out_c = pw.predict_core(torch.from_numpy(np.tile(s0, (B, 1))), torch.from_numpy(Q[:, :, None]))
+    assert not out_c.is_cuda
+    # predict: numpy, tolerant shapes
+    p = pw.predict(s0[0], Q[:, :, None])
+    np.testing.assert_array_equal(p, out_np)
+    one = pw.predict(s0[0], Q[0, :, None])
+    if integ == "ODE_v0":
+        assert one.shape == (T + 1, 6)  # squeezed for batch 1 (predictor_ODE_v0.py:74)
+        with pytest.raises(ValueError):
+            pw.predict(np.tile(s0, (3, 1)), Q[:, :, None])
+    else:
+        assert one.shape == (1, T + 1, 6)
+    np.testing.assert_array_equal(np.squeeze(one), out_np[0])
+    pw.update(Q0=Q[:, :1, None], s=s0)  # no-op for ODE predictors
+    c = pw.copy()
+    assert c.predictor_type == integ and c.predictor is None
+    with pytest.raises(ValueError):
+        cps.PredictorWrapper().configure(batch_size=1, horizon=5, dt=0.02, predictor_specification="nonsense")
+
+
+@pytest.mark.parametrize("name", ["default", "quadratic_boundary", "quadratic_boundary_grad_minimal",
+                                  "quadratic_boundary_grad"])
+def test_cost_wrapper_interface(name):
+    import cartpolesimulation_b200 as cps
+    z, meta = load_golden("costs")
+    traj, Q = z["traj"], z["Q"]
+    K, T = Q.shape
+    tp, te, up = z["settings"][1]
+    vp = cps.VariableParameters(target_position=torch.tensor(tp, dtype=torch.float32),
+                                target_equilibrium=torch.tensor(te, dtype=torch.float32))
+    cw = cps.CostFunctionWrapper()
+    cw.configure(batch_size=K, horizon=T, variable_parameters=vp, environment_name="CartPole",
+                 computation_library=None, cost_function_specification=name.replace("_", "-"))
+    assert cw.cost_function_name == name
+    tt, qq = torch.from_numpy(traj).cuda(), torch.from_numpy(Q[:, :, None]).cuda()
+    J = cw.get_trajectory_cost(tt, qq, np.float32(up))
+    st = cw.get_stage_cost(tt[:, :-1, :], qq, np.float32(up))
+    term = cw.get_terminal_cost(tt[:, -1, :])
+    assert J.shape == (K,) and st.shape == (K, T) and term.shape == (K, 1) and J.is_cuda
+    assert vec_err(J.cpu().numpy(), z[f"{name}__1__J"]) < 2e-6
+    np.testing.assert_array_equal(term.cpu().numpy().reshape(-1), z[f"{name}__1__terminal"])
+    if name in ("default", "quadratic_boundary"):
+        assert cw.cost_function.MAX_COST == float(z[f"{name}__max_cost"])
+    else:
+        assert vec_err(st.cpu().numpy(), z[f"{name}__1__stage"]) < 2e-6
+        summed = cw.get_summed_stage_cost(tt, qq, np.float32(up))
+        np.testing.assert_allclose(summed.cpu().numpy(), z[f"{name}__1__stage"].sum(1), rtol=1e-5)
+    # numpy in -> numpy out
+    Jn = cw.get_trajectory_cost(traj, Q[:, :, None], up)
+    assert isinstance(Jn, np.ndarray)
+    np.testing.assert_array_equal(Jn, J.cpu().numpy())
+    # hot reload contract (cost_function_wrapper.py:71-74)
+    cw.cost_function.reload_cost_parameters_from_config_flag = True
+    cw.update_cost_parameters_from_config()
+    assert cw.cost_function.reload_cost_parameters_from_config_flag is False
+    with pytest.raises(ValueError):
+        cps.CostFunctionWrapper().configure(batch_size=1, horizon=1, variable_parameters=vp,
+                                            cost_function_specification="quadratic_boundary_nonconvex")
