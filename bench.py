@@ -32,7 +32,7 @@ if REPO not in sys.path:
     sys.path.insert(0, REPO)
 
 FLOP_PER_STATE_STEP = 32.0   # 24 (ODE rhs) + 8 (integrator), FMA = 2
-MUFU_PER_STATE_STEP = 3.0    # rcp + sin + cos when the MUFU path is used; 1 (rcp) with the accurate sincosf
+MUFU_PER_STATE_STEP = 3.0    # rcp + sin + cos when the MUFU path is used; 1 (rcp) otherwise
 B_DEFAULT, T_DEFAULT, N_SUB, DT = 1 << 20, 50, 10, 0.02
 METRIC = "rollout_state_steps_per_sec"
 UNIT = "state-steps/s"
@@ -210,7 +210,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     B, T = args.batch, args.horizon
     eng = Engine(B, T, dt=DT, substeps=N_SUB, integrator="ODE_v0", cost=None, device=local_rank,
-                 fast_sincos=args.fast_sincos)
+                 fast_sincos=args.fast_sincos, substep_sincos=args.substep_sincos)
     s0_np, Q_np = make_inputs(B, T, seed=1234 + rank)
     s0 = torch.from_numpy(s0_np).to(dev)
     Q = torch.from_numpy(Q_np).to(dev)           # [T, B] time-major, 200 MB > L2 (126 MB): no L2 flush needed
@@ -325,7 +325,9 @@ def run_ours(args):
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(B, T), "per_gpu_batch": B, "l2": "inputs larger than L2 (Q = %d MB)" % (Q.numel() * 4 >> 20),
-                       "sincos": "MUFU" if args.fast_sincos else "sincosf (1 ulp)"},
+                       "sincos": ("MUFU every substep" if args.fast_sincos else "sincosf every substep")
+                       if (args.fast_sincos or args.substep_sincos) else
+                       "rotation substeps + sincosf resync per control step (default)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * e2e_s / e2e_steps, "api": "cps_rollout_host (pinned host buffers)"},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
@@ -344,7 +346,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=B_DEFAULT, help="cartpoles per GPU")
     ap.add_argument("--horizon", type=int, default=T_DEFAULT)
-    ap.add_argument("--fast-sincos", action="store_true", help="MUFU sin/cos variant (parity-checked separately)")
+    ap.add_argument("--fast-sincos", action="store_true", help="MUFU sin/cos every substep (parity-checked separately)")
+    ap.add_argument("--substep-sincos", action="store_true", help="sincosf every substep, literally as the reference")
     ap.add_argument("--no-mppi", action="store_true")
     ap.add_argument("--mppi-calls", type=int, default=1000)
     args = ap.parse_args()

@@ -21,7 +21,7 @@ EULER_V0, EULER_CROMER = 0, 1
 COST_NONE, COST_DEFAULT, COST_QUADRATIC_BOUNDARY, COST_QB_GRAD_MINIMAL, COST_QB_GRAD = -1, 0, 1, 2, 3
 NOISE_INDUCING, NOISE_DIRECT = 0, 1
 ROLLOUT_MAJOR, TIME_MAJOR = 0, 1
-FLAG_FAST_SINCOS, FLAG_EXACT_ATAN2, FLAG_FAST_DIV = 0x1, 0x2, 0x4
+FLAG_FAST_SINCOS, FLAG_EXACT_ATAN2, FLAG_FAST_DIV, FLAG_SUBSTEP_SINCOS = 0x1, 0x2, 0x4, 0x8
 PH_COUNT = 9
 
 

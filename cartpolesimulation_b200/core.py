@@ -45,7 +45,8 @@ class Engine:
     def __init__(self, num_rollouts: int, horizon: int, dt: float = 0.02, substeps: int = 10,
                  integrator: str = "ODE", cost: str | None = "quadratic_boundary_grad_minimal",
                  noise_mode: str = "inducing", interp_period: int = 10, device: int | None = None,
-                 fast_sincos: bool = False, exact_atan2: bool = False, fast_div: bool = False):
+                 fast_sincos: bool = False, exact_atan2: bool = False, fast_div: bool = False,
+                 substep_sincos: bool = False):
         if integrator not in INTEGRATORS:
             raise ValueError(f"unknown integrator {integrator!r}; expected one of {list(INTEGRATORS)}")
         if cost not in COSTS:
@@ -55,8 +56,10 @@ class Engine:
         self.lib = L.lib()
         dev = torch.cuda.current_device() if device is None else int(device)
         self.device = torch.device("cuda", dev)
+        if fast_sincos or exact_atan2:
+            substep_sincos = True  # both only make sense when sin/cos are evaluated every substep
         flags = (L.FLAG_FAST_SINCOS if fast_sincos else 0) | (L.FLAG_EXACT_ATAN2 if exact_atan2 else 0) \
-            | (L.FLAG_FAST_DIV if fast_div else 0)
+            | (L.FLAG_FAST_DIV if fast_div else 0) | (L.FLAG_SUBSTEP_SINCOS if substep_sincos else 0)
         self.K, self.T, self.n, self.dt, self.p = int(num_rollouts), int(horizon), int(substeps), float(dt), int(interp_period)
         self.integrator, self.cost_name = integrator, cost
         self.noise_mode = {"inducing": L.NOISE_INDUCING, "direct": L.NOISE_DIRECT}[noise_mode]

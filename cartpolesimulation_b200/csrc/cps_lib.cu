@@ -137,7 +137,7 @@ __device__ __forceinline__ void merge_and_finish(const MppiParams &mp, const flo
 // K1 + K2: the MPPI solve
 // =====================================================================================================
 template <int INTEG, int COST, int SC, int NOISE, bool FAST_DIV, bool EXACT_ATAN2>
-__global__ void __launch_bounds__(256) mppi_kernel(const __grid_constant__ MppiArgs a) {
+__global__ void __launch_bounds__(256, 4) mppi_kernel(const __grid_constant__ MppiArgs a) {
     extern __shared__ float smem[];
     const MppiParams &mp = a.mp;
     const int T = mp.T, p = mp.p;
@@ -160,9 +160,8 @@ __global__ void __launch_bounds__(256) mppi_kernel(const __grid_constant__ MppiA
     }
     __syncthreads();
 
-    State z;
-    z.th = a.s[IDX_ANGLE]; z.w = a.s[IDX_ANGLED]; z.c = a.s[IDX_COS]; z.s = a.s[IDX_SIN];
-    z.x = a.s[IDX_POS]; z.v = a.s[IDX_POSD];
+    State z = load_state(a.s);
+    const OdeParams ode = pin_params(a.ode, z.th);  // loop-invariant constants pinned in registers
     float c_cost = cosf(z.th);  // the plugins take cos(angle) of the stored angle, not angle_cos (default.py:34)
 
     const float *nz = a.noise + (long long)(active ? k : 0) * a.ns_k;
@@ -204,7 +203,7 @@ __global__ void __launch_bounds__(256) mppi_kernel(const __grid_constant__ MppiA
             if (a.u_run_out) a.u_run_out[(long long)k * T + t] = u;
             if (traj) store_state(traj + (long long)t * a.ts_t, a.ts_c, z);
         }
-        control_step<INTEG, SC, FAST_DIV, EXACT_ATAN2>(a.ode, z, u);
+        control_step<INTEG, SC, FAST_DIV, EXACT_ATAN2>(ode, z, u);
         c_cost = z.c;
         up = u;
     }
@@ -275,12 +274,11 @@ __global__ void __launch_bounds__(128) finalize_kernel(const __grid_constant__ F
 // K3: open-loop batched rollouts
 // =====================================================================================================
 template <int INTEG, int SC, bool FAST_DIV, bool EXACT_ATAN2>
-__global__ void __launch_bounds__(256) rollout_kernel(const __grid_constant__ RolloutArgs a) {
+__global__ void __launch_bounds__(256, 4) rollout_kernel(const __grid_constant__ RolloutArgs a) {
+    const OdeParams ode = pin_params(a.ode, a.s0[0]);
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x; b < a.B; b += stride) {
-        const float *s = a.s0 + b * a.ss_b;
-        State z;
-        z.th = s[IDX_ANGLE]; z.w = s[IDX_ANGLED]; z.c = s[IDX_COS]; z.s = s[IDX_SIN]; z.x = s[IDX_POS]; z.v = s[IDX_POSD];
+        State z = load_state(a.s0 + b * a.ss_b);
         const float *q = a.Q + b * a.qs_b;
         float *traj = a.traj_out ? a.traj_out + b * a.ts_k : nullptr;
         float qn = q[0];
@@ -289,7 +287,7 @@ __global__ void __launch_bounds__(256) rollout_kernel(const __grid_constant__ Ro
             const float Q = qn;
             if (t + 1 < a.T) qn = q[(long long)(t + 1) * a.qs_t];  // prefetch under the integration
             if (traj) store_state(traj + (long long)t * a.ts_t, a.ts_c, z);
-            control_step<INTEG, SC, FAST_DIV, EXACT_ATAN2>(a.ode, z, Q);
+            control_step<INTEG, SC, FAST_DIV, EXACT_ATAN2>(ode, z, Q);
         }
         if (traj) store_state(traj + (long long)a.T * a.ts_t, a.ts_c, z);
         if (a.final_out) store_state(a.final_out + b * 6, 1, z);
@@ -654,12 +652,23 @@ static mppi_fn pick_mppi3(unsigned flags) {
     if (fd) return ea ? mppi_kernel<INTEG, COST, SC, NOISE, true, true> : mppi_kernel<INTEG, COST, SC, NOISE, true, false>;
     return ea ? mppi_kernel<INTEG, COST, SC, NOISE, false, true> : mppi_kernel<INTEG, COST, SC, NOISE, false, false>;
 }
+static int sc_mode(unsigned flags) {
+    if (flags & CPS_FLAG_SUBSTEP_SINCOS) return (flags & CPS_FLAG_FAST_SINCOS) ? SC_MUFU : SC_ACCURATE;
+    return SC_ROTATE;
+}
+template <int INTEG, int COST, int NOISE>
+static mppi_fn pick_mppi2b(unsigned flags) {
+    switch (sc_mode(flags)) {
+    case SC_ACCURATE: return pick_mppi3<INTEG, COST, SC_ACCURATE, NOISE>(flags);
+    case SC_MUFU: return pick_mppi3<INTEG, COST, SC_MUFU, NOISE>(flags);
+    default: return (flags & CPS_FLAG_FAST_DIV) ? mppi_kernel<INTEG, COST, SC_ROTATE, NOISE, true, false>
+                                                : mppi_kernel<INTEG, COST, SC_ROTATE, NOISE, false, false>;
+    }
+}
 template <int INTEG, int COST>
 static mppi_fn pick_mppi2(int noise, unsigned flags) {
-    const bool fast = flags & CPS_FLAG_FAST_SINCOS;
-    if (noise == CPS_NOISE_INDUCING)
-        return fast ? pick_mppi3<INTEG, COST, SC_MUFU, CPS_NOISE_INDUCING>(flags) : pick_mppi3<INTEG, COST, SC_ACCURATE, CPS_NOISE_INDUCING>(flags);
-    return fast ? pick_mppi3<INTEG, COST, SC_MUFU, CPS_NOISE_DIRECT>(flags) : pick_mppi3<INTEG, COST, SC_ACCURATE, CPS_NOISE_DIRECT>(flags);
+    if (noise == CPS_NOISE_INDUCING) return pick_mppi2b<INTEG, COST, CPS_NOISE_INDUCING>(flags);
+    return pick_mppi2b<INTEG, COST, CPS_NOISE_DIRECT>(flags);
 }
 template <int INTEG>
 static mppi_fn pick_mppi1(int cost, int noise, unsigned flags) {
@@ -682,10 +691,17 @@ static rollout_fn pick_rollout2(unsigned flags) {
     if (fd) return ea ? rollout_kernel<INTEG, SC, true, true> : rollout_kernel<INTEG, SC, true, false>;
     return ea ? rollout_kernel<INTEG, SC, false, true> : rollout_kernel<INTEG, SC, false, false>;
 }
+template <int INTEG>
+static rollout_fn pick_rollout1(unsigned flags) {
+    switch (sc_mode(flags)) {
+    case SC_ACCURATE: return pick_rollout2<INTEG, SC_ACCURATE>(flags);
+    case SC_MUFU: return pick_rollout2<INTEG, SC_MUFU>(flags);
+    default: return (flags & CPS_FLAG_FAST_DIV) ? rollout_kernel<INTEG, SC_ROTATE, true, false>
+                                                : rollout_kernel<INTEG, SC_ROTATE, false, false>;
+    }
+}
 static rollout_fn pick_rollout(const cps_config &c) {
-    const bool fast = c.flags & CPS_FLAG_FAST_SINCOS;
-    if (c.integrator == CPS_EULER_V0) return fast ? pick_rollout2<0, SC_MUFU>(c.flags) : pick_rollout2<0, SC_ACCURATE>(c.flags);
-    return fast ? pick_rollout2<1, SC_MUFU>(c.flags) : pick_rollout2<1, SC_ACCURATE>(c.flags);
+    return c.integrator == CPS_EULER_V0 ? pick_rollout1<0>(c.flags) : pick_rollout1<1>(c.flags);
 }
 static cost_fn pick_cost(int cost) {
     switch (cost) {

@@ -65,11 +65,15 @@ typedef enum cps_noise_mode { CPS_NOISE_INDUCING = 0, CPS_NOISE_DIRECT = 1 } cps
  *  *_TIME_MAJOR is the coalesced order the kernels prefer ([n_ind][K], [T][B], [T+1][6][B]). */
 typedef enum cps_layout { CPS_ROLLOUT_MAJOR = 0, CPS_TIME_MAJOR = 1 } cps_layout;
 
-/* cps_config.flags */
-#define CPS_FLAG_FAST_SINCOS 0x1u   /* MUFU.SIN/COS (__sincosf) instead of the 1-ulp sincosf */
-#define CPS_FLAG_EXACT_ATAN2 0x2u   /* Euler-Cromer wrap by atan2f(sin, cos) as the reference writes it, instead of
-                                       the mathematically identical +-2*pi fold */
-#define CPS_FLAG_FAST_DIV 0x4u      /* MUFU.RCP without the Newton step in the ODE right-hand side */
+/* cps_config.flags.  Default (flags = 0): "rotation" substeps -- (cos, sin) are advanced with the angle-addition
+ * formulas by the substep increment h*angleD and re-derived from the (compensated) angle with sincosf once per
+ * control step; as accurate as evaluating sincosf every substep (DESIGN.md "rotation mode"), far fewer instructions. */
+#define CPS_FLAG_FAST_SINCOS 0x1u     /* with SUBSTEP_SINCOS: MUFU.SIN/COS (__sincosf) instead of the 1-ulp sincosf */
+#define CPS_FLAG_EXACT_ATAN2 0x2u     /* with SUBSTEP_SINCOS, Euler-Cromer: wrap by atan2f(sin, cos) as the reference
+                                         writes it, instead of the mathematically identical +-2*pi fold */
+#define CPS_FLAG_FAST_DIV 0x4u        /* MUFU.RCP without the Newton step in the ODE right-hand side */
+#define CPS_FLAG_SUBSTEP_SINCOS 0x8u  /* evaluate sin/cos of the angle in EVERY substep, literally as
+                                         cartpole_equations.py:245-248 / cartpole_numba.py:66-76 do */
 
 typedef struct cps_config {
     int struct_size;      /* = sizeof(cps_config), ABI check */

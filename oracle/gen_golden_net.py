@@ -1,0 +1,114 @@
+"""Golden vectors for the autoregressive neural predictor (GRU / Dense), produced by the UNMODIFIED reference
+predictor_autoregressive_neural (SI_Toolkit/src/SI_Toolkit/Predictors/predictor_autoregressive_neural.py) with the
+torch Sequence network (Functions/Pytorch/Network.py).
+
+No dynamics model ships with the reference (config_predictors.yml:10-11,32-33 point to a directory that is not in
+the tree), so the weights are synthetic: default torch init under torch.manual_seed, saved through
+Sequence.state_dict() into a scratch model directory with a hand-written net-info .txt (format:
+Functions/General/Initialization.py:35-104) and a normalisation table with the value ranges of the shipped
+GymlikeCartPole/Dense-7IN-32H1-32H2-1OUT-0/NI_2024-08-17_22-23-01.csv.  TEST INFRASTRUCTURE ONLY.
+"""
+from __future__ import annotations
+
+import contextlib
+import io
+import os
+import shutil
+import tempfile
+
+import numpy as np
+
+from oracle import ref_loader as R
+from oracle.gen_golden import hanging_state, make_states, save
+
+INPUTS = ["Q", "angleD", "angle_cos", "angle_sin", "position", "positionD"]
+OUTPUTS = ["angleD", "angle_cos", "angle_sin", "position", "positionD"]
+# mean, std, max, min rows (Normalising.py header); minmax_sym uses max/min only
+NORM = {"Q": (0, 0.5, 1.0, -1.0), "angle": (0, 1.8, np.pi, -np.pi), "angleD": (0, 4.0, 18.38, -18.38),
+        "angle_cos": (0, 0.7, 1.0, -1.0), "angle_sin": (0, 0.7, 1.0, -1.0), "position": (0, 0.08, 0.198, -0.198),
+        "positionD": (0, 0.3, 1.125, -1.125)}
+
+
+def write_model_dir(root, full_name, net_type_name, seed, weight_scale=1.0):
+    import torch
+    from SI_Toolkit.Functions.Pytorch.Network import Sequence
+    d = os.path.join(root, full_name)
+    os.makedirs(d, exist_ok=True)
+    short = "-".join(p for p in full_name.split("-") if not (p.endswith("IN") or p.endswith("OUT")))[:-2]  # drop index
+    ni = os.path.join(d, "NI.csv")
+    cols = list(NORM.keys())
+    with open(ni, "w") as f:
+        f.write("," + ",".join(cols) + "\n")
+        for r, rowname in enumerate(["mean", "std", "max", "min"]):
+            f.write(rowname + "," + ",".join(repr(float(NORM[c][r])) for c in cols) + "\n")
+    with open(os.path.join(d, full_name + ".txt"), "w") as f:
+        f.write("\n".join([
+            "CREATED:", "2026-01-01 00:00:00", "", "LIBRARY:", "Pytorch", "", "NET NAME:", short, "",
+            "NET FULL NAME:", full_name, "", "INPUTS:", ", ".join(INPUTS), "", "OUTPUTS:", ", ".join(OUTPUTS), "",
+            "TYPE:", net_type_name, "", "NORMALIZATION:", ni, "", "NORMALIZE:", "True", "",
+            "WASH OUT LENGTH:", "10", "", "CONSTRUCT NETWORK:", "with cells", ""]))
+    torch.manual_seed(seed)
+    with contextlib.redirect_stdout(io.StringIO()):
+        net = Sequence(short, INPUTS, OUTPUTS, batch_size=1, construct_network="with cells")
+    if weight_scale != 1.0:
+        with torch.no_grad():
+            for p in net.parameters():
+                p.mul_(weight_scale)
+    torch.save(net.state_dict(), os.path.join(d, "ckpt.pt"))
+    return {k: v.detach().cpu().numpy().astype(np.float32) for k, v in net.state_dict().items()}
+
+
+def gen_net():
+    import torch
+    R.load()
+    from SI_Toolkit.Predictors.predictor_autoregressive_neural import predictor_autoregressive_neural
+    rng = np.random.default_rng(99)
+    root = tempfile.mkdtemp(prefix="cps_models_")
+    try:
+        for full_name, tname, seed, scale in (("GRU-6IN-64H1-64H2-5OUT-0", "GRU", 7, 1.0),
+                                              ("GRU-6IN-32H1-32H2-5OUT-0", "GRU", 8, 2.0),
+                                              ("Dense-6IN-32H1-32H2-5OUT-0", "Dense", 9, 1.5)):
+            sd = write_model_dir(root, full_name, tname, seed, scale)
+            K, T = 96, 50
+            with contextlib.redirect_stdout(io.StringIO()), torch.inference_mode():
+                pred = predictor_autoregressive_neural(model_name=full_name, path_to_model=root + os.sep, horizon=T,
+                                                       dt=0.02, batch_size=K, disable_individual_compilation=True,
+                                                       update_before_predicting=False)
+                s_single = hanging_state()
+                s0 = np.tile(s_single, (K, 1))
+                Q = np.clip(rng.normal(0, 0.3, (K, T, 1)), -1, 1).astype(np.float32)
+                arrays = {"state_dict_keys": np.array(list(sd.keys()))}
+                for k, v in sd.items():
+                    arrays["w__" + k] = v
+                # (1) rollout from zero hidden state
+                out1 = pred.predict_core(torch.from_numpy(s0), torch.from_numpy(Q)).numpy().astype(np.float32)
+                # (2) advance the stored hidden state with 3 applied controls (update_internal_state_tf), then roll out
+                s_seq, q_seq = [], []
+                s_cur = s0.copy()
+                for i in range(3):
+                    q0 = np.full((K, 1, 1), 0.2 * (i + 1) - 0.3, dtype=np.float32)
+                    pred.update_internal_state_tf(torch.from_numpy(q0), torch.from_numpy(s_cur))
+                    s_seq.append(s_cur[0].copy())
+                    q_seq.append(float(q0[0, 0, 0]))
+                    s_cur = s_cur.copy()
+                    s_cur[:, 1] += 0.05  # a slightly different measured state each tick
+                h_after = None
+                if tname == "GRU":
+                    h_after = np.stack([h[0].numpy() for h in pred.memory_states_ref[0]], 0).astype(np.float32)
+                out2 = pred.predict_core(torch.from_numpy(s_cur), torch.from_numpy(Q)).numpy().astype(np.float32)
+                # (3) per-rollout different initial states
+                s_rand = make_states(rng, K, "random")
+                out3 = pred.predict_core(torch.from_numpy(s_rand), torch.from_numpy(Q)).numpy().astype(np.float32)
+            arrays.update(s0=s_single, Q=Q[:, :, 0], traj_zero_h=out1, upd_s=np.stack(s_seq),
+                          upd_q=np.array(q_seq, dtype=np.float32), s_after=s_cur[0], traj_after_updates=out2,
+                          s_rand=s_rand, traj_rand=out3,
+                          norm_table=np.array([[NORM[c][r] for c in NORM] for r in range(4)], dtype=np.float64),
+                          norm_cols=np.array(list(NORM.keys())))
+            if h_after is not None:
+                arrays["h_after_updates"] = h_after
+            meta = dict(ref="SI_Toolkit/Predictors/predictor_autoregressive_neural.py:266-313,332-352 (torch Sequence, "
+                            "synthetic seeded weights)", net=full_name, type=tname, inputs=INPUTS, outputs=OUTPUTS,
+                        K=K, T=T, seed=seed, weight_scale=scale)
+            save("net_" + full_name.replace("-", "_"), meta, **arrays)
+    finally:
+        shutil.rmtree(root, ignore_errors=True)

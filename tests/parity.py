@@ -2,8 +2,11 @@
 
 Metric: element-wise relative error is meaningless at zero crossings
 (angleD, positionD, angle_sin pass through 0), so trajectories are compared per state channel with the
-norm-wise error  max|a-b| / max|b|  over all rollouts and time steps; the angle channel is compared
-modulo 2*pi (an fp32-vs-fp64 wrap decision at +-pi legitimately flips it by 2*pi).
+range-relative error  max|a-b| / range  over all rollouts and time steps, where range = max|b| for angleD,
+position and positionD and the natural range for the bounded channels (pi for angle, 1 for angle_cos /
+angle_sin -- otherwise a batch that stays near +-pi, where |sin| is tiny, would be judged against that tiny
+number); the angle channel is compared modulo 2*pi (an fp32-vs-fp64 wrap decision at +-pi legitimately flips
+it by 2*pi).
 """
 import json
 import os
@@ -27,8 +30,9 @@ def traj_err(a, b):
     d = a - b
     d[..., 0] = (d[..., 0] + np.pi) % (2 * np.pi) - np.pi
     out = {}
+    natural = {"angle": np.pi, "angle_cos": 1.0, "angle_sin": 1.0}
     for c, n in enumerate(CHANNELS):
-        scale = max(np.abs(b[..., c]).max(), 1e-30)
+        scale = natural.get(n, max(np.abs(b[..., c]).max(), 1e-30))
         out[n] = np.abs(d[..., c]).max() / scale
     return out
 

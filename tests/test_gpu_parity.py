@@ -35,14 +35,19 @@ ROLL_CASES = ["known", "random", "edge", "wrap", "upright", "tiled", "varL", "T1
 CHAOTIC = ("random", "edge", "wrap", "varL", "T100")
 
 
+# kernel variants: default = rotation substeps; the others evaluate sin/cos every substep like the reference text
+VARIANTS = {"rotate": {}, "substep_sincos": dict(substep_sincos=True), "exact_atan2": dict(exact_atan2=True)}
+
+
+@pytest.mark.parametrize("variant", list(VARIANTS))
 @pytest.mark.parametrize("case", ROLL_CASES)
 @pytest.mark.parametrize("integ,fname", [("ODE_v0", "rollout_ode_v0"), ("ODE", "rollout_ode")])
-def test_rollout_vs_reference_golden(integ, fname, case):
+def test_rollout_vs_reference_golden(integ, fname, case, variant):
     z, meta = load_golden(fname)
     s0, Q, ref = z[f"{case}__s0"], z[f"{case}__Q"], z[f"{case}__traj"]
     Lv, m_pole, n = z[f"{case}__var"]
     B, T = Q.shape
-    eng = _engine(B, T, dt=meta["dt"], substeps=int(n), integrator=integ, cost=None)
+    eng = _engine(B, T, dt=meta["dt"], substeps=int(n), integrator=integ, cost=None, **VARIANTS[variant])
     eng.set_variable_parameters(L=Lv, m_pole=m_pole)
     s_in = s0[0] if s0.shape[0] == 1 else s0
     traj, fin = eng.rollout(cuda(s_in), cuda(Q), want_final=True)
@@ -74,8 +79,9 @@ def test_rollout_vs_oracle_layouts_and_flags(integ):
     # time-major (coalesced) layout of controls and trajectories must give bit-identical numbers
     t_tm, _ = eng.rollout(cuda(s), cuda(Q.T), q_layout=L.TIME_MAJOR, traj_layout=L.TIME_MAJOR)
     np.testing.assert_array_equal(t_tm.permute(2, 0, 1).cpu().numpy(), t_rm.cpu().numpy())
-    # exact atan2 / fast-math variants stay within the tolerance of the MPPI operating point
-    for kw, tol in ((dict(exact_atan2=True), 1e-5), (dict(fast_sincos=True), 5e-5), (dict(fast_div=True), 2e-5)):
+    # every kernel variant stays within the tolerance of the MPPI operating point (MUFU sin/cos: looser, measured)
+    for kw, tol in ((dict(substep_sincos=True), 1e-5), (dict(exact_atan2=True), 1e-5), (dict(fast_sincos=True), 5e-5),
+                    (dict(fast_div=True), 2e-5), (dict(fast_div=True, substep_sincos=True), 2e-5)):
         e2 = _engine(B, T, integrator=integ, cost=None, **kw)
         t2, _ = e2.rollout(cuda(s), cuda(Q))
         err = traj_err(t2.cpu().numpy(), ref)
@@ -116,13 +122,15 @@ MPPI_RUNS = ["ode_gradmin", "v0_gradmin", "ode_gradmin_K2000", "ode_grad", "ode_
              "ode_gradmin_T100", "ode_gradmin_T51"]
 
 
+@pytest.mark.parametrize("variant", ["rotate", "substep_sincos"])
 @pytest.mark.parametrize("run", MPPI_RUNS)
-def test_mppi_step_vs_reference_golden(run):
+def test_mppi_step_vs_reference_golden(run, variant):
     """Identical injected noise, identical u_nom, identical s: u / u_nom / J of every solve against the reference."""
     L = _L()
     z, m = load_golden("mppi_" + run)
     T, K = m["T"], m["K"]
-    eng = _engine(K, T, dt=m["dt"], substeps=m["n"], integrator=m["predictor"], cost=m["cost"], interp_period=m["p"])
+    eng = _engine(K, T, dt=m["dt"], substeps=m["n"], integrator=m["predictor"], cost=m["cost"], interp_period=m["p"],
+                  **VARIANTS[variant])
     eng.set_variable_parameters(target_position=m["target_position"], target_equilibrium=m["target_equilibrium"])
     J = torch.empty(K, device="cuda")
     traj = torch.empty((K, T + 1, 6), device="cuda")
