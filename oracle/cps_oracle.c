@@ -218,6 +218,58 @@ void cps_oracle_rollout_cromer(const float *s0, int s0_batched, const float *Q, 
 }
 
 /* ---------------------------------------------------------------------------------------
+ * float64 "truth" integration of either scheme: same formulas, no float32 rounding anywhere (inputs are the
+ * float32 values promoted).  Not a restatement of any reference code path -- it measures the noise floor:
+ * how far the reference's own float32 outputs are from the exact iteration, so that the CUDA kernels can be
+ * required to be no further away than that (tests/test_gpu_parity.py::test_fp32_noise_floor).
+ * ------------------------------------------------------------------------------------- */
+void cps_oracle_rollout_f64(int integrator, const float *s0, int s0_batched, const float *Q, int B, int T, int n,
+                            double dt, const float *ph, double *traj /* [B][T+1][6] */) {
+    const double h = dt / (double)n;
+    const double k = ph[PH_K], m_cart = ph[PH_MCART], m_pole = ph[PH_MPOLE], g = ph[PH_G];
+    const double J_fric = ph[PH_JFRIC], M_fric = ph[PH_MFRIC], L = ph[PH_L], u_max = ph[PH_UMAX];
+    const double thl = ph[PH_TRACK_HALF], kp1 = k + 1.0, L_half = L / 2.0;
+#pragma omp parallel for schedule(static)
+    for (int b = 0; b < B; ++b) {
+        const float *s = s0 + (s0_batched ? (size_t)b * 6 : 0);
+        double angle = s[IDX_ANGLE], angleD = s[IDX_ANGLED], ca = s[IDX_COS], sa = s[IDX_SIN];
+        double position = s[IDX_POS], positionD = s[IDX_POSD];
+        double *row = traj + (size_t)b * (T + 1) * 6;
+        row[0] = angle; row[1] = angleD; row[2] = ca; row[3] = sa; row[4] = position; row[5] = positionD;
+        for (int t = 0; t < T; ++t) {
+            const double u = u_max * (double)Q[(size_t)b * T + t];
+            for (int i = 0; i < n; ++i) {
+                const double A = kp1 * (m_cart + m_pole) - m_pole * (ca * ca);
+                const double F_fric = -M_fric * positionD, T_fric = -J_fric * angleD;
+                const double pDD = (m_pole * g * sa * ca + (T_fric * ca) / L_half
+                                    + kp1 * (-(m_pole * L_half * (angleD * angleD) * sa) + F_fric + u)) / A;
+                const double aDD = (g * sa + pDD * ca + T_fric / (m_pole * L_half)) / (kp1 * L_half);
+                if (integrator == 0) {
+                    const double an = angle + angleD * h, pn = position + positionD * h;
+                    angleD += aDD * h; positionD += pDD * h; angle = an; position = pn;
+                    ca = cos(angle);
+                    if (position >= thl || -position >= thl) {
+                        angleD -= 2.0 * (positionD * ca) / (0.5 * L);
+                        angle += angleD * h;
+                        positionD = -positionD;
+                        position += positionD * h;
+                    }
+                    angle = wrap_fmod(angle);
+                    ca = cos(angle); sa = sin(angle);
+                } else {
+                    angleD += aDD * h; positionD += pDD * h;
+                    angle += angleD * h; position += positionD * h;
+                    ca = cos(angle); sa = sin(angle);
+                    angle = atan2(sa, ca);
+                }
+            }
+            double *o = row + (size_t)(t + 1) * 6;
+            o[0] = angle; o[1] = angleD; o[2] = ca; o[3] = sa; o[4] = position; o[5] = positionD;
+        }
+    }
+}
+
+/* ---------------------------------------------------------------------------------------
  * Cost plugins (float32, torch op order).
  * cp[] layout per plugin:
  *  DEFAULT / QUADRATIC_BOUNDARY: [dd_weight, ep_weight, cc_weight, ccrc_weight, R, MAX_COST]

@@ -62,7 +62,7 @@ def test_optimizer_step_sequence_matches_reference(run, logging):
             lv = opt.logging_values
             assert lv["Q_logged"].shape == (m["K"], m["T"], 1)
             assert lv["rollout_trajectories_logged"].shape == (m["K"], m["T"] + 1, 6)
-            assert vec_err(lv["J_logged"], z["J"][i]) < 1e-5
+            assert vec_err(lv["J_logged"], z["J"][i]) < 3e-5
             np.testing.assert_array_equal(lv["s_logged"], z["s"][i])
             if i == 0:
                 np.testing.assert_allclose(lv["Q_logged"][:, :, 0], z["u_run0"], rtol=0, atol=3e-7)
