@@ -58,7 +58,10 @@ def test_rollout_vs_reference_golden(integ, fname, case, variant):
     e1 = traj_err(got[:, :2], ref[:, :2])
     assert max(e1.values()) < 3e-6, e1
     e = traj_err(got, ref)
-    tol = 3e-4 if case in CHAOTIC else 1e-5
+    # 1e-5 on the MPPI operating point (hanging start, MPPI-sized perturbations); near the unstable upright
+    # equilibrium the reference's own fp32 output is already ~6e-6 from an fp64 integration (test_fp32_noise_floor),
+    # so two fp32 realisations can differ by ~2e-5 there; random high-energy states amplify further
+    tol = 3e-4 if case in CHAOTIC else (3e-5 if case == "upright" else 1e-5)
     assert max(e.values()) < tol, e
 
 
