@@ -145,7 +145,7 @@ class optimizer_mppi_b200:
         self._own_rng = CudaNormalGenerator(self.seed, self.device)
         self.rng = self._own_rng
         self._s_dev = torch.zeros(6, device=self.device)
-        self._s_pin = torch.zeros(6, pin_memory=True)
+        self._s_pin = torch.zeros(6, pin_memory=torch.cuda.is_available())
         self._var = None
         self.optimizer_reset()
 

@@ -75,9 +75,10 @@ def available() -> bool:
     return os.path.isdir(os.path.join(REF, "Control_Toolkit", "Optimizers"))
 
 
-def load():
-    """Make the reference importable; idempotent.  Changes cwd to the reference root
-    (its YAML configs are opened cwd-relative at import time)."""
+def load(workdir=None):
+    """Make the reference importable; idempotent.  Changes cwd to the reference root (its YAML configs are opened
+    cwd-relative at import time) or, if given, to `workdir`: a scratch workspace holding edited COPIES of the
+    application-specific folders, which then shadow the reference's."""
     global _LOADED
     if _LOADED:
         return
@@ -85,10 +86,11 @@ def load():
         raise RuntimeError(f"reference tree not found at {REF}")
     os.environ.setdefault("NUMBA_CACHE_DIR", os.path.join(tempfile.gettempdir(), "cps_numba_cache"))
     os.makedirs(os.environ["NUMBA_CACHE_DIR"], exist_ok=True)
-    os.chdir(REF)
-    for p in (os.path.join(REF, "SI_Toolkit", "src"), REF):
-        if p not in sys.path:
-            sys.path.insert(0, p)
+    os.chdir(workdir or REF)
+    for p in (REF, os.path.join(REF, "SI_Toolkit", "src")) + ((workdir,) if workdir else ()):
+        if p in sys.path:
+            sys.path.remove(p)
+        sys.path.insert(0, p)
     for n in _STUB_NAMES:
         if n not in sys.modules:
             try:
