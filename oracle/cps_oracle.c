@@ -454,22 +454,12 @@ static inline float clipf(float x, float lo, float hi) { return x < lo ? lo : (x
  * delta_u_in: if non-NULL, [K][T] perturbations are taken as given (post-interpolation injection),
  * else they are interpolated from eps[K][n_ind].
  * Optional outputs (may be NULL): J[K], traj[K][T+1][6], u_run[K][T], delta_u_out[K][T]. Returns u. */
-float cps_oracle_mppi_step(int integrator, int cost_id, const float *cp, const float *mp, const float *ph,
-                           const float *s, float *u_nom, const float *eps, const float *delta_u_in, float u_prev,
-                           float target_position, float target_equilibrium, int K, int T, int n, double dt, int p,
-                           float *J_out, float *traj_out, float *u_run_out, float *delta_u_out) {
-    const float cc_weight = mp[0], R = mp[1], LBD = mp[2], NU = mp[3], stdev = mp[4], lo = mp[5], hi = mp[6];
-    float *delta_u = (float *)malloc(sizeof(float) * (size_t)K * T);
-    float *u_run = (float *)malloc(sizeof(float) * (size_t)K * T);
-    float *traj = (float *)malloc(sizeof(float) * (size_t)K * (T + 1) * 6);
-    float *J = (float *)malloc(sizeof(float) * (size_t)K);
-    /* u_nom = concat([u_nom[1:], u_nom[-1:]]) (:183) */
-    for (int t = 0; t + 1 < T; ++t) u_nom[t] = u_nom[t + 1];
-    if (delta_u_in) memcpy(delta_u, delta_u_in, sizeof(float) * (size_t)K * T);
-    else cps_oracle_interpolate(eps, K, T, p, stdev, delta_u);
-    for (size_t i = 0; i < (size_t)K * T; ++i) u_run[i] = clipf(u_nom[i % T] + delta_u[i], lo, hi); /* :185-186 */
-    if (integrator == 0) cps_oracle_rollout_v0(s, 0, u_run, K, T, n, dt, ph, ph[PH_L], traj, NULL);
-    else cps_oracle_rollout_cromer(s, 0, u_run, K, T, n, dt, ph, traj, NULL);
+/* Everything of _predict_and_cost that follows the rollout (:188-190): trajectory cost, MPPI correction cost,
+ * exp-weighted average, clip.  u_nom is the SHIFTED nominal sequence on entry and the updated one on exit. */
+static float mppi_tail(int cost_id, const float *cp, const float *mp, const float *ph, float *u_nom,
+                       const float *delta_u, const float *u_run, const float *traj, float u_prev,
+                       float target_position, float target_equilibrium, int K, int T, float *J) {
+    const float cc_weight = mp[0], R = mp[1], LBD = mp[2], NU = mp[3], lo = mp[5], hi = mp[6];
     cps_oracle_trajectory_cost(cost_id, cp, traj, u_run, u_prev, K, T, ph[PH_TRACK_HALF], target_position,
                                target_equilibrium, J);
     /* mppi_correction_cost (:153-154), summed over the horizon */
@@ -494,13 +484,69 @@ float cps_oracle_mppi_step(int integrator, int cost_id, const float *cp, const f
         for (int t = 0; t < T; ++t) b[t] += (double)(w * delta_u[(size_t)k * T + t]);
     }
     for (int t = 0; t < T; ++t) u_nom[t] = clipf(u_nom[t] + (float)b[t] / (float)a, lo, hi); /* :189 */
-    const float u = u_nom[0];
+    free(b);
+    return u_nom[0];
+}
+
+void cps_oracle_net_rollout(int net_type, int n_state_in, int n_layers, const int *hsz, int n_out,
+                            const float *weights, const int *in_idx, const int *out_idx, const float *norm_a,
+                            const float *norm_b, const float *denorm_A, const float *denorm_B, const float *s0,
+                            int s0_batched, const float *Q, const float *h0, int h0_batched, int B, int T,
+                            float *traj, float *h_final);
+
+/* integrator: 0 = ODE_v0, 1 = ODE, 2 = neural (net_* arguments used; h0 = the predictor's stored hidden state,
+ * shared by all rollouts, predictor_autoregressive_neural.py:291). */
+static float mppi_step_impl(int integrator, int cost_id, const float *cp, const float *mp, const float *ph,
+                            const float *s, float *u_nom, const float *eps, const float *delta_u_in, float u_prev,
+                            float target_position, float target_equilibrium, int K, int T, int n, double dt, int p,
+                            float *J_out, float *traj_out, float *u_run_out, float *delta_u_out,
+                            int net_type, int n_state_in, int n_layers, const int *hsz, int n_out,
+                            const float *weights, const int *in_idx, const int *out_idx, const float *norm_a,
+                            const float *norm_b, const float *denorm_A, const float *denorm_B, const float *h0) {
+    const float stdev = mp[4], lo = mp[5], hi = mp[6];
+    float *delta_u = (float *)malloc(sizeof(float) * (size_t)K * T);
+    float *u_run = (float *)malloc(sizeof(float) * (size_t)K * T);
+    float *traj = (float *)malloc(sizeof(float) * (size_t)K * (T + 1) * 6);
+    float *J = (float *)malloc(sizeof(float) * (size_t)K);
+    /* u_nom = concat([u_nom[1:], u_nom[-1:]]) (:183) */
+    for (int t = 0; t + 1 < T; ++t) u_nom[t] = u_nom[t + 1];
+    if (delta_u_in) memcpy(delta_u, delta_u_in, sizeof(float) * (size_t)K * T);
+    else cps_oracle_interpolate(eps, K, T, p, stdev, delta_u);
+    for (size_t i = 0; i < (size_t)K * T; ++i) u_run[i] = clipf(u_nom[i % T] + delta_u[i], lo, hi); /* :185-186 */
+    if (integrator == 0) cps_oracle_rollout_v0(s, 0, u_run, K, T, n, dt, ph, ph[PH_L], traj, NULL);
+    else if (integrator == 1) cps_oracle_rollout_cromer(s, 0, u_run, K, T, n, dt, ph, traj, NULL);
+    else cps_oracle_net_rollout(net_type, n_state_in, n_layers, hsz, n_out, weights, in_idx, out_idx, norm_a, norm_b,
+                                denorm_A, denorm_B, s, 0, u_run, h0, 0, K, T, traj, NULL);
+    const float u = mppi_tail(cost_id, cp, mp, ph, u_nom, delta_u, u_run, traj, u_prev, target_position,
+                              target_equilibrium, K, T, J);
     if (J_out) memcpy(J_out, J, sizeof(float) * (size_t)K);
     if (traj_out) memcpy(traj_out, traj, sizeof(float) * (size_t)K * (T + 1) * 6);
     if (u_run_out) memcpy(u_run_out, u_run, sizeof(float) * (size_t)K * T);
     if (delta_u_out) memcpy(delta_u_out, delta_u, sizeof(float) * (size_t)K * T);
-    free(b); free(J); free(traj); free(u_run); free(delta_u);
+    free(J); free(traj); free(u_run); free(delta_u);
     return u;
+}
+
+float cps_oracle_mppi_step(int integrator, int cost_id, const float *cp, const float *mp, const float *ph,
+                           const float *s, float *u_nom, const float *eps, const float *delta_u_in, float u_prev,
+                           float target_position, float target_equilibrium, int K, int T, int n, double dt, int p,
+                           float *J_out, float *traj_out, float *u_run_out, float *delta_u_out) {
+    return mppi_step_impl(integrator, cost_id, cp, mp, ph, s, u_nom, eps, delta_u_in, u_prev, target_position,
+                          target_equilibrium, K, T, n, dt, p, J_out, traj_out, u_run_out, delta_u_out, 0, 0, 0, NULL, 0,
+                          NULL, NULL, NULL, NULL, NULL, NULL, NULL, NULL);
+}
+
+/* optimizer_mppi with predictor_autoregressive_neural (optimizer_mppi.py:180-192 with predict_core of
+ * predictor_autoregressive_neural.py:266-313). */
+float cps_oracle_mppi_step_net(int cost_id, const float *cp, const float *mp, const float *ph, const float *s,
+                               float *u_nom, const float *eps, float u_prev, float target_position,
+                               float target_equilibrium, int K, int T, int p, float *J_out, float *traj_out,
+                               float *u_run_out, int net_type, int n_state_in, int n_layers, const int *hsz, int n_out,
+                               const float *weights, const int *in_idx, const int *out_idx, const float *norm_a,
+                               const float *norm_b, const float *denorm_A, const float *denorm_B, const float *h0) {
+    return mppi_step_impl(2, cost_id, cp, mp, ph, s, u_nom, eps, NULL, u_prev, target_position, target_equilibrium, K, T,
+                          1, 0.0, p, J_out, traj_out, u_run_out, NULL, net_type, n_state_in, n_layers, hsz, n_out,
+                          weights, in_idx, out_idx, norm_a, norm_b, denorm_A, denorm_B, h0);
 }
 
 /* ---------------------------------------------------------------------------------------

@@ -252,6 +252,7 @@ def main(which=None):
     try:
         from oracle import gen_golden_net
         todo["net"] = gen_golden_net.gen_net
+        todo["mppi_net"] = gen_golden_net.gen_mppi_net
     except ImportError:
         pass
     for k, fn in todo.items():

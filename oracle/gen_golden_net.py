@@ -112,3 +112,91 @@ def gen_net():
             save("net_" + full_name.replace("-", "_"), meta, **arrays)
     finally:
         shutil.rmtree(root, ignore_errors=True)
+
+
+class NeuralCoreAdapter:
+    """PredictorWrapper-shaped holder around the unmodified predictor_autoregressive_neural, with the wrapper's
+    `update` (SI_Toolkit/src/SI_Toolkit/Predictors/predictor_wrapper.py:173-177)."""
+
+    def __init__(self, predictor):
+        self.predictor = predictor
+        self.predictor_type = "neural"
+        self.num_states, self.num_control_inputs = 6, 1
+        self.horizon, self.batch_size = predictor.horizon, predictor.batch_size
+
+    def predict_core(self, s, Q):
+        return self.predictor.predict_core(s, Q)
+
+    def update(self, Q0, s):
+        import torch
+        self.predictor.update_internal_state_tf(s=torch.as_tensor(s, dtype=torch.float32),
+                                                Q0=torch.as_tensor(Q0, dtype=torch.float32))
+
+    def copy(self):
+        return R._NullPredictor()
+
+    def configure(self, **kw):
+        pass
+
+
+def gen_mppi_net():
+    """optimizer_mppi (unmodified, torch lib, injected noise) driving predictor_autoregressive_neural: a closed loop
+    of several solves, so the hidden-state update after every solve (optimizer_mppi.py:191,194-196) is pinned too."""
+    import torch
+    from oracle import oracle as O
+    R.load()
+    from SI_Toolkit.Predictors.predictor_autoregressive_neural import predictor_autoregressive_neural
+    root = tempfile.mkdtemp(prefix="cps_models_")
+    try:
+        for (run, full_name, tname, seed, scale, cost, K, T, steps) in (
+                ("gru64_gradmin", "GRU-6IN-64H1-64H2-5OUT-0", "GRU", 7, 1.0, "quadratic_boundary_grad_minimal", 256, 50, 4),
+                ("gru32_grad", "GRU-6IN-32H1-32H2-5OUT-0", "GRU", 8, 2.0, "quadratic_boundary_grad", 128, 35, 3),
+                ("dense32_gradmin", "Dense-6IN-32H1-32H2-5OUT-0", "Dense", 9, 1.5, "quadratic_boundary_grad_minimal", 128, 50, 3)):
+            sd = write_model_dir(root, full_name, tname, seed, scale)
+            lib = R.torch_lib()
+            if cost == "quadratic_boundary_grad":
+                from oracle.gen_golden import _patch_torch_lib_for_grad
+                _patch_torch_lib_for_grad(lib)
+            vp = R.variable_parameters(lib, 0.0, 1.0)
+            cw = R.cost_function(cost, lib, vp, K, T)
+            with contextlib.redirect_stdout(io.StringIO()):
+                pred = predictor_autoregressive_neural(model_name=full_name, path_to_model=root + os.sep, horizon=T,
+                                                       dt=0.02, batch_size=K, disable_individual_compilation=True,
+                                                       update_before_predicting=False)
+            opt = R.optimizer_mppi(NeuralCoreAdapter(pred), cw, K, T, logging=True)
+            n_ind = opt.Interpolator.number_of_interpolation_inducing_points
+            gen = torch.Generator().manual_seed(3)
+            draws = [torch.normal(0.0, 1.0, size=(K, n_ind, 1), generator=gen, dtype=torch.float32) for _ in range(steps)]
+            opt.rng = R.InjectedNormal(draws)
+            s = hanging_state()
+            arrays = {"eps": np.stack([d.numpy()[:, :, 0] for d in draws], 0), "state_dict_keys": np.array(list(sd.keys()))}
+            for k, v in sd.items():
+                arrays["w__" + k] = v
+            S, U, UNOM, JJ, UPREV, HH = [], [], [], [], [], []
+            for i in range(steps):
+                UPREV.append(np.float32(opt.u))
+                with torch.inference_mode(), contextlib.redirect_stdout(io.StringIO()):
+                    u = opt.step(s.copy())
+                S.append(s.copy())
+                U.append(np.float32(u))
+                UNOM.append(opt.u_nom.numpy().reshape(-1).astype(np.float32))
+                JJ.append(opt.logging_values["J_logged"].astype(np.float32))
+                if tname == "GRU":  # hidden state AFTER the post-solve update, row 0 (all rows are identical)
+                    HH.append(np.concatenate([h[0].numpy().reshape(-1) for h in pred.memory_states_ref[0]]).astype(np.float32))
+                if i == 0:
+                    arrays["u_run0"] = opt.logging_values["Q_logged"][:, :, 0].astype(np.float32)
+                    arrays["traj0"] = opt.logging_values["rollout_trajectories_logged"][:32].astype(np.float32)
+                s = O.rollout("ODE", s, np.array([[u]], dtype=np.float32), n=10, dt=0.02)[0, 1]
+            arrays.update(s=np.stack(S), u=np.array(U), u_nom=np.stack(UNOM), J=np.stack(JJ), u_prev=np.array(UPREV),
+                          norm_table=np.array([[NORM[c][r] for c in NORM] for r in range(4)], dtype=np.float64),
+                          norm_cols=np.array(list(NORM.keys())))
+            if HH:
+                arrays["h_after"] = np.stack(HH)
+            meta = dict(ref="Control_Toolkit/Optimizers/optimizer_mppi.py:180-224 + predictor_autoregressive_neural.py:266-352 "
+                            "(torch lib, injected rng.normal draws, synthetic seeded weights)",
+                        net=full_name, type=tname, inputs=INPUTS, outputs=OUTPUTS, predictor="neural", cost=cost, K=K, T=T,
+                        steps=steps, target_position=0.0, target_equilibrium=1.0, dt=0.02, p=10, cc_weight=1.0, R=1.0,
+                        LBD=100.0, NU=1000.0, SQRTRHOINV=0.03, seed=seed, weight_scale=scale)
+            save("mppi_net_" + run, meta, **arrays)
+    finally:
+        shutil.rmtree(root, ignore_errors=True)

@@ -1,0 +1,46 @@
+"""Builds the flat network description (cps_net_load / cps_oracle_net_rollout arguments) from a net golden file.
+
+Follows the reference's bookkeeping: SI_Toolkit/src/SI_Toolkit/Predictors/predictor_autoregressive_neural.py:163-199
+(input/output index maps), Functions/General/Normalising.py:15-108 (minmax_sym coefficients, computed in float32 as
+the torch library does)."""
+import json
+
+import numpy as np
+
+STATE_VARIABLES = ["angle", "angleD", "angle_cos", "angle_sin", "position", "positionD"]
+
+
+def minmax_sym_coeffs(table, cols, names):
+    """(a, b, A, B) float32 vectors for `names`; table rows: mean, std, max, min (Normalising.py:1-9)."""
+    t = np.asarray(table, dtype=np.float32)
+    idx = [list(cols).index(n) for n in names]
+    mx, mn = t[2, idx], t[3, idx]
+    a = np.float32(2.0) / (mx - mn)
+    b = np.float32(-1.0) + np.float32(2.0) * (-mn / (mx - mn))
+    A = (mx - mn) / np.float32(2.0)
+    B = (mx - mn) / np.float32(2.0) + mn
+    return a.astype(np.float32), b.astype(np.float32), A.astype(np.float32), B.astype(np.float32)
+
+
+def net_spec_from_golden(z):
+    meta = json.loads(str(z["meta"]))
+    inputs, outputs, ntype = meta["inputs"], meta["outputs"], meta["type"]
+    keys = [str(k) for k in z["state_dict_keys"]]
+    n_lay = max(int(k.split(".")[1]) for k in keys)  # index of the output layer
+    layers, hsz = [], []
+    for l in range(n_lay):
+        if ntype == "GRU":
+            lay = tuple(z[f"w__layers.{l}.{n}"] for n in ("weight_ih", "weight_hh", "bias_ih", "bias_hh"))
+            hsz.append(lay[1].shape[1])
+        else:
+            lay = (z[f"w__layers.{l}.weight"], z[f"w__layers.{l}.bias"])
+            hsz.append(lay[0].shape[0])
+        layers.append(lay)
+    out_layer = (z[f"w__layers.{n_lay}.weight"], z[f"w__layers.{n_lay}.bias"])
+    cols = [str(c) for c in z["norm_cols"]]
+    a, b, _, _ = minmax_sym_coeffs(z["norm_table"], cols, inputs)
+    _, _, A, B = minmax_sym_coeffs(z["norm_table"], cols, outputs)
+    return dict(net_type=ntype, hsz=hsz, layers=layers, out_layer=out_layer,
+                in_idx=[STATE_VARIABLES.index(n) for n in inputs[1:]],
+                out_idx=[STATE_VARIABLES.index(n) for n in outputs],
+                norm_a=a, norm_b=b, denorm_A=A, denorm_B=B, meta=meta)
