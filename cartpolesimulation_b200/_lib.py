@@ -17,7 +17,8 @@ CPS_OK = 0
 STATUS_NAMES = {0: "CPS_OK", 1: "CPS_ERR_INVALID", 2: "CPS_ERR_CUDA", 3: "CPS_ERR_UNSUPPORTED",
                 4: "CPS_ERR_NOT_CONFIGURED"}
 
-EULER_V0, EULER_CROMER = 0, 1
+EULER_V0, EULER_CROMER, PREDICTOR_NEURAL = 0, 1, 2
+NET_GRU, NET_DENSE, NET_MAX_LAYERS = 0, 1, 4
 COST_NONE, COST_DEFAULT, COST_QUADRATIC_BOUNDARY, COST_QB_GRAD_MINIMAL, COST_QB_GRAD = -1, 0, 1, 2, 3
 NOISE_INDUCING, NOISE_DIRECT = 0, 1
 ROLLOUT_MAJOR, TIME_MAJOR = 0, 1
@@ -29,6 +30,15 @@ class cps_config(C.Structure):
     _fields_ = [("struct_size", C.c_int), ("device", C.c_int), ("num_rollouts", C.c_int), ("horizon", C.c_int),
                 ("substeps", C.c_int), ("dt", C.c_float), ("integrator", C.c_int), ("cost_id", C.c_int),
                 ("noise_mode", C.c_int), ("interp_period", C.c_int), ("flags", C.c_uint)]
+
+
+class cps_net_desc(C.Structure):
+    _fields_ = [("struct_size", C.c_int), ("net_type", C.c_int), ("n_layers", C.c_int),
+                ("hidden", C.c_int * 4), ("n_state_in", C.c_int), ("in_idx", C.c_int * 6), ("n_out", C.c_int),
+                ("out_idx", C.c_int * 6), ("norm_a", C.c_float * 7), ("norm_b", C.c_float * 7),
+                ("denorm_A", C.c_float * 6), ("denorm_B", C.c_float * 6), ("differential", C.c_int),
+                ("diff_p1", C.c_float * 6), ("diff_p2", C.c_float * 6), ("out_norm_a", C.c_float * 6),
+                ("out_norm_b", C.c_float * 6), ("out_to_in", C.c_int * 6)]
 
 
 # name -> (restype, argtypes); every symbol include/cps.h declares
@@ -56,6 +66,13 @@ SYMBOLS = {
     "cps_mppi_finalize": (C.c_int, [_VP, _VP, C.c_int, _VP, _VP]),
     "cps_rollout": (C.c_int, [_VP, _VP, C.c_int, _VP, C.c_int, C.c_int, C.c_int, _VP, C.c_int, _VP]),
     "cps_rollout_host": (C.c_int, [_VP, _VP, C.c_int, _VP, C.c_int, C.c_int, C.c_int, _VP, C.c_int, _VP]),
+    "cps_net_load": (C.c_int, [_VP, C.POINTER(cps_net_desc), _FP, C.c_longlong]),
+    "cps_net_rollout": (C.c_int, [_VP, _VP, C.c_int, _VP, C.c_int, C.c_int, C.c_int, _VP, C.c_int, _VP, C.c_int, _VP]),
+    "cps_net_update": (C.c_int, [_VP, _VP, _VP]),
+    "cps_net_state_size": (C.c_int, [_VP]),
+    "cps_net_reset_state": (C.c_int, [_VP]),
+    "cps_net_get_state": (C.c_int, [_VP, _FP]),
+    "cps_net_set_state": (C.c_int, [_VP, _FP]),
     "cps_trajectory_cost": (C.c_int, [_VP, _VP, _VP, C.c_float, C.c_int, C.c_int, _VP]),
     "cps_stage_cost": (C.c_int, [_VP, _VP, C.c_int, _VP, C.c_float, C.c_int, C.c_int, C.c_int, _VP]),
     "cps_terminal_cost": (C.c_int, [_VP, _VP, C.c_int, _VP]),
@@ -71,7 +88,7 @@ def library_path() -> str:
 
 def build(verbose: bool = False) -> str:
     """Compile csrc/*.cu for sm_100a into the in-tree libcps_b200.so (nvcc cross-compiles without a GPU)."""
-    out = subprocess.run(["make", "-C", _CSRC], capture_output=True, text=True)
+    out = subprocess.run(["make", "-j4", "-C", _CSRC], capture_output=True, text=True)
     if verbose or out.returncode != 0:
         print(out.stdout[-4000:])
         print(out.stderr[-4000:])
@@ -116,4 +133,6 @@ def check(rc: int, handle=None):
         raise ValueError(f"{name}: {msg}")
     if rc == 3:
         raise NotImplementedError(f"{name}: {msg}")
+    if rc == 4:
+        raise RuntimeError(f"{name}: {msg}")
     raise CpsError(f"{name}: {msg}")

@@ -27,7 +27,7 @@ def _check_dev(t, name, device, dtype=torch.float32):
     return t
 
 
-INTEGRATORS = {"ODE_v0": L.EULER_V0, "ODE": L.EULER_CROMER}
+INTEGRATORS = {"ODE_v0": L.EULER_V0, "ODE": L.EULER_CROMER, "neural": L.PREDICTOR_NEURAL}
 COSTS = {None: L.COST_NONE, "none": L.COST_NONE, "default": L.COST_DEFAULT,
          "quadratic_boundary": L.COST_QUADRATIC_BOUNDARY,
          "quadratic_boundary_grad_minimal": L.COST_QB_GRAD_MINIMAL,
@@ -235,6 +235,95 @@ class Engine:
         self._chk(self.lib.cps_rollout_host(self._h, vp(s0_np), batched, vp(Q2), q_layout, B, T, vp(traj_out),
                                             traj_layout, vp(final_out)))
         return traj_out, final_out
+
+    # -- neural predictor ------------------------------------------------------------------------------
+    def net_load(self, spec: dict):
+        """cps_net_load.  spec: dict(net_type 'GRU'|'Dense', hsz, weights (flat float32, include/cps.h order), in_idx,
+        out_idx, norm_a, norm_b, denorm_A, denorm_B[, differential, diff_p1, diff_p2, out_norm_a, out_norm_b,
+        out_to_in])."""
+        d = L.cps_net_desc()
+        d.struct_size = C.sizeof(L.cps_net_desc)
+        if spec["net_type"] not in ("GRU", "Dense"):
+            raise NotImplementedError(f"network type {spec['net_type']!r} is not supported (GRU and Dense are)")
+        d.net_type = {"GRU": L.NET_GRU, "Dense": L.NET_DENSE}[spec["net_type"]]
+        hsz = [int(x) for x in spec["hsz"]]
+        if len(hsz) > L.NET_MAX_LAYERS:
+            raise NotImplementedError(f"at most {L.NET_MAX_LAYERS} hidden layers are supported")
+        d.n_layers = len(hsz)
+        for i, v in enumerate(hsz):
+            d.hidden[i] = v
+        d.n_state_in, d.n_out = len(spec["in_idx"]), len(spec["out_idx"])
+        for i, v in enumerate(spec["in_idx"]):
+            d.in_idx[i] = int(v)
+        for i, v in enumerate(spec["out_idx"]):
+            d.out_idx[i] = int(v)
+        for name in ("norm_a", "norm_b", "denorm_A", "denorm_B", "diff_p1", "diff_p2", "out_norm_a", "out_norm_b"):
+            if spec.get(name) is not None:
+                for i, v in enumerate(np.asarray(spec[name], dtype=np.float32).reshape(-1)):
+                    getattr(d, name)[i] = float(v)
+        d.differential = int(bool(spec.get("differential", False)))
+        for i, v in enumerate(spec.get("out_to_in", []) or []):
+            d.out_to_in[i] = int(v)
+        w = np.ascontiguousarray(spec["weights"], dtype=np.float32).reshape(-1)
+        self.use_current_stream()
+        self._chk(self.lib.cps_net_load(self._h, C.byref(d), w.ctypes.data_as(L._FP), w.shape[0]))
+        self.net_htot = int(self.lib.cps_net_state_size(self._h))
+
+    def net_rollout(self, s0, Q, q_layout=L.ROLLOUT_MAJOR, traj_layout=L.ROLLOUT_MAJOR, h0=None, want_traj=True,
+                    want_h=False, traj_out=None):
+        """cps_net_rollout on device tensors; h0 None = the stored hidden state, [Htot] shared, or [B, Htot]."""
+        self.use_current_stream()
+        _check_dev(s0, "s0", self.device)
+        _check_dev(Q, "Q", self.device)
+        Q2 = Q.reshape(Q.shape[0], Q.shape[1])
+        B, T = (Q2.shape if q_layout == L.ROLLOUT_MAJOR else Q2.shape[::-1])
+        if s0.numel() == 6:
+            batched = 0
+        elif s0.shape[0] == B and s0.numel() == 6 * B:
+            batched = 1
+        else:
+            raise ValueError("Batch size of control input contradict batch size of initial state")
+        h_b = 0
+        if h0 is not None:
+            _check_dev(h0, "h0", self.device)
+            if h0.numel() == self.net_htot:
+                h_b = 0
+            elif h0.numel() == self.net_htot * B:
+                h_b = 1
+            else:
+                raise ValueError(f"h0 has {h0.numel()} elements, expected {self.net_htot} or {self.net_htot * B}")
+        if want_traj and traj_out is None:
+            shape = (B, T + 1, 6) if traj_layout == L.ROLLOUT_MAJOR else (T + 1, 6, B)
+            traj_out = torch.empty(shape, device=self.device, dtype=torch.float32)
+        h_final = torch.empty((B, self.net_htot), device=self.device, dtype=torch.float32) if want_h else None
+        self._chk(self.lib.cps_net_rollout(self._h, _ptr(s0), batched, _ptr(Q2), q_layout, B, T, _ptr(h0), h_b,
+                                           _ptr(traj_out), traj_layout, _ptr(h_final)))
+        return traj_out, h_final
+
+    def net_update(self, s, q0):
+        """cps_net_update: advance the stored hidden state by one step on (q0 [1], s [6]) -- device tensors."""
+        self.use_current_stream()
+        _check_dev(s, "s", self.device)
+        _check_dev(q0, "q0", self.device)
+        self._chk(self.lib.cps_net_update(self._h, _ptr(s), _ptr(q0)))
+
+    def net_reset_state(self):
+        self.use_current_stream()
+        self._chk(self.lib.cps_net_reset_state(self._h))
+
+    def net_get_state(self) -> np.ndarray:
+        self.use_current_stream()
+        out = np.zeros(max(self.net_htot, 1), dtype=np.float32)
+        self._chk(self.lib.cps_net_get_state(self._h, out.ctypes.data_as(L._FP)))
+        return out[:self.net_htot]
+
+    def net_set_state(self, state):
+        self.use_current_stream()
+        v = np.ascontiguousarray(np.asarray(state, dtype=np.float32).reshape(-1))
+        if v.shape[0] != self.net_htot:
+            raise ValueError(f"hidden state has {v.shape[0]} entries, expected {self.net_htot}")
+        if self.net_htot:
+            self._chk(self.lib.cps_net_set_state(self._h, v.ctypes.data_as(L._FP)))
 
     # -- standalone costs -----------------------------------------------------------------------------
     def trajectory_cost(self, traj, Q, u_prev=0.0):

@@ -1,0 +1,127 @@
+// cps_internal.cuh -- declarations shared by the translation units of libcps_b200.so (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <string>
+
+#include "../../include/cps.h"
+#include "cps_device.cuh"
+
+using namespace cps;
+
+// =====================================================================================================
+// kernel argument blocks (passed by value: they live in the constant bank)
+// =====================================================================================================
+struct MppiArgs {
+    OdeParams ode;
+    CostParams cost;
+    MppiParams mp;
+    const float *s;          // [6]
+    const float *noise;      // INDUCING: n_ind x K draws, DIRECT: T x K delta_u
+    long long ns_i, ns_k;    // element strides of `noise` along channel / rollout
+    float u_prev;
+    float *u_nom;            // [T] in/out
+    float *u_out;            // [1]
+    float *J_out;            // [K] or null
+    float *traj_out;         // K x (T+1) x 6 or null
+    long long ts_k, ts_t, ts_c;
+    float *u_run_out;        // [K][T] or null
+    float *partials;         // [gridDim.x][2 + n_red]
+    unsigned *ticket;
+    int *nonfinite;
+    float *shard_out;        // non-null: stop after the local merge and write {m, S, E[n_red]}
+};
+
+struct RolloutArgs {
+    OdeParams ode;
+    const float *s0;
+    long long ss_b;          // 6 if batched, 0 if one shared state
+    const float *Q;
+    long long qs_b, qs_t;
+    int B, T;
+    float *traj_out;
+    long long ts_k, ts_t, ts_c;
+    float *final_out;        // [B][6] or null
+};
+
+struct CostArgs {
+    CostParams cost;
+    const float *traj;       // [K][rows][6], rows = T+1 (or T for get_stage_cost on states[:, :-1])
+    const float *Q;          // [K][T]
+    float u_prev;
+    int K, T, rows;
+    float inv_T1;
+    float *J;                // [K] or null
+    float *stage;            // [K][T] or null
+    int unshifted;
+};
+
+struct FinalizeArgs {
+    MppiParams mp;
+    const float *partials;   // [n_parts][2 + n_red]
+    int n_parts;
+    float *u_nom;
+    float *u_out;
+    float *shard_out;
+};
+
+
+struct NetState;  // cps_net.cu
+
+struct cps_handle {
+    cps_config cfg;
+    int n_ind, n_red;
+    float phys[CPS_PH_COUNT];
+    float cost_in[24];
+    int cost_in_n;
+    float mppi_in[7];  // cc_weight, R, LBD, NU, sigma, lo, hi
+    float target_position, target_equilibrium, L_var, m_pole_var;
+    OdeParams ode;
+    CostParams cost;
+    MppiParams mp;
+    cudaStream_t stream;
+    // scratch owned by the handle
+    float *d_partials;
+    unsigned *d_ticket;
+    int *d_nonfinite;
+    float *d_s, *d_unom, *d_u;
+    float *h_pin;  // pinned: [0..6) s, [8] u
+    int grid, block;
+    size_t smem;
+    int shard;
+    float *shard_out;
+    // growable buffers of cps_rollout_host
+    float *d_rs0, *d_rQ, *d_rtraj, *d_rfinal;
+    size_t cap_rs0, cap_rQ, cap_rtraj, cap_rfinal;
+    long long launches;
+    std::string err;
+    NetState *net;  // neural predictor (cps_net_load), owned
+};
+
+extern thread_local std::string g_create_err;
+
+// cps_net.cu
+void cps_net_free(cps_handle *h);
+int cps_net_mppi_step(cps_handle *h, const float *s_dev, const float *noise_dev, int noise_layout, float u_prev,
+                      float *u_nom_dev, float *u_out_dev, float *J_out_dev, float *traj_out_dev, int traj_layout,
+                      float *u_run_out_dev);
+
+static inline int fail(cps_handle *h, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf;
+    else g_create_err = buf;
+    return code;
+}
+
+#define CUDA_TRY(h, expr)                                                                          \
+    do {                                                                                           \
+        cudaError_t e_ = (expr);                                                                   \
+        if (e_ != cudaSuccess) return fail(h, CPS_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e_)); \
+    } while (0)
+

@@ -17,121 +17,7 @@
 #include <new>
 #include <string>
 
-#include "../../include/cps.h"
-#include "cps_device.cuh"
-
-using namespace cps;
-
-// =====================================================================================================
-// kernel argument blocks (passed by value: they live in the constant bank)
-// =====================================================================================================
-struct MppiArgs {
-    OdeParams ode;
-    CostParams cost;
-    MppiParams mp;
-    const float *s;          // [6]
-    const float *noise;      // INDUCING: n_ind x K draws, DIRECT: T x K delta_u
-    long long ns_i, ns_k;    // element strides of `noise` along channel / rollout
-    float u_prev;
-    float *u_nom;            // [T] in/out
-    float *u_out;            // [1]
-    float *J_out;            // [K] or null
-    float *traj_out;         // K x (T+1) x 6 or null
-    long long ts_k, ts_t, ts_c;
-    float *u_run_out;        // [K][T] or null
-    float *partials;         // [gridDim.x][2 + n_red]
-    unsigned *ticket;
-    int *nonfinite;
-    float *shard_out;        // non-null: stop after the local merge and write {m, S, E[n_red]}
-};
-
-struct RolloutArgs {
-    OdeParams ode;
-    const float *s0;
-    long long ss_b;          // 6 if batched, 0 if one shared state
-    const float *Q;
-    long long qs_b, qs_t;
-    int B, T;
-    float *traj_out;
-    long long ts_k, ts_t, ts_c;
-    float *final_out;        // [B][6] or null
-};
-
-struct CostArgs {
-    CostParams cost;
-    const float *traj;       // [K][rows][6], rows = T+1 (or T for get_stage_cost on states[:, :-1])
-    const float *Q;          // [K][T]
-    float u_prev;
-    int K, T, rows;
-    float inv_T1;
-    float *J;                // [K] or null
-    float *stage;            // [K][T] or null
-    int unshifted;
-};
-
-struct FinalizeArgs {
-    MppiParams mp;
-    const float *partials;   // [n_parts][2 + n_red]
-    int n_parts;
-    float *u_nom;
-    float *u_out;
-    float *shard_out;
-};
-
-__device__ __forceinline__ void store_state(float *base, long long ts_c, const State &z) {
-    base[0 * ts_c] = z.th;
-    base[1 * ts_c] = z.w;
-    base[2 * ts_c] = z.c;
-    base[3 * ts_c] = z.s;
-    base[4 * ts_c] = z.x;
-    base[5 * ts_c] = z.v;
-}
-
-// Merge `n_parts` partial records {m, S, E[0..n_red)} with the online-softmax rule and either finish the MPPI update
-// (u_nom <- clip(shift(u_nom) + Delta), u = u_nom[0]) or emit the merged record (K sharded over GPUs).
-// Called by one whole block; s_E is shared scratch of >= n_red + 2 floats; s_unom holds the SHIFTED nominal inputs.
-__device__ __forceinline__ void merge_and_finish(const MppiParams &mp, const float *partials, int n_parts, float *s_E,
-                                                 const float *s_unom, float *u_nom, float *u_out, float *shard_out,
-                                                 bool direct_noise) {
-    const int rec = 2 + mp.n_red;
-    const int tid = threadIdx.x;
-    // global minimum (every thread redundantly; n_parts is small and the records sit in L2)
-    float m = INFINITY;
-    for (int b = 0; b < n_parts; ++b) m = fminf(m, __ldcg(partials + (size_t)b * rec));
-    for (int c = tid; c < mp.n_red + 1; c += blockDim.x) {
-        float acc = 0.0f;
-        for (int b = 0; b < n_parts; ++b) {  // fixed order -> deterministic
-            const float mb = __ldcg(partials + (size_t)b * rec);
-            const float f = expf(-(mb - m) * mp.inv_lambda);
-            acc = fmaf(__ldcg(partials + (size_t)b * rec + 1 + c), f, acc);
-        }
-        s_E[c] = acc;  // s_E[0] = S, s_E[1+i] = E[i]
-    }
-    __syncthreads();
-    if (shard_out) {
-        if (tid == 0) shard_out[0] = m;
-        for (int c = tid; c < mp.n_red + 1; c += blockDim.x) shard_out[1 + c] = s_E[c];
-        return;
-    }
-    const float invS = 1.0f / s_E[0];
-    for (int t = tid; t < mp.T; t += blockDim.x) {
-        float delta;
-        if (direct_noise) {
-            delta = s_E[1 + t] * invS;
-        } else {
-            const int i = t / mp.p, j = t - i * mp.p;
-            if (i == mp.n_ind - 1) {  // last interpolation row: weight 1/p (Interpolator.py:73-74)
-                delta = mp.sigma * (s_E[1 + i] * mp.inv_p) * invS;
-            } else {
-                const float w1 = (float)j / (float)mp.p, w0 = (float)(mp.p - j) / (float)mp.p;
-                delta = mp.sigma * fmaf(s_E[1 + i], w0, s_E[2 + i] * w1) * invS;
-            }
-        }
-        const float un = clampf(s_unom[t] + delta, mp.lo, mp.hi);
-        u_nom[t] = un;
-        if (t == 0) *u_out = un;
-    }
-}
+#include "cps_internal.cuh"
 
 // =====================================================================================================
 // K1 + K2: the MPPI solve
@@ -330,53 +216,7 @@ __global__ void __launch_bounds__(256) terminal_cost_kernel(CostParams C, const 
 // =====================================================================================================
 // host side
 // =====================================================================================================
-struct cps_handle {
-    cps_config cfg;
-    int n_ind, n_red;
-    float phys[CPS_PH_COUNT];
-    float cost_in[24];
-    int cost_in_n;
-    float mppi_in[7];  // cc_weight, R, LBD, NU, sigma, lo, hi
-    float target_position, target_equilibrium, L_var, m_pole_var;
-    OdeParams ode;
-    CostParams cost;
-    MppiParams mp;
-    cudaStream_t stream;
-    // scratch owned by the handle
-    float *d_partials;
-    unsigned *d_ticket;
-    int *d_nonfinite;
-    float *d_s, *d_unom, *d_u;
-    float *h_pin;  // pinned: [0..6) s, [8] u
-    int grid, block;
-    size_t smem;
-    int shard;
-    float *shard_out;
-    // growable buffers of cps_rollout_host
-    float *d_rs0, *d_rQ, *d_rtraj, *d_rfinal;
-    size_t cap_rs0, cap_rQ, cap_rtraj, cap_rfinal;
-    long long launches;
-    std::string err;
-};
-
-static thread_local std::string g_create_err;
-
-static int fail(cps_handle *h, int code, const char *fmt, ...) {
-    char buf[512];
-    va_list ap;
-    va_start(ap, fmt);
-    vsnprintf(buf, sizeof(buf), fmt, ap);
-    va_end(ap);
-    if (h) h->err = buf;
-    else g_create_err = buf;
-    return code;
-}
-
-#define CUDA_TRY(h, expr)                                                                          \
-    do {                                                                                           \
-        cudaError_t e_ = (expr);                                                                   \
-        if (e_ != cudaSuccess) return fail(h, CPS_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e_)); \
-    } while (0)
+thread_local std::string g_create_err;
 
 static void fold_ode(cps_handle *h) {
     const double k = h->phys[CPS_PH_K], mc = h->phys[CPS_PH_M_CART], g = h->phys[CPS_PH_G];
@@ -496,7 +336,7 @@ extern "C" int cps_create(const cps_config *cfg, cps_handle **out) {
                     (int)sizeof(cps_config));
     if (cfg->num_rollouts < 1 || cfg->horizon < 1 || cfg->substeps < 1 || !(cfg->dt > 0.0f) || cfg->interp_period < 1)
         return fail(nullptr, CPS_ERR_INVALID, "cps_create: K, T, n, dt and period must be positive");
-    if (cfg->integrator != CPS_EULER_V0 && cfg->integrator != CPS_EULER_CROMER)
+    if (cfg->integrator != CPS_EULER_V0 && cfg->integrator != CPS_EULER_CROMER && cfg->integrator != CPS_PREDICTOR_NEURAL)
         return fail(nullptr, CPS_ERR_UNSUPPORTED, "cps_create: unknown integrator %d", cfg->integrator);
     if (cfg->cost_id < CPS_COST_NONE || cfg->cost_id > CPS_COST_QB_GRAD)
         return fail(nullptr, CPS_ERR_UNSUPPORTED, "cps_create: unknown cost id %d", cfg->cost_id);
@@ -547,6 +387,7 @@ extern "C" int cps_create(const cps_config *cfg, cps_handle **out) {
     // the SMs; large K -> 128-thread blocks
     const int K = cfg->num_rollouts;
     h->block = (K <= 148 * 32 * 4) ? 32 : (K <= 148 * 64 * 8 ? 64 : 128);
+    if (cfg->integrator == CPS_PREDICTOR_NEURAL) h->block = 16;  // rollouts per CTA of net_kernel (cps_net.cu)
     h->grid = (K + h->block - 1) / h->block;
     const int nwarps = h->block / 32;
     h->smem = sizeof(float) * ((size_t)cfg->horizon + 2 * (size_t)cfg->interp_period
@@ -585,6 +426,7 @@ extern "C" int cps_create(const cps_config *cfg, cps_handle **out) {
 extern "C" void cps_destroy(cps_handle *h) {
     if (!h) return;
     cudaSetDevice(h->cfg.device);
+    cps_net_free(h);
     cudaFree(h->d_partials); cudaFree(h->d_ticket); cudaFree(h->d_nonfinite);
     cudaFree(h->d_s); cudaFree(h->d_unom); cudaFree(h->d_u);
     cudaFree(h->d_rs0); cudaFree(h->d_rQ); cudaFree(h->d_rtraj); cudaFree(h->d_rfinal);
@@ -726,6 +568,9 @@ extern "C" int cps_mppi_step(cps_handle *h, const float *s_dev, const float *noi
     if (!s_dev || !noise_dev || !u_nom_dev || !u_out_dev) return fail(h, CPS_ERR_INVALID, "cps_mppi_step: null pointer");
     if (h->shard && !h->shard_out) return fail(h, CPS_ERR_INVALID, "cps_mppi_step: shard mode without an output buffer");
     CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    if (h->cfg.integrator == CPS_PREDICTOR_NEURAL)
+        return cps_net_mppi_step(h, s_dev, noise_dev, noise_layout, u_prev, u_nom_dev, u_out_dev, J_out_dev, traj_out_dev,
+                                 traj_layout, u_run_out_dev);
     MppiArgs a;
     a.ode = h->ode; a.cost = h->cost; a.mp = h->mp;
     a.s = s_dev; a.noise = noise_dev;
@@ -850,6 +695,10 @@ extern "C" int cps_rollout(cps_handle *h, const float *s0_dev, int s0_batched, c
     if (!s0_dev || !Q_dev) return fail(h, CPS_ERR_INVALID, "cps_rollout: null input pointer");
     if (!traj_out_dev && !final_out_dev) return fail(h, CPS_ERR_INVALID, "cps_rollout: no output requested");
     CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    if (h->cfg.integrator == CPS_PREDICTOR_NEURAL) {
+        if (final_out_dev) return fail(h, CPS_ERR_UNSUPPORTED, "cps_rollout: final_out is not available with the neural predictor");
+        return cps_net_rollout(h, s0_dev, s0_batched, Q_dev, q_layout, B, T, nullptr, 0, traj_out_dev, traj_layout, nullptr);
+    }
     return rollout_launch(h, s0_dev, s0_batched, Q_dev, q_layout, B, T, traj_out_dev, traj_layout, final_out_dev);
 }
 
@@ -869,6 +718,8 @@ extern "C" int cps_rollout_host(cps_handle *h, const float *s0_host, int s0_batc
     if (B == 0) return CPS_OK;
     if (!s0_host || !Q_host) return fail(h, CPS_ERR_INVALID, "cps_rollout_host: null input pointer");
     if (!traj_out_host && !final_out_host) return fail(h, CPS_ERR_INVALID, "cps_rollout_host: no output requested");
+    if (h->cfg.integrator == CPS_PREDICTOR_NEURAL && final_out_host)
+        return fail(h, CPS_ERR_UNSUPPORTED, "cps_rollout_host: final_out is not available with the neural predictor");
     CUDA_TRY(h, cudaSetDevice(h->cfg.device));
     const size_t n_s0 = sizeof(float) * 6 * (s0_batched ? (size_t)B : 1), n_Q = sizeof(float) * (size_t)B * T;
     const size_t n_traj = sizeof(float) * (size_t)B * (T + 1) * 6, n_fin = sizeof(float) * (size_t)B * 6;
@@ -879,8 +730,11 @@ extern "C" int cps_rollout_host(cps_handle *h, const float *s0_host, int s0_batc
     if (final_out_host && (rc = grow(h, &h->d_rfinal, &h->cap_rfinal, n_fin)) != CPS_OK) return rc;
     CUDA_TRY(h, cudaMemcpyAsync(h->d_rs0, s0_host, n_s0, cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(h, cudaMemcpyAsync(h->d_rQ, Q_host, n_Q, cudaMemcpyHostToDevice, h->stream));
-    rc = rollout_launch(h, h->d_rs0, s0_batched, h->d_rQ, q_layout, B, T, traj_out_host ? h->d_rtraj : nullptr,
-                        traj_layout, final_out_host ? h->d_rfinal : nullptr);
+    if (h->cfg.integrator == CPS_PREDICTOR_NEURAL)
+        rc = cps_net_rollout(h, h->d_rs0, s0_batched, h->d_rQ, q_layout, B, T, nullptr, 0, h->d_rtraj, traj_layout, nullptr);
+    else
+        rc = rollout_launch(h, h->d_rs0, s0_batched, h->d_rQ, q_layout, B, T, traj_out_host ? h->d_rtraj : nullptr,
+                            traj_layout, final_out_host ? h->d_rfinal : nullptr);
     if (rc != CPS_OK) return rc;
     if (traj_out_host) CUDA_TRY(h, cudaMemcpyAsync(traj_out_host, h->d_rtraj, n_traj, cudaMemcpyDeviceToHost, h->stream));
     if (final_out_host) CUDA_TRY(h, cudaMemcpyAsync(final_out_host, h->d_rfinal, n_fin, cudaMemcpyDeviceToHost, h->stream));

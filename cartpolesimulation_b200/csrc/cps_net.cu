@@ -1,0 +1,720 @@
+// cps_net.cu -- autoregressive neural predictor (GRU / Dense) of libcps_b200.so, FP32 CUDA-core path.
+//
+// Reference: SI_Toolkit/src/SI_Toolkit/Predictors/predictor_autoregressive_neural.py:266-313 (_predict_core),
+// :332-352 (_update_internal_state_tf); Functions/Pytorch/Network.py:239-287 (Sequence.forward, GRUCell / Linear
+// stack); Predictors/autoregression.py:33-158 (feedback loop, differential variant);
+// Functions/General/Normalising.py:15-186; ToolkitCustomization/predictors_customization.py:71-139 (augmentation).
+//
+// net_kernel<R, COST, MPPI>: one CTA advances a tile of R rollouts through the whole horizon.
+//   * all weights live in shared memory for the whole launch (2x64 GRU: 156 KB), fetched once with one bulk
+//     asynchronous copy (cp.async.bulk + mbarrier);
+//   * 4 compute warps: thread (row group g, unit j) keeps the gate pre-activations of RT = 8 rollouts for one hidden
+//     unit in registers; weights are read conflict-free ([in][3H] layout, consecutive lanes = consecutive units),
+//     activations as broadcast float4 ([unit][R] layout) -> 24 FMAs per 5 shared-memory loads;
+//   * 1 "row" warp (lane = rollout) trails the compute warps by one network step: de-normalisation, angle
+//     augmentation, trajectory store, stage / terminal cost, MPPI perturbation interpolation and the next control,
+//     overlapped with the next step's layer-1 products;
+//   * MPPI = true additionally does what mppi_kernel does after the rollout (block partials, last-block merge,
+//     clipped u_nom / u) and then advances the stored hidden state by one step on (u, s)
+//     (optimizer_mppi.py:191,194-196) -- one launch per solve.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "cps_internal.cuh"
+
+#define NET_NC 128          // compute threads
+#define NET_NT (NET_NC + 32)  // + the row warp
+#define NET_RT 8            // rollouts per compute thread
+
+struct NetDev {
+    int type, n_layers, n_in, n_state_in, n_out, htot, n_weights;
+    int hsz[CPS_NET_MAX_LAYERS];
+    int hoff[CPS_NET_MAX_LAYERS];   // offset of layer l inside the concatenated hidden state
+    int in_idx[6], out_idx[6];
+    float norm_a[7], norm_b[7], denorm_A[6], denorm_B[6];
+    int differential;
+    float p1[6], p2[6], on_a[6], on_b[6];
+    int out_to_in[6];
+    int has_angle, has_sin, has_cos;   // which of these the network outputs (the others are augmented)
+    // offsets (in floats) into the device weight buffer
+    int off_wih[CPS_NET_MAX_LAYERS], off_whh[CPS_NET_MAX_LAYERS], off_bih[CPS_NET_MAX_LAYERS], off_bhh[CPS_NET_MAX_LAYERS];
+    int off_wout, off_bout;
+};
+
+struct NetState {
+    NetDev dev;
+    float *d_weights;   // device layout: per layer W_ih^T [in][G*H], W_hh^T [H][3H], b_ih, b_hh; W_out^T [H][n_out], b_out
+    float *d_href;      // stored hidden state [htot] (memory_states_ref; rows are identical across the batch)
+    size_t smem_weights;  // bytes of the weight image
+    bool weights_in_smem;
+};
+
+struct NetArgs {
+    NetDev net;
+    const float *weights;
+    const float *s0;
+    long long ss_b;
+    const float *Q;           // plain rollouts: controls
+    long long qs_b, qs_t;
+    int B, T;
+    const float *h0;
+    long long hs_b;           // 0: one shared hidden state, htot: per rollout
+    float *traj_out;
+    long long ts_k, ts_t, ts_c;
+    float *h_final;           // [B][htot] or null
+    // MPPI mode
+    CostParams cost;
+    MppiParams mp;
+    const float *noise;
+    long long ns_i, ns_k;
+    float u_prev;
+    float *u_nom, *u_out, *J_out, *u_run_out, *partials;
+    unsigned *ticket;
+    int *nonfinite;
+    float *shard_out;
+    float *h_ref;             // stored hidden state to advance after the solve (null: skip)
+};
+
+// ---- small device helpers ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+// 1 - 2/(1 + e^{2x}): absolute error ~1e-7, saturates correctly for large |x|
+__device__ __forceinline__ float tanh_f(float x) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x)); }
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+// acc[q][r] += sum_i Wt[i][q*H + j] * x[i][g*RT + r]
+template <int R, int NG>
+__device__ __forceinline__ void matvec_acc(const float *__restrict__ Wt, const float *__restrict__ x, int in_len, int H,
+                                           int j, int g, float (&acc)[NG][NET_RT]) {
+    const float *w = Wt + j;
+    const float *xv = x + g * NET_RT;
+    const int ws = NG * H;
+#pragma unroll 4
+    for (int i = 0; i < in_len; ++i) {
+        const float4 x0 = *reinterpret_cast<const float4 *>(xv + i * R);
+        const float4 x1 = *reinterpret_cast<const float4 *>(xv + i * R + 4);
+#pragma unroll
+        for (int q = 0; q < NG; ++q) {
+            const float wq = w[i * ws + q * H];
+            acc[q][0] = fmaf(wq, x0.x, acc[q][0]); acc[q][1] = fmaf(wq, x0.y, acc[q][1]);
+            acc[q][2] = fmaf(wq, x0.z, acc[q][2]); acc[q][3] = fmaf(wq, x0.w, acc[q][3]);
+            acc[q][4] = fmaf(wq, x1.x, acc[q][4]); acc[q][5] = fmaf(wq, x1.y, acc[q][5]);
+            acc[q][6] = fmaf(wq, x1.z, acc[q][6]); acc[q][7] = fmaf(wq, x1.w, acc[q][7]);
+        }
+    }
+}
+
+// torch.nn.GRUCell (gate order r, z, n): r = s(W_ir x + b_ir + W_hr h + b_hr), z likewise,
+// n = tanh(W_in x + b_in + r (W_hn h + b_hn)), h' = (h - n) z + n.
+template <int R>
+__device__ __forceinline__ void gru_layer(const NetDev &N, const float *W, int l, const float *xin, int in_len,
+                                          const float *hprev, float *hnew, int tid) {
+    const int H = N.hsz[l];
+    const float *Wih = W + N.off_wih[l], *Whh = W + N.off_whh[l], *bih = W + N.off_bih[l], *bhh = W + N.off_bhh[l];
+    for (int item = tid; item < (R / NET_RT) * H; item += NET_NC) {
+        const int j = item % H, g = item / H;
+        float ai[3][NET_RT], ah[3][NET_RT];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            const float bi = bih[q * H + j], bh = bhh[q * H + j];
+#pragma unroll
+            for (int r = 0; r < NET_RT; ++r) { ai[q][r] = (q < 2) ? bi + bh : bi; ah[q][r] = (q < 2) ? 0.0f : bh; }
+        }
+        matvec_acc<R, 3>(Wih, xin, in_len, H, j, g, ai);
+        // r and z accumulate both products in one register set; the n gate keeps them apart
+        {
+            const float *w = Whh + j;
+            const float *xv = hprev + g * NET_RT;
+#pragma unroll 4
+            for (int i = 0; i < H; ++i) {
+                const float4 x0 = *reinterpret_cast<const float4 *>(xv + i * R);
+                const float4 x1 = *reinterpret_cast<const float4 *>(xv + i * R + 4);
+                const float xr[NET_RT] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+                const float wr = w[i * 3 * H], wz = w[i * 3 * H + H], wn = w[i * 3 * H + 2 * H];
+#pragma unroll
+                for (int r = 0; r < NET_RT; ++r) {
+                    ai[0][r] = fmaf(wr, xr[r], ai[0][r]);
+                    ai[1][r] = fmaf(wz, xr[r], ai[1][r]);
+                    ah[2][r] = fmaf(wn, xr[r], ah[2][r]);
+                }
+            }
+        }
+        const float *ho = hprev + j * R + g * NET_RT;
+        float *hn = hnew + j * R + g * NET_RT;
+        float out[NET_RT];
+#pragma unroll
+        for (int r = 0; r < NET_RT; ++r) {
+            const float rr = sigmoid_f(ai[0][r]);
+            const float zz = sigmoid_f(ai[1][r]);
+            const float nn = tanh_f(fmaf(rr, ah[2][r], ai[2][r]));
+            out[r] = fmaf(ho[r] - nn, zz, nn);
+        }
+        *reinterpret_cast<float4 *>(hn) = make_float4(out[0], out[1], out[2], out[3]);
+        *reinterpret_cast<float4 *>(hn + 4) = make_float4(out[4], out[5], out[6], out[7]);
+    }
+}
+
+// Dense layer: a = tanh(W x + b) (Functions/Pytorch/Network.py:255-260)
+template <int R>
+__device__ __forceinline__ void dense_layer(const NetDev &N, const float *W, int l, const float *xin, int in_len,
+                                            float *act, int tid) {
+    const int H = N.hsz[l];
+    const float *Wt = W + N.off_wih[l], *b = W + N.off_bih[l];
+    for (int item = tid; item < (R / NET_RT) * H; item += NET_NC) {
+        const int j = item % H, g = item / H;
+        float a[1][NET_RT];
+#pragma unroll
+        for (int r = 0; r < NET_RT; ++r) a[0][r] = b[j];
+        matvec_acc<R, 1>(Wt, xin, in_len, H, j, g, a);
+        float *o = act + j * R + g * NET_RT;
+#pragma unroll
+        for (int r = 0; r < NET_RT; ++r) o[r] = tanh_f(a[0][r]);
+    }
+}
+
+// Linear output layer + feedback: y = W_out h + b_out; next net input = y (or the integrated state, differential nets)
+template <int R>
+__device__ __forceinline__ void out_layer(const NetDev &N, const float *W, const float *hlast, float *ybuf, float *snorm,
+                                          float *xnext, int tid) {
+    const int H = N.hsz[N.n_layers - 1];
+    const float *Wo = W + N.off_wout, *bo = W + N.off_bout;
+    for (int item = tid; item < R * N.n_out; item += NET_NC) {
+        const int r = item % R, o = item / R;
+        float y0 = bo[o], y1 = 0.0f;
+        int j = 0;
+        for (; j + 1 < H; j += 2) {
+            y0 = fmaf(Wo[j * N.n_out + o], hlast[j * R + r], y0);
+            y1 = fmaf(Wo[(j + 1) * N.n_out + o], hlast[(j + 1) * R + r], y1);
+        }
+        if (j < H) y0 = fmaf(Wo[j * N.n_out + o], hlast[j * R + r], y0);
+        float y = y0 + y1;
+        if (N.differential) {  // autoregression.py:149-154
+            y = snorm[o * R + r] + fmaf(N.p1[o], y, N.p2[o]);
+            snorm[o * R + r] = y;
+            for (int i = 0; i < N.n_state_in; ++i)
+                if (N.out_to_in[i] == o) xnext[(1 + i) * R + r] = y;
+        } else if (o < N.n_state_in) {
+            xnext[(1 + o) * R + r] = y;  // autoregression.py:94-98: the output is the next input
+        }
+        ybuf[o * R + r] = y;
+    }
+}
+
+// de-normalise, scatter into the 6-vector state, augment (predictors_customization.py:120-139)
+template <int R>
+__device__ __forceinline__ void compose_state(const NetDev &N, const float *ybuf, int r, float (&st)[6]) {
+#pragma unroll
+    for (int c = 0; c < 6; ++c) st[c] = 0.0f;
+    for (int o = 0; o < N.n_out; ++o) {
+        const float v = fmaf(N.denorm_A[o], ybuf[o * R + r], N.denorm_B[o]);
+        const int c = N.out_idx[o];
+#pragma unroll
+        for (int cc = 0; cc < 6; ++cc)
+            if (cc == c) st[cc] = v;
+    }
+    if (!N.has_angle && N.has_sin && N.has_cos) st[IDX_ANGLE] = atan2f(st[IDX_SIN], st[IDX_COS]);
+    if (N.has_angle && !N.has_sin) st[IDX_SIN] = sinf(st[IDX_ANGLE]);
+    if (N.has_angle && !N.has_cos) st[IDX_COS] = cosf(st[IDX_ANGLE]);
+}
+
+template <int R, int COST, bool MPPI>
+__global__ void __launch_bounds__(NET_NT, 1) net_kernel(const __grid_constant__ NetArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    __shared__ __align__(8) unsigned long long s_bar;
+    __shared__ unsigned s_ticket;
+    const NetDev &N = a.net;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const bool row_warp = tid >= NET_NC;
+    const int T = a.T;
+    const int row0 = blockIdx.x * R;
+
+    // ---- shared-memory carve-up ------------------------------------------------------------------------------
+    float *wsm = smem;                              // [n_weights]
+    float *hb = wsm + N.n_weights;                  // GRU: [2][htot][R]; Dense: [htot][R] activations
+    const int hstride = N.htot * R;
+    float *xin = hb + 2 * hstride;                  // [2][n_in][R]
+    float *ybuf = xin + 2 * N.n_in * R;             // [n_out][R]
+    float *snorm = ybuf + 8 * R;                    // [n_out][R] (differential nets)
+    float *s_unom = snorm + 8 * R;                  // MPPI: [T] shifted nominal inputs, then [p] w0, [p] w1, scratch
+    float *s_w0 = s_unom + (MPPI ? a.mp.T : 0);
+    float *s_w1 = s_w0 + (MPPI ? a.mp.p : 0);
+    float *s_red = s_w1 + (MPPI ? a.mp.p : 0);      // [n_red + 2]
+
+    // ---- weights: one bulk asynchronous copy global -> shared ---------------------------------------------------
+    if (tid == 0) {
+        const unsigned bar = smem_u32(&s_bar);
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const unsigned bytes = (unsigned)N.n_weights * 4u;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        unsigned done = 0;
+        while (done < bytes) {
+            const unsigned chunk = min(bytes - done, 32768u);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(smem_u32(wsm) + done), "l"(reinterpret_cast<const char *>(a.weights) + done), "r"(chunk),
+                         "r"(bar) : "memory");
+            done += chunk;
+        }
+    }
+
+    // ---- prologue: hidden state, first network input --------------------------------------------------------------
+    if (N.type == CPS_NET_GRU) {
+        for (int idx = tid; idx < N.htot * R; idx += NET_NT) {
+            const int j = idx / R, r = idx % R;
+            const int b = min(row0 + r, a.B - 1);
+            hb[idx] = a.h0[(long long)b * a.hs_b + j];
+        }
+    }
+    if (MPPI) {
+        // warm-start shift at the START of the solve (optimizer_mppi.py:183)
+        for (int t = tid; t < T; t += NET_NT) s_unom[t] = a.u_nom[min(t + 1, T - 1)];
+        for (int j = tid; j < a.mp.p; j += NET_NT) {
+            s_w0[j] = (float)(a.mp.p - j) / (float)a.mp.p;
+            s_w1[j] = (float)j / (float)a.mp.p;
+        }
+    }
+    for (int idx = tid; idx < N.n_state_in * R; idx += NET_NT) {
+        const int i = idx / R, r = idx % R;
+        const int b = min(row0 + r, a.B - 1);
+        xin[(1 + i) * R + r] = fmaf(N.norm_a[1 + i], a.s0[(long long)b * a.ss_b + N.in_idx[i]], N.norm_b[1 + i]);
+    }
+    if (N.differential) {  // dmah.set_starting_point (autoregression.py:145-146)
+        for (int idx = tid; idx < N.n_out * R; idx += NET_NT) {
+            const int o = idx / R, r = idx % R;
+            const int b = min(row0 + r, a.B - 1);
+            snorm[idx] = fmaf(N.on_a[o], a.s0[(long long)b * a.ss_b + N.out_idx[o]], N.on_b[o]);
+        }
+    }
+    __syncthreads();  // also publishes the mbarrier init
+
+    // ---- row-warp state --------------------------------------------------------------------------------------
+    const int r_row = lane;                        // rollout handled by this lane of the row warp
+    const bool row_valid = row_warp && r_row < R;
+    const int k = row0 + r_row;
+    const bool active = row_valid && k < a.B;
+    const int kc = min(k, a.B - 1);
+    float Jacc = 0.0f, corr = 0.0f, up = a.u_prev, u_cur = 0.0f, du_cur = 0.0f;
+    int seg = 0, jj = 0;
+    float na = 0.0f, nb = 0.0f;
+    const float *nz = nullptr;
+    const float *qrow = nullptr;
+    float *traj = nullptr;
+    if (row_warp) {
+        traj = (a.traj_out && active) ? a.traj_out + (long long)k * a.ts_k : nullptr;
+        if (MPPI) {
+            nz = a.noise + (long long)kc * a.ns_k;
+            na = nz[0] * a.mp.sigma;
+            nb = (a.mp.n_ind > 1) ? nz[a.ns_i] * a.mp.sigma : 0.0f;
+        } else {
+            qrow = a.Q + (long long)kc * a.qs_b;
+        }
+    }
+    // control of step t (row warp): MPPI: clip(u_nom[t] + delta_u[t]) with delta_u interpolated from the inducing
+    // points (Interpolator.py:53-77); else Q[k][t]
+    auto next_control = [&](int t) {
+        if (MPPI) {
+            const MppiParams &mp = a.mp;
+            du_cur = (seg == mp.n_ind - 1) ? na * mp.inv_p : fmaf(na, s_w0[jj], nb * s_w1[jj]);
+            if (++jj == mp.p) {
+                jj = 0; ++seg; na = nb;
+                nb = (seg + 1 < mp.n_ind) ? nz[(long long)(seg + 1) * a.ns_i] * mp.sigma : 0.0f;
+            }
+            u_cur = clampf(s_unom[t] + du_cur, mp.lo, mp.hi);
+        } else {
+            u_cur = qrow[(long long)t * a.qs_t];
+        }
+    };
+    if (row_valid) {
+        next_control(0);
+        xin[r_row] = fmaf(N.norm_a[0], u_cur, N.norm_b[0]);
+    }
+    // all threads: wait for the weights
+    {
+        const unsigned bar = smem_u32(&s_bar);
+        unsigned ok = 0;
+        while (!ok) {
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(ok) : "r"(bar) : "memory");
+        }
+    }
+    __syncthreads();
+
+    // ---- the horizon ------------------------------------------------------------------------------------------
+    int p = 0;  // hidden-state buffer holding h(t-1)
+    float st[6];
+#pragma unroll 1
+    for (int t = 0; t < T; ++t) {
+        float *x_cur = xin + (t & 1) * N.n_in * R;
+        float *x_nxt = xin + ((t + 1) & 1) * N.n_in * R;
+        if (row_warp) {
+            if (row_valid) {
+                // state s_t: the initial state, or the previous step's network output
+                if (t == 0) {
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) st[c] = a.s0[(long long)kc * a.ss_b + c];
+                } else {
+                    compose_state<R>(N, ybuf, r_row, st);
+                }
+                if (traj) {
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) traj[(long long)t * a.ts_t + c * a.ts_c] = st[c];
+                }
+                if (MPPI) {
+                    if (COST != COST_NONE) {
+                        float sc = stage_cost<COST>(a.cost, cosf(st[IDX_ANGLE]), st[IDX_ANGLED], st[IDX_POS], u_cur, up);
+                        if (COST == COST_DEFAULT || COST == COST_QB) sc -= a.cost.max_cost;
+                        Jacc += sc;
+                    }
+                    corr = fmaf(a.mp.cc_half_nu * du_cur, du_cur,
+                                fmaf(a.mp.cc_R * u_cur, du_cur, fmaf(a.mp.cc_half_R * u_cur, u_cur, corr)));
+                    if (a.u_run_out && active) a.u_run_out[(long long)k * T + t] = u_cur;
+                    up = u_cur;
+                }
+                if (t + 1 < T) {
+                    next_control(t + 1);
+                    x_nxt[r_row] = fmaf(N.norm_a[0], u_cur, N.norm_b[0]);
+                }
+            }
+            __syncthreads();
+            for (int l = 1; l < N.n_layers; ++l) __syncthreads();
+            __syncthreads();
+        } else {
+            const float *in = x_cur;
+            int in_len = N.n_in;
+            for (int l = 0; l < N.n_layers; ++l) {
+                float *hl = hb + N.hoff[l] * R;
+                if (N.type == CPS_NET_GRU) {
+                    gru_layer<R>(N, wsm, l, in, in_len, hl + p * hstride, hl + (1 - p) * hstride, tid);
+                    in = hl + (1 - p) * hstride;
+                } else {
+                    dense_layer<R>(N, wsm, l, in, in_len, hl, tid);
+                    in = hl;
+                }
+                in_len = N.hsz[l];
+                __syncthreads();
+            }
+            out_layer<R>(N, wsm, in, ybuf, snorm, x_nxt, tid);
+            __syncthreads();
+        }
+        p ^= 1;
+    }
+
+    // ---- last state, costs, hidden state out ---------------------------------------------------------------------
+    float J = 0.0f;
+    if (row_valid) {
+        compose_state<R>(N, ybuf, r_row, st);
+        if (traj) {
+#pragma unroll
+            for (int c = 0; c < 6; ++c) traj[(long long)T * a.ts_t + c * a.ts_c] = st[c];
+        }
+        if (MPPI) {
+            if (COST != COST_NONE) Jacc += terminal_cost<COST>(a.cost, st[IDX_ANGLE], st[IDX_POS]);
+            J = fmaf(Jacc, a.mp.inv_T1, corr);
+            if (active) {
+                if (a.J_out) a.J_out[k] = J;
+                if (!isfinite(J)) atomicAdd(a.nonfinite, 1);
+            }
+        }
+    }
+    if (a.h_final && N.type == CPS_NET_GRU) {
+        for (int idx = tid; idx < N.htot * R; idx += NET_NT) {
+            const int j = idx / R, r = idx % R;
+            if (row0 + r < a.B) a.h_final[(long long)(row0 + r) * N.htot + j] = hb[p * hstride + idx];
+        }
+    }
+    if (!MPPI) return;
+
+    // ---- MPPI: block partial (row warp), last block merges and finishes -------------------------------------------
+    const MppiParams &mp = a.mp;
+    const int rec = 2 + mp.n_red;
+    if (row_warp) {
+        const float m = warp_min(active ? J : INFINITY);
+        const float wgt = active ? expf(-(J - m) * mp.inv_lambda) : 0.0f;
+        float *part = a.partials + (size_t)blockIdx.x * rec;
+        const float S = warp_sum(wgt);
+        if (lane == 0) { part[0] = m; part[1] = S; }
+        for (int i = 0; i < mp.n_red; ++i) {
+            const float e = active ? nz[(long long)i * a.ns_i] : 0.0f;
+            const float v = warp_sum(wgt * e);
+            if (lane == 0) part[2 + i] = v;
+        }
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_ticket = atomicAdd(a.ticket, 1u);
+    __syncthreads();
+    if (s_ticket != gridDim.x - 1) return;
+    __threadfence();
+    merge_and_finish(mp, a.partials, gridDim.x, s_red, s_unom, a.u_nom, a.u_out, a.shard_out, false);
+    if (tid == 0) *a.ticket = 0u;
+    if (a.shard_out || !a.h_ref || N.type != CPS_NET_GRU) return;
+
+    // ---- advance the stored hidden state by one step on (u, s) (optimizer_mppi.py:191,194-196) --------------------
+    __syncthreads();
+    const float u_sel = __ldcg(a.u_out);
+    for (int idx = tid; idx < N.htot * R; idx += NET_NT) hb[idx] = a.h_ref[idx / R];
+    for (int idx = tid; idx < N.n_in * R; idx += NET_NT) {
+        const int i = idx / R;
+        const float v = (i == 0) ? u_sel : a.s0[N.in_idx[i - 1]];
+        xin[idx] = fmaf(N.norm_a[i], v, N.norm_b[i]);
+    }
+    __syncthreads();
+    {
+        const float *in = xin;
+        int in_len = N.n_in;
+        for (int l = 0; l < N.n_layers; ++l) {
+            float *hl = hb + N.hoff[l] * R;
+            if (!row_warp) gru_layer<R>(N, wsm, l, in, in_len, hl, hl + hstride, tid);
+            in = hl + hstride;
+            in_len = N.hsz[l];
+            __syncthreads();
+        }
+    }
+    for (int j = tid; j < N.htot; j += NET_NT) a.h_ref[j] = hb[hstride + j * R];
+}
+
+// =====================================================================================================
+// host side
+// =====================================================================================================
+static size_t net_smem_bytes(const NetDev &N, int R, bool mppi, const MppiParams *mp) {
+    size_t f = (size_t)N.n_weights + 2 * (size_t)N.htot * R + 2 * (size_t)N.n_in * R + 16 * (size_t)R;
+    if (mppi) f += (size_t)mp->T + 2 * (size_t)mp->p + (size_t)mp->n_red + 4;
+    return f * sizeof(float);
+}
+
+typedef void (*net_fn)(const NetArgs);
+
+static net_fn pick_net(int cost, bool mppi) {
+    if (!mppi) return net_kernel<16, COST_NONE, false>;
+    switch (cost) {
+    case CPS_COST_DEFAULT: return net_kernel<16, COST_DEFAULT, true>;
+    case CPS_COST_QUADRATIC_BOUNDARY: return net_kernel<16, COST_QB, true>;
+    case CPS_COST_QB_GRAD_MINIMAL: return net_kernel<16, COST_GRADMIN, true>;
+    case CPS_COST_QB_GRAD: return net_kernel<16, COST_GRAD, true>;
+    default: return net_kernel<16, COST_NONE, true>;
+    }
+}
+
+void cps_net_free(cps_handle *h) {
+    if (!h || !h->net) return;
+    cudaFree(h->net->d_weights);
+    cudaFree(h->net->d_href);
+    delete h->net;
+    h->net = nullptr;
+}
+
+extern "C" int cps_net_load(cps_handle *h, const cps_net_desc *d, const float *w, long long n_weights) {
+    if (!h) return CPS_ERR_INVALID;
+    if (!d || !w) return fail(h, CPS_ERR_INVALID, "cps_net_load: null argument");
+    if (d->struct_size != (int)sizeof(cps_net_desc))
+        return fail(h, CPS_ERR_INVALID, "cps_net_load: cps_net_desc size mismatch (%d vs %d)", d->struct_size,
+                    (int)sizeof(cps_net_desc));
+    if (d->net_type != CPS_NET_GRU && d->net_type != CPS_NET_DENSE)
+        return fail(h, CPS_ERR_UNSUPPORTED, "cps_net_load: network type %d is not supported (GRU and Dense are)", d->net_type);
+    if (d->n_layers < 1 || d->n_layers > CPS_NET_MAX_LAYERS)
+        return fail(h, CPS_ERR_UNSUPPORTED, "cps_net_load: 1..%d hidden layers supported", CPS_NET_MAX_LAYERS);
+    if (d->n_state_in < 0 || d->n_state_in > 6 || d->n_out < 1 || d->n_out > 6)
+        return fail(h, CPS_ERR_INVALID, "cps_net_load: need 0..6 state inputs and 1..6 outputs");
+    if (!d->differential && d->n_state_in > d->n_out)
+        return fail(h, CPS_ERR_INVALID, "cps_net_load: the outputs feed back as the next inputs, so n_out >= n_state_in is required");
+    NetDev N;
+    memset(&N, 0, sizeof(N));
+    N.type = d->net_type; N.n_layers = d->n_layers; N.n_state_in = d->n_state_in; N.n_in = 1 + d->n_state_in;
+    N.n_out = d->n_out; N.differential = d->differential ? 1 : 0;
+    for (int i = 0; i < d->n_state_in; ++i) {
+        if (d->in_idx[i] < 0 || d->in_idx[i] > 5) return fail(h, CPS_ERR_INVALID, "cps_net_load: in_idx out of range");
+        N.in_idx[i] = d->in_idx[i];
+        if (d->differential && (d->out_to_in[i] < 0 || d->out_to_in[i] >= d->n_out))
+            return fail(h, CPS_ERR_INVALID, "cps_net_load: out_to_in out of range");
+        N.out_to_in[i] = d->out_to_in[i];
+    }
+    for (int o = 0; o < d->n_out; ++o) {
+        if (d->out_idx[o] < 0 || d->out_idx[o] > 5) return fail(h, CPS_ERR_INVALID, "cps_net_load: out_idx out of range");
+        N.out_idx[o] = d->out_idx[o];
+        if (d->out_idx[o] == IDX_ANGLE) N.has_angle = 1;
+        if (d->out_idx[o] == IDX_SIN) N.has_sin = 1;
+        if (d->out_idx[o] == IDX_COS) N.has_cos = 1;
+        N.denorm_A[o] = d->denorm_A[o]; N.denorm_B[o] = d->denorm_B[o];
+        N.p1[o] = d->diff_p1[o]; N.p2[o] = d->diff_p2[o]; N.on_a[o] = d->out_norm_a[o]; N.on_b[o] = d->out_norm_b[o];
+    }
+    for (int i = 0; i < N.n_in; ++i) { N.norm_a[i] = d->norm_a[i]; N.norm_b[i] = d->norm_b[i]; }
+    // device image: transposed weights, every block 16-byte aligned
+    const int G = (N.type == CPS_NET_GRU) ? 3 : 1;
+    std::vector<float> img;
+    auto align4 = [&]() { while (img.size() % 4) img.push_back(0.0f); };
+    long long need = 0;
+    int in_len = N.n_in, htot = 0;
+    for (int l = 0; l < N.n_layers; ++l) {
+        const int H = d->hidden[l];
+        if (H < 1 || H > 128) return fail(h, CPS_ERR_UNSUPPORTED, "cps_net_load: hidden sizes 1..128 supported, got %d", H);
+        need += (long long)G * H * in_len + (N.type == CPS_NET_GRU ? 3LL * H * H + 6LL * H : H);
+        in_len = H;
+    }
+    need += (long long)N.n_out * in_len + N.n_out;
+    if (need != n_weights)
+        return fail(h, CPS_ERR_INVALID, "cps_net_load: expected %lld weights for this architecture, got %lld", need, n_weights);
+    for (long long i = 0; i < n_weights; ++i)
+        if (!std::isfinite(w[i])) return fail(h, CPS_ERR_INVALID, "cps_net_load: weight %lld is not finite", i);
+    const float *p = w;
+    in_len = N.n_in;
+    auto put_T = [&](const float *src, int rows, int cols) {  // src [rows][cols] -> image [cols][rows]
+        const int off = (int)img.size();
+        img.resize(off + (size_t)rows * cols);
+        for (int r = 0; r < rows; ++r)
+            for (int c = 0; c < cols; ++c) img[off + (size_t)c * rows + r] = src[(size_t)r * cols + c];
+        align4();
+        return off;
+    };
+    auto put = [&](const float *src, int n) {
+        const int off = (int)img.size();
+        img.insert(img.end(), src, src + n);
+        align4();
+        return off;
+    };
+    for (int l = 0; l < N.n_layers; ++l) {
+        const int H = d->hidden[l];
+        N.hsz[l] = H; N.hoff[l] = htot; htot += H;
+        N.off_wih[l] = put_T(p, G * H, in_len); p += (size_t)G * H * in_len;
+        if (N.type == CPS_NET_GRU) {
+            N.off_whh[l] = put_T(p, 3 * H, H); p += (size_t)3 * H * H;
+            N.off_bih[l] = put(p, 3 * H); p += 3 * H;
+            N.off_bhh[l] = put(p, 3 * H); p += 3 * H;
+        } else {
+            N.off_bih[l] = put(p, H); p += H;
+        }
+        in_len = H;
+    }
+    N.off_wout = put_T(p, N.n_out, in_len); p += (size_t)N.n_out * in_len;
+    N.off_bout = put(p, N.n_out);
+    N.htot = htot;
+    N.n_weights = (int)img.size();
+    const size_t smem = net_smem_bytes(N, 16, true, &h->mp);
+    if (smem > 227 * 1024)
+        return fail(h, CPS_ERR_UNSUPPORTED, "cps_net_load: the network needs %zu bytes of shared memory per CTA (limit 227 KB); "
+                    "larger networks are not supported by this build", smem);
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    cps_net_free(h);
+    NetState *S = new (std::nothrow) NetState();
+    if (!S) return fail(h, CPS_ERR_INVALID, "cps_net_load: out of host memory");
+    S->dev = N; S->d_weights = nullptr; S->d_href = nullptr; S->smem_weights = img.size() * sizeof(float);
+    S->weights_in_smem = true;
+    h->net = S;
+    CUDA_TRY(h, cudaMalloc(&S->d_weights, img.size() * sizeof(float)));
+    CUDA_TRY(h, cudaMalloc(&S->d_href, sizeof(float) * (size_t)(htot > 0 ? htot : 1)));
+    CUDA_TRY(h, cudaMemcpy(S->d_weights, img.data(), img.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CUDA_TRY(h, cudaMemset(S->d_href, 0, sizeof(float) * (size_t)(htot > 0 ? htot : 1)));
+    return CPS_OK;
+}
+
+static int net_launch(cps_handle *h, NetArgs &a, bool mppi, int n_rows) {
+    NetState *S = h->net;
+    a.net = S->dev;
+    a.weights = S->d_weights;
+    const int R = 16;
+    const size_t smem = net_smem_bytes(S->dev, R, mppi, &h->mp);
+    net_fn fn = pick_net(h->cfg.cost_id, mppi);
+    CUDA_TRY(h, cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = (n_rows + R - 1) / R;
+    fn<<<grid, NET_NT, smem, h->stream>>>(a);
+    h->launches += 1;
+    CUDA_TRY(h, cudaGetLastError());
+    return CPS_OK;
+}
+
+extern "C" int cps_net_rollout(cps_handle *h, const float *s0_dev, int s0_batched, const float *Q_dev, int q_layout, int B,
+                               int T, const float *h0_dev, int h0_batched, float *traj_out_dev, int traj_layout,
+                               float *h_final_dev) {
+    if (!h) return CPS_ERR_INVALID;
+    if (!h->net) return fail(h, CPS_ERR_NOT_CONFIGURED, "cps_net_rollout: no network loaded (cps_net_load)");
+    if (B < 0 || T < 1) return fail(h, CPS_ERR_INVALID, "cps_net_rollout: need B >= 0 and T >= 1");
+    if (B == 0) return CPS_OK;
+    if (!s0_dev || !Q_dev) return fail(h, CPS_ERR_INVALID, "cps_net_rollout: null input pointer");
+    if (!traj_out_dev && !h_final_dev) return fail(h, CPS_ERR_INVALID, "cps_net_rollout: no output requested");
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    NetArgs a;
+    memset(&a, 0, sizeof(a));
+    a.s0 = s0_dev; a.ss_b = s0_batched ? 6 : 0;
+    a.Q = Q_dev;
+    if (q_layout == CPS_TIME_MAJOR) { a.qs_b = 1; a.qs_t = B; } else { a.qs_b = T; a.qs_t = 1; }
+    a.B = B; a.T = T;
+    a.h0 = h0_dev ? h0_dev : h->net->d_href;
+    a.hs_b = (h0_dev && h0_batched) ? h->net->dev.htot : 0;
+    a.traj_out = traj_out_dev;
+    if (traj_layout == CPS_TIME_MAJOR) { a.ts_k = 1; a.ts_t = 6LL * B; a.ts_c = B; }
+    else { a.ts_k = (T + 1) * 6LL; a.ts_t = 6; a.ts_c = 1; }
+    a.h_final = h_final_dev;
+    return net_launch(h, a, false, B);
+}
+
+extern "C" int cps_net_update(cps_handle *h, const float *s_dev, const float *q0_dev) {
+    if (!h) return CPS_ERR_INVALID;
+    if (!h->net) return fail(h, CPS_ERR_NOT_CONFIGURED, "cps_net_update: no network loaded (cps_net_load)");
+    if (!s_dev || !q0_dev) return fail(h, CPS_ERR_INVALID, "cps_net_update: null pointer");
+    if (h->net->dev.type != CPS_NET_GRU) return CPS_OK;  // Dense: nothing to update (:334-335)
+    return cps_net_rollout(h, s_dev, 0, q0_dev, CPS_ROLLOUT_MAJOR, 1, 1, nullptr, 0, nullptr, CPS_ROLLOUT_MAJOR,
+                           h->net->d_href);
+}
+
+extern "C" int cps_net_state_size(const cps_handle *h) { return (h && h->net) ? h->net->dev.htot : -1; }
+
+extern "C" int cps_net_reset_state(cps_handle *h) {
+    if (!h) return CPS_ERR_INVALID;
+    if (!h->net) return fail(h, CPS_ERR_NOT_CONFIGURED, "cps_net_reset_state: no network loaded");
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    if (h->net->dev.htot > 0) CUDA_TRY(h, cudaMemsetAsync(h->net->d_href, 0, sizeof(float) * h->net->dev.htot, h->stream));
+    return CPS_OK;
+}
+
+extern "C" int cps_net_get_state(cps_handle *h, float *out) {
+    if (!h || !out) return CPS_ERR_INVALID;
+    if (!h->net) return fail(h, CPS_ERR_NOT_CONFIGURED, "cps_net_get_state: no network loaded");
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    if (h->net->dev.htot > 0) {
+        CUDA_TRY(h, cudaMemcpyAsync(out, h->net->d_href, sizeof(float) * h->net->dev.htot, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    }
+    return CPS_OK;
+}
+
+extern "C" int cps_net_set_state(cps_handle *h, const float *in) {
+    if (!h || !in) return CPS_ERR_INVALID;
+    if (!h->net) return fail(h, CPS_ERR_NOT_CONFIGURED, "cps_net_set_state: no network loaded");
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    if (h->net->dev.htot > 0) {
+        CUDA_TRY(h, cudaMemcpyAsync(h->net->d_href, in, sizeof(float) * h->net->dev.htot, cudaMemcpyHostToDevice, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    }
+    return CPS_OK;
+}
+
+// cps_mppi_step with CPS_PREDICTOR_NEURAL (called from cps_lib.cu)
+int cps_net_mppi_step(cps_handle *h, const float *s_dev, const float *noise_dev, int noise_layout, float u_prev,
+                      float *u_nom_dev, float *u_out_dev, float *J_out_dev, float *traj_out_dev, int traj_layout,
+                      float *u_run_out_dev) {
+    if (!h->net) return fail(h, CPS_ERR_NOT_CONFIGURED, "cps_mppi_step: neural predictor without a network (cps_net_load)");
+    if (h->cfg.noise_mode != CPS_NOISE_INDUCING)
+        return fail(h, CPS_ERR_UNSUPPORTED, "cps_mppi_step: the neural predictor supports CPS_NOISE_INDUCING only");
+    NetArgs a;
+    memset(&a, 0, sizeof(a));
+    const long long K = h->cfg.num_rollouts;
+    const int T = h->cfg.horizon;
+    a.s0 = s_dev; a.ss_b = 0;
+    a.B = (int)K; a.T = T;
+    a.h0 = h->net->d_href; a.hs_b = 0;
+    a.traj_out = traj_out_dev;
+    if (traj_layout == CPS_TIME_MAJOR) { a.ts_k = 1; a.ts_t = 6LL * K; a.ts_c = K; }
+    else { a.ts_k = (T + 1) * 6LL; a.ts_t = 6; a.ts_c = 1; }
+    a.cost = h->cost; a.mp = h->mp;
+    a.noise = noise_dev;
+    if (noise_layout == CPS_TIME_MAJOR) { a.ns_i = K; a.ns_k = 1; } else { a.ns_i = 1; a.ns_k = h->n_red; }
+    a.u_prev = u_prev;
+    a.u_nom = u_nom_dev; a.u_out = u_out_dev; a.J_out = J_out_dev; a.u_run_out = u_run_out_dev;
+    a.partials = h->d_partials; a.ticket = h->d_ticket; a.nonfinite = h->d_nonfinite;
+    a.shard_out = h->shard ? h->shard_out : nullptr;
+    a.h_ref = h->net->d_href;
+    return net_launch(h, a, true, (int)K);
+}

@@ -42,8 +42,10 @@ typedef enum cps_status {
  *  CPS_EULER_V0     predictor_ODE_v0: explicit Euler + edge bounce + fmod wrap
  *                   (CartPole/cartpole_numba.py:56-78, CartPole/cartpole_equations.py:341-364)
  *  CPS_EULER_CROMER predictor_ODE: semi-implicit Euler + atan2 wrap, no bounce
- *                   (CartPole/cartpole_equations.py:214-261,292-308) */
-typedef enum cps_integrator { CPS_EULER_V0 = 0, CPS_EULER_CROMER = 1 } cps_integrator;
+ *                   (CartPole/cartpole_equations.py:214-261,292-308)
+ *  CPS_PREDICTOR_NEURAL predictor_autoregressive_neural: GRU / Dense network loaded with cps_net_load
+ *                   (SI_Toolkit/src/SI_Toolkit/Predictors/predictor_autoregressive_neural.py:266-352) */
+typedef enum cps_integrator { CPS_EULER_V0 = 0, CPS_EULER_CROMER = 1, CPS_PREDICTOR_NEURAL = 2 } cps_integrator;
 
 /* Cost plugins (Control_Toolkit_ASF/Cost_Functions/CartPole/<name>.py) */
 typedef enum cps_cost {
@@ -170,6 +172,54 @@ int cps_rollout(cps_handle *h, const float *s0_dev, int s0_batched, const float 
  * device buffers that grow on demand (the only *_host call that may allocate, on first use / growth). */
 int cps_rollout_host(cps_handle *h, const float *s0_host, int s0_batched, const float *Q_host, int q_layout, int B,
                      int T, float *traj_out_host, int traj_layout, float *final_out_host);
+
+/* ---- autoregressive neural predictor (GRU / Dense) ------------------------------------------------------ */
+/* What predictor_autoregressive_neural.__init__ derives from the net-info file, the normalisation table and the
+ * checkpoint (predictor_autoregressive_neural.py:163-231, Functions/General/Normalising.py:15-186):
+ * the network consumes [control, state features in_idx[0..n_state_in)] and produces the state features
+ * out_idx[0..n_out); inputs are normalised x = a*v + b, outputs de-normalised v = A*y + B; missing features are
+ * zero; angle = atan2(sin, cos) (or sin/cos of a predicted angle) is appended
+ * (SI_Toolkit_ASF/ToolkitCustomization/predictors_customization.py:71-139).
+ * differential != 0 (outputs named D_*; Predictors/autoregression.py:118-158): the network predicts normalised
+ * derivatives; the normalised state advances by diff_p1*y + diff_p2 per step from the normalised initial values
+ * out_norm_a*s[out_idx]+out_norm_b, and net input i is fed from integrated output out_to_in[i]. */
+#define CPS_NET_MAX_LAYERS 4
+#define CPS_NET_GRU 0
+#define CPS_NET_DENSE 1
+typedef struct cps_net_desc {
+    int struct_size;                 /* = sizeof(cps_net_desc) */
+    int net_type;                    /* CPS_NET_GRU (torch GRUCell / keras GRU reset_after) | CPS_NET_DENSE (tanh MLP) */
+    int n_layers;                    /* hidden layers (<= CPS_NET_MAX_LAYERS); a linear output layer follows */
+    int hidden[CPS_NET_MAX_LAYERS];  /* units per hidden layer (each <= 128) */
+    int n_state_in;                  /* state features among the net inputs (<= 6); inputs = 1 + n_state_in */
+    int in_idx[6];                   /* their indices into the 6-vector state */
+    int n_out;                       /* net outputs (<= 6) */
+    int out_idx[6];
+    float norm_a[7], norm_b[7];      /* [0] control input, [1 + i] state input i */
+    float denorm_A[6], denorm_B[6];
+    int differential;
+    float diff_p1[6], diff_p2[6], out_norm_a[6], out_norm_b[6];
+    int out_to_in[6];
+} cps_net_desc;
+
+/* Weights, float32, concatenated per hidden layer -- GRU: w_ih [3H][in], w_hh [3H][H], b_ih [3H], b_hh [3H] in torch
+ * GRUCell order (gates r, z, n; Functions/Pytorch/Network.py:146-148); Dense: w [H][in], b [H] -- then the output
+ * layer w [n_out][H_last], b [n_out].  Copies them to the device in the kernels' layout and zeroes the stored hidden
+ * state (net.reset_internal_states(), predictor_autoregressive_neural.py:112-113).  May allocate. */
+int cps_net_load(cps_handle *h, const cps_net_desc *desc, const float *weights_host, long long n_weights);
+/* predictor.predict_core(s, Q) (predictor_autoregressive_neural.py:266-313): like cps_rollout.  h0_dev: initial
+ * hidden state, concatenated over the layers -- NULL: the handle's stored state (memory_states_ref, :291), else
+ * [Htot] shared or [B][Htot] if h0_batched.  h_final_dev: optional [B][Htot] hidden state after the T steps. */
+int cps_net_rollout(cps_handle *h, const float *s0_dev, int s0_batched, const float *Q_dev, int q_layout, int B, int T,
+                    const float *h0_dev, int h0_batched, float *traj_out_dev, int traj_layout, float *h_final_dev);
+/* update_internal_state_tf (:332-352): advance the stored hidden state by one network step on the measured state
+ * s_dev [6] and the applied control q0_dev [1] (both DEVICE pointers).  No-op for Dense networks.  cps_mppi_step
+ * with CPS_PREDICTOR_NEURAL does this itself after the solve (optimizer_mppi.py:191) unless K is sharded. */
+int cps_net_update(cps_handle *h, const float *s_dev, const float *q0_dev);
+int cps_net_state_size(const cps_handle *h);                       /* Htot (0 for Dense), -1 if no net is loaded */
+int cps_net_reset_state(cps_handle *h);
+int cps_net_get_state(cps_handle *h, float *state_host /* [Htot] */);
+int cps_net_set_state(cps_handle *h, const float *state_host /* [Htot] */);
 
 /* ---- standalone cost plugin (for the other optimizers; CostFunctionWrapper interface) ---------------------- */
 /* get_trajectory_cost (Control_Toolkit/Cost_Functions/__init__.py:74-93): traj_dev [K][T+1][6], Q_dev [K][T]

@@ -1,0 +1,171 @@
+"""GPU parity of the autoregressive neural predictor (cps_net_*; net_kernel) and of the MPPI solve that drives it,
+against goldens from the unmodified reference (tests/golden/net_*.npz, mppi_net_*.npz) and against the CPU oracle.
+Tolerances: trajectories 1e-5 range-relative (north_star; measured ~1e-6), J 1e-5, controls 1e-4."""
+import numpy as np
+import pytest
+
+from tests.netutil import net_spec_from_golden
+from tests.parity import load_golden, traj_err, vec_err
+
+pytestmark = pytest.mark.gpu
+
+NET_GOLDENS = ["net_GRU_6IN_64H1_64H2_5OUT_0", "net_GRU_6IN_32H1_32H2_5OUT_0", "net_Dense_6IN_32H1_32H2_5OUT_0"]
+MPPI_NET_RUNS = ["gru64_gradmin", "gru32_grad", "dense32_gradmin"]
+
+
+def engine_spec(sp):
+    from oracle import oracle as O
+    d = dict(sp)
+    d["weights"] = O.pack_net_weights(sp["net_type"], sp["layers"], sp["out_layer"])
+    return d
+
+
+def oracle_args(sp):
+    from oracle import oracle as O
+    return (sp["net_type"], sp["hsz"], O.pack_net_weights(sp["net_type"], sp["layers"], sp["out_layer"]), sp["in_idx"],
+            sp["out_idx"], sp["norm_a"], sp["norm_b"], sp["denorm_A"], sp["denorm_B"])
+
+
+def make_engine(sp, K, T, cost=None):
+    from cartpolesimulation_b200.core import Engine
+    eng = Engine(K, T, integrator="neural", cost=cost, device=0)
+    eng.net_load(engine_spec(sp))
+    return eng
+
+
+@pytest.mark.parametrize("name", NET_GOLDENS)
+def test_net_rollout_vs_reference_golden(name):
+    import torch
+    z, m = load_golden(name)
+    sp = net_spec_from_golden(z)
+    K, T = z["Q"].shape
+    eng = make_engine(sp, K, T)
+    dev = eng.device
+    Q = torch.from_numpy(z["Q"]).to(dev)
+    traj, _ = eng.net_rollout(torch.from_numpy(z["s0"]).to(dev), Q)
+    assert max(traj_err(traj.cpu().numpy(), z["traj_zero_h"]).values()) < 1e-5
+    e1 = max(traj_err(traj.cpu().numpy()[:, :2], z["traj_zero_h"][:, :2]).values())
+    assert e1 < 2e-6, e1
+    for s, q in zip(z["upd_s"], z["upd_q"]):
+        eng.net_update(torch.from_numpy(s).to(dev), torch.tensor([q], device=dev))
+    if sp["net_type"] == "GRU":
+        assert np.abs(eng.net_get_state() - z["h_after_updates"].reshape(-1)).max() < 2e-6
+    else:
+        assert eng.net_htot == 0 or sp["net_type"] == "Dense"
+    traj2, _ = eng.net_rollout(torch.from_numpy(z["s_after"]).to(dev), Q)
+    assert max(traj_err(traj2.cpu().numpy(), z["traj_after_updates"]).values()) < 1e-5
+    # per-rollout initial states, time-major layouts, explicit shared h0, hidden state out
+    h0 = torch.from_numpy(eng.net_get_state()).to(dev) if eng.net_htot else None
+    traj3, hf = eng.net_rollout(torch.from_numpy(z["s_rand"]).to(dev), Q.t().contiguous(), q_layout=1, traj_layout=1,
+                                h0=h0, want_h=True)
+    t3 = traj3.permute(2, 0, 1).cpu().numpy()
+    assert max(traj_err(t3, z["traj_rand"]).values()) < 1e-5
+    # the stored state is untouched by rollouts
+    if sp["net_type"] == "GRU":
+        assert np.abs(eng.net_get_state() - z["h_after_updates"].reshape(-1)).max() < 2e-6
+        eng.net_reset_state()
+        assert np.abs(eng.net_get_state()).max() == 0.0
+
+
+@pytest.mark.parametrize("name", NET_GOLDENS[:2])
+@pytest.mark.parametrize("B,T", [(1, 1), (17, 3), (2000, 50), (4099, 20)])
+def test_net_rollout_vs_oracle_sizes(name, B, T):
+    """ragged tiles (B not a multiple of 16), per-rollout hidden states, B = 1."""
+    import torch
+    from oracle import oracle as O
+    z, m = load_golden(name)
+    sp = net_spec_from_golden(z)
+    eng = make_engine(sp, B, T)
+    dev = eng.device
+    rng = np.random.default_rng(B * 100 + T)
+    ang = rng.uniform(-np.pi, np.pi, B)
+    s0 = np.stack([ang, rng.uniform(-3, 3, B), np.cos(ang), np.sin(ang), rng.uniform(-0.15, 0.15, B),
+                   rng.uniform(-0.5, 0.5, B)], 1).astype(np.float32)
+    Q = rng.uniform(-1, 1, (B, T)).astype(np.float32)
+    h0 = rng.uniform(-0.5, 0.5, (B, sum(sp["hsz"]))).astype(np.float32)
+    ref, href = O.net_rollout(*oracle_args(sp), s0, Q, h0=h0, want_h=True)
+    traj, hf = eng.net_rollout(torch.from_numpy(s0).to(dev), torch.from_numpy(Q).to(dev), h0=torch.from_numpy(h0).to(dev),
+                               want_h=True)
+    assert max(traj_err(traj.cpu().numpy(), ref).values()) < 1e-5
+    assert np.abs(hf.cpu().numpy() - href).max() < 5e-6
+
+
+@pytest.mark.parametrize("run", MPPI_NET_RUNS)
+def test_net_mppi_vs_reference_golden(run):
+    import torch
+    from cartpolesimulation_b200 import _lib as L
+    z, m = load_golden("mppi_net_" + run)
+    sp = net_spec_from_golden(z)
+    K, T = m["K"], m["T"]
+    eng = make_engine(sp, K, T, cost=m["cost"])
+    eng.set_variable_parameters(m["target_position"], m["target_equilibrium"])
+    dev = eng.device
+    J = torch.empty(K, device=dev)
+    traj = torch.empty((K, T + 1, 6), device=dev)
+    u_run = torch.empty((K, T), device=dev)
+    u_nom = np.zeros(T, dtype=np.float32)
+    h = np.zeros(sum(sp["hsz"]), np.float32)
+    for i in range(m["steps"]):
+        eng.set_u_nom(u_nom)
+        eng.net_set_state(h)
+        eps = torch.from_numpy(z["eps"][i]).to(dev)  # [K, n_ind], the reference's layout
+        u = eng.mppi_step(torch.from_numpy(z["s"][i]).to(dev), eps, L.ROLLOUT_MAJOR, float(z["u_prev"][i]), None, J, traj,
+                          L.ROLLOUT_MAJOR, u_run)
+        torch.cuda.synchronize()
+        if i == 0:
+            np.testing.assert_allclose(u_run.cpu().numpy(), z["u_run0"], rtol=0, atol=2e-7)
+            assert max(traj_err(traj.cpu().numpy()[:32], z["traj0"]).values()) < 1e-5
+        assert vec_err(J.cpu().numpy(), z["J"][i]) < 1e-5
+        assert abs(float(u.cpu()[0]) - float(z["u"][i])) < 1e-4
+        np.testing.assert_allclose(eng.get_u_nom(), z["u_nom"][i], rtol=0, atol=1e-4)
+        if sp["net_type"] == "GRU":  # the solve advanced the stored hidden state on (u, s) (optimizer_mppi.py:191)
+            assert np.abs(eng.net_get_state() - z["h_after"][i]).max() < 5e-6
+            h = z["h_after"][i].copy()
+        u_nom = z["u_nom"][i].copy()
+    assert eng.nonfinite_costs() == 0
+
+
+def test_net_mppi_K2000_vs_oracle_and_time_major_noise():
+    import torch
+    from oracle import oracle as O
+    from cartpolesimulation_b200 import _lib as L
+    z, m = load_golden("mppi_net_gru64_gradmin")
+    sp = net_spec_from_golden(z)
+    K, T = 2000, 50
+    eng = make_engine(sp, K, T, cost="quadratic_boundary_grad_minimal")
+    dev = eng.device
+    rng = np.random.default_rng(5)
+    eps = rng.standard_normal((K, eng.n_ind)).astype(np.float32)
+    u_nom = rng.uniform(-0.3, 0.3, T).astype(np.float32)
+    h = rng.uniform(-0.3, 0.3, sum(sp["hsz"])).astype(np.float32)
+    s = z["s"][1]
+    ref = O.mppi_step_net("quadratic_boundary_grad_minimal", *oracle_args(sp), s, u_nom, eps, h0=h, u_prev=0.1)
+    eng.set_u_nom(u_nom)
+    eng.net_set_state(h)
+    J = torch.empty(K, device=dev)
+    u = eng.mppi_step(torch.from_numpy(s).to(dev), torch.from_numpy(np.ascontiguousarray(eps.T)).to(dev), L.TIME_MAJOR, 0.1,
+                      None, J)
+    assert vec_err(J.cpu().numpy(), ref["J"]) < 1e-5
+    assert abs(float(u.cpu()[0]) - float(ref["u"])) < 1e-4
+    np.testing.assert_allclose(eng.get_u_nom(), ref["u_nom"], rtol=0, atol=1e-4)
+    _, hf = O.net_rollout(*oracle_args(sp), s, np.array([[ref["u"]]], np.float32), h0=h, want_h=True)
+    assert np.abs(eng.net_get_state() - hf[0]).max() < 5e-6
+
+
+def test_net_errors():
+    from cartpolesimulation_b200.core import Engine
+    import torch
+    eng = Engine(64, 10, integrator="neural", cost=None, device=0)
+    with pytest.raises(RuntimeError):  # CPS_ERR_NOT_CONFIGURED: no network loaded
+        eng.net_htot = 0
+        eng.net_rollout(torch.zeros(6, device=eng.device), torch.zeros((4, 10), device=eng.device))
+    z, m = load_golden(NET_GOLDENS[0])
+    sp = engine_spec(net_spec_from_golden(z))
+    bad = dict(sp)
+    bad["weights"] = sp["weights"][:-1]
+    with pytest.raises(ValueError):
+        eng.net_load(bad)
+    bad = dict(sp)
+    bad["net_type"] = "LSTM"
+    with pytest.raises(NotImplementedError):
+        eng.net_load(bad)
