@@ -3,7 +3,8 @@
 Same constructor keywords, `configure`, `step(s, time) -> np scalar`, `optimizer_reset`, and the attributes other
 code reads (`u_nom`, `u`, `rollout_trajectories`, `logging_values`, `optimal_trajectory`,
 `optimal_control_sequence`, `num_rollouts`, `mpc_horizon`, `optimizer_name`).  The whole of
-`_predict_and_cost` (:180-192) runs as one CUDA kernel launch (cps_mppi_step); the predictor and cost-function
+`_predict_and_cost` (:180-192), including the hidden-state update of a recurrent predictor (:191,194-196), runs as one
+CUDA kernel launch (cps_mppi_step); predictors: ODE, ODE_v0 and neural (GRU / Dense); the predictor and cost-function
 objects handed in are only inspected for their configuration (predictor type / substeps, cost plugin name and
 weights, variable_parameters), so both this package's wrappers and the reference's own
 PredictorWrapper / CostFunctionWrapper instances work.
@@ -124,11 +125,20 @@ class optimizer_mppi_b200:
             raise ValueError("optimizer_mppi_b200 implements the CartPole path: 6 states, 1 control input")
         self.num_states, self.num_control_inputs = int(num_states), int(num_control_inputs)
         ptype, n = _extract_predictor(self.predictor, predictor_specification)
-        if ptype not in ("ODE", "ODE_v0"):
-            if ptype == "neural":
-                raise NotImplementedError("neural predictors are driven through predictor_autoregressive_neural "
-                                          "(cartpolesimulation_b200.neural), not the fused ODE kernel")
+        if ptype not in ("ODE", "ODE_v0", "neural"):
             raise ValueError(f"optimizer_mppi_b200 does not support predictor type {ptype!r} (no CPU fallback)")
+        net_spec = None
+        if ptype == "neural":
+            # the network comes from the configured predictor: this package's predictor_autoregressive_neural
+            # (net_spec) or the reference's own object (torch net + net_info + normalization_info)
+            from . import neural
+            inner = getattr(self.predictor, "predictor", self.predictor)
+            net_spec = getattr(inner, "net_spec", None)
+            if net_spec is None:
+                if not hasattr(inner, "net_info"):
+                    raise ValueError("neural predictor: configure the PredictorWrapper before the optimizer "
+                                     "(controller_mpc.py:69-76 does)")
+                net_spec = neural.spec_from_reference_predictor(inner)
         cost_name, cost_cfg = _extract_cost(self.cost_function)
         self.dt = float(dt)
         self.engine = Engine(num_rollouts=self.num_rollouts, horizon=self.mpc_horizon, dt=self.dt, substeps=n,
@@ -137,6 +147,9 @@ class optimizer_mppi_b200:
                              fast_sincos=self._fast_sincos, exact_atan2=self._exact_atan2)
         self.device = self.engine.device
         self.cost_name = cost_name
+        self.predictor_type = ptype
+        if net_spec is not None:
+            self.engine.net_load(net_spec)
         self.engine.set_cost_params(cfgmod.cost_vector(cost_name, cost_cfg))
         self.engine.set_mppi_params(self.cc_weight, self.R, self.LBD, self.NU, self._SQRTRHOINV,
                                     float(self.action_low[0]), float(self.action_high[0]))
@@ -175,7 +188,8 @@ class optimizer_mppi_b200:
         return self._traj
 
     def optimizer_reset(self):
-        """u_nom = 0.5 (lo + hi) (optimizer_mppi.py:226-230)."""
+        """u_nom = 0.5 (lo + hi) (optimizer_mppi.py:226-230).  The stored hidden state of a recurrent predictor is
+        NOT reset, as in the reference."""
         self.engine.mppi_reset(0.5 * float(self.action_low[0] + self.action_high[0]))
 
     def _refresh_variable_parameters(self):
@@ -219,6 +233,9 @@ class optimizer_mppi_b200:
         self._refresh_variable_parameters()
         noise, layout = self._draw_noise()
         u_prev = float(np.asarray(self.u).reshape(-1)[0])
+        h_before = None
+        if self.calculate_optimal_trajectory and self.predictor_type == "neural" and self.engine.net_htot:
+            h_before = torch.from_numpy(self.engine.net_get_state()).to(self.device)
         if self.materialize_rollouts or self.optimizer_logging:
             K, T = self.num_rollouts, self.mpc_horizon
             if self._J is None:
@@ -243,6 +260,11 @@ class optimizer_mppi_b200:
         if self.calculate_optimal_trajectory:  # _predict_optimal_trajectory (:198-201): nominal rollout from s
             un = torch.from_numpy(self.engine.get_u_nom().reshape(1, -1)).to(self.device)
             self._s_dev.copy_(torch.from_numpy(s))
-            traj, _ = self.engine.rollout(self._s_dev, un)
+            if self.predictor_type == "neural":
+                # the reference's batch-1 predictor copy rolls out from its own hidden state and advances it AFTER
+                # predicting (:198-201), i.e. from the state before this solve's update
+                traj, _ = self.engine.net_rollout(self._s_dev, un, h0=h_before)
+            else:
+                traj, _ = self.engine.rollout(self._s_dev, un)
             self.optimal_trajectory = traj.cpu().numpy()
         return self.u

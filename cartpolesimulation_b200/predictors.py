@@ -212,6 +212,8 @@ class PredictorWrapper:
         predictor_name = {"ODE": "ODE_default", "ODE_v0": "ODE_v0_default", "neural": "neural_default",
                           "GP": "GP_default"}.get(comps[0])
         model_name = None
+        if predictor_name == "GP_default" and predictor_name not in self.predictors_config:
+            raise NotImplementedError('GP predictors are outside the B200 hot path (they need gpflow/TF)')
         if predictor_name is None and comps[0] in self.predictors_config:
             predictor_name = comps[0]
         if predictor_name is None:

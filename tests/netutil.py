@@ -44,3 +44,31 @@ def net_spec_from_golden(z):
                 in_idx=[STATE_VARIABLES.index(n) for n in inputs[1:]],
                 out_idx=[STATE_VARIABLES.index(n) for n in outputs],
                 norm_a=a, norm_b=b, denorm_A=A, denorm_B=B, meta=meta)
+
+
+def write_model_dir(root, z):
+    """Writes <root>/<net full name>/{<name>.txt, ckpt.pt, NI.csv} from a net golden file, in the reference's formats
+    (Functions/General/Initialization.py:35-104; torch state_dict of Functions/Pytorch/Network.py Sequence).
+    Returns the model path to use as `predictor_specification` / `model_name`."""
+    import os
+    import torch
+    meta = json.loads(str(z["meta"]))
+    full = meta["net"]
+    d = os.path.join(root, full)
+    os.makedirs(d, exist_ok=True)
+    short = "-".join(p for p in full.split("-") if not (p.endswith("IN") or p.endswith("OUT")))[:-2]
+    cols = [str(c) for c in z["norm_cols"]]
+    ni = os.path.join(d, "NI.csv")
+    with open(ni, "w") as f:
+        f.write("," + ",".join(cols) + "\n")
+        for r, rowname in enumerate(["mean", "std", "max", "min"]):
+            f.write(rowname + "," + ",".join(repr(float(z["norm_table"][r, c])) for c in range(len(cols))) + "\n")
+    with open(os.path.join(d, full + ".txt"), "w") as f:
+        f.write("\n".join([
+            "CREATED:", "2026-01-01 00:00:00", "", "LIBRARY:", "Pytorch", "", "NET NAME:", short, "",
+            "NET FULL NAME:", full, "", "INPUTS:", ", ".join(meta["inputs"]), "", "OUTPUTS:", ", ".join(meta["outputs"]),
+            "", "TYPE:", meta["type"], "", "NORMALIZATION:", ni, "", "NORMALIZE:", "True", "",
+            "WASH OUT LENGTH:", "10", "", "CONSTRUCT NETWORK:", "with cells", ""]))
+    sd = {str(k): torch.from_numpy(np.array(z["w__" + str(k)])) for k in z["state_dict_keys"]}
+    torch.save(sd, os.path.join(d, "ckpt.pt"))
+    return os.path.join(root, full)

@@ -187,3 +187,75 @@ def test_cost_wrapper_interface(name):
     with pytest.raises(ValueError):
         cps.CostFunctionWrapper().configure(batch_size=1, horizon=1, variable_parameters=vp,
                                             cost_function_specification="quadratic_boundary_nonconvex")
+
+
+# ------------------------------------------------------------------------------------------------------------
+# neural predictor through the plugin objects
+# ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["net_GRU_6IN_64H1_64H2_5OUT_0", "net_Dense_6IN_32H1_32H2_5OUT_0"])
+def test_neural_predictor_wrapper_interface(name, tmp_path):
+    """PredictorWrapper -> predictor_autoregressive_neural loaded from a model directory in the reference's format
+    (net-info .txt, torch checkpoint, normalisation csv): predict_core / update / predict vs the reference's outputs."""
+    import cartpolesimulation_b200 as cps
+    from tests.netutil import write_model_dir
+    z, m = load_golden(name)
+    model = write_model_dir(str(tmp_path), z)
+    K, T = z["Q"].shape
+    pw = cps.PredictorWrapper()
+    pw.configure(batch_size=K, horizon=T, dt=0.02, predictor_specification=model)
+    assert pw.predictor_type == "neural" and pw.num_states == 6 and pw.num_control_inputs == 1
+    pw.predictor.update_before_predicting = False
+    s0 = np.tile(z["s0"], (K, 1))
+    Q = z["Q"][:, :, None]
+    out = pw.predict_core(torch.from_numpy(s0), torch.from_numpy(Q))     # torch CPU in -> torch CPU out
+    assert isinstance(out, torch.Tensor) and out.device.type == "cpu" and tuple(out.shape) == (K, T + 1, 6)
+    assert max(traj_err(out.numpy(), z["traj_zero_h"]).values()) < 1e-5
+    s_cur = s0.copy()
+    for i in range(3):  # PredictorWrapper.update -> update_internal_state_tf (predictor_wrapper.py:173-177)
+        pw.update(Q0=np.full((K, 1, 1), z["upd_q"][i], np.float32), s=s_cur)
+        s_cur = s_cur.copy()
+        s_cur[:, 1] += 0.05
+    if m["type"] == "GRU":
+        assert np.abs(pw.predictor.engine.net_get_state() - z["h_after_updates"].reshape(-1)).max() < 2e-6
+    out2 = pw.predict(s_cur, Q)                                            # numpy in -> numpy out
+    assert isinstance(out2, np.ndarray)
+    assert max(traj_err(out2, z["traj_after_updates"]).values()) < 1e-5
+    dev = pw.predictor.device
+    out3 = pw.predict_core(torch.from_numpy(z["s_rand"]).to(dev), torch.from_numpy(Q).to(dev))  # CUDA in -> CUDA out
+    assert out3.device == dev
+    assert max(traj_err(out3.cpu().numpy(), z["traj_rand"]).values()) < 1e-5
+    with pytest.raises(ValueError):
+        pw.predict_core(torch.from_numpy(s0), torch.from_numpy(z["Q"]))    # Q without the feature axis
+
+
+def test_neural_predictor_errors(tmp_path):
+    import cartpolesimulation_b200 as cps
+    pw = cps.PredictorWrapper()
+    with pytest.raises(FileNotFoundError):
+        pw.configure(batch_size=4, horizon=5, dt=0.02, predictor_specification=str(tmp_path / "GRU-6IN-8H1-5OUT-0"))
+    with pytest.raises(NotImplementedError):
+        pw.configure(batch_size=4, horizon=5, dt=0.02, predictor_specification="GP")
+
+
+@pytest.mark.parametrize("run", ["gru64_gradmin", "dense32_gradmin", "gru32_grad"])
+def test_optimizer_neural_closed_loop_matches_reference(run, tmp_path):
+    """optimizer_mppi_b200 + neural predictor, the same closed loop the golden was recorded on (injected draws); the
+    solver carries its own u_nom, u_prev and hidden state from step to step."""
+    from tests.netutil import write_model_dir
+    z, m = load_golden("mppi_net_" + run)
+    m = dict(m)
+    m["predictor"] = write_model_dir(str(tmp_path), z)
+    opt, vp = _make_optimizer(m, logging=(run == "gru64_gradmin"))
+    K, n_ind = m["K"], z["eps"].shape[2]
+    opt.rng = InjectedNormal([torch.from_numpy(z["eps"][i]).reshape(K, n_ind, 1) for i in range(m["steps"])])
+    for i in range(m["steps"]):
+        u = opt.step(z["s"][i].copy())
+        assert isinstance(u, np.ndarray) and u.dtype == np.float32
+        assert abs(float(u) - float(z["u"][i])) < 2e-4, (i, float(u), float(z["u"][i]))
+        np.testing.assert_allclose(opt.u_nom.numpy().reshape(-1), z["u_nom"][i], rtol=0, atol=2e-4)
+        if "h_after" in z.files:
+            assert np.abs(opt.engine.net_get_state() - z["h_after"][i]).max() < 1e-5
+        if opt.optimizer_logging:
+            assert vec_err(opt.logging_values["J_logged"], z["J"][i]) < 2e-5
+            if i == 0:
+                assert max(traj_err(opt.logging_values["rollout_trajectories_logged"][:32], z["traj0"]).values()) < 1e-5
