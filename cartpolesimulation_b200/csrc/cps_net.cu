@@ -5,15 +5,18 @@
 // stack); Predictors/autoregression.py:33-158 (feedback loop, differential variant);
 // Functions/General/Normalising.py:15-186; ToolkitCustomization/predictors_customization.py:71-139 (augmentation).
 //
-// net_kernel<R, COST, MPPI>: one CTA advances a tile of R rollouts through the whole horizon.
+// net_kernel<R, HT, MPPI>: one CTA advances a tile of R (16 | 32) rollouts through the whole horizon.
 //   * all weights live in shared memory for the whole launch (2x64 GRU: 156 KB), fetched once with one bulk
 //     asynchronous copy (cp.async.bulk + mbarrier);
-//   * 4 compute warps: thread (row group g, unit j) keeps the gate pre-activations of RT = 8 rollouts for one hidden
-//     unit in registers; weights are read conflict-free ([in][3H] layout, consecutive lanes = consecutive units),
-//     activations as broadcast float4 ([unit][R] layout) -> 24 FMAs per 5 shared-memory loads;
-//   * 1 "row" warp (lane = rollout) trails the compute warps by one network step: de-normalisation, angle
-//     augmentation, trajectory store, stage / terminal cost, MPPI perturbation interpolation and the next control,
-//     overlapped with the next step's layer-1 products;
+//   * R/4 compute warps: thread (row group g, unit j) keeps the gate pre-activations of 8 rollouts for one hidden
+//     unit in registers as 4 packed pairs and accumulates them with FFMA2 (fma.rn.f32x2: two IEEE fp32 FMAs per
+//     issue slot); weights are read conflict-free ([in][3H] layout, consecutive lanes = consecutive units),
+//     activations as broadcast 16-byte loads ([unit][R] layout) -> 24 FMAs per 5 shared-memory loads and 12 issue
+//     slots; HT = compile-time hidden size (64, 32; 0 = any) turns the address arithmetic into immediates;
+//   * 1 "row" warp (lane = rollout): the linear output layer, the feedback into the next network input,
+//     de-normalisation, angle augmentation, trajectory store, stage / terminal cost, MPPI perturbation interpolation
+//     and the next control.  The recurrent product W_hh h of the first layer does not depend on the fed-back output,
+//     so the compute warps run it while the row warp produces the input: the output layer is off the critical path;
 //   * MPPI = true additionally does what mppi_kernel does after the rollout (block partials, last-block merge,
 //     clipped u_nom / u) and then advances the stored hidden state by one step on (u, s)
 //     (optimizer_mppi.py:191,194-196) -- one launch per solve.
@@ -26,9 +29,9 @@
 
 #include "cps_internal.cuh"
 
-#define NET_NC 128          // compute threads
-#define NET_NT (NET_NC + 32)  // + the row warp
 #define NET_RT 8            // rollouts per compute thread
+
+typedef unsigned long long u64;
 
 struct NetDev {
     int type, n_layers, n_in, n_state_in, n_out, htot, n_weights;
@@ -49,8 +52,7 @@ struct NetState {
     NetDev dev;
     float *d_weights;   // device layout: per layer W_ih^T [in][G*H], W_hh^T [H][3H], b_ih, b_hh; W_out^T [H][n_out], b_out
     float *d_href;      // stored hidden state [htot] (memory_states_ref; rows are identical across the batch)
-    size_t smem_weights;  // bytes of the weight image
-    bool weights_in_smem;
+    int ht;             // common hidden size if the kernels have a specialisation for it (64, 32), else 0
 };
 
 struct NetArgs {
@@ -67,6 +69,7 @@ struct NetArgs {
     long long ts_k, ts_t, ts_c;
     float *h_final;           // [B][htot] or null
     // MPPI mode
+    int cost_id;
     CostParams cost;
     MppiParams mp;
     const float *noise;
@@ -86,149 +89,210 @@ __device__ __forceinline__ float tanh_f(float x) { return 1.0f - __fdividef(2.0f
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 
-// acc[q][r] += sum_i Wt[i][q*H + j] * x[i][g*RT + r]
-template <int R, int NG>
-__device__ __forceinline__ void matvec_acc(const float *__restrict__ Wt, const float *__restrict__ x, int in_len, int H,
-                                           int j, int g, float (&acc)[NG][NET_RT]) {
-    const float *w = Wt + j;
-    const float *xv = x + g * NET_RT;
-    const int ws = NG * H;
-#pragma unroll 4
+// Packed FP32 pairs (Blackwell FFMA2: two IEEE fp32 FMAs per issue slot; same results as two fmaf).
+__device__ __forceinline__ u64 pack2(float lo, float hi) {
+    u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(u64 v, float &lo, float &hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ u64 ffma2(u64 a, u64 b, u64 c) {
+    u64 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+
+// acc[q][.] += sum_i Wt[i][q*H + j] * x[i][g*8 .. g*8+8), rows held as 4 packed pairs.
+// Wt points at column j already; ws = row stride of Wt (NG*H); x points at the thread's row group.
+template <int R, int NG, int HT>
+__device__ __forceinline__ void matvec_acc2(const float *__restrict__ w, const float *__restrict__ xv, int in_len, int H,
+                                            u64 (&acc)[NG][4]) {
+    const int Hc = HT ? HT : H;
+    const int ws = NG * Hc;
+#pragma unroll 8
     for (int i = 0; i < in_len; ++i) {
-        const float4 x0 = *reinterpret_cast<const float4 *>(xv + i * R);
-        const float4 x1 = *reinterpret_cast<const float4 *>(xv + i * R + 4);
+        const ulonglong2 x0 = *reinterpret_cast<const ulonglong2 *>(xv + i * R);
+        const ulonglong2 x1 = *reinterpret_cast<const ulonglong2 *>(xv + i * R + 4);
 #pragma unroll
         for (int q = 0; q < NG; ++q) {
-            const float wq = w[i * ws + q * H];
-            acc[q][0] = fmaf(wq, x0.x, acc[q][0]); acc[q][1] = fmaf(wq, x0.y, acc[q][1]);
-            acc[q][2] = fmaf(wq, x0.z, acc[q][2]); acc[q][3] = fmaf(wq, x0.w, acc[q][3]);
-            acc[q][4] = fmaf(wq, x1.x, acc[q][4]); acc[q][5] = fmaf(wq, x1.y, acc[q][5]);
-            acc[q][6] = fmaf(wq, x1.z, acc[q][6]); acc[q][7] = fmaf(wq, x1.w, acc[q][7]);
+            const float wq = w[i * ws + q * Hc];
+            const u64 ww = pack2(wq, wq);
+            acc[q][0] = ffma2(ww, x0.x, acc[q][0]);
+            acc[q][1] = ffma2(ww, x0.y, acc[q][1]);
+            acc[q][2] = ffma2(ww, x1.x, acc[q][2]);
+            acc[q][3] = ffma2(ww, x1.y, acc[q][3]);
         }
     }
 }
 
 // torch.nn.GRUCell (gate order r, z, n): r = s(W_ir x + b_ir + W_hr h + b_hr), z likewise,
 // n = tanh(W_in x + b_in + r (W_hn h + b_hn)), h' = (h - n) z + n.
-template <int R>
-__device__ __forceinline__ void gru_layer(const NetDev &N, const float *W, int l, const float *xin, int in_len,
-                                          const float *hprev, float *hnew, int tid) {
-    const int H = N.hsz[l];
-    const float *Wih = W + N.off_wih[l], *Whh = W + N.off_whh[l], *bih = W + N.off_bih[l], *bhh = W + N.off_bhh[l];
-    for (int item = tid; item < (R / NET_RT) * H; item += NET_NC) {
-        const int j = item % H, g = item / H;
-        float ai[3][NET_RT], ah[3][NET_RT];
+// The pre-activations of one hidden unit for 8 rollouts: acc[0] = r, acc[1] = z (both products summed), acc[2] = the
+// hidden part of n; the input part of n is added by gru_ih_finish.
+template <int R, int HT>
+__device__ __forceinline__ void gru_hh(const NetDev &N, const float *W, int l, const float *hprev, int j, int g,
+                                       u64 (&acc)[3][4]) {
+    const int H = HT ? HT : N.hsz[l];
+    const float *bih = W + N.off_bih[l], *bhh = W + N.off_bhh[l];
 #pragma unroll
-        for (int q = 0; q < 3; ++q) {
-            const float bi = bih[q * H + j], bh = bhh[q * H + j];
+    for (int q = 0; q < 3; ++q) {
+        const float b = (q < 2) ? bih[q * H + j] + bhh[q * H + j] : bhh[q * H + j];
+        const u64 bb = pack2(b, b);
 #pragma unroll
-            for (int r = 0; r < NET_RT; ++r) { ai[q][r] = (q < 2) ? bi + bh : bi; ah[q][r] = (q < 2) ? 0.0f : bh; }
-        }
-        matvec_acc<R, 3>(Wih, xin, in_len, H, j, g, ai);
-        // r and z accumulate both products in one register set; the n gate keeps them apart
-        {
-            const float *w = Whh + j;
-            const float *xv = hprev + g * NET_RT;
-#pragma unroll 4
-            for (int i = 0; i < H; ++i) {
-                const float4 x0 = *reinterpret_cast<const float4 *>(xv + i * R);
-                const float4 x1 = *reinterpret_cast<const float4 *>(xv + i * R + 4);
-                const float xr[NET_RT] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-                const float wr = w[i * 3 * H], wz = w[i * 3 * H + H], wn = w[i * 3 * H + 2 * H];
-#pragma unroll
-                for (int r = 0; r < NET_RT; ++r) {
-                    ai[0][r] = fmaf(wr, xr[r], ai[0][r]);
-                    ai[1][r] = fmaf(wz, xr[r], ai[1][r]);
-                    ah[2][r] = fmaf(wn, xr[r], ah[2][r]);
-                }
-            }
-        }
-        const float *ho = hprev + j * R + g * NET_RT;
-        float *hn = hnew + j * R + g * NET_RT;
-        float out[NET_RT];
-#pragma unroll
-        for (int r = 0; r < NET_RT; ++r) {
-            const float rr = sigmoid_f(ai[0][r]);
-            const float zz = sigmoid_f(ai[1][r]);
-            const float nn = tanh_f(fmaf(rr, ah[2][r], ai[2][r]));
-            out[r] = fmaf(ho[r] - nn, zz, nn);
-        }
-        *reinterpret_cast<float4 *>(hn) = make_float4(out[0], out[1], out[2], out[3]);
-        *reinterpret_cast<float4 *>(hn + 4) = make_float4(out[4], out[5], out[6], out[7]);
+        for (int r = 0; r < 4; ++r) acc[q][r] = bb;
     }
+    matvec_acc2<R, 3, HT>(W + N.off_whh[l] + j, hprev + g * NET_RT, H, H, acc);
+}
+
+template <int R, int HT>
+__device__ __forceinline__ void gru_ih_finish(const NetDev &N, const float *W, int l, const float *xin, int in_len,
+                                              const float *hprev, float *hnew, int j, int g, u64 (&acc)[3][4]) {
+    const int H = HT ? HT : N.hsz[l];
+    const float *Wih = W + N.off_wih[l] + j, *bih = W + N.off_bih[l];
+    u64 ai[3][4];
+    const float bn = bih[2 * H + j];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) { ai[0][r] = acc[0][r]; ai[1][r] = acc[1][r]; ai[2][r] = pack2(bn, bn); }
+    matvec_acc2<R, 3, HT>(Wih, xin + g * NET_RT, in_len, H, ai);
+    const float *ho = hprev + j * R + g * NET_RT;
+    float *hn = hnew + j * R + g * NET_RT;
+    float out[NET_RT];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        float r0, r1, z0, z1, ni0, ni1, nh0, nh1;
+        unpack2(ai[0][r], r0, r1); unpack2(ai[1][r], z0, z1); unpack2(ai[2][r], ni0, ni1); unpack2(acc[2][r], nh0, nh1);
+        const float n0 = tanh_f(fmaf(sigmoid_f(r0), nh0, ni0)), n1 = tanh_f(fmaf(sigmoid_f(r1), nh1, ni1));
+        out[2 * r] = fmaf(ho[2 * r] - n0, sigmoid_f(z0), n0);
+        out[2 * r + 1] = fmaf(ho[2 * r + 1] - n1, sigmoid_f(z1), n1);
+    }
+    *reinterpret_cast<float4 *>(hn) = make_float4(out[0], out[1], out[2], out[3]);
+    *reinterpret_cast<float4 *>(hn + 4) = make_float4(out[4], out[5], out[6], out[7]);
 }
 
 // Dense layer: a = tanh(W x + b) (Functions/Pytorch/Network.py:255-260)
-template <int R>
-__device__ __forceinline__ void dense_layer(const NetDev &N, const float *W, int l, const float *xin, int in_len,
-                                            float *act, int tid) {
-    const int H = N.hsz[l];
-    const float *Wt = W + N.off_wih[l], *b = W + N.off_bih[l];
-    for (int item = tid; item < (R / NET_RT) * H; item += NET_NC) {
-        const int j = item % H, g = item / H;
-        float a[1][NET_RT];
+template <int R, int HT>
+__device__ __forceinline__ void dense_unit(const NetDev &N, const float *W, int l, const float *xin, int in_len,
+                                           float *act, int j, int g) {
+    const int H = HT ? HT : N.hsz[l];
+    const float b = (W + N.off_bih[l])[j];
+    u64 a[1][4];
 #pragma unroll
-        for (int r = 0; r < NET_RT; ++r) a[0][r] = b[j];
-        matvec_acc<R, 1>(Wt, xin, in_len, H, j, g, a);
-        float *o = act + j * R + g * NET_RT;
+    for (int r = 0; r < 4; ++r) a[0][r] = pack2(b, b);
+    matvec_acc2<R, 1, HT>(W + N.off_wih[l] + j, xin + g * NET_RT, in_len, H, a);
+    float *o = act + j * R + g * NET_RT;
 #pragma unroll
-        for (int r = 0; r < NET_RT; ++r) o[r] = tanh_f(a[0][r]);
+    for (int r = 0; r < 4; ++r) {
+        float v0, v1;
+        unpack2(a[0][r], v0, v1);
+        o[2 * r] = tanh_f(v0);
+        o[2 * r + 1] = tanh_f(v1);
     }
 }
 
-// Linear output layer + feedback: y = W_out h + b_out; next net input = y (or the integrated state, differential nets)
+// One network step of the compute warps (threads 0 .. NC-1): hidden layers only.  GRU: reads h(t-1) from buffer p of
+// every layer and writes h(t) into buffer 1-p.  The recurrent product of layer 0 does not depend on this step's
+// input, so it runs BEFORE the first barrier, while the row warp is still producing that input (the previous
+// step's output layer + feedback); the caller's row warp must execute 1 + n_layers matching barriers.
+template <int R, int HT>
+__device__ __forceinline__ void compute_step(const NetDev &N, const float *W, float *hb, int hstride, int p,
+                                             const float *xin, int tid) {
+    constexpr int NC = R * 8;
+    const bool gru = N.type == CPS_NET_GRU;
+    const int H0 = HT ? HT : N.hsz[0];
+    const bool split = gru && (R / NET_RT) * H0 <= NC;   // one (unit, row group) item per thread
+    const int j0 = tid % H0, g0 = tid / H0;
+    const bool has0 = tid < (R / NET_RT) * H0;
+    u64 acc[3][4];
+    if (split && has0) gru_hh<R, HT>(N, W, 0, hb + p * hstride, j0, g0, acc);
+    __syncthreads();  // the row warp has written this step's network input
+    const float *in = xin;
+    int in_len = N.n_in;
+    for (int l = 0; l < N.n_layers; ++l) {
+        const int H = HT ? HT : N.hsz[l];
+        float *hl = hb + N.hoff[l] * R;
+        if (gru) {
+            if (l == 0 && split) {
+                if (has0) gru_ih_finish<R, HT>(N, W, 0, in, in_len, hl + p * hstride, hl + (1 - p) * hstride, j0, g0, acc);
+            } else {
+                for (int item = tid; item < (R / NET_RT) * H; item += NC) {
+                    const int j = item % H, g = item / H;
+                    u64 a2[3][4];
+                    gru_hh<R, HT>(N, W, l, hl + p * hstride, j, g, a2);
+                    gru_ih_finish<R, HT>(N, W, l, in, in_len, hl + p * hstride, hl + (1 - p) * hstride, j, g, a2);
+                }
+            }
+            in = hl + (1 - p) * hstride;
+        } else {
+            for (int item = tid; item < (R / NET_RT) * H; item += NC) dense_unit<R, HT>(N, W, l, in, in_len, hl, item % H, item / H);
+            in = hl;
+        }
+        in_len = H;
+        __syncthreads();
+    }
+}
+
+// Linear output layer for one rollout, by the row warp: y = W_out h + b_out.  R = 16: lane = r + 16 * half, the two
+// halves take alternate units and are combined with one shuffle; R = 32: lane = r.
 template <int R>
-__device__ __forceinline__ void out_layer(const NetDev &N, const float *W, const float *hlast, float *ybuf, float *snorm,
-                                          float *xnext, int tid) {
+__device__ __forceinline__ void out_layer_row(const NetDev &N, const float *W, const float *hlast, int lane, float (&y)[6]) {
     const int H = N.hsz[N.n_layers - 1];
     const float *Wo = W + N.off_wout, *bo = W + N.off_bout;
-    for (int item = tid; item < R * N.n_out; item += NET_NC) {
-        const int r = item % R, o = item / R;
-        float y0 = bo[o], y1 = 0.0f;
-        int j = 0;
-        for (; j + 1 < H; j += 2) {
-            y0 = fmaf(Wo[j * N.n_out + o], hlast[j * R + r], y0);
-            y1 = fmaf(Wo[(j + 1) * N.n_out + o], hlast[(j + 1) * R + r], y1);
-        }
-        if (j < H) y0 = fmaf(Wo[j * N.n_out + o], hlast[j * R + r], y0);
-        float y = y0 + y1;
-        if (N.differential) {  // autoregression.py:149-154
-            y = snorm[o * R + r] + fmaf(N.p1[o], y, N.p2[o]);
-            snorm[o * R + r] = y;
-            for (int i = 0; i < N.n_state_in; ++i)
-                if (N.out_to_in[i] == o) xnext[(1 + i) * R + r] = y;
-        } else if (o < N.n_state_in) {
-            xnext[(1 + o) * R + r] = y;  // autoregression.py:94-98: the output is the next input
-        }
-        ybuf[o * R + r] = y;
+    constexpr int NS = 32 / R;          // lanes per rollout
+    const int r = lane % R, part = lane / R;
+#pragma unroll
+    for (int o = 0; o < 6; ++o) y[o] = (o < N.n_out && part == 0) ? bo[o] : 0.0f;
+    for (int j = part; j < H; j += NS) {
+        const float hv = hlast[j * R + r];
+#pragma unroll
+        for (int o = 0; o < 6; ++o)
+            if (o < N.n_out) y[o] = fmaf(Wo[j * N.n_out + o], hv, y[o]);
+    }
+    if (NS == 2) {
+#pragma unroll
+        for (int o = 0; o < 6; ++o) y[o] += __shfl_xor_sync(0xffffffffu, y[o], 16);
     }
 }
 
 // de-normalise, scatter into the 6-vector state, augment (predictors_customization.py:120-139)
-template <int R>
-__device__ __forceinline__ void compose_state(const NetDev &N, const float *ybuf, int r, float (&st)[6]) {
+__device__ __forceinline__ void compose_state(const NetDev &N, const float (&y)[6], float (&st)[6]) {
 #pragma unroll
     for (int c = 0; c < 6; ++c) st[c] = 0.0f;
-    for (int o = 0; o < N.n_out; ++o) {
-        const float v = fmaf(N.denorm_A[o], ybuf[o * R + r], N.denorm_B[o]);
-        const int c = N.out_idx[o];
 #pragma unroll
-        for (int cc = 0; cc < 6; ++cc)
-            if (cc == c) st[cc] = v;
+    for (int o = 0; o < 6; ++o) {
+        if (o < N.n_out) {
+            const float v = fmaf(N.denorm_A[o], y[o], N.denorm_B[o]);
+            const int c = N.out_idx[o];
+#pragma unroll
+            for (int cc = 0; cc < 6; ++cc)
+                if (cc == c) st[cc] = v;
+        }
     }
     if (!N.has_angle && N.has_sin && N.has_cos) st[IDX_ANGLE] = atan2f(st[IDX_SIN], st[IDX_COS]);
     if (N.has_angle && !N.has_sin) st[IDX_SIN] = sinf(st[IDX_ANGLE]);
     if (N.has_angle && !N.has_cos) st[IDX_COS] = cosf(st[IDX_ANGLE]);
 }
 
-template <int R, int COST, bool MPPI>
-__global__ void __launch_bounds__(NET_NT, 1) net_kernel(const __grid_constant__ NetArgs a) {
+__device__ __forceinline__ float stage_cost_rt(int id, const CostParams &C, float ca, float w, float x, float u, float up) {
+    switch (id) {
+    case CPS_COST_DEFAULT: return stage_cost<COST_DEFAULT>(C, ca, w, x, u, up) - C.max_cost;  // get_stage_cost shift (:63-64)
+    case CPS_COST_QUADRATIC_BOUNDARY: return stage_cost<COST_QB>(C, ca, w, x, u, up) - C.max_cost;
+    case CPS_COST_QB_GRAD_MINIMAL: return stage_cost<COST_GRADMIN>(C, ca, w, x, u, up);
+    case CPS_COST_QB_GRAD: return stage_cost<COST_GRAD>(C, ca, w, x, u, up);
+    default: return 0.0f;
+    }
+}
+
+template <int R, int HT, bool MPPI>
+__global__ void __launch_bounds__(R * 8 + 32, 1) net_kernel(const __grid_constant__ NetArgs a) {
+    constexpr int NC = R * 8, NT = NC + 32;
     extern __shared__ __align__(16) float smem[];
     __shared__ __align__(8) unsigned long long s_bar;
     __shared__ unsigned s_ticket;
     const NetDev &N = a.net;
     const int tid = threadIdx.x, lane = tid & 31;
-    const bool row_warp = tid >= NET_NC;
+    const bool row_warp = tid >= NC;
     const int T = a.T;
     const int row0 = blockIdx.x * R;
 
@@ -236,9 +300,8 @@ __global__ void __launch_bounds__(NET_NT, 1) net_kernel(const __grid_constant__ 
     float *wsm = smem;                              // [n_weights]
     float *hb = wsm + N.n_weights;                  // GRU: [2][htot][R]; Dense: [htot][R] activations
     const int hstride = N.htot * R;
-    float *xin = hb + 2 * hstride;                  // [2][n_in][R]
-    float *ybuf = xin + 2 * N.n_in * R;             // [n_out][R]
-    float *snorm = ybuf + 8 * R;                    // [n_out][R] (differential nets)
+    float *xin = hb + 2 * hstride;                  // [n_in][R]
+    float *snorm = xin + 8 * R;                     // [n_out][R] (differential nets: integrated normalised state)
     float *s_unom = snorm + 8 * R;                  // MPPI: [T] shifted nominal inputs, then [p] w0, [p] w1, scratch
     float *s_w0 = s_unom + (MPPI ? a.mp.T : 0);
     float *s_w1 = s_w0 + (MPPI ? a.mp.p : 0);
@@ -261,9 +324,9 @@ __global__ void __launch_bounds__(NET_NT, 1) net_kernel(const __grid_constant__ 
         }
     }
 
-    // ---- prologue: hidden state, first network input --------------------------------------------------------------
+    // ---- prologue: hidden state, MPPI tables ------------------------------------------------------------------------
     if (N.type == CPS_NET_GRU) {
-        for (int idx = tid; idx < N.htot * R; idx += NET_NT) {
+        for (int idx = tid; idx < N.htot * R; idx += NT) {
             const int j = idx / R, r = idx % R;
             const int b = min(row0 + r, a.B - 1);
             hb[idx] = a.h0[(long long)b * a.hs_b + j];
@@ -271,33 +334,21 @@ __global__ void __launch_bounds__(NET_NT, 1) net_kernel(const __grid_constant__ 
     }
     if (MPPI) {
         // warm-start shift at the START of the solve (optimizer_mppi.py:183)
-        for (int t = tid; t < T; t += NET_NT) s_unom[t] = a.u_nom[min(t + 1, T - 1)];
-        for (int j = tid; j < a.mp.p; j += NET_NT) {
+        for (int t = tid; t < T; t += NT) s_unom[t] = a.u_nom[min(t + 1, T - 1)];
+        for (int j = tid; j < a.mp.p; j += NT) {
             s_w0[j] = (float)(a.mp.p - j) / (float)a.mp.p;
             s_w1[j] = (float)j / (float)a.mp.p;
-        }
-    }
-    for (int idx = tid; idx < N.n_state_in * R; idx += NET_NT) {
-        const int i = idx / R, r = idx % R;
-        const int b = min(row0 + r, a.B - 1);
-        xin[(1 + i) * R + r] = fmaf(N.norm_a[1 + i], a.s0[(long long)b * a.ss_b + N.in_idx[i]], N.norm_b[1 + i]);
-    }
-    if (N.differential) {  // dmah.set_starting_point (autoregression.py:145-146)
-        for (int idx = tid; idx < N.n_out * R; idx += NET_NT) {
-            const int o = idx / R, r = idx % R;
-            const int b = min(row0 + r, a.B - 1);
-            snorm[idx] = fmaf(N.on_a[o], a.s0[(long long)b * a.ss_b + N.out_idx[o]], N.on_b[o]);
         }
     }
     __syncthreads();  // also publishes the mbarrier init
 
     // ---- row-warp state --------------------------------------------------------------------------------------
-    const int r_row = lane;                        // rollout handled by this lane of the row warp
-    const bool row_valid = row_warp && r_row < R;
+    const int r_row = lane % R;                    // rollout handled by this lane of the row warp
+    const bool row_lead = row_warp && lane < R;    // the lane that owns the rollout's bookkeeping
     const int k = row0 + r_row;
-    const bool active = row_valid && k < a.B;
+    const bool active = row_lead && k < a.B;
     const int kc = min(k, a.B - 1);
-    float Jacc = 0.0f, corr = 0.0f, up = a.u_prev, u_cur = 0.0f, du_cur = 0.0f;
+    float Jacc = 0.0f, corr = 0.0f, up = a.u_prev, u_cur = 0.0f, du_cur = 0.0f, u_nxt = 0.0f, du_nxt = 0.0f;
     int seg = 0, jj = 0;
     float na = 0.0f, nb = 0.0f;
     const float *nz = nullptr;
@@ -318,20 +369,17 @@ __global__ void __launch_bounds__(NET_NT, 1) net_kernel(const __grid_constant__ 
     auto next_control = [&](int t) {
         if (MPPI) {
             const MppiParams &mp = a.mp;
-            du_cur = (seg == mp.n_ind - 1) ? na * mp.inv_p : fmaf(na, s_w0[jj], nb * s_w1[jj]);
+            du_nxt = (seg == mp.n_ind - 1) ? na * mp.inv_p : fmaf(na, s_w0[jj], nb * s_w1[jj]);
             if (++jj == mp.p) {
                 jj = 0; ++seg; na = nb;
                 nb = (seg + 1 < mp.n_ind) ? nz[(long long)(seg + 1) * a.ns_i] * mp.sigma : 0.0f;
             }
-            u_cur = clampf(s_unom[t] + du_cur, mp.lo, mp.hi);
+            u_nxt = clampf(s_unom[t] + du_nxt, mp.lo, mp.hi);
         } else {
-            u_cur = qrow[(long long)t * a.qs_t];
+            u_nxt = qrow[(long long)t * a.qs_t];
         }
     };
-    if (row_valid) {
-        next_control(0);
-        xin[r_row] = fmaf(N.norm_a[0], u_cur, N.norm_b[0]);
-    }
+    if (row_warp) next_control(0);
     // all threads: wait for the weights
     {
         const unsigned bar = smem_u32(&s_bar);
@@ -345,74 +393,82 @@ __global__ void __launch_bounds__(NET_NT, 1) net_kernel(const __grid_constant__ 
 
     // ---- the horizon ------------------------------------------------------------------------------------------
     int p = 0;  // hidden-state buffer holding h(t-1)
-    float st[6];
+    float st[6], y[6];
+    const float *hlast_base = hb + N.hoff[N.n_layers - 1] * R;
 #pragma unroll 1
     for (int t = 0; t < T; ++t) {
-        float *x_cur = xin + (t & 1) * N.n_in * R;
-        float *x_nxt = xin + ((t + 1) & 1) * N.n_in * R;
         if (row_warp) {
-            if (row_valid) {
-                // state s_t: the initial state, or the previous step's network output
-                if (t == 0) {
+            // (1) this step's network input: control + state features (the initial state, or the previous output)
+            if (t == 0) {
 #pragma unroll
-                    for (int c = 0; c < 6; ++c) st[c] = a.s0[(long long)kc * a.ss_b + c];
-                } else {
-                    compose_state<R>(N, ybuf, r_row, st);
+                for (int c = 0; c < 6; ++c) st[c] = a.s0[(long long)kc * a.ss_b + c];
+                if (row_lead) {
+                    for (int i = 0; i < N.n_state_in; ++i)
+                        xin[(1 + i) * R + r_row] = fmaf(N.norm_a[1 + i], a.s0[(long long)kc * a.ss_b + N.in_idx[i]], N.norm_b[1 + i]);
+                    if (N.differential)  // dmah.set_starting_point (autoregression.py:145-146)
+                        for (int o = 0; o < N.n_out; ++o)
+                            snorm[o * R + r_row] = fmaf(N.on_a[o], a.s0[(long long)kc * a.ss_b + N.out_idx[o]], N.on_b[o]);
                 }
-                if (traj) {
+            } else {
+                out_layer_row<R>(N, wsm, hlast_base + (N.type == CPS_NET_GRU ? p * hstride : 0), lane, y);
+                if (row_lead) {
+                    if (N.differential) {  // autoregression.py:149-154
 #pragma unroll
-                    for (int c = 0; c < 6; ++c) traj[(long long)t * a.ts_t + c * a.ts_c] = st[c];
-                }
-                if (MPPI) {
-                    if (COST != COST_NONE) {
-                        float sc = stage_cost<COST>(a.cost, cosf(st[IDX_ANGLE]), st[IDX_ANGLED], st[IDX_POS], u_cur, up);
-                        if (COST == COST_DEFAULT || COST == COST_QB) sc -= a.cost.max_cost;
-                        Jacc += sc;
+                        for (int o = 0; o < 6; ++o) {
+                            if (o < N.n_out) {
+                                y[o] = snorm[o * R + r_row] + fmaf(N.p1[o], y[o], N.p2[o]);
+                                snorm[o * R + r_row] = y[o];
+                            }
+                        }
+                        for (int i = 0; i < N.n_state_in; ++i) xin[(1 + i) * R + r_row] = snorm[N.out_to_in[i] * R + r_row];
+                    } else {
+#pragma unroll
+                        for (int o = 0; o < 6; ++o)  // autoregression.py:94-98: the output is the next input
+                            if (o < N.n_state_in) xin[(1 + o) * R + r_row] = y[o];
                     }
-                    corr = fmaf(a.mp.cc_half_nu * du_cur, du_cur,
-                                fmaf(a.mp.cc_R * u_cur, du_cur, fmaf(a.mp.cc_half_R * u_cur, u_cur, corr)));
-                    if (a.u_run_out && active) a.u_run_out[(long long)k * T + t] = u_cur;
-                    up = u_cur;
-                }
-                if (t + 1 < T) {
-                    next_control(t + 1);
-                    x_nxt[r_row] = fmaf(N.norm_a[0], u_cur, N.norm_b[0]);
                 }
             }
+            u_cur = u_nxt; du_cur = du_nxt;
+            if (row_lead) xin[r_row] = fmaf(N.norm_a[0], u_cur, N.norm_b[0]);
             __syncthreads();
-            for (int l = 1; l < N.n_layers; ++l) __syncthreads();
-            __syncthreads();
+            // (2) behind the compute warps: state s_t -> trajectory row, stage cost, next control
+            if (t > 0) compose_state(N, y, st);
+            if (traj) {
+#pragma unroll
+                for (int c = 0; c < 6; ++c) traj[(long long)t * a.ts_t + c * a.ts_c] = st[c];
+            }
+            if (MPPI) {
+                Jacc += stage_cost_rt(a.cost_id, a.cost, cosf(st[IDX_ANGLE]), st[IDX_ANGLED], st[IDX_POS], u_cur, up);
+                corr = fmaf(a.mp.cc_half_nu * du_cur, du_cur,
+                            fmaf(a.mp.cc_R * u_cur, du_cur, fmaf(a.mp.cc_half_R * u_cur, u_cur, corr)));
+                if (a.u_run_out && active) a.u_run_out[(long long)k * T + t] = u_cur;
+                up = u_cur;
+            }
+            if (t + 1 < T) next_control(t + 1);
+            for (int l = 0; l < N.n_layers; ++l) __syncthreads();
         } else {
-            const float *in = x_cur;
-            int in_len = N.n_in;
-            for (int l = 0; l < N.n_layers; ++l) {
-                float *hl = hb + N.hoff[l] * R;
-                if (N.type == CPS_NET_GRU) {
-                    gru_layer<R>(N, wsm, l, in, in_len, hl + p * hstride, hl + (1 - p) * hstride, tid);
-                    in = hl + (1 - p) * hstride;
-                } else {
-                    dense_layer<R>(N, wsm, l, in, in_len, hl, tid);
-                    in = hl;
-                }
-                in_len = N.hsz[l];
-                __syncthreads();
-            }
-            out_layer<R>(N, wsm, in, ybuf, snorm, x_nxt, tid);
-            __syncthreads();
+            compute_step<R, HT>(N, wsm, hb, hstride, p, xin, tid);
         }
         p ^= 1;
     }
 
     // ---- last state, costs, hidden state out ---------------------------------------------------------------------
     float J = 0.0f;
-    if (row_valid) {
-        compose_state<R>(N, ybuf, r_row, st);
+    if (row_warp) {
+        out_layer_row<R>(N, wsm, hlast_base + (N.type == CPS_NET_GRU ? p * hstride : 0), lane, y);
+        if (N.differential && row_lead) {
+#pragma unroll
+            for (int o = 0; o < 6; ++o)
+                if (o < N.n_out) y[o] = snorm[o * R + r_row] + fmaf(N.p1[o], y[o], N.p2[o]);
+        }
+        compose_state(N, y, st);
         if (traj) {
 #pragma unroll
             for (int c = 0; c < 6; ++c) traj[(long long)T * a.ts_t + c * a.ts_c] = st[c];
         }
         if (MPPI) {
-            if (COST != COST_NONE) Jacc += terminal_cost<COST>(a.cost, st[IDX_ANGLE], st[IDX_POS]);
+            if (a.cost_id == CPS_COST_DEFAULT || a.cost_id == CPS_COST_QUADRATIC_BOUNDARY)
+                Jacc += terminal_cost<COST_DEFAULT>(a.cost, st[IDX_ANGLE], st[IDX_POS]);
             J = fmaf(Jacc, a.mp.inv_T1, corr);
             if (active) {
                 if (a.J_out) a.J_out[k] = J;
@@ -421,7 +477,7 @@ __global__ void __launch_bounds__(NET_NT, 1) net_kernel(const __grid_constant__ 
         }
     }
     if (a.h_final && N.type == CPS_NET_GRU) {
-        for (int idx = tid; idx < N.htot * R; idx += NET_NT) {
+        for (int idx = tid; idx < N.htot * R; idx += NT) {
             const int j = idx / R, r = idx % R;
             if (row0 + r < a.B) a.h_final[(long long)(row0 + r) * N.htot + j] = hb[p * hstride + idx];
         }
@@ -456,47 +512,43 @@ __global__ void __launch_bounds__(NET_NT, 1) net_kernel(const __grid_constant__ 
     // ---- advance the stored hidden state by one step on (u, s) (optimizer_mppi.py:191,194-196) --------------------
     __syncthreads();
     const float u_sel = __ldcg(a.u_out);
-    for (int idx = tid; idx < N.htot * R; idx += NET_NT) hb[idx] = a.h_ref[idx / R];
-    for (int idx = tid; idx < N.n_in * R; idx += NET_NT) {
+    for (int idx = tid; idx < N.htot * R; idx += NT) hb[idx] = a.h_ref[idx / R];
+    for (int idx = tid; idx < N.n_in * R; idx += NT) {
         const int i = idx / R;
         const float v = (i == 0) ? u_sel : a.s0[N.in_idx[i - 1]];
         xin[idx] = fmaf(N.norm_a[i], v, N.norm_b[i]);
     }
     __syncthreads();
-    {
-        const float *in = xin;
-        int in_len = N.n_in;
-        for (int l = 0; l < N.n_layers; ++l) {
-            float *hl = hb + N.hoff[l] * R;
-            if (!row_warp) gru_layer<R>(N, wsm, l, in, in_len, hl, hl + hstride, tid);
-            in = hl + hstride;
-            in_len = N.hsz[l];
-            __syncthreads();
-        }
+    if (row_warp) {
+        for (int l = 0; l <= N.n_layers; ++l) __syncthreads();
+    } else {
+        compute_step<R, HT>(N, wsm, hb, hstride, 0, xin, tid);
     }
-    for (int j = tid; j < N.htot; j += NET_NT) a.h_ref[j] = hb[hstride + j * R];
+    for (int j = tid; j < N.htot; j += NT) a.h_ref[j] = hb[hstride + j * R];
 }
 
 // =====================================================================================================
 // host side
 // =====================================================================================================
 static size_t net_smem_bytes(const NetDev &N, int R, bool mppi, const MppiParams *mp) {
-    size_t f = (size_t)N.n_weights + 2 * (size_t)N.htot * R + 2 * (size_t)N.n_in * R + 16 * (size_t)R;
+    size_t f = (size_t)N.n_weights + 2 * (size_t)N.htot * R + 16 * (size_t)R;
     if (mppi) f += (size_t)mp->T + 2 * (size_t)mp->p + (size_t)mp->n_red + 4;
     return f * sizeof(float);
 }
 
 typedef void (*net_fn)(const NetArgs);
 
-static net_fn pick_net(int cost, bool mppi) {
-    if (!mppi) return net_kernel<16, COST_NONE, false>;
-    switch (cost) {
-    case CPS_COST_DEFAULT: return net_kernel<16, COST_DEFAULT, true>;
-    case CPS_COST_QUADRATIC_BOUNDARY: return net_kernel<16, COST_QB, true>;
-    case CPS_COST_QB_GRAD_MINIMAL: return net_kernel<16, COST_GRADMIN, true>;
-    case CPS_COST_QB_GRAD: return net_kernel<16, COST_GRAD, true>;
-    default: return net_kernel<16, COST_NONE, true>;
+template <int R, bool MPPI>
+static net_fn pick_net2(int ht) {
+    switch (ht) {
+    case 64: return net_kernel<R, 64, MPPI>;
+    case 32: return net_kernel<R, 32, MPPI>;
+    default: return net_kernel<R, 0, MPPI>;
     }
+}
+static net_fn pick_net(int R, int ht, bool mppi) {
+    if (R == 32) return mppi ? pick_net2<32, true>(ht) : pick_net2<32, false>(ht);
+    return mppi ? pick_net2<16, true>(ht) : pick_net2<16, false>(ht);
 }
 
 void cps_net_free(cps_handle *h) {
@@ -593,6 +645,10 @@ extern "C" int cps_net_load(cps_handle *h, const cps_net_desc *d, const float *w
     N.htot = htot;
     N.n_weights = (int)img.size();
     const size_t smem = net_smem_bytes(N, 16, true, &h->mp);
+    int ht = N.hsz[0];
+    for (int l = 1; l < N.n_layers; ++l)
+        if (N.hsz[l] != ht) ht = 0;
+    if (ht != 64 && ht != 32) ht = 0;
     if (smem > 227 * 1024)
         return fail(h, CPS_ERR_UNSUPPORTED, "cps_net_load: the network needs %zu bytes of shared memory per CTA (limit 227 KB); "
                     "larger networks are not supported by this build", smem);
@@ -600,8 +656,7 @@ extern "C" int cps_net_load(cps_handle *h, const cps_net_desc *d, const float *w
     cps_net_free(h);
     NetState *S = new (std::nothrow) NetState();
     if (!S) return fail(h, CPS_ERR_INVALID, "cps_net_load: out of host memory");
-    S->dev = N; S->d_weights = nullptr; S->d_href = nullptr; S->smem_weights = img.size() * sizeof(float);
-    S->weights_in_smem = true;
+    S->dev = N; S->d_weights = nullptr; S->d_href = nullptr; S->ht = ht;
     h->net = S;
     CUDA_TRY(h, cudaMalloc(&S->d_weights, img.size() * sizeof(float)));
     CUDA_TRY(h, cudaMalloc(&S->d_href, sizeof(float) * (size_t)(htot > 0 ? htot : 1)));
@@ -614,12 +669,14 @@ static int net_launch(cps_handle *h, NetArgs &a, bool mppi, int n_rows) {
     NetState *S = h->net;
     a.net = S->dev;
     a.weights = S->d_weights;
-    const int R = 16;
+    // small batches: 16 rollouts per CTA spread the work over more SMs; large ones: 32 (two warps per scheduler)
+    int R = (n_rows > 148 * 16 && !mppi) ? 32 : 16;
+    if (net_smem_bytes(S->dev, R, mppi, &h->mp) > 227 * 1024) R = 16;
     const size_t smem = net_smem_bytes(S->dev, R, mppi, &h->mp);
-    net_fn fn = pick_net(h->cfg.cost_id, mppi);
+    net_fn fn = pick_net(R, S->ht, mppi);
     CUDA_TRY(h, cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = (n_rows + R - 1) / R;
-    fn<<<grid, NET_NT, smem, h->stream>>>(a);
+    fn<<<grid, R * 8 + 32, smem, h->stream>>>(a);
     h->launches += 1;
     CUDA_TRY(h, cudaGetLastError());
     return CPS_OK;
@@ -708,7 +765,7 @@ int cps_net_mppi_step(cps_handle *h, const float *s_dev, const float *noise_dev,
     a.traj_out = traj_out_dev;
     if (traj_layout == CPS_TIME_MAJOR) { a.ts_k = 1; a.ts_t = 6LL * K; a.ts_c = K; }
     else { a.ts_k = (T + 1) * 6LL; a.ts_t = 6; a.ts_c = 1; }
-    a.cost = h->cost; a.mp = h->mp;
+    a.cost_id = h->cfg.cost_id; a.cost = h->cost; a.mp = h->mp;
     a.noise = noise_dev;
     if (noise_layout == CPS_TIME_MAJOR) { a.ns_i = K; a.ns_k = 1; } else { a.ns_i = 1; a.ns_k = h->n_red; }
     a.u_prev = u_prev;

@@ -86,7 +86,11 @@ def test_net_rollout_vs_oracle_sizes(name, B, T):
     ref, href = O.net_rollout(*oracle_args(sp), s0, Q, h0=h0, want_h=True)
     traj, hf = eng.net_rollout(torch.from_numpy(s0).to(dev), torch.from_numpy(Q).to(dev), h0=torch.from_numpy(h0).to(dev),
                                want_h=True)
-    assert max(traj_err(traj.cpu().numpy(), ref).values()) < 1e-5
+    e = traj_err(traj.cpu().numpy(), ref)
+    # angle = atan2(sin, cos) of un-normalised network outputs: ill-conditioned where |(sin, cos)| is small, so the
+    # angle channel amplifies the 1e-7 differences of the other channels by 1/|(sin, cos)|
+    assert e.pop("angle") < 1e-4
+    assert max(e.values()) < 2e-6, e
     assert np.abs(hf.cpu().numpy() - href).max() < 5e-6
 
 
