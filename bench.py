@@ -99,18 +99,17 @@ def make_inputs(B, T, seed):
 def cpu_port_rate(B_sample, T, threads=None, repeats=1, seed=0):
     """state-steps/s of the oracle port (cps_oracle_rollout_v0, OpenMP) on this host."""
     from oracle import oracle as O
-    if threads:
-        O.lib().cps_oracle_set_num_threads(int(threads))
+    # all host cores unless told otherwise (torchrun exports OMP_NUM_THREADS=1, which is not what a CPU baseline wants)
+    O.lib().cps_oracle_set_num_threads(int(threads) if threads else (os.cpu_count() or 1))
     s0, Q = make_inputs(B_sample, T, seed)
     Qr = np.ascontiguousarray(Q.T)
     O.rollout("ODE_v0", s0[:64], Qr[:64], n=N_SUB, dt=DT)  # warm up (thread pool, page faults)
-    best = None
+    total = 0.0
     for _ in range(repeats):
         t0 = time.perf_counter()
         O.rollout("ODE_v0", s0, Qr, n=N_SUB, dt=DT)
-        dt_ = time.perf_counter() - t0
-        best = dt_ if best is None else min(best, dt_)
-    return B_sample * T * N_SUB / best, best, O.lib().cps_oracle_num_threads()
+        total += time.perf_counter() - t0
+    return B_sample * T * N_SUB * repeats / total, total, O.lib().cps_oracle_num_threads()
 
 
 def run_reference(args):
@@ -190,7 +189,104 @@ def mppi_latency(device, n_calls=1000):
                      "kernel_ms_median": float(np.median(ks)), "calls": n_calls,
                      "state_steps_per_solve": K * T * N_SUB}
     out["config"] = "K=2000, T=50, n=10, cost quadratic_boundary_grad_minimal, optimizer_mppi_b200.step(numpy s) -> numpy u"
+    out["neural_GRU_2x64"] = neural_latency(device, n_calls=min(n_calls, 300))
+    out["ODE_K65536_T100"] = big_solve(device)
     return out
+
+
+def _event_times(fn, n, warm=5):
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(n):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        e1.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return ts
+
+
+def neural_latency(device, n_calls=300):
+    """BASELINE.json configs[2]: MPPI + autoregressive GRU (2x64 hidden), K=2000, T=50; synthetic seeded weights (no
+    dynamics model ships with the reference).  One launch per solve: rollout + cost + update + hidden-state step."""
+    import torch
+    from cartpolesimulation_b200.core import Engine
+    from cartpolesimulation_b200.neural import net_flops_per_step, synthetic_net_spec
+    K, T = 2000, 50
+    spec = synthetic_net_spec((64, 64), "GRU", seed=0)
+    eng = Engine(K, T, integrator="neural", cost="quadratic_boundary_grad_minimal", device=device)
+    eng.net_load(spec)
+    a = np.pi - 1e-3
+    s_np = np.array([a, 0.0, np.cos(a), np.sin(a), 0.0, 0.0], dtype=np.float32)
+    s = torch.from_numpy(s_np).to(eng.device)
+    noise = torch.randn((eng.n_ind, K), device=eng.device)
+    ks = _event_times(lambda: eng.mppi_step(s, noise, 1, 0.0), 50)
+    lat = np.empty(n_calls)
+    for i in range(n_calls):
+        t0 = time.perf_counter()
+        eng.mppi_step_host(s_np, noise, 1, 0.0)
+        lat[i] = time.perf_counter() - t0
+    flops = net_flops_per_step(spec) * K * T
+    kms = float(np.median(ks))
+    out = {"latency_ms_median": float(np.median(lat) * 1e3), "latency_ms_p99": float(np.percentile(lat, 99) * 1e3),
+           "kernel_ms_median": kms, "net_steps_per_s": K * T / (kms * 1e-3), "fp32_tflops": flops / (kms * 1e-3) / 1e12,
+           "flop_per_solve": flops, "api": "cps_mppi_step_host (numpy s -> float u), net_kernel<16,64,MPPI>"}
+    try:  # the same solve by the CPU oracle port (C, OpenMP), once, on the host cores
+        from oracle import oracle as O
+        eps = noise.t().contiguous().cpu().numpy()
+        args = (spec["net_type"], spec["hsz"], spec["weights"], spec["in_idx"], spec["out_idx"], spec["norm_a"],
+                spec["norm_b"], spec["denorm_A"], spec["denorm_B"])
+        O.lib().cps_oracle_set_num_threads(os.cpu_count() or 1)
+        O.mppi_step_net("quadratic_boundary_grad_minimal", *args, s_np, np.zeros(T, np.float32), eps[:64])
+        t0 = time.perf_counter()
+        O.mppi_step_net("quadratic_boundary_grad_minimal", *args, s_np, np.zeros(T, np.float32), eps)
+        out["cpu_port_ms"] = (time.perf_counter() - t0) * 1e3
+        out["cpu_port_threads"] = O.lib().cps_oracle_num_threads()
+    except Exception as ex:
+        out["cpu_port_ms"] = repr(ex)
+    return out
+
+
+def big_solve(device):
+    """BASELINE.json configs[3]: MPPI K=65536, T=100, fused quadratic+barrier cost (quadratic_boundary), one GPU."""
+    import torch
+    from cartpolesimulation_b200.core import Engine
+    K, T = 65536, 100
+    out = {}
+    for cost in ("quadratic_boundary", "quadratic_boundary_grad_minimal"):
+        eng = Engine(K, T, integrator="ODE", cost=cost, device=device)
+        a = np.pi - 1e-3
+        s = torch.tensor([a, 0.0, np.cos(a), np.sin(a), 0.0, 0.0], device=eng.device, dtype=torch.float32)
+        noise = torch.randn((eng.n_ind, K), device=eng.device)
+        ks = _event_times(lambda: eng.mppi_step(s, noise, 1, 0.0), 30)
+        kms = float(np.median(ks))
+        out[cost] = {"kernel_ms_median": kms, "state_steps_per_s": K * T * N_SUB / (kms * 1e-3)}
+        eng.close()
+    return out
+
+
+def sharded_solve(local_rank, world, n=30):
+    """configs[3] with K sharded over the ranks: local rollouts + ONE all-gather of n_ind+2 floats per rank (NCCL) +
+    merge.  Device time of the slowest rank."""
+    import torch
+    import torch.distributed as dist
+    from cartpolesimulation_b200.distributed import ShardedMPPI
+    K, T = 65536, 100
+    sm = ShardedMPPI(K, T, integrator="ODE", cost="quadratic_boundary", device=local_rank)
+    a = np.pi - 1e-3
+    s = torch.tensor([a, 0.0, np.cos(a), np.sin(a), 0.0, 0.0], device=sm.device, dtype=torch.float32)
+    noise = torch.randn((sm.engine.n_ind, sm.K_local), device=sm.device)
+    ks = _event_times(lambda: sm.step(s, noise, 1, 0.0), n)
+    t = torch.tensor([float(np.median(ks))], device=sm.device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    kms = float(t.item())
+    return {"K_total": K, "T": T, "ranks": world, "solve_ms_median_max_over_ranks": kms,
+            "state_steps_per_s": K * T * N_SUB / (kms * 1e-3), "exchange_bytes_per_rank": 4 * sm.rec}
 
 
 def run_ours(args):
@@ -207,6 +303,10 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # stdout carries exactly ONE JSON line: NCCL's banner ("NCCL version ...") goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     B, T = args.batch, args.horizon
     eng = Engine(B, T, dt=DT, substeps=N_SUB, integrator="ODE_v0", cost=None, device=local_rank,
@@ -244,8 +344,6 @@ def run_ours(args):
     launches = eng.launch_count() - launches0
     total_ms = t_all0.elapsed_time(t_all1)
     kern_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
-    sampler.stop_flag = True
-    sampler.join(timeout=1.0)
     if world > 1:
         t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -270,10 +368,18 @@ def run_ours(args):
         t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
+    sampler.stop_flag = True   # the clock record covers both timed regions (device-resident and e2e)
+    sampler.join(timeout=1.0)
     e2e_value = steps_per_pass * e2e_steps * world / e2e_s
     h2d = s0_pin.numel() * 4 + Q_pin.numel() * 4
     d2h = traj_pin.numel() * 4
 
+    sharded = None
+    if world > 1 and not args.no_mppi:
+        try:
+            sharded = sharded_solve(local_rank, world)
+        except Exception as ex:
+            sharded = {"error": repr(ex)}
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -309,9 +415,10 @@ def run_ours(args):
     # ---- cpu baseline: oracle port on a bounded sample ---------------------------------------------------------
     rate0, _, threads = cpu_port_rate(4096, T)
     B_sample = int(min(B, max(4096, rate0 * 10.0 / (T * N_SUB))))   # ~10 s of CPU work
-    cpu_rate, cpu_s, threads = cpu_port_rate(B_sample, T)
+    reps = max(1, int(round(10.0 * rate0 / (B_sample * T * N_SUB))))
+    cpu_rate, cpu_s, threads = cpu_port_rate(B_sample, T, repeats=reps)
     cpu_baseline = {"value": cpu_rate, "unit": UNIT, "cores": threads, "kind": "port",
-                    "sample": f"{B_sample} of {B} cartpoles x {T * N_SUB} substeps, {cpu_s:.1f} s",
+                    "sample": f"{reps} x ({B_sample} of {B} cartpoles x {T * N_SUB} substeps), {cpu_s:.1f} s of CPU work",
                     "host_cores": os.cpu_count()}
 
     mppi = None
@@ -331,7 +438,7 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * e2e_s / e2e_steps, "api": "cps_rollout_host (pinned host buffers)"},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
-            "clocks": sampler.summary(), "mppi_solve": mppi}
+            "clocks": sampler.summary(), "mppi_solve": mppi, "mppi_sharded": sharded}
     print(json.dumps(line))
     if world > 1:
         dist.barrier()

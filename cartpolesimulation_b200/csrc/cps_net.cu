@@ -670,7 +670,7 @@ static int net_launch(cps_handle *h, NetArgs &a, bool mppi, int n_rows) {
     a.net = S->dev;
     a.weights = S->d_weights;
     // small batches: 16 rollouts per CTA spread the work over more SMs; large ones: 32 (two warps per scheduler)
-    int R = (n_rows > 148 * 16 && !mppi) ? 32 : 16;
+    int R = (n_rows > 148 * 16) ? 32 : 16;
     if (net_smem_bytes(S->dev, R, mppi, &h->mp) > 227 * 1024) R = 16;
     const size_t smem = net_smem_bytes(S->dev, R, mppi, &h->mp);
     net_fn fn = pick_net(R, S->ht, mppi);

@@ -1,0 +1,87 @@
+"""Multi-GPU forms of the path, one process per GPU over torch.distributed.
+
+  ShardedMPPI        ONE MPPI solve with its K rollouts partitioned over the ranks.  Every rank rolls out its
+                     contiguous slice of rollouts (its own slice of the noise draws; s, u_nom and the scalars are
+                     replicated) and reduces it to a partial record (min J, sum w, sum w*eps[.]) = n_ind + 2 floats
+                     (cps_mppi_set_shard).  The only exchange is one all-gather of those records
+                     (32 B per rank at n_ind = 6; NCCL over NVLink on GPUs); every rank then merges them with
+                     the online-softmax rule (cps_mppi_finalize) and holds the identical u_nom / u.
+  replica_slice      independent experiments / open-loop batches: plain partition, no collective at all.
+
+The reference has no counterpart: it parallelises by running one process per experiment on a SLURM array
+(others/EulerClusterScripts/ParallelDataGeneration.sh).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n: int, world: int, rank: int) -> tuple[int, int]:
+    """Contiguous partition of n items over `world` ranks; the first n % world ranks get one more."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError(f"bad rank {rank} of {world}")
+    base, rem = divmod(int(n), world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def replica_slice(n: int, group=None) -> tuple[int, int]:
+    """This rank's share of n independent units (experiments, cartpoles of an open-loop batch)."""
+    if dist.is_available() and dist.is_initialized():
+        return shard_bounds(n, dist.get_world_size(group), dist.get_rank(group))
+    return 0, int(n)
+
+
+class ShardedMPPI:
+    """One MPPI solve over K_total rollouts sharded across the ranks of `group`.
+
+    engine_factory(K_local) must return an object with the Engine methods used here (mppi_step, set_shard,
+    partial_size, mppi_finalize, n_ind, device, and for recurrent predictors net_update / net_htot); the default
+    builds a cartpolesimulation_b200.core.Engine from **engine_kwargs.
+    """
+
+    def __init__(self, num_rollouts: int, horizon: int, group=None, engine_factory=None, **engine_kwargs):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.K_total, self.T = int(num_rollouts), int(horizon)
+        if self.K_total < self.world:
+            raise ValueError(f"cannot shard {self.K_total} rollouts over {self.world} ranks")
+        self.lo, self.hi = shard_bounds(self.K_total, self.world, self.rank)
+        self.K_local = self.hi - self.lo
+        if engine_factory is None:
+            from .core import Engine
+            engine_factory = lambda k: Engine(num_rollouts=k, horizon=self.T, **engine_kwargs)
+        self.engine = engine_factory(self.K_local)
+        self.device = self.engine.device
+        self.rec = int(self.engine.partial_size())
+        self._partial = torch.zeros(self.rec, device=self.device, dtype=torch.float32)
+        self._gathered = torch.zeros(self.world * self.rec, device=self.device, dtype=torch.float32)
+        self.engine.set_shard(self._partial)
+        self.recurrent = bool(getattr(self.engine, "net_htot", 0))
+
+    def noise_slice(self, noise_full: torch.Tensor, time_major: bool = True) -> torch.Tensor:
+        """This rank's rollouts of a full noise tensor ([n_ind, K_total] time-major, or [K_total, n_ind])."""
+        part = noise_full[:, self.lo:self.hi] if time_major else noise_full[self.lo:self.hi]
+        return part.contiguous()
+
+    def step(self, s: torch.Tensor, noise_local: torch.Tensor, noise_layout: int = 1, u_prev: float = 0.0) -> torch.Tensor:
+        """s: device tensor [6] (identical on all ranks); noise_local: this rank's draws.  Returns the device tensor
+        [1] holding u -- identical on every rank.  No host synchronisation."""
+        self.engine.mppi_step(s, noise_local, noise_layout, u_prev)   # -> self._partial (stream-ordered)
+        if self.world > 1:
+            dist.all_gather_into_tensor(self._gathered, self._partial, group=self.group)
+        else:
+            self._gathered.copy_(self._partial)
+        u = self.engine.mppi_finalize(self._gathered)
+        if self.recurrent:  # the fused kernel skips the hidden-state update when K is sharded (u is not known yet)
+            self.engine.net_update(s, u)
+        return u
+
+    def get_u_nom(self) -> np.ndarray:
+        return self.engine.get_u_nom()
+
+    def reset(self, value: float = 0.0):
+        self.engine.mppi_reset(value)

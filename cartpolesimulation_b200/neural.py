@@ -174,6 +174,48 @@ def build_net_spec(net_type, inputs, outputs, hsz, weights, norm=None, dt=None):
     return spec
 
 
+# value ranges of the reference's shipped normalisation table
+# (GymlikeCartPole/Dense-7IN-32H1-32H2-1OUT-0/NI_2024-08-17_22-23-01.csv)
+DEFAULT_RANGES = {"Q": (1.0, -1.0), "angle": (np.pi, -np.pi), "angleD": (18.38, -18.38), "angle_cos": (1.0, -1.0),
+                  "angle_sin": (1.0, -1.0), "position": (0.198, -0.198), "positionD": (1.125, -1.125)}
+
+
+def synthetic_net_spec(hsz=(64, 64), net_type="GRU", seed=0):
+    """A randomly initialised network of the architecture the reference's configs name (GRU-6IN-<H1>-<H2>-5OUT,
+    config_predictors.yml:10,32): no dynamics model ships with the reference, so benchmarks and smoke tests use seeded
+    weights with torch's default GRUCell / Linear initialisation U(-1/sqrt(H), 1/sqrt(H))."""
+    inputs = ["Q", "angleD", "angle_cos", "angle_sin", "position", "positionD"]
+    outputs = inputs[1:]
+    rng = np.random.default_rng(seed)
+    parts, n_in = [], len(inputs)
+    G = 3 if net_type == "GRU" else 1
+    for H in hsz:
+        k = 1.0 / np.sqrt(H)
+        parts.append(rng.uniform(-k, k, (G * H, n_in)))
+        if net_type == "GRU":
+            parts += [rng.uniform(-k, k, (3 * H, H)), rng.uniform(-k, k, 3 * H), rng.uniform(-k, k, 3 * H)]
+        else:
+            parts.append(rng.uniform(-k, k, H))
+        n_in = H
+    k = 1.0 / np.sqrt(n_in)
+    parts += [rng.uniform(-k, k, (len(outputs), n_in)), rng.uniform(-k, k, len(outputs))]
+    w = np.concatenate([q.reshape(-1) for q in parts]).astype(np.float32)
+    cols = list(DEFAULT_RANGES)
+    table = np.array([[0.0] * len(cols), [1.0] * len(cols), [DEFAULT_RANGES[c][0] for c in cols],
+                      [DEFAULT_RANGES[c][1] for c in cols]])
+    return build_net_spec(net_type, inputs, outputs, list(hsz), w, (cols, table))
+
+
+def net_flops_per_step(spec) -> int:
+    """FLOPs of one network step for one rollout (multiply-add = 2)."""
+    G = 3 if spec["net_type"] == "GRU" else 1
+    f, i = 0, 1 + len(spec["in_idx"])
+    for H in spec["hsz"]:
+        f += 2 * G * H * (i + (H if G == 3 else 0))
+        i = H
+    return f + 2 * len(spec["out_idx"]) * i
+
+
 def load_model(model_name, path_to_model=None, dt=None):
     """(spec, net_info) of a stored network: <path_to_models>/<net_name>/{<net_name>.txt, ckpt.pt | <net_name>.pt, NI csv}."""
     model_name = os.path.normpath(model_name)

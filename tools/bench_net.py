@@ -12,39 +12,7 @@ import torch
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
 
-NORM = {"Q": (1.0, -1.0), "angle": (np.pi, -np.pi), "angleD": (18.38, -18.38), "angle_cos": (1.0, -1.0),
-        "angle_sin": (1.0, -1.0), "position": (0.198, -0.198), "positionD": (1.125, -1.125)}
-INPUTS = ["Q", "angleD", "angle_cos", "angle_sin", "position", "positionD"]
-OUTPUTS = INPUTS[1:]
-
-
-def synthetic_spec(hsz=(64, 64), net_type="GRU", seed=0):
-    from cartpolesimulation_b200.neural import build_net_spec
-    rng = np.random.default_rng(seed)
-    parts, n_in = [], len(INPUTS)
-    G = 3 if net_type == "GRU" else 1
-    for H in hsz:
-        k = 1.0 / np.sqrt(H)
-        parts.append(rng.uniform(-k, k, (G * H, n_in)))
-        if net_type == "GRU":
-            parts += [rng.uniform(-k, k, (3 * H, H)), rng.uniform(-k, k, 3 * H), rng.uniform(-k, k, 3 * H)]
-        else:
-            parts.append(rng.uniform(-k, k, H))
-        n_in = H
-    k = 1.0 / np.sqrt(n_in)
-    parts += [rng.uniform(-k, k, (len(OUTPUTS), n_in)), rng.uniform(-k, k, len(OUTPUTS))]
-    w = np.concatenate([p.reshape(-1) for p in parts]).astype(np.float32)
-    cols = list(NORM)
-    table = np.array([[0.0] * len(cols), [1.0] * len(cols), [NORM[c][0] for c in cols], [NORM[c][1] for c in cols]])
-    return build_net_spec(net_type, INPUTS, OUTPUTS, list(hsz), w, (cols, table))
-
-
-def flops_per_step(hsz, n_in=6, n_out=5, G=3):
-    f, i = 0, n_in
-    for H in hsz:
-        f += 2 * G * H * (i + (H if G == 3 else 0))
-        i = H
-    return f + 2 * n_out * i
+from cartpolesimulation_b200.neural import net_flops_per_step, synthetic_net_spec
 
 
 def main():
@@ -54,7 +22,7 @@ def main():
     ap.add_argument("--iters", type=int, default=50)
     args = ap.parse_args()
     from cartpolesimulation_b200.core import Engine
-    spec = synthetic_spec()
+    spec = synthetic_net_spec()
     K, T = args.K, args.T
     eng = Engine(K, T, integrator="neural", cost="quadratic_boundary_grad_minimal", device=0)
     eng.net_load(spec)
@@ -74,7 +42,7 @@ def main():
         e1.synchronize()
         ts.append(e0.elapsed_time(e1))
     ms = float(np.median(ts))
-    fl = flops_per_step((64, 64)) * K * T
+    fl = net_flops_per_step(spec) * K * T
     print(f"neural MPPI solve K={K} T={T} GRU 2x64: kernel {ms * 1e3:.1f} us median, {K * T / ms * 1e3:.3e} net-steps/s, "
           f"{fl / ms / 1e9:.2f} TFLOP/s fp32 ({fl / 1e9:.2f} GFLOP per solve)")
     # host-to-host latency through step_host
