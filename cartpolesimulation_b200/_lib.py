@@ -23,6 +23,7 @@ COST_NONE, COST_DEFAULT, COST_QUADRATIC_BOUNDARY, COST_QB_GRAD_MINIMAL, COST_QB_
 NOISE_INDUCING, NOISE_DIRECT = 0, 1
 ROLLOUT_MAJOR, TIME_MAJOR = 0, 1
 FLAG_FAST_SINCOS, FLAG_EXACT_ATAN2, FLAG_FAST_DIV, FLAG_SUBSTEP_SINCOS = 0x1, 0x2, 0x4, 0x8
+FLAG_NET_TENSOR_CORES, FLAG_NET_FP32 = 0x10, 0x20
 PH_COUNT = 9
 
 

@@ -46,7 +46,7 @@ class Engine:
                  integrator: str = "ODE", cost: str | None = "quadratic_boundary_grad_minimal",
                  noise_mode: str = "inducing", interp_period: int = 10, device: int | None = None,
                  fast_sincos: bool = False, exact_atan2: bool = False, fast_div: bool = False,
-                 substep_sincos: bool = False):
+                 substep_sincos: bool = False, net_kernel: str | None = None):
         if integrator not in INTEGRATORS:
             raise ValueError(f"unknown integrator {integrator!r}; expected one of {list(INTEGRATORS)}")
         if cost not in COSTS:
@@ -60,6 +60,9 @@ class Engine:
             substep_sincos = True  # both only make sense when sin/cos are evaluated every substep
         flags = (L.FLAG_FAST_SINCOS if fast_sincos else 0) | (L.FLAG_EXACT_ATAN2 if exact_atan2 else 0) \
             | (L.FLAG_FAST_DIV if fast_div else 0) | (L.FLAG_SUBSTEP_SINCOS if substep_sincos else 0)
+        if net_kernel not in (None, "tensor", "fp32"):
+            raise ValueError("net_kernel must be None (choose by batch size), 'tensor' or 'fp32'")
+        flags |= {None: 0, "tensor": L.FLAG_NET_TENSOR_CORES, "fp32": L.FLAG_NET_FP32}[net_kernel]
         self.K, self.T, self.n, self.dt, self.p = int(num_rollouts), int(horizon), int(substeps), float(dt), int(interp_period)
         self.integrator, self.cost_name = integrator, cost
         self.noise_mode = {"inducing": L.NOISE_INDUCING, "direct": L.NOISE_DIRECT}[noise_mode]

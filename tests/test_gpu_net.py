@@ -26,9 +26,9 @@ def oracle_args(sp):
             sp["out_idx"], sp["norm_a"], sp["norm_b"], sp["denorm_A"], sp["denorm_B"])
 
 
-def make_engine(sp, K, T, cost=None):
+def make_engine(sp, K, T, cost=None, net_kernel=None):
     from cartpolesimulation_b200.core import Engine
-    eng = Engine(K, T, integrator="neural", cost=cost, device=0)
+    eng = Engine(K, T, integrator="neural", cost=cost, device=0, net_kernel=net_kernel)
     eng.net_load(engine_spec(sp))
     return eng
 
@@ -173,3 +173,119 @@ def test_net_errors():
     bad["net_type"] = "LSTM"
     with pytest.raises(NotImplementedError):
         eng.net_load(bad)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# tensor-core kernel (tcgen05, fp16 hi/lo split operands, fp32 accumulation in tensor memory): same tolerances
+# ------------------------------------------------------------------------------------------------------------
+TC_NET = "net_GRU_6IN_64H1_64H2_5OUT_0"
+
+
+def test_tc_rollout_vs_reference_golden():
+    import torch
+    z, m = load_golden(TC_NET)
+    sp = net_spec_from_golden(z)
+    K, T = z["Q"].shape
+    eng = make_engine(sp, K, T, net_kernel="tensor")
+    dev = eng.device
+    Q = torch.from_numpy(z["Q"]).to(dev)
+    traj, _ = eng.net_rollout(torch.from_numpy(z["s0"]).to(dev), Q)
+    e = traj_err(traj.cpu().numpy(), z["traj_zero_h"])
+    assert max(e.values()) < 1e-5, e
+    e1 = max(traj_err(traj.cpu().numpy()[:, :2], z["traj_zero_h"][:, :2]).values())
+    assert e1 < 2e-6, e1
+    for s, q in zip(z["upd_s"], z["upd_q"]):
+        eng.net_update(torch.from_numpy(s).to(dev), torch.tensor([q], device=dev))
+    assert np.abs(eng.net_get_state() - z["h_after_updates"].reshape(-1)).max() < 2e-6
+    traj2, _ = eng.net_rollout(torch.from_numpy(z["s_after"]).to(dev), Q)
+    assert max(traj_err(traj2.cpu().numpy(), z["traj_after_updates"]).values()) < 1e-5
+    traj3, hf = eng.net_rollout(torch.from_numpy(z["s_rand"]).to(dev), Q.t().contiguous(), q_layout=1, traj_layout=1,
+                                want_h=True)
+    assert max(traj_err(traj3.permute(2, 0, 1).cpu().numpy(), z["traj_rand"]).values()) < 1e-5
+
+
+@pytest.mark.parametrize("B,T", [(1, 1), (129, 3), (2000, 50), (20000, 10)])
+def test_tc_rollout_vs_oracle_sizes(B, T):
+    import torch
+    from oracle import oracle as O
+    z, m = load_golden(TC_NET)
+    sp = net_spec_from_golden(z)
+    eng = make_engine(sp, B, T, net_kernel="tensor")
+    dev = eng.device
+    rng = np.random.default_rng(B * 100 + T)
+    ang = rng.uniform(-np.pi, np.pi, B)
+    s0 = np.stack([ang, rng.uniform(-3, 3, B), np.cos(ang), np.sin(ang), rng.uniform(-0.15, 0.15, B),
+                   rng.uniform(-0.5, 0.5, B)], 1).astype(np.float32)
+    Q = rng.uniform(-1, 1, (B, T)).astype(np.float32)
+    h0 = rng.uniform(-0.5, 0.5, (B, sum(sp["hsz"]))).astype(np.float32)
+    ref, href = O.net_rollout(*oracle_args(sp), s0, Q, h0=h0, want_h=True)
+    traj, hf = eng.net_rollout(torch.from_numpy(s0).to(dev), torch.from_numpy(Q).to(dev), h0=torch.from_numpy(h0).to(dev),
+                               want_h=True)
+    e = traj_err(traj.cpu().numpy(), ref)
+    assert e.pop("angle") < 1e-4     # atan2 of small-norm outputs, see test_net_rollout_vs_oracle_sizes
+    assert max(e.values()) < 3e-6, e
+    assert np.abs(hf.cpu().numpy() - href).max() < 5e-6
+
+
+def test_tc_mppi_vs_reference_golden():
+    import torch
+    from cartpolesimulation_b200 import _lib as L
+    z, m = load_golden("mppi_net_gru64_gradmin")
+    sp = net_spec_from_golden(z)
+    K, T = m["K"], m["T"]
+    eng = make_engine(sp, K, T, cost=m["cost"], net_kernel="tensor")
+    dev = eng.device
+    J = torch.empty(K, device=dev)
+    traj = torch.empty((K, T + 1, 6), device=dev)
+    u_run = torch.empty((K, T), device=dev)
+    u_nom = np.zeros(T, dtype=np.float32)
+    h = np.zeros(sum(sp["hsz"]), np.float32)
+    for i in range(m["steps"]):
+        eng.set_u_nom(u_nom)
+        eng.net_set_state(h)
+        eps = torch.from_numpy(z["eps"][i]).to(dev)
+        u = eng.mppi_step(torch.from_numpy(z["s"][i]).to(dev), eps, L.ROLLOUT_MAJOR, float(z["u_prev"][i]), None, J, traj,
+                          L.ROLLOUT_MAJOR, u_run)
+        torch.cuda.synchronize()
+        if i == 0:
+            np.testing.assert_allclose(u_run.cpu().numpy(), z["u_run0"], rtol=0, atol=2e-7)
+            assert max(traj_err(traj.cpu().numpy()[:32], z["traj0"]).values()) < 1e-5
+        assert vec_err(J.cpu().numpy(), z["J"][i]) < 1e-5
+        assert abs(float(u.cpu()[0]) - float(z["u"][i])) < 1e-4
+        np.testing.assert_allclose(eng.get_u_nom(), z["u_nom"][i], rtol=0, atol=1e-4)
+        assert np.abs(eng.net_get_state() - z["h_after"][i]).max() < 5e-6
+        h = z["h_after"][i].copy()
+        u_nom = z["u_nom"][i].copy()
+    assert eng.nonfinite_costs() == 0
+
+
+def test_tc_matches_fp32_kernel_K65536():
+    """full-size property: both kernels, same inputs -> same costs and control (K = 65536, T = 50)."""
+    import torch
+    from cartpolesimulation_b200 import _lib as L
+    z, m = load_golden("mppi_net_gru64_gradmin")
+    sp = net_spec_from_golden(z)
+    K, T = 65536, 50
+    out = {}
+    rng = np.random.default_rng(1)
+    for kern in ("fp32", "tensor"):
+        eng = make_engine(sp, K, T, cost="quadratic_boundary_grad_minimal", net_kernel=kern)
+        if kern == "fp32":
+            noise = torch.from_numpy(rng.standard_normal((eng.n_ind, K)).astype(np.float32)).to(eng.device)
+        J = torch.empty(K, device=eng.device)
+        u = eng.mppi_step(torch.from_numpy(z["s"][1]).to(eng.device), noise, L.TIME_MAJOR, 0.0, None, J)
+        out[kern] = (float(u.cpu()[0]), J.cpu().numpy(), eng.get_u_nom(), eng.net_get_state())
+        assert eng.nonfinite_costs() == 0
+    assert vec_err(out["tensor"][1], out["fp32"][1]) < 1e-5
+    assert abs(out["tensor"][0] - out["fp32"][0]) < 1e-5
+    np.testing.assert_allclose(out["tensor"][2], out["fp32"][2], rtol=0, atol=1e-5)
+    np.testing.assert_allclose(out["tensor"][3], out["fp32"][3], rtol=0, atol=5e-6)
+
+
+def test_tc_flag_rejected_for_other_networks():
+    z, m = load_golden("net_GRU_6IN_32H1_32H2_5OUT_0")
+    sp = net_spec_from_golden(z)
+    import torch
+    eng = make_engine(sp, 256, 10, net_kernel="tensor")
+    with pytest.raises(NotImplementedError):
+        eng.net_rollout(torch.zeros(6, device=eng.device), torch.zeros((256, 10), device=eng.device))

@@ -20,11 +20,12 @@ def main():
     ap.add_argument("--K", type=int, default=2000)
     ap.add_argument("--T", type=int, default=50)
     ap.add_argument("--iters", type=int, default=50)
+    ap.add_argument("--kernel", default=None, choices=[None, "tensor", "fp32"])
     args = ap.parse_args()
     from cartpolesimulation_b200.core import Engine
     spec = synthetic_net_spec()
     K, T = args.K, args.T
-    eng = Engine(K, T, integrator="neural", cost="quadratic_boundary_grad_minimal", device=0)
+    eng = Engine(K, T, integrator="neural", cost="quadratic_boundary_grad_minimal", device=0, net_kernel=args.kernel)
     eng.net_load(spec)
     dev = eng.device
     a = np.pi - 1e-3
