@@ -190,6 +190,7 @@ def mppi_latency(device, n_calls=1000):
                      "state_steps_per_solve": K * T * N_SUB}
     out["config"] = "K=2000, T=50, n=10, cost quadratic_boundary_grad_minimal, optimizer_mppi_b200.step(numpy s) -> numpy u"
     out["neural_GRU_2x64"] = neural_latency(device, n_calls=min(n_calls, 300))
+    out["neural_GRU_2x64_K65536"] = neural_big(device)
     out["ODE_K65536_T100"] = big_solve(device)
     return out
 
@@ -248,6 +249,29 @@ def neural_latency(device, n_calls=300):
         out["cpu_port_threads"] = O.lib().cps_oracle_num_threads()
     except Exception as ex:
         out["cpu_port_ms"] = repr(ex)
+    return out
+
+
+def neural_big(device):
+    """The same GRU solve at K = 65536 (T = 50): tcgen05 tensor-core kernel vs the FP32 CUDA-core kernel."""
+    import torch
+    from cartpolesimulation_b200.core import Engine
+    from cartpolesimulation_b200.neural import net_flops_per_step, synthetic_net_spec
+    K, T = 65536, 50
+    spec = synthetic_net_spec((64, 64), "GRU", seed=0)
+    out = {}
+    for kern in ("tensor", "fp32"):
+        eng = Engine(K, T, integrator="neural", cost="quadratic_boundary_grad_minimal", device=device, net_kernel=kern)
+        eng.net_load(spec)
+        a = np.pi - 1e-3
+        s = torch.tensor([a, 0.0, np.cos(a), np.sin(a), 0.0, 0.0], device=eng.device, dtype=torch.float32)
+        noise = torch.randn((eng.n_ind, K), device=eng.device)
+        kms = float(np.median(_event_times(lambda: eng.mppi_step(s, noise, 1, 0.0), 10, warm=3)))
+        out[kern] = {"kernel_ms_median": kms, "net_steps_per_s": K * T / (kms * 1e-3),
+                     "effective_fp32_tflops": net_flops_per_step(spec) * K * T / (kms * 1e-3) / 1e12}
+        eng.close()
+    out["note"] = ("tensor = net_tc_kernel (tcgen05.mma kind::f16, fp16 hi/lo 3-pass split, fp32 accumulators in TMEM): "
+                   "3x the algorithmic MACs on the tensor pipe; effective_fp32_tflops counts the algorithmic FLOPs only")
     return out
 
 

@@ -89,6 +89,19 @@ __device__ __forceinline__ void st8(uint32_t addr, const uint32_t (&v)[8]) {
 }
 __device__ __forceinline__ void ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// e^{-x} for x clamped to [-20, 20]: one FMUL-free MUFU.EX2 (ex2.approx.ftz of x * -log2 e)
+__device__ __forceinline__ float ex2_neg(float x) {
+    const float t = fminf(fmaxf(x, -20.0f), 20.0f) * -1.4426950408889634f;
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t));
+    return r;
+}
+__device__ __forceinline__ float rcp_f(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 // v (already scaled) -> fp16 hi + fp16 lo
 __device__ __forceinline__ void split_h(float v, __half &hi, __half &lo) {
     hi = __float2half_rn(v);
@@ -186,13 +199,28 @@ __device__ __forceinline__ void gru_epilogue(uint32_t tl, const float *cst, uint
         float h[16];
         read_operand16(tl, c_hi + (u0 >> 1), c_lo + (u0 >> 1), h);   // includes the tcgen05.wait::ld
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
+        for (int i = 0; i < 16; i += 2) {
+            // two units at a time: 6 exponentials + 2 reciprocals (instead of 6 + 6): 1/a = (b c d) / (a b c d).
+            // Pre-activations are clamped to +-20 (sigmoid(-20) = 2e-9, tanh(10) = 1 - 4e-9), which bounds the products.
             const float4 c0 = *reinterpret_cast<const float4 *>(cst + (u0 + i) * 8);
             const float4 c1 = *reinterpret_cast<const float4 *>(cst + (u0 + i) * 8 + 4);
-            const float r = sigmoid_f(fmaf(__uint_as_float(R[i]), c0.x, c0.y));
-            const float z = sigmoid_f(fmaf(__uint_as_float(Z[i]), c0.z, c0.w));
-            const float n = tanh_f(fmaf(r, fmaf(__uint_as_float(NH[i]), c1.z, c1.w), fmaf(__uint_as_float(NI[i]), c1.x, c1.y)));
-            h[i] = fmaf(h[i] - n, z, n);
+            const float4 d0 = *reinterpret_cast<const float4 *>(cst + (u0 + i + 1) * 8);
+            const float4 d1 = *reinterpret_cast<const float4 *>(cst + (u0 + i + 1) * 8 + 4);
+            const float ar = 1.0f + ex2_neg(fmaf(__uint_as_float(R[i]), c0.x, c0.y));
+            const float az = 1.0f + ex2_neg(fmaf(__uint_as_float(Z[i]), c0.z, c0.w));
+            const float br = 1.0f + ex2_neg(fmaf(__uint_as_float(R[i + 1]), d0.x, d0.y));
+            const float bz = 1.0f + ex2_neg(fmaf(__uint_as_float(Z[i + 1]), d0.z, d0.w));
+            const float pa = ar * az, pb = br * bz;
+            const float inv = rcp_f(pa * pb);
+            const float ia = pb * inv, ib = pa * inv;           // 1/(ar az), 1/(br bz)
+            const float r0 = az * ia, z0 = ar * ia, r1 = bz * ib, z1 = br * ib;
+            const float n0p = fmaf(r0, fmaf(__uint_as_float(NH[i]), c1.z, c1.w), fmaf(__uint_as_float(NI[i]), c1.x, c1.y));
+            const float n1p = fmaf(r1, fmaf(__uint_as_float(NH[i + 1]), d1.z, d1.w), fmaf(__uint_as_float(NI[i + 1]), d1.x, d1.y));
+            const float e0 = 1.0f + ex2_neg(-2.0f * n0p), e1 = 1.0f + ex2_neg(-2.0f * n1p);   // 1 + e^{2 n}
+            const float inv2 = rcp_f(e0 * e1);
+            const float n0 = fmaf(-2.0f * e1, inv2, 1.0f), n1 = fmaf(-2.0f * e0, inv2, 1.0f);  // tanh = 1 - 2 / (1 + e^{2n})
+            h[i] = fmaf(h[i] - n0, z0, n0);
+            h[i + 1] = fmaf(h[i + 1] - n1, z1, n1);
         }
         write_operand16(tl, c_hi + (u0 >> 1), c_lo + (u0 >> 1), h);
     }
