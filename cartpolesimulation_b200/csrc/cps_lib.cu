@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(256, 4) mppi_kernel(const __grid_constant__ Mp
 __global__ void __launch_bounds__(128) finalize_kernel(const __grid_constant__ FinalizeArgs a, int direct_noise) {
     extern __shared__ float smem[];
     float *s_unom = smem;            // [T]
-    float *s_E = s_unom + a.mp.T;    // [n_red + 2]
+    float *s_E = s_unom + a.mp.T;    // [n_red + 2 + nwarps]
     const int T = a.mp.T;
     for (int t = threadIdx.x; t < T; t += blockDim.x) s_unom[t] = a.u_nom[min(t + 1, T - 1)];
     __syncthreads();
@@ -656,7 +656,7 @@ extern "C" int cps_mppi_finalize(cps_handle *h, const float *partials_dev, int n
     FinalizeArgs a;
     a.mp = h->mp; a.partials = partials_dev; a.n_parts = n_ranks; a.u_nom = u_nom_dev; a.u_out = u_out_dev;
     a.shard_out = nullptr;
-    const size_t smem = sizeof(float) * ((size_t)h->cfg.horizon + h->n_red + 4);
+    const size_t smem = sizeof(float) * ((size_t)h->cfg.horizon + h->n_red + 2 + 4);  // + one float per warp
     finalize_kernel<<<1, 128, smem, h->stream>>>(a, h->cfg.noise_mode == CPS_NOISE_DIRECT);
     h->launches += 1;
     CUDA_TRY(h, cudaGetLastError());

@@ -428,7 +428,7 @@ __global__ void __launch_bounds__(R * 8 + 32, 1) net_kernel(const __grid_constan
 // =====================================================================================================
 static size_t net_smem_bytes(const NetDev &N, int R, bool mppi, const MppiParams *mp) {
     size_t f = (size_t)N.n_weights + 2 * (size_t)N.htot * R + 16 * (size_t)R;
-    if (mppi) f += (size_t)mp->T + 2 * (size_t)mp->p + (size_t)mp->n_red + 4;
+    if (mppi) f += (size_t)mp->T + 2 * (size_t)mp->p + (size_t)mp->n_red + 2 + 16;  // + one float per warp (merge)
     return f * sizeof(float);
 }
 

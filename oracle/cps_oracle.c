@@ -692,3 +692,78 @@ void cps_oracle_net_rollout(int net_type, int n_state_in, int n_layers, const in
         free(h); free(scratch);
     }
 }
+
+/* ---------------------------------------------------------------------------------------
+ * The plant: CartPole.update_state (CartPole/__init__.py:283-324), one tick of dt_simulation.
+ * State lives in a float32 array (self.s); every scalar read from it is float32, the time step is a
+ * Python float, second derivatives are float64 results of the numba-compiled _cartpole_ode.
+ * ------------------------------------------------------------------------------------- */
+
+/* _cartpole_ode as numba types it for CartPole.cartpole_ode (CartPole/__init__.py:342-343 ->
+ * cartpole_equations.py:165-179 -> :44-105): (ca, sa, angleD, positionD) float32 scalars from self.s,
+ * u float32 (Q2u, :160-164), k / m_cart / g / J_fric / M_fric 0-d float32 arrays, L and m_pole Python
+ * floats (float(L), float(m_pole)).  float32 x float32 products stay float32; anything touching a
+ * float64 operand, an integer literal or `**` promotes to float64. */
+static inline void ode_plant(float ca, float sa, float angleD, float positionD, float u, const float *ph, double L,
+                             double m_pole, double *angleDD, double *positionDD) {
+    const float k = ph[PH_K], m_cart = ph[PH_MCART], g = ph[PH_G], J_fric = ph[PH_JFRIC], M_fric = ph[PH_MFRIC];
+    const double kp1 = (double)(k + 1.0f);                    /* float32 (pinned against the live plant) */
+    const float ca2 = ca * ca, aD2 = angleD * angleD;        /* x ** 2 of a float32 scalar stays float32 */
+    const double A = kp1 * ((double)m_cart + m_pole) - m_pole * (double)ca2;
+    const float F_fric = (-M_fric) * positionD;
+    const float T_fric = (-J_fric) * angleD;
+    const double L_half = L / 2.0;
+    const double pDD = (((m_pole * (double)g) * (double)sa) * (double)ca + (double)(T_fric * ca) / L_half
+                        + kp1 * (-(((m_pole * L_half) * (double)aD2) * (double)sa) + (double)F_fric + (double)u)) / A;
+    *positionDD = pDD;
+    *angleDD = ((double)(g * sa) + pDD * (double)ca + (double)T_fric / (m_pole * L_half)) / (kp1 * L_half);
+}
+
+/* python math.fmod form (CartPole/_CartPole_mathematical_helpers.py:13-21) on a float32 angle */
+static inline double wrap_angle_rad_py(double angle) { return wrap_fmod(angle); }
+
+/* One plant tick with the stored second derivatives (computed at the end of the previous tick with the
+ * control that was active then): cartpole_integration (Euler-Cromer, cartpole_equations.py:368-378),
+ * edge_bounce (:341-347 via CartPole/__init__.py:460-470), cos/sin of the UNWRAPPED angle (:329-331),
+ * wrap (:333-334).  Each assignment into self.s rounds to float32. */
+static inline void plant_integrate(float *s, double angleDD, double positionDD, double dt, const float *ph, double L) {
+    const float angle = s[IDX_ANGLE], angleD = s[IDX_ANGLED], position = s[IDX_POS], positionD = s[IDX_POSD];
+    const double angleD_next = (double)angleD + angleDD * dt;
+    const double positionD_next = (double)positionD + positionDD * dt;
+    const double angle_next = (double)angle + angleD_next * dt;
+    const double position_next = (double)position + positionD_next * dt;
+    s[IDX_ANGLE] = (float)angle_next; s[IDX_ANGLED] = (float)angleD_next;
+    s[IDX_POS] = (float)position_next; s[IDX_POSD] = (float)positionD_next;
+    /* edge_bounce_numba(angle, cos(angle), angleD, position, positionD, dt, L=float(L)) on the float32 values */
+    const float thl = ph[PH_TRACK_HALF];
+    if (s[IDX_POS] >= thl || -s[IDX_POS] >= thl) {
+        const float a = s[IDX_ANGLE], aD = s[IDX_ANGLED], p = s[IDX_POS], pD = s[IDX_POSD];
+        const float ca = cosf(a);
+        const double aD2 = (double)aD - 2.0 * (double)(pD * ca) / (0.5 * L);
+        const double a2 = (double)a + aD2 * dt;
+        const float pD2 = -pD;
+        const double p2 = (double)p + (double)pD2 * dt;
+        s[IDX_ANGLE] = (float)a2; s[IDX_ANGLED] = (float)aD2; s[IDX_POS] = (float)p2; s[IDX_POSD] = pD2;
+    }
+    s[IDX_COS] = cosf(s[IDX_ANGLE]);
+    s[IDX_SIN] = sinf(s[IDX_ANGLE]);
+    s[IDX_ANGLE] = (float)wrap_angle_rad_py((double)s[IDX_ANGLE]);
+}
+
+/* One controller period of the plant: second derivatives from (s, Q) (set_cartpole_state_at_t0 / Update_Q ->
+ * Q2u -> cartpole_ode, CartPole/__init__.py:317-321,883-885), then n_sim ticks; the derivatives are refreshed
+ * at the end of every tick with the same Q (:317-321).  ticks_out: [n_sim][6] state after each tick or NULL;
+ * dd_out: [n_sim + 1][2] second derivatives before tick 0 and after each tick, or NULL. */
+void cps_oracle_plant_period(float *s, float Q, int n_sim, double dt_sim, const float *ph, double L, double m_pole,
+                             float *ticks_out, double *dd_out) {
+    const float u = ph[PH_UMAX] * Q;
+    double aDD, pDD;
+    ode_plant(s[IDX_COS], s[IDX_SIN], s[IDX_ANGLED], s[IDX_POSD], u, ph, L, m_pole, &aDD, &pDD);
+    if (dd_out) { dd_out[0] = aDD; dd_out[1] = pDD; }
+    for (int i = 0; i < n_sim; ++i) {
+        plant_integrate(s, aDD, pDD, dt_sim, ph, L);
+        ode_plant(s[IDX_COS], s[IDX_SIN], s[IDX_ANGLED], s[IDX_POSD], u, ph, L, m_pole, &aDD, &pDD);
+        if (ticks_out) memcpy(ticks_out + (size_t)i * 6, s, 6 * sizeof(float));
+        if (dd_out) { dd_out[2 * (i + 1)] = aDD; dd_out[2 * (i + 1) + 1] = pDD; }
+    }
+}
