@@ -25,6 +25,9 @@ ROLLOUT_MAJOR, TIME_MAJOR = 0, 1
 FLAG_FAST_SINCOS, FLAG_EXACT_ATAN2, FLAG_FAST_DIV, FLAG_SUBSTEP_SINCOS = 0x1, 0x2, 0x4, 0x8
 FLAG_NET_TENSOR_CORES, FLAG_NET_FP32 = 0x10, 0x20
 PH_COUNT = 9
+FLEET_NOISE_SUPPLIED, FLEET_NOISE_PHILOX, FLEET_RECORD = 0, 1, 16
+FLEET_RECORD_COLUMNS = ("time", "angle", "angleD", "angleDD", "angle_cos", "angle_sin", "position", "positionD",
+                        "positionDD", "Q_calculated", "Q_applied", "u", "target_position", "target_equilibrium")
 
 
 class cps_config(C.Structure):
@@ -40,6 +43,12 @@ class cps_net_desc(C.Structure):
                 ("denorm_A", C.c_float * 6), ("denorm_B", C.c_float * 6), ("differential", C.c_int),
                 ("diff_p1", C.c_float * 6), ("diff_p2", C.c_float * 6), ("out_norm_a", C.c_float * 6),
                 ("out_norm_b", C.c_float * 6), ("out_to_in", C.c_int * 6)]
+
+
+class cps_fleet_config(C.Structure):
+    _fields_ = [("struct_size", C.c_int), ("n_experiments", C.c_int), ("sim_substeps", C.c_int),
+                ("noise_source", C.c_int), ("dt_simulation", C.c_double), ("seed", C.c_ulonglong),
+                ("experiment_offset", C.c_longlong)]
 
 
 # name -> (restype, argtypes); every symbol include/cps.h declares
@@ -77,6 +86,12 @@ SYMBOLS = {
     "cps_trajectory_cost": (C.c_int, [_VP, _VP, _VP, C.c_float, C.c_int, C.c_int, _VP]),
     "cps_stage_cost": (C.c_int, [_VP, _VP, C.c_int, _VP, C.c_float, C.c_int, C.c_int, C.c_int, _VP]),
     "cps_terminal_cost": (C.c_int, [_VP, _VP, C.c_int, _VP]),
+    "cps_fleet_create": (C.c_int, [_VP, C.POINTER(cps_fleet_config)]),
+    "cps_fleet_set_states": (C.c_int, [_VP, _FP, C.c_longlong]),
+    "cps_fleet_get_states": (C.c_int, [_VP, _FP, _FP, _FP]),
+    "cps_fleet_period": (C.c_longlong, [_VP]),
+    "cps_fleet_step": (C.c_int, [_VP, C.c_int, _VP, _VP, _VP, _VP, _VP]),
+    "cps_fleet_noise": (C.c_int, [_VP, C.c_longlong, _VP]),
     "cps_measure_peaks": (C.c_int, [_VP, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "cps_launch_count": (C.c_longlong, [_VP]),
     "cps_nonfinite_costs": (C.c_int, [_VP, C.POINTER(C.c_int)]),

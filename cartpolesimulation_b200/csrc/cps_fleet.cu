@@ -1,0 +1,406 @@
+// cps_fleet.cu -- E independent closed-loop experiments advanced together (BASELINE configs[4]: data_generator with
+// 8192 MPPI-controlled cartpoles).
+//
+// One launch = one controller period of EVERY experiment:
+//   grid (blocks_per_experiment, E).  All blocks of experiment e run its MPPI solve (mppi_solve_block, the same code
+//   as mppi_kernel) on the experiment's own state, nominal inputs, last control and targets; the block that finishes
+//   last merges the partials, obtains Q = u_nom[0], writes the experiment's record row and then integrates the PLANT
+//   (CartPole.update_state, CartPole/__init__.py:283-324: Euler-Cromer at dt_simulation, edge bounce, cos/sin, fmod
+//   wrap; second derivatives refreshed every tick) for one controller period in the reference's mixed
+//   float32/float64 arithmetic, and stores the new state.  Nothing returns to the host between periods.
+//
+// Perturbations are either supplied ([E][n_ind][K] standard-normal draws per period -- the "identical injected noise"
+// hook of the parity tests) or generated in the kernel: Philox4x32-10 keyed by the seed, counter = (rollout, draw group,
+// period, GLOBAL experiment index) + Box-Muller, staged in shared memory so the integration loop keeps its registers.
+// The streams depend only on the global experiment index, so results do not change with the sharding over GPUs.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstring>
+#include <new>
+
+#include "cps_internal.cuh"
+
+struct PlantParams {
+    float k, m_cart, g, J_fric, M_fric, u_max, thl;
+    double L, m_pole, dt;
+    int n_sim;
+};
+
+struct FleetArgs {
+    OdeParams ode;              // the controller's model (L, m_pole "for controller")
+    CostParams cost_up, cost_dn;  // folded for target_equilibrium = +1 / -1 (quadratic_boundary_grad selects its set)
+    MppiParams mp;
+    PlantParams plant;
+    int bpe;                    // blocks per experiment
+    float *s;                   // [E][8] current state (6 used)
+    float *u_nom;               // [E][T]
+    float *u_prev;              // [E] last returned control
+    const float *tp, *te;       // [E] targets of this period (null: 0 / +1)
+    const float *noise;         // supplied draws [E][n_ind][K] of this period, or null (Philox)
+    unsigned long long seed;
+    unsigned period;            // controller period index (Philox counter)
+    unsigned e_offset;          // global index of local experiment 0
+    float *partials;            // [E][bpe][2 + n_red]
+    unsigned *tickets;          // [E]
+    int *nonfinite;
+    float *record;              // [E][CPS_FLEET_RECORD] of this period, or null
+    float *J_out;               // [E][K] or null
+    double time;                // period * dt_control
+};
+
+// ---- Philox4x32-10 (Salmon et al., SC'11), the counter-based generator torch / TF / cuRAND also use ---------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const unsigned hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u;
+        k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+
+// Two standard normals from two 32-bit words (Box-Muller on 24-bit uniforms in (0, 1)).
+__device__ __forceinline__ void box_muller(unsigned a, unsigned b, float &n0, float &n1) {
+    const float u1 = ((float)(a >> 8) + 0.5f) * 5.9604644775390625e-8f;  // 2^-24
+    const float u2 = ((float)(b >> 8) + 0.5f) * 5.9604644775390625e-8f;
+    const float r = sqrtf(-2.0f * logf(u1));
+    float sn, cs;
+    sincospif(2.0f * u2, &sn, &cs);
+    n0 = r * cs;
+    n1 = r * sn;
+}
+
+// Draws i = 0..n_ind-1 of rollout k, experiment e_global, controller period `period`; dst[i * stride].
+__device__ __forceinline__ void fleet_draws(unsigned long long seed, unsigned period, unsigned e_global, unsigned k,
+                                            int n_ind, float *dst, long long stride) {
+    const uint2 key = make_uint2((unsigned)seed, (unsigned)(seed >> 32));
+    for (int g = 0; 4 * g < n_ind; ++g) {
+        const uint4 r = philox4x32_10(make_uint4(k, (unsigned)g, period, e_global), key);
+        float n[4];
+        box_muller(r.x, r.y, n[0], n[1]);
+        box_muller(r.z, r.w, n[2], n[3]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (4 * g + q < n_ind) dst[(long long)(4 * g + q) * stride] = n[q];
+    }
+}
+
+// cps_fleet_noise: materialise the draws the kernel generates, [E][n_ind][K]
+__global__ void __launch_bounds__(256) fleet_noise_kernel(unsigned long long seed, unsigned period, unsigned e_offset, int E,
+                                                          int K, int n_ind, float *out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x, e = blockIdx.y;
+    if (k >= K || e >= E) return;
+    fleet_draws(seed, period, e_offset + (unsigned)e, (unsigned)k, n_ind, out + ((size_t)e * n_ind) * K + k, K);
+}
+
+// ---- the plant (device restatement of oracle/cps_oracle.c: ode_plant, plant_integrate; no FMA contraction) ------------
+__device__ __forceinline__ void plant_ode(const PlantParams &P, float ca, float sa, float angleD, float positionD, float u,
+                                          double &angleDD, double &positionDD) {
+    const double kp1 = (double)__fadd_rn(P.k, 1.0f);
+    const float ca2 = __fmul_rn(ca, ca), aD2 = __fmul_rn(angleD, angleD);
+    const double A = __dsub_rn(__dmul_rn(kp1, __dadd_rn((double)P.m_cart, P.m_pole)), __dmul_rn(P.m_pole, (double)ca2));
+    const float F_fric = __fmul_rn(-P.M_fric, positionD);
+    const float T_fric = __fmul_rn(-P.J_fric, angleD);
+    const double L_half = P.L / 2.0;
+    const double grav = __dmul_rn(__dmul_rn(__dmul_rn(P.m_pole, (double)P.g), (double)sa), (double)ca);
+    const double fric = (double)__fmul_rn(T_fric, ca) / L_half;
+    const double centr = -__dmul_rn(__dmul_rn(__dmul_rn(P.m_pole, L_half), (double)aD2), (double)sa);
+    const double inner = __dadd_rn(__dadd_rn(centr, (double)F_fric), (double)u);
+    const double pDD = __dadd_rn(__dadd_rn(grav, fric), __dmul_rn(kp1, inner)) / A;
+    positionDD = pDD;
+    const double num = __dadd_rn(__dadd_rn((double)__fmul_rn(P.g, sa), __dmul_rn(pDD, (double)ca)),
+                                 (double)T_fric / __dmul_rn(P.m_pole, L_half));
+    angleDD = num / __dmul_rn(kp1, L_half);
+}
+
+__device__ __forceinline__ double plant_wrap(double angle) {
+    const double two_pi = 6.283185307179586, pi = 3.141592653589793;
+    const double m = fmod(angle, two_pi);
+    if (m < -pi) return m + two_pi;
+    if (m > pi) return m - two_pi;
+    return m;
+}
+
+__device__ __forceinline__ void plant_tick(const PlantParams &P, float *s, double aDD, double pDD) {
+    const float angle = s[IDX_ANGLE], angleD = s[IDX_ANGLED], position = s[IDX_POS], positionD = s[IDX_POSD];
+    const double angleD_next = __dadd_rn((double)angleD, __dmul_rn(aDD, P.dt));
+    const double positionD_next = __dadd_rn((double)positionD, __dmul_rn(pDD, P.dt));
+    const double angle_next = __dadd_rn((double)angle, __dmul_rn(angleD_next, P.dt));
+    const double position_next = __dadd_rn((double)position, __dmul_rn(positionD_next, P.dt));
+    s[IDX_ANGLE] = (float)angle_next; s[IDX_ANGLED] = (float)angleD_next;
+    s[IDX_POS] = (float)position_next; s[IDX_POSD] = (float)positionD_next;
+    if (s[IDX_POS] >= P.thl || -s[IDX_POS] >= P.thl) {  // edge_bounce (cartpole_equations.py:341-347)
+        const float a = s[IDX_ANGLE], aD = s[IDX_ANGLED], p = s[IDX_POS], pD = s[IDX_POSD];
+        const float ca = cosf(a);
+        const double aD2 = __dsub_rn((double)aD, __dmul_rn(2.0, (double)__fmul_rn(pD, ca)) / __dmul_rn(0.5, P.L));
+        const double a2 = __dadd_rn((double)a, __dmul_rn(aD2, P.dt));
+        const float pD2 = -pD;
+        const double p2 = __dadd_rn((double)p, __dmul_rn((double)pD2, P.dt));
+        s[IDX_ANGLE] = (float)a2; s[IDX_ANGLED] = (float)aD2; s[IDX_POS] = (float)p2; s[IDX_POSD] = pD2;
+    }
+    s[IDX_COS] = cosf(s[IDX_ANGLE]);   // of the UNWRAPPED angle (CartPole/__init__.py:329-334)
+    s[IDX_SIN] = sinf(s[IDX_ANGLE]);
+    s[IDX_ANGLE] = (float)plant_wrap((double)s[IDX_ANGLE]);
+}
+
+template <int INTEG, int COST, bool PHILOX>
+__global__ void __launch_bounds__(256, 4) fleet_kernel(const __grid_constant__ FleetArgs a) {
+    extern __shared__ float smem[];
+    __shared__ CostParams s_cost;
+    const MppiParams &mp = a.mp;
+    const int e = blockIdx.y, tid = threadIdx.x;
+    const float tp = a.tp ? a.tp[e] : 0.0f, te = a.te ? a.te[e] : 1.0f;
+    if (tid == 0) {
+        s_cost = (te == 1.0f) ? a.cost_up : a.cost_dn;
+        s_cost.target_position = tp;
+        s_cost.target_equilibrium = te;
+    }
+    const int nwarps = blockDim.x >> 5;
+    float *s_eps = smem + mp.T + 2 * mp.p + nwarps * (mp.n_red + 2) + mp.n_red + 4;  // [n_ind][blockDim.x]
+    const int k = blockIdx.x * blockDim.x + tid;
+    if (PHILOX)
+        fleet_draws(a.seed, a.period, a.e_offset + (unsigned)e, (unsigned)min(k, mp.K - 1), mp.n_ind, s_eps + tid, blockDim.x);
+    __syncthreads();
+
+    SolveIO io;
+    io.s = a.s + (size_t)e * 8;
+    if (PHILOX) {  // rollout k of this block sits at s_eps[i * blockDim.x + tid]
+        io.noise = s_eps - (long long)blockIdx.x * blockDim.x;
+        io.ns_i = blockDim.x; io.ns_k = 1;
+    } else {
+        io.noise = a.noise + (size_t)e * mp.n_ind * mp.K;
+        io.ns_i = mp.K; io.ns_k = 1;
+    }
+    io.u_prev = a.u_prev[e];
+    io.u_nom = a.u_nom + (size_t)e * mp.T;
+    io.u_out = a.u_prev + e;   // the returned control becomes the next period's u_prev (optimizer_mppi.py:210)
+    io.J_out = a.J_out ? a.J_out + (size_t)e * mp.K : nullptr;
+    io.traj_out = nullptr; io.ts_k = io.ts_t = io.ts_c = 0; io.u_run_out = nullptr;
+    io.partials = a.partials + (size_t)e * a.bpe * (mp.n_red + 2);
+    io.ticket = a.tickets + e;
+    io.nonfinite = a.nonfinite;
+    io.shard_out = nullptr;
+    const bool last = mppi_solve_block<INTEG, COST, SC_ROTATE, CPS_NOISE_INDUCING, false, false>(a.ode, s_cost, mp, io, smem,
+                                                                                                blockIdx.x, a.bpe);
+    if (!last) return;
+    __syncthreads();
+    if (tid != 0) return;
+
+    // ---- the plant: one controller period with Q held (CartPole/__init__.py:283-324, 475-527) -------------------------
+    const PlantParams &P = a.plant;
+    float s[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) s[c] = io.s[c];
+    const float Q = *io.u_out;   // written by this thread in merge_and_finish
+    const float u = __fmul_rn(P.u_max, Q);
+    double aDD, pDD;
+    plant_ode(P, s[IDX_COS], s[IDX_SIN], s[IDX_ANGLED], s[IDX_POSD], u, aDD, pDD);
+    if (a.record) {
+        float *r = a.record + (size_t)e * CPS_FLEET_RECORD;
+        r[0] = (float)a.time;
+        r[1] = s[IDX_ANGLE]; r[2] = s[IDX_ANGLED]; r[3] = (float)aDD; r[4] = s[IDX_COS]; r[5] = s[IDX_SIN];
+        r[6] = s[IDX_POS]; r[7] = s[IDX_POSD]; r[8] = (float)pDD;
+        r[9] = Q; r[10] = Q; r[11] = u; r[12] = tp; r[13] = te; r[14] = 0.0f; r[15] = 0.0f;
+    }
+    for (int i = 0; i < P.n_sim; ++i) {
+        plant_tick(P, s, aDD, pDD);
+        plant_ode(P, s[IDX_COS], s[IDX_SIN], s[IDX_ANGLED], s[IDX_POSD], u, aDD, pDD);
+    }
+    float *so = a.s + (size_t)e * 8;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) so[c] = s[c];
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------------------
+struct FleetState {
+    cps_fleet_config cfg;
+    int E, bpe, block;
+    size_t smem;
+    float *d_s, *d_unom, *d_uprev, *d_partials;
+    unsigned *d_tickets;
+    long long period;
+    CostParams cost_up, cost_dn;
+};
+
+void cps_fleet_free(cps_handle *h) {
+    FleetState *F = h->fleet;
+    if (!F) return;
+    cudaFree(F->d_s); cudaFree(F->d_unom); cudaFree(F->d_uprev); cudaFree(F->d_partials); cudaFree(F->d_tickets);
+    delete F;
+    h->fleet = nullptr;
+}
+
+typedef void (*fleet_fn)(const FleetArgs);
+template <int INTEG, bool PHILOX>
+static fleet_fn pick_fleet2(int cost) {
+    switch (cost) {
+    case CPS_COST_DEFAULT: return fleet_kernel<INTEG, COST_DEFAULT, PHILOX>;
+    case CPS_COST_QUADRATIC_BOUNDARY: return fleet_kernel<INTEG, COST_QB, PHILOX>;
+    case CPS_COST_QB_GRAD_MINIMAL: return fleet_kernel<INTEG, COST_GRADMIN, PHILOX>;
+    case CPS_COST_QB_GRAD: return fleet_kernel<INTEG, COST_GRAD, PHILOX>;
+    default: return nullptr;
+    }
+}
+static fleet_fn pick_fleet(int integ, int cost, bool philox) {
+    if (integ == CPS_EULER_V0) return philox ? pick_fleet2<0, true>(cost) : pick_fleet2<0, false>(cost);
+    return philox ? pick_fleet2<1, true>(cost) : pick_fleet2<1, false>(cost);
+}
+
+extern "C" int cps_fleet_create(cps_handle *h, const cps_fleet_config *cfg) {
+    if (!h) return CPS_ERR_INVALID;
+    if (!cfg || cfg->struct_size != (int)sizeof(cps_fleet_config))
+        return fail(h, CPS_ERR_INVALID, "cps_fleet_create: cps_fleet_config size mismatch");
+    if (cfg->n_experiments < 1 || cfg->sim_substeps < 1 || !(cfg->dt_simulation > 0.0))
+        return fail(h, CPS_ERR_INVALID, "cps_fleet_create: need n_experiments >= 1, sim_substeps >= 1, dt_simulation > 0");
+    if (cfg->noise_source != CPS_FLEET_NOISE_SUPPLIED && cfg->noise_source != CPS_FLEET_NOISE_PHILOX)
+        return fail(h, CPS_ERR_INVALID, "cps_fleet_create: unknown noise source %d", cfg->noise_source);
+    if (h->cfg.integrator == CPS_PREDICTOR_NEURAL)
+        return fail(h, CPS_ERR_UNSUPPORTED, "cps_fleet_create: fleets run with the ODE predictors only");
+    if (h->cfg.cost_id == CPS_COST_NONE) return fail(h, CPS_ERR_NOT_CONFIGURED, "cps_fleet_create: the handle has no cost function");
+    if (h->cfg.noise_mode != CPS_NOISE_INDUCING)
+        return fail(h, CPS_ERR_UNSUPPORTED, "cps_fleet_create: fleets use inducing-point noise (CPS_NOISE_INDUCING)");
+    if (cfg->n_experiments > 65535) return fail(h, CPS_ERR_INVALID, "cps_fleet_create: at most 65535 experiments per handle");
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    cps_fleet_free(h);
+    FleetState *F = new (std::nothrow) FleetState();
+    if (!F) return fail(h, CPS_ERR_INVALID, "cps_fleet_create: out of host memory");
+    memset(F, 0, sizeof(*F));
+    F->cfg = *cfg;
+    F->E = cfg->n_experiments;
+    const int K = h->cfg.num_rollouts, T = h->cfg.horizon;
+    F->block = K >= 256 ? 256 : ((K + 31) / 32) * 32;
+    F->bpe = (K + F->block - 1) / F->block;
+    const int nwarps = F->block / 32;
+    size_t fl = (size_t)T + 2 * (size_t)h->cfg.interp_period + (size_t)nwarps * (h->n_red + 2) + (size_t)h->n_red + 4;
+    if (cfg->noise_source == CPS_FLEET_NOISE_PHILOX) fl += (size_t)h->n_ind * F->block;
+    F->smem = fl * sizeof(float);
+    if (F->smem > 200 * 1024) { delete F; return fail(h, CPS_ERR_UNSUPPORTED, "cps_fleet_create: horizon too large for shared memory"); }
+    h->fleet = F;
+    const size_t E = F->E;
+    CUDA_TRY(h, cudaMalloc(&F->d_s, sizeof(float) * E * 8));
+    CUDA_TRY(h, cudaMalloc(&F->d_unom, sizeof(float) * E * T));
+    CUDA_TRY(h, cudaMalloc(&F->d_uprev, sizeof(float) * E));
+    CUDA_TRY(h, cudaMalloc(&F->d_partials, sizeof(float) * E * F->bpe * (h->n_red + 2)));
+    CUDA_TRY(h, cudaMalloc(&F->d_tickets, sizeof(unsigned) * E));
+    CUDA_TRY(h, cudaMemset(F->d_s, 0, sizeof(float) * E * 8));
+    CUDA_TRY(h, cudaMemset(F->d_unom, 0, sizeof(float) * E * T));
+    CUDA_TRY(h, cudaMemset(F->d_uprev, 0, sizeof(float) * E));
+    CUDA_TRY(h, cudaMemset(F->d_tickets, 0, sizeof(unsigned) * E));
+    CUDA_TRY(h, cudaDeviceSynchronize());
+    return CPS_OK;
+}
+
+extern "C" int cps_fleet_set_states(cps_handle *h, const float *s_host, long long period) {
+    if (!h) return CPS_ERR_INVALID;
+    FleetState *F = h->fleet;
+    if (!F) return fail(h, CPS_ERR_NOT_CONFIGURED, "cps_fleet_set_states: no fleet (cps_fleet_create)");
+    if (!s_host || period < 0) return fail(h, CPS_ERR_INVALID, "cps_fleet_set_states: bad argument");
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    float *tmp = new (std::nothrow) float[(size_t)F->E * 8];
+    if (!tmp) return fail(h, CPS_ERR_INVALID, "cps_fleet_set_states: out of host memory");
+    for (int e = 0; e < F->E; ++e) {
+        for (int c = 0; c < 6; ++c) tmp[(size_t)e * 8 + c] = s_host[(size_t)e * 6 + c];
+        tmp[(size_t)e * 8 + 6] = tmp[(size_t)e * 8 + 7] = 0.0f;
+    }
+    cudaError_t er = cudaMemcpyAsync(F->d_s, tmp, sizeof(float) * (size_t)F->E * 8, cudaMemcpyHostToDevice, h->stream);
+    if (er == cudaSuccess) er = cudaMemsetAsync(F->d_unom, 0, sizeof(float) * (size_t)F->E * h->cfg.horizon, h->stream);
+    if (er == cudaSuccess) er = cudaMemsetAsync(F->d_uprev, 0, sizeof(float) * (size_t)F->E, h->stream);
+    if (er == cudaSuccess) er = cudaStreamSynchronize(h->stream);
+    delete[] tmp;
+    CUDA_TRY(h, er);
+    F->period = period;
+    return CPS_OK;
+}
+
+extern "C" int cps_fleet_get_states(cps_handle *h, float *s_host, float *u_nom_host, float *u_prev_host) {
+    if (!h) return CPS_ERR_INVALID;
+    FleetState *F = h->fleet;
+    if (!F) return fail(h, CPS_ERR_NOT_CONFIGURED, "cps_fleet_get_states: no fleet (cps_fleet_create)");
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    if (s_host) {
+        float *tmp = new (std::nothrow) float[(size_t)F->E * 8];
+        if (!tmp) return fail(h, CPS_ERR_INVALID, "cps_fleet_get_states: out of host memory");
+        cudaError_t er = cudaMemcpyAsync(tmp, F->d_s, sizeof(float) * (size_t)F->E * 8, cudaMemcpyDeviceToHost, h->stream);
+        if (er == cudaSuccess) er = cudaStreamSynchronize(h->stream);
+        if (er == cudaSuccess)
+            for (int e = 0; e < F->E; ++e)
+                for (int c = 0; c < 6; ++c) s_host[(size_t)e * 6 + c] = tmp[(size_t)e * 8 + c];
+        delete[] tmp;
+        CUDA_TRY(h, er);
+    }
+    if (u_nom_host)
+        CUDA_TRY(h, cudaMemcpyAsync(u_nom_host, F->d_unom, sizeof(float) * (size_t)F->E * h->cfg.horizon, cudaMemcpyDeviceToHost, h->stream));
+    if (u_prev_host)
+        CUDA_TRY(h, cudaMemcpyAsync(u_prev_host, F->d_uprev, sizeof(float) * (size_t)F->E, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return CPS_OK;
+}
+
+extern "C" long long cps_fleet_period(const cps_handle *h) { return (h && h->fleet) ? h->fleet->period : -1; }
+
+// CostParams for a given target equilibrium: fold_cost() depends on it for quadratic_boundary_grad (weight set, w[9]).
+int cps_fold_cost_for(cps_handle *h, float target_equilibrium, CostParams *out);
+
+extern "C" int cps_fleet_step(cps_handle *h, int n_periods, const float *tp_dev, const float *te_dev, const float *noise_dev,
+                              float *record_dev, float *J_out_dev) {
+    if (!h) return CPS_ERR_INVALID;
+    FleetState *F = h->fleet;
+    if (!F) return fail(h, CPS_ERR_NOT_CONFIGURED, "cps_fleet_step: no fleet (cps_fleet_create)");
+    if (n_periods < 0) return fail(h, CPS_ERR_INVALID, "cps_fleet_step: n_periods < 0");
+    const bool philox = F->cfg.noise_source == CPS_FLEET_NOISE_PHILOX;
+    if (!philox && !noise_dev) return fail(h, CPS_ERR_INVALID, "cps_fleet_step: this fleet expects supplied noise");
+    if (philox && noise_dev) return fail(h, CPS_ERR_INVALID, "cps_fleet_step: this fleet generates its noise (Philox); pass NULL");
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    FleetArgs a;
+    a.ode = h->ode; a.mp = h->mp;
+    int rc;
+    if ((rc = cps_fold_cost_for(h, 1.0f, &a.cost_up)) != CPS_OK) return rc;
+    if ((rc = cps_fold_cost_for(h, -1.0f, &a.cost_dn)) != CPS_OK) return rc;
+    PlantParams &P = a.plant;
+    P.k = h->phys[CPS_PH_K]; P.m_cart = h->phys[CPS_PH_M_CART]; P.g = h->phys[CPS_PH_G]; P.J_fric = h->phys[CPS_PH_J_FRIC];
+    P.M_fric = h->phys[CPS_PH_M_FRIC]; P.u_max = h->phys[CPS_PH_U_MAX]; P.thl = h->phys[CPS_PH_TRACK_HALF_LENGTH];
+    P.L = (double)h->phys[CPS_PH_L]; P.m_pole = (double)h->phys[CPS_PH_M_POLE];
+    P.dt = F->cfg.dt_simulation; P.n_sim = F->cfg.sim_substeps;
+    a.bpe = F->bpe;
+    a.s = F->d_s; a.u_nom = F->d_unom; a.u_prev = F->d_uprev;
+    a.seed = F->cfg.seed; a.e_offset = (unsigned)F->cfg.experiment_offset;
+    a.partials = F->d_partials; a.tickets = F->d_tickets; a.nonfinite = h->d_nonfinite;
+    fleet_fn fn = pick_fleet(h->cfg.integrator, h->cfg.cost_id, philox);
+    if (!fn) return fail(h, CPS_ERR_NOT_CONFIGURED, "cps_fleet_step: no kernel for this configuration");
+    if (F->smem > 48 * 1024) CUDA_TRY(h, cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F->smem));
+    const size_t E = F->E, K = h->cfg.num_rollouts;
+    const double dt_control = F->cfg.dt_simulation * F->cfg.sim_substeps;
+    const dim3 grid(F->bpe, F->E);
+    for (int j = 0; j < n_periods; ++j) {
+        a.tp = tp_dev ? tp_dev + (size_t)j * E : nullptr;
+        a.te = te_dev ? te_dev + (size_t)j * E : nullptr;
+        a.noise = noise_dev ? noise_dev + (size_t)j * E * h->n_ind * K : nullptr;
+        a.record = record_dev ? record_dev + (size_t)j * E * CPS_FLEET_RECORD : nullptr;
+        a.J_out = J_out_dev ? J_out_dev + (size_t)j * E * K : nullptr;
+        a.period = (unsigned)F->period;
+        a.time = (double)F->period * dt_control;
+        fn<<<grid, F->block, F->smem, h->stream>>>(a);
+        F->period += 1;
+        h->launches += 1;
+    }
+    CUDA_TRY(h, cudaGetLastError());
+    return CPS_OK;
+}
+
+extern "C" int cps_fleet_noise(cps_handle *h, long long period, float *out_dev) {
+    if (!h) return CPS_ERR_INVALID;
+    FleetState *F = h->fleet;
+    if (!F) return fail(h, CPS_ERR_NOT_CONFIGURED, "cps_fleet_noise: no fleet (cps_fleet_create)");
+    if (!out_dev || period < 0) return fail(h, CPS_ERR_INVALID, "cps_fleet_noise: bad argument");
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    const int K = h->cfg.num_rollouts;
+    const dim3 grid((K + 255) / 256, F->E);
+    fleet_noise_kernel<<<grid, 256, 0, h->stream>>>(F->cfg.seed, (unsigned)period, (unsigned)F->cfg.experiment_offset, F->E, K,
+                                                    h->n_ind, out_dev);
+    h->launches += 1;
+    CUDA_TRY(h, cudaGetLastError());
+    return CPS_OK;
+}

@@ -18,20 +18,7 @@ struct MppiArgs {
     OdeParams ode;
     CostParams cost;
     MppiParams mp;
-    const float *s;          // [6]
-    const float *noise;      // INDUCING: n_ind x K draws, DIRECT: T x K delta_u
-    long long ns_i, ns_k;    // element strides of `noise` along channel / rollout
-    float u_prev;
-    float *u_nom;            // [T] in/out
-    float *u_out;            // [1]
-    float *J_out;            // [K] or null
-    float *traj_out;         // K x (T+1) x 6 or null
-    long long ts_k, ts_t, ts_c;
-    float *u_run_out;        // [K][T] or null
-    float *partials;         // [gridDim.x][2 + n_red]
-    unsigned *ticket;
-    int *nonfinite;
-    float *shard_out;        // non-null: stop after the local merge and write {m, S, E[n_red]}
+    SolveIO io;
 };
 
 struct RolloutArgs {
@@ -68,7 +55,8 @@ struct FinalizeArgs {
 };
 
 
-struct NetState;  // cps_net.cu
+struct NetState;    // cps_net.cu
+struct FleetState;  // cps_fleet.cu
 
 struct cps_handle {
     cps_config cfg;
@@ -97,11 +85,16 @@ struct cps_handle {
     size_t cap_rs0, cap_rQ, cap_rtraj, cap_rfinal;
     long long launches;
     std::string err;
-    NetState *net;  // neural predictor (cps_net_load), owned
+    NetState *net;      // neural predictor (cps_net_load), owned
+    FleetState *fleet;  // closed-loop experiments (cps_fleet_create), owned
 };
 
 extern thread_local std::string g_create_err;
 
+// cps_fleet.cu
+void cps_fleet_free(cps_handle *h);
+// cps_lib.cu: cost parameters folded for a given target equilibrium
+int cps_fold_cost_for(cps_handle *h, float target_equilibrium, CostParams *out);
 // cps_net.cu
 void cps_net_free(cps_handle *h);
 int cps_net_mppi_step(cps_handle *h, const float *s_dev, const float *noise_dev, int noise_layout, float u_prev,

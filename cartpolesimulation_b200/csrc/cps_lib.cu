@@ -25,124 +25,8 @@
 template <int INTEG, int COST, int SC, int NOISE, bool FAST_DIV, bool EXACT_ATAN2>
 __global__ void __launch_bounds__(256, 4) mppi_kernel(const __grid_constant__ MppiArgs a) {
     extern __shared__ float smem[];
-    const MppiParams &mp = a.mp;
-    const int T = mp.T, p = mp.p;
-    float *s_unom = smem;                 // [T]   shifted nominal inputs
-    float *s_w0 = s_unom + T;             // [p]   (p-j)/p
-    float *s_w1 = s_w0 + p;               // [p]   j/p
-    float *s_red = s_w1 + p;              // [nwarps][n_red + 2] then reused as s_E
-    __shared__ float s_bcast[2];
-    __shared__ unsigned s_ticket;
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-    const int k = blockIdx.x * blockDim.x + tid;
-    const bool active = k < mp.K;
-
-    // warm-start shift at the START of the solve: u_nom <- [u_nom[1:], u_nom[-1]] (optimizer_mppi.py:183)
-    for (int t = tid; t < T; t += blockDim.x) s_unom[t] = a.u_nom[min(t + 1, T - 1)];
-    for (int j = tid; j < p; j += blockDim.x) {
-        s_w0[j] = (float)(p - j) / (float)p;  // float32 division, as numpy does for interp_mat / step
-        s_w1[j] = (float)j / (float)p;
-    }
-    __syncthreads();
-
-    State z = load_state(a.s);
-    const OdeParams ode = pin_params(a.ode, z.th);  // loop-invariant constants pinned in registers
-    float c_cost = cosf(z.th);  // the plugins take cos(angle) of the stored angle, not angle_cos (default.py:34)
-
-    const float *nz = a.noise + (long long)(active ? k : 0) * a.ns_k;
-    float *traj = a.traj_out ? a.traj_out + (long long)(active ? k : 0) * a.ts_k : nullptr;
-
-    float Jacc = 0.0f, corr = 0.0f, up = a.u_prev;
-    int seg = 0, j = 0;
-    float na = 0.0f, nb = 0.0f, du_next = 0.0f;
-    if (NOISE == CPS_NOISE_INDUCING) {
-        na = nz[0] * mp.sigma;
-        nb = (mp.n_ind > 1) ? nz[a.ns_i] * mp.sigma : 0.0f;
-    } else {
-        du_next = nz[0];
-    }
-
-#pragma unroll 1
-    for (int t = 0; t < T; ++t) {
-        float du;
-        if (NOISE == CPS_NOISE_INDUCING) {
-            // delta_u = (eps * sigma) @ W: two non-zero tent weights per step (Interpolator.py:53-77)
-            du = (seg == mp.n_ind - 1) ? na * mp.inv_p : fmaf(na, s_w0[j], nb * s_w1[j]);
-            if (++j == p) {
-                j = 0; ++seg; na = nb;
-                nb = (seg + 1 < mp.n_ind) ? nz[(long long)(seg + 1) * a.ns_i] * mp.sigma : 0.0f;
-            }
-        } else {
-            du = du_next;
-            if (t + 1 < T) du_next = nz[(long long)(t + 1) * a.ns_i];  // prefetch under the integration
-        }
-        const float u = clampf(s_unom[t] + du, mp.lo, mp.hi);  // u_run = clip(u_nom + delta_u) (:185-186)
-        if (COST != COST_NONE) {
-            float st = stage_cost<COST>(a.cost, c_cost, z.w, z.x, u, up);
-            if (COST == COST_DEFAULT || COST == COST_QB) st -= a.cost.max_cost;  // get_stage_cost shift (:63-64)
-            Jacc += st;
-        }
-        // mppi_correction_cost (:153-154); delta_u is the UNCLIPPED perturbation, u the clipped input
-        corr = fmaf(mp.cc_half_nu * du, du, fmaf(mp.cc_R * u, du, fmaf(mp.cc_half_R * u, u, corr)));
-        if (active) {
-            if (a.u_run_out) a.u_run_out[(long long)k * T + t] = u;
-            if (traj) store_state(traj + (long long)t * a.ts_t, a.ts_c, z);
-        }
-        control_step<INTEG, SC, FAST_DIV, EXACT_ATAN2>(ode, z, u);
-        c_cost = z.c;
-        up = u;
-    }
-    if (COST != COST_NONE) Jacc += terminal_cost<COST>(a.cost, z.th, z.x);
-    if (active && traj) store_state(traj + (long long)T * a.ts_t, a.ts_c, z);
-    // mean over the T+1 entries (Cost_Functions/__init__.py:90-93) + summed correction
-    const float J = fmaf(Jacc, mp.inv_T1, corr);
-    if (active) {
-        if (a.J_out) a.J_out[k] = J;
-        if (!isfinite(J)) atomicAdd(a.nonfinite, 1);
-    }
-
-    // ---- K2: block partials -------------------------------------------------------------------------
-    const int rec = 2 + mp.n_red;
-    float m = warp_min(active ? J : INFINITY);
-    if (lane == 0) s_red[warp] = m;
-    __syncthreads();
-    if (tid == 0) {
-        float mm = s_red[0];
-        for (int w = 1; w < nwarps; ++w) mm = fminf(mm, s_red[w]);
-        s_bcast[0] = mm;
-    }
-    __syncthreads();
-    m = s_bcast[0];
-    const float wgt = active ? expf(-(J - m) * mp.inv_lambda) : 0.0f;  // exp(-(S - rho)/LBD) (:164)
-    {
-        const float v = warp_sum(wgt);
-        if (lane == 0) s_red[warp * rec + 0] = v;
-    }
-    for (int i = 0; i < mp.n_red; ++i) {
-        const float e = active ? nz[(long long)i * a.ns_i] : 0.0f;  // L1/L2 hit: read once already
-        const float v = warp_sum(wgt * e);
-        if (lane == 0) s_red[warp * rec + 1 + i] = v;
-    }
-    __syncthreads();
-    float *part = a.partials + (size_t)blockIdx.x * rec;
-    for (int c = tid; c < mp.n_red + 1; c += blockDim.x) {
-        float acc = 0.0f;
-        for (int w = 0; w < nwarps; ++w) acc += s_red[w * rec + c];
-        part[1 + c] = acc;
-    }
-    if (tid == 0) part[0] = m;
-
-    // ---- last block merges all partials and finishes the update -----------------------------------------
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) s_ticket = atomicAdd(a.ticket, 1u);
-    __syncthreads();
-    if (s_ticket != gridDim.x - 1) return;
-    __threadfence();
-    merge_and_finish(mp, a.partials, gridDim.x, s_red, s_unom, a.u_nom, a.u_out, a.shard_out,
-                     NOISE == CPS_NOISE_DIRECT);
-    if (tid == 0) *a.ticket = 0u;  // re-arm for the next launch
+    mppi_solve_block<INTEG, COST, SC, NOISE, FAST_DIV, EXACT_ATAN2>(a.ode, a.cost, a.mp, a.io, smem, blockIdx.x,
+                                                                    gridDim.x);
 }
 
 // Merge of gathered per-rank partials (K sharded over GPUs).
@@ -243,14 +127,13 @@ static void fold_ode(cps_handle *h) {
     o.n = h->cfg.substeps;
 }
 
-static int fold_cost(cps_handle *h) {
-    CostParams &c = h->cost;
+static int fold_cost_into(cps_handle *h, float target_equilibrium, CostParams &c) {
     memset(&c, 0, sizeof(c));
     const float thl = h->phys[CPS_PH_TRACK_HALF_LENGTH];
     c.thl = thl;
     c.inv_2thl = 1.0f / (2.0f * thl);
     c.target_position = h->target_position;
-    c.target_equilibrium = h->target_equilibrium;
+    c.target_equilibrium = target_equilibrium;
     const float *w = h->cost_in;
     switch (h->cfg.cost_id) {
     case CPS_COST_NONE: break;
@@ -281,13 +164,13 @@ static int fold_cost(cps_handle *h) {
         if (h->cost_in_n == 11) {
             memcpy(v, w, sizeof(v));
         } else if (h->cost_in_n == 19) {
-            const float *set = (h->target_equilibrium == 1.0f) ? w : w + 8;
+            const float *set = (target_equilibrium == 1.0f) ? w : w + 8;
             for (int i = 0; i < 7; ++i) v[i] = set[i];
             v[7] = w[16]; v[8] = w[17]; v[9] = set[7]; v[10] = w[18];
         } else {
             return fail(h, CPS_ERR_INVALID, "cost params: need 11 or 19 values for quadratic_boundary_grad");
         }
-        const float e = h->target_equilibrium;
+        const float e = target_equilibrium;
         c.w[0] = v[0]; c.w[1] = v[1]; c.w[2] = v[2]; c.w[3] = v[3]; c.w[4] = v[4]; c.w[5] = v[5] * v[7]; c.w[6] = v[6];
         c.w[7] = v[8] * thl;
         c.w[8] = 1.0f / ((1.0f - v[8]) * thl);
@@ -298,6 +181,12 @@ static int fold_cost(cps_handle *h) {
     default: return fail(h, CPS_ERR_UNSUPPORTED, "unknown cost id %d", h->cfg.cost_id);
     }
     return CPS_OK;
+}
+
+static int fold_cost(cps_handle *h) { return fold_cost_into(h, h->target_equilibrium, h->cost); }
+
+int cps_fold_cost_for(cps_handle *h, float target_equilibrium, CostParams *out) {
+    return fold_cost_into(h, target_equilibrium, *out);
 }
 
 static void fold_mppi(cps_handle *h) {
@@ -427,6 +316,7 @@ extern "C" void cps_destroy(cps_handle *h) {
     if (!h) return;
     cudaSetDevice(h->cfg.device);
     cps_net_free(h);
+    cps_fleet_free(h);
     cudaFree(h->d_partials); cudaFree(h->d_ticket); cudaFree(h->d_nonfinite);
     cudaFree(h->d_s); cudaFree(h->d_unom); cudaFree(h->d_u);
     cudaFree(h->d_rs0); cudaFree(h->d_rQ); cudaFree(h->d_rtraj); cudaFree(h->d_rfinal);
@@ -573,16 +463,17 @@ extern "C" int cps_mppi_step(cps_handle *h, const float *s_dev, const float *noi
                                  traj_layout, u_run_out_dev);
     MppiArgs a;
     a.ode = h->ode; a.cost = h->cost; a.mp = h->mp;
-    a.s = s_dev; a.noise = noise_dev;
+    SolveIO &io = a.io;
+    io.s = s_dev; io.noise = noise_dev;
     const long long K = h->cfg.num_rollouts;
-    if (noise_layout == CPS_TIME_MAJOR) { a.ns_i = K; a.ns_k = 1; }
-    else { a.ns_i = 1; a.ns_k = h->n_red; }
-    a.u_prev = u_prev;
-    a.u_nom = u_nom_dev; a.u_out = u_out_dev; a.J_out = J_out_dev; a.traj_out = traj_out_dev;
-    traj_strides(traj_layout, K, h->cfg.horizon, a.ts_k, a.ts_t, a.ts_c);
-    a.u_run_out = u_run_out_dev;
-    a.partials = h->d_partials; a.ticket = h->d_ticket; a.nonfinite = h->d_nonfinite;
-    a.shard_out = h->shard ? h->shard_out : nullptr;
+    if (noise_layout == CPS_TIME_MAJOR) { io.ns_i = K; io.ns_k = 1; }
+    else { io.ns_i = 1; io.ns_k = h->n_red; }
+    io.u_prev = u_prev;
+    io.u_nom = u_nom_dev; io.u_out = u_out_dev; io.J_out = J_out_dev; io.traj_out = traj_out_dev;
+    traj_strides(traj_layout, K, h->cfg.horizon, io.ts_k, io.ts_t, io.ts_c);
+    io.u_run_out = u_run_out_dev;
+    io.partials = h->d_partials; io.ticket = h->d_ticket; io.nonfinite = h->d_nonfinite;
+    io.shard_out = h->shard ? h->shard_out : nullptr;
     mppi_fn fn = pick_mppi(h->cfg);
     if (h->smem > 48 * 1024) CUDA_TRY(h, cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
     fn<<<h->grid, h->block, h->smem, h->stream>>>(a);

@@ -237,6 +237,49 @@ int cps_stage_cost(cps_handle *h, const float *states_dev, int rows, const float
 /* get_terminal_cost (default.py:44-68 etc.): states_dev [K][6] -> out_dev [K]. */
 int cps_terminal_cost(cps_handle *h, const float *states_dev, int K, float *out_dev);
 
+/* ---- fleet: E independent closed-loop experiments advanced together ---------------------------------------- */
+/* BASELINE configs[4] (data_generator: 8192 independent MPPI-controlled cartpoles).  What run_data_generator does
+ * for ONE cartpole per process (CartPole/data_generator.py via CartPole/__init__.py:659-739: every dt_controller
+ * the controller solves, then the plant -- CartPole.update_state, :283-324 -- advances sim_substeps ticks of
+ * dt_simulation with the control held) happens here for E cartpoles per launch, on the device, with no host round
+ * trip between periods.  Each experiment owns its state, nominal inputs u_nom[T], last control, targets and noise
+ * stream; the handle's (K, T, n, integrator, cost, MPPI parameters) are shared.  The plant uses the handle's physical
+ * parameters (cps_set_physics); the controller's model uses L / m_pole from cps_set_variable_parameters.
+ * Control disturbance, measurement noise and latency (all off in the shipped configuration,
+ * cartpole_physical_parameters.yml:13-18) are not modelled. */
+#define CPS_FLEET_NOISE_SUPPLIED 0  /* caller passes standard-normal draws [period][E][n_ind][K] */
+#define CPS_FLEET_NOISE_PHILOX 1    /* drawn in the kernel: Philox4x32-10 + Box-Muller, counter = (rollout, draw group,
+                                       period, experiment_offset + e), key = seed; cps_fleet_noise materialises them */
+#define CPS_FLEET_RECORD 16         /* floats per record row: time, angle, angleD, angleDD, angle_cos, angle_sin, position,
+                                       positionD, positionDD, Q_calculated, Q_applied, u, target_position,
+                                       target_equilibrium, 0, 0 (the CSV columns of CartPole/__init__.py:221-258) */
+typedef struct cps_fleet_config {
+    int struct_size;                 /* = sizeof(cps_fleet_config) */
+    int n_experiments;               /* E on this device */
+    int sim_substeps;                /* plant ticks per controller period: dt.control / dt.simulation (config_data_gen.yml:25-27) */
+    int noise_source;                /* CPS_FLEET_NOISE_* */
+    double dt_simulation;            /* plant tick, 0.002 s */
+    unsigned long long seed;
+    long long experiment_offset;     /* global index of local experiment 0 (sharding over GPUs) */
+} cps_fleet_config;
+int cps_fleet_create(cps_handle *h, const cps_fleet_config *cfg);
+/* s_host [E][6]: initial states (angle_cos / angle_sin are taken as given).  Zeroes u_nom and the last control
+ * (optimizer_reset + Q_ccrc = 0, CartPole/__init__.py:871) and sets the period counter. */
+int cps_fleet_set_states(cps_handle *h, const float *s_host, long long period);
+/* Any of the outputs may be NULL: s_host [E][6], u_nom_host [E][T], u_prev_host [E].  Synchronises. */
+int cps_fleet_get_states(cps_handle *h, float *s_host, float *u_nom_host, float *u_prev_host);
+long long cps_fleet_period(const cps_handle *h);
+/* Advance every experiment by n_periods controller periods (one launch each, stream-ordered, no synchronisation).
+ * tp_dev / te_dev: [n_periods][E] target position / equilibrium seen by the controller in each period (NULL: 0 / +1;
+ * the reference evaluates random_track_f(time) and the up/down flip schedule on the plant tick that precedes the
+ * solve, CartPole/__init__.py:360-388); noise_dev: [n_periods][E][n_ind][K] for CPS_FLEET_NOISE_SUPPLIED, else NULL;
+ * record_dev: [n_periods][E][CPS_FLEET_RECORD] (row = state at the START of the period with the control chosen for
+ * it, what save_csv_routine logs at dt_save = dt_controller) or NULL; J_out_dev: [n_periods][E][K] or NULL. */
+int cps_fleet_step(cps_handle *h, int n_periods, const float *tp_dev, const float *te_dev, const float *noise_dev,
+                   float *record_dev, float *J_out_dev);
+/* The draws CPS_FLEET_NOISE_PHILOX uses in controller period `period`: out_dev [E][n_ind][K]. */
+int cps_fleet_noise(cps_handle *h, long long period, float *out_dev);
+
 /* Roofline denominators for the compute-bound rollout kernels, measured on this device with two microbenchmarks
  * (dense FFMA chains; MUFU.EX2 chains): FP32 TFLOP/s (FMA = 2 flops) and MUFU Gop/s.  Synchronises. */
 int cps_measure_peaks(cps_handle *h, double *fp32_tflops, double *mufu_gops);

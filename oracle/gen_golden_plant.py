@@ -174,9 +174,38 @@ def gen_closed_loop():
         print(f"closed_loop_{name}: {len(ctrl.calls)} solves, final state {states[-1]}")
 
 
+def gen_datagen():
+    """Host-side pieces of the data generator: generate_random_initial_state (CartPole/data_generator.py:238-275) and
+    Generate_Random_Trace_Function (CartPole/random_target_generator.py:9-87) with seeded numpy Generators."""
+    from CartPole.data_generator import generate_random_initial_state
+    from CartPole.random_target_generator import Generate_Random_Trace_Function
+    from CartPole.state_utilities import create_cartpole_state
+    out = {}
+    times = np.concatenate([[0.0], np.cumsum(np.full(1800, 0.002))])[::10]
+    for seed in range(6):
+        rng = np.random.default_rng([5, seed])
+        stub = create_cartpole_state()
+        stub[:] = np.nan
+        s0 = generate_random_initial_state(stub, init_limits=[0.8, 0.5, [0.0, 180.0], 1200.0], rng=rng)
+        itype = ("previous", "0-derivative-smooth", "linear")[seed % 3]
+        end_at = 1.0 * 0.198 * rng.uniform(-1.0, 1.0)
+        f = Generate_Random_Trace_Function(length_of_experiment=3.6 if seed < 4 else 0.9, rtf_rng=rng,
+                                           track_relative_complexity=2.0, interpolation_type=itype, turning_points=None,
+                                           turning_points_period="regular" if seed % 2 == 0 else "random",
+                                           start_random_target_position_at=float(s0[4]),
+                                           end_random_target_position_at=end_at, used_track_fraction=1.0)
+        out[f"s0_{seed}"] = np.asarray(s0, np.float32)
+        out[f"tp_{seed}"] = np.asarray(f(np.minimum(times, 3.6 if seed < 4 else 0.9)), np.float64)
+    meta = dict(entry="generate_random_initial_state + Generate_Random_Trace_Function with np.random.default_rng([5, seed])",
+                n=6)
+    np.savez_compressed(os.path.join(GOLDEN, "datagen_host.npz"), times=times, meta=json.dumps(meta), **out)
+    print("datagen_host: 6 seeds")
+
+
 if __name__ == "__main__":
     R.load()
     os.makedirs(GOLDEN, exist_ok=True)
     gen_plant()
+    gen_datagen()
     if "--no-closed-loop" not in sys.argv:
         gen_closed_loop()
