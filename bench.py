@@ -192,6 +192,21 @@ def mppi_latency(device, n_calls=1000):
     out["neural_GRU_2x64"] = neural_latency(device, n_calls=min(n_calls, 300))
     out["neural_GRU_2x64_K65536"] = neural_big(device)
     out["ODE_K65536_T100"] = big_solve(device)
+    try:
+        out["fleet_1024x2000x50"] = fleet_bench(device, E_total=1024, periods=20)
+        from oracle import oracle as O
+        O.lib().cps_oracle_set_num_threads(os.cpu_count() or 1)
+        eps = np.random.default_rng(0).standard_normal((K, 6)).astype(np.float32)
+        s = np.array([np.pi - 1e-3, 0.0, np.cos(np.pi - 1e-3), np.sin(np.pi - 1e-3), 0.0, 0.0], dtype=np.float32)
+        O.mppi_step("ODE", "quadratic_boundary_grad_minimal", s, np.zeros(T, np.float32), eps=eps[:64])
+        t0 = time.perf_counter()
+        for _ in range(5):
+            r = O.mppi_step("ODE", "quadratic_boundary_grad_minimal", s, np.zeros(T, np.float32), eps=eps)
+            O.plant_period(s, float(r["u"]))
+        out["fleet_1024x2000x50"]["cpu_port_ms_per_experiment_period"] = (time.perf_counter() - t0) / 5 * 1e3
+        out["fleet_1024x2000x50"]["cpu_port_threads"] = O.lib().cps_oracle_num_threads()
+    except Exception as ex:
+        out["fleet_1024x2000x50"] = {"error": repr(ex)}
     return out
 
 
@@ -290,6 +305,41 @@ def big_solve(device):
         kms = float(np.median(ks))
         out[cost] = {"kernel_ms_median": kms, "state_steps_per_s": K * T * N_SUB / (kms * 1e-3)}
         eng.close()
+    return out
+
+
+def fleet_bench(device, E_total=8192, world=1, rank=0, periods=20, K=2000, T=50):
+    """BASELINE.json configs[4]: data_generator with 8192 independent MPPI-controlled cartpoles (K=2000, T=50 each),
+    sharded over the ranks (no data-path collective).  One launch = one controller period of every local experiment:
+    MPPI solve + plant, noise drawn in the kernel (Philox), targets from the host-side data-generator tables."""
+    import torch
+    from cartpolesimulation_b200.fleet import DataGenConfig, Fleet, make_experiments
+    E = E_total // world
+    off = rank * E
+    cfg = DataGenConfig(length_of_experiment=max(2.0, periods * 0.02 * 2))
+    s0, tp, te = make_experiments(E, periods, cfg, seed=0, experiment_offset=off)
+    fl = Fleet(E, K, T, integrator="ODE", cost="quadratic_boundary_grad_minimal", noise="philox", seed=0,
+               experiment_offset=off, device=device)
+    tp_d, te_d = torch.from_numpy(tp).to(fl.device), torch.from_numpy(te).to(fl.device)
+    rec = torch.zeros((periods, E, 16), device=fl.device)
+    fl.reset(s0)
+    fl.run(min(3, periods), tp_d[:3].contiguous(), te_d[:3].contiguous(), None, None)   # warm-up
+    fl.reset(s0)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    fl.run(periods, tp_d, te_d, None, rec)
+    e1.record()
+    e1.synchronize()
+    ms = e0.elapsed_time(e1)
+    rec_h = rec.cpu().numpy()
+    out = {"experiments_total": E_total, "experiments_per_gpu": E, "K": K, "T": T, "periods": periods,
+           "ms_per_period": ms / periods, "experiment_periods_per_s_per_gpu": E * periods / (ms * 1e-3),
+           "state_steps_per_s_per_gpu": float(E) * K * T * N_SUB * periods / (ms * 1e-3),
+           "sim_seconds_per_wall_second_per_gpu": E * periods * 0.02 / (ms * 1e-3),
+           "finite": bool(np.isfinite(rec_h).all()), "launches": periods,
+           "d2h_record_bytes": int(rec.numel() * 4)}
+    fl.close()
     return out
 
 
@@ -399,11 +449,20 @@ def run_ours(args):
     d2h = traj_pin.numel() * 4
 
     sharded = None
+    fleet = None
     if world > 1 and not args.no_mppi:
         try:
             sharded = sharded_solve(local_rank, world)
         except Exception as ex:
             sharded = {"error": repr(ex)}
+        try:  # configs[4]: 8192 experiments over the ranks; the slowest rank's time decides
+            fleet = fleet_bench(local_rank, E_total=8192, world=world, rank=rank, periods=10)
+            t = torch.tensor([fleet["ms_per_period"]], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            fleet["ms_per_period_max_over_ranks"] = float(t.item())
+            fleet["state_steps_per_s_all_gpus"] = 8192.0 * 2000 * 50 * N_SUB / (float(t.item()) * 1e-3)
+        except Exception as ex:
+            fleet = {"error": repr(ex)}
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -462,7 +521,7 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * e2e_s / e2e_steps, "api": "cps_rollout_host (pinned host buffers)"},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
-            "clocks": sampler.summary(), "mppi_solve": mppi, "mppi_sharded": sharded}
+            "clocks": sampler.summary(), "mppi_solve": mppi, "mppi_sharded": sharded, "fleet_sharded": fleet}
     print(json.dumps(line))
     if world > 1:
         dist.barrier()

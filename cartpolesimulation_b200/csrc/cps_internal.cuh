@@ -83,6 +83,10 @@ struct cps_handle {
     // growable buffers of cps_rollout_host
     float *d_rs0, *d_rQ, *d_rtraj, *d_rfinal;
     size_t cap_rs0, cap_rQ, cap_rtraj, cap_rfinal;
+    // cps_rollout_host pipeline: copy-in / copy-out streams and per-chunk events (created on first use)
+    cudaStream_t st_in, st_out;
+    cudaEvent_t ev_start, ev_in[16], ev_k[16];
+    int pipe_ready;
     long long launches;
     std::string err;
     NetState *net;      // neural predictor (cps_net_load), owned

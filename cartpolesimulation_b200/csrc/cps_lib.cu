@@ -321,6 +321,10 @@ extern "C" void cps_destroy(cps_handle *h) {
     cudaFree(h->d_s); cudaFree(h->d_unom); cudaFree(h->d_u);
     cudaFree(h->d_rs0); cudaFree(h->d_rQ); cudaFree(h->d_rtraj); cudaFree(h->d_rfinal);
     if (h->h_pin) cudaFreeHost(h->h_pin);
+    if (h->pipe_ready) {
+        cudaStreamDestroy(h->st_in); cudaStreamDestroy(h->st_out); cudaEventDestroy(h->ev_start);
+        for (int i = 0; i < 16; ++i) { cudaEventDestroy(h->ev_in[i]); cudaEventDestroy(h->ev_k[i]); }
+    }
     delete h;
 }
 
@@ -555,17 +559,20 @@ extern "C" int cps_mppi_finalize(cps_handle *h, const float *partials_dev, int n
 }
 
 // ---- open-loop rollouts -------------------------------------------------------------------------------
+// B cartpoles starting at the given pointers; B_full is the batch size the time-major strides refer to (a chunk of a
+// larger batch keeps the full batch's row pitch).
 static int rollout_launch(cps_handle *h, const float *s0, int s0_batched, const float *Q, int q_layout, int B, int T,
-                          float *traj, int traj_layout, float *fin) {
+                          float *traj, int traj_layout, float *fin, long long B_full = -1) {
+    if (B_full < 0) B_full = B;
     RolloutArgs a;
     a.ode = h->ode;
     a.s0 = s0; a.ss_b = s0_batched ? 6 : 0;
     a.Q = Q;
-    if (q_layout == CPS_TIME_MAJOR) { a.qs_b = 1; a.qs_t = B; }
+    if (q_layout == CPS_TIME_MAJOR) { a.qs_b = 1; a.qs_t = B_full; }
     else { a.qs_b = T; a.qs_t = 1; }
     a.B = B; a.T = T;
     a.traj_out = traj;
-    traj_strides(traj_layout, B, T, a.ts_k, a.ts_t, a.ts_c);
+    traj_strides(traj_layout, B_full, T, a.ts_k, a.ts_t, a.ts_c);
     a.final_out = fin;
     const int block = (B <= 148 * 32 * 4) ? 32 : 128;
     long long grid = ((long long)B + block - 1) / block;
@@ -619,6 +626,58 @@ extern "C" int cps_rollout_host(cps_handle *h, const float *s0_host, int s0_batc
     if ((rc = grow(h, &h->d_rQ, &h->cap_rQ, n_Q)) != CPS_OK) return rc;
     if (traj_out_host && (rc = grow(h, &h->d_rtraj, &h->cap_rtraj, n_traj)) != CPS_OK) return rc;
     if (final_out_host && (rc = grow(h, &h->d_rfinal, &h->cap_rfinal, n_fin)) != CPS_OK) return rc;
+    // Large ODE batches: split into chunks and pipeline copy-in / kernel / copy-out on three streams, so that the
+    // host->device copies of chunk c+1 and the kernel of chunk c run under the device->host copy of chunk c-1 (PCIe
+    // is full duplex; the trajectory copy-out is the long pole).  Time-major arrays are copied as 2-D slabs.
+    const int n_chunks = (h->cfg.integrator != CPS_PREDICTOR_NEURAL && B >= (1 << 16)) ? 8 : 1;
+    if (n_chunks > 1) {
+        if (!h->pipe_ready) {
+            CUDA_TRY(h, cudaStreamCreateWithFlags(&h->st_in, cudaStreamNonBlocking));
+            CUDA_TRY(h, cudaStreamCreateWithFlags(&h->st_out, cudaStreamNonBlocking));
+            CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_start, cudaEventDisableTiming));
+            for (int i = 0; i < 16; ++i) {
+                CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
+                CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_k[i], cudaEventDisableTiming));
+            }
+            h->pipe_ready = 1;
+        }
+        // everything queued on the handle's stream so far happens before the pipeline starts
+        CUDA_TRY(h, cudaEventRecord(h->ev_start, h->stream));
+        CUDA_TRY(h, cudaStreamWaitEvent(h->st_in, h->ev_start, 0));
+        CUDA_TRY(h, cudaStreamWaitEvent(h->st_out, h->ev_start, 0));
+        const size_t rows = (size_t)(T + 1) * 6, pitch = sizeof(float) * (size_t)B;
+        if (!s0_batched) CUDA_TRY(h, cudaMemcpyAsync(h->d_rs0, s0_host, n_s0, cudaMemcpyHostToDevice, h->st_in));
+        for (int c = 0; c < n_chunks; ++c) {
+            const long long b0 = (long long)B * c / n_chunks, b1 = (long long)B * (c + 1) / n_chunks, nb = b1 - b0;
+            if (s0_batched)
+                CUDA_TRY(h, cudaMemcpyAsync(h->d_rs0 + b0 * 6, s0_host + b0 * 6, sizeof(float) * 6 * nb, cudaMemcpyHostToDevice, h->st_in));
+            if (q_layout == CPS_TIME_MAJOR)
+                CUDA_TRY(h, cudaMemcpy2DAsync(h->d_rQ + b0, pitch, Q_host + b0, pitch, sizeof(float) * nb, T, cudaMemcpyHostToDevice, h->st_in));
+            else
+                CUDA_TRY(h, cudaMemcpyAsync(h->d_rQ + b0 * T, Q_host + b0 * T, sizeof(float) * nb * T, cudaMemcpyHostToDevice, h->st_in));
+            CUDA_TRY(h, cudaEventRecord(h->ev_in[c], h->st_in));
+            CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_in[c], 0));
+            const float *q_c = h->d_rQ + (q_layout == CPS_TIME_MAJOR ? b0 : b0 * T);
+            float *traj_c = traj_out_host ? h->d_rtraj + (traj_layout == CPS_TIME_MAJOR ? b0 : b0 * (long long)rows) : nullptr;
+            float *fin_c = final_out_host ? h->d_rfinal + b0 * 6 : nullptr;
+            rc = rollout_launch(h, h->d_rs0 + (s0_batched ? b0 * 6 : 0), s0_batched, q_c, q_layout, (int)nb, T, traj_c,
+                                traj_layout, fin_c, B);
+            if (rc != CPS_OK) return rc;
+            CUDA_TRY(h, cudaEventRecord(h->ev_k[c], h->stream));
+            CUDA_TRY(h, cudaStreamWaitEvent(h->st_out, h->ev_k[c], 0));
+            if (traj_out_host) {
+                if (traj_layout == CPS_TIME_MAJOR)
+                    CUDA_TRY(h, cudaMemcpy2DAsync(traj_out_host + b0, pitch, h->d_rtraj + b0, pitch, sizeof(float) * nb, rows, cudaMemcpyDeviceToHost, h->st_out));
+                else
+                    CUDA_TRY(h, cudaMemcpyAsync(traj_out_host + b0 * rows, h->d_rtraj + b0 * rows, sizeof(float) * nb * rows, cudaMemcpyDeviceToHost, h->st_out));
+            }
+            if (final_out_host)
+                CUDA_TRY(h, cudaMemcpyAsync(final_out_host + b0 * 6, h->d_rfinal + b0 * 6, sizeof(float) * 6 * nb, cudaMemcpyDeviceToHost, h->st_out));
+        }
+        CUDA_TRY(h, cudaStreamSynchronize(h->st_out));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        return CPS_OK;
+    }
     CUDA_TRY(h, cudaMemcpyAsync(h->d_rs0, s0_host, n_s0, cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(h, cudaMemcpyAsync(h->d_rQ, Q_host, n_Q, cudaMemcpyHostToDevice, h->stream));
     if (h->cfg.integrator == CPS_PREDICTOR_NEURAL)

@@ -314,3 +314,36 @@ def test_error_behaviour():
     # empty batch is a no-op, not an error
     t, _ = eng.rollout(torch.zeros(6, device="cuda"), torch.zeros((0, 10), device="cuda"))
     assert t.shape == (0, 11, 6)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B", [1000, 70001])
+@pytest.mark.parametrize("layout", ["time_major", "rollout_major"])
+def test_rollout_host_pipelined_chunks_bit_identical(layout, B):
+    """cps_rollout_host splits batches >= 65536 into 8 chunks pipelined over three streams (2-D slab copies for the
+    time-major arrays); the result must be bit-identical to the single-launch device path, ragged chunk sizes included."""
+    import torch
+    from cartpolesimulation_b200 import _lib as L
+    from cartpolesimulation_b200.core import Engine
+    T = 6
+    rng = np.random.default_rng(5)
+    ang = rng.uniform(-np.pi, np.pi, B).astype(np.float32)
+    s0 = np.stack([ang, rng.uniform(-5, 5, B), np.cos(ang), np.sin(ang), rng.uniform(-0.19, 0.19, B),
+                   rng.uniform(-1, 1, B)], 1).astype(np.float32)
+    lay = L.TIME_MAJOR if layout == "time_major" else L.ROLLOUT_MAJOR
+    Q = rng.uniform(-1, 1, (T, B) if lay == L.TIME_MAJOR else (B, T)).astype(np.float32)
+    eng = Engine(64, T, integrator="ODE_v0", cost=None)
+    traj_d, fin_d = eng.rollout(torch.from_numpy(s0).cuda(), torch.from_numpy(Q).cuda(), q_layout=lay, traj_layout=lay,
+                                want_final=True)
+    torch.cuda.synchronize()
+    traj_h = np.full(tuple(traj_d.shape), np.nan, dtype=np.float32)
+    fin_h = np.full((B, 6), np.nan, dtype=np.float32)
+    eng.rollout_host(s0, Q, lay, lay, traj_out=traj_h, final_out=fin_h)
+    np.testing.assert_array_equal(traj_h, traj_d.cpu().numpy())
+    np.testing.assert_array_equal(fin_h, fin_d.cpu().numpy())
+    # shared initial state (tiled), trajectory only
+    traj_d2, _ = eng.rollout(torch.from_numpy(s0[0]).cuda(), torch.from_numpy(Q).cuda(), q_layout=lay, traj_layout=lay)
+    traj_h2 = np.full(tuple(traj_d2.shape), np.nan, dtype=np.float32)
+    eng.rollout_host(s0[0], Q, lay, lay, traj_out=traj_h2)
+    np.testing.assert_array_equal(traj_h2, traj_d2.cpu().numpy())
+    eng.close()
