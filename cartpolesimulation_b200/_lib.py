@@ -23,7 +23,8 @@ COST_NONE, COST_DEFAULT, COST_QUADRATIC_BOUNDARY, COST_QB_GRAD_MINIMAL, COST_QB_
 NOISE_INDUCING, NOISE_DIRECT = 0, 1
 ROLLOUT_MAJOR, TIME_MAJOR = 0, 1
 FLAG_FAST_SINCOS, FLAG_EXACT_ATAN2, FLAG_FAST_DIV, FLAG_SUBSTEP_SINCOS = 0x1, 0x2, 0x4, 0x8
-FLAG_NET_TENSOR_CORES, FLAG_NET_FP32 = 0x10, 0x20
+FLAG_NET_TENSOR_CORES, FLAG_NET_FP32, FLAG_NO_PAIRS = 0x10, 0x20, 0x40
+PAIR_MIN_BATCH = 262144
 PH_COUNT = 9
 FLEET_NOISE_SUPPLIED, FLEET_NOISE_PHILOX, FLEET_RECORD = 0, 1, 16
 FLEET_RECORD_COLUMNS = ("time", "angle", "angleD", "angleDD", "angle_cos", "angle_sin", "position", "positionD",

@@ -46,7 +46,7 @@ class Engine:
                  integrator: str = "ODE", cost: str | None = "quadratic_boundary_grad_minimal",
                  noise_mode: str = "inducing", interp_period: int = 10, device: int | None = None,
                  fast_sincos: bool = False, exact_atan2: bool = False, fast_div: bool = False,
-                 substep_sincos: bool = False, net_kernel: str | None = None):
+                 substep_sincos: bool = False, net_kernel: str | None = None, no_pairs: bool = False):
         if integrator not in INTEGRATORS:
             raise ValueError(f"unknown integrator {integrator!r}; expected one of {list(INTEGRATORS)}")
         if cost not in COSTS:
@@ -63,6 +63,7 @@ class Engine:
         if net_kernel not in (None, "tensor", "fp32"):
             raise ValueError("net_kernel must be None (choose by batch size), 'tensor' or 'fp32'")
         flags |= {None: 0, "tensor": L.FLAG_NET_TENSOR_CORES, "fp32": L.FLAG_NET_FP32}[net_kernel]
+        flags |= L.FLAG_NO_PAIRS if no_pairs else 0
         self.K, self.T, self.n, self.dt, self.p = int(num_rollouts), int(horizon), int(substeps), float(dt), int(interp_period)
         self.integrator, self.cost_name = integrator, cost
         self.noise_mode = {"inducing": L.NOISE_INDUCING, "direct": L.NOISE_DIRECT}[noise_mode]

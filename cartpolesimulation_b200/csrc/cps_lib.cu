@@ -57,10 +57,49 @@ __global__ void __launch_bounds__(256, 4) rollout_kernel(const __grid_constant__
             const float Q = qn;
             if (t + 1 < a.T) qn = q[(long long)(t + 1) * a.qs_t];  // prefetch under the integration
             if (traj) store_state(traj + (long long)t * a.ts_t, a.ts_c, z);
-            control_step<INTEG, SC, FAST_DIV, EXACT_ATAN2>(ode, z, Q);
+            control_step<INTEG, SC, FAST_DIV, EXACT_ATAN2, true>(ode, z, Q);
         }
         if (traj) store_state(traj + (long long)a.T * a.ts_t, a.ts_c, z);
         if (a.final_out) store_state(a.final_out + b * 6, 1, z);
+    }
+}
+
+// Two cartpoles per thread (packed FP32, see cps_device.cuh "two cartpoles per thread"): thread p owns cartpoles
+// 2p and 2p+1 of a time-major batch, so controls arrive as one 8-byte load and every state channel leaves as one
+// 8-byte store per control step (256 B per warp and channel).  Bit-identical to rollout_kernel<INTEG, SC_ROTATE>.
+__device__ __forceinline__ void store_state2(float *base, long long ts_c, const State2 &z) {
+    *reinterpret_cast<unsigned long long *>(base + 0 * ts_c) = z.th.v;
+    *reinterpret_cast<unsigned long long *>(base + 1 * ts_c) = z.w.v;
+    *reinterpret_cast<unsigned long long *>(base + 2 * ts_c) = z.c.v;
+    *reinterpret_cast<unsigned long long *>(base + 3 * ts_c) = z.s.v;
+    *reinterpret_cast<unsigned long long *>(base + 4 * ts_c) = z.x.v;
+    *reinterpret_cast<unsigned long long *>(base + 5 * ts_c) = z.v.v;
+}
+
+template <int INTEG, bool FAST_DIV>
+__global__ void __launch_bounds__(128) rollout_pair_kernel(const __grid_constant__ RolloutArgs a) {
+    const OdeParams ode = pin_params(a.ode, a.s0[0]);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long n_pairs = (long long)a.B >> 1;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n_pairs; p += stride) {
+        const long long b = 2 * p;
+        State2 z = join_states(load_state(a.s0 + b * a.ss_b), load_state(a.s0 + (b + 1) * a.ss_b));
+        const float *q = a.Q + b;
+        float *traj = a.traj_out ? a.traj_out + b : nullptr;
+        unsigned long long qn = *reinterpret_cast<const unsigned long long *>(q);
+#pragma unroll 1
+        for (int t = 0; t < a.T; ++t) {
+            F2 Q;
+            Q.v = qn;
+            if (t + 1 < a.T) qn = *reinterpret_cast<const unsigned long long *>(q + (long long)(t + 1) * a.qs_t);
+            if (traj) store_state2(traj + (long long)t * a.ts_t, a.ts_c, z);
+            control_step2<INTEG, FAST_DIV>(ode, z, Q);
+        }
+        if (traj) store_state2(traj + (long long)a.T * a.ts_t, a.ts_c, z);
+        if (a.final_out) {
+            store_state(a.final_out + b * 6, 1, half_state(z, 0));
+            store_state(a.final_out + (b + 1) * 6, 1, half_state(z, 1));
+        }
     }
 }
 
@@ -574,12 +613,30 @@ static int rollout_launch(cps_handle *h, const float *s0, int s0_batched, const 
     a.traj_out = traj;
     traj_strides(traj_layout, B_full, T, a.ts_k, a.ts_t, a.ts_c);
     a.final_out = fin;
-    const int block = (B <= 148 * 32 * 4) ? 32 : 128;
-    long long grid = ((long long)B + block - 1) / block;
-    const long long max_grid = 148LL * 16 * 8;  // grid-stride beyond 8 full waves
-    if (grid > max_grid) grid = max_grid;
-    rollout_fn fn = pick_rollout(h->cfg);
-    fn<<<(unsigned)grid, block, 0, h->stream>>>(a);
+    // Large time-major batches in rotation mode: two cartpoles per thread with packed FP32 (needs an even batch and
+    // 8-byte aligned rows; below ~2 cartpoles per resident thread the one-per-thread kernel hides latency better).
+    const bool pairs = sc_mode(h->cfg.flags) == SC_ROTATE && !(h->cfg.flags & CPS_FLAG_NO_PAIRS) && B >= CPS_PAIR_MIN_BATCH &&
+                       (B % 2) == 0 && (B_full % 2) == 0 && q_layout == CPS_TIME_MAJOR &&
+                       (!traj || traj_layout == CPS_TIME_MAJOR) && ((uintptr_t)Q % 8) == 0 && ((uintptr_t)traj % 8) == 0;
+    if (pairs) {
+        const int block = 128;
+        long long grid = ((long long)(B / 2) + block - 1) / block;
+        const long long max_grid = 148LL * 16 * 8;
+        if (grid > max_grid) grid = max_grid;
+        rollout_fn fn;
+        if (h->cfg.integrator == CPS_EULER_V0)
+            fn = (h->cfg.flags & CPS_FLAG_FAST_DIV) ? rollout_pair_kernel<0, true> : rollout_pair_kernel<0, false>;
+        else
+            fn = (h->cfg.flags & CPS_FLAG_FAST_DIV) ? rollout_pair_kernel<1, true> : rollout_pair_kernel<1, false>;
+        fn<<<(unsigned)grid, block, 0, h->stream>>>(a);
+    } else {
+        const int block = (B <= 148 * 32 * 4) ? 32 : 128;
+        long long grid = ((long long)B + block - 1) / block;
+        const long long max_grid = 148LL * 16 * 8;  // grid-stride beyond 8 full waves
+        if (grid > max_grid) grid = max_grid;
+        rollout_fn fn = pick_rollout(h->cfg);
+        fn<<<(unsigned)grid, block, 0, h->stream>>>(a);
+    }
     h->launches += 1;
     CUDA_TRY(h, cudaGetLastError());
     return CPS_OK;

@@ -77,6 +77,9 @@ typedef enum cps_layout { CPS_ROLLOUT_MAJOR = 0, CPS_TIME_MAJOR = 1 } cps_layout
 #define CPS_FLAG_SUBSTEP_SINCOS 0x8u  /* evaluate sin/cos of the angle in EVERY substep, literally as
                                          cartpole_equations.py:245-248 / cartpole_numba.py:66-76 do */
 
+#define CPS_FLAG_NO_PAIRS 0x40u         /* open-loop rollouts: never use the two-cartpoles-per-thread packed-FP32 kernel
+                                           (it is bit-identical to the one-per-thread kernel; the flag exists for A/B timing) */
+#define CPS_PAIR_MIN_BATCH 262144       /* smallest batch the packed-pair rollout kernel is used for */
 #define CPS_FLAG_NET_TENSOR_CORES 0x10u /* neural predictor: force the tcgen05 tensor-core kernel (2 x 64 GRU only) */
 #define CPS_FLAG_NET_FP32 0x20u         /* neural predictor: force the FP32 CUDA-core kernel (default: by batch size) */
 

@@ -347,3 +347,45 @@ def test_rollout_host_pipelined_chunks_bit_identical(layout, B):
     eng.rollout_host(s0[0], Q, lay, lay, traj_out=traj_h2)
     np.testing.assert_array_equal(traj_h2, traj_d2.cpu().numpy())
     eng.close()
+
+
+@pytest.mark.parametrize("shared_s0", [False, True])
+@pytest.mark.parametrize("integ", ["ODE_v0", "ODE"])
+def test_rollout_pair_kernel_bit_identical(integ, shared_s0):
+    """Large time-major batches run two cartpoles per thread with packed FP32 (rollout_pair_kernel: FFMA2/FMUL2/FADD2).
+    Each half performs the arithmetic of the one-per-thread kernel, so trajectories and final states must be
+    bit-identical -- including pairs in which one or both cartpoles hit the track end (edge_bounce) or spin fast
+    enough (|h * angleD| > 0.2) to take the guarded path, and a sample of rows must agree with the oracle."""
+    from oracle import oracle as O
+    L = _L()
+    B, T = L.PAIR_MIN_BATCH, 12
+    rng = np.random.default_rng(21)
+    ang = rng.uniform(-np.pi, np.pi, B).astype(np.float32)
+    s0 = np.stack([ang, rng.uniform(-6, 6, B), np.cos(ang), np.sin(ang), rng.uniform(-0.16, 0.16, B),
+                   rng.uniform(-0.4, 0.4, B)], 1).astype(np.float32)
+    s0[::7, 4] = rng.choice([-1.0, 1.0], s0[::7].shape[0]) * rng.uniform(0.18, 0.1979, s0[::7].shape[0])  # near the track end
+    s0[::7, 5] = np.sign(s0[::7, 4]) * rng.uniform(0.3, 1.0, s0[::7].shape[0])                              # moving outwards
+    s0[5::1001, 1] = rng.choice([-1.0, 1.0], s0[5::1001].shape[0]) * rng.uniform(101.0, 140.0, s0[5::1001].shape[0])  # |d| > 0.2
+    Q = rng.uniform(-1, 1, (T, B)).astype(np.float32)
+    s_in = cuda(s0[3] if shared_s0 else s0)
+    Qd = cuda(Q)
+    outs = []
+    for no_pairs in (False, True):
+        eng = _engine(B, T, integrator=integ, cost=None, no_pairs=no_pairs)
+        traj, fin = eng.rollout(s_in, Qd, q_layout=L.TIME_MAJOR, traj_layout=L.TIME_MAJOR, want_final=True)
+        torch.cuda.synchronize()
+        outs.append((traj, fin))
+        eng.close()
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert torch.equal(outs[0][1], outs[1][1])
+    # final-state-only launch takes the same path
+    eng = _engine(B, T, integrator=integ, cost=None)
+    _, fin2 = eng.rollout(s_in, Qd, q_layout=L.TIME_MAJOR, want_traj=False, want_final=True)
+    assert torch.equal(fin2, outs[0][1])
+    eng.close()
+    if not shared_s0:
+        rows = np.r_[0:256, 5:B:1001][:512]
+        ref = O.rollout(integ, s0[rows], np.ascontiguousarray(Q[:, rows].T), want_traj=False)
+        calm = np.abs(s0[rows, 1]) < 50
+        e = traj_err(outs[0][1][rows].cpu().numpy()[calm], ref[calm])
+        assert max(e.values()) < 5e-5, e
