@@ -193,6 +193,10 @@ def mppi_latency(device, n_calls=1000):
     out["neural_GRU_2x64_K65536"] = neural_big(device)
     out["ODE_K65536_T100"] = big_solve(device)
     try:
+        out["legacy_controller_mppi_cartpole"] = legacy_latency(device, n_calls=min(n_calls, 300))
+    except Exception as ex:
+        out["legacy_controller_mppi_cartpole"] = {"error": repr(ex)}
+    try:
         out["fleet_1024x2000x50"] = fleet_bench(device, E_total=1024, periods=20)
         from oracle import oracle as O
         O.lib().cps_oracle_set_num_threads(os.cpu_count() or 1)
@@ -207,6 +211,52 @@ def mppi_latency(device, n_calls=1000):
         out["fleet_1024x2000x50"]["cpu_port_threads"] = O.lib().cps_oracle_num_threads()
     except Exception as ex:
         out["fleet_1024x2000x50"] = {"error": repr(ex)}
+    return out
+
+
+def legacy_latency(device, n_calls=300):
+    """the legacy controller_mppi_cartpole at its shipped configuration (config_controllers.yml:9-30:
+    K=3500, T=35, 'interpolated' sampling, predictor ODE): controller.step(numpy s) -> numpy Q, host-drawn perturbations
+    (numpy SFC64 + scipy interp1d, as in the reference) included; kernel-only time from CUDA events; the CPU port of the
+    same iteration beside it."""
+    import torch
+    from cartpolesimulation_b200.controller_mppi_cartpole_b200 import controller_mppi_cartpole_b200
+    ctrl = controller_mppi_cartpole_b200(dict(seed=1), dt=DT, device=device)
+    K, T = ctrl.num_rollouts, ctrl.mpc_horizon
+    a = np.pi - 1e-3
+    s = np.array([a, 0.0, np.cos(a), np.sin(a), 0.0, 0.0], dtype=np.float32)
+    for _ in range(20):
+        ctrl.step(s)
+    lat, samp = np.empty(n_calls), np.empty(n_calls)
+    for i in range(n_calls):
+        t0 = time.perf_counter()
+        ctrl.step(s)
+        lat[i] = time.perf_counter() - t0
+    for i in range(n_calls):
+        t0 = time.perf_counter()
+        ctrl.initialize_perturbations(stdev=ctrl.SQRTRHODTINV, sampling_type=ctrl.SAMPLING_TYPE)
+        samp[i] = time.perf_counter() - t0
+    eng = ctrl.engine
+    du = torch.from_numpy(np.ascontiguousarray(ctrl.delta_u.T, dtype=np.float32)).to(eng.device)
+    s_dev = torch.from_numpy(s).to(eng.device)
+    ks = _event_times(lambda: eng.legacy_step(s_dev, du, 1), 50, warm=10)
+    out = {"latency_ms_median": float(np.median(lat) * 1e3), "latency_ms_p99": float(np.percentile(lat, 99) * 1e3),
+           "host_sampler_ms_median": float(np.median(samp) * 1e3), "kernel_ms_median": float(np.median(ks)),
+           "calls": n_calls, "K": K, "T": T, "state_steps_per_solve": K * T * N_SUB,
+           "api": "controller_mppi_cartpole_b200.step(numpy s) -> numpy Q (cps_legacy_step_host, legacy_mppi_kernel<ODE>)"}
+    try:
+        from oracle import legacy as OL
+        from oracle import oracle as O
+        O.lib().cps_oracle_set_num_threads(os.cpu_count() or 1)
+        d = np.asarray(ctrl.delta_u, np.float32)
+        OL.iteration("ODE", s, np.zeros(T, np.float32), np.zeros(T, np.float32), d[:64])
+        t0 = time.perf_counter()
+        for _ in range(3):
+            OL.iteration("ODE", s, np.zeros(T, np.float32), np.zeros(T, np.float32), d)
+        out["cpu_port_ms"] = (time.perf_counter() - t0) / 3 * 1e3
+        out["cpu_port_threads"] = O.lib().cps_oracle_num_threads()
+    except Exception as ex:
+        out["cpu_port_ms"] = repr(ex)
     return out
 
 

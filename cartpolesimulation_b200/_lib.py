@@ -20,6 +20,7 @@ STATUS_NAMES = {0: "CPS_OK", 1: "CPS_ERR_INVALID", 2: "CPS_ERR_CUDA", 3: "CPS_ER
 EULER_V0, EULER_CROMER, PREDICTOR_NEURAL = 0, 1, 2
 NET_GRU, NET_DENSE, NET_MAX_LAYERS = 0, 1, 4
 COST_NONE, COST_DEFAULT, COST_QUADRATIC_BOUNDARY, COST_QB_GRAD_MINIMAL, COST_QB_GRAD = -1, 0, 1, 2, 3
+COST_LEGACY_MPPI = 4
 NOISE_INDUCING, NOISE_DIRECT = 0, 1
 ROLLOUT_MAJOR, TIME_MAJOR = 0, 1
 FLAG_FAST_SINCOS, FLAG_EXACT_ATAN2, FLAG_FAST_DIV, FLAG_SUBSTEP_SINCOS = 0x1, 0x2, 0x4, 0x8
@@ -75,6 +76,12 @@ SYMBOLS = {
     "cps_mppi_set_shard": (C.c_int, [_VP, C.c_int, _VP]),
     "cps_mppi_partial_size": (C.c_int, [_VP]),
     "cps_mppi_finalize": (C.c_int, [_VP, _VP, C.c_int, _VP, _VP]),
+    "cps_legacy_step": (C.c_int, [_VP, _VP, _VP, C.c_int, _VP, _VP, _VP, C.c_int, _VP]),
+    "cps_legacy_step_host": (C.c_int, [_VP, _FP, _VP, C.c_int, _FP]),
+    "cps_legacy_advance": (C.c_int, [_VP, _FP]),
+    "cps_legacy_reset": (C.c_int, [_VP]),
+    "cps_legacy_get_inputs": (C.c_int, [_VP, _FP, _FP]),
+    "cps_legacy_set_inputs": (C.c_int, [_VP, _FP, _FP]),
     "cps_rollout": (C.c_int, [_VP, _VP, C.c_int, _VP, C.c_int, C.c_int, C.c_int, _VP, C.c_int, _VP]),
     "cps_rollout_host": (C.c_int, [_VP, _VP, C.c_int, _VP, C.c_int, C.c_int, C.c_int, _VP, C.c_int, _VP]),
     "cps_net_load": (C.c_int, [_VP, C.POINTER(cps_net_desc), _FP, C.c_longlong]),

@@ -31,7 +31,8 @@ INTEGRATORS = {"ODE_v0": L.EULER_V0, "ODE": L.EULER_CROMER, "neural": L.PREDICTO
 COSTS = {None: L.COST_NONE, "none": L.COST_NONE, "default": L.COST_DEFAULT,
          "quadratic_boundary": L.COST_QUADRATIC_BOUNDARY,
          "quadratic_boundary_grad_minimal": L.COST_QB_GRAD_MINIMAL,
-         "quadratic_boundary_grad": L.COST_QB_GRAD}
+         "quadratic_boundary_grad": L.COST_QB_GRAD,
+         "legacy_mppi": L.COST_LEGACY_MPPI}  # q() + phi() of controller_mppi_cartpole (legacy front-end)
 
 
 class Engine:
@@ -177,6 +178,65 @@ class Engine:
         if v.shape[0] != self.T:
             raise ValueError(f"u_nom has {v.shape[0]} entries, expected {self.T}")
         self._chk(self.lib.cps_mppi_set_u_nom(self._h, v.ctypes.data_as(L._FP)))
+
+    # -- legacy front-end (controller_mppi_cartpole) ------------------------------------------------
+    def legacy_step(self, s, delta_u, layout=L.ROLLOUT_MAJOR, S_out=None, traj_out=None, traj_layout=L.ROLLOUT_MAJOR,
+                    u_upd_out=None):
+        """Device-pointer form (cps_legacy_step).  s: cuda [6]; delta_u: cuda K x T in `layout` order.  Returns the cuda
+        tensor [1] holding u[0] after the update (no synchronisation)."""
+        self.use_current_stream()
+        _check_dev(s, "s", self.device)
+        _check_dev(delta_u, "delta_u", self.device)
+        if delta_u.numel() != self.K * self.T:
+            raise ValueError(f"delta_u has {delta_u.numel()} elements, expected {self.K * self.T}")
+        for t, name, numel in ((S_out, "S_out", self.K), (traj_out, "traj_out", self.K * (self.T + 1) * 6),
+                               (u_upd_out, "u_upd_out", self.T)):
+            if t is not None:
+                _check_dev(t, name, self.device)
+                if t.numel() != numel:
+                    raise ValueError(f"{name} has {t.numel()} elements, expected {numel}")
+        self._chk(self.lib.cps_legacy_step(self._h, _ptr(s), _ptr(delta_u), layout, _ptr(self._u_dev), _ptr(S_out),
+                                           _ptr(traj_out), traj_layout, _ptr(u_upd_out)))
+        return self._u_dev
+
+    def legacy_step_host(self, s_np, delta_u_np, layout=L.ROLLOUT_MAJOR) -> float:
+        """Host form (cps_legacy_step_host): numpy state and numpy float32 perturbations in, python float out."""
+        self.use_current_stream()
+        if delta_u_np.dtype != np.float32 or not delta_u_np.flags.c_contiguous or delta_u_np.size != self.K * self.T:
+            raise ValueError(f"delta_u must be a C-contiguous float32 array of {self.K * self.T} elements")
+        for i in range(6):
+            self._s_host[i] = s_np[i]
+        self._chk(self.lib.cps_legacy_step_host(self._h, self._s_host, C.c_void_p(delta_u_np.ctypes.data), layout,
+                                                self._u_host))
+        return self._u_host[0]
+
+    def legacy_advance(self) -> float:
+        self.use_current_stream()
+        self._chk(self.lib.cps_legacy_advance(self._h, self._u_host))
+        return self._u_host[0]
+
+    def legacy_reset(self):
+        self.use_current_stream()
+        self._chk(self.lib.cps_legacy_reset(self._h))
+
+    def legacy_get_inputs(self):
+        self.use_current_stream()
+        u, up = np.zeros(self.T, np.float32), np.zeros(self.T, np.float32)
+        self._chk(self.lib.cps_legacy_get_inputs(self._h, u.ctypes.data_as(L._FP), up.ctypes.data_as(L._FP)))
+        return u, up
+
+    def legacy_set_inputs(self, u=None, u_prev=None):
+        self.use_current_stream()
+        ptrs = []
+        for v in (u, u_prev):
+            if v is None:
+                ptrs.append(None)
+                continue
+            v = np.ascontiguousarray(np.asarray(v, dtype=np.float32).reshape(-1))
+            if v.shape[0] != self.T:
+                raise ValueError(f"expected {self.T} entries, got {v.shape[0]}")
+            ptrs.append(v)
+        self._chk(self.lib.cps_legacy_set_inputs(self._h, *[None if v is None else v.ctypes.data_as(L._FP) for v in ptrs]))
 
     def partial_size(self):
         return self.lib.cps_mppi_partial_size(self._h)

@@ -75,6 +75,8 @@ struct cps_handle {
     unsigned *d_ticket;
     int *d_nonfinite;
     float *d_s, *d_unom, *d_u;
+    float *d_uprev;   // legacy front-end: previous nominal sequence [T]
+    float *d_ldu;     // legacy front-end: staging of delta_u for cps_legacy_step_host [K][T]
     float *h_pin;  // pinned: [0..6) s, [8] u
     int grid, block;
     size_t smem;

@@ -217,6 +217,17 @@ static int fold_cost_into(cps_handle *h, float target_equilibrium, CostParams &c
         c.w[10] = cosf(v[10]);
         break;
     }
+    case CPS_COST_LEGACY_MPPI: {
+        // in: [dd_weight, ep_weight, ekp_weight, ekc_weight, ccrc_weight] (controller_mppi_cartpole.py:245-257)
+        if (h->cost_in_n < 5) return fail(h, CPS_ERR_INVALID, "cost params: need 5 values for the legacy controller_mppi_cartpole cost");
+        c.w[0] = w[0]; c.w[1] = w[1] * 0.25f; c.w[2] = w[2]; c.w[3] = w[3]; c.w[4] = w[4];
+        // |x| > 0.95 * TrackHalfLength is evaluated in double by numba (:142); for a float x that is x > RD(threshold)
+        const double thr = 0.95 * (double)thl;
+        float thr_f = (float)thr;
+        if ((double)thr_f > thr) thr_f = nextafterf(thr_f, 0.0f);
+        c.w[5] = thr_f;
+        break;
+    }
     default: return fail(h, CPS_ERR_UNSUPPORTED, "unknown cost id %d", h->cfg.cost_id);
     }
     return CPS_OK;
@@ -266,8 +277,10 @@ extern "C" int cps_create(const cps_config *cfg, cps_handle **out) {
         return fail(nullptr, CPS_ERR_INVALID, "cps_create: K, T, n, dt and period must be positive");
     if (cfg->integrator != CPS_EULER_V0 && cfg->integrator != CPS_EULER_CROMER && cfg->integrator != CPS_PREDICTOR_NEURAL)
         return fail(nullptr, CPS_ERR_UNSUPPORTED, "cps_create: unknown integrator %d", cfg->integrator);
-    if (cfg->cost_id < CPS_COST_NONE || cfg->cost_id > CPS_COST_QB_GRAD)
+    if (cfg->cost_id < CPS_COST_NONE || cfg->cost_id > CPS_COST_LEGACY_MPPI)
         return fail(nullptr, CPS_ERR_UNSUPPORTED, "cps_create: unknown cost id %d", cfg->cost_id);
+    if (cfg->cost_id == CPS_COST_LEGACY_MPPI && (cfg->noise_mode != CPS_NOISE_DIRECT || cfg->integrator == CPS_PREDICTOR_NEURAL))
+        return fail(nullptr, CPS_ERR_INVALID, "cps_create: CPS_COST_LEGACY_MPPI needs CPS_NOISE_DIRECT and an ODE integrator");
     if (cfg->noise_mode != CPS_NOISE_INDUCING && cfg->noise_mode != CPS_NOISE_DIRECT)
         return fail(nullptr, CPS_ERR_INVALID, "cps_create: unknown noise mode %d", cfg->noise_mode);
     int ndev = 0;
@@ -294,18 +307,21 @@ extern "C" int cps_create(const cps_config *cfg, cps_handle **out) {
     {
         const float d_def[6] = {600.0f, 20000.0f, 1.0f, 1.0f, 1.0f, 6000019968.0f};
         const float d_min[7] = {10.0f, 10000.0f, 40.0f, 1.0f, 5.0f, 1.0f, 0.85f};
+        const float d_leg[5] = {120.0f, 50000.0f, 0.01f, 5.0f, 1.0f};  // config_controllers.yml:16-21
         const float d_grad[19] = {500.0f, 0.0f, 10000.0f, 6000.0f, 30.0f, 5.0f, 0.0f, 0.0f,
                                   500.0f, 0.0f, 10000.0f, 6000.0f, 30.0f, 5.0f, 0.0f, 100.0f, 1.0f, 0.85f, 0.0f};
         switch (cfg->cost_id) {
         case CPS_COST_DEFAULT: case CPS_COST_QUADRATIC_BOUNDARY: memcpy(h->cost_in, d_def, sizeof(d_def)); h->cost_in_n = 6; break;
         case CPS_COST_QB_GRAD_MINIMAL: memcpy(h->cost_in, d_min, sizeof(d_min)); h->cost_in_n = 7; break;
         case CPS_COST_QB_GRAD: memcpy(h->cost_in, d_grad, sizeof(d_grad)); h->cost_in_n = 19; break;
+        case CPS_COST_LEGACY_MPPI: memcpy(h->cost_in, d_leg, sizeof(d_leg)); h->cost_in_n = 5; break;
         default: h->cost_in_n = 0; break;
         }
     }
     // defaults: config_optimizers.yml:87-97
     const float mp[7] = {1.0f, 1.0f, 100.0f, 1000.0f, (float)(0.03 / std::sqrt((double)cfg->dt)), -1.0f, 1.0f};
     memcpy(h->mppi_in, mp, sizeof(mp));
+    if (cfg->cost_id == CPS_COST_LEGACY_MPPI) h->mppi_in[4] = (float)(0.02 / std::sqrt((double)cfg->dt));  // config_controllers.yml:27
     fold_ode(h);
     fold_mppi(h);
     int rc = fold_cost(h);
@@ -341,6 +357,10 @@ extern "C" int cps_create(const cps_config *cfg, cps_handle **out) {
     CREATE_TRY(cudaMalloc(&h->d_s, sizeof(float) * 8));
     CREATE_TRY(cudaMalloc(&h->d_unom, sizeof(float) * (size_t)cfg->horizon));
     CREATE_TRY(cudaMalloc(&h->d_u, sizeof(float) * 4));
+    if (cfg->cost_id == CPS_COST_LEGACY_MPPI) {
+        CREATE_TRY(cudaMalloc(&h->d_uprev, sizeof(float) * (size_t)cfg->horizon));
+        CREATE_TRY(cudaMemset(h->d_uprev, 0, sizeof(float) * (size_t)cfg->horizon));
+    }
     CREATE_TRY(cudaMallocHost(&h->h_pin, sizeof(float) * 16));
     CREATE_TRY(cudaMemset(h->d_ticket, 0, sizeof(unsigned)));
     CREATE_TRY(cudaMemset(h->d_nonfinite, 0, sizeof(int)));
@@ -357,7 +377,7 @@ extern "C" void cps_destroy(cps_handle *h) {
     cps_net_free(h);
     cps_fleet_free(h);
     cudaFree(h->d_partials); cudaFree(h->d_ticket); cudaFree(h->d_nonfinite);
-    cudaFree(h->d_s); cudaFree(h->d_unom); cudaFree(h->d_u);
+    cudaFree(h->d_s); cudaFree(h->d_unom); cudaFree(h->d_u); cudaFree(h->d_uprev); cudaFree(h->d_ldu);
     cudaFree(h->d_rs0); cudaFree(h->d_rQ); cudaFree(h->d_rtraj); cudaFree(h->d_rfinal);
     if (h->h_pin) cudaFreeHost(h->h_pin);
     if (h->pipe_ready) {
@@ -500,6 +520,7 @@ extern "C" int cps_mppi_step(cps_handle *h, const float *s_dev, const float *noi
     if (!h) return CPS_ERR_INVALID;
     if (!s_dev || !noise_dev || !u_nom_dev || !u_out_dev) return fail(h, CPS_ERR_INVALID, "cps_mppi_step: null pointer");
     if (h->shard && !h->shard_out) return fail(h, CPS_ERR_INVALID, "cps_mppi_step: shard mode without an output buffer");
+    if (h->cfg.cost_id == CPS_COST_LEGACY_MPPI) return fail(h, CPS_ERR_INVALID, "cps_mppi_step: this handle is a legacy controller_mppi_cartpole front-end; use cps_legacy_step");
     CUDA_TRY(h, cudaSetDevice(h->cfg.device));
     if (h->cfg.integrator == CPS_PREDICTOR_NEURAL)
         return cps_net_mppi_step(h, s_dev, noise_dev, noise_layout, u_prev, u_nom_dev, u_out_dev, J_out_dev, traj_out_dev,
@@ -791,6 +812,7 @@ extern "C" int cps_terminal_cost(cps_handle *h, const float *states_dev, int K, 
     CUDA_TRY(h, cudaSetDevice(h->cfg.device));
     const int grid = (K + 127) / 128;
     switch (h->cfg.cost_id) {
+    case CPS_COST_LEGACY_MPPI:  // phi() is default.py's terminal cost (controller_mppi_cartpole.py:271-298)
     case CPS_COST_DEFAULT: terminal_cost_kernel<COST_DEFAULT><<<grid, 128, 0, h->stream>>>(h->cost, states_dev, K, out_dev); break;
     case CPS_COST_QUADRATIC_BOUNDARY: terminal_cost_kernel<COST_QB><<<grid, 128, 0, h->stream>>>(h->cost, states_dev, K, out_dev); break;
     case CPS_COST_QB_GRAD_MINIMAL: terminal_cost_kernel<COST_GRADMIN><<<grid, 128, 0, h->stream>>>(h->cost, states_dev, K, out_dev); break;

@@ -53,7 +53,10 @@ typedef enum cps_cost {
     CPS_COST_DEFAULT = 0,             /* default.py:19-88 */
     CPS_COST_QUADRATIC_BOUNDARY = 1,  /* quadratic_boundary.py:22-87 */
     CPS_COST_QB_GRAD_MINIMAL = 2,     /* quadratic_boundary_grad_minimal.py:17-140 */
-    CPS_COST_QB_GRAD = 3              /* quadratic_boundary_grad.py:17-268 */
+    CPS_COST_QB_GRAD = 3,             /* quadratic_boundary_grad.py:17-268 */
+    CPS_COST_LEGACY_MPPI = 4          /* q() + phi() of the legacy controller_mppi_cartpole
+                                         (Control_Toolkit_ASF/Controllers/controller_mppi_cartpole.py:218-298); only with
+                                         the cps_legacy_* entry points and CPS_NOISE_DIRECT */
 } cps_cost;
 
 /* Where the MPPI perturbations come from (Control_Toolkit/Optimizers/optimizer_mppi.py:169-178):
@@ -165,6 +168,38 @@ float *cps_mppi_u_nom_dev(cps_handle *h);
 int cps_mppi_set_shard(cps_handle *h, int enabled, float *partial_out_dev);
 int cps_mppi_partial_size(const cps_handle *h);
 int cps_mppi_finalize(cps_handle *h, const float *partials_dev, int n_ranks, float *u_nom_dev, float *u_out_dev);
+
+/* ---- legacy front-end: controller_mppi_cartpole ------------------------------------------------------------ */
+/* The repository's original MPPI controller (Control_Toolkit_ASF/Controllers/controller_mppi_cartpole.py), which
+ * README.md:46 calls "MPPI with predictor_ODE_v0".  Same rollouts, different bookkeeping:
+ *   - delta_u [K][T] is drawn on the host by one of five sampling types (:392-457) and passed in as is;
+ *   - the rollouts run on u + delta_u WITHOUT clipping (:190-192);
+ *   - cost = SUM over the T stage costs q() (:218-268: dd with a 1e6 track-edge indicator at 0.95, ep, ekp, ekc,
+ *     cc = cc_weight*(0.5(1-1/NU) R du^2 + R u du + 0.5 R u^2) on the NOMINAL u, replaced by 1e5 where |u+du| > 1,
+ *     ccrc against the PREVIOUS nominal sequence u_prev[t]) + phi() (:271-298);
+ *   - u += sum(w du)/sum(w), not clipped (:301-335); the controller returns u[0]; afterwards u_prev <- u and u is
+ *     shifted left with a ZERO appended (:534-539).
+ * Handle: cost_id = CPS_COST_LEGACY_MPPI, noise_mode = CPS_NOISE_DIRECT.  cps_set_cost_params takes
+ * [dd_weight, ep_weight, ekp_weight, ekc_weight, ccrc_weight] (config_controllers.yml:16-21); cc_weight, R, LBD, NU come
+ * from cps_set_mppi_params (its sigma and limits are unused: the host draws delta_u and clips the returned control).
+ * The handle owns u [T] and u_prev [T] (both zero after cps_create / cps_legacy_reset).
+ *
+ * One update_every-th iteration (:481-500 + :530-539) as ONE kernel launch.  s_dev [6]; delta_u_dev K x T in `layout`
+ * order; u_out_dev [1] = u[0] after the update (before actuator noise and clipping, which stay on the host, :526-528).
+ * Optional outputs (NULL to skip): S_out_dev [K] = S_tilde_k; traj_out_dev K x (T+1) x 6 in traj_layout order;
+ * u_upd_out_dev [T] = u after the update, before the shift (what LOGS["inputs"] records, :503). */
+int cps_legacy_step(cps_handle *h, const float *s_dev, const float *delta_u_dev, int layout, float *u_out_dev,
+                    float *S_out_dev, float *traj_out_dev, int traj_layout, float *u_upd_out_dev);
+/* Host-buffer form, what controller_mppi_cartpole.step makes per call: s_host [6] and delta_u_host (K x T, `layout`
+ * order; pinned memory makes the copy asynchronous) are copied up, *u_out_host = u[0].  Synchronises. */
+int cps_legacy_step_host(cps_handle *h, const float *s_host, const float *delta_u_host, int layout, float *u_out_host);
+/* An iteration that is not a multiple of update_every (:481): no solve; u_out = u[0], u_prev <- u, shift.  u_out_host
+ * may be NULL.  Synchronises only if u_out_host is given. */
+int cps_legacy_advance(cps_handle *h, float *u_out_host);
+int cps_legacy_reset(cps_handle *h);
+/* u [T] and u_prev [T]; either pointer may be NULL.  Synchronise. */
+int cps_legacy_get_inputs(cps_handle *h, float *u_host, float *u_prev_host);
+int cps_legacy_set_inputs(cps_handle *h, const float *u_host, const float *u_prev_host);
 
 /* ---- open-loop batched rollouts (the predictor interface) ------------------------------------------------ */
 /* predictor.predict_core(s, Q) (SI_Toolkit/src/SI_Toolkit/Predictors/predictor_ODE.py:86-97,
