@@ -100,6 +100,15 @@ SYMBOLS = {
     "cps_fleet_period": (C.c_longlong, [_VP]),
     "cps_fleet_step": (C.c_int, [_VP, C.c_int, _VP, _VP, _VP, _VP, _VP]),
     "cps_fleet_noise": (C.c_int, [_VP, C.c_longlong, _VP]),
+    "cps_plan_cost": (C.c_int, [_VP, _VP, _VP, C.c_int, C.c_int, C.c_int, C.c_float, _VP, _VP, C.c_int]),
+    "cps_plan_random_action": (C.c_int, [_VP, _VP, _VP, C.c_int, C.c_float, _VP, _VP, _VP]),
+    "cps_plan_random_action_host": (C.c_int, [_VP, _FP, _VP, C.c_int, C.c_float, _FP]),
+    "cps_cem_configure": (C.c_int, [_VP, C.c_int, C.c_float, C.c_float]),
+    "cps_cem_reset": (C.c_int, [_VP]),
+    "cps_cem_step": (C.c_int, [_VP, _VP, _VP, C.c_int, C.c_int, C.c_float, _VP, _VP, _VP]),
+    "cps_cem_step_host": (C.c_int, [_VP, _FP, _VP, C.c_int, C.c_int, C.c_float, _FP]),
+    "cps_cem_get_distribution": (C.c_int, [_VP, _FP, _FP]),
+    "cps_cem_set_distribution": (C.c_int, [_VP, _FP, _FP]),
     "cps_measure_peaks": (C.c_int, [_VP, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "cps_launch_count": (C.c_longlong, [_VP]),
     "cps_nonfinite_costs": (C.c_int, [_VP, C.POINTER(C.c_int)]),

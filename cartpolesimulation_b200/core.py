@@ -417,6 +417,107 @@ class Engine:
         self._chk(self.lib.cps_terminal_cost(self._h, _ptr(states), K, _ptr(out)))
         return out
 
+    # -- forward-only planners (random action, CEM) ----------------------------------------------------
+    def _q_dims(self, Q, layout):
+        if Q.dim() < 2:
+            raise ValueError("Q must be [K, T] (ROLLOUT_MAJOR) or [T, K] (TIME_MAJOR)")
+        a, b = int(Q.shape[0]), int(Q.shape[1])
+        if Q.numel() != a * b:
+            raise ValueError("one control input only: trailing dimensions of Q must be 1")
+        return (b, a) if layout == L.TIME_MAJOR else (a, b)
+
+    def plan_cost(self, s, Q, q_layout=L.ROLLOUT_MAJOR, u_prev=0.0, want_traj=False, traj_layout=L.ROLLOUT_MAJOR):
+        """predict_and_cost of the forward-only optimizers (cps_plan_cost): J [K], and the trajectories if asked."""
+        self.use_current_stream()
+        _check_dev(s, "s", self.device)
+        _check_dev(Q, "Q", self.device)
+        K, T = self._q_dims(Q, q_layout)
+        J = torch.empty((K,), device=self.device, dtype=torch.float32)
+        traj = None
+        if want_traj:
+            shape = (T + 1, 6, K) if traj_layout == L.TIME_MAJOR else (K, T + 1, 6)
+            traj = torch.empty(shape, device=self.device, dtype=torch.float32)
+        self._chk(self.lib.cps_plan_cost(self._h, _ptr(s), _ptr(Q), q_layout, K, T, float(u_prev), _ptr(J), _ptr(traj),
+                                         traj_layout))
+        return J, traj
+
+    def plan_random_action(self, s, Q, q_layout=L.ROLLOUT_MAJOR, u_prev=0.0, J_out=None, best_out=None):
+        """cps_plan_random_action: returns the cuda tensor [1] holding Q[argmin J, 0] (no synchronisation)."""
+        self.use_current_stream()
+        _check_dev(s, "s", self.device)
+        _check_dev(Q, "Q", self.device)
+        if self._q_dims(Q, q_layout) != (self.K, self.T):
+            raise ValueError(f"Q has shape {tuple(Q.shape)}, expected K = {self.K}, T = {self.T}")
+        if best_out is not None:
+            _check_dev(best_out, "best_out", self.device, torch.int32)
+        self._chk(self.lib.cps_plan_random_action(self._h, _ptr(s), _ptr(Q), q_layout, float(u_prev), _ptr(self._u_dev),
+                                                  _ptr(J_out), _ptr(best_out)))
+        return self._u_dev
+
+    def plan_random_action_host(self, s_np, Q, q_layout=L.ROLLOUT_MAJOR, u_prev=0.0) -> float:
+        self.use_current_stream()
+        _check_dev(Q, "Q", self.device)
+        if self._q_dims(Q, q_layout) != (self.K, self.T):
+            raise ValueError(f"Q has shape {tuple(Q.shape)}, expected K = {self.K}, T = {self.T}")
+        for i in range(6):
+            self._s_host[i] = s_np[i]
+        self._chk(self.lib.cps_plan_random_action_host(self._h, self._s_host, _ptr(Q), q_layout, float(u_prev),
+                                                       self._u_host))
+        return self._u_host[0]
+
+    def cem_configure(self, best_k, initial_stdev, stdev_min):
+        self.use_current_stream()
+        self._chk(self.lib.cps_cem_configure(self._h, int(best_k), float(initial_stdev), float(stdev_min)))
+
+    def cem_reset(self):
+        self.use_current_stream()
+        self._chk(self.lib.cps_cem_reset(self._h))
+
+    def _cem_eps(self, eps, layout):
+        _check_dev(eps, "eps", self.device)
+        if eps.dim() < 3 or eps.numel() != eps.shape[0] * self.K * self.T:
+            raise ValueError(f"eps has shape {tuple(eps.shape)}, expected [iterations, K, T] or [iterations, T, K]")
+        if self._q_dims(eps[0], layout) != (self.K, self.T):
+            raise ValueError(f"eps has shape {tuple(eps.shape)}, expected K = {self.K}, T = {self.T}")
+        return int(eps.shape[0])
+
+    def cem_step(self, s, eps, eps_layout=L.ROLLOUT_MAJOR, u_prev=0.0, Q_out=None, J_out=None):
+        """cps_cem_step: eps.shape[0] outer iterations; returns the cuda tensor [1] holding u (no synchronisation)."""
+        self.use_current_stream()
+        _check_dev(s, "s", self.device)
+        n_it = self._cem_eps(eps, eps_layout)
+        self._chk(self.lib.cps_cem_step(self._h, _ptr(s), _ptr(eps), eps_layout, n_it, float(u_prev), _ptr(self._u_dev),
+                                        _ptr(Q_out), _ptr(J_out)))
+        return self._u_dev
+
+    def cem_step_host(self, s_np, eps, eps_layout=L.ROLLOUT_MAJOR, u_prev=0.0) -> float:
+        self.use_current_stream()
+        n_it = self._cem_eps(eps, eps_layout)
+        for i in range(6):
+            self._s_host[i] = s_np[i]
+        self._chk(self.lib.cps_cem_step_host(self._h, self._s_host, _ptr(eps), eps_layout, n_it, float(u_prev),
+                                             self._u_host))
+        return self._u_host[0]
+
+    def cem_get_distribution(self):
+        self.use_current_stream()
+        mu, sd = np.zeros(self.T, dtype=np.float32), np.zeros(self.T, dtype=np.float32)
+        self._chk(self.lib.cps_cem_get_distribution(self._h, mu.ctypes.data_as(L._FP), sd.ctypes.data_as(L._FP)))
+        return mu, sd
+
+    def cem_set_distribution(self, mean=None, stdev=None):
+        self.use_current_stream()
+        def arr(v):
+            if v is None:
+                return None, None
+            a = np.ascontiguousarray(np.asarray(v, dtype=np.float32).reshape(-1))
+            if a.shape[0] != self.T:
+                raise ValueError(f"distribution vectors have {self.T} entries")
+            return a, a.ctypes.data_as(L._FP)
+        m, mp_ = arr(mean)
+        s_, sp = arr(stdev)
+        self._chk(self.lib.cps_cem_set_distribution(self._h, mp_, sp))
+
     def measure_peaks(self):
         """(FP32 TFLOP/s, MUFU Gop/s) measured on this device by two microbenchmark kernels."""
         self.use_current_stream()

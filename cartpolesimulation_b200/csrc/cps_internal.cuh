@@ -57,6 +57,7 @@ struct FinalizeArgs {
 
 struct NetState;    // cps_net.cu
 struct FleetState;  // cps_fleet.cu
+struct PlanState;   // cps_plan.cu
 
 struct cps_handle {
     cps_config cfg;
@@ -93,12 +94,15 @@ struct cps_handle {
     std::string err;
     NetState *net;      // neural predictor (cps_net_load), owned
     FleetState *fleet;  // closed-loop experiments (cps_fleet_create), owned
+    PlanState *plan;    // forward-only planners (cps_plan_*, cps_cem_*), owned
 };
 
 extern thread_local std::string g_create_err;
 
 // cps_fleet.cu
 void cps_fleet_free(cps_handle *h);
+// cps_plan.cu
+void cps_plan_free(cps_handle *h);
 // cps_lib.cu: cost parameters folded for a given target equilibrium
 int cps_fold_cost_for(cps_handle *h, float target_equilibrium, CostParams *out);
 // cps_net.cu

@@ -1,0 +1,514 @@
+// cps_plan.cu -- the forward-only optimizers' predict_and_cost and their selection step.
+//
+// optimizer_random_action_tf and optimizer_cem_tf (Control_Toolkit/Optimizers/optimizer_random_action_tf.py:42-49,
+// optimizer_cem_tf.py:57-83) evaluate K candidate input plans Q[K][T] from one state:
+//     rollout_trajectory = predictor.predict_core(s, Q);  traj_cost = cost_function.get_trajectory_cost(traj, Q, u)
+// and then pick from the sorted costs: the best plan's first input (random action), or the cem_best_k elites whose
+// per-step mean / standard deviation become the next sampling distribution (CEM).  In the reference these are three
+// framework ops with the [K][T+1][6] trajectory tensor in between; here it is ONE launch per evaluation:
+//   every thread integrates one plan (the same control_step / stage_cost device code as mppi_kernel) and keeps the
+//   cost in a register; the block that finishes last (atomic ticket) selects on the K costs -- arg-min, or a radix
+//   select of the best_k-th smallest cost with ties taken in index order -- and finishes the optimizer's update
+//   (elite mean / population std per horizon step, and after the last CEM iteration the std clip, the shift of both
+//   vectors and u = elite_Q[0, 0]).  CEM plans are built in the kernel from supplied standard-normal draws,
+//   Q = clip(mu + eps * std) with separately rounded multiply and add (tf.multiply, then +), so they are bit-equal to
+//   the reference's; nothing returns to the host between the outer iterations of one solve.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstring>
+#include <new>
+
+#include "cps_internal.cuh"
+
+enum { PLAN_Q = 0, PLAN_CEM = 1 };
+enum { SELECT_NONE = 0, SELECT_ARGMIN = 1, SELECT_CEM = 2 };
+
+struct PlanArgs {
+    OdeParams ode;
+    CostParams cost;
+    const float *s;               // [6]
+    const float *Q;               // PLAN_Q: plans; PLAN_CEM: standard-normal draws
+    long long qs_k, qs_t;         // element strides along plan / horizon step
+    const float *mu, *sd;         // PLAN_CEM: sampling distribution [T]
+    float lo, hi, inv_T1, u_prev;
+    int K, T;
+    float *J;                     // [K]; required when select != SELECT_NONE
+    float *Q_out;                 // PLAN_CEM: the sampled plans, same strides as Q, or null
+    float *traj_out;
+    long long ts_k, ts_t, ts_c;
+    int select;
+    int best_k, last_iter;
+    float sd_min, sd_init, mid;
+    unsigned *ticket;
+    int *elite;                   // [K] scratch: indices of the elites, ascending
+    float *mu_out, *sd_out;       // CEM: updated distribution [T]
+    float *u_out;                 // [1]
+    int *best_out;                // [1] or null: index of the cheapest plan
+    int *nonfinite;
+};
+
+struct PlanState {
+    int best_k;
+    float sd_init, sd_min;
+    float *d_J, *d_mu, *d_sd;
+    int *d_elite, *d_best;
+    unsigned *d_ticket;
+    int configured_cem;
+};
+
+// cost -> unsigned key with the same order; NaN sorts last
+__device__ __forceinline__ unsigned order_key(float J) {
+    if (J != J) return 0xFFFFFFFFu;
+    const unsigned b = __float_as_uint(J);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+__device__ __forceinline__ float cem_plan_value(float mu, float eps, float sd, float lo, float hi) {
+    return clampf(__fadd_rn(mu, __fmul_rn(eps, sd)), lo, hi);  // tile(mu) + multiply(normal, stdev), then clip (:66-68)
+}
+
+// Exclusive prefix of v over the block (thread order) and the block total.  s_w: [nwarps] shared scratch.
+__device__ __forceinline__ int block_excl_scan(int v, int *s_w, int &total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int n = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += n;
+    }
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    int base = 0;
+    total = 0;
+    for (int w = 0; w < nwarps; ++w) {
+        const int c = s_w[w];
+        if (w < warp) base += c;
+        total += c;
+    }
+    __syncthreads();
+    return base + incl - v;
+}
+
+// Run by the block that finished last.  s_mu / s_sd: the distribution the plans were sampled from (PLAN_CEM);
+// s_mu2 / s_sd2: [T] scratch for the updated one.
+template <int MODE>
+__device__ __forceinline__ void plan_select(const PlanArgs &a, const float *s_mu, const float *s_sd, float *s_mu2,
+                                            float *s_sd2) {
+    __shared__ unsigned s_hist[256];
+    __shared__ unsigned s_prefix, s_remaining;
+    __shared__ int s_w[8];
+    __shared__ unsigned long long s_bestw[8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nt = blockDim.x, nwarps = nt >> 5;
+    const int K = a.K, T = a.T;
+
+    // ---- cheapest plan, lowest index among equal costs (sorted_cost[0]) ---------------------------------------------------
+    unsigned long long best = ~0ull;
+    for (int i = tid; i < K; i += nt) {
+        const unsigned long long c = ((unsigned long long)order_key(__ldcg(a.J + i)) << 32) | (unsigned)i;
+        best = c < best ? c : best;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long n = __shfl_xor_sync(0xffffffffu, best, o);
+        best = n < best ? n : best;
+    }
+    if (lane == 0) s_bestw[warp] = best;
+    __syncthreads();
+    for (int w = 0; w < nwarps; ++w) best = s_bestw[w] < best ? s_bestw[w] : best;
+    const int best_idx = (int)(best & 0xFFFFFFFFull);
+    if (tid == 0 && a.best_out) *a.best_out = best_idx;
+    if (a.select == SELECT_ARGMIN) {
+        if (tid == 0) *a.u_out = a.Q[(long long)best_idx * a.qs_k];  // Q[best_idx, 0, :] (random_action_tf.py:69)
+        return;
+    }
+
+    // ---- CEM: the best_k-th smallest key by an 8-bit radix select ----------------------------------------------------------
+    const int bk = min(a.best_k, K);
+    if (tid == 0) { s_prefix = 0u; s_remaining = (unsigned)bk; }
+    unsigned mask = 0u;
+    for (int shift = 24; shift >= 0; shift -= 8) {
+        for (int b = tid; b < 256; b += nt) s_hist[b] = 0u;
+        __syncthreads();
+        const unsigned prefix = s_prefix;
+        for (int i = tid; i < K; i += nt) {
+            const unsigned key = order_key(__ldcg(a.J + i));
+            if ((key & mask) == prefix) atomicAdd(&s_hist[(key >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            unsigned cum = 0u, rem = s_remaining;
+            for (int b = 0; b < 256; ++b) {
+                const unsigned c = s_hist[b];
+                if (cum + c >= rem) { s_prefix = prefix | ((unsigned)b << shift); s_remaining = rem - cum; break; }
+                cum += c;
+            }
+        }
+        mask |= 255u << shift;
+        __syncthreads();
+    }
+    const unsigned kth = s_prefix;
+    const int ties_wanted = (int)s_remaining;  // how many plans with key == kth belong to the elites (lowest indices)
+
+    // ---- elite indices in ascending order (ordered compaction) ---------------------------------------------------------------
+    int n_eq_before = 0, n_el_before = 0;
+    for (int base = 0; base < K; base += nt) {
+        const int i = base + tid;
+        unsigned key = 0xFFFFFFFFu;
+        bool in = i < K;
+        if (in) key = order_key(__ldcg(a.J + i));
+        const int eq = (in && key == kth) ? 1 : 0;
+        int tot_eq, tot_el;
+        const int eq_rank = n_eq_before + block_excl_scan(eq, s_w, tot_eq);
+        const int el = (in && (key < kth || (eq && eq_rank < ties_wanted))) ? 1 : 0;
+        const int pos = n_el_before + block_excl_scan(el, s_w, tot_el);
+        if (el) a.elite[pos] = i;
+        n_eq_before += tot_eq;
+        n_el_before += tot_el;
+    }
+    __syncthreads();
+
+    // ---- per horizon step: mean and population standard deviation over the elites (cem_tf.py:79-81) ------------------------
+    for (int t = warp; t < T; t += nwarps) {
+        float sum = 0.0f;
+        for (int e = lane; e < bk; e += 32) {
+            const int k = a.elite[e];
+            sum += cem_plan_value(s_mu[t], a.Q[(long long)k * a.qs_k + (long long)t * a.qs_t], s_sd[t], a.lo, a.hi);
+        }
+        const float mean = __fdiv_rn(warp_sum(sum), (float)bk);
+        float ss = 0.0f;
+        for (int e = lane; e < bk; e += 32) {
+            const int k = a.elite[e];
+            const float d = cem_plan_value(s_mu[t], a.Q[(long long)k * a.qs_k + (long long)t * a.qs_t], s_sd[t], a.lo, a.hi) - mean;
+            ss = fmaf(d, d, ss);
+        }
+        const float var = __fdiv_rn(warp_sum(ss), (float)bk);
+        if (lane == 0) { s_mu2[t] = mean; s_sd2[t] = sqrtf(var); }
+    }
+    __syncthreads();
+    if (!a.last_iter) {
+        for (int t = tid; t < T; t += nt) { a.mu_out[t] = s_mu2[t]; a.sd_out[t] = s_sd2[t]; }
+        return;
+    }
+    // after the last outer iteration: clip the std from below, shift both vectors by one step and refill the tail
+    // (cem_tf.py:96-99); u = elite_Q[0, 0] is the cheapest plan's first input
+    for (int t = tid; t < T; t += nt) {
+        if (t + 1 < T) {
+            a.mu_out[t] = s_mu2[t + 1];
+            a.sd_out[t] = clampf(s_sd2[t + 1], a.sd_min, 1.0e8f);
+        } else {
+            a.mu_out[t] = a.mid;
+            a.sd_out[t] = a.sd_init;
+        }
+    }
+    if (tid == 0) *a.u_out = cem_plan_value(s_mu[0], a.Q[(long long)best_idx * a.qs_k], s_sd[0], a.lo, a.hi);
+}
+
+template <int INTEG, int COST, int MODE>
+__global__ void __launch_bounds__(256, 4) plan_kernel(const __grid_constant__ PlanArgs a) {
+    extern __shared__ float smem[];   // PLAN_CEM: mu[T], sd[T], mu2[T], sd2[T]
+    __shared__ unsigned s_ticket;
+    const int tid = threadIdx.x, T = a.T;
+    float *s_mu = smem, *s_sd = smem + T;
+    if (MODE == PLAN_CEM) {
+        for (int t = tid; t < T; t += blockDim.x) { s_mu[t] = a.mu[t]; s_sd[t] = a.sd[t]; }
+        __syncthreads();
+    }
+    const int k = blockIdx.x * blockDim.x + tid;
+    const bool active = k < a.K;
+    const int kc = min(k, a.K - 1);
+
+    State z = load_state(a.s);
+    const OdeParams ode = pin_params(a.ode, z.th);
+    float c_cost = cosf(z.th);  // the plugins take cos(angle) of the stored angle (default.py:34)
+    const float *q = a.Q + (long long)kc * a.qs_k;
+    float *qo = (MODE == PLAN_CEM && a.Q_out) ? a.Q_out + (long long)kc * a.qs_k : nullptr;
+    float *traj = a.traj_out ? a.traj_out + (long long)kc * a.ts_k : nullptr;
+    float Jacc = 0.0f, up = a.u_prev;
+    float qn = q[0];
+#pragma unroll 1
+    for (int t = 0; t < T; ++t) {
+        float u = qn;
+        if (t + 1 < T) qn = q[(long long)(t + 1) * a.qs_t];  // prefetch under the integration
+        if (MODE == PLAN_CEM) {
+            u = cem_plan_value(s_mu[t], u, s_sd[t], a.lo, a.hi);
+            if (active && qo) qo[(long long)t * a.qs_t] = u;
+        }
+        if (COST != COST_NONE) {
+            float st = stage_cost<COST>(a.cost, c_cost, z.w, z.x, u, up);
+            if (COST == COST_DEFAULT || COST == COST_QB) st -= a.cost.max_cost;  // get_stage_cost shift
+            Jacc += st;
+        }
+        if (active && traj) store_state(traj + (long long)t * a.ts_t, a.ts_c, z);
+        control_step<INTEG, SC_ROTATE, false, false>(ode, z, u);
+        c_cost = z.c;
+        up = u;
+    }
+    if (COST != COST_NONE) Jacc += terminal_cost<COST>(a.cost, z.th, z.x);
+    if (active && traj) store_state(traj + (long long)T * a.ts_t, a.ts_c, z);
+    const float J = Jacc * a.inv_T1;  // mean over the T+1 entries (Cost_Functions/__init__.py:90-93)
+    if (active) {
+        if (a.J) a.J[k] = J;
+        if (!isfinite(J)) atomicAdd(a.nonfinite, 1);
+    }
+    if (a.select == SELECT_NONE) return;
+
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_ticket = atomicAdd(a.ticket, 1u);
+    __syncthreads();
+    if (s_ticket != gridDim.x - 1u) return;
+    __threadfence();
+    plan_select<MODE>(a, s_mu, s_sd, smem + 2 * T, smem + 3 * T);
+    if (tid == 0) *a.ticket = 0u;  // re-arm
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------------------
+typedef void (*plan_fn)(const PlanArgs);
+template <int INTEG, int MODE>
+static plan_fn pick_plan2(int cost) {
+    switch (cost) {
+    case CPS_COST_DEFAULT: return plan_kernel<INTEG, COST_DEFAULT, MODE>;
+    case CPS_COST_QUADRATIC_BOUNDARY: return plan_kernel<INTEG, COST_QB, MODE>;
+    case CPS_COST_QB_GRAD_MINIMAL: return plan_kernel<INTEG, COST_GRADMIN, MODE>;
+    case CPS_COST_QB_GRAD: return plan_kernel<INTEG, COST_GRAD, MODE>;
+    default: return nullptr;
+    }
+}
+static plan_fn pick_plan(int integ, int cost, int mode) {
+    if (integ == CPS_EULER_V0) return mode == PLAN_CEM ? pick_plan2<0, PLAN_CEM>(cost) : pick_plan2<0, PLAN_Q>(cost);
+    return mode == PLAN_CEM ? pick_plan2<1, PLAN_CEM>(cost) : pick_plan2<1, PLAN_Q>(cost);
+}
+
+void cps_plan_free(cps_handle *h) {
+    PlanState *P = h->plan;
+    if (!P) return;
+    cudaFree(P->d_J); cudaFree(P->d_mu); cudaFree(P->d_sd); cudaFree(P->d_elite); cudaFree(P->d_best); cudaFree(P->d_ticket);
+    delete P;
+    h->plan = nullptr;
+}
+
+static int plan_state(cps_handle *h, PlanState **out) {
+    if (h->plan) { *out = h->plan; return CPS_OK; }
+    PlanState *P = new (std::nothrow) PlanState();
+    if (!P) return fail(h, CPS_ERR_INVALID, "cps_plan: out of host memory");
+    memset(P, 0, sizeof(*P));
+    h->plan = P;
+    const size_t K = h->cfg.num_rollouts, T = h->cfg.horizon;
+    CUDA_TRY(h, cudaMalloc(&P->d_J, sizeof(float) * K));
+    CUDA_TRY(h, cudaMalloc(&P->d_mu, sizeof(float) * T));
+    CUDA_TRY(h, cudaMalloc(&P->d_sd, sizeof(float) * T));
+    CUDA_TRY(h, cudaMalloc(&P->d_elite, sizeof(int) * K));
+    CUDA_TRY(h, cudaMalloc(&P->d_best, sizeof(int)));
+    CUDA_TRY(h, cudaMalloc(&P->d_ticket, sizeof(unsigned)));
+    CUDA_TRY(h, cudaMemset(P->d_ticket, 0, sizeof(unsigned)));
+    CUDA_TRY(h, cudaMemset(P->d_mu, 0, sizeof(float) * T));
+    CUDA_TRY(h, cudaMemset(P->d_sd, 0, sizeof(float) * T));
+    *out = P;
+    return CPS_OK;
+}
+
+static int plan_check(cps_handle *h, const char *who) {
+    if (h->cfg.integrator == CPS_PREDICTOR_NEURAL)
+        return fail(h, CPS_ERR_UNSUPPORTED, "%s: ODE predictors only (neural predictor: cps_net_rollout + cps_trajectory_cost)", who);
+    if (h->cfg.cost_id == CPS_COST_NONE || h->cfg.cost_id == CPS_COST_LEGACY_MPPI)
+        return fail(h, CPS_ERR_NOT_CONFIGURED, "%s: the handle has no cost-function plugin", who);
+    if (h->cfg.flags & (CPS_FLAG_SUBSTEP_SINCOS | CPS_FLAG_FAST_DIV))
+        return fail(h, CPS_ERR_UNSUPPORTED, "%s: built for the default (rotation) substeps only", who);
+    return CPS_OK;
+}
+
+static void plan_common(cps_handle *h, PlanArgs &a, const float *s_dev, float u_prev, int K, int T) {
+    memset(&a, 0, sizeof(a));
+    a.ode = h->ode; a.cost = h->cost;
+    a.s = s_dev;
+    a.lo = h->mppi_in[5]; a.hi = h->mppi_in[6];
+    a.inv_T1 = 1.0f / (float)(T + 1);
+    a.u_prev = u_prev;
+    a.K = K; a.T = T;
+    a.nonfinite = h->d_nonfinite;
+}
+
+static void plan_geometry(int K, int &grid, int &block) {
+    block = (K <= 148 * 32 * 4) ? 32 : (K <= 148 * 64 * 8 ? 64 : 128);
+    grid = (K + block - 1) / block;
+}
+
+extern "C" int cps_plan_cost(cps_handle *h, const float *s_dev, const float *Q_dev, int q_layout, int K, int T, float u_prev,
+                             float *J_out_dev, float *traj_out_dev, int traj_layout) {
+    if (!h) return CPS_ERR_INVALID;
+    if (!s_dev || !Q_dev || !J_out_dev) return fail(h, CPS_ERR_INVALID, "cps_plan_cost: null pointer");
+    if (K < 1 || T < 1) return fail(h, CPS_ERR_INVALID, "cps_plan_cost: K and T must be positive");
+    int rc = plan_check(h, "cps_plan_cost");
+    if (rc != CPS_OK) return rc;
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    PlanArgs a;
+    plan_common(h, a, s_dev, u_prev, K, T);
+    a.Q = Q_dev;
+    if (q_layout == CPS_TIME_MAJOR) { a.qs_k = 1; a.qs_t = K; } else { a.qs_k = T; a.qs_t = 1; }
+    a.J = J_out_dev;
+    a.traj_out = traj_out_dev;
+    if (traj_layout == CPS_TIME_MAJOR) { a.ts_k = 1; a.ts_t = 6LL * K; a.ts_c = K; }
+    else { a.ts_k = (T + 1) * 6LL; a.ts_t = 6; a.ts_c = 1; }
+    a.select = SELECT_NONE;
+    int grid, block;
+    plan_geometry(K, grid, block);
+    plan_fn fn = pick_plan(h->cfg.integrator, h->cfg.cost_id, PLAN_Q);
+    fn<<<grid, block, 0, h->stream>>>(a);
+    h->launches += 1;
+    CUDA_TRY(h, cudaGetLastError());
+    return CPS_OK;
+}
+
+extern "C" int cps_plan_random_action(cps_handle *h, const float *s_dev, const float *Q_dev, int q_layout, float u_prev,
+                                      float *u_out_dev, float *J_out_dev, int *best_out_dev) {
+    if (!h) return CPS_ERR_INVALID;
+    if (!s_dev || !Q_dev || !u_out_dev) return fail(h, CPS_ERR_INVALID, "cps_plan_random_action: null pointer");
+    int rc = plan_check(h, "cps_plan_random_action");
+    if (rc != CPS_OK) return rc;
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    PlanState *P;
+    if ((rc = plan_state(h, &P)) != CPS_OK) return rc;
+    const int K = h->cfg.num_rollouts, T = h->cfg.horizon;
+    PlanArgs a;
+    plan_common(h, a, s_dev, u_prev, K, T);
+    a.Q = Q_dev;
+    if (q_layout == CPS_TIME_MAJOR) { a.qs_k = 1; a.qs_t = K; } else { a.qs_k = T; a.qs_t = 1; }
+    a.J = J_out_dev ? J_out_dev : P->d_J;
+    a.select = SELECT_ARGMIN;
+    a.ticket = P->d_ticket; a.elite = P->d_elite;
+    a.u_out = u_out_dev;
+    a.best_out = best_out_dev ? best_out_dev : P->d_best;
+    int grid, block;
+    plan_geometry(K, grid, block);
+    plan_fn fn = pick_plan(h->cfg.integrator, h->cfg.cost_id, PLAN_Q);
+    fn<<<grid, block, 0, h->stream>>>(a);
+    h->launches += 1;
+    CUDA_TRY(h, cudaGetLastError());
+    return CPS_OK;
+}
+
+extern "C" int cps_plan_random_action_host(cps_handle *h, const float *s_host, const float *Q_dev, int q_layout, float u_prev,
+                                           float *u_out_host) {
+    if (!h) return CPS_ERR_INVALID;
+    if (!s_host || !u_out_host) return fail(h, CPS_ERR_INVALID, "cps_plan_random_action_host: null pointer");
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    memcpy(h->h_pin, s_host, sizeof(float) * 6);
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_s, h->h_pin, sizeof(float) * 6, cudaMemcpyHostToDevice, h->stream));
+    int rc = cps_plan_random_action(h, h->d_s, Q_dev, q_layout, u_prev, h->d_u, nullptr, nullptr);
+    if (rc != CPS_OK) return rc;
+    CUDA_TRY(h, cudaMemcpyAsync(h->h_pin + 8, h->d_u, sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    *u_out_host = h->h_pin[8];
+    return CPS_OK;
+}
+
+// ---- CEM --------------------------------------------------------------------------------------------------------------
+extern "C" int cps_cem_reset(cps_handle *h) {
+    if (!h) return CPS_ERR_INVALID;
+    PlanState *P = h->plan;
+    if (!P || !P->configured_cem) return fail(h, CPS_ERR_NOT_CONFIGURED, "cps_cem_reset: cps_cem_configure first");
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    const int T = h->cfg.horizon;
+    float *tmp = new (std::nothrow) float[2 * (size_t)T];
+    if (!tmp) return fail(h, CPS_ERR_INVALID, "cps_cem_reset: out of host memory");
+    const float mid = (h->mppi_in[5] + h->mppi_in[6]) * 0.5f;  // optimizer_reset (cem_tf.py:112-116)
+    for (int t = 0; t < T; ++t) { tmp[t] = mid; tmp[T + t] = P->sd_init; }
+    cudaError_t e = cudaMemcpyAsync(P->d_mu, tmp, sizeof(float) * T, cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(P->d_sd, tmp + T, sizeof(float) * T, cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    delete[] tmp;
+    CUDA_TRY(h, e);
+    return CPS_OK;
+}
+
+extern "C" int cps_cem_configure(cps_handle *h, int best_k, float initial_stdev, float stdev_min) {
+    if (!h) return CPS_ERR_INVALID;
+    int rc = plan_check(h, "cps_cem_configure");
+    if (rc != CPS_OK) return rc;
+    if (best_k < 1 || best_k > h->cfg.num_rollouts)
+        return fail(h, CPS_ERR_INVALID, "cps_cem_configure: cem_best_k must lie in [1, num_rollouts]");
+    if (!(initial_stdev >= 0.0f) || !(stdev_min >= 0.0f)) return fail(h, CPS_ERR_INVALID, "cps_cem_configure: negative stdev");
+    if (sizeof(float) * 4 * (size_t)h->cfg.horizon > 200 * 1024)
+        return fail(h, CPS_ERR_UNSUPPORTED, "cps_cem_configure: horizon too large for shared memory");
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    PlanState *P;
+    if ((rc = plan_state(h, &P)) != CPS_OK) return rc;
+    P->best_k = best_k; P->sd_init = initial_stdev; P->sd_min = stdev_min;
+    P->configured_cem = 1;
+    return cps_cem_reset(h);
+}
+
+extern "C" int cps_cem_step(cps_handle *h, const float *s_dev, const float *eps_dev, int eps_layout, int n_iterations,
+                            float u_prev, float *u_out_dev, float *Q_out_dev, float *J_out_dev) {
+    if (!h) return CPS_ERR_INVALID;
+    PlanState *P = h->plan;
+    if (!P || !P->configured_cem) return fail(h, CPS_ERR_NOT_CONFIGURED, "cps_cem_step: cps_cem_configure first");
+    if (!s_dev || !eps_dev || !u_out_dev) return fail(h, CPS_ERR_INVALID, "cps_cem_step: null pointer");
+    if (n_iterations < 1) return fail(h, CPS_ERR_INVALID, "cps_cem_step: n_iterations < 1");
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    const int K = h->cfg.num_rollouts, T = h->cfg.horizon;
+    PlanArgs a;
+    plan_common(h, a, s_dev, u_prev, K, T);
+    if (eps_layout == CPS_TIME_MAJOR) { a.qs_k = 1; a.qs_t = K; } else { a.qs_k = T; a.qs_t = 1; }
+    a.mu = P->d_mu; a.sd = P->d_sd; a.mu_out = P->d_mu; a.sd_out = P->d_sd;
+    a.J = J_out_dev ? J_out_dev : P->d_J;
+    a.select = SELECT_CEM;
+    a.best_k = P->best_k; a.sd_min = P->sd_min; a.sd_init = P->sd_init;
+    a.mid = (a.lo + a.hi) * 0.5f;
+    a.ticket = P->d_ticket; a.elite = P->d_elite;
+    a.u_out = u_out_dev; a.best_out = P->d_best;
+    int grid, block;
+    plan_geometry(K, grid, block);
+    const size_t smem = sizeof(float) * 4 * (size_t)T;
+    plan_fn fn = pick_plan(h->cfg.integrator, h->cfg.cost_id, PLAN_CEM);
+    if (smem > 48 * 1024) CUDA_TRY(h, cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    for (int it = 0; it < n_iterations; ++it) {
+        a.Q = eps_dev + (size_t)it * K * T;
+        a.last_iter = (it == n_iterations - 1) ? 1 : 0;
+        a.Q_out = a.last_iter ? Q_out_dev : nullptr;   // Q_logged is the last iteration's plans (cem_tf.py:93)
+        fn<<<grid, block, smem, h->stream>>>(a);
+        h->launches += 1;
+    }
+    CUDA_TRY(h, cudaGetLastError());
+    return CPS_OK;
+}
+
+extern "C" int cps_cem_step_host(cps_handle *h, const float *s_host, const float *eps_dev, int eps_layout, int n_iterations,
+                                 float u_prev, float *u_out_host) {
+    if (!h) return CPS_ERR_INVALID;
+    if (!s_host || !u_out_host) return fail(h, CPS_ERR_INVALID, "cps_cem_step_host: null pointer");
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    memcpy(h->h_pin, s_host, sizeof(float) * 6);
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_s, h->h_pin, sizeof(float) * 6, cudaMemcpyHostToDevice, h->stream));
+    int rc = cps_cem_step(h, h->d_s, eps_dev, eps_layout, n_iterations, u_prev, h->d_u, nullptr, nullptr);
+    if (rc != CPS_OK) return rc;
+    CUDA_TRY(h, cudaMemcpyAsync(h->h_pin + 8, h->d_u, sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    *u_out_host = h->h_pin[8];
+    return CPS_OK;
+}
+
+extern "C" int cps_cem_get_distribution(cps_handle *h, float *mu_host, float *stdev_host) {
+    if (!h) return CPS_ERR_INVALID;
+    PlanState *P = h->plan;
+    if (!P || !P->configured_cem) return fail(h, CPS_ERR_NOT_CONFIGURED, "cps_cem_get_distribution: cps_cem_configure first");
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    const size_t T = h->cfg.horizon;
+    if (mu_host) CUDA_TRY(h, cudaMemcpyAsync(mu_host, P->d_mu, sizeof(float) * T, cudaMemcpyDeviceToHost, h->stream));
+    if (stdev_host) CUDA_TRY(h, cudaMemcpyAsync(stdev_host, P->d_sd, sizeof(float) * T, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return CPS_OK;
+}
+
+extern "C" int cps_cem_set_distribution(cps_handle *h, const float *mu_host, const float *stdev_host) {
+    if (!h) return CPS_ERR_INVALID;
+    PlanState *P = h->plan;
+    if (!P || !P->configured_cem) return fail(h, CPS_ERR_NOT_CONFIGURED, "cps_cem_set_distribution: cps_cem_configure first");
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    const size_t T = h->cfg.horizon;
+    if (mu_host) CUDA_TRY(h, cudaMemcpyAsync(P->d_mu, mu_host, sizeof(float) * T, cudaMemcpyHostToDevice, h->stream));
+    if (stdev_host) CUDA_TRY(h, cudaMemcpyAsync(P->d_sd, stdev_host, sizeof(float) * T, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return CPS_OK;
+}

@@ -1,0 +1,235 @@
+"""optimizer_random_action_b200 and optimizer_cem_b200 -- the reference's forward-only optimizers on the GPU
+(SURVEY.md 8f row f3).
+
+Mirrors of Control_Toolkit/Optimizers/optimizer_random_action_tf.py:12-86 and optimizer_cem_tf.py:12-117: the same
+constructor keywords, `configure`, `step(s, time) -> np scalar`, `optimizer_reset`, and the attributes other code
+reads (`u`, `logging_values`, `num_rollouts`, `mpc_horizon`, `optimizer_name`; CEM: `dist_mue`, `stdev`, `count`).
+`predict_and_cost` (predictor.predict_core + cost_function.get_trajectory_cost) and the selection on the sorted costs
+run as one CUDA kernel launch per evaluation (cps_plan_random_action / cps_cem_step); a CEM solve is `cem_outer_it`
+launches with no host round trip in between.  The predictor and cost-function objects handed in are only inspected
+for their configuration, so this package's wrappers and the reference's own work alike.  ODE / ODE_v0 predictors;
+no CPU fallback.
+
+Semantics kept from the reference: `self.u` (the `u_prev` of the cost's control-change term) is the last RETURNED
+control, 0.0 initially (Optimizers/__init__.py:35); CEM samples Q = clip(mean + normal * stdev) (:66-68), takes the
+`cem_best_k` cheapest plans (ties: lowest index), updates mean / population stdev from them (:79-81), and only after
+the last outer iteration clips the stdev to [cem_stdev_min, 1e8] and shifts both vectors (:96-99); the first call runs
+`warmup_iterations` iterations when `warmup` is set (:93); u = elite_Q[0, 0] of the last iteration.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from . import config as cfgmod
+from .core import Engine
+from .optimizer_mppi_b200 import CudaNormalGenerator, _extract_cost, _extract_predictor
+from .predictors import read_variable
+
+
+class CudaGenerator(CudaNormalGenerator):
+    """normal / uniform draws on the device with the call shapes of tf.random.Generator."""
+
+    def uniform(self, shape, minval=0.0, maxval=1.0, dtype=torch.float32):
+        out = torch.empty(tuple(shape), device=self.device, dtype=dtype)
+        return out.uniform_(float(minval), float(maxval), generator=self.rng)
+
+
+class _forward_optimizer:
+    supported_computation_libraries = ("Numpy", "TF", "Pytorch")
+
+    def __init__(self, predictor, cost_function, control_limits, computation_library=None, seed=None,
+                 mpc_horizon: int = 35, num_rollouts: int = 200, optimizer_logging: bool = False,
+                 calculate_optimal_trajectory: bool = False, device=None, **kwargs):
+        self.lib = computation_library
+        self.num_rollouts = int(num_rollouts)
+        self.mpc_horizon = int(mpc_horizon)
+        self.cost_function = cost_function
+        self.predictor = predictor
+        self.u = 0.0  # template_optimizer.__init__ (Optimizers/__init__.py:35)
+        self.num_states = None
+        self.num_control_inputs = None
+        lo, hi = control_limits
+        self.action_low = np.asarray(lo, dtype=np.float32).reshape(-1)
+        self.action_high = np.asarray(hi, dtype=np.float32).reshape(-1)
+        self.seed = seed
+        self.logging_values = {}
+        self.optimizer_logging = bool(optimizer_logging)
+        self._device_arg = device
+        self.engine = None
+        self.rng = None
+        self._own_rng = None
+        self._var = None
+
+    def configure(self, num_states: int, num_control_inputs: int, default_configure: bool = True, dt: float = None,
+                  predictor_specification: str = None, **kwargs):
+        if int(num_control_inputs) != 1 or int(num_states) != 6:
+            raise ValueError(f"{type(self).__name__} implements the CartPole path: 6 states, 1 control input")
+        self.num_states, self.num_control_inputs = int(num_states), int(num_control_inputs)
+        ptype, n = _extract_predictor(self.predictor, predictor_specification)
+        if ptype not in ("ODE", "ODE_v0"):
+            raise NotImplementedError(f"{type(self).__name__} supports the ODE / ODE_v0 predictors, not {ptype!r} "
+                                      "(no CPU fallback)")
+        if dt is None:
+            dt = getattr(self.predictor, "dt", None) or 0.02
+        cost_name, cost_cfg = _extract_cost(self.cost_function)
+        self.dt = float(dt)
+        self.engine = Engine(num_rollouts=self.num_rollouts, horizon=self.mpc_horizon, dt=self.dt, substeps=n,
+                             integrator=ptype, cost=cost_name, device=self._device_arg)
+        self.device = self.engine.device
+        self.cost_name, self.predictor_type = cost_name, ptype
+        self.engine.set_cost_params(cfgmod.cost_vector(cost_name, cost_cfg))
+        # only the control limits of this block are used by the planners
+        self.engine.set_mppi_params(lo=float(self.action_low[0]), hi=float(self.action_high[0]))
+        self._own_rng = CudaGenerator(self.seed, self.device)
+        self.rng = self._own_rng
+        self._var = None
+        self._configure_engine()
+        if default_configure:
+            self.optimizer_reset()
+
+    def _configure_engine(self):
+        pass
+
+    @property
+    def optimizer_name(self):
+        return self.__class__.__name__.replace("optimizer_", "").replace("_", "-").lower()
+
+    def _refresh_variable_parameters(self):
+        vp = getattr(self.cost_function, "variable_parameters", None)
+        if vp is None:
+            vp = getattr(getattr(self.cost_function, "cost_function", None), "variable_parameters", None)
+        var = (read_variable(vp, "target_position", 0.0), read_variable(vp, "target_equilibrium", 1.0),
+               read_variable(vp, "L", cfgmod.DEFAULT_PHYSICS["L"]),
+               read_variable(vp, "m_pole", cfgmod.DEFAULT_PHYSICS["m_pole"]))
+        if var != self._var:
+            self.engine.set_variable_parameters(*var)
+            self._var = var
+
+    def refresh_cost_parameters(self):
+        _, cfg = _extract_cost(self.cost_function)
+        self.engine.set_cost_params(cfgmod.cost_vector(self.cost_name, cfg))
+
+    def _state(self, s):
+        if self.engine is None:
+            raise RuntimeError(f"{type(self).__name__}.step called before configure")
+        s = np.asarray(s, dtype=np.float32).reshape(-1)
+        if s.shape[0] != 6:
+            raise ValueError(f"state must have 6 entries, got {s.shape[0]}")
+        if self.optimizer_logging:
+            self.logging_values = {"s_logged": s.copy()}
+        self._refresh_variable_parameters()
+        return s
+
+    def _log_rollouts(self, s, Q_kt):
+        """Q_logged / J_logged / rollout_trajectories_logged of the reference: a second evaluation of the final plans
+        with the trajectories materialised (logging only; not on the control path)."""
+        u_prev = float(np.asarray(self._u_prev_logged).reshape(-1)[0])
+        J, traj = self.engine.plan_cost(torch.from_numpy(s).to(self.device), Q_kt.contiguous(), L.ROLLOUT_MAJOR, u_prev,
+                                        want_traj=True)
+        self.logging_values["Q_logged"] = Q_kt.cpu().numpy()[:, :, None]
+        self.logging_values["J_logged"] = J.cpu().numpy()
+        self.logging_values["rollout_trajectories_logged"] = traj.cpu().numpy()
+        self.logging_values["u_logged"] = self.u
+
+
+class optimizer_random_action_b200(_forward_optimizer):
+    """optimizer_random_action_tf: K uniform random plans, the cheapest one's first input."""
+
+    def _draw(self):
+        K, T = self.num_rollouts, self.mpc_horizon
+        lo, hi = float(self.action_low[0]), float(self.action_high[0])
+        if self.rng is self._own_rng:
+            return self._own_rng.uniform((T, K), lo, hi), L.TIME_MAJOR
+        Q = self.rng.uniform(shape=[K, T, 1], minval=lo, maxval=hi, dtype=torch.float32)  # reference call (:58-63)
+        return torch.as_tensor(Q).to(device=self.device, dtype=torch.float32).reshape(K, T).contiguous(), L.ROLLOUT_MAJOR
+
+    def step(self, s: np.ndarray, time=None):
+        s = self._state(s)
+        Q, layout = self._draw()
+        self._u_prev_logged = self.u
+        u = self.engine.plan_random_action_host(s, Q, layout, float(np.asarray(self.u).reshape(-1)[0]))
+        self.u = np.array(u, dtype=np.float32)
+        if self.optimizer_logging:
+            self._log_rollouts(s, Q.t() if layout == L.TIME_MAJOR else Q)
+        return self.u
+
+    def optimizer_reset(self):
+        if self.rng is not None and self.rng is self._own_rng:
+            self._draw()  # the reference draws (and discards) one batch here (:81-86), advancing the generator
+
+
+class optimizer_cem_b200(_forward_optimizer):
+    """optimizer_cem_tf: cross-entropy method with a per-step Gaussian over the input plan."""
+
+    def __init__(self, predictor, cost_function, control_limits, computation_library=None, seed=None,
+                 mpc_horizon: int = 35, cem_outer_it: int = 3, cem_initial_action_stdev: float = 0.5,
+                 num_rollouts: int = 200, cem_stdev_min: float = 0.01, cem_best_k: int = 40, warmup: bool = False,
+                 warmup_iterations: int = 250, optimizer_logging: bool = False,
+                 calculate_optimal_trajectory: bool = False, device=None, **kwargs):
+        super().__init__(predictor=predictor, cost_function=cost_function, control_limits=control_limits,
+                         computation_library=computation_library, seed=seed, mpc_horizon=mpc_horizon,
+                         num_rollouts=num_rollouts, optimizer_logging=optimizer_logging,
+                         calculate_optimal_trajectory=calculate_optimal_trajectory, device=device)
+        self.cem_outer_it = int(cem_outer_it)
+        self.cem_initial_action_stdev = float(cem_initial_action_stdev)
+        self.cem_stdev_min = float(cem_stdev_min)
+        self.cem_best_k = int(cem_best_k)
+        self.warmup = bool(warmup)
+        self.warmup_iterations = int(warmup_iterations)
+        self.count = 0
+
+    def _configure_engine(self):
+        self.engine.cem_configure(self.cem_best_k, self.cem_initial_action_stdev, self.cem_stdev_min)
+
+    # the distribution lives on the device inside the handle; the reference's [1, T, 1] tensors on demand
+    @property
+    def dist_mue(self):
+        return torch.from_numpy(self.engine.cem_get_distribution()[0]).reshape(1, self.mpc_horizon, 1)
+
+    @dist_mue.setter
+    def dist_mue(self, value):
+        v = value.detach().cpu().numpy() if isinstance(value, torch.Tensor) else np.asarray(value)
+        self.engine.cem_set_distribution(mean=v.reshape(-1))
+
+    @property
+    def stdev(self):
+        return torch.from_numpy(self.engine.cem_get_distribution()[1]).reshape(1, self.mpc_horizon, 1)
+
+    @stdev.setter
+    def stdev(self, value):
+        v = value.detach().cpu().numpy() if isinstance(value, torch.Tensor) else np.asarray(value)
+        self.engine.cem_set_distribution(stdev=v.reshape(-1))
+
+    def _draw(self, iterations):
+        K, T = self.num_rollouts, self.mpc_horizon
+        if self.rng is self._own_rng:
+            return self._own_rng.normal((iterations, T, K)), L.TIME_MAJOR
+        eps = [torch.as_tensor(self.rng.normal(shape=(K, T, 1), dtype=torch.float32)).reshape(K, T)
+               for _ in range(iterations)]  # one reference-shaped call per outer iteration (:66-67)
+        return torch.stack(eps).to(device=self.device, dtype=torch.float32).contiguous(), L.ROLLOUT_MAJOR
+
+    def step(self, s: np.ndarray, time=None):
+        s = self._state(s)
+        iterations = self.warmup_iterations if self.warmup and self.count == 0 else self.cem_outer_it
+        eps, layout = self._draw(iterations)
+        u_prev = float(np.asarray(self.u).reshape(-1)[0])
+        self._u_prev_logged = self.u
+        if self.optimizer_logging:
+            K, T = self.num_rollouts, self.mpc_horizon
+            Q = torch.empty((T, K) if layout == L.TIME_MAJOR else (K, T), device=self.device)
+            u_dev = self.engine.cem_step(torch.from_numpy(s).to(self.device), eps, layout, u_prev, Q_out=Q)
+            u = float(u_dev.cpu()[0])
+        else:
+            u = self.engine.cem_step_host(s, eps, layout, u_prev)
+        self.u = np.array(u, dtype=np.float32)
+        if self.optimizer_logging:
+            self._log_rollouts(s, Q.t() if layout == L.TIME_MAJOR else Q)
+        self.count += 1
+        return self.u
+
+    def optimizer_reset(self):
+        self.engine.cem_reset()
+        self.count = 0
+        self.u = 0.0

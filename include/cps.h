@@ -318,6 +318,43 @@ int cps_fleet_step(cps_handle *h, int n_periods, const float *tp_dev, const floa
 /* The draws CPS_FLEET_NOISE_PHILOX uses in controller period `period`: out_dev [E][n_ind][K]. */
 int cps_fleet_noise(cps_handle *h, long long period, float *out_dev);
 
+/* ---- forward-only planners: predict_and_cost and the selection step ----------------------- */
+/* optimizer_random_action_tf / optimizer_cem_tf / optimizer_cem_gmm_tf evaluate K candidate input plans from one state
+ * with predictor.predict_core(s, Q) followed by cost_function.get_trajectory_cost(trajectory, Q, u_prev)
+ * (Control_Toolkit/Optimizers/optimizer_random_action_tf.py:42-49, optimizer_cem_tf.py:57-61,
+ * optimizer_cem_gmm_tf.py:53-54) and select on the sorted costs.  Here evaluation and selection are one launch; the
+ * trajectory tensor is only written when asked for.  ODE predictors and the four cost plugins; plans are clipped by
+ * the caller (random action) or in the kernel (CEM) to the control limits of cps_set_mppi_params (lo, hi).
+ *
+ * cps_plan_cost: J_out_dev[k] = get_trajectory_cost(predict_core(s, Q), Q, u_prev)[k] for K plans of length T
+ * (any K, T; Q_dev [K][T] CPS_ROLLOUT_MAJOR or [T][K] CPS_TIME_MAJOR); traj_out_dev as in cps_mppi_step or NULL. */
+int cps_plan_cost(cps_handle *h, const float *s_dev, const float *Q_dev, int q_layout, int K, int T, float u_prev,
+                  float *J_out_dev, float *traj_out_dev, int traj_layout);
+/* optimizer_random_action_tf.step (:52-79) for the handle's (K, T): u_out_dev[0] = Q[argmin J, 0], ties to the lowest
+ * index.  J_out_dev [K] and best_out_dev [1] (index of the cheapest plan) may be NULL. */
+int cps_plan_random_action(cps_handle *h, const float *s_dev, const float *Q_dev, int q_layout, float u_prev,
+                           float *u_out_dev, float *J_out_dev, int *best_out_dev);
+int cps_plan_random_action_host(cps_handle *h, const float *s_host, const float *Q_dev, int q_layout, float u_prev,
+                                float *u_out_host);
+/* optimizer_cem_tf (:12-117).  cps_cem_configure: cem_best_k, cem_initial_action_stdev, cem_stdev_min; allocates the
+ * sampling distribution (mean, stdev per horizon step) and resets it as optimizer_reset does (:112-116).
+ * cps_cem_step: n_iterations outer iterations (cem_outer_it, or warmup_iterations on the first call), one launch each:
+ * Q = clip(mean + eps * stdev), predict_and_cost, the cem_best_k cheapest plans (ties to the lowest index), mean and
+ * population stdev of the elites per step (update_distribution, :63-83); after the last iteration stdev is clipped to
+ * [cem_stdev_min, 1e8], both vectors are shifted by one step (tail: initial stdev, mid-range mean) and
+ * u_out_dev[0] = elite_Q[0, 0] (:96-99).  eps_dev: standard-normal draws [n_iterations][K][T] (or [n_iterations][T][K]
+ * with CPS_TIME_MAJOR); Q_out_dev (same layout, one iteration) receives the LAST iteration's plans, J_out_dev [K] its
+ * costs; both may be NULL. */
+int cps_cem_configure(cps_handle *h, int best_k, float initial_stdev, float stdev_min);
+int cps_cem_reset(cps_handle *h);
+int cps_cem_step(cps_handle *h, const float *s_dev, const float *eps_dev, int eps_layout, int n_iterations, float u_prev,
+                 float *u_out_dev, float *Q_out_dev, float *J_out_dev);
+int cps_cem_step_host(cps_handle *h, const float *s_host, const float *eps_dev, int eps_layout, int n_iterations,
+                      float u_prev, float *u_out_host);
+/* dist_mue / stdev [T]; either pointer may be NULL.  Synchronise. */
+int cps_cem_get_distribution(cps_handle *h, float *mean_host, float *stdev_host);
+int cps_cem_set_distribution(cps_handle *h, const float *mean_host, const float *stdev_host);
+
 /* Roofline denominators for the compute-bound rollout kernels, measured on this device with two microbenchmarks
  * (dense FFMA chains; MUFU.EX2 chains): FP32 TFLOP/s (FMA = 2 flops) and MUFU Gop/s.  Synchronises. */
 int cps_measure_peaks(cps_handle *h, double *fp32_tflops, double *mufu_gops);

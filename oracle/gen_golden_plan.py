@@ -1,0 +1,121 @@
+"""Golden vectors for the forward-only optimizers: tests/golden/plan_*.npz.
+
+TEST INFRASTRUCTURE ONLY.  Runs the UNMODIFIED reference classes optimizer_random_action_tf and optimizer_cem_tf
+(Control_Toolkit/Optimizers/optimizer_random_action_tf.py, optimizer_cem_tf.py) in this container.  TensorFlow is not
+installed here, so the handful of tf.* ops these two files call is supplied by oracle/tf_shim.py (torch CPU float32);
+the optimizers' own Python runs as is, on the reference's torch predictor_ODE (or numba predictor_ODE_v0) and the
+reference's cost plugins, with the generator's draws injected so that the CUDA path can be fed the same numbers.
+
+    python oracle/gen_golden_plan.py
+"""
+from __future__ import annotations
+
+import contextlib
+import io
+import os
+import sys
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+
+from oracle import tf_shim  # noqa: E402
+
+tf_shim.install()  # before the reference is imported
+
+from oracle import ref_loader as R  # noqa: E402
+from oracle.gen_golden import hanging_state, make_states, save  # noqa: E402
+
+
+def _make(cls_name, pred, cost, K, T, tp, te, **params):
+    import importlib
+    import torch
+    from SI_Toolkit.computation_library import TensorFlowLibrary
+    lib = R.torch_lib()
+    vp = R.variable_parameters(lib, tp, te)
+    cw = R.cost_function(cost, lib, vp, K, T)
+    Pred = R.ODEv0CoreAdapter if pred == "ODE_v0" else R.ODECoreAdapter
+    predictor = Pred(T, K, 0.02, 10, None if pred == "ODE_v0" else vp)
+    mod = importlib.import_module("Control_Toolkit.Optimizers." + cls_name)
+    cls = getattr(mod, cls_name)
+    opt = cls(predictor=predictor, cost_function=cw,
+              control_limits=(np.array([-1.0], dtype=np.float32), np.array([1.0], dtype=np.float32)),
+              computation_library=TensorFlowLibrary(), seed=1, mpc_horizon=T, num_rollouts=K,
+              optimizer_logging=True, calculate_optimal_trajectory=False, **params)
+    opt.rng = tf_shim.InjectedDraws([torch.zeros(K, T, 1)])  # optimizer_reset of random-action draws once
+    opt.configure(num_states=6, num_control_inputs=1)
+    return opt
+
+
+def gen_random_action():
+    from oracle import oracle as O
+    runs = [("ra_ode_gradmin", "ODE", "quadratic_boundary_grad_minimal", 640, 35, 4, 0.0, 1.0),
+            ("ra_v0_qb", "ODE_v0", "quadratic_boundary", 256, 35, 3, 0.05, 1.0),
+            ("ra_ode_default", "ODE", "default", 200, 20, 3, 0.0, -1.0)]
+    for (name, pred, cost, K, T, steps, tp, te) in runs:
+        rng = np.random.default_rng(abs(hash(name)) % (2 ** 31))
+        opt = _make("optimizer_random_action_tf", pred, cost, K, T, tp, te)
+        Qs = [rng.uniform(-1, 1, (K, T, 1)).astype(np.float32) for _ in range(steps)]
+        opt.rng = tf_shim.InjectedDraws(Qs)
+        s = make_states(rng, 1, "random")[0] if "default" in name else hanging_state()
+        S, U, JJ, UP = [], [], [], []
+        for i in range(steps):
+            UP.append(np.float32(opt.u))
+            u = opt.step(s.copy())
+            S.append(s.copy()); U.append(np.float32(u)); JJ.append(opt.logging_values["J_logged"].astype(np.float32))
+            s = O.rollout("ODE", s, np.array([[u]], dtype=np.float32))[0, 1]
+        save("plan_" + name, dict(ref="Control_Toolkit/Optimizers/optimizer_random_action_tf.py:52-79 (tf ops from "
+                                      "oracle/tf_shim.py, injected uniform draws)", predictor=pred, cost=cost, K=K, T=T,
+                                  steps=steps, target_position=tp, target_equilibrium=te),
+             Q=np.stack([q[:, :, 0] for q in Qs]), s=np.stack(S), u=np.array(U), J=np.stack(JJ), u_prev=np.array(UP))
+
+
+def gen_cem():
+    from oracle import oracle as O
+    runs = [  # name, predictor, cost, K, T, steps, outer iterations, best_k, tp, te
+        ("cem_ode_gradmin", "ODE", "quadratic_boundary_grad_minimal", 200, 35, 4, 3, 40, 0.0, 1.0),
+        ("cem_v0_gradmin", "ODE_v0", "quadratic_boundary_grad_minimal", 200, 35, 3, 3, 40, 0.0, 1.0),
+        ("cem_ode_qb", "ODE", "quadratic_boundary", 256, 20, 3, 2, 17, 0.05, 1.0),
+        ("cem_ode_K1024", "ODE", "quadratic_boundary_grad_minimal", 1024, 40, 2, 2, 100, 0.0, 1.0),
+    ]
+    for (name, pred, cost, K, T, steps, iters, best_k, tp, te) in runs:
+        rng = np.random.default_rng(abs(hash(name)) % (2 ** 31))
+        opt = _make("optimizer_cem_tf", pred, cost, K, T, tp, te, cem_outer_it=iters, cem_initial_action_stdev=0.5,
+                    cem_stdev_min=0.01, cem_best_k=best_k, warmup=False, warmup_iterations=250)
+        eps = rng.standard_normal((steps, iters, K, T)).astype(np.float32)
+        opt.rng = tf_shim.InjectedDraws([eps[i, j][:, :, None] for i in range(steps) for j in range(iters)])
+        s = hanging_state()
+        S, U, JJ, QQ, UP, MU, SD = [], [], [], [], [], [], []
+        for i in range(steps):
+            UP.append(np.float32(opt.u))
+            u = opt.step(s.copy())
+            S.append(s.copy()); U.append(np.float32(u))
+            JJ.append(opt.logging_values["J_logged"].astype(np.float32))
+            QQ.append(opt.logging_values["Q_logged"][:, :, 0].astype(np.float32))
+            MU.append(opt.dist_mue.numpy().reshape(-1).astype(np.float32))
+            SD.append(opt.stdev.numpy().reshape(-1).astype(np.float32))
+            s = O.rollout("ODE", s, np.array([[u]], dtype=np.float32))[0, 1]
+        save("plan_" + name, dict(ref="Control_Toolkit/Optimizers/optimizer_cem_tf.py:63-109 (tf ops from "
+                                      "oracle/tf_shim.py, injected normal draws)", predictor=pred, cost=cost, K=K, T=T,
+                                  steps=steps, iterations=iters, best_k=best_k, initial_stdev=0.5, stdev_min=0.01,
+                                  target_position=tp, target_equilibrium=te),
+             eps=eps, s=np.stack(S), u=np.array(U), J=np.stack(JJ), Q=np.stack(QQ), u_prev=np.array(UP),
+             mean=np.stack(MU), stdev=np.stack(SD))
+
+
+def main():
+    if not R.available():
+        raise SystemExit("reference tree not available; fixtures can only be regenerated in the build container")
+    R.load()
+    for fn in (gen_random_action, gen_cem):
+        with contextlib.redirect_stdout(io.StringIO()) as buf:
+            try:
+                fn()
+            finally:
+                txt = buf.getvalue()
+        print("\n".join(l for l in txt.splitlines() if l.startswith("wrote")))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,130 @@
+"""A stand-in `tensorflow` module, just large enough to EXECUTE the reference's forward-only optimizers
+(Control_Toolkit/Optimizers/optimizer_random_action_tf.py, optimizer_cem_tf.py) in this container, where TensorFlow is
+not installed.
+
+TEST INFRASTRUCTURE ONLY (used by oracle/gen_golden_plan.py; never imported by the product, the GPU tests or bench.py).
+The optimizers' own Python -- control flow, call order, slicing, the distribution update and shift -- runs unmodified;
+only the ~15 `tf.*` ops it calls are supplied here, on torch CPU float32 tensors, following the documented TF semantics:
+  tf.argsort            ascending; equal keys keep index order (TF's CPU kernel sorts with a stable top-k)
+  tf.math.reduce_std    population standard deviation: sqrt(mean(|x - mean(x)|^2)) (tf.math.reduce_variance)
+  tf.clip_by_value, tf.tile, tf.gather, tf.concat, tf.reduce_mean, tf.squeeze, tf.multiply, tf.zeros, tf.ones,
+  tf.convert_to_tensor, tf.constant, tf.ensure_shape: their numpy namesakes.
+Everything else resolves to an inert stub so that `TensorFlowLibrary()` (SI_Toolkit/computation_library.py:306-...) can
+be constructed; none of those attributes is called on this path.  What this pins is the optimizer LOGIC of the
+reference, not TensorFlow's kernels (the summation order inside reduce_mean / reduce_std is TF's own; the parity
+tolerance on the distribution covers it).
+"""
+from __future__ import annotations
+
+import sys
+import types
+
+import numpy as np
+import torch
+
+
+class _Inert:
+    def __init__(self, name):
+        self._n = name
+
+    def __call__(self, *a, **k):
+        return _Inert(self._n + "()")
+
+    def __getattr__(self, name):
+        if name.startswith("__") and name.endswith("__"):
+            raise AttributeError(name)
+        return _Inert(self._n + "." + name)
+
+    def __mro_entries__(self, bases):
+        return (object,)
+
+    def __iter__(self):
+        return iter(())
+
+
+class _Mod(types.ModuleType):
+    def __getattr__(self, name):
+        if name.startswith("__") and name.endswith("__"):
+            raise AttributeError(name)
+        obj = _Inert(f"{self.__name__}.{name}")
+        setattr(self, name, obj)
+        return obj
+
+
+def _t(x, dtype=None):
+    if isinstance(x, torch.Tensor):
+        return x if dtype is None else x.to(dtype)
+    return torch.as_tensor(np.asarray(x), dtype=dtype)
+
+
+def _constant(x, dtype=None):
+    a = np.asarray(x)
+    if dtype is None and a.dtype.kind in "iu":  # np.tile(s, tf.constant([K, 1])) needs plain integers
+        return a
+    return _t(a, dtype)
+
+
+def _tile(x, reps):
+    return _t(x).repeat(*[int(r) for r in reps])
+
+
+def _argsort(x, axis=-1, direction="ASCENDING", stable=False):
+    return torch.sort(_t(x), dim=axis, descending=(direction != "ASCENDING"), stable=True).indices
+
+
+def _reduce_std(x, axis=None, keepdims=False):
+    x = _t(x)
+    m = torch.mean(x, dim=axis, keepdim=True)
+    v = torch.mean((x - m) * (x - m), dim=axis, keepdim=keepdims)
+    return torch.sqrt(v)
+
+
+def install():
+    """Put the shim into sys.modules as `tensorflow` (before oracle.ref_loader.load()).  Idempotent."""
+    cur = sys.modules.get("tensorflow")
+    if getattr(cur, "_cps_shim", False):
+        return cur
+    tf = _Mod("tensorflow")
+    tf.__path__ = []
+    tf._cps_shim = True
+    tf.float32, tf.float64, tf.int32 = torch.float32, torch.float64, torch.int32
+    tf.Tensor = torch.Tensor
+    tf.constant = _constant
+    tf.convert_to_tensor = lambda x, dtype=None: _t(x, dtype)
+    tf.zeros = lambda shape, dtype=torch.float32: torch.zeros(tuple(int(v) for v in np.atleast_1d(shape)), dtype=dtype)
+    tf.ones = lambda shape, dtype=torch.float32: torch.ones(tuple(int(v) for v in np.atleast_1d(shape)), dtype=dtype)
+    tf.tile = _tile
+    tf.multiply = lambda a, b: _t(a) * _t(b)
+    tf.clip_by_value = lambda x, lo, hi: torch.minimum(torch.maximum(_t(x), _t(lo)), _t(hi))
+    tf.argsort = _argsort
+    tf.gather = lambda x, idx, axis=0: torch.index_select(_t(x), axis, _t(idx).reshape(-1).long())
+    tf.reduce_mean = lambda x, axis=None, keepdims=False: torch.mean(_t(x), dim=axis, keepdim=keepdims)
+    tf.concat = lambda xs, axis=0: torch.cat([_t(x, torch.float32) for x in xs], dim=axis)
+    tf.squeeze = lambda x, axis=None: torch.squeeze(_t(x)) if axis is None else torch.squeeze(_t(x), axis)
+    tf.ensure_shape = lambda x, shape: x
+    math = _Mod("tensorflow.math")
+    math.reduce_std = _reduce_std
+    tf.math = math
+    sys.modules["tensorflow"] = tf
+    sys.modules["tensorflow.math"] = math
+    return tf
+
+
+class InjectedDraws:
+    """Replaces optimizer.rng (a tf.random.Generator): hands out pre-supplied tensors in call order."""
+
+    def __init__(self, draws):
+        self.draws = [torch.as_tensor(np.asarray(d), dtype=torch.float32) for d in draws]
+        self.i = 0
+
+    def _next(self, shape):
+        d = self.draws[self.i]
+        self.i += 1
+        assert [int(v) for v in shape] == list(d.shape), (list(shape), d.shape)
+        return d
+
+    def normal(self, shape, dtype=None, **kw):
+        return self._next(shape)
+
+    def uniform(self, shape, minval=None, maxval=None, dtype=None, **kw):
+        return self._next(shape)
