@@ -47,7 +47,33 @@ struct FleetArgs {
     float *record;              // [E][CPS_FLEET_RECORD] of this period, or null
     float *J_out;               // [E][K] or null
     double time;                // period * dt_control
+    // relabel mode (cps_fleet_relabel): states come from a recording, the plant is not integrated
+    const float *replay_s;      // [E][6] recorded states of this row, or null (closed loop)
+    const float *L_row, *mp_row;  // [E] controller-model pole length / mass of this row, or null (handle's values)
+    float *Q_out;               // [E] controls computed for this row
+    float k, m_cart, g, J_fric, M_fric, u_max;  // physical constants for the device-side fold of (L, m_pole)
+    float m_pole_fixed;         // ODE_v0 takes only L from the variable parameters
+    float L_default, mp_default;  // the handle's L / m_pole "for controller" when only one of the arrays is given
 };
+
+// fold_ode (cps_lib.cu) on the device, same double-precision expressions: the controller's model constants for a
+// per-experiment pole length / mass (add_control_along_trajectories feeds L per recorded row).
+template <int INTEG>
+__device__ __forceinline__ void fold_ode_device(const FleetArgs &a, double L, double mp_in, OdeParams &o) {
+    const double k = a.k, mc = a.m_cart, g = a.g, J = a.J_fric, M = a.M_fric;
+    const double mp = (INTEG == 0) ? (double)a.m_pole_fixed : mp_in;
+    const double kp1 = k + 1.0, Lh = L / 2.0;
+    o.KM = (float)(kp1 * (mc + mp));
+    o.m_p = (float)mp;
+    o.c1 = (float)(mp * g);
+    o.c2 = (float)(kp1 * mp * Lh);
+    o.c3 = (float)(J / Lh);
+    o.c5 = (float)(kp1 * M);
+    o.d1 = (float)(g / (kp1 * Lh));
+    o.d2 = (float)(1.0 / (kp1 * Lh));
+    o.d3 = (float)(J / (mp * Lh * kp1 * Lh));
+    o.bounce = (float)(2.0 / (0.5 * L));
+}
 
 // ---- Philox4x32-10 (Salmon et al., SC'11), the counter-based generator torch / TF / cuRAND also use ---------------------
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
@@ -166,7 +192,7 @@ __global__ void __launch_bounds__(256, 4) fleet_kernel(const __grid_constant__ F
     __syncthreads();
 
     SolveIO io;
-    io.s = a.s + (size_t)e * 8;
+    io.s = a.replay_s ? a.replay_s + (size_t)e * 6 : a.s + (size_t)e * 8;
     if (PHILOX) {  // rollout k of this block sits at s_eps[i * blockDim.x + tid]
         io.noise = s_eps - (long long)blockIdx.x * blockDim.x;
         io.ns_i = blockDim.x; io.ns_k = 1;
@@ -183,11 +209,19 @@ __global__ void __launch_bounds__(256, 4) fleet_kernel(const __grid_constant__ F
     io.ticket = a.tickets + e;
     io.nonfinite = a.nonfinite;
     io.shard_out = nullptr;
-    const bool last = mppi_solve_block<INTEG, COST, SC_ROTATE, CPS_NOISE_INDUCING, false, false>(a.ode, s_cost, mp, io, smem,
+    OdeParams ode = a.ode;
+    if (a.L_row || a.mp_row)
+        fold_ode_device<INTEG>(a, a.L_row ? (double)a.L_row[e] : (double)a.L_default,
+                               a.mp_row ? (double)a.mp_row[e] : (double)a.mp_default, ode);
+    const bool last = mppi_solve_block<INTEG, COST, SC_ROTATE, CPS_NOISE_INDUCING, false, false>(ode, s_cost, mp, io, smem,
                                                                                                 blockIdx.x, a.bpe);
     if (!last) return;
     __syncthreads();
     if (tid != 0) return;
+    if (a.replay_s) {   // relabel: the control is the result; the next row brings its own state
+        a.Q_out[e] = *io.u_out;
+        return;
+    }
 
     // ---- the plant: one controller period with Q held (CartPole/__init__.py:283-324, 475-527) -------------------------
     const PlantParams &P = a.plant;
@@ -315,6 +349,18 @@ extern "C" int cps_fleet_set_states(cps_handle *h, const float *s_host, long lon
     return CPS_OK;
 }
 
+extern "C" int cps_fleet_reset(cps_handle *h, long long period) {
+    if (!h) return CPS_ERR_INVALID;
+    FleetState *F = h->fleet;
+    if (!F) return fail(h, CPS_ERR_NOT_CONFIGURED, "cps_fleet_reset: no fleet (cps_fleet_create)");
+    if (period < 0) return fail(h, CPS_ERR_INVALID, "cps_fleet_reset: period < 0");
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    CUDA_TRY(h, cudaMemsetAsync(F->d_unom, 0, sizeof(float) * (size_t)F->E * h->cfg.horizon, h->stream));
+    CUDA_TRY(h, cudaMemsetAsync(F->d_uprev, 0, sizeof(float) * (size_t)F->E, h->stream));
+    F->period = period;
+    return CPS_OK;
+}
+
 extern "C" int cps_fleet_get_states(cps_handle *h, float *s_host, float *u_nom_host, float *u_prev_host) {
     if (!h) return CPS_ERR_INVALID;
     FleetState *F = h->fleet;
@@ -344,9 +390,10 @@ extern "C" long long cps_fleet_period(const cps_handle *h) { return (h && h->fle
 // CostParams for a given target equilibrium: fold_cost() depends on it for quadratic_boundary_grad (weight set, w[9]).
 int cps_fold_cost_for(cps_handle *h, float target_equilibrium, CostParams *out);
 
-extern "C" int cps_fleet_step(cps_handle *h, int n_periods, const float *tp_dev, const float *te_dev, const float *noise_dev,
-                              float *record_dev, float *J_out_dev) {
-    if (!h) return CPS_ERR_INVALID;
+// Shared by cps_fleet_step (closed loop: replay_dev == nullptr) and cps_fleet_relabel (states from a recording).
+static int fleet_launch(cps_handle *h, int n_periods, const float *tp_dev, const float *te_dev, const float *noise_dev,
+                        float *record_dev, float *J_out_dev, const float *replay_dev, const float *L_dev,
+                        const float *mp_dev, float *Q_out_dev) {
     FleetState *F = h->fleet;
     if (!F) return fail(h, CPS_ERR_NOT_CONFIGURED, "cps_fleet_step: no fleet (cps_fleet_create)");
     if (n_periods < 0) return fail(h, CPS_ERR_INVALID, "cps_fleet_step: n_periods < 0");
@@ -368,6 +415,9 @@ extern "C" int cps_fleet_step(cps_handle *h, int n_periods, const float *tp_dev,
     a.s = F->d_s; a.u_nom = F->d_unom; a.u_prev = F->d_uprev;
     a.seed = F->cfg.seed; a.e_offset = (unsigned)F->cfg.experiment_offset;
     a.partials = F->d_partials; a.tickets = F->d_tickets; a.nonfinite = h->d_nonfinite;
+    a.k = P.k; a.m_cart = P.m_cart; a.g = P.g; a.J_fric = P.J_fric; a.M_fric = P.M_fric; a.u_max = P.u_max;
+    a.m_pole_fixed = h->phys[CPS_PH_M_POLE];
+    a.L_default = h->L_var; a.mp_default = h->m_pole_var;
     fleet_fn fn = pick_fleet(h->cfg.integrator, h->cfg.cost_id, philox);
     if (!fn) return fail(h, CPS_ERR_NOT_CONFIGURED, "cps_fleet_step: no kernel for this configuration");
     if (F->smem > 48 * 1024) CUDA_TRY(h, cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F->smem));
@@ -380,6 +430,10 @@ extern "C" int cps_fleet_step(cps_handle *h, int n_periods, const float *tp_dev,
         a.noise = noise_dev ? noise_dev + (size_t)j * E * h->n_ind * K : nullptr;
         a.record = record_dev ? record_dev + (size_t)j * E * CPS_FLEET_RECORD : nullptr;
         a.J_out = J_out_dev ? J_out_dev + (size_t)j * E * K : nullptr;
+        a.replay_s = replay_dev ? replay_dev + (size_t)j * E * 6 : nullptr;
+        a.L_row = L_dev ? L_dev + (size_t)j * E : nullptr;
+        a.mp_row = mp_dev ? mp_dev + (size_t)j * E : nullptr;
+        a.Q_out = Q_out_dev ? Q_out_dev + (size_t)j * E : nullptr;
         a.period = (unsigned)F->period;
         a.time = (double)F->period * dt_control;
         fn<<<grid, F->block, F->smem, h->stream>>>(a);
@@ -388,6 +442,20 @@ extern "C" int cps_fleet_step(cps_handle *h, int n_periods, const float *tp_dev,
     }
     CUDA_TRY(h, cudaGetLastError());
     return CPS_OK;
+}
+
+extern "C" int cps_fleet_step(cps_handle *h, int n_periods, const float *tp_dev, const float *te_dev, const float *noise_dev,
+                              float *record_dev, float *J_out_dev) {
+    if (!h) return CPS_ERR_INVALID;
+    return fleet_launch(h, n_periods, tp_dev, te_dev, noise_dev, record_dev, J_out_dev, nullptr, nullptr, nullptr, nullptr);
+}
+
+extern "C" int cps_fleet_relabel(cps_handle *h, int n_rows, const float *states_dev, const float *tp_dev, const float *te_dev,
+                                 const float *L_dev, const float *m_pole_dev, const float *noise_dev, float *Q_out_dev,
+                                 float *J_out_dev) {
+    if (!h) return CPS_ERR_INVALID;
+    if (!states_dev || !Q_out_dev) return fail(h, CPS_ERR_INVALID, "cps_fleet_relabel: null pointer");
+    return fleet_launch(h, n_rows, tp_dev, te_dev, noise_dev, nullptr, J_out_dev, states_dev, L_dev, m_pole_dev, Q_out_dev);
 }
 
 extern "C" int cps_fleet_noise(cps_handle *h, long long period, float *out_dev) {

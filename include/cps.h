@@ -315,6 +315,21 @@ long long cps_fleet_period(const cps_handle *h);
  * it, what save_csv_routine logs at dt_save = dt_controller) or NULL; J_out_dev: [n_periods][E][K] or NULL. */
 int cps_fleet_step(cps_handle *h, int n_periods, const float *tp_dev, const float *te_dev, const float *noise_dev,
                    float *record_dev, float *J_out_dev);
+/* Offline relabelling: add_control_along_trajectories
+ * (SI_Toolkit/src/SI_Toolkit/General/preprocess_data_add_control_along_trajectories.py:53-140) calls controller.step once
+ * per recorded row -- `updated_attributes` first, then one solve from the recorded state -- sequentially within a file
+ * (the optimizer keeps its warm start and last control) and independently across files (the reference runs a 120-way
+ * SLURM array, others/EulerClusterScripts/ControllerAlongTrajectories.sh).  Here E files advance in lockstep, one
+ * launch per row: states_dev [n_rows][E][6] recorded states; tp_dev / te_dev / L_dev / m_pole_dev [n_rows][E] the
+ * row's attributes (NULL: 0 / +1 / the handle's L / m_pole; ODE_v0 ignores m_pole as the reference does);
+ * noise_dev as in cps_fleet_step; Q_out_dev [n_rows][E] the controls; J_out_dev as in cps_fleet_step or NULL.
+ * The fleet's plant state is not touched.  Rows of a Monte-Carlo integration over an attribute (:118-128, 64
+ * evaluations per recorded row by default) are simply consecutive rows here; the caller averages.
+ * cps_fleet_reset: controller.reset() for every file (zero warm start and last control) + the period counter. */
+int cps_fleet_relabel(cps_handle *h, int n_rows, const float *states_dev, const float *tp_dev, const float *te_dev,
+                      const float *L_dev, const float *m_pole_dev, const float *noise_dev, float *Q_out_dev,
+                      float *J_out_dev);
+int cps_fleet_reset(cps_handle *h, long long period);
 /* The draws CPS_FLEET_NOISE_PHILOX uses in controller period `period`: out_dev [E][n_ind][K]. */
 int cps_fleet_noise(cps_handle *h, long long period, float *out_dev);
 

@@ -1,0 +1,76 @@
+"""CPU tests of the host side of offline relabelling (cartpolesimulation_b200/relabel.py): the reference's
+attribute-name conventions and the row/evaluation expansion handed to the device, with the device stage recorded."""
+import numpy as np
+import pandas as pd
+import pytest
+
+from cartpolesimulation_b200 import relabel as RL
+from tests.parity import load_golden
+
+STATE = ["angle", "angleD", "angle_cos", "angle_sin", "position", "positionD"]
+
+
+class Recorder:
+    def __init__(self, E):
+        self.E, self.calls, self.resets = E, [], 0
+
+    def reset(self, period=0):
+        self.resets += 1
+
+    def relabel(self, states, tp, te, L, mp, noise=None):
+        self.calls.append(dict(states=states, tp=tp, te=te, L=L, mp=mp))
+        return np.tile(np.arange(states.shape[0], dtype=np.float32)[:, None], (1, self.E))
+
+
+def test_expansion_matches_what_the_reference_feeds_its_controller():
+    z, m = load_golden("relabel_plain_ode")
+    E = m["files"]
+    dfs = [pd.DataFrame(z[f"f{f}__table"], columns=m["columns"]) for f in range(E)]
+    rec = Recorder(E)
+    cfg = dict(state_components=STATE, environment_attributes_dict=m["environment_attributes_dict"])
+    out = RL.add_control_along_trajectories(dfs, cfg, "Q_calculated_offline", relabeller=rec)
+    c = rec.calls[0]
+    assert rec.resets == 1 and c["mp"] is None
+    for f in range(E):   # exactly the recorded controller.step inputs of the reference run
+        np.testing.assert_array_equal(c["states"][:, f], z[f"f{f}__s"])
+        np.testing.assert_array_equal(c["tp"][:, f], z[f"f{f}__tp"].astype(np.float32))
+        np.testing.assert_array_equal(c["te"][:, f], z[f"f{f}__te"].astype(np.float32))
+        np.testing.assert_array_equal(c["L"][:, f], z[f"f{f}__L"].astype(np.float32))
+        np.testing.assert_array_equal(out[f]["Q_calculated_offline"].to_numpy(), np.arange(m["rows"]))
+
+
+def test_integration_expands_rows_and_averages():
+    z, m = load_golden("relabel_integrate_ode")
+    dfs = [pd.DataFrame(z[f"f{f}__table"], columns=m["columns"]) for f in range(2)]
+    dfs[1] = dfs[1].iloc[:3].copy()
+    rec = Recorder(2)
+    cfg = dict(state_components=STATE, environment_attributes_dict=m["environment_attributes_dict"])
+    out = RL.add_control_along_trajectories(dfs, cfg, "Q", integration_num_evals=6, relabeller=rec, seed=1,
+                                            save_output_only=True)
+    c = rec.calls[0]
+    ev = 8   # 6 is rounded up to the next power of two, as the reference does for Sobol sequences (:326-331)
+    assert c["states"].shape == (5 * ev, 2, 6)
+    s = c["states"].reshape(5, ev, 2, 6)
+    assert (s == s[:, :1]).all()                      # the same recorded state for every evaluation of a row
+    L = c["L"].reshape(5, ev, 2)
+    assert (L >= 0.25).all() and (L <= 0.55).all() and np.unique(L[:, :, 0]).size == 5 * ev
+    assert abs(L[:, :, 0].mean() - 0.4) < 0.02        # low-discrepancy sample of [0.25, 0.55]
+    np.testing.assert_array_equal(s[3:, :, 1], np.broadcast_to(s[2:3, :, 1], s[3:, :, 1].shape))  # short file idles on its last row
+    assert [len(o) for o in out] == [5, 3]
+    np.testing.assert_allclose(out[0]["Q"].to_numpy(), np.arange(5) * ev + (ev - 1) / 2)   # mean over the evaluations
+
+
+def test_attribute_name_conventions():
+    df = pd.DataFrame({"L": np.linspace(0.3, 0.5, 50)})
+    d2, env = RL.process_random_sampling(df.copy(), {"L": "L_random_uniform_0.25_0.55", "x": "L"}, np.random.default_rng(0))
+    assert env == {"L": "L_random_uniform", "x": "L"} and d2["L_random_uniform"].between(0.25, 0.55).all()
+    d3, env = RL.process_random_sampling(df.copy(), {"L": "L_random_uniform_0.2_0.5_0.1_"}, np.random.default_rng(0))
+    assert set(np.round(d3["L_random_uniform"], 6)) <= {0.2, 0.3, 0.4, 0.5}
+    f, r, env = RL.get_integration_features({"L": "L_integrate_0.25_0.55_", "target_position": "target_position"})
+    assert f == ["L"] and r == {"L": (0.25, 0.55)} and env["L"] == "L"
+    with pytest.raises(NotImplementedError):
+        RL.add_control_along_trajectories([df], dict(environment_attributes_dict={"L": "L_differentiate_"}), relabeller=Recorder(1))
+    with pytest.raises(NotImplementedError):
+        RL.add_control_along_trajectories([df.assign(**{c: 0.0 for c in STATE})],
+                                          dict(environment_attributes_dict={"L": "L_integrate_0.25_0.55_"}),
+                                          integration_method="nquad", relabeller=Recorder(1))
