@@ -211,6 +211,95 @@ def mppi_latency(device, n_calls=1000):
         out["fleet_1024x2000x50"]["cpu_port_threads"] = O.lib().cps_oracle_num_threads()
     except Exception as ex:
         out["fleet_1024x2000x50"] = {"error": repr(ex)}
+    for key, fn in (("forward_optimizers", planner_latency), ("relabel_256_files", relabel_bench)):
+        try:
+            out[key] = fn(device)
+        except Exception as ex:
+            out[key] = {"error": repr(ex)}
+    return out
+
+
+def planner_latency(device, n_calls=300):
+    """optimizer_cem_b200 / optimizer_random_action_b200 .step(numpy s) -> numpy u with the
+    reference's shipped settings (config_optimizers.yml: cem-tf 200 rollouts x 35 steps, 3 outer iterations, 40 elites;
+    random-action-tf 640 x 35) and CEM at K = 2000, T = 50; CPU port = the oracle restatement on all host threads."""
+    import cartpolesimulation_b200 as cps
+    from cartpolesimulation_b200.optimizer_forward_b200 import optimizer_cem_b200, optimizer_random_action_b200
+    from oracle import oracle as O
+    a = np.pi - 1e-3
+    s = np.array([a, 0.0, np.cos(a), np.sin(a), 0.0, 0.0], dtype=np.float32)
+    lim = (np.array([-1.0], np.float32), np.array([1.0], np.float32))
+    out = {}
+    cases = (("cem_200x35_it3", optimizer_cem_b200, 200, 35, dict(cem_outer_it=3, cem_best_k=40)),
+             ("cem_2000x50_it3", optimizer_cem_b200, 2000, 50, dict(cem_outer_it=3, cem_best_k=200)),
+             ("random_action_640x35", optimizer_random_action_b200, 640, 35, {}))
+    for name, cls, K, T, kw in cases:
+        vp = cps.VariableParameters(target_position=0.0, target_equilibrium=1.0, L=0.395, m_pole=0.087)
+        cost, pred = cps.CostFunctionWrapper(), cps.PredictorWrapper()
+        opt = cls(predictor=pred, cost_function=cost, control_limits=lim, seed=1, mpc_horizon=T, num_rollouts=K,
+                  device=device, **kw)
+        pred.configure(batch_size=K, horizon=T, dt=0.02, variable_parameters=vp, predictor_specification="ODE")
+        cost.configure(batch_size=K, horizon=T, variable_parameters=vp, environment_name="CartPole",
+                       computation_library=None, cost_function_specification="quadratic_boundary_grad_minimal")
+        opt.configure(num_states=6, num_control_inputs=1, dt=0.02, predictor_specification="ODE")
+        for _ in range(20):
+            opt.step(s)
+        lat = []
+        for _ in range(n_calls):
+            t0 = time.perf_counter()
+            opt.step(s)
+            lat.append((time.perf_counter() - t0) * 1e3)
+        n0 = opt.engine.launch_count()
+        opt.step(s)
+        rec = {"latency_ms_median": float(np.median(lat)), "latency_ms_p99": float(np.percentile(lat, 99)),
+               "launches_per_solve": opt.engine.launch_count() - n0, "calls": n_calls,
+               "state_steps_per_solve": K * T * N_SUB * kw.get("cem_outer_it", 1)}
+        O.lib().cps_oracle_set_num_threads(os.cpu_count() or 1)
+        rng = np.random.default_rng(0)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            if cls is optimizer_cem_b200:
+                O.cem_step("ODE", "quadratic_boundary_grad_minimal", s, rng.standard_normal((3, K, T)).astype(np.float32),
+                           np.zeros(T, np.float32), np.full(T, 0.5, np.float32), kw["cem_best_k"], 0.01, 0.5)
+            else:
+                O.random_action_step("ODE", "quadratic_boundary_grad_minimal", s, rng.uniform(-1, 1, (K, T)).astype(np.float32))
+        rec["cpu_port_ms"] = (time.perf_counter() - t0) / 3 * 1e3
+        rec["cpu_port_threads"] = O.lib().cps_oracle_num_threads()
+        out[name] = rec
+        opt.engine.close()
+    out["api"] = "optimizer_cem_b200 / optimizer_random_action_b200 .step(numpy s) -> numpy u (cps_cem_step_host, cps_plan_random_action_host; plan_kernel)"
+    return out
+
+
+def relabel_bench(device, E=256, rows=50, K=2000, T=50):
+    """add_control_along_trajectories for E recorded files in lockstep (cps_fleet_relabel), MPPI
+    K = 2000, T = 50 per row, per-row pole length, in-kernel noise; host arrays in, labels out."""
+    import torch
+    from cartpolesimulation_b200.relabel import Relabeller
+    from oracle import oracle as O
+    rng = np.random.default_rng(0)
+    ang = rng.uniform(-np.pi, np.pi, (rows, E))
+    s = np.stack([ang, rng.uniform(-3, 3, (rows, E)), np.cos(ang), np.sin(ang), rng.uniform(-0.1, 0.1, (rows, E)),
+                  rng.uniform(-0.3, 0.3, (rows, E))], axis=2).astype(np.float32)
+    Lr = rng.uniform(0.25, 0.55, (rows, E)).astype(np.float32)
+    tp = rng.uniform(-0.1, 0.1, (rows, E)).astype(np.float32)
+    rl = Relabeller(E, K, T, noise="philox", seed=1, device=device)
+    rl.relabel(s[:5], tp[:5], None, Lr[:5])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    Q = rl.relabel(s, tp, None, Lr)
+    dt_s = time.perf_counter() - t0
+    out = {"files": E, "rows_per_file": rows, "K": K, "T": T, "ms_per_row_of_all_files": dt_s / rows * 1e3,
+           "labels_per_s": E * rows / dt_s, "state_steps_per_s": E * rows * K * T * N_SUB / dt_s,
+           "finite": bool(np.isfinite(Q).all()), "launches": rows,
+           "api": "Relabeller.relabel (numpy in, numpy out; cps_fleet_relabel, fleet_kernel in replay mode)"}
+    O.lib().cps_oracle_set_num_threads(os.cpu_count() or 1)
+    eps = rng.standard_normal((4, K, 6)).astype(np.float32)
+    t0 = time.perf_counter()
+    O.relabel_file("ODE", "quadratic_boundary_grad_minimal", T, s[:4, 0], eps, tp[:4, 0], None, Lr[:4, 0])
+    out["cpu_port_ms_per_label"] = (time.perf_counter() - t0) / 4 * 1e3
+    out["cpu_port_threads"] = O.lib().cps_oracle_num_threads()
+    rl.close()
     return out
 
 

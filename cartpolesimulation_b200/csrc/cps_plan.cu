@@ -41,7 +41,9 @@ struct PlanArgs {
     int best_k, last_iter;
     float sd_min, sd_init, mid;
     unsigned *ticket;
-    int *elite;                   // [K] scratch: indices of the elites, ascending
+    int *elite;                   // [K] scratch: indices of the elites, ascending (when they do not fit in shared memory)
+    int elite_smem;               // capacity of the shared-memory elite list
+    int defer_stats;              // CEM: stop after the elite list; cem_update_kernel computes the statistics
     float *mu_out, *sd_out;       // CEM: updated distribution [T]
     float *u_out;                 // [1]
     int *best_out;                // [1] or null: index of the cheapest plan
@@ -51,7 +53,8 @@ struct PlanArgs {
 struct PlanState {
     int best_k;
     float sd_init, sd_min;
-    float *d_J, *d_mu, *d_sd;
+    float *d_J, *d_mu, *d_sd;     // d_mu / d_sd: two buffers of T floats each; `cur` is the live one
+    int cur;
     int *d_elite, *d_best;
     unsigned *d_ticket;
     int configured_cem;
@@ -94,28 +97,37 @@ __device__ __forceinline__ int block_excl_scan(int v, int *s_w, int &total) {
 // s_mu2 / s_sd2: [T] scratch for the updated one.
 template <int MODE>
 __device__ __forceinline__ void plan_select(const PlanArgs &a, const float *s_mu, const float *s_sd, float *s_mu2,
-                                            float *s_sd2) {
+                                            float *s_sd2, int *s_elite) {
     __shared__ unsigned s_hist[256];
     __shared__ unsigned s_prefix, s_remaining;
     __shared__ int s_w[8];
     __shared__ unsigned long long s_bestw[8];
+    __shared__ unsigned s_maxw[8];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nt = blockDim.x, nwarps = nt >> 5;
     const int K = a.K, T = a.T;
 
-    // ---- cheapest plan, lowest index among equal costs (sorted_cost[0]) ---------------------------------------------------
+    // ---- cheapest plan, lowest index among equal costs (sorted_cost[0]); the largest key bounds the radix select ----------
     unsigned long long best = ~0ull;
+    unsigned kmax = 0u;
+#pragma unroll 8
     for (int i = tid; i < K; i += nt) {
-        const unsigned long long c = ((unsigned long long)order_key(__ldcg(a.J + i)) << 32) | (unsigned)i;
+        const unsigned key = order_key(__ldcg(a.J + i));
+        const unsigned long long c = ((unsigned long long)key << 32) | (unsigned)i;
         best = c < best ? c : best;
+        kmax = max(kmax, key);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         const unsigned long long n = __shfl_xor_sync(0xffffffffu, best, o);
         best = n < best ? n : best;
+        kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
     }
-    if (lane == 0) s_bestw[warp] = best;
+    if (lane == 0) { s_bestw[warp] = best; s_maxw[warp] = kmax; }
     __syncthreads();
-    for (int w = 0; w < nwarps; ++w) best = s_bestw[w] < best ? s_bestw[w] : best;
+    for (int w = 0; w < nwarps; ++w) {
+        best = s_bestw[w] < best ? s_bestw[w] : best;
+        kmax = max(kmax, s_maxw[w]);
+    }
     const int best_idx = (int)(best & 0xFFFFFFFFull);
     if (tid == 0 && a.best_out) *a.best_out = best_idx;
     if (a.select == SELECT_ARGMIN) {
@@ -123,62 +135,124 @@ __device__ __forceinline__ void plan_select(const PlanArgs &a, const float *s_mu
         return;
     }
 
-    // ---- CEM: the best_k-th smallest key by an 8-bit radix select ----------------------------------------------------------
+    // ---- CEM: the best_k-th smallest key by an 8-bit radix select over the bits in which the keys differ -------------------
+    // All keys lie in [kmin, kmax] and share the bits above the highest bit of kmin ^ kmax; starting below them spreads
+    // the first digit over the bins (the costs of one solve share sign, exponent and often leading mantissa bits, which
+    // would otherwise send every plan to one bin: tens of thousands of serialised same-address atomics).
     const int bk = min(a.best_k, K);
-    if (tid == 0) { s_prefix = 0u; s_remaining = (unsigned)bk; }
-    unsigned mask = 0u;
-    for (int shift = 24; shift >= 0; shift -= 8) {
+    const unsigned kmin = (unsigned)(best >> 32);
+    int hi = 32 - __clz((int)(kmin ^ kmax));   // number of low bits that vary (0: all costs equal)
+    if (tid == 0) { s_prefix = (hi >= 32) ? 0u : (kmin & ~((1u << hi) - 1u)); s_remaining = (unsigned)bk; }
+    __syncthreads();
+    while (hi > 0) {
+        const int w = min(8, hi), shift = hi - w;
+        const unsigned mask = (hi >= 32) ? 0u : ~((1u << hi) - 1u), digit = (1u << w) - 1u;
         for (int b = tid; b < 256; b += nt) s_hist[b] = 0u;
         __syncthreads();
         const unsigned prefix = s_prefix;
-        for (int i = tid; i < K; i += nt) {
-            const unsigned key = order_key(__ldcg(a.J + i));
-            if ((key & mask) == prefix) atomicAdd(&s_hist[(key >> shift) & 255u], 1u);
-        }
-        __syncthreads();
-        if (tid == 0) {
-            unsigned cum = 0u, rem = s_remaining;
-            for (int b = 0; b < 256; ++b) {
-                const unsigned c = s_hist[b];
-                if (cum + c >= rem) { s_prefix = prefix | ((unsigned)b << shift); s_remaining = rem - cum; break; }
-                cum += c;
+        for (int base = 0; base < K; base += nt * 8) {   // 8 independent loads in flight per thread, then the atomics
+            float v[8];
+            unsigned key[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = __ldcg(a.J + min(base + q * nt + tid, K - 1));   // unconditional: the loads batch
+#pragma unroll
+            for (int q = 0; q < 8; ++q) key[q] = order_key(v[q]);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const bool in = base + q * nt + tid < K && (key[q] & mask) == prefix;
+                const unsigned bin = (key[q] >> shift) & digit;
+                // the two most popular bins of the warp are added once each (a few outliers stretch [kmin, kmax] and put
+                // the bulk into one bin again); the rest add individually
+                unsigned todo = __ballot_sync(0xffffffffu, in);
+                for (int r = 0; r < 2 && todo; ++r) {
+                    const int leader = __ffs(todo) - 1;
+                    const unsigned b0 = __shfl_sync(0xffffffffu, bin, leader);
+                    const unsigned same = __ballot_sync(0xffffffffu, in && bin == b0) & todo;
+                    if (lane == leader) atomicAdd(&s_hist[b0], (unsigned)__popc(same));
+                    todo &= ~same;
+                }
+                if (todo & (1u << lane)) atomicAdd(&s_hist[bin], 1u);
             }
         }
-        mask |= 255u << shift;
+        __syncthreads();
+        if (warp == 0) {   // the bin that holds rank `rem`: each lane owns 8 consecutive bins, shuffle scan over the lanes
+            const unsigned rem = s_remaining;
+            unsigned c[8], mine = 0u;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { c[j] = s_hist[lane * 8 + j]; mine += c[j]; }
+            unsigned incl = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned n = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += n;
+            }
+            const unsigned before = incl - mine;
+            const unsigned hit = __ballot_sync(0xffffffffu, incl >= rem);   // non-empty: the total is >= rem
+            if (lane == __ffs(hit) - 1) {
+                unsigned cum = before;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (cum + c[j] >= rem) { s_prefix = prefix | ((unsigned)(lane * 8 + j) << shift); s_remaining = rem - cum; break; }
+                    cum += c[j];
+                }
+            }
+        }
+        hi = shift;
         __syncthreads();
     }
     const unsigned kth = s_prefix;
     const int ties_wanted = (int)s_remaining;  // how many plans with key == kth belong to the elites (lowest indices)
 
-    // ---- elite indices in ascending order (ordered compaction) ---------------------------------------------------------------
+    // ---- elite indices in ascending order (ordered compaction); the list lives in shared memory when it fits ----------------
+    int *elite = (bk <= a.elite_smem) ? s_elite : a.elite;
     int n_eq_before = 0, n_el_before = 0;
-    for (int base = 0; base < K; base += nt) {
-        const int i = base + tid;
-        unsigned key = 0xFFFFFFFFu;
-        bool in = i < K;
-        if (in) key = order_key(__ldcg(a.J + i));
-        const int eq = (in && key == kth) ? 1 : 0;
+    for (int base = 0; base < K; base += nt * 8) {   // each thread owns 8 consecutive plans of the chunk
+        const int i0 = base + tid * 8;
+        float v[8];
+        unsigned key[8];
+        int eq = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = __ldcg(a.J + min(i0 + j, K - 1));
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            key[j] = order_key(v[j]);
+            eq += (i0 + j < K && key[j] == kth) ? 1 : 0;
+        }
         int tot_eq, tot_el;
-        const int eq_rank = n_eq_before + block_excl_scan(eq, s_w, tot_eq);
-        const int el = (in && (key < kth || (eq && eq_rank < ties_wanted))) ? 1 : 0;
-        const int pos = n_el_before + block_excl_scan(el, s_w, tot_el);
-        if (el) a.elite[pos] = i;
+        int eq_rank = n_eq_before + block_excl_scan(eq, s_w, tot_eq);
+        unsigned take = 0u;
+        int el = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const bool in = i0 + j < K;
+            const bool is_eq = in && key[j] == kth;
+            if (in && (key[j] < kth || (is_eq && eq_rank < ties_wanted))) { take |= 1u << j; ++el; }
+            eq_rank += is_eq ? 1 : 0;
+        }
+        int pos = n_el_before + block_excl_scan(el, s_w, tot_el);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (take & (1u << j)) elite[pos++] = i0 + j;
         n_eq_before += tot_eq;
         n_el_before += tot_el;
     }
     __syncthreads();
+    if (a.defer_stats) {
+        if (a.last_iter && tid == 0) *a.u_out = cem_plan_value(s_mu[0], a.Q[(long long)best_idx * a.qs_k], s_sd[0], a.lo, a.hi);
+        return;
+    }
 
     // ---- per horizon step: mean and population standard deviation over the elites (cem_tf.py:79-81) ------------------------
     for (int t = warp; t < T; t += nwarps) {
         float sum = 0.0f;
         for (int e = lane; e < bk; e += 32) {
-            const int k = a.elite[e];
+            const int k = elite[e];
             sum += cem_plan_value(s_mu[t], a.Q[(long long)k * a.qs_k + (long long)t * a.qs_t], s_sd[t], a.lo, a.hi);
         }
         const float mean = __fdiv_rn(warp_sum(sum), (float)bk);
         float ss = 0.0f;
         for (int e = lane; e < bk; e += 32) {
-            const int k = a.elite[e];
+            const int k = elite[e];
             const float d = cem_plan_value(s_mu[t], a.Q[(long long)k * a.qs_k + (long long)t * a.qs_t], s_sd[t], a.lo, a.hi) - mean;
             ss = fmaf(d, d, ss);
         }
@@ -204,9 +278,55 @@ __device__ __forceinline__ void plan_select(const PlanArgs &a, const float *s_mu
     if (tid == 0) *a.u_out = cem_plan_value(s_mu[0], a.Q[(long long)best_idx * a.qs_k], s_sd[0], a.lo, a.hi);
 }
 
+// CEM statistics for large elite sets: one block per horizon step (plan_select leaves the elite list in a.elite).  Reads
+// the distribution the plans were sampled from (a.mu, a.sd) and writes the updated one to the OTHER buffer
+// (a.mu_out, a.sd_out), so blocks do not race on the shifted write of the last iteration.
+__global__ void __launch_bounds__(256) cem_update_kernel(const __grid_constant__ PlanArgs a) {
+    __shared__ float s_part[8];
+    __shared__ float s_bc;
+    const int t = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int bk = min(a.best_k, a.K), T = a.T;
+    const float mu = a.mu[t], sd = a.sd[t];
+    const float *q = a.Q + (long long)t * a.qs_t;
+    float sum = 0.0f;
+#pragma unroll 4
+    for (int e = tid; e < bk; e += 256) sum += cem_plan_value(mu, q[(long long)a.elite[e] * a.qs_k], sd, a.lo, a.hi);
+    sum = warp_sum(sum);
+    if (lane == 0) s_part[warp] = sum;
+    __syncthreads();
+    if (tid == 0) {
+        float v = 0.0f;
+        for (int w = 0; w < 8; ++w) v += s_part[w];
+        s_bc = __fdiv_rn(v, (float)bk);
+    }
+    __syncthreads();
+    const float mean = s_bc;
+    float ss = 0.0f;
+#pragma unroll 4
+    for (int e = tid; e < bk; e += 256) {
+        const float d = cem_plan_value(mu, q[(long long)a.elite[e] * a.qs_k], sd, a.lo, a.hi) - mean;
+        ss = fmaf(d, d, ss);
+    }
+    ss = warp_sum(ss);
+    __syncthreads();
+    if (lane == 0) s_part[warp] = ss;
+    __syncthreads();
+    if (tid != 0) return;
+    float v = 0.0f;
+    for (int w = 0; w < 8; ++w) v += s_part[w];
+    const float stdev = sqrtf(__fdiv_rn(v, (float)bk));
+    if (!a.last_iter) {
+        a.mu_out[t] = mean;
+        a.sd_out[t] = stdev;
+    } else {   // clip, shift by one step, refill the tail (cem_tf.py:96-99)
+        if (t > 0) { a.mu_out[t - 1] = mean; a.sd_out[t - 1] = clampf(stdev, a.sd_min, 1.0e8f); }
+        if (t == T - 1) { a.mu_out[t] = a.mid; a.sd_out[t] = a.sd_init; }
+    }
+}
+
 template <int INTEG, int COST, int MODE>
 __global__ void __launch_bounds__(256, 4) plan_kernel(const __grid_constant__ PlanArgs a) {
-    extern __shared__ float smem[];   // PLAN_CEM: mu[T], sd[T], mu2[T], sd2[T]
+    extern __shared__ float smem[];   // PLAN_CEM: mu[T], sd[T], mu2[T], sd2[T], elite list [elite_smem]
     __shared__ unsigned s_ticket;
     const int tid = threadIdx.x, T = a.T;
     float *s_mu = smem, *s_sd = smem + T;
@@ -259,7 +379,7 @@ __global__ void __launch_bounds__(256, 4) plan_kernel(const __grid_constant__ Pl
     __syncthreads();
     if (s_ticket != gridDim.x - 1u) return;
     __threadfence();
-    plan_select<MODE>(a, s_mu, s_sd, smem + 2 * T, smem + 3 * T);
+    plan_select<MODE>(a, s_mu, s_sd, smem + 2 * T, smem + 3 * T, reinterpret_cast<int *>(smem + 4 * T));
     if (tid == 0) *a.ticket = 0u;  // re-arm
 }
 
@@ -296,14 +416,14 @@ static int plan_state(cps_handle *h, PlanState **out) {
     h->plan = P;
     const size_t K = h->cfg.num_rollouts, T = h->cfg.horizon;
     CUDA_TRY(h, cudaMalloc(&P->d_J, sizeof(float) * K));
-    CUDA_TRY(h, cudaMalloc(&P->d_mu, sizeof(float) * T));
-    CUDA_TRY(h, cudaMalloc(&P->d_sd, sizeof(float) * T));
+    CUDA_TRY(h, cudaMalloc(&P->d_mu, sizeof(float) * 2 * T));
+    CUDA_TRY(h, cudaMalloc(&P->d_sd, sizeof(float) * 2 * T));
     CUDA_TRY(h, cudaMalloc(&P->d_elite, sizeof(int) * K));
     CUDA_TRY(h, cudaMalloc(&P->d_best, sizeof(int)));
     CUDA_TRY(h, cudaMalloc(&P->d_ticket, sizeof(unsigned)));
     CUDA_TRY(h, cudaMemset(P->d_ticket, 0, sizeof(unsigned)));
-    CUDA_TRY(h, cudaMemset(P->d_mu, 0, sizeof(float) * T));
-    CUDA_TRY(h, cudaMemset(P->d_sd, 0, sizeof(float) * T));
+    CUDA_TRY(h, cudaMemset(P->d_mu, 0, sizeof(float) * 2 * T));
+    CUDA_TRY(h, cudaMemset(P->d_sd, 0, sizeof(float) * 2 * T));
     *out = P;
     return CPS_OK;
 }
@@ -329,8 +449,12 @@ static void plan_common(cps_handle *h, PlanArgs &a, const float *s_dev, float u_
     a.nonfinite = h->d_nonfinite;
 }
 
-static void plan_geometry(int K, int &grid, int &block) {
-    block = (K <= 148 * 32 * 4) ? 32 : (K <= 148 * 64 * 8 ? 64 : 128);
+// Without a selection step small K is latency bound: one warp per block spreads the warps over the SMs.  With one, the
+// block that finishes last works alone on the K costs, so blocks are 256 wide (rollout latency is the same: the
+// 10 x T substep dependence chain of one warp; 8 warps share an SM without slowing each other).
+static void plan_geometry(int K, bool select, int &grid, int &block) {
+    if (select) block = 256;
+    else block = (K <= 148 * 32 * 4) ? 32 : (K <= 148 * 64 * 8 ? 64 : 128);
     grid = (K + block - 1) / block;
 }
 
@@ -352,7 +476,7 @@ extern "C" int cps_plan_cost(cps_handle *h, const float *s_dev, const float *Q_d
     else { a.ts_k = (T + 1) * 6LL; a.ts_t = 6; a.ts_c = 1; }
     a.select = SELECT_NONE;
     int grid, block;
-    plan_geometry(K, grid, block);
+    plan_geometry(K, false, grid, block);
     plan_fn fn = pick_plan(h->cfg.integrator, h->cfg.cost_id, PLAN_Q);
     fn<<<grid, block, 0, h->stream>>>(a);
     h->launches += 1;
@@ -380,7 +504,7 @@ extern "C" int cps_plan_random_action(cps_handle *h, const float *s_dev, const f
     a.u_out = u_out_dev;
     a.best_out = best_out_dev ? best_out_dev : P->d_best;
     int grid, block;
-    plan_geometry(K, grid, block);
+    plan_geometry(K, true, grid, block);
     plan_fn fn = pick_plan(h->cfg.integrator, h->cfg.cost_id, PLAN_Q);
     fn<<<grid, block, 0, h->stream>>>(a);
     h->launches += 1;
@@ -414,8 +538,8 @@ extern "C" int cps_cem_reset(cps_handle *h) {
     if (!tmp) return fail(h, CPS_ERR_INVALID, "cps_cem_reset: out of host memory");
     const float mid = (h->mppi_in[5] + h->mppi_in[6]) * 0.5f;  // optimizer_reset (cem_tf.py:112-116)
     for (int t = 0; t < T; ++t) { tmp[t] = mid; tmp[T + t] = P->sd_init; }
-    cudaError_t e = cudaMemcpyAsync(P->d_mu, tmp, sizeof(float) * T, cudaMemcpyHostToDevice, h->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(P->d_sd, tmp + T, sizeof(float) * T, cudaMemcpyHostToDevice, h->stream);
+    cudaError_t e = cudaMemcpyAsync(P->d_mu + (size_t)P->cur * T, tmp, sizeof(float) * T, cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(P->d_sd + (size_t)P->cur * T, tmp + T, sizeof(float) * T, cudaMemcpyHostToDevice, h->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
     delete[] tmp;
     CUDA_TRY(h, e);
@@ -429,7 +553,7 @@ extern "C" int cps_cem_configure(cps_handle *h, int best_k, float initial_stdev,
     if (best_k < 1 || best_k > h->cfg.num_rollouts)
         return fail(h, CPS_ERR_INVALID, "cps_cem_configure: cem_best_k must lie in [1, num_rollouts]");
     if (!(initial_stdev >= 0.0f) || !(stdev_min >= 0.0f)) return fail(h, CPS_ERR_INVALID, "cps_cem_configure: negative stdev");
-    if (sizeof(float) * 4 * (size_t)h->cfg.horizon > 200 * 1024)
+    if (sizeof(float) * 4 * (size_t)h->cfg.horizon + sizeof(int) * 2048 > 200 * 1024)
         return fail(h, CPS_ERR_UNSUPPORTED, "cps_cem_configure: horizon too large for shared memory");
     CUDA_TRY(h, cudaSetDevice(h->cfg.device));
     PlanState *P;
@@ -451,7 +575,6 @@ extern "C" int cps_cem_step(cps_handle *h, const float *s_dev, const float *eps_
     PlanArgs a;
     plan_common(h, a, s_dev, u_prev, K, T);
     if (eps_layout == CPS_TIME_MAJOR) { a.qs_k = 1; a.qs_t = K; } else { a.qs_k = T; a.qs_t = 1; }
-    a.mu = P->d_mu; a.sd = P->d_sd; a.mu_out = P->d_mu; a.sd_out = P->d_sd;
     a.J = J_out_dev ? J_out_dev : P->d_J;
     a.select = SELECT_CEM;
     a.best_k = P->best_k; a.sd_min = P->sd_min; a.sd_init = P->sd_init;
@@ -459,16 +582,28 @@ extern "C" int cps_cem_step(cps_handle *h, const float *s_dev, const float *eps_
     a.ticket = P->d_ticket; a.elite = P->d_elite;
     a.u_out = u_out_dev; a.best_out = P->d_best;
     int grid, block;
-    plan_geometry(K, grid, block);
-    const size_t smem = sizeof(float) * 4 * (size_t)T;
+    plan_geometry(K, true, grid, block);
+    a.elite_smem = 0;   // set below once defer_stats is known
+    const size_t smem = sizeof(float) * 4 * (size_t)T + sizeof(int) * (size_t)(((long long)P->best_k * T > 2048) ? 0 : P->best_k);
     plan_fn fn = pick_plan(h->cfg.integrator, h->cfg.cost_id, PLAN_CEM);
     if (smem > 48 * 1024) CUDA_TRY(h, cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // small elite sets: the selecting block also computes the T x best_k statistics; large ones: a second launch with
+    // one block per horizon step
+    a.defer_stats = ((long long)P->best_k * T > 2048) ? 1 : 0;
+    a.elite_smem = a.defer_stats ? 0 : P->best_k;   // the update kernel reads the list from global memory
     for (int it = 0; it < n_iterations; ++it) {
         a.Q = eps_dev + (size_t)it * K * T;
         a.last_iter = (it == n_iterations - 1) ? 1 : 0;
         a.Q_out = a.last_iter ? Q_out_dev : nullptr;   // Q_logged is the last iteration's plans (cem_tf.py:93)
+        a.mu = P->d_mu + (size_t)P->cur * T; a.sd = P->d_sd + (size_t)P->cur * T;
+        a.mu_out = P->d_mu + (size_t)(1 - P->cur) * T; a.sd_out = P->d_sd + (size_t)(1 - P->cur) * T;
         fn<<<grid, block, smem, h->stream>>>(a);
         h->launches += 1;
+        if (a.defer_stats) {
+            cem_update_kernel<<<T, 256, 0, h->stream>>>(a);
+            h->launches += 1;
+        }
+        P->cur = 1 - P->cur;
     }
     CUDA_TRY(h, cudaGetLastError());
     return CPS_OK;
@@ -495,8 +630,8 @@ extern "C" int cps_cem_get_distribution(cps_handle *h, float *mu_host, float *st
     if (!P || !P->configured_cem) return fail(h, CPS_ERR_NOT_CONFIGURED, "cps_cem_get_distribution: cps_cem_configure first");
     CUDA_TRY(h, cudaSetDevice(h->cfg.device));
     const size_t T = h->cfg.horizon;
-    if (mu_host) CUDA_TRY(h, cudaMemcpyAsync(mu_host, P->d_mu, sizeof(float) * T, cudaMemcpyDeviceToHost, h->stream));
-    if (stdev_host) CUDA_TRY(h, cudaMemcpyAsync(stdev_host, P->d_sd, sizeof(float) * T, cudaMemcpyDeviceToHost, h->stream));
+    if (mu_host) CUDA_TRY(h, cudaMemcpyAsync(mu_host, P->d_mu + P->cur * T, sizeof(float) * T, cudaMemcpyDeviceToHost, h->stream));
+    if (stdev_host) CUDA_TRY(h, cudaMemcpyAsync(stdev_host, P->d_sd + P->cur * T, sizeof(float) * T, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     return CPS_OK;
 }
@@ -507,8 +642,8 @@ extern "C" int cps_cem_set_distribution(cps_handle *h, const float *mu_host, con
     if (!P || !P->configured_cem) return fail(h, CPS_ERR_NOT_CONFIGURED, "cps_cem_set_distribution: cps_cem_configure first");
     CUDA_TRY(h, cudaSetDevice(h->cfg.device));
     const size_t T = h->cfg.horizon;
-    if (mu_host) CUDA_TRY(h, cudaMemcpyAsync(P->d_mu, mu_host, sizeof(float) * T, cudaMemcpyHostToDevice, h->stream));
-    if (stdev_host) CUDA_TRY(h, cudaMemcpyAsync(P->d_sd, stdev_host, sizeof(float) * T, cudaMemcpyHostToDevice, h->stream));
+    if (mu_host) CUDA_TRY(h, cudaMemcpyAsync(P->d_mu + P->cur * T, mu_host, sizeof(float) * T, cudaMemcpyHostToDevice, h->stream));
+    if (stdev_host) CUDA_TRY(h, cudaMemcpyAsync(P->d_sd + P->cur * T, stdev_host, sizeof(float) * T, cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     return CPS_OK;
 }

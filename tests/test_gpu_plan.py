@@ -293,3 +293,21 @@ def test_optimizer_random_action_b200():
     own, _ = _make(optimizer_random_action_b200, m)
     us = [float(own.step(z["s"][0])) for _ in range(3)]
     assert all(-1.0 <= v <= 1.0 for v in us) and len(set(us)) > 1
+
+
+@pytest.mark.parametrize("K", [200, 5000])
+def test_cem_all_costs_equal(K):
+    """Identical plans -> identical costs: the radix select has no varying bit, the elites are the first best_k plans,
+    the elite spread is zero and the stdev floor applies."""
+    from cartpolesimulation_b200 import _lib as L
+    T, best_k = 25, 33
+    eng = _engine(K, T, "ODE", "quadratic_boundary_grad_minimal")
+    eng.cem_configure(best_k, 0.5, 0.02)
+    J = torch.empty(K, device="cuda")
+    best = None
+    u = eng.cem_step(torch.from_numpy(_hanging()).cuda(), torch.zeros((2, K, T), device="cuda"), L.ROLLOUT_MAJOR, 0.0, J_out=J)
+    Jh = J.cpu().numpy()
+    assert (Jh == Jh[0]).all() and float(u.cpu()[0]) == 0.0
+    mu, sd = eng.cem_get_distribution()
+    assert (mu == 0.0).all()
+    np.testing.assert_array_equal(sd, np.r_[np.full(T - 1, 0.02, np.float32), np.float32(0.5)])
