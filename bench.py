@@ -515,6 +515,10 @@ def run_ours(args):
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_cpus, all_cpus = None, os.sched_getaffinity(0)
+    if world > 1:   # one process per GPU: keep the pinned host buffers of the e2e leg on the GPU's own NUMA node
+        from cartpolesimulation_b200.distributed import bind_to_gpu_numa
+        numa_cpus = bind_to_gpu_numa(local_rank)
     if world > 1:
         # stdout carries exactly ONE JSON line: NCCL's banner ("NCCL version ...") goes to stderr
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
@@ -581,6 +585,8 @@ def run_ours(args):
         t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
+    if numa_cpus:
+        os.sched_setaffinity(0, all_cpus)   # the CPU baseline below uses every host core again
     sampler.stop_flag = True   # the clock record covers both timed regions (device-resident and e2e)
     sampler.join(timeout=1.0)
     e2e_value = steps_per_pass * e2e_steps * world / e2e_s
@@ -658,7 +664,8 @@ def run_ours(args):
                        if (args.fast_sincos or args.substep_sincos) else
                        "rotation substeps + sincosf resync per control step (default)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": 1e3 * e2e_s / e2e_steps, "api": "cps_rollout_host (pinned host buffers)"},
+                    "ms_per_step": 1e3 * e2e_s / e2e_steps, "api": "cps_rollout_host (pinned host buffers)",
+                    "numa_bound_cpus": len(numa_cpus) if numa_cpus else None},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
             "clocks": sampler.summary(), "mppi_solve": mppi, "mppi_sharded": sharded, "fleet_sharded": fleet}
     print(json.dumps(line))

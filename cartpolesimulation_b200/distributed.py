@@ -18,6 +18,29 @@ import torch
 import torch.distributed as dist
 
 
+def bind_to_gpu_numa(device_index: int) -> list | None:
+    """Pin the calling process to the CPUs NVML reports as local to the GPU (its NUMA node), so that pinned host
+    buffers allocated afterwards land in memory next to the GPU's PCIe root.  One process per GPU on a two-socket box
+    otherwise sends half of the host<->device traffic across the socket interconnect.  Returns the CPU list, or None if
+    NVML / the cpuset does not allow it (nothing is changed then)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+        h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode() if not uuid.startswith("GPU-") else uuid.encode())
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = [64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if not cpus or len(cpus) == len(allowed):
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return None
+
+
 def shard_bounds(n: int, world: int, rank: int) -> tuple[int, int]:
     """Contiguous partition of n items over `world` ranks; the first n % world ranks get one more."""
     if world < 1 or not (0 <= rank < world):
