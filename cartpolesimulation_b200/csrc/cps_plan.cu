@@ -71,6 +71,16 @@ __device__ __forceinline__ float cem_plan_value(float mu, float eps, float sd, f
     return clampf(__fadd_rn(mu, __fmul_rn(eps, sd)), lo, hi);  // tile(mu) + multiply(normal, stdev), then clip (:66-68)
 }
 
+// Costs 4g .. 4g+3 of the selecting block's pass over J: one 16-byte L2 load when the buffer is 16-byte aligned and K a
+// multiple of 4 (vec), else four clamped 4-byte loads.  g must be a valid group (4g < K).
+__device__ __forceinline__ float4 load_costs4(const float *J, int g, int K, bool vec) {
+    if (vec) return __ldcg(reinterpret_cast<const float4 *>(J) + g);
+    float4 v;
+    v.x = __ldcg(J + min(4 * g, K - 1)); v.y = __ldcg(J + min(4 * g + 1, K - 1));
+    v.z = __ldcg(J + min(4 * g + 2, K - 1)); v.w = __ldcg(J + min(4 * g + 3, K - 1));
+    return v;
+}
+
 // Exclusive prefix of v over the block (thread order) and the block total.  s_w: [nwarps] shared scratch.
 __device__ __forceinline__ int block_excl_scan(int v, int *s_w, int &total) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -107,14 +117,24 @@ __device__ __forceinline__ void plan_select(const PlanArgs &a, const float *s_mu
     const int K = a.K, T = a.T;
 
     // ---- cheapest plan, lowest index among equal costs (sorted_cost[0]); the largest key bounds the radix select ----------
+    const bool vec = ((reinterpret_cast<unsigned long long>(a.J) & 15ull) == 0ull) && (K % 4 == 0);
+    const int G = (K + 3) / 4;   // groups of four consecutive costs
     unsigned long long best = ~0ull;
     unsigned kmax = 0u;
-#pragma unroll 8
-    for (int i = tid; i < K; i += nt) {
-        const unsigned key = order_key(__ldcg(a.J + i));
-        const unsigned long long c = ((unsigned long long)key << 32) | (unsigned)i;
-        best = c < best ? c : best;
-        kmax = max(kmax, key);
+#pragma unroll 4
+    for (int g = tid; g < G; g += nt) {
+        const float4 v = load_costs4(a.J, g, K, vec);
+        const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int i = 4 * g + e;
+            if (i < K) {
+                const unsigned key = order_key(vv[e]);
+                const unsigned long long c = ((unsigned long long)key << 32) | (unsigned)i;
+                best = c < best ? c : best;
+                kmax = max(kmax, key);
+            }
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -150,28 +170,29 @@ __device__ __forceinline__ void plan_select(const PlanArgs &a, const float *s_mu
         for (int b = tid; b < 256; b += nt) s_hist[b] = 0u;
         __syncthreads();
         const unsigned prefix = s_prefix;
-        for (int base = 0; base < K; base += nt * 8) {   // 8 independent loads in flight per thread, then the atomics
-            float v[8];
-            unsigned key[8];
+        for (int base = 0; base < G; base += nt * 8) {   // 8 independent 16-byte loads in flight per thread, then the atomics
+            float4 v[8];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) v[q] = __ldcg(a.J + min(base + q * nt + tid, K - 1));   // unconditional: the loads batch
-#pragma unroll
-            for (int q = 0; q < 8; ++q) key[q] = order_key(v[q]);
+            for (int q = 0; q < 8; ++q) v[q] = load_costs4(a.J, min(base + q * nt + tid, G - 1), K, vec);   // unconditional: the loads batch
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-                const bool in = base + q * nt + tid < K && (key[q] & mask) == prefix;
-                const unsigned bin = (key[q] >> shift) & digit;
-                // the two most popular bins of the warp are added once each (a few outliers stretch [kmin, kmax] and put
-                // the bulk into one bin again); the rest add individually
-                unsigned todo = __ballot_sync(0xffffffffu, in);
-                for (int r = 0; r < 2 && todo; ++r) {
-                    const int leader = __ffs(todo) - 1;
-                    const unsigned b0 = __shfl_sync(0xffffffffu, bin, leader);
-                    const unsigned same = __ballot_sync(0xffffffffu, in && bin == b0) & todo;
-                    if (lane == leader) atomicAdd(&s_hist[b0], (unsigned)__popc(same));
-                    todo &= ~same;
+                const int g = base + q * nt + tid;
+                const float vv[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const unsigned key = order_key(vv[e]);
+                    const bool in = g < G && 4 * g + e < K && (key & mask) == prefix;
+                    const unsigned bin = (key >> shift) & digit;
+                    // a few outliers stretch [kmin, kmax] and put the bulk into one bin again: when the whole warp agrees
+                    // (one MATCH.ALL), lane 0 adds 32; otherwise every lane adds for itself
+                    int uniform;
+                    __match_all_sync(0xffffffffu, in ? bin : 0xFFFFFFFFu, &uniform);
+                    if (uniform) {
+                        if (lane == 0 && in) atomicAdd(&s_hist[bin], 32u);
+                    } else if (in) {
+                        atomicAdd(&s_hist[bin], 1u);
+                    }
                 }
-                if (todo & (1u << lane)) atomicAdd(&s_hist[bin], 1u);
             }
         }
         __syncthreads();
@@ -208,11 +229,10 @@ __device__ __forceinline__ void plan_select(const PlanArgs &a, const float *s_mu
     int n_eq_before = 0, n_el_before = 0;
     for (int base = 0; base < K; base += nt * 8) {   // each thread owns 8 consecutive plans of the chunk
         const int i0 = base + tid * 8;
-        float v[8];
         unsigned key[8];
         int eq = 0;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = __ldcg(a.J + min(i0 + j, K - 1));
+        const float4 va = load_costs4(a.J, min(i0 / 4, G - 1), K, vec), vb = load_costs4(a.J, min(i0 / 4 + 1, G - 1), K, vec);
+        const float v[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             key[j] = order_key(v[j]);
