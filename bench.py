@@ -32,6 +32,9 @@ if REPO not in sys.path:
     sys.path.insert(0, REPO)
 
 FLOP_PER_STATE_STEP = 32.0   # 24 (ODE rhs) + 8 (integrator), FMA = 2
+# FMA-pipe lane operations the pair kernel executes per state-step (ncu instruction mix): 30 packed in the
+# substep loop + ~2.6 scalar per-control-step work (sincosf resync, compensated angle) + ~1.5 IMAD.MOV
+FP32_LANE_OPS_PER_STATE_STEP = 34.5
 MUFU_PER_STATE_STEP = 3.0    # rcp + sin + cos when the MUFU path is used; 1 (rcp) otherwise
 B_DEFAULT, T_DEFAULT, N_SUB, DT = 1 << 20, 50, 10, 0.02
 METRIC = "rollout_state_steps_per_sec"
@@ -625,15 +628,24 @@ def run_ours(args):
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     alg_bytes = 4.0 * B * T + 24.0 * B * (T + 1) + 24.0 * B   # Q in, trajectory out, s0 in
-    traffic = None
+    traffic, ncu_view = None, None
     try:
-        traffic = json.load(open(os.path.join(REPO, "profiles", "roofline_traffic.json"))).get("rollout_kernel_dram_bytes_per_launch")
+        rt = json.load(open(os.path.join(REPO, "profiles", "roofline_traffic.json")))
+        traffic = rt.get("rollout_kernel_dram_bytes_per_launch")
+        ncu_view = rt.get("ncu")   # pipe utilisation of the same kernel from the committed ncu capture (not measured live)
     except Exception:
         pass
     roofline = {"bound": "fp32", "kernel": "rollout_kernel<ODE_v0>", "achieved": achieved_tflops, "peak": fp32_peak,
                 "unit": "TFLOP/s", "frac": achieved_tflops / fp32_peak if fp32_peak else None, "traffic": traffic,
                 "peak_source": "cps_measure_peaks FFMA microbenchmark, this run (not in MEASURED_PEAKS.json)",
                 "flop_per_state_step": FLOP_PER_STATE_STEP, "kernel_ms": kern_ms,
+                "fp32_pipe": {"lane_ops_per_state_step": FP32_LANE_OPS_PER_STATE_STEP,
+                              "achieved_frac_of_lanes": rate_1gpu * FP32_LANE_OPS_PER_STATE_STEP / (fp32_peak * 1e12 / 2.0)
+                              if fp32_peak else None,
+                              "note": "FMA-pipe lane operations executed per state-step (FMUL/FADD occupy a lane like an FMA): "
+                                      "30 in the substep loop + ~4.5 amortised per-control-step work; peak = measured FFMA "
+                                      "lane rate (roofline.peak / 2)"},
+                "ncu": ncu_view,
                 "mufu": {"achieved_gops": rate_1gpu * (MUFU_PER_STATE_STEP if args.fast_sincos else 1.0) / 1e9,
                          "peak_gops": mufu_peak},
                 "hbm": {"achieved_gbs": alg_bytes / (kern_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,

@@ -12,6 +12,8 @@ KEEP = [
     "smsp__warps_eligible.avg.per_cycle_active", "smsp__inst_executed.sum",
     "smsp__thread_inst_executed_per_inst_executed.ratio", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
     "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+    "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed",
     "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
     "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
     "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
@@ -19,7 +21,7 @@ KEEP = [
     "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
     "sm__inst_executed_pipe_uniform.avg.pct_of_peak_sustained_active",
     "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
-    "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct", "sm__cycles_elapsed.avg",
+    "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct", "sm__cycles_elapsed.avg", "sm__cycles_active.avg", "sm__cycles_active.max",
     "smsp__cycles_active.avg", "sm__sass_thread_inst_executed_op_ffma_pred_on.sum",
     "sm__sass_thread_inst_executed_op_fmul_pred_on.sum", "sm__sass_thread_inst_executed_op_fadd_pred_on.sum",
     "smsp__sass_thread_inst_executed_op_fp32_pred_on.sum",
