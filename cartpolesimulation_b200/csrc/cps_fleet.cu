@@ -391,15 +391,15 @@ extern "C" long long cps_fleet_period(const cps_handle *h) { return (h && h->fle
 int cps_fold_cost_for(cps_handle *h, float target_equilibrium, CostParams *out);
 
 // Shared by cps_fleet_step (closed loop: replay_dev == nullptr) and cps_fleet_relabel (states from a recording).
-static int fleet_launch(cps_handle *h, int n_periods, const float *tp_dev, const float *te_dev, const float *noise_dev,
-                        float *record_dev, float *J_out_dev, const float *replay_dev, const float *L_dev,
-                        const float *mp_dev, float *Q_out_dev) {
+static int fleet_launch(cps_handle *h, const char *who, int n_periods, const float *tp_dev, const float *te_dev,
+                        const float *noise_dev, float *record_dev, float *J_out_dev, const float *replay_dev,
+                        const float *L_dev, const float *mp_dev, float *Q_out_dev) {
     FleetState *F = h->fleet;
-    if (!F) return fail(h, CPS_ERR_NOT_CONFIGURED, "cps_fleet_step: no fleet (cps_fleet_create)");
-    if (n_periods < 0) return fail(h, CPS_ERR_INVALID, "cps_fleet_step: n_periods < 0");
+    if (!F) return fail(h, CPS_ERR_NOT_CONFIGURED, "%s: no fleet (cps_fleet_create)", who);
+    if (n_periods < 0) return fail(h, CPS_ERR_INVALID, "%s: negative number of periods / rows", who);
     const bool philox = F->cfg.noise_source == CPS_FLEET_NOISE_PHILOX;
-    if (!philox && !noise_dev) return fail(h, CPS_ERR_INVALID, "cps_fleet_step: this fleet expects supplied noise");
-    if (philox && noise_dev) return fail(h, CPS_ERR_INVALID, "cps_fleet_step: this fleet generates its noise (Philox); pass NULL");
+    if (!philox && !noise_dev) return fail(h, CPS_ERR_INVALID, "%s: this fleet expects supplied noise", who);
+    if (philox && noise_dev) return fail(h, CPS_ERR_INVALID, "%s: this fleet generates its noise (Philox); pass NULL", who);
     CUDA_TRY(h, cudaSetDevice(h->cfg.device));
     FleetArgs a;
     a.ode = h->ode; a.mp = h->mp;
@@ -419,7 +419,7 @@ static int fleet_launch(cps_handle *h, int n_periods, const float *tp_dev, const
     a.m_pole_fixed = h->phys[CPS_PH_M_POLE];
     a.L_default = h->L_var; a.mp_default = h->m_pole_var;
     fleet_fn fn = pick_fleet(h->cfg.integrator, h->cfg.cost_id, philox);
-    if (!fn) return fail(h, CPS_ERR_NOT_CONFIGURED, "cps_fleet_step: no kernel for this configuration");
+    if (!fn) return fail(h, CPS_ERR_NOT_CONFIGURED, "%s: no kernel for this configuration", who);
     if (F->smem > 48 * 1024) CUDA_TRY(h, cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F->smem));
     const size_t E = F->E, K = h->cfg.num_rollouts;
     const double dt_control = F->cfg.dt_simulation * F->cfg.sim_substeps;
@@ -447,7 +447,7 @@ static int fleet_launch(cps_handle *h, int n_periods, const float *tp_dev, const
 extern "C" int cps_fleet_step(cps_handle *h, int n_periods, const float *tp_dev, const float *te_dev, const float *noise_dev,
                               float *record_dev, float *J_out_dev) {
     if (!h) return CPS_ERR_INVALID;
-    return fleet_launch(h, n_periods, tp_dev, te_dev, noise_dev, record_dev, J_out_dev, nullptr, nullptr, nullptr, nullptr);
+    return fleet_launch(h, "cps_fleet_step", n_periods, tp_dev, te_dev, noise_dev, record_dev, J_out_dev, nullptr, nullptr, nullptr, nullptr);
 }
 
 extern "C" int cps_fleet_relabel(cps_handle *h, int n_rows, const float *states_dev, const float *tp_dev, const float *te_dev,
@@ -455,7 +455,7 @@ extern "C" int cps_fleet_relabel(cps_handle *h, int n_rows, const float *states_
                                  float *J_out_dev) {
     if (!h) return CPS_ERR_INVALID;
     if (!states_dev || !Q_out_dev) return fail(h, CPS_ERR_INVALID, "cps_fleet_relabel: null pointer");
-    return fleet_launch(h, n_rows, tp_dev, te_dev, noise_dev, nullptr, J_out_dev, states_dev, L_dev, m_pole_dev, Q_out_dev);
+    return fleet_launch(h, "cps_fleet_relabel", n_rows, tp_dev, te_dev, noise_dev, nullptr, J_out_dev, states_dev, L_dev, m_pole_dev, Q_out_dev);
 }
 
 extern "C" int cps_fleet_noise(cps_handle *h, long long period, float *out_dev) {

@@ -433,17 +433,22 @@ static int plan_state(cps_handle *h, PlanState **out) {
     PlanState *P = new (std::nothrow) PlanState();
     if (!P) return fail(h, CPS_ERR_INVALID, "cps_plan: out of host memory");
     memset(P, 0, sizeof(*P));
-    h->plan = P;
     const size_t K = h->cfg.num_rollouts, T = h->cfg.horizon;
-    CUDA_TRY(h, cudaMalloc(&P->d_J, sizeof(float) * K));
-    CUDA_TRY(h, cudaMalloc(&P->d_mu, sizeof(float) * 2 * T));
-    CUDA_TRY(h, cudaMalloc(&P->d_sd, sizeof(float) * 2 * T));
-    CUDA_TRY(h, cudaMalloc(&P->d_elite, sizeof(int) * K));
-    CUDA_TRY(h, cudaMalloc(&P->d_best, sizeof(int)));
-    CUDA_TRY(h, cudaMalloc(&P->d_ticket, sizeof(unsigned)));
-    CUDA_TRY(h, cudaMemset(P->d_ticket, 0, sizeof(unsigned)));
-    CUDA_TRY(h, cudaMemset(P->d_mu, 0, sizeof(float) * 2 * T));
-    CUDA_TRY(h, cudaMemset(P->d_sd, 0, sizeof(float) * 2 * T));
+    cudaError_t e = cudaMalloc(&P->d_J, sizeof(float) * K);
+    if (e == cudaSuccess) e = cudaMalloc(&P->d_mu, sizeof(float) * 2 * T);
+    if (e == cudaSuccess) e = cudaMalloc(&P->d_sd, sizeof(float) * 2 * T);
+    if (e == cudaSuccess) e = cudaMalloc(&P->d_elite, sizeof(int) * K);
+    if (e == cudaSuccess) e = cudaMalloc(&P->d_best, sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc(&P->d_ticket, sizeof(unsigned));
+    if (e == cudaSuccess) e = cudaMemset(P->d_ticket, 0, sizeof(unsigned));
+    if (e == cudaSuccess) e = cudaMemset(P->d_mu, 0, sizeof(float) * 2 * T);
+    if (e == cudaSuccess) e = cudaMemset(P->d_sd, 0, sizeof(float) * 2 * T);
+    if (e != cudaSuccess) {   // nothing half-built stays attached to the handle
+        cudaFree(P->d_J); cudaFree(P->d_mu); cudaFree(P->d_sd); cudaFree(P->d_elite); cudaFree(P->d_best); cudaFree(P->d_ticket);
+        delete P;
+        return fail(h, CPS_ERR_CUDA, "cps_plan: allocating the planner scratch: %s", cudaGetErrorString(e));
+    }
+    h->plan = P;
     *out = P;
     return CPS_OK;
 }
