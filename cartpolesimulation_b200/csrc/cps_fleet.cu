@@ -16,6 +16,7 @@
 #include <cuda_runtime.h>
 
 #include <cmath>
+#include <cstdint>
 #include <cstring>
 #include <new>
 
@@ -172,7 +173,7 @@ __device__ __forceinline__ void plant_tick(const PlantParams &P, float *s, doubl
     s[IDX_ANGLE] = (float)plant_wrap((double)s[IDX_ANGLE]);
 }
 
-template <int INTEG, int COST, bool PHILOX>
+template <int INTEG, int COST, bool PHILOX, bool PAIR>
 __global__ void __launch_bounds__(256, 4) fleet_kernel(const __grid_constant__ FleetArgs a) {
     extern __shared__ float smem[];
     __shared__ CostParams s_cost;
@@ -185,17 +186,26 @@ __global__ void __launch_bounds__(256, 4) fleet_kernel(const __grid_constant__ F
         s_cost.target_equilibrium = te;
     }
     const int nwarps = blockDim.x >> 5;
-    float *s_eps = smem + mp.T + 2 * mp.p + nwarps * (mp.n_red + 2) + mp.n_red + 4;  // [n_ind][blockDim.x]
-    const int k = blockIdx.x * blockDim.x + tid;
-    if (PHILOX)
-        fleet_draws(a.seed, a.period, a.e_offset + (unsigned)e, (unsigned)min(k, mp.K - 1), mp.n_ind, s_eps + tid, blockDim.x);
+    // [n_ind][rollouts of this block]; even offset: a pair's draws are read as one 8-byte word
+    float *s_eps = smem + ((mp.T + 2 * mp.p + nwarps * (mp.n_red + 2) + mp.n_red + 4 + 1) & ~1);
+    const int per_block = PAIR ? 2 * (int)blockDim.x : (int)blockDim.x;   // rollouts per block
+    if (PHILOX) {
+        if (PAIR) {
+            const int k = 2 * (blockIdx.x * blockDim.x + tid);
+            fleet_draws(a.seed, a.period, a.e_offset + (unsigned)e, (unsigned)min(k, mp.K - 2), mp.n_ind, s_eps + 2 * tid, per_block);
+            fleet_draws(a.seed, a.period, a.e_offset + (unsigned)e, (unsigned)min(k + 1, mp.K - 1), mp.n_ind, s_eps + 2 * tid + 1, per_block);
+        } else {
+            const int k = blockIdx.x * blockDim.x + tid;
+            fleet_draws(a.seed, a.period, a.e_offset + (unsigned)e, (unsigned)min(k, mp.K - 1), mp.n_ind, s_eps + tid, per_block);
+        }
+    }
     __syncthreads();
 
     SolveIO io;
     io.s = a.replay_s ? a.replay_s + (size_t)e * 6 : a.s + (size_t)e * 8;
-    if (PHILOX) {  // rollout k of this block sits at s_eps[i * blockDim.x + tid]
-        io.noise = s_eps - (long long)blockIdx.x * blockDim.x;
-        io.ns_i = blockDim.x; io.ns_k = 1;
+    if (PHILOX) {  // rollout k of the experiment sits at s_eps[i * per_block + (k - first rollout of this block)]
+        io.noise = s_eps - (long long)blockIdx.x * per_block;
+        io.ns_i = per_block; io.ns_k = 1;
     } else {
         io.noise = a.noise + (size_t)e * mp.n_ind * mp.K;
         io.ns_i = mp.K; io.ns_k = 1;
@@ -213,8 +223,9 @@ __global__ void __launch_bounds__(256, 4) fleet_kernel(const __grid_constant__ F
     if (a.L_row || a.mp_row)
         fold_ode_device<INTEG>(a, a.L_row ? (double)a.L_row[e] : (double)a.L_default,
                                a.mp_row ? (double)a.mp_row[e] : (double)a.mp_default, ode);
-    const bool last = mppi_solve_block<INTEG, COST, SC_ROTATE, CPS_NOISE_INDUCING, false, false>(ode, s_cost, mp, io, smem,
-                                                                                                blockIdx.x, a.bpe);
+    const bool last = PAIR ? mppi_solve_block2<INTEG, COST>(ode, s_cost, mp, io, smem, blockIdx.x, a.bpe)
+                           : mppi_solve_block<INTEG, COST, SC_ROTATE, CPS_NOISE_INDUCING, false, false>(ode, s_cost, mp, io, smem,
+                                                                                                       blockIdx.x, a.bpe);
     if (!last) return;
     __syncthreads();
     if (tid != 0) return;
@@ -251,7 +262,7 @@ __global__ void __launch_bounds__(256, 4) fleet_kernel(const __grid_constant__ F
 // ---- host side ---------------------------------------------------------------------------------------------------------
 struct FleetState {
     cps_fleet_config cfg;
-    int E, bpe, block;
+    int E, bpe, block, pair;   // pair: two rollouts per thread (packed FP32), K even
     size_t smem;
     float *d_s, *d_unom, *d_uprev, *d_partials;
     unsigned *d_tickets;
@@ -268,19 +279,23 @@ void cps_fleet_free(cps_handle *h) {
 }
 
 typedef void (*fleet_fn)(const FleetArgs);
-template <int INTEG, bool PHILOX>
+template <int INTEG, bool PHILOX, bool PAIR>
 static fleet_fn pick_fleet2(int cost) {
     switch (cost) {
-    case CPS_COST_DEFAULT: return fleet_kernel<INTEG, COST_DEFAULT, PHILOX>;
-    case CPS_COST_QUADRATIC_BOUNDARY: return fleet_kernel<INTEG, COST_QB, PHILOX>;
-    case CPS_COST_QB_GRAD_MINIMAL: return fleet_kernel<INTEG, COST_GRADMIN, PHILOX>;
-    case CPS_COST_QB_GRAD: return fleet_kernel<INTEG, COST_GRAD, PHILOX>;
+    case CPS_COST_DEFAULT: return fleet_kernel<INTEG, COST_DEFAULT, PHILOX, PAIR>;
+    case CPS_COST_QUADRATIC_BOUNDARY: return fleet_kernel<INTEG, COST_QB, PHILOX, PAIR>;
+    case CPS_COST_QB_GRAD_MINIMAL: return fleet_kernel<INTEG, COST_GRADMIN, PHILOX, PAIR>;
+    case CPS_COST_QB_GRAD: return fleet_kernel<INTEG, COST_GRAD, PHILOX, PAIR>;
     default: return nullptr;
     }
 }
-static fleet_fn pick_fleet(int integ, int cost, bool philox) {
-    if (integ == CPS_EULER_V0) return philox ? pick_fleet2<0, true>(cost) : pick_fleet2<0, false>(cost);
-    return philox ? pick_fleet2<1, true>(cost) : pick_fleet2<1, false>(cost);
+template <int INTEG>
+static fleet_fn pick_fleet1(int cost, bool philox, bool pair) {
+    if (pair) return philox ? pick_fleet2<INTEG, true, true>(cost) : pick_fleet2<INTEG, false, true>(cost);
+    return philox ? pick_fleet2<INTEG, true, false>(cost) : pick_fleet2<INTEG, false, false>(cost);
+}
+static fleet_fn pick_fleet(int integ, int cost, bool philox, bool pair) {
+    return integ == CPS_EULER_V0 ? pick_fleet1<0>(cost, philox, pair) : pick_fleet1<1>(cost, philox, pair);
 }
 
 extern "C" int cps_fleet_create(cps_handle *h, const cps_fleet_config *cfg) {
@@ -305,11 +320,15 @@ extern "C" int cps_fleet_create(cps_handle *h, const cps_fleet_config *cfg) {
     F->cfg = *cfg;
     F->E = cfg->n_experiments;
     const int K = h->cfg.num_rollouts, T = h->cfg.horizon;
-    F->block = K >= 256 ? 256 : ((K + 31) / 32) * 32;
-    F->bpe = (K + F->block - 1) / F->block;
+    // fleets are throughput work: two rollouts per thread in packed FP32 whenever K is even (mppi_solve_block2)
+    F->pair = (K % 2 == 0 && K >= 64 && !(h->cfg.flags & CPS_FLAG_NO_PAIRS)) ? 1 : 0;
+    const int threads = F->pair ? K / 2 : K;   // threads per experiment
+    F->block = threads >= 256 ? 256 : ((threads + 31) / 32) * 32;
+    F->bpe = (threads + F->block - 1) / F->block;
     const int nwarps = F->block / 32;
     size_t fl = (size_t)T + 2 * (size_t)h->cfg.interp_period + (size_t)nwarps * (h->n_red + 2) + (size_t)h->n_red + 4;
-    if (cfg->noise_source == CPS_FLEET_NOISE_PHILOX) fl += (size_t)h->n_ind * F->block;
+    fl = (fl + 1) & ~(size_t)1;
+    if (cfg->noise_source == CPS_FLEET_NOISE_PHILOX) fl += (size_t)h->n_ind * F->block * (F->pair ? 2 : 1);
     F->smem = fl * sizeof(float);
     if (F->smem > 200 * 1024) { delete F; return fail(h, CPS_ERR_UNSUPPORTED, "cps_fleet_create: horizon too large for shared memory"); }
     h->fleet = F;
@@ -418,7 +437,9 @@ static int fleet_launch(cps_handle *h, const char *who, int n_periods, const flo
     a.k = P.k; a.m_cart = P.m_cart; a.g = P.g; a.J_fric = P.J_fric; a.M_fric = P.M_fric; a.u_max = P.u_max;
     a.m_pole_fixed = h->phys[CPS_PH_M_POLE];
     a.L_default = h->L_var; a.mp_default = h->m_pole_var;
-    fleet_fn fn = pick_fleet(h->cfg.integrator, h->cfg.cost_id, philox);
+    if (F->pair && noise_dev && ((uintptr_t)noise_dev % 8) != 0)
+        return fail(h, CPS_ERR_INVALID, "%s: supplied noise must be 8-byte aligned", who);
+    fleet_fn fn = pick_fleet(h->cfg.integrator, h->cfg.cost_id, philox, F->pair != 0);
     if (!fn) return fail(h, CPS_ERR_NOT_CONFIGURED, "%s: no kernel for this configuration", who);
     if (F->smem > 48 * 1024) CUDA_TRY(h, cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F->smem));
     const size_t E = F->E, K = h->cfg.num_rollouts;
