@@ -29,6 +29,13 @@ __global__ void __launch_bounds__(256, 4) mppi_kernel(const __grid_constant__ Mp
                                                                     gridDim.x);
 }
 
+// The throughput form: two rollouts per thread in packed FP32 (mppi_solve_block2); chosen by cps_mppi_step for large K.
+template <int INTEG, int COST>
+__global__ void __launch_bounds__(128, 4) mppi_pair_kernel(const __grid_constant__ MppiArgs a) {
+    extern __shared__ float smem[];
+    mppi_solve_block2<INTEG, COST>(a.ode, a.cost, a.mp, a.io, smem, blockIdx.x, gridDim.x);
+}
+
 // Merge of gathered per-rank partials (K sharded over GPUs).
 __global__ void __launch_bounds__(128) finalize_kernel(const __grid_constant__ FinalizeArgs a, int direct_noise) {
     extern __shared__ float smem[];
@@ -476,6 +483,19 @@ static mppi_fn pick_mppi1(int cost, int noise, unsigned flags) {
     default: return pick_mppi2<INTEG, COST_NONE>(noise, flags);
     }
 }
+template <int INTEG>
+static mppi_fn pick_mppi_pair1(int cost) {
+    switch (cost) {
+    case CPS_COST_DEFAULT: return mppi_pair_kernel<INTEG, COST_DEFAULT>;
+    case CPS_COST_QUADRATIC_BOUNDARY: return mppi_pair_kernel<INTEG, COST_QB>;
+    case CPS_COST_QB_GRAD_MINIMAL: return mppi_pair_kernel<INTEG, COST_GRADMIN>;
+    case CPS_COST_QB_GRAD: return mppi_pair_kernel<INTEG, COST_GRAD>;
+    default: return mppi_pair_kernel<INTEG, COST_NONE>;
+    }
+}
+static mppi_fn pick_mppi_pair(const cps_config &c) {
+    return c.integrator == CPS_EULER_V0 ? pick_mppi_pair1<0>(c.cost_id) : pick_mppi_pair1<1>(c.cost_id);
+}
 static mppi_fn pick_mppi(const cps_config &c) {
     return c.integrator == CPS_EULER_V0 ? pick_mppi1<0>(c.cost_id, c.noise_mode, c.flags)
                                         : pick_mppi1<1>(c.cost_id, c.noise_mode, c.flags);
@@ -539,9 +559,25 @@ extern "C" int cps_mppi_step(cps_handle *h, const float *s_dev, const float *noi
     io.u_run_out = u_run_out_dev;
     io.partials = h->d_partials; io.ticket = h->d_ticket; io.nonfinite = h->d_nonfinite;
     io.shard_out = h->shard ? h->shard_out : nullptr;
-    mppi_fn fn = pick_mppi(h->cfg);
-    if (h->smem > 48 * 1024) CUDA_TRY(h, cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
-    fn<<<h->grid, h->block, h->smem, h->stream>>>(a);
+    // Large K is issue-bound, not latency-bound: two rollouts per thread in packed FP32 (same arithmetic per rollout; the
+    // block sums associate pairs first).  Needs the kernel's native noise order and no per-rollout logging outputs.
+    const bool pairs = K >= CPS_MPPI_PAIR_MIN_ROLLOUTS && (K % 2) == 0 && sc_mode(h->cfg.flags) == SC_ROTATE &&
+                       !(h->cfg.flags & (CPS_FLAG_FAST_DIV | CPS_FLAG_NO_PAIRS)) && h->cfg.noise_mode == CPS_NOISE_INDUCING &&
+                       noise_layout == CPS_TIME_MAJOR && ((uintptr_t)noise_dev % 8) == 0 && !traj_out_dev && !u_run_out_dev;
+    if (pairs) {
+        const long long threads = K / 2;
+        const int block = threads <= 148 * 32 * 4 ? 32 : (threads <= 148 * 64 * 8 ? 64 : 128);
+        const int grid = (int)((threads + block - 1) / block);   // grid <= h->grid: the partial records fit
+        const size_t smem = sizeof(float) * ((size_t)h->cfg.horizon + 2 * (size_t)h->cfg.interp_period
+                                             + (size_t)(block / 32) * (h->n_red + 2) + (size_t)h->n_red + 4);
+        mppi_fn fn = pick_mppi_pair(h->cfg);
+        if (smem > 48 * 1024) CUDA_TRY(h, cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        fn<<<grid, block, smem, h->stream>>>(a);
+    } else {
+        mppi_fn fn = pick_mppi(h->cfg);
+        if (h->smem > 48 * 1024) CUDA_TRY(h, cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+        fn<<<h->grid, h->block, h->smem, h->stream>>>(a);
+    }
     h->launches += 1;
     CUDA_TRY(h, cudaGetLastError());
     return CPS_OK;

@@ -252,11 +252,23 @@ def test_mppi_full_size_properties():
     rel = ((Jc + corr - J1)[unclipped].abs().max() / J1.abs().max()).item()
     assert unclipped.float().mean().item() > 0.5
     assert rel < 2e-6, rel
-    # (2)
+    # (2) without the logging outputs this K takes the packed two-rollouts-per-thread kernel: every rollout's cost is
+    # bit-identical to the one-per-thread kernel's (same arithmetic per rollout), the update agrees to summation order,
+    # and the packed kernel itself is bitwise reproducible run to run
     eng.mppi_reset(0.0)
     u2 = eng.mppi_step(s, noise, L.TIME_MAJOR, 0.0, None, J).clone()
-    assert torch.equal(u1, u2) and torch.equal(J, J1)
-    np.testing.assert_array_equal(eng.get_u_nom(), un1)
+    assert torch.equal(J, J1)
+    assert abs(float(u2.cpu()[0]) - float(u1.cpu()[0])) < 2e-6
+    un2 = eng.get_u_nom()
+    np.testing.assert_allclose(un2, un1, rtol=0, atol=2e-6)
+    eng.mppi_reset(0.0)
+    u2b = eng.mppi_step(s, noise, L.TIME_MAJOR, 0.0, None, J).clone()
+    assert torch.equal(u2, u2b) and torch.equal(J, J1)
+    np.testing.assert_array_equal(eng.get_u_nom(), un2)
+    one = _engine(K, T, integrator="ODE", cost="quadratic_boundary_grad_minimal", no_pairs=True)   # A/B flag
+    one.mppi_reset(0.0)
+    u2c = one.mppi_step(s, noise, L.TIME_MAJOR, 0.0, None, J).clone()
+    assert torch.equal(u2c, u1) and torch.equal(J, J1)
     # (3)
     perm = torch.randperm(K, generator=g, device="cuda")
     eng.mppi_reset(0.0)
