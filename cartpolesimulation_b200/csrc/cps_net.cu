@@ -578,10 +578,10 @@ static int net_launch(cps_handle *h, NetArgs &a, bool mppi, int n_rows) {
     a.net = S->dev;
     a.weights = S->d_weights;
     a.tc = S->d_tc;
-    // tensor cores (tcgen05, 128 rollouts per CTA) pay off once there are enough rollouts to occupy the SMs with
-    // 128-row tiles; below that the FP32 kernel's 16-row tiles spread the same work over more SMs
+    // tensor cores (tcgen05, 128 rollouts per CTA): a solve takes ~0.42 ms of per-step latency whatever the batch (T = 50);
+    // the FP32 kernel's 16-row tiles take 0.38 ms while they fit one wave (148 x 16 rollouts) and 0.64 ms beyond
     const unsigned fl = h->cfg.flags;
-    const bool want_tc = (fl & CPS_FLAG_NET_TENSOR_CORES) || (!(fl & CPS_FLAG_NET_FP32) && n_rows >= 4096);
+    const bool want_tc = (fl & CPS_FLAG_NET_TENSOR_CORES) || (!(fl & CPS_FLAG_NET_FP32) && n_rows > 148 * 16);
     if ((fl & CPS_FLAG_NET_TENSOR_CORES) && !S->d_tc)
         return fail(h, CPS_ERR_UNSUPPORTED, "CPS_FLAG_NET_TENSOR_CORES: the tensor-core kernel supports 2 x 64 GRU networks only");
     if (want_tc && S->d_tc) return cps_net_tc_launch(h, a, mppi, n_rows);
