@@ -19,6 +19,8 @@ struct MppiArgs {
     CostParams cost;
     MppiParams mp;
     SolveIO io;
+    float s_inline[6];   // cps_mppi_step_host: the state travels in the parameter block (no host-to-device copy)
+    int use_inline;
 };
 
 struct RolloutArgs {
@@ -79,6 +81,8 @@ struct cps_handle {
     float *d_uprev;   // legacy front-end: previous nominal sequence [T]
     float *d_ldu;     // legacy front-end: staging of delta_u for cps_legacy_step_host [K][T]
     float *h_pin;  // pinned: [0..6) s, [8] u
+    float *h_pin_dev;        // device view of h_pin (mapped): the solve writes u straight into host memory
+    const float *inline_s;   // set by cps_mppi_step_host around its cps_mppi_step call
     int grid, block;
     size_t smem;
     int shard;

@@ -25,15 +25,18 @@
 template <int INTEG, int COST, int SC, int NOISE, bool FAST_DIV, bool EXACT_ATAN2>
 __global__ void __launch_bounds__(256, 4) mppi_kernel(const __grid_constant__ MppiArgs a) {
     extern __shared__ float smem[];
-    mppi_solve_block<INTEG, COST, SC, NOISE, FAST_DIV, EXACT_ATAN2>(a.ode, a.cost, a.mp, a.io, smem, blockIdx.x,
-                                                                    gridDim.x);
+    SolveIO io = a.io;
+    if (a.use_inline) io.s = a.s_inline;   // constant-bank reads instead of a global load of the state
+    mppi_solve_block<INTEG, COST, SC, NOISE, FAST_DIV, EXACT_ATAN2>(a.ode, a.cost, a.mp, io, smem, blockIdx.x, gridDim.x);
 }
 
 // The throughput form: two rollouts per thread in packed FP32 (mppi_solve_block2); chosen by cps_mppi_step for large K.
 template <int INTEG, int COST>
 __global__ void __launch_bounds__(128, 4) mppi_pair_kernel(const __grid_constant__ MppiArgs a) {
     extern __shared__ float smem[];
-    mppi_solve_block2<INTEG, COST>(a.ode, a.cost, a.mp, a.io, smem, blockIdx.x, gridDim.x);
+    SolveIO io = a.io;
+    if (a.use_inline) io.s = a.s_inline;
+    mppi_solve_block2<INTEG, COST>(a.ode, a.cost, a.mp, io, smem, blockIdx.x, gridDim.x);
 }
 
 // Merge of gathered per-rank partials (K sharded over GPUs).
@@ -368,7 +371,8 @@ extern "C" int cps_create(const cps_config *cfg, cps_handle **out) {
         CREATE_TRY(cudaMalloc(&h->d_uprev, sizeof(float) * (size_t)cfg->horizon));
         CREATE_TRY(cudaMemset(h->d_uprev, 0, sizeof(float) * (size_t)cfg->horizon));
     }
-    CREATE_TRY(cudaMallocHost(&h->h_pin, sizeof(float) * 16));
+    CREATE_TRY(cudaHostAlloc(&h->h_pin, sizeof(float) * 16, cudaHostAllocMapped));
+    if (cudaHostGetDevicePointer((void **)&h->h_pin_dev, h->h_pin, 0) != cudaSuccess) { h->h_pin_dev = nullptr; cudaGetLastError(); }
     CREATE_TRY(cudaMemset(h->d_ticket, 0, sizeof(unsigned)));
     CREATE_TRY(cudaMemset(h->d_nonfinite, 0, sizeof(int)));
     CREATE_TRY(cudaMemset(h->d_unom, 0, sizeof(float) * (size_t)cfg->horizon));
@@ -548,6 +552,8 @@ extern "C" int cps_mppi_step(cps_handle *h, const float *s_dev, const float *noi
                                  traj_layout, u_run_out_dev);
     MppiArgs a;
     a.ode = h->ode; a.cost = h->cost; a.mp = h->mp;
+    a.use_inline = h->inline_s ? 1 : 0;
+    for (int c = 0; c < 6; ++c) a.s_inline[c] = h->inline_s ? h->inline_s[c] : 0.0f;
     SolveIO &io = a.io;
     io.s = s_dev; io.noise = noise_dev;
     const long long K = h->cfg.num_rollouts;
@@ -588,6 +594,18 @@ extern "C" int cps_mppi_step_host(cps_handle *h, const float *s_host, const floa
     if (!h) return CPS_ERR_INVALID;
     if (!s_host || !u_out_host) return fail(h, CPS_ERR_INVALID, "cps_mppi_step_host: null pointer");
     CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    if (h->cfg.integrator != CPS_PREDICTOR_NEURAL && h->h_pin_dev && !h->shard) {
+        // ODE predictors: ONE operation on the stream.  The state rides in the kernel's parameter block and the block that
+        // finishes the update writes u straight into mapped pinned host memory; no copy in either direction.
+        h->inline_s = s_host;
+        int rc = cps_mppi_step(h, h->d_s, noise_dev, noise_layout, u_prev, h->d_unom, h->h_pin_dev + 8, nullptr, nullptr,
+                               CPS_ROLLOUT_MAJOR, nullptr);
+        h->inline_s = nullptr;
+        if (rc != CPS_OK) return rc;
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        *u_out_host = h->h_pin[8];
+        return CPS_OK;
+    }
     memcpy(h->h_pin, s_host, sizeof(float) * 6);
     CUDA_TRY(h, cudaMemcpyAsync(h->d_s, h->h_pin, sizeof(float) * 6, cudaMemcpyHostToDevice, h->stream));
     int rc = cps_mppi_step(h, h->d_s, noise_dev, noise_layout, u_prev, h->d_unom, h->d_u, nullptr, nullptr,

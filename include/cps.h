@@ -155,7 +155,9 @@ int cps_mppi_step(cps_handle *h, const float *s_dev, const float *noise_dev, int
 /* Host-buffer form of the same call, the one the reference-facing optimizer.step(s) makes: s_host [6] is copied
  * up, the control comes back in *u_out_host; u_nom lives in the handle (cps_mppi_reset zeroes it like
  * optimizer_reset, optimizer_mppi.py:226-230).  noise_dev stays a DEVICE pointer: the draws are produced on the
- * device (the reference draws them inside step() too, :169-175).  Synchronises. */
+ * device (the reference draws them inside step() too, :169-175).  Synchronises.  With the ODE predictors this is ONE
+ * operation on the stream: the state travels in the kernel's parameter block and the control is written by the kernel
+ * into mapped pinned host memory (no copy in either direction). */
 int cps_mppi_step_host(cps_handle *h, const float *s_host, const float *noise_dev, int noise_layout, float u_prev,
                        float *u_out_host);
 int cps_mppi_reset(cps_handle *h, float u_nom_init);
