@@ -28,6 +28,8 @@ struct PlanArgs {
     OdeParams ode;
     CostParams cost;
     const float *s;               // [6]
+    float s_inline[6];            // *_host entry points: the state travels in the parameter block
+    int use_inline;
     const float *Q;               // PLAN_Q: plans; PLAN_CEM: standard-normal draws
     long long qs_k, qs_t;         // element strides along plan / horizon step
     const float *mu, *sd;         // PLAN_CEM: sampling distribution [T]
@@ -358,7 +360,7 @@ __global__ void __launch_bounds__(256, 4) plan_kernel(const __grid_constant__ Pl
     const bool active = k < a.K;
     const int kc = min(k, a.K - 1);
 
-    State z = load_state(a.s);
+    State z = load_state(a.use_inline ? a.s_inline : a.s);
     const OdeParams ode = pin_params(a.ode, z.th);
     float c_cost = cosf(z.th);  // the plugins take cos(angle) of the stored angle (default.py:34)
     const float *q = a.Q + (long long)kc * a.qs_k;
@@ -467,6 +469,8 @@ static void plan_common(cps_handle *h, PlanArgs &a, const float *s_dev, float u_
     memset(&a, 0, sizeof(a));
     a.ode = h->ode; a.cost = h->cost;
     a.s = s_dev;
+    a.use_inline = h->inline_s ? 1 : 0;
+    for (int c = 0; c < 6; ++c) a.s_inline[c] = h->inline_s ? h->inline_s[c] : 0.0f;
     a.lo = h->mppi_in[5]; a.hi = h->mppi_in[6];
     a.inv_T1 = 1.0f / (float)(T + 1);
     a.u_prev = u_prev;
@@ -542,11 +546,13 @@ extern "C" int cps_plan_random_action_host(cps_handle *h, const float *s_host, c
     if (!h) return CPS_ERR_INVALID;
     if (!s_host || !u_out_host) return fail(h, CPS_ERR_INVALID, "cps_plan_random_action_host: null pointer");
     CUDA_TRY(h, cudaSetDevice(h->cfg.device));
-    memcpy(h->h_pin, s_host, sizeof(float) * 6);
-    CUDA_TRY(h, cudaMemcpyAsync(h->d_s, h->h_pin, sizeof(float) * 6, cudaMemcpyHostToDevice, h->stream));
-    int rc = cps_plan_random_action(h, h->d_s, Q_dev, q_layout, u_prev, h->d_u, nullptr, nullptr);
+    // one stream operation: state in the parameter block, control written into mapped pinned host memory
+    float *u_dst = h->h_pin_dev ? h->h_pin_dev + 8 : h->d_u;
+    h->inline_s = s_host;
+    int rc = cps_plan_random_action(h, h->d_s, Q_dev, q_layout, u_prev, u_dst, nullptr, nullptr);
+    h->inline_s = nullptr;
     if (rc != CPS_OK) return rc;
-    CUDA_TRY(h, cudaMemcpyAsync(h->h_pin + 8, h->d_u, sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    if (!h->h_pin_dev) CUDA_TRY(h, cudaMemcpyAsync(h->h_pin + 8, h->d_u, sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     *u_out_host = h->h_pin[8];
     return CPS_OK;
@@ -639,11 +645,12 @@ extern "C" int cps_cem_step_host(cps_handle *h, const float *s_host, const float
     if (!h) return CPS_ERR_INVALID;
     if (!s_host || !u_out_host) return fail(h, CPS_ERR_INVALID, "cps_cem_step_host: null pointer");
     CUDA_TRY(h, cudaSetDevice(h->cfg.device));
-    memcpy(h->h_pin, s_host, sizeof(float) * 6);
-    CUDA_TRY(h, cudaMemcpyAsync(h->d_s, h->h_pin, sizeof(float) * 6, cudaMemcpyHostToDevice, h->stream));
-    int rc = cps_cem_step(h, h->d_s, eps_dev, eps_layout, n_iterations, u_prev, h->d_u, nullptr, nullptr);
+    float *u_dst = h->h_pin_dev ? h->h_pin_dev + 8 : h->d_u;
+    h->inline_s = s_host;
+    int rc = cps_cem_step(h, h->d_s, eps_dev, eps_layout, n_iterations, u_prev, u_dst, nullptr, nullptr);
+    h->inline_s = nullptr;
     if (rc != CPS_OK) return rc;
-    CUDA_TRY(h, cudaMemcpyAsync(h->h_pin + 8, h->d_u, sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    if (!h->h_pin_dev) CUDA_TRY(h, cudaMemcpyAsync(h->h_pin + 8, h->d_u, sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     *u_out_host = h->h_pin[8];
     return CPS_OK;
