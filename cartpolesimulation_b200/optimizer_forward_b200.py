@@ -38,6 +38,19 @@ class CudaGenerator(CudaNormalGenerator):
 
 class _forward_optimizer:
     supported_computation_libraries = ("Numpy", "TF", "Pytorch")
+    NOISE_RING = 256   # solves per device RNG call when the optimizer draws its own numbers
+
+    def _ring_draw(self, shape, draw):
+        """One solve's draws (tensor of `shape`) out of a ring filled by a single generator call per NOISE_RING solves:
+        a device RNG launch costs ~8 us of host time, a good part of a solve at these sizes."""
+        ring = getattr(self, "_ring", None)
+        if ring is None or tuple(ring.shape[1:]) != tuple(shape) or self._ring_i >= ring.shape[0]:
+            n = max(1, min(self.NOISE_RING, (64 << 20) // (4 * int(np.prod(shape)))))
+            self._ring = draw((n,) + tuple(shape))
+            self._ring_i = 0
+        out = self._ring[self._ring_i]
+        self._ring_i += 1
+        return out
 
     def __init__(self, predictor, cost_function, control_limits, computation_library=None, seed=None,
                  mpc_horizon: int = 35, num_rollouts: int = 200, optimizer_logging: bool = False,
@@ -141,7 +154,7 @@ class optimizer_random_action_b200(_forward_optimizer):
         K, T = self.num_rollouts, self.mpc_horizon
         lo, hi = float(self.action_low[0]), float(self.action_high[0])
         if self.rng is self._own_rng:
-            return self._own_rng.uniform((T, K), lo, hi), L.TIME_MAJOR
+            return self._ring_draw((T, K), lambda shp: self._own_rng.uniform(shp, lo, hi)), L.TIME_MAJOR
         Q = self.rng.uniform(shape=[K, T, 1], minval=lo, maxval=hi, dtype=torch.float32)  # reference call (:58-63)
         return torch.as_tensor(Q).to(device=self.device, dtype=torch.float32).reshape(K, T).contiguous(), L.ROLLOUT_MAJOR
 
@@ -205,7 +218,9 @@ class optimizer_cem_b200(_forward_optimizer):
     def _draw(self, iterations):
         K, T = self.num_rollouts, self.mpc_horizon
         if self.rng is self._own_rng:
-            return self._own_rng.normal((iterations, T, K)), L.TIME_MAJOR
+            if iterations != self.cem_outer_it:   # the warm-up solve
+                return self._own_rng.normal((iterations, T, K)), L.TIME_MAJOR
+            return self._ring_draw((iterations, T, K), self._own_rng.normal), L.TIME_MAJOR
         eps = [torch.as_tensor(self.rng.normal(shape=(K, T, 1), dtype=torch.float32)).reshape(K, T)
                for _ in range(iterations)]  # one reference-shaped call per outer iteration (:66-67)
         return torch.stack(eps).to(device=self.device, dtype=torch.float32).contiguous(), L.ROLLOUT_MAJOR

@@ -83,6 +83,7 @@ def _extract_predictor(predictor, predictor_specification):
 
 class optimizer_mppi_b200:
     supported_computation_libraries = ("Numpy", "TF", "Pytorch")
+    NOISE_RING = 256   # solves per device RNG call when the optimizer draws its own noise
 
     def __init__(self, predictor, cost_function, control_limits, computation_library=None, seed=None,
                  cc_weight: float = 1.0, R: float = 1.0, LBD: float = 100.0, mpc_horizon: int = 35,
@@ -114,7 +115,7 @@ class optimizer_mppi_b200:
         self.engine = None
         self.rng = None
         self._own_rng = None
-        self._next_noise = None
+        self._ring, self._ring_i = None, 0
         self._var = None
         self._J = self._traj = self._u_run = None
 
@@ -212,10 +213,15 @@ class optimizer_mppi_b200:
     def _draw_noise(self):
         K, n_ind = self.num_rollouts, self.engine.n_ind
         if self.rng is self._own_rng:
-            if self._next_noise is not None:
-                noise, self._next_noise = self._next_noise, None
-                return noise, L.TIME_MAJOR
-            return self._own_rng.normal((n_ind, K)), L.TIME_MAJOR
+            # draws for NOISE_RING solves come from one generator call: the per-solve cost of a device RNG launch
+            # (~8 us of host time, a sixth of the solve) is paid once per ring
+            if self._ring is None or self._ring_i >= self._ring.shape[0]:
+                ring = max(1, min(self.NOISE_RING, (64 << 20) // (4 * n_ind * K)))
+                self._ring = self._own_rng.normal((ring, n_ind, K))
+                self._ring_i = 0
+            noise = self._ring[self._ring_i]
+            self._ring_i += 1
+            return noise, L.TIME_MAJOR
         # a caller-supplied generator (e.g. injected draws): reference call shape and layout (:172-174)
         eps = self.rng.normal([K, n_ind, 1], dtype=torch.float32)
         eps = torch.as_tensor(eps).to(device=self.device, dtype=torch.float32).reshape(K, n_ind).contiguous()
@@ -249,8 +255,6 @@ class optimizer_mppi_b200:
             u = float(u_dev.cpu()[0])
         else:
             u = self.engine.mppi_step_host(s, noise, layout, u_prev)
-        if self.rng is self._own_rng:  # draw the next solve's noise now; it does not depend on s
-            self._next_noise = self._own_rng.normal((self.engine.n_ind, self.num_rollouts))
         self.u = np.array(u, dtype=np.float32)
         if self.optimizer_logging:
             self.logging_values["Q_logged"] = self._u_run.cpu().numpy()
