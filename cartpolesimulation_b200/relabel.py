@@ -10,9 +10,10 @@ fleet_kernel launch per row of all files (cps_fleet_relabel), nothing returning 
 
 Attribute-name conventions of the reference are kept (:166-263): `<col>_random_uniform_<lo>_<hi>[_<step>]` draws the
 attribute per row, `<col>_integrate_<lo>_<hi>_` averages the control over a scrambled-Sobol sample of the attribute
-(`integration_num_evals` consecutive controller steps per row, :318-345).  `<col>_differentiate_` and
-integration_method='nquad' need the controller's answers to choose their next query point and are not offered here
-(NotImplementedError).  No CPU fallback.
+(`integration_num_evals` consecutive controller steps per row, :318-345), `<col>_differentiate_` labels the derivative of
+the control with respect to the attribute (five controller steps per row and feature at value + {-2..2} * 0.5e-3, then a
+Savitzky-Golay first derivative, :348-470).  integration_method='nquad' (adaptive quadrature: the next query point
+depends on the controller's answers) and method='nd' are not offered (NotImplementedError).  No CPU fallback.
 """
 from __future__ import annotations
 
@@ -144,6 +145,26 @@ def get_integration_features(environment_attributes_dict):
     return features, ranges, env
 
 
+def get_differentiation_features(environment_attributes_dict, output_variable_names):
+    """:266-300: (features, attribute dict with plain column names, output column names)."""
+    env = dict(environment_attributes_dict)
+    features = []
+    for key, value in env.items():
+        m = _DIFFERENTIATE.match(value)
+        if m:
+            features.append(m.group(1))
+            env[key] = m.group(1)
+    if features:
+        names = [f"{o}_d{f}" for o in output_variable_names for f in features] \
+            + [f"{o[1:]}_d{f}" for o in output_variable_names for f in features]   # the reference's naming (:289-296)
+    else:
+        names = list(output_variable_names)
+    return features, env, names
+
+
+DIFF_STEP, DIFF_WINDOW, DIFF_POLYORDER = 0.5e-3, 5, 1   # differentiation() defaults (:352-354,:370-373)
+
+
 def sobol_samples(features, ranges, num_evals, n_rows, seed=None):
     """The Monte-Carlo sample of :318-337: per row a freshly scrambled Sobol sequence of 2^ceil(log2 N) points scaled
     to the feature ranges.  Returns [n_rows, N, d]."""
@@ -175,13 +196,9 @@ def add_control_along_trajectories(dfs, controller_config, controller_output_var
     files = [dfs] if single else list(dfs)
     if not files:
         return []
-    names = controller_output_variable_name if isinstance(controller_output_variable_name, list) \
-        else [controller_output_variable_name]
-    if len(names) != 1:
+    if isinstance(controller_output_variable_name, list) and len(controller_output_variable_name) != 1:
         raise ValueError("one control input: exactly one output variable name")
     env0 = dict(controller_config["environment_attributes_dict"])
-    if any(_DIFFERENTIATE.match(v) for v in env0.values()):
-        raise NotImplementedError("<feature>_differentiate_ is not offered by the GPU relabeller")
     state_components = list(controller_config.get("state_components", STATE_COMPONENTS))
     rng = np.random.default_rng(seed)
     originals, tables, env = [], [], None
@@ -189,16 +206,23 @@ def add_control_along_trajectories(dfs, controller_config, controller_output_var
         df, env_f = process_random_sampling(df, env0, rng)
         originals.append(df.copy())
         tables.append(df_modifier(df))
-        features, ranges, env = get_integration_features(env_f)
+        features, ranges, env_i = get_integration_features(env_f)
+        diff_features, env, names = get_differentiation_features(env_i, [controller_output_variable_name]
+                                                                 if not isinstance(controller_output_variable_name, list)
+                                                                 else controller_output_variable_name)
+    if features and diff_features:
+        raise ValueError("Cannot integrate and differentiate at the same time.")
     if features and integration_method != "monte_carlo":
         raise NotImplementedError("integration_method='nquad' is adaptive (sequential on the host); use 'monte_carlo'")
-    unknown = [k for k in features if k not in _CONTROLLER_ATTRIBUTES]
+    unknown = [k for k in features + diff_features if k not in _CONTROLLER_ATTRIBUTES]
     if unknown:
-        raise ValueError(f"cannot integrate over {unknown}: the controller's attributes are {_CONTROLLER_ATTRIBUTES}")
+        raise ValueError(f"cannot sweep {unknown}: the controller's attributes are {_CONTROLLER_ATTRIBUTES}")
     ev = 1
     if features:
         m = int(np.ceil(np.log2(integration_num_evals)))
         ev = 2 ** m
+    elif diff_features:
+        ev = DIFF_WINDOW * len(diff_features)
     E = len(files)
     rows = [len(t) for t in tables]
     R = max(rows)
@@ -207,6 +231,7 @@ def add_control_along_trajectories(dfs, controller_config, controller_output_var
     for k in _CONTROLLER_ATTRIBUTES:
         if k in env or k in features:
             attrs[k] = np.zeros((R * ev, E), dtype=np.float32)
+    offsets = (np.arange(DIFF_WINDOW) - (DIFF_WINDOW - 1) // 2) * DIFF_STEP
     for e, t in enumerate(tables):
         n = rows[e]
         idx = np.minimum(np.arange(R), n - 1)   # shorter files idle on their last row; those labels are dropped
@@ -219,6 +244,12 @@ def add_control_along_trajectories(dfs, controller_config, controller_output_var
             smp = sobol_samples(features, ranges, ev, R, seed=None if seed is None else [int(seed), e])
             for j, f in enumerate(features):
                 attrs[f][:, e] = smp[:, :, j].reshape(-1).astype(np.float32)
+        for j, f in enumerate(diff_features):   # window j of every row sweeps feature f (:449-454)
+            base = t[env[f]].to_numpy(dtype=np.float64)[idx]
+            if np.isnan(base).any():
+                raise ValueError(f"column {env[f]} has NaN entries; the derivative is undefined there")
+            sweep = attrs[f][:, e].reshape(R, ev)
+            sweep[:, j * DIFF_WINDOW:(j + 1) * DIFF_WINDOW] = (base[:, None] + offsets[None, :]).astype(np.float32)
     own = relabeller is None
     if own:
         relabeller = Relabeller(E, **dict(controller_config.get("mppi", {})))
@@ -231,14 +262,23 @@ def add_control_along_trajectories(dfs, controller_config, controller_output_var
     finally:
         if own:
             relabeller.close()
-    Q = Q.reshape(R, ev, E).astype(np.float64).mean(axis=1)   # np.mean(evaluations) of :339-345
+    Q = Q.reshape(R, ev, E).astype(np.float64)
+    if diff_features:
+        from scipy.signal import savgol_filter
+        half = (DIFF_WINDOW - 1) // 2
+        u = Q.reshape(R, len(diff_features), DIFF_WINDOW, E)
+        der = savgol_filter(u, window_length=DIFF_WINDOW, polyorder=DIFF_POLYORDER, deriv=1, delta=DIFF_STEP, axis=2,
+                            mode="constant")[:, :, half, :]
+        labels = np.concatenate([der, u[:, :, half, :]], axis=1)   # [R, 2 * features, E]: jacobian, then central outputs
+    else:
+        labels = Q.mean(axis=1)[:, None, :]   # np.mean(evaluations) of :339-345
     out = []
     for e in range(E):
-        lab = Q[:rows[e], e]
+        lab = labels[:rows[e], :, e]
         if save_output_only:
-            out.append(pd.DataFrame(lab[:, None], columns=names))
+            out.append(pd.DataFrame(lab, columns=names))
         else:
             d = originals[e]
-            d[names[0]] = lab
+            d[names] = lab
             out.append(d)
     return out[0] if single else out

@@ -95,14 +95,16 @@ def gen(name, pred, cost, K, T, n_files, n_rows, env_attrs, n_evals):
         n_ind = opt.Interpolator.number_of_interpolation_inducing_points
         gen_ = torch.Generator().manual_seed(100 + f)
         draws = [torch.normal(0.0, 1.0, size=(K, n_ind, 1), generator=gen_, dtype=torch.float32)
-                 for _ in range(n_rows * max(n_evals, 1))]
+                 for _ in range(n_rows * max(n_evals, 1, 5))]
         opt.rng = R.InjectedNormal(draws)
         ctrl = RecordingController(opt, vp, draws, vp_np)
         cfg = dict(state_components=STATE_COLUMNS, environment_attributes_dict=dict(env_attrs))
         out = add_control_along_trajectories(df.copy(), cfg, controller_creator=lambda c, a: ctrl,
                                              controller_output_variable_name="Q_calculated_offline",
                                              integration_method="monte_carlo", integration_num_evals=n_evals)
-        assert len(ctrl.calls) == n_rows * max(n_evals, 1), "the reference swallowed an exception (it prints and goes on)"
+        n_diff = sum(1 for v in env_attrs.values() if v.endswith("_differentiate_"))
+        per_row = 5 * n_diff if n_diff else max(n_evals, 1)   # savgol window 5 per differentiated feature (:365-372)
+        assert len(ctrl.calls) == n_rows * per_row, "the reference swallowed an exception (it prints and goes on)"
         n_calls = len(ctrl.calls)
         arrays[f"f{f}__s"] = np.stack([c["s"] for c in ctrl.calls])
         arrays[f"f{f}__tp"] = np.array([c["tp"] for c in ctrl.calls], dtype=np.float64)
@@ -110,7 +112,9 @@ def gen(name, pred, cost, K, T, n_files, n_rows, env_attrs, n_evals):
         arrays[f"f{f}__L"] = np.array([c["L"] for c in ctrl.calls], dtype=np.float64)
         arrays[f"f{f}__eps"] = np.stack([c["eps"] for c in ctrl.calls])
         arrays[f"f{f}__u"] = np.array([c["u"] for c in ctrl.calls], dtype=np.float32)
-        arrays[f"f{f}__Q_calculated_offline"] = out["Q_calculated_offline"].to_numpy(dtype=np.float64)
+        for col in out.columns:
+            if "calculated_offline" in col:
+                arrays[f"f{f}__{col}"] = out[col].to_numpy(dtype=np.float64)
         arrays[f"f{f}__table"] = df[["time"] + STATE_COLUMNS + ["target_position", "target_equilibrium", "L"]].to_numpy()
     save("relabel_" + name, dict(ref="SI_Toolkit/General/preprocess_data_add_control_along_trajectories.py:53-140 driving "
                                      "optimizer_mppi (torch lib, injected draws) through a controller_mpc.step-shaped hook",
@@ -132,6 +136,8 @@ def main():
             gen("plain_ode", "ODE", "quadratic_boundary_grad_minimal", 256, 30, 3, 10, plain, 0)
             gen("plain_v0", "ODE_v0", "quadratic_boundary_grad_minimal", 128, 30, 2, 8, plain, 0)
             gen("integrate_ode", "ODE", "quadratic_boundary_grad", 128, 20, 2, 5, integ, 4)
+            diff = {"target_position": "target_position", "target_equilibrium": "target_equilibrium", "L": "L_differentiate_"}
+            gen("differentiate_ode", "ODE", "quadratic_boundary_grad_minimal", 128, 20, 2, 4, diff, 0)
         finally:
             txt = buf.getvalue()
     print("\n".join(l for l in txt.splitlines() if l.startswith("wrote") or "Error" in l))

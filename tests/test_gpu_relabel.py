@@ -16,7 +16,8 @@ def _stack(z, m, key, dtype=np.float32):
     return np.stack([z[f"f{f}__{key}"] for f in range(m["files"])], axis=1).astype(dtype)   # [calls, E, ...]
 
 
-@pytest.mark.parametrize("name", ["relabel_plain_ode", "relabel_plain_v0", "relabel_integrate_ode"])
+@pytest.mark.parametrize("name", ["relabel_plain_ode", "relabel_plain_v0", "relabel_integrate_ode",
+                                  "relabel_differentiate_ode"])
 def test_relabel_matches_reference(name):
     from cartpolesimulation_b200.relabel import Relabeller
     z, m = load_golden(name)
@@ -30,6 +31,9 @@ def test_relabel_matches_reference(name):
     np.testing.assert_allclose(Q, ref, rtol=0, atol=1e-4)   # north_star: selected control within 1e-4
     ev = max(m["evals"], 1)
     for f in range(E):
+        if "differentiate" in name:   # central output of the five-point window; the derivative amplifies 1e-4 by 1/step
+            np.testing.assert_allclose(Q[:, f].reshape(m["rows"], 5)[:, 2], z[f"f{f}___calculated_offline_dL"], rtol=0, atol=1e-4)
+            continue
         label = Q[:, f].reshape(m["rows"], ev).astype(np.float64).mean(axis=1)
         np.testing.assert_allclose(label, z[f"f{f}__Q_calculated_offline"], rtol=0, atol=1e-4)
     # a second pass after reset() reproduces the first bit for bit (warm start and last control were cleared)

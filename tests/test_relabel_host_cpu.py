@@ -69,8 +69,36 @@ def test_attribute_name_conventions():
     f, r, env = RL.get_integration_features({"L": "L_integrate_0.25_0.55_", "target_position": "target_position"})
     assert f == ["L"] and r == {"L": (0.25, 0.55)} and env["L"] == "L"
     with pytest.raises(NotImplementedError):
-        RL.add_control_along_trajectories([df], dict(environment_attributes_dict={"L": "L_differentiate_"}), relabeller=Recorder(1))
-    with pytest.raises(NotImplementedError):
         RL.add_control_along_trajectories([df.assign(**{c: 0.0 for c in STATE})],
                                           dict(environment_attributes_dict={"L": "L_integrate_0.25_0.55_"}),
                                           integration_method="nquad", relabeller=Recorder(1))
+
+
+def test_differentiation_expansion_and_labels_match_the_reference():
+    """`<col>_differentiate_`: five controller steps per row at value + {-2..2} * 0.5e-3 (what the reference fed its
+    controller), and from the controls the reference got back, the same derivative / central-output labels."""
+    z, m = load_golden("relabel_differentiate_ode")
+    E, R = m["files"], m["rows"]
+    dfs = [pd.DataFrame(z[f"f{f}__table"], columns=m["columns"]) for f in range(E)]
+
+    class Replay(Recorder):   # answers with the controls the reference's controller returned
+        def relabel(self, states, tp, te, L, mp, noise=None):
+            super().relabel(states, tp, te, L, mp)
+            return np.stack([z[f"f{f}__u"] for f in range(E)], axis=1).astype(np.float32)
+
+    rec = Replay(E)
+    cfg = dict(state_components=STATE, environment_attributes_dict=m["environment_attributes_dict"])
+    out = RL.add_control_along_trajectories(dfs, cfg, "Q_calculated_offline", relabeller=rec)
+    c = rec.calls[0]
+    for f in range(E):
+        np.testing.assert_array_equal(c["states"][:, f], z[f"f{f}__s"])
+        np.testing.assert_array_equal(c["L"][:, f], z[f"f{f}__L"].astype(np.float32))
+        np.testing.assert_array_equal(c["tp"][:, f], z[f"f{f}__tp"].astype(np.float32))
+        assert list(out[f].columns[-2:]) == ["Q_calculated_offline_dL", "_calculated_offline_dL"]   # the reference's names
+        np.testing.assert_allclose(out[f]["Q_calculated_offline_dL"].to_numpy(), z[f"f{f}__Q_calculated_offline_dL"],
+                                   rtol=1e-5, atol=1e-4)   # float32 controls vs the reference's float64 bookkeeping
+        np.testing.assert_allclose(out[f]["_calculated_offline_dL"].to_numpy(), z[f"f{f}___calculated_offline_dL"],
+                                   rtol=0, atol=1e-7)
+    with pytest.raises(ValueError):
+        RL.add_control_along_trajectories(dfs, dict(state_components=STATE, environment_attributes_dict={
+            "L": "L_differentiate_", "target_position": "target_position_integrate_-0.1_0.1_"}), relabeller=Recorder(E))
