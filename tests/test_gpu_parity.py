@@ -401,3 +401,34 @@ def test_rollout_pair_kernel_bit_identical(integ, shared_s0):
         calm = np.abs(s0[rows, 1]) < 50
         e = traj_err(outs[0][1][rows].cpu().numpy()[calm], ref[calm])
         assert max(e.values()) < 5e-5, e
+
+
+@pytest.mark.parametrize("K_total,parts", [(65536, 2), (65536, 4), (4000, 2)])
+def test_sharded_solve_on_one_device_matches_the_whole(K_total, parts):
+    """K split over `parts` handles in shard mode (what ShardedMPPI does across ranks), partial records concatenated
+    (the all-gather) and merged by cps_mppi_finalize: same control as one handle over all K.  Slices of >= 16384
+    rollouts take the packed two-per-thread kernel, smaller ones the one-per-thread kernel."""
+    L = _L()
+    T = 60
+    g = torch.Generator(device="cuda").manual_seed(9)
+    whole = _engine(K_total, T, integrator="ODE", cost="quadratic_boundary_grad_minimal")
+    noise = torch.randn((whole.n_ind, K_total), generator=g, device="cuda")
+    s = cuda(np.array([3.0, 0.2, np.cos(3.0), np.sin(3.0), 0.01, 0.0]))
+    whole.mppi_reset(0.0)
+    u_ref = float(whole.mppi_step(s, noise, L.TIME_MAJOR, 0.1).cpu()[0])
+    un_ref = whole.get_u_nom()
+    Kl = K_total // parts
+    engines, recs = [], []
+    for p in range(parts):
+        e = _engine(Kl, T, integrator="ODE", cost="quadratic_boundary_grad_minimal")
+        buf = torch.zeros(e.partial_size(), device="cuda")
+        e.set_shard(buf)
+        e.mppi_reset(0.0)
+        e.mppi_step(s, noise[:, p * Kl:(p + 1) * Kl].contiguous(), L.TIME_MAJOR, 0.1)
+        engines.append(e)
+        recs.append(buf)
+    gathered = torch.cat(recs)
+    for e in engines:   # every "rank" merges the same records and ends with the same nominal inputs
+        u = float(e.mppi_finalize(gathered).cpu()[0])
+        assert abs(u - u_ref) < 2e-6
+        np.testing.assert_allclose(e.get_u_nom(), un_ref, rtol=0, atol=2e-6)
