@@ -13,6 +13,7 @@
 //   vectors and u = elite_Q[0, 0]).  CEM plans are built in the kernel from supplied standard-normal draws,
 //   Q = clip(mu + eps * std) with separately rounded multiply and add (tf.multiply, then +), so they are bit-equal to
 //   the reference's; nothing returns to the host between the outer iterations of one solve.
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
 #include <cmath>
@@ -46,6 +47,11 @@ struct PlanArgs {
     int *elite;                   // [K] scratch: indices of the elites, ascending (when they do not fit in shared memory)
     int elite_smem;               // capacity of the shared-memory elite list
     int defer_stats;              // CEM: stop after the elite list; cem_update_kernel computes the statistics
+    // multi-block selection (cem_select_kernel, K > CPS_CEM_MULTIBLOCK_MIN): grid-wide scratch, zero between launches
+    unsigned long long *g_best;   // [1] min over (key << 32 | index)
+    unsigned *g_kmax;             // [1]
+    unsigned *g_hist;             // [4][256]
+    int *g_cnt;                   // [2][grid] per-block counts: keys below the threshold / equal to it
     float *mu_out, *sd_out;       // CEM: updated distribution [T]
     float *u_out;                 // [1]
     int *best_out;                // [1] or null: index of the cheapest plan
@@ -59,6 +65,9 @@ struct PlanState {
     int cur;
     int *d_elite, *d_best;
     unsigned *d_ticket;
+    unsigned long long *d_gbest;
+    unsigned *d_gkmax, *d_ghist;
+    int *d_gcnt;
     int configured_cem;
 };
 
@@ -300,6 +309,166 @@ __device__ __forceinline__ void plan_select(const PlanArgs &a, const float *s_mu
     if (tid == 0) *a.u_out = cem_plan_value(s_mu[0], a.Q[(long long)best_idx * a.qs_k], s_sd[0], a.lo, a.hi);
 }
 
+// Selection over many plans (K > CPS_CEM_MULTIBLOCK_MIN) by the whole grid: one block per SM, launched cooperatively, each
+// owning a contiguous slice of the costs; grid-wide steps are separated by grid.sync().  Same result as plan_select
+// (cheapest plan with the lowest index; the best_k smallest costs with ties in index order; elite list ascending); the
+// statistics follow in cem_update_kernel.  A single block needs ~125 us for 65 536 costs (instruction latency, 2 warps
+// per scheduler); spread over 148 SMs every step is a few hundred keys per block.
+#define CPS_CEM_MULTIBLOCK_MIN 8192
+__global__ void __launch_bounds__(256) cem_select_kernel(const __grid_constant__ PlanArgs a) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    __shared__ unsigned s_hist[256];
+    __shared__ unsigned s_prefix, s_remaining;
+    __shared__ int s_w[8];
+    __shared__ unsigned long long s_bestw[8];
+    __shared__ unsigned s_maxw[8];
+    __shared__ int s_base;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nt = blockDim.x, nwarps = nt >> 5;
+    const int K = a.K, G = gridDim.x, b = blockIdx.x;
+    const int per = ((K + G - 1) / G + 7) & ~7;            // slice length, a multiple of 8
+    const int lo = min(b * per, K), hi = min(lo + per, K);  // this block's costs [lo, hi)
+    const int bk = min(a.best_k, K);
+
+    // ---- grid minimum (with index) and maximum key ------------------------------------------------------------------------
+    unsigned long long best = ~0ull;
+    unsigned kmax = 0u;
+    for (int i = lo + tid; i < hi; i += nt) {
+        const unsigned key = order_key(__ldcg(a.J + i));
+        const unsigned long long c = ((unsigned long long)key << 32) | (unsigned)i;
+        best = c < best ? c : best;
+        kmax = max(kmax, key);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long n = __shfl_xor_sync(0xffffffffu, best, o);
+        best = n < best ? n : best;
+        kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+    }
+    if (lane == 0) { s_bestw[warp] = best; s_maxw[warp] = kmax; }
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < nwarps; ++w) { best = s_bestw[w] < best ? s_bestw[w] : best; kmax = max(kmax, s_maxw[w]); }
+        if (lo < hi) { atomicMin(a.g_best, best); atomicMax(a.g_kmax, kmax); }
+    }
+    grid.sync();
+    best = __ldcg(a.g_best);
+    kmax = __ldcg(a.g_kmax);
+    const int best_idx = (int)(best & 0xFFFFFFFFull);
+    const unsigned kmin = (unsigned)(best >> 32);
+
+    // ---- radix select over the bits in which the keys differ (every block reaches the same prefix) -----------------------------
+    int hbits = 32 - __clz((int)(kmin ^ kmax));
+    unsigned prefix = (hbits >= 32) ? 0u : (kmin & ~((1u << hbits) - 1u));
+    unsigned remaining = (unsigned)bk;
+    int pass = 0;
+    while (hbits > 0) {
+        const int w = min(8, hbits), shift = hbits - w;
+        const unsigned mask = (hbits >= 32) ? 0u : ~((1u << hbits) - 1u), digit = (1u << w) - 1u;
+        for (int q = tid; q < 256; q += nt) s_hist[q] = 0u;
+        __syncthreads();
+        for (int i = lo + tid; i < hi; i += nt) {
+            const unsigned key = order_key(__ldcg(a.J + i));
+            if ((key & mask) == prefix) atomicAdd(&s_hist[(key >> shift) & digit], 1u);
+        }
+        __syncthreads();
+        unsigned *gh = a.g_hist + pass * 256;
+        for (int q = tid; q < 256; q += nt)
+            if (s_hist[q]) atomicAdd(gh + q, s_hist[q]);
+        grid.sync();
+        if (warp == 0) {   // every block finds the bin of rank `remaining` in the merged histogram
+            unsigned c[8], mine = 0u;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { c[j] = __ldcg(gh + lane * 8 + j); mine += c[j]; }
+            unsigned incl = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned n = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += n;
+            }
+            const unsigned before = incl - mine;
+            const unsigned hit = __ballot_sync(0xffffffffu, incl >= remaining);
+            if (lane == __ffs(hit) - 1) {
+                unsigned cum = before;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (cum + c[j] >= remaining) { s_prefix = prefix | ((unsigned)(lane * 8 + j) << shift); s_remaining = remaining - cum; break; }
+                    cum += c[j];
+                }
+            }
+        }
+        __syncthreads();
+        prefix = s_prefix;
+        remaining = s_remaining;
+        hbits = shift;
+        ++pass;
+        __syncthreads();
+    }
+    const unsigned kth = prefix;
+    const int ties_wanted = (int)remaining;
+
+    // ---- per-block counts, then the ordered compaction at the block's offset ------------------------------------------------
+    int n_less = 0, n_eq = 0;
+    for (int i = lo + tid; i < hi; i += nt) {
+        const unsigned key = order_key(__ldcg(a.J + i));
+        n_less += key < kth ? 1 : 0;
+        n_eq += key == kth ? 1 : 0;
+    }
+    int tot_less, tot_eq;
+    block_excl_scan(n_less, s_w, tot_less);
+    block_excl_scan(n_eq, s_w, tot_eq);
+    if (tid == 0) { a.g_cnt[b] = tot_less; a.g_cnt[G + b] = tot_eq; }
+    grid.sync();
+    if (tid == 0) {   // elites and ties in the blocks before this one
+        int el = 0, eq = 0;
+        for (int q = 0; q < b; ++q) {
+            const int l = __ldcg(a.g_cnt + q), e = __ldcg(a.g_cnt + G + q);
+            el += l + max(0, min(e, ties_wanted - eq));
+            eq += e;
+        }
+        s_base = el;
+        s_remaining = (unsigned)eq;
+    }
+    __syncthreads();
+    int n_el_before = s_base, n_eq_before = (int)s_remaining;
+    for (int base = lo; base < hi; base += nt * 8) {   // each thread owns 8 consecutive plans of the chunk
+        const int i0 = base + tid * 8;
+        unsigned key[8];
+        int eq = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            key[j] = order_key(__ldcg(a.J + min(i0 + j, K - 1)));
+            eq += (i0 + j < hi && key[j] == kth) ? 1 : 0;
+        }
+        int teq, tel;
+        int eq_rank = n_eq_before + block_excl_scan(eq, s_w, teq);
+        unsigned take = 0u;
+        int el = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const bool in = i0 + j < hi;
+            const bool is_eq = in && key[j] == kth;
+            if (in && (key[j] < kth || (is_eq && eq_rank < ties_wanted))) { take |= 1u << j; ++el; }
+            eq_rank += is_eq ? 1 : 0;
+        }
+        int pos = n_el_before + block_excl_scan(el, s_w, tel);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (take & (1u << j)) a.elite[pos++] = i0 + j;
+        n_eq_before += teq;
+        n_el_before += tel;
+    }
+    if (b == 0) {   // outputs, and the scratch goes back to its resting state (all blocks are past their last read of it)
+        if (tid == 0) {
+            if (a.best_out) *a.best_out = best_idx;
+            if (a.last_iter) *a.u_out = cem_plan_value(a.mu[0], a.Q[(long long)best_idx * a.qs_k], a.sd[0], a.lo, a.hi);
+            *a.g_best = ~0ull;
+            *a.g_kmax = 0u;
+        }
+        for (int q = tid; q < 4 * 256; q += nt) a.g_hist[q] = 0u;
+    }
+}
+
 // CEM statistics for large elite sets: one block per horizon step (plan_select leaves the elite list in a.elite).  Reads
 // the distribution the plans were sampled from (a.mu, a.sd) and writes the updated one to the OTHER buffer
 // (a.mu_out, a.sd_out), so blocks do not race on the shifted write of the last iteration.
@@ -426,6 +595,7 @@ void cps_plan_free(cps_handle *h) {
     PlanState *P = h->plan;
     if (!P) return;
     cudaFree(P->d_J); cudaFree(P->d_mu); cudaFree(P->d_sd); cudaFree(P->d_elite); cudaFree(P->d_best); cudaFree(P->d_ticket);
+    cudaFree(P->d_gbest); cudaFree(P->d_gkmax); cudaFree(P->d_ghist); cudaFree(P->d_gcnt);
     delete P;
     h->plan = nullptr;
 }
@@ -442,11 +612,19 @@ static int plan_state(cps_handle *h, PlanState **out) {
     if (e == cudaSuccess) e = cudaMalloc(&P->d_elite, sizeof(int) * K);
     if (e == cudaSuccess) e = cudaMalloc(&P->d_best, sizeof(int));
     if (e == cudaSuccess) e = cudaMalloc(&P->d_ticket, sizeof(unsigned));
+    if (e == cudaSuccess) e = cudaMalloc(&P->d_gbest, sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc(&P->d_gkmax, sizeof(unsigned));
+    if (e == cudaSuccess) e = cudaMalloc(&P->d_ghist, sizeof(unsigned) * 4 * 256);
+    if (e == cudaSuccess) e = cudaMalloc(&P->d_gcnt, sizeof(int) * 2 * 1024);
+    if (e == cudaSuccess) e = cudaMemset(P->d_gbest, 0xFF, sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemset(P->d_gkmax, 0, sizeof(unsigned));
+    if (e == cudaSuccess) e = cudaMemset(P->d_ghist, 0, sizeof(unsigned) * 4 * 256);
     if (e == cudaSuccess) e = cudaMemset(P->d_ticket, 0, sizeof(unsigned));
     if (e == cudaSuccess) e = cudaMemset(P->d_mu, 0, sizeof(float) * 2 * T);
     if (e == cudaSuccess) e = cudaMemset(P->d_sd, 0, sizeof(float) * 2 * T);
     if (e != cudaSuccess) {   // nothing half-built stays attached to the handle
         cudaFree(P->d_J); cudaFree(P->d_mu); cudaFree(P->d_sd); cudaFree(P->d_elite); cudaFree(P->d_best); cudaFree(P->d_ticket);
+        cudaFree(P->d_gbest); cudaFree(P->d_gkmax); cudaFree(P->d_ghist); cudaFree(P->d_gcnt);
         delete P;
         return fail(h, CPS_ERR_CUDA, "cps_plan: allocating the planner scratch: %s", cudaGetErrorString(e));
     }
@@ -622,6 +800,22 @@ extern "C" int cps_cem_step(cps_handle *h, const float *s_dev, const float *eps_
     // one block per horizon step
     a.defer_stats = ((long long)P->best_k * T > 2048) ? 1 : 0;
     a.elite_smem = a.defer_stats ? 0 : P->best_k;   // the update kernel reads the list from global memory
+    // many plans: rollouts + costs without a selecting block (the latency geometry of cps_plan_cost), then the selection by
+    // the whole grid (cem_select_kernel, cooperative launch, one block per SM) and the statistics kernel
+    const bool multi = K > CPS_CEM_MULTIBLOCK_MIN;
+    int sel_grid = 1;
+    if (multi) {
+        int dev = 0, sms = 148, coop = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+        if (!coop) return fail(h, CPS_ERR_UNSUPPORTED, "cps_cem_step: the device does not support cooperative launches");
+        sel_grid = sms < 1024 ? sms : 1024;
+        plan_geometry(K, false, grid, block);
+        a.select = SELECT_NONE;
+        a.defer_stats = 1;
+        a.g_best = P->d_gbest; a.g_kmax = P->d_gkmax; a.g_hist = P->d_ghist; a.g_cnt = P->d_gcnt;
+    }
     for (int it = 0; it < n_iterations; ++it) {
         a.Q = eps_dev + (size_t)it * K * T;
         a.last_iter = (it == n_iterations - 1) ? 1 : 0;
@@ -630,6 +824,11 @@ extern "C" int cps_cem_step(cps_handle *h, const float *s_dev, const float *eps_
         a.mu_out = P->d_mu + (size_t)(1 - P->cur) * T; a.sd_out = P->d_sd + (size_t)(1 - P->cur) * T;
         fn<<<grid, block, smem, h->stream>>>(a);
         h->launches += 1;
+        if (multi) {
+            void *args[] = {(void *)&a};
+            CUDA_TRY(h, cudaLaunchCooperativeKernel((const void *)cem_select_kernel, dim3(sel_grid), dim3(256), args, 0, h->stream));
+            h->launches += 1;
+        }
         if (a.defer_stats) {
             cem_update_kernel<<<T, 256, 0, h->stream>>>(a);
             h->launches += 1;

@@ -358,7 +358,8 @@ int cps_plan_random_action_host(cps_handle *h, const float *s_host, const float 
 /* optimizer_cem_tf (:12-117).  cps_cem_configure: cem_best_k, cem_initial_action_stdev, cem_stdev_min; allocates the
  * sampling distribution (mean, stdev per horizon step) and resets it as optimizer_reset does (:112-116).
  * cps_cem_step: n_iterations outer iterations (cem_outer_it, or warmup_iterations on the first call), one launch each
- * (two when cem_best_k * T > 2048: the elite statistics then run as a second kernel with one block per step):
+ * (two when cem_best_k * T > 2048: the elite statistics then run as a second kernel with one block per step; three
+ * above 8192 rollouts: the selection then runs as a cooperative kernel with one block per SM):
  * Q = clip(mean + eps * stdev), predict_and_cost, the cem_best_k cheapest plans (ties to the lowest index), mean and
  * population stdev of the elites per step (update_distribution, :63-83); after the last iteration stdev is clipped to
  * [cem_stdev_min, 1e8], both vectors are shifted by one step (tail: initial stdev, mid-range mean) and
