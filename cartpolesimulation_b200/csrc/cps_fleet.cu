@@ -55,6 +55,7 @@ struct FleetArgs {
     float k, m_cart, g, J_fric, M_fric, u_max;  // physical constants for the device-side fold of (L, m_pole)
     float m_pole_fixed;         // ODE_v0 takes only L from the variable parameters
     float L_default, mp_default;  // the handle's L / m_pole "for controller" when only one of the arrays is given
+    double h_step;                // substep dt / n in double, for the device-side fold
 };
 
 // fold_ode (cps_lib.cu) on the device, same double-precision expressions: the controller's model constants for a
@@ -74,6 +75,10 @@ __device__ __forceinline__ void fold_ode_device(const FleetArgs &a, double L, do
     o.d2 = (float)(1.0 / (kp1 * Lh));
     o.d3 = (float)(J / (mp * Lh * kp1 * Lh));
     o.bounce = (float)(2.0 / (0.5 * L));
+    const double hh = a.h_step;
+    o.hd1 = (float)(hh * (g / (kp1 * Lh)));
+    o.hd2 = (float)(hh * (1.0 / (kp1 * Lh)));
+    o.hd3 = (float)(hh * (J / (mp * Lh * kp1 * Lh)));
 }
 
 // ---- Philox4x32-10 (Salmon et al., SC'11), the counter-based generator torch / TF / cuRAND also use ---------------------
@@ -437,6 +442,7 @@ static int fleet_launch(cps_handle *h, const char *who, int n_periods, const flo
     a.k = P.k; a.m_cart = P.m_cart; a.g = P.g; a.J_fric = P.J_fric; a.M_fric = P.M_fric; a.u_max = P.u_max;
     a.m_pole_fixed = h->phys[CPS_PH_M_POLE];
     a.L_default = h->L_var; a.mp_default = h->m_pole_var;
+    a.h_step = (double)h->cfg.dt / (double)h->cfg.substeps;
     if (F->pair && noise_dev && ((uintptr_t)noise_dev % 8) != 0)
         return fail(h, CPS_ERR_INVALID, "%s: supplied noise must be 8-byte aligned", who);
     fleet_fn fn = pick_fleet(h->cfg.integrator, h->cfg.cost_id, philox, F->pair != 0);

@@ -171,6 +171,12 @@ static void fold_ode(cps_handle *h) {
     o.d3 = (float)(J / (mp * Lh * kp1 * Lh));
     o.u_scale = (float)(kp1 * umax);
     o.h = (float)((double)h->cfg.dt / (double)h->cfg.substeps);
+    {   // rotation substeps: the step folded into the angular-acceleration constants (ode_rhs_w)
+        const double hh = (double)h->cfg.dt / (double)h->cfg.substeps;
+        o.hd1 = (float)(hh * (g / (kp1 * Lh)));
+        o.hd2 = (float)(hh * (1.0 / (kp1 * Lh)));
+        o.hd3 = (float)(hh * (J / (mp * Lh * kp1 * Lh)));
+    }
     o.thl = h->phys[CPS_PH_TRACK_HALF_LENGTH];
     o.bounce = (float)(2.0 / (0.5 * L));
     o.n = h->cfg.substeps;
