@@ -32,9 +32,9 @@ if REPO not in sys.path:
     sys.path.insert(0, REPO)
 
 FLOP_PER_STATE_STEP = 32.0   # 24 (ODE rhs) + 8 (integrator), FMA = 2
-# FMA-pipe lane operations the pair kernel executes per state-step (ncu instruction mix): 30 packed in the
-# substep loop + ~2.6 scalar per-control-step work (sincosf resync, compensated angle) + ~1.5 IMAD.MOV
-FP32_LANE_OPS_PER_STATE_STEP = 34.5
+# FMA-pipe lane operations the pair kernel executes per state-step (ncu instruction mix): 29 packed in the
+# substep loop + ~2.6 scalar per-control-step work (sincosf resync, compensated angle) + ~2 IMAD.MOV
+FP32_LANE_OPS_PER_STATE_STEP = 33.5
 MUFU_PER_STATE_STEP = 3.0    # rcp + sin + cos when the MUFU path is used; 1 (rcp) otherwise
 B_DEFAULT, T_DEFAULT, N_SUB, DT = 1 << 20, 50, 10, 0.02
 METRIC = "rollout_state_steps_per_sec"
@@ -643,7 +643,7 @@ def run_ours(args):
                               "achieved_frac_of_lanes": rate_1gpu * FP32_LANE_OPS_PER_STATE_STEP / (fp32_peak * 1e12 / 2.0)
                               if fp32_peak else None,
                               "note": "FMA-pipe lane operations executed per state-step (FMUL/FADD occupy a lane like an FMA): "
-                                      "30 in the substep loop + ~4.5 amortised per-control-step work; peak = measured FFMA "
+                                      "29 in the substep loop + ~4.5 amortised per-control-step work and moves; peak = measured FFMA "
                                       "lane rate (roofline.peak / 2)"},
                 "ncu": ncu_view,
                 "mufu": {"achieved_gops": rate_1gpu * (MUFU_PER_STATE_STEP if args.fast_sincos else 1.0) / 1e9,
