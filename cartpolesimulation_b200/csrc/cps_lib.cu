@@ -572,7 +572,8 @@ extern "C" int cps_mppi_step(cps_handle *h, const float *s_dev, const float *noi
     io.partials = h->d_partials; io.ticket = h->d_ticket; io.nonfinite = h->d_nonfinite;
     io.shard_out = h->shard ? h->shard_out : nullptr;
     // Large K is issue-bound, not latency-bound: two rollouts per thread in packed FP32 (same arithmetic per rollout; the
-    // block sums associate pairs first).  Needs the kernel's native noise order and no per-rollout logging outputs.
+    // block sums associate pairs first).  Measured (tools/ab_pairs.py): 10 % faster at K = 65536, 10-15 % SLOWER at 16384
+    // and 32768, where the solve is still bound by the latency of one rollout's dependence chain.  Needs the kernel's native noise order and no per-rollout logging outputs.
     const bool pairs = K >= CPS_MPPI_PAIR_MIN_ROLLOUTS && (K % 2) == 0 && sc_mode(h->cfg.flags) == SC_ROTATE &&
                        !(h->cfg.flags & (CPS_FLAG_FAST_DIV | CPS_FLAG_NO_PAIRS)) && h->cfg.noise_mode == CPS_NOISE_INDUCING &&
                        noise_layout == CPS_TIME_MAJOR && ((uintptr_t)noise_dev % 8) == 0 && !traj_out_dev && !u_run_out_dev;

@@ -17,6 +17,7 @@
 #include <cuda_runtime.h>
 
 #include <cmath>
+#include <cstdint>
 #include <cstring>
 #include <new>
 
@@ -574,6 +575,84 @@ __global__ void __launch_bounds__(256, 4) plan_kernel(const __grid_constant__ Pl
     if (tid == 0) *a.ticket = 0u;  // re-arm
 }
 
+// Many plans, no selecting block, time-major plans: two plans per thread (k, k + 1) in packed FP32, as mppi_solve_block2
+// does for the MPPI solve.  Per plan the arithmetic is that of plan_kernel, so the costs are bit-identical (tested).
+#define CPS_PLAN_PAIR_MIN 65536   /* measured: at 16384 and 32768 plans one per thread is 10-25 % faster (latency regime) */
+template <int INTEG, int COST, int MODE>
+__global__ void __launch_bounds__(128, 4) plan_pair_kernel(const __grid_constant__ PlanArgs a) {
+    extern __shared__ float smem[];   // PLAN_CEM: mu[T], sd[T]
+    const int tid = threadIdx.x, T = a.T;
+    float *s_mu = smem, *s_sd = smem + T;
+    if (MODE == PLAN_CEM) {
+        for (int t = tid; t < T; t += blockDim.x) { s_mu[t] = a.mu[t]; s_sd[t] = a.sd[t]; }
+        __syncthreads();
+    }
+    const int k = 2 * (blockIdx.x * blockDim.x + tid);   // K is even: both plans active or both not
+    if (k >= a.K) return;
+    const State z1 = load_state(a.use_inline ? a.s_inline : a.s);
+    State2 z = join_states(z1, z1);
+    const OdeParams ode = pin_params(a.ode, z1.th);
+    float cc0 = cosf(z1.th), cc1 = cc0;
+    const float *q = a.Q + k;                            // qs_k == 1
+    float *qo = (MODE == PLAN_CEM && a.Q_out) ? a.Q_out + k : nullptr;
+    float Ja0 = 0.0f, Ja1 = 0.0f, up0 = a.u_prev, up1 = a.u_prev;
+    float2 qn = *reinterpret_cast<const float2 *>(q);
+#pragma unroll 1
+    for (int t = 0; t < T; ++t) {
+        float u0 = qn.x, u1 = qn.y;
+        if (t + 1 < T) qn = *reinterpret_cast<const float2 *>(q + (long long)(t + 1) * a.qs_t);
+        if (MODE == PLAN_CEM) {
+            u0 = cem_plan_value(s_mu[t], u0, s_sd[t], a.lo, a.hi);
+            u1 = cem_plan_value(s_mu[t], u1, s_sd[t], a.lo, a.hi);
+            if (qo) *reinterpret_cast<float2 *>(qo + (long long)t * a.qs_t) = make_float2(u0, u1);
+        }
+        if (COST != COST_NONE) {
+            float st0 = stage_cost<COST>(a.cost, cc0, lo(z.w), lo(z.x), u0, up0);
+            float st1 = stage_cost<COST>(a.cost, cc1, hi(z.w), hi(z.x), u1, up1);
+            if (COST == COST_DEFAULT || COST == COST_QB) { st0 -= a.cost.max_cost; st1 -= a.cost.max_cost; }
+            Ja0 += st0; Ja1 += st1;
+        }
+        control_step2<INTEG, false>(ode, z, f2(u0, u1));
+        cc0 = lo(z.c); cc1 = hi(z.c);
+        up0 = u0; up1 = u1;
+    }
+    if (COST != COST_NONE) {
+        Ja0 += terminal_cost<COST>(a.cost, lo(z.th), lo(z.x));
+        Ja1 += terminal_cost<COST>(a.cost, hi(z.th), hi(z.x));
+    }
+    const float J0 = Ja0 * a.inv_T1, J1 = Ja1 * a.inv_T1;
+    a.J[k] = J0; a.J[k + 1] = J1;
+    if (!isfinite(J0)) atomicAdd(a.nonfinite, 1);
+    if (!isfinite(J1)) atomicAdd(a.nonfinite, 1);
+}
+
+template <int INTEG, int MODE>
+static void (*pick_plan_pair2(int cost))(const PlanArgs) {
+    switch (cost) {
+    case CPS_COST_DEFAULT: return plan_pair_kernel<INTEG, COST_DEFAULT, MODE>;
+    case CPS_COST_QUADRATIC_BOUNDARY: return plan_pair_kernel<INTEG, COST_QB, MODE>;
+    case CPS_COST_QB_GRAD_MINIMAL: return plan_pair_kernel<INTEG, COST_GRADMIN, MODE>;
+    case CPS_COST_QB_GRAD: return plan_pair_kernel<INTEG, COST_GRAD, MODE>;
+    default: return nullptr;
+    }
+}
+static void (*pick_plan_pair(int integ, int cost, int mode))(const PlanArgs) {
+    if (integ == CPS_EULER_V0) return mode == PLAN_CEM ? pick_plan_pair2<0, PLAN_CEM>(cost) : pick_plan_pair2<0, PLAN_Q>(cost);
+    return mode == PLAN_CEM ? pick_plan_pair2<1, PLAN_CEM>(cost) : pick_plan_pair2<1, PLAN_Q>(cost);
+}
+// true when a launch described by `a` (select == SELECT_NONE) can take the packed kernel
+static bool plan_pair_ok(const cps_handle *h, const PlanArgs &a) {
+    return a.K >= CPS_PLAN_PAIR_MIN && (a.K % 2) == 0 && a.qs_k == 1 && (a.qs_t % 2) == 0 && !a.traj_out && a.J &&
+           !(h->cfg.flags & CPS_FLAG_NO_PAIRS) && ((uintptr_t)a.Q % 8) == 0 && (!a.Q_out || ((uintptr_t)a.Q_out % 8) == 0);
+}
+static void plan_pair_launch(cps_handle *h, const PlanArgs &a, int mode) {
+    const long long threads = a.K / 2;
+    const int block = threads <= 148 * 32 * 4 ? 32 : (threads <= 148 * 64 * 8 ? 64 : 128);
+    const int grid = (int)((threads + block - 1) / block);
+    const size_t smem = mode == PLAN_CEM ? sizeof(float) * 2 * (size_t)a.T : 0;
+    pick_plan_pair(h->cfg.integrator, h->cfg.cost_id, mode)<<<grid, block, smem, h->stream>>>(a);
+}
+
 // ---- host side ---------------------------------------------------------------------------------------------------------
 typedef void (*plan_fn)(const PlanArgs);
 template <int INTEG, int MODE>
@@ -682,10 +761,14 @@ extern "C" int cps_plan_cost(cps_handle *h, const float *s_dev, const float *Q_d
     if (traj_layout == CPS_TIME_MAJOR) { a.ts_k = 1; a.ts_t = 6LL * K; a.ts_c = K; }
     else { a.ts_k = (T + 1) * 6LL; a.ts_t = 6; a.ts_c = 1; }
     a.select = SELECT_NONE;
-    int grid, block;
-    plan_geometry(K, false, grid, block);
-    plan_fn fn = pick_plan(h->cfg.integrator, h->cfg.cost_id, PLAN_Q);
-    fn<<<grid, block, 0, h->stream>>>(a);
+    if (plan_pair_ok(h, a)) {
+        plan_pair_launch(h, a, PLAN_Q);
+    } else {
+        int grid, block;
+        plan_geometry(K, false, grid, block);
+        plan_fn fn = pick_plan(h->cfg.integrator, h->cfg.cost_id, PLAN_Q);
+        fn<<<grid, block, 0, h->stream>>>(a);
+    }
     h->launches += 1;
     CUDA_TRY(h, cudaGetLastError());
     return CPS_OK;
@@ -822,7 +905,8 @@ extern "C" int cps_cem_step(cps_handle *h, const float *s_dev, const float *eps_
         a.Q_out = a.last_iter ? Q_out_dev : nullptr;   // Q_logged is the last iteration's plans (cem_tf.py:93)
         a.mu = P->d_mu + (size_t)P->cur * T; a.sd = P->d_sd + (size_t)P->cur * T;
         a.mu_out = P->d_mu + (size_t)(1 - P->cur) * T; a.sd_out = P->d_sd + (size_t)(1 - P->cur) * T;
-        fn<<<grid, block, smem, h->stream>>>(a);
+        if (multi && plan_pair_ok(h, a) && sizeof(float) * 2 * (size_t)T <= 48 * 1024) plan_pair_launch(h, a, PLAN_CEM);
+        else fn<<<grid, block, smem, h->stream>>>(a);
         h->launches += 1;
         if (multi) {
             void *args[] = {(void *)&a};

@@ -83,7 +83,7 @@ typedef enum cps_layout { CPS_ROLLOUT_MAJOR = 0, CPS_TIME_MAJOR = 1 } cps_layout
 #define CPS_FLAG_NO_PAIRS 0x40u         /* rollouts, large-K solves, fleets: never use the two-per-thread packed-FP32 kernels
                                            (per rollout they execute the same arithmetic; the flag exists for A/B timing) */
 #define CPS_PAIR_MIN_BATCH 262144       /* smallest batch the packed-pair rollout kernel is used for */
-#define CPS_MPPI_PAIR_MIN_ROLLOUTS 16384 /* cps_mppi_step: from this K on (even K, native noise order, no logging outputs)
+#define CPS_MPPI_PAIR_MIN_ROLLOUTS 65536 /* cps_mppi_step: from this K on (even K, native noise order, no logging outputs)
                                            the solve runs two rollouts per thread in packed FP32 */
 #define CPS_FLAG_NET_TENSOR_CORES 0x10u /* neural predictor: force the tcgen05 tensor-core kernel (2 x 64 GRU only) */
 #define CPS_FLAG_NET_FP32 0x20u         /* neural predictor: force the FP32 CUDA-core kernel (default: by batch size) */

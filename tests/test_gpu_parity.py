@@ -406,8 +406,8 @@ def test_rollout_pair_kernel_bit_identical(integ, shared_s0):
 @pytest.mark.parametrize("K_total,parts", [(65536, 2), (65536, 4), (4000, 2)])
 def test_sharded_solve_on_one_device_matches_the_whole(K_total, parts):
     """K split over `parts` handles in shard mode (what ShardedMPPI does across ranks), partial records concatenated
-    (the all-gather) and merged by cps_mppi_finalize: same control as one handle over all K.  Slices of >= 16384
-    rollouts take the packed two-per-thread kernel, smaller ones the one-per-thread kernel."""
+    (the all-gather) and merged by cps_mppi_finalize: same control as one handle over all K.  The whole (K = 65536) takes the packed
+    two-per-thread kernel, the slices the one-per-thread kernel."""
     L = _L()
     T = 60
     g = torch.Generator(device="cuda").manual_seed(9)

@@ -311,3 +311,33 @@ def test_cem_all_costs_equal(K):
     mu, sd = eng.cem_get_distribution()
     assert (mu == 0.0).all()
     np.testing.assert_array_equal(sd, np.r_[np.full(T - 1, 0.02, np.float32), np.float32(0.5)])
+
+
+def test_packed_planner_kernels_match_the_one_per_thread_kernels():
+    """From 65536 time-major plans on, rollouts + costs run two plans per thread in packed FP32: every cost is
+    bit-identical to the one-plan-per-thread kernel's (reached here through the rollout-major layout), for the plain
+    evaluation and for a CEM solve (sampled plans, costs, distribution and control)."""
+    from cartpolesimulation_b200 import _lib as L
+    rng = np.random.default_rng(21)
+    K, T = 65536, 40
+    s = torch.from_numpy(_hanging()).cuda()
+    for integ in ("ODE", "ODE_v0"):
+        eng = _engine(K, T, integ, "quadratic_boundary", 0.02, 1.0)
+        Q = torch.from_numpy(rng.uniform(-1, 1, (K, T)).astype(np.float32)).cuda()
+        J_one, _ = eng.plan_cost(s, Q, L.ROLLOUT_MAJOR, 0.3)
+        J_two, _ = eng.plan_cost(s, Q.t().contiguous(), L.TIME_MAJOR, 0.3)
+        assert torch.equal(J_one, J_two)
+    eps = rng.standard_normal((2, K, T)).astype(np.float32)
+    res = []
+    for layout in (L.ROLLOUT_MAJOR, L.TIME_MAJOR):
+        eng = _engine(K, T, "ODE", "quadratic_boundary_grad_minimal")
+        eng.cem_configure(500, 0.5, 0.01)
+        e = eps if layout == L.ROLLOUT_MAJOR else np.ascontiguousarray(eps.transpose(0, 2, 1))
+        Qo = torch.empty((K, T) if layout == L.ROLLOUT_MAJOR else (T, K), device="cuda")
+        J = torch.empty(K, device="cuda")
+        u = float(eng.cem_step(s, torch.from_numpy(e).cuda(), layout, 0.0, Q_out=Qo, J_out=J).cpu()[0])
+        res.append((u, J.cpu().numpy(), (Qo if layout == L.ROLLOUT_MAJOR else Qo.t()).cpu().numpy()) + eng.cem_get_distribution())
+    a, b = res
+    assert a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    np.testing.assert_array_equal(a[3], b[3])
+    np.testing.assert_array_equal(a[4], b[4])
