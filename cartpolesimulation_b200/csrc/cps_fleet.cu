@@ -325,8 +325,10 @@ extern "C" int cps_fleet_create(cps_handle *h, const cps_fleet_config *cfg) {
     F->cfg = *cfg;
     F->E = cfg->n_experiments;
     const int K = h->cfg.num_rollouts, T = h->cfg.horizon;
-    // fleets are throughput work: two rollouts per thread in packed FP32 whenever K is even (mppi_solve_block2)
-    F->pair = (K % 2 == 0 && K >= 64 && !(h->cfg.flags & CPS_FLAG_NO_PAIRS)) ? 1 : 0;
+    // large fleets are throughput work: two rollouts per thread in packed FP32 (mppi_solve_block2) from 65536 rollouts
+    // per launch on, as for a single solve (tools/ab_fleet_pairs.py: 14 % faster at E = 256 and 1024, 30 % slower at E <= 16)
+    F->pair = (K % 2 == 0 && K >= 64 && (long long)cfg->n_experiments * K >= CPS_MPPI_PAIR_MIN_ROLLOUTS &&
+               !(h->cfg.flags & CPS_FLAG_NO_PAIRS)) ? 1 : 0;
     const int threads = F->pair ? K / 2 : K;   // threads per experiment
     F->block = threads >= 256 ? 256 : ((threads + 31) / 32) * 32;
     F->bpe = (threads + F->block - 1) / F->block;

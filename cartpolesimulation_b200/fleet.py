@@ -167,11 +167,11 @@ class Fleet:
     def __init__(self, n_experiments: int, num_rollouts: int = 2000, horizon: int = 50, dt: float = 0.02,
                  substeps: int = 10, integrator: str = "ODE", cost: str = "quadratic_boundary_grad_minimal",
                  interp_period: int = 10, device: int | None = None, noise: str = "philox", seed: int = 0,
-                 experiment_offset: int = 0, dt_simulation: float = 0.002):
+                 experiment_offset: int = 0, dt_simulation: float = 0.002, no_pairs: bool = False):
         if noise not in ("philox", "supplied"):
             raise ValueError("noise must be 'philox' or 'supplied'")
         self.engine = Engine(num_rollouts, horizon, dt=dt, substeps=substeps, integrator=integrator, cost=cost,
-                             interp_period=interp_period, device=device)
+                             interp_period=interp_period, device=device, no_pairs=no_pairs)
         self.E, self.K, self.T = int(n_experiments), int(num_rollouts), int(horizon)
         self.n_ind, self.device = self.engine.n_ind, self.engine.device
         n_sim = int(round(dt / dt_simulation))
