@@ -37,10 +37,10 @@ class Relabeller:
     def __init__(self, n_files: int, num_rollouts: int = 2000, horizon: int = 50, dt: float = 0.02, substeps: int = 10,
                  integrator: str = "ODE", cost: str = "quadratic_boundary_grad_minimal", interp_period: int = 10,
                  device: int | None = None, noise: str = "philox", seed: int = 0, file_offset: int = 0,
-                 cost_config: dict | None = None, mppi: dict | None = None):
+                 cost_config: dict | None = None, mppi: dict | None = None, no_pairs: bool = False):
         self.fleet = Fleet(n_files, num_rollouts, horizon, dt=dt, substeps=substeps, integrator=integrator, cost=cost,
                            interp_period=interp_period, device=device, noise=noise, seed=seed,
-                           experiment_offset=file_offset)
+                           experiment_offset=file_offset, no_pairs=no_pairs)
         self.engine = self.fleet.engine
         self.E, self.K, self.T, self.n_ind, self.device = n_files, self.fleet.K, self.fleet.T, self.fleet.n_ind, self.fleet.device
         if cost_config is not None:

@@ -229,3 +229,34 @@ def test_fleet_errors():
     fl.close()
     with pytest.raises(NotImplementedError):
         Fleet(2, 64, 10, integrator="neural")
+
+
+@pytest.mark.parametrize("integ", ["ODE", "ODE_v0"])
+def test_packed_fleet_solve_matches_one_rollout_per_thread(integ):
+    """From 65536 rollouts per launch on the fleet's solve runs two rollouts per thread in packed FP32: per rollout the
+    same arithmetic (bit-identical costs), the control equal to summation order; closed loop and relabel mode."""
+    from cartpolesimulation_b200.fleet import Fleet, make_experiments
+    from cartpolesimulation_b200.relabel import Relabeller
+    E, K, T, P = 40, 2000, 30, 3
+    s0, tp, te = make_experiments(E, P, seed=3)
+    out = []
+    for no_pairs in (True, False):
+        fl = Fleet(E, K, T, integrator=integ, noise="philox", seed=7, device=0, no_pairs=no_pairs)
+        fl.reset(s0)
+        rec = torch.zeros((P, E, 16), device="cuda")
+        J = torch.zeros((P, E, K), device="cuda")
+        fl.run(P, torch.from_numpy(tp).cuda(), torch.from_numpy(te).cuda(), record=rec, J_out=J)
+        out.append((rec.cpu().numpy(), J.cpu().numpy(), fl.states()))
+        fl.close()
+    (r1, J1, s1), (r2, J2, s2) = out
+    np.testing.assert_array_equal(J1[0], J2[0])                       # first period: identical inputs -> identical costs
+    np.testing.assert_allclose(r2[..., 9], r1[..., 9], rtol=0, atol=5e-6)   # Q_calculated of every period
+    np.testing.assert_allclose(s2, s1, rtol=0, atol=2e-4)             # closed loop over three periods
+    rng = np.random.default_rng(1)
+    ang = rng.uniform(-np.pi, np.pi, (4, E))
+    st = np.stack([ang, rng.uniform(-3, 3, (4, E)), np.cos(ang), np.sin(ang), rng.uniform(-0.1, 0.1, (4, E)),
+                   rng.uniform(-0.3, 0.3, (4, E))], axis=2).astype(np.float32)
+    Lr = rng.uniform(0.25, 0.55, (4, E)).astype(np.float32)
+    q = [Relabeller(E, K, T, integrator=integ, noise="philox", seed=5, device=0, no_pairs=n).relabel(st, pole_length=Lr)
+         for n in (True, False)]
+    np.testing.assert_allclose(q[1], q[0], rtol=0, atol=5e-6)
