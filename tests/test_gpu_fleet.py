@@ -260,3 +260,29 @@ def test_packed_fleet_solve_matches_one_rollout_per_thread(integ):
     q = [Relabeller(E, K, T, integrator=integ, noise="philox", seed=5, device=0, no_pairs=n).relabel(st, pole_length=Lr)
          for n in (True, False)]
     np.testing.assert_allclose(q[1], q[0], rtol=0, atol=5e-6)
+
+
+def test_fleet_full_size_is_independent_of_the_sharding():
+    """BASELINE configs[4] size: 8192 experiments x (K = 2000, T = 50).  Size-independent property: the record rows of a
+    period do not depend on how the experiments are split over devices (in-kernel Philox streams are keyed by the global
+    experiment index) -- one fleet of 8192 against four fleets of 2048 with their offsets, bit for bit; every control
+    inside the limits and finite."""
+    from cartpolesimulation_b200.fleet import Fleet, make_experiments
+    E, K, T, P = 8192, 2000, 50, 2
+    s0, tp, te = make_experiments(E, P, seed=11)
+    tp_d, te_d = torch.from_numpy(tp).cuda(), torch.from_numpy(te).cuda()
+    whole = Fleet(E, K, T, noise="philox", seed=4, device=0)
+    whole.reset(s0)
+    rec = torch.zeros((P, E, 16), device="cuda")
+    whole.run(P, tp_d, te_d, record=rec)
+    rec = rec.cpu().numpy()
+    whole.close()
+    assert np.isfinite(rec).all() and (np.abs(rec[..., 9]) <= 1.0).all()
+    for part in range(4):
+        lo, hi = part * 2048, (part + 1) * 2048
+        fl = Fleet(2048, K, T, noise="philox", seed=4, device=0, experiment_offset=lo)
+        fl.reset(s0[lo:hi])
+        r = torch.zeros((P, 2048, 16), device="cuda")
+        fl.run(P, tp_d[:, lo:hi].contiguous(), te_d[:, lo:hi].contiguous(), record=r)
+        np.testing.assert_array_equal(r.cpu().numpy(), rec[:, lo:hi])
+        fl.close()
