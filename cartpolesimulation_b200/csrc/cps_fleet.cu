@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(256, 4) fleet_kernel(const __grid_constant__ F
         s_cost.target_equilibrium = te;
     }
     const int nwarps = blockDim.x >> 5;
-    // [n_ind][rollouts of this block]; even offset: a pair's draws are read as one 8-byte word
+    // [n_ind][rollouts of this block]; even offset: a pair's draws are read as one 8-byte word (layout: mppi_smem_floats)
     float *s_eps = smem + ((mp.T + 2 * mp.p + nwarps * (mp.n_red + 2) + mp.n_red + 4 + 1) & ~1);
     const int per_block = PAIR ? 2 * (int)blockDim.x : (int)blockDim.x;   // rollouts per block
     if (PHILOX) {
@@ -269,6 +269,7 @@ struct FleetState {
     cps_fleet_config cfg;
     int E, bpe, block, pair;   // pair: two rollouts per thread (packed FP32), K even
     size_t smem;
+    int rs_off;                // MppiParams::rs_off for this geometry
     float *d_s, *d_unom, *d_uprev, *d_partials;
     unsigned *d_tickets;
     long long period;
@@ -332,11 +333,10 @@ extern "C" int cps_fleet_create(cps_handle *h, const cps_fleet_config *cfg) {
     const int threads = F->pair ? K / 2 : K;   // threads per experiment
     F->block = threads >= 256 ? 256 : ((threads + 31) / 32) * 32;
     F->bpe = (threads + F->block - 1) / F->block;
-    const int nwarps = F->block / 32;
-    size_t fl = (size_t)T + 2 * (size_t)h->cfg.interp_period + (size_t)nwarps * (h->n_red + 2) + (size_t)h->n_red + 4;
-    fl = (fl + 1) & ~(size_t)1;
-    if (cfg->noise_source == CPS_FLEET_NOISE_PHILOX) fl += (size_t)h->n_ind * F->block * (F->pair ? 2 : 1);
-    F->smem = fl * sizeof(float);
+    MppiParams mp_geo = h->mp;
+    const size_t draws = (cfg->noise_source == CPS_FLEET_NOISE_PHILOX) ? (size_t)h->n_ind * F->block * (F->pair ? 2 : 1) : 0;
+    F->smem = sizeof(float) * mppi_smem_floats(mp_geo, h->cfg.cost_id, F->block, F->pair ? 2 : 1, draws);
+    F->rs_off = mp_geo.rs_off;
     if (F->smem > 200 * 1024) { delete F; return fail(h, CPS_ERR_UNSUPPORTED, "cps_fleet_create: horizon too large for shared memory"); }
     h->fleet = F;
     const size_t E = F->E;
@@ -429,6 +429,7 @@ static int fleet_launch(cps_handle *h, const char *who, int n_periods, const flo
     CUDA_TRY(h, cudaSetDevice(h->cfg.device));
     FleetArgs a;
     a.ode = h->ode; a.mp = h->mp;
+    a.mp.rs_off = F->rs_off;
     int rc;
     if ((rc = cps_fold_cost_for(h, 1.0f, &a.cost_up)) != CPS_OK) return rc;
     if ((rc = cps_fold_cost_for(h, -1.0f, &a.cost_dn)) != CPS_OK) return rc;

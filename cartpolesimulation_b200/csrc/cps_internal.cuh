@@ -103,6 +103,19 @@ struct cps_handle {
 
 extern thread_local std::string g_create_err;
 
+// Dynamic shared memory (in floats) of mppi_solve_block / mppi_solve_block2 for a block of `block` threads carrying
+// `per_thread` rollouts each: [T] shifted nominal inputs, 2 [p] tent weights, reduction scratch, `extra` floats the
+// caller appends (fleet: Philox draws) and, for the MAX_COST plugins, the row-sum slots (cps_device.cuh RowSumPlan).
+// Sets mp.rs_off.
+static inline size_t mppi_smem_floats(MppiParams &mp, int cost_id, int block, int per_thread, size_t extra = 0) {
+    size_t fl = (size_t)mp.T + 2 * (size_t)mp.p + (size_t)(block / 32) * (mp.n_red + 2) + (size_t)mp.n_red + 4;
+    fl = ((fl + 1) & ~(size_t)1) + ((extra + 1) & ~(size_t)1);
+    mp.rs_off = (int)fl;
+    if (cost_id == CPS_COST_DEFAULT || cost_id == CPS_COST_QUADRATIC_BOUNDARY)
+        fl += (size_t)row_sum_slots(mp.T + 1) * block * per_thread;
+    return fl;
+}
+
 // cps_fleet.cu
 void cps_fleet_free(cps_handle *h);
 // cps_plan.cu

@@ -116,26 +116,33 @@ __global__ void __launch_bounds__(128) rollout_pair_kernel(const __grid_constant
 // =====================================================================================================
 // standalone cost plugin
 // =====================================================================================================
+// get_trajectory_cost sums its T+1 entries in the reference backend's order for every plugin (RowSumPlan, cps_device.cuh;
+// dynamic shared memory: row_sum_slots(T + 1) x blockDim floats) and divides by T+1.
 template <int COST>
 __global__ void __launch_bounds__(256) cost_kernel(const __grid_constant__ CostArgs a) {
+    extern __shared__ float smem[];
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= a.K) return;
     const float *tr = a.traj + (size_t)k * a.rows * 6;
     const float *q = a.Q + (size_t)k * a.T;
     const float shift = a.unshifted ? 0.0f : a.cost.max_cost;
-    float acc = 0.0f, up = a.u_prev;
+    const RowSumPlan rsp = row_sum_plan(a.T + 1);
+    float *sl = smem + threadIdx.x;
+    const int ss = blockDim.x;
+    float tail = 0.0f, up = a.u_prev;
+    if (a.J) row_sum_init(rsp, sl, ss);
     for (int t = 0; t < a.T; ++t) {
         const float *s = tr + (size_t)t * 6;
         const float u = q[t];
         const float c = stage_cost<COST>(a.cost, cosf(s[IDX_ANGLE]), s[IDX_ANGLED], s[IDX_POS], u, up) - shift;
         if (a.stage) a.stage[(size_t)k * a.T + t] = c;
-        acc += c;
+        if (a.J) row_sum_push(rsp, sl, ss, tail, t, c);
         up = u;
     }
     if (a.J) {
         const float *s = tr + (size_t)a.T * 6;
-        acc += terminal_cost<COST>(a.cost, s[IDX_ANGLE], s[IDX_POS]);
-        a.J[k] = acc * a.inv_T1;
+        row_sum_push(rsp, sl, ss, tail, a.T, terminal_cost<COST>(a.cost, s[IDX_ANGLE], s[IDX_POS]));
+        a.J[k] = __fdiv_rn(row_sum_finish(rsp, sl, ss, tail), (float)(a.T + 1));
     }
 }
 
@@ -271,6 +278,8 @@ static void fold_mppi(cps_handle *h) {
     m.n_ind = h->n_ind;
     m.n_red = h->n_red;
     m.inv_T1 = 1.0f / (float)(m.T + 1);
+    m.T1 = (float)(m.T + 1);
+    m.rs_off = 0;
     m.inv_p = 1.0f / (float)m.p;
 }
 
@@ -349,9 +358,7 @@ extern "C" int cps_create(const cps_config *cfg, cps_handle **out) {
     h->block = (K <= 148 * 32 * 4) ? 32 : (K <= 148 * 64 * 8 ? 64 : 128);
     if (cfg->integrator == CPS_PREDICTOR_NEURAL) h->block = 16;  // rollouts per CTA of net_kernel (cps_net.cu)
     h->grid = (K + h->block - 1) / h->block;
-    const int nwarps = h->block / 32;
-    h->smem = sizeof(float) * ((size_t)cfg->horizon + 2 * (size_t)cfg->interp_period
-                               + (size_t)nwarps * (h->n_red + 2) + (size_t)h->n_red + 4);
+    h->smem = sizeof(float) * mppi_smem_floats(h->mp, cfg->cost_id, h->block, 1);
     if (h->smem > 200 * 1024) {
         g_create_err = "cps_create: horizon too large for the shared-memory staging of this build";
         delete h;
@@ -581,12 +588,13 @@ extern "C" int cps_mppi_step(cps_handle *h, const float *s_dev, const float *noi
         const long long threads = K / 2;
         const int block = threads <= 148 * 32 * 4 ? 32 : (threads <= 148 * 64 * 8 ? 64 : 128);
         const int grid = (int)((threads + block - 1) / block);   // grid <= h->grid: the partial records fit
-        const size_t smem = sizeof(float) * ((size_t)h->cfg.horizon + 2 * (size_t)h->cfg.interp_period
-                                             + (size_t)(block / 32) * (h->n_red + 2) + (size_t)h->n_red + 4);
+        const size_t smem = sizeof(float) * mppi_smem_floats(a.mp, h->cfg.cost_id, block, 2);
+        if (smem > 200 * 1024) return fail(h, CPS_ERR_UNSUPPORTED, "cps_mppi_step: horizon too large for the shared-memory staging of this build");
         mppi_fn fn = pick_mppi_pair(h->cfg);
         if (smem > 48 * 1024) CUDA_TRY(h, cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         fn<<<grid, block, smem, h->stream>>>(a);
     } else {
+        mppi_smem_floats(a.mp, h->cfg.cost_id, h->block, 1);   // a.mp.rs_off for this geometry
         mppi_fn fn = pick_mppi(h->cfg);
         if (h->smem > 48 * 1024) CUDA_TRY(h, cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
         fn<<<h->grid, h->block, h->smem, h->stream>>>(a);
@@ -845,7 +853,9 @@ static int cost_launch(cps_handle *h, const float *traj, int rows, const float *
     a.cost = h->cost; a.traj = traj; a.Q = Q; a.u_prev = u_prev; a.K = K; a.T = T; a.rows = rows;
     a.inv_T1 = 1.0f / (float)(T + 1);
     a.J = J; a.stage = stage; a.unshifted = unshifted;
-    fn<<<(K + 127) / 128, 128, 0, h->stream>>>(a);
+    const size_t smem = J ? sizeof(float) * (size_t)row_sum_slots(T + 1) * 128 : 0;
+    if (smem > 48 * 1024) CUDA_TRY(h, cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fn<<<(K + 127) / 128, 128, smem, h->stream>>>(a);
     h->launches += 1;
     CUDA_TRY(h, cudaGetLastError());
     return CPS_OK;

@@ -201,7 +201,8 @@ __global__ void __launch_bounds__(R * 8 + 32, 1) net_kernel(const __grid_constan
     float *s_unom = snorm + 8 * R;                  // MPPI: [T] shifted nominal inputs, then [p] w0, [p] w1, scratch
     float *s_w0 = s_unom + (MPPI ? a.mp.T : 0);
     float *s_w1 = s_w0 + (MPPI ? a.mp.p : 0);
-    float *s_red = s_w1 + (MPPI ? a.mp.p : 0);      // [n_red + 2]
+    float *s_red = s_w1 + (MPPI ? a.mp.p : 0);      // [n_red + 2 + 16]
+    float *s_rs = s_red + (MPPI ? a.mp.n_red + 2 + 16 : 0);   // MAX_COST plugins: row-sum slots [32][R] (RowSumPlan)
 
     // ---- weights: one bulk asynchronous copy global -> shared ---------------------------------------------------
     if (tid == 0) {
@@ -245,6 +246,12 @@ __global__ void __launch_bounds__(R * 8 + 32, 1) net_kernel(const __grid_constan
     const bool active = row_lead && k < a.B;
     const int kc = min(k, a.B - 1);
     float Jacc = 0.0f, corr = 0.0f, up = a.u_prev, u_cur = 0.0f, du_cur = 0.0f, u_nxt = 0.0f, du_nxt = 0.0f;
+    // default / quadratic_boundary: the T+1 cost entries are summed in the reference backend's order (cps_device.cuh)
+    const bool rowsum = MPPI && (a.cost_id == CPS_COST_DEFAULT || a.cost_id == CPS_COST_QUADRATIC_BOUNDARY);
+    const RowSumPlan rsp = row_sum_plan(T + 1);
+    float *sl = s_rs + r_row;
+    float rs_tail = 0.0f;
+    if (rowsum && row_lead) row_sum_init(rsp, sl, R);
     int seg = 0, jj = 0;
     float na = 0.0f, nb = 0.0f;
     const float *nz = nullptr;
@@ -334,7 +341,9 @@ __global__ void __launch_bounds__(R * 8 + 32, 1) net_kernel(const __grid_constan
                 for (int c = 0; c < 6; ++c) traj[(long long)t * a.ts_t + c * a.ts_c] = st[c];
             }
             if (MPPI) {
-                Jacc += stage_cost_rt(a.cost_id, a.cost, cosf(st[IDX_ANGLE]), st[IDX_ANGLED], st[IDX_POS], u_cur, up);
+                const float stc = stage_cost_rt(a.cost_id, a.cost, cosf(st[IDX_ANGLE]), st[IDX_ANGLED], st[IDX_POS], u_cur, up);
+                if (rowsum) { if (row_lead) row_sum_push(rsp, sl, R, rs_tail, t, stc); }
+                else Jacc += stc;
                 corr = fmaf(a.mp.cc_half_nu * du_cur, du_cur,
                             fmaf(a.mp.cc_R * u_cur, du_cur, fmaf(a.mp.cc_half_R * u_cur, u_cur, corr)));
                 if (a.u_run_out && active) a.u_run_out[(long long)k * T + t] = u_cur;
@@ -363,9 +372,13 @@ __global__ void __launch_bounds__(R * 8 + 32, 1) net_kernel(const __grid_constan
             for (int c = 0; c < 6; ++c) traj[(long long)T * a.ts_t + c * a.ts_c] = st[c];
         }
         if (MPPI) {
-            if (a.cost_id == CPS_COST_DEFAULT || a.cost_id == CPS_COST_QUADRATIC_BOUNDARY)
-                Jacc += terminal_cost<COST_DEFAULT>(a.cost, st[IDX_ANGLE], st[IDX_POS]);
-            J = fmaf(Jacc, a.mp.inv_T1, corr);
+            if (rowsum) {
+                if (row_lead) {
+                    row_sum_push(rsp, sl, R, rs_tail, T, terminal_cost<COST_DEFAULT>(a.cost, st[IDX_ANGLE], st[IDX_POS]));
+                    Jacc = row_sum_finish(rsp, sl, R, rs_tail);
+                }
+            }
+            J = __fdiv_rn(Jacc, a.mp.T1) + corr;   // mean over T+1 entries (true division, as torch.mean) + correction
             if (active) {
                 if (a.J_out) a.J_out[k] = J;
                 if (!isfinite(J)) atomicAdd(a.nonfinite, 1);
@@ -429,6 +442,7 @@ __global__ void __launch_bounds__(R * 8 + 32, 1) net_kernel(const __grid_constan
 static size_t net_smem_bytes(const NetDev &N, int R, bool mppi, const MppiParams *mp) {
     size_t f = (size_t)N.n_weights + 2 * (size_t)N.htot * R + 16 * (size_t)R;
     if (mppi) f += (size_t)mp->T + 2 * (size_t)mp->p + (size_t)mp->n_red + 2 + 16;  // + one float per warp (merge)
+    if (mppi) f += 32 * (size_t)R;   // row-sum slots of the MAX_COST plugins (T + 1 < 512: one accumulator level)
     return f * sizeof(float);
 }
 
@@ -583,8 +597,12 @@ static int net_launch(cps_handle *h, NetArgs &a, bool mppi, int n_rows) {
     const unsigned fl = h->cfg.flags;
     const bool want_tc = (fl & CPS_FLAG_NET_TENSOR_CORES) || (!(fl & CPS_FLAG_NET_FP32) && n_rows > 148 * 16);
     if ((fl & CPS_FLAG_NET_TENSOR_CORES) && !S->d_tc)
-        return fail(h, CPS_ERR_UNSUPPORTED, "CPS_FLAG_NET_TENSOR_CORES: the tensor-core kernel supports 2 x 64 GRU networks only");
-    if (want_tc && S->d_tc) return cps_net_tc_launch(h, a, mppi, n_rows);
+        return fail(h, CPS_ERR_UNSUPPORTED, "CPS_FLAG_NET_TENSOR_CORES: the tensor-core kernel supports plain (not differential, D_*) 2 x 64 GRU networks only");
+    // the MAX_COST plugins need the backend-ordered row sum (RowSumPlan), which lives in the FP32 kernel
+    const bool shifted = mppi && (h->cfg.cost_id == CPS_COST_DEFAULT || h->cfg.cost_id == CPS_COST_QUADRATIC_BOUNDARY);
+    if ((fl & CPS_FLAG_NET_TENSOR_CORES) && shifted)
+        return fail(h, CPS_ERR_UNSUPPORTED, "CPS_FLAG_NET_TENSOR_CORES: default / quadratic_boundary run on the FP32 network kernel");
+    if (want_tc && S->d_tc && !shifted) return cps_net_tc_launch(h, a, mppi, n_rows);
     // small batches: 16 rollouts per CTA spread the work over more SMs; large ones: 32 (two warps per scheduler)
     int R = (n_rows > 148 * 16) ? 32 : 16;
     if (net_smem_bytes(S->dev, R, mppi, &h->mp) > 227 * 1024) R = 16;
@@ -671,6 +689,8 @@ int cps_net_mppi_step(cps_handle *h, const float *s_dev, const float *noise_dev,
     if (!h->net) return fail(h, CPS_ERR_NOT_CONFIGURED, "cps_mppi_step: neural predictor without a network (cps_net_load)");
     if (h->cfg.noise_mode != CPS_NOISE_INDUCING)
         return fail(h, CPS_ERR_UNSUPPORTED, "cps_mppi_step: the neural predictor supports CPS_NOISE_INDUCING only");
+    if ((h->cfg.cost_id == CPS_COST_DEFAULT || h->cfg.cost_id == CPS_COST_QUADRATIC_BOUNDARY) && row_sum_slots(h->cfg.horizon + 1) > 32)
+        return fail(h, CPS_ERR_UNSUPPORTED, "cps_mppi_step: default / quadratic_boundary with the neural predictor support horizons below 511");
     NetArgs a;
     memset(&a, 0, sizeof(a));
     const long long K = h->cfg.num_rollouts;

@@ -408,7 +408,7 @@ __global__ void __launch_bounds__(TC_NT, 1) net_tc_kernel(const __grid_constant_
         if (MPPI) {
             if (a.cost_id == CPS_COST_DEFAULT || a.cost_id == CPS_COST_QUADRATIC_BOUNDARY)
                 Jacc += terminal_cost<COST_DEFAULT>(a.cost, st[IDX_ANGLE], st[IDX_POS]);
-            J = fmaf(Jacc, a.mp.inv_T1, corr);
+            J = __fdiv_rn(Jacc, a.mp.T1) + corr;   // mean over T+1 entries (true division, as torch.mean) + correction
             if (active) {
                 if (a.J_out) a.J_out[k] = J;
                 if (!isfinite(J)) atomicAdd(a.nonfinite, 1);

@@ -37,6 +37,7 @@ struct PlanArgs {
     const float *mu, *sd;         // PLAN_CEM: sampling distribution [T]
     float lo, hi, inv_T1, u_prev;
     int K, T;
+    int rs_off;                   // float offset (even) of the row-sum slots in dynamic shared memory (MAX_COST plugins)
     float *J;                     // [K]; required when select != SELECT_NONE
     float *Q_out;                 // PLAN_CEM: the sampled plans, same strides as Q, or null
     float *traj_out;
@@ -537,6 +538,13 @@ __global__ void __launch_bounds__(256, 4) plan_kernel(const __grid_constant__ Pl
     float *qo = (MODE == PLAN_CEM && a.Q_out) ? a.Q_out + (long long)kc * a.qs_k : nullptr;
     float *traj = a.traj_out ? a.traj_out + (long long)kc * a.ts_k : nullptr;
     float Jacc = 0.0f, up = a.u_prev;
+    // default / quadratic_boundary: the T+1 entries are summed in the reference backend's order (cps_device.cuh RowSumPlan)
+    constexpr bool ROWSUM = (COST == COST_DEFAULT || COST == COST_QB);
+    const RowSumPlan rsp = row_sum_plan(T + 1);
+    float *sl = smem + a.rs_off + tid;
+    const int ss = blockDim.x;
+    float rs_tail = 0.0f;
+    if (ROWSUM) row_sum_init(rsp, sl, ss);
     float qn = q[0];
 #pragma unroll 1
     for (int t = 0; t < T; ++t) {
@@ -547,18 +555,26 @@ __global__ void __launch_bounds__(256, 4) plan_kernel(const __grid_constant__ Pl
             if (active && qo) qo[(long long)t * a.qs_t] = u;
         }
         if (COST != COST_NONE) {
-            float st = stage_cost<COST>(a.cost, c_cost, z.w, z.x, u, up);
-            if (COST == COST_DEFAULT || COST == COST_QB) st -= a.cost.max_cost;  // get_stage_cost shift
-            Jacc += st;
+            const float st = stage_cost<COST>(a.cost, c_cost, z.w, z.x, u, up);
+            if (ROWSUM) row_sum_push(rsp, sl, ss, rs_tail, t, st - a.cost.max_cost);  // get_stage_cost shift
+            else Jacc += st;
         }
         if (active && traj) store_state(traj + (long long)t * a.ts_t, a.ts_c, z);
         control_step<INTEG, SC_ROTATE, false, false>(ode, z, u);
         c_cost = z.c;
         up = u;
     }
-    if (COST != COST_NONE) Jacc += terminal_cost<COST>(a.cost, z.th, z.x);
+    if (COST != COST_NONE) {
+        const float term = terminal_cost<COST>(a.cost, z.th, z.x);
+        if (ROWSUM) {
+            row_sum_push(rsp, sl, ss, rs_tail, T, term);
+            Jacc = row_sum_finish(rsp, sl, ss, rs_tail);
+        } else {
+            Jacc += term;
+        }
+    }
     if (active && traj) store_state(traj + (long long)T * a.ts_t, a.ts_c, z);
-    const float J = Jacc * a.inv_T1;  // mean over the T+1 entries (Cost_Functions/__init__.py:90-93)
+    const float J = __fdiv_rn(Jacc, (float)(T + 1));  // mean over the T+1 entries (Cost_Functions/__init__.py:90-93)
     if (active) {
         if (a.J) a.J[k] = J;
         if (!isfinite(J)) atomicAdd(a.nonfinite, 1);
@@ -596,6 +612,12 @@ __global__ void __launch_bounds__(128, 4) plan_pair_kernel(const __grid_constant
     const float *q = a.Q + k;                            // qs_k == 1
     float *qo = (MODE == PLAN_CEM && a.Q_out) ? a.Q_out + k : nullptr;
     float Ja0 = 0.0f, Ja1 = 0.0f, up0 = a.u_prev, up1 = a.u_prev;
+    constexpr bool ROWSUM = (COST == COST_DEFAULT || COST == COST_QB);   // see plan_kernel
+    const RowSumPlan rsp = row_sum_plan(T + 1);
+    float2 *sl = reinterpret_cast<float2 *>(smem + a.rs_off) + tid;
+    const int ss = blockDim.x;
+    float2 rs_tail = make_float2(0.0f, 0.0f);
+    if (ROWSUM) row_sum_init(rsp, sl, ss);
     float2 qn = *reinterpret_cast<const float2 *>(q);
 #pragma unroll 1
     for (int t = 0; t < T; ++t) {
@@ -607,20 +629,26 @@ __global__ void __launch_bounds__(128, 4) plan_pair_kernel(const __grid_constant
             if (qo) *reinterpret_cast<float2 *>(qo + (long long)t * a.qs_t) = make_float2(u0, u1);
         }
         if (COST != COST_NONE) {
-            float st0 = stage_cost<COST>(a.cost, cc0, lo(z.w), lo(z.x), u0, up0);
-            float st1 = stage_cost<COST>(a.cost, cc1, hi(z.w), hi(z.x), u1, up1);
-            if (COST == COST_DEFAULT || COST == COST_QB) { st0 -= a.cost.max_cost; st1 -= a.cost.max_cost; }
-            Ja0 += st0; Ja1 += st1;
+            const float st0 = stage_cost<COST>(a.cost, cc0, lo(z.w), lo(z.x), u0, up0);
+            const float st1 = stage_cost<COST>(a.cost, cc1, hi(z.w), hi(z.x), u1, up1);
+            if (ROWSUM) row_sum_push(rsp, sl, ss, rs_tail, t, make_float2(st0 - a.cost.max_cost, st1 - a.cost.max_cost));
+            else { Ja0 += st0; Ja1 += st1; }
         }
         control_step2<INTEG, false>(ode, z, f2(u0, u1));
         cc0 = lo(z.c); cc1 = hi(z.c);
         up0 = u0; up1 = u1;
     }
     if (COST != COST_NONE) {
-        Ja0 += terminal_cost<COST>(a.cost, lo(z.th), lo(z.x));
-        Ja1 += terminal_cost<COST>(a.cost, hi(z.th), hi(z.x));
+        const float tm0 = terminal_cost<COST>(a.cost, lo(z.th), lo(z.x)), tm1 = terminal_cost<COST>(a.cost, hi(z.th), hi(z.x));
+        if (ROWSUM) {
+            row_sum_push(rsp, sl, ss, rs_tail, T, make_float2(tm0, tm1));
+            const float2 r = row_sum_finish(rsp, sl, ss, rs_tail);
+            Ja0 = r.x; Ja1 = r.y;
+        } else {
+            Ja0 += tm0; Ja1 += tm1;
+        }
     }
-    const float J0 = Ja0 * a.inv_T1, J1 = Ja1 * a.inv_T1;
+    const float J0 = __fdiv_rn(Ja0, (float)(T + 1)), J1 = __fdiv_rn(Ja1, (float)(T + 1));
     a.J[k] = J0; a.J[k + 1] = J1;
     if (!isfinite(J0)) atomicAdd(a.nonfinite, 1);
     if (!isfinite(J1)) atomicAdd(a.nonfinite, 1);
@@ -640,17 +668,29 @@ static void (*pick_plan_pair(int integ, int cost, int mode))(const PlanArgs) {
     if (integ == CPS_EULER_V0) return mode == PLAN_CEM ? pick_plan_pair2<0, PLAN_CEM>(cost) : pick_plan_pair2<0, PLAN_Q>(cost);
     return mode == PLAN_CEM ? pick_plan_pair2<1, PLAN_CEM>(cost) : pick_plan_pair2<1, PLAN_Q>(cost);
 }
+// Dynamic shared memory of a plan launch: `base` bytes of the kernel's own staging, then (MAX_COST plugins) the row-sum
+// slots of the block's rollouts.  Sets a.rs_off.
+static size_t plan_smem(const cps_handle *h, PlanArgs &a, size_t base, int block, int per_thread) {
+    size_t fl = ((base + 3) / 4 + 1) & ~(size_t)1;
+    a.rs_off = (int)fl;
+    if (h->cfg.cost_id == CPS_COST_DEFAULT || h->cfg.cost_id == CPS_COST_QUADRATIC_BOUNDARY)
+        fl += (size_t)row_sum_slots(a.T + 1) * block * per_thread;
+    else if (base == 0) return 0;
+    return fl * sizeof(float);
+}
 // true when a launch described by `a` (select == SELECT_NONE) can take the packed kernel
 static bool plan_pair_ok(const cps_handle *h, const PlanArgs &a) {
     return a.K >= CPS_PLAN_PAIR_MIN && (a.K % 2) == 0 && a.qs_k == 1 && (a.qs_t % 2) == 0 && !a.traj_out && a.J &&
            !(h->cfg.flags & CPS_FLAG_NO_PAIRS) && ((uintptr_t)a.Q % 8) == 0 && (!a.Q_out || ((uintptr_t)a.Q_out % 8) == 0);
 }
-static void plan_pair_launch(cps_handle *h, const PlanArgs &a, int mode) {
+static void plan_pair_launch(cps_handle *h, PlanArgs &a, int mode) {
     const long long threads = a.K / 2;
     const int block = threads <= 148 * 32 * 4 ? 32 : (threads <= 148 * 64 * 8 ? 64 : 128);
     const int grid = (int)((threads + block - 1) / block);
-    const size_t smem = mode == PLAN_CEM ? sizeof(float) * 2 * (size_t)a.T : 0;
-    pick_plan_pair(h->cfg.integrator, h->cfg.cost_id, mode)<<<grid, block, smem, h->stream>>>(a);
+    const size_t smem = plan_smem(h, a, mode == PLAN_CEM ? sizeof(float) * 2 * (size_t)a.T : 0, block, 2);
+    auto fn = pick_plan_pair(h->cfg.integrator, h->cfg.cost_id, mode);
+    if (smem > 48 * 1024) cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    fn<<<grid, block, smem, h->stream>>>(a);
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------------------
@@ -767,7 +807,9 @@ extern "C" int cps_plan_cost(cps_handle *h, const float *s_dev, const float *Q_d
         int grid, block;
         plan_geometry(K, false, grid, block);
         plan_fn fn = pick_plan(h->cfg.integrator, h->cfg.cost_id, PLAN_Q);
-        fn<<<grid, block, 0, h->stream>>>(a);
+        const size_t smem = plan_smem(h, a, 0, block, 1);
+        if (smem > 48 * 1024) CUDA_TRY(h, cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        fn<<<grid, block, smem, h->stream>>>(a);
     }
     h->launches += 1;
     CUDA_TRY(h, cudaGetLastError());
@@ -796,7 +838,9 @@ extern "C" int cps_plan_random_action(cps_handle *h, const float *s_dev, const f
     int grid, block;
     plan_geometry(K, true, grid, block);
     plan_fn fn = pick_plan(h->cfg.integrator, h->cfg.cost_id, PLAN_Q);
-    fn<<<grid, block, 0, h->stream>>>(a);
+    const size_t smem = plan_smem(h, a, 0, block, 1);
+    if (smem > 48 * 1024) CUDA_TRY(h, cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fn<<<grid, block, smem, h->stream>>>(a);
     h->launches += 1;
     CUDA_TRY(h, cudaGetLastError());
     return CPS_OK;
@@ -878,7 +922,6 @@ extern "C" int cps_cem_step(cps_handle *h, const float *s_dev, const float *eps_
     a.elite_smem = 0;   // set below once defer_stats is known
     const size_t smem = sizeof(float) * 4 * (size_t)T + sizeof(int) * (size_t)(((long long)P->best_k * T > 2048) ? 0 : P->best_k);
     plan_fn fn = pick_plan(h->cfg.integrator, h->cfg.cost_id, PLAN_CEM);
-    if (smem > 48 * 1024) CUDA_TRY(h, cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // small elite sets: the selecting block also computes the T x best_k statistics; large ones: a second launch with
     // one block per horizon step
     a.defer_stats = ((long long)P->best_k * T > 2048) ? 1 : 0;
@@ -905,8 +948,14 @@ extern "C" int cps_cem_step(cps_handle *h, const float *s_dev, const float *eps_
         a.Q_out = a.last_iter ? Q_out_dev : nullptr;   // Q_logged is the last iteration's plans (cem_tf.py:93)
         a.mu = P->d_mu + (size_t)P->cur * T; a.sd = P->d_sd + (size_t)P->cur * T;
         a.mu_out = P->d_mu + (size_t)(1 - P->cur) * T; a.sd_out = P->d_sd + (size_t)(1 - P->cur) * T;
-        if (multi && plan_pair_ok(h, a) && sizeof(float) * 2 * (size_t)T <= 48 * 1024) plan_pair_launch(h, a, PLAN_CEM);
-        else fn<<<grid, block, smem, h->stream>>>(a);
+        if (multi && plan_pair_ok(h, a) && sizeof(float) * 2 * (size_t)T <= 48 * 1024) {
+            plan_pair_launch(h, a, PLAN_CEM);
+        } else {
+            const size_t sm = plan_smem(h, a, smem, block, 1);
+            if (sm > 200 * 1024) return fail(h, CPS_ERR_UNSUPPORTED, "cps_cem_step: horizon too large for shared memory");
+            if (sm > 48 * 1024) CUDA_TRY(h, cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            fn<<<grid, block, sm, h->stream>>>(a);
+        }
         h->launches += 1;
         if (multi) {
             void *args[] = {(void *)&a};

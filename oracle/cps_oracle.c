@@ -377,24 +377,89 @@ void cps_oracle_stage_cost(int cost_id, const float *cp, const float *traj, cons
     }
 }
 
+/* Summation order of torch's CPU `sum` over a contiguous row of n float32 values -- the order `lib.mean(..., 1)` of
+ * get_trajectory_cost (Control_Toolkit/Cost_Functions/__init__.py:90-93) runs in with the torch library, since
+ * torch.mean on CPU is sum followed by a TRUE division by n.  It is a library detail (ATen/native/cpu/SumKernel.cpp,
+ * cascade_sum; torch 2.11), established empirically with exact-arithmetic probes (which pairs of addends meet before a
+ * third one) and checked bit for bit against torch.sum for n = 1..5000 (tests/test_oracle_golden.py::test_torch_row_sum):
+ *   - vectors of 8 lanes (the kernel is built for AVX2 even on AVX-512 hosts), 4 vector accumulators ("ilp"):
+ *     element e < 8*(n/8) sits in vector v = e/8, lane e%8; vectors of the complete groups of 4 accumulate into
+ *     acc[v%4], every 16 groups the accumulators cascade into a second (third, fourth) level; left-over vectors go to
+ *     accumulator 0; then acc0 += acc1, acc2, acc3;
+ *   - the n%8 tail elements are summed sequentially from zero, then the 8 lanes of acc0 are added in lane order;
+ *   - n < 8: scalar path, 4 interleaved accumulators, left-overs to accumulator 0, then a0 + a1 + a2 + a3.
+ * With the MAX_COST plugins every addend is ~ -6e9 (ulp 512) and the row sum ~ -3e11 (ulp 32768): the order decides
+ * the bucket a rollout lands in, so it has to be THIS order for the controls to agree with the reference. */
+#define TRS_LEVELS 4
+float cps_oracle_torch_row_sum(const float *x, int n) {
+    if (n < 8) {
+        float a[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        const int g = n / 4;
+        for (int i = 0; i < g; ++i)
+            for (int k = 0; k < 4; ++k) a[k] += x[i * 4 + k];
+        for (int i = g * 4; i < n; ++i) a[0] += x[i];
+        for (int k = 1; k < 4; ++k) a[0] += a[k];
+        return a[0];
+    }
+    const int vec_size = n / 8, size_ilp = vec_size / 4;
+    int level_power = 4;
+    {   /* max(4, CeilLog2(size_ilp) / 4) */
+        int cl = 0;
+        while ((1 << cl) < size_ilp) ++cl;
+        if (cl / TRS_LEVELS > level_power) level_power = cl / TRS_LEVELS;
+    }
+    const int level_step = 1 << level_power, level_mask = level_step - 1;
+    float acc[TRS_LEVELS][4][8];
+    memset(acc, 0, sizeof(acc));
+    int i = 0;
+    while (i + level_step <= size_ilp) {
+        for (int j = 0; j < level_step; ++j, ++i)
+            for (int k = 0; k < 4; ++k)
+                for (int l = 0; l < 8; ++l) acc[0][k][l] += x[(i * 4 + k) * 8 + l];
+        for (int j = 1; j < TRS_LEVELS; ++j) {
+            for (int k = 0; k < 4; ++k)
+                for (int l = 0; l < 8; ++l) { acc[j][k][l] += acc[j - 1][k][l]; acc[j - 1][k][l] = 0.0f; }
+            if ((i & (level_mask << (j * level_power))) != 0) break;
+        }
+    }
+    for (; i < size_ilp; ++i)
+        for (int k = 0; k < 4; ++k)
+            for (int l = 0; l < 8; ++l) acc[0][k][l] += x[(i * 4 + k) * 8 + l];
+    for (int j = 1; j < TRS_LEVELS; ++j)
+        for (int k = 0; k < 4; ++k)
+            for (int l = 0; l < 8; ++l) acc[0][k][l] += acc[j][k][l];
+    for (int v = size_ilp * 4; v < vec_size; ++v)
+        for (int l = 0; l < 8; ++l) acc[0][0][l] += x[v * 8 + l];
+    for (int k = 1; k < 4; ++k)
+        for (int l = 0; l < 8; ++l) acc[0][0][l] += acc[0][k][l];
+    float fin = 0.0f;
+    for (int e = vec_size * 8; e < n; ++e) fin += x[e];
+    for (int l = 0; l < 8; ++l) fin += acc[0][0][l];
+    return fin;
+}
+
 /* cost_function_base.get_trajectory_cost (Control_Toolkit/Cost_Functions/__init__.py:74-93):
- * mean over the T+1 entries [stage_0 - MAX .. stage_{T-1} - MAX, terminal].  The summation order of
- * torch.mean is a library detail; this restatement sums sequentially in float32. */
+ * mean over the T+1 entries [stage_0 - MAX .. stage_{T-1} - MAX, terminal], in the summation order of the torch
+ * library (cps_oracle_torch_row_sum), then divided by T+1. */
 void cps_oracle_trajectory_cost(int cost_id, const float *cp, const float *traj, const float *Q, float u_prev,
                                 int K, int T, float thl, float target_position, float target_equilibrium,
                                 float *J) {
     const float max_cost = cost_is_shifted(cost_id) ? cp[5] : 0.0f;
-#pragma omp parallel for schedule(static)
-    for (int k = 0; k < K; ++k) {
-        float acc = 0.0f;
-        for (int t = 0; t < T; ++t) {
-            const float up = (t == 0) ? u_prev : Q[(size_t)k * T + t - 1];
-            const float c = stage_cost_one(cost_id, cp, traj + ((size_t)k * (T + 1) + t) * 6, Q[(size_t)k * T + t], up,
-                                           thl, target_position, target_equilibrium);
-            acc += c - max_cost;
+#pragma omp parallel
+    {
+        float *row = (float *)malloc(sizeof(float) * (size_t)(T + 1));
+#pragma omp for schedule(static)
+        for (int k = 0; k < K; ++k) {
+            for (int t = 0; t < T; ++t) {
+                const float up = (t == 0) ? u_prev : Q[(size_t)k * T + t - 1];
+                const float c = stage_cost_one(cost_id, cp, traj + ((size_t)k * (T + 1) + t) * 6, Q[(size_t)k * T + t], up,
+                                               thl, target_position, target_equilibrium);
+                row[t] = c - max_cost;
+            }
+            row[T] = terminal_cost_one(cost_id, traj + ((size_t)k * (T + 1) + T) * 6, thl, target_position);
+            J[k] = cps_oracle_torch_row_sum(row, T + 1) / (float)(T + 1);
         }
-        acc += terminal_cost_one(cost_id, traj + ((size_t)k * (T + 1) + T) * 6, thl, target_position);
-        J[k] = acc / (float)(T + 1);
+        free(row);
     }
 }
 
@@ -464,14 +529,15 @@ static float mppi_tail(int cost_id, const float *cp, const float *mp, const floa
                                target_equilibrium, J);
     /* mppi_correction_cost (:153-154), summed over the horizon */
     const float c1 = (0.5f * (1.0f - 1.0f / NU)) * R;
+    float *row = (float *)malloc(sizeof(float) * (size_t)T);
     for (int k = 0; k < K; ++k) {
-        float acc = 0.0f;
         for (int t = 0; t < T; ++t) {
             const float du = delta_u[(size_t)k * T + t], u = u_run[(size_t)k * T + t];
-            acc += cc_weight * ((c1 * (du * du) + (R * u) * du) + (0.5f * R) * (u * u));
+            row[t] = cc_weight * ((c1 * (du * du) + (R * u) * du) + (0.5f * R) * (u * u));
         }
-        J[k] = J[k] + acc;
+        J[k] = J[k] + cps_oracle_torch_row_sum(row, T); /* lib.sum(..., (1, 2)) of a contiguous [K, T, 1] (:159) */
     }
+    free(row);
     /* reward_weighted_average (:162-167) */
     float rho = J[0];
     for (int k = 1; k < K; ++k) rho = (J[k] < rho) ? J[k] : rho;

@@ -205,8 +205,18 @@ def gen_mppi():
         ("ode_default", "ODE", "default", 256, 50, 3, 0.0, 1.0),
         ("ode_gradmin_T100", "ODE", "quadratic_boundary_grad_minimal", 256, 100, 2, 0.1, 1.0),
         ("ode_gradmin_T51", "ODE", "quadratic_boundary_grad_minimal", 128, 51, 2, 0.0, 1.0),
+        # BASELINE.json configs[0] exactly: predictor_ODE_v0 (explicit Euler, numba), K = 2000, T = 50
+        ("v0_gradmin_K2000", "ODE_v0", "quadratic_boundary_grad_minimal", 2000, 50, 2, 0.0, 1.0),
+        # BASELINE.json configs[3] at full size: K = 65536, T = 100, barrier cost (and the shift-free plugin).  The
+        # draws are not stored (2.9 MB per solve): tests regenerate them from the seed and check their digest.
+        ("ode_qb_K65536_T100", "ODE", "quadratic_boundary", 65536, 100, 1, 0.0, 1.0),
+        ("ode_gradmin_K65536_T100", "ODE", "quadratic_boundary_grad_minimal", 65536, 100, 1, 0.0, 1.0),
     ]
+    only = [x for x in os.environ.get("CPS_GOLDEN_ONLY", "").split(",") if x]
     for (name, pred, cost, K, T, steps, tp, te) in runs:
+        if only and name not in only:
+            continue
+        big = K >= 65536
         rng = np.random.default_rng(abs(hash(name)) % (2 ** 31))
         gen = torch.Generator().manual_seed(1)
         lib = R.torch_lib()
@@ -222,7 +232,8 @@ def gen_mppi():
         draws = [torch.normal(0.0, 1.0, size=(K, n_ind, 1), generator=gen, dtype=torch.float32) for _ in range(steps)]
         opt.rng = R.InjectedNormal(draws)
         s = hanging_state()
-        arrays = {"eps": np.stack([d.numpy()[:, :, 0] for d in draws], 0)}
+        eps_all = np.stack([d.numpy()[:, :, 0] for d in draws], 0)
+        arrays = {} if big else {"eps": eps_all}
         S, U, UNOM, JJ, UPREV = [], [], [], [], []
         for i in range(steps):
             UPREV.append(np.float32(opt.u))
@@ -233,7 +244,8 @@ def gen_mppi():
             UNOM.append(opt.u_nom.numpy().reshape(-1).astype(np.float32))
             JJ.append(opt.logging_values["J_logged"].astype(np.float32))
             if i == 0:
-                arrays["u_run0"] = opt.logging_values["Q_logged"][:, :, 0].astype(np.float32)
+                if not big:
+                    arrays["u_run0"] = opt.logging_values["Q_logged"][:, :, 0].astype(np.float32)
                 arrays["traj0"] = opt.logging_values["rollout_trajectories_logged"][:32].astype(np.float32)
             # advance the "plant" one control step with the applied control (input generation only)
             s = O.rollout("ODE", s, np.array([[u]], dtype=np.float32), n=10, dt=0.02)[0, 1]
@@ -241,6 +253,11 @@ def gen_mppi():
         meta = dict(ref="Control_Toolkit/Optimizers/optimizer_mppi.py:180-224 (torch lib, injected rng.normal draws)",
                     predictor=pred, cost=cost, K=K, T=T, steps=steps, target_position=tp, target_equilibrium=te,
                     n=10, dt=0.02, p=10, cc_weight=1.0, R=1.0, LBD=100.0, NU=1000.0, SQRTRHOINV=0.03)
+        if big:
+            import hashlib
+            meta.update(eps_seed=1, eps_sha256=hashlib.sha256(eps_all.tobytes()).hexdigest(),
+                        eps_recipe="gen = torch.Generator().manual_seed(eps_seed); per solve torch.normal(0.0, 1.0, "
+                                   "size=(K, n_ind, 1), generator=gen, dtype=torch.float32)[:, :, 0]")
         save("mppi_" + name, meta, **arrays)
 
 

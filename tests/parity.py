@@ -27,6 +27,25 @@ def load_golden(name):
     return z, meta
 
 
+def golden_eps(z, meta):
+    """The injected N(0,1) draws of an MPPI golden, [steps, K, n_ind].  The config-4-size fixtures do not store them
+    (2.9 MB per solve): they are regenerated from the seed exactly as oracle/gen_golden.py drew them and checked against
+    the recorded digest."""
+    if "eps" in z.files:
+        return z["eps"]
+    import hashlib
+
+    import torch
+    n_ind = int(np.ceil((meta["T"] - 1) / meta["p"])) + 1
+    gen = torch.Generator().manual_seed(meta["eps_seed"])
+    eps = np.stack([torch.normal(0.0, 1.0, size=(meta["K"], n_ind, 1), generator=gen, dtype=torch.float32).numpy()[:, :, 0]
+                    for _ in range(meta["steps"])], 0)
+    if hashlib.sha256(eps.tobytes()).hexdigest() != meta["eps_sha256"]:
+        import pytest
+        pytest.skip("torch's CPU generator does not reproduce the recorded draws on this host")
+    return eps
+
+
 def traj_err(a, b):
     """per-channel norm-wise relative error of trajectories a vs reference b ([..., 6])."""
     a = np.asarray(a, dtype=np.float64)
@@ -49,3 +68,30 @@ def vec_err(a, b):
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
     return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
+
+
+# ---- measured-error record ---------------------------------------------------------------------------------------
+# GPU parity tests call record(...) with the errors they measured; the file travels back from the GPU box in
+# gpurun_out/ and is committed as profiles/parity_r02.json, so that every tolerance in the tests can be read next to
+# the error actually achieved (tolerances are set to <= ~2x the measured value).
+_RECORD_PATH = os.environ.get("CPS_PARITY_RECORD") or os.path.join(os.path.dirname(GOLDEN), "..", "gpurun_out",
+                                                                   "parity_measured.json")
+
+
+def record(test, case, **values):
+    """Merge {test: {case: values}} into the measured-error file (best effort: never fails a test)."""
+    try:
+        path = os.path.abspath(_RECORD_PATH)
+        if not os.path.isdir(os.path.dirname(path)):
+            return
+        data = {}
+        if os.path.exists(path):
+            with open(path) as f:
+                data = json.load(f)
+        clean = {k: (float(v) if isinstance(v, (int, float, np.floating, np.integer)) else
+                     {kk: float(vv) for kk, vv in v.items()} if isinstance(v, dict) else str(v)) for k, v in values.items()}
+        data.setdefault(test, {})[case] = clean
+        with open(path, "w") as f:
+            json.dump(data, f, indent=1, sort_keys=True)
+    except Exception:
+        pass
