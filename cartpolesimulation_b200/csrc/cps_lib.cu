@@ -608,8 +608,10 @@ extern "C" int cps_mppi_step_host(cps_handle *h, const float *s_host, const floa
                                   float u_prev, float *u_out_host) {
     if (!h) return CPS_ERR_INVALID;
     if (!s_host || !u_out_host) return fail(h, CPS_ERR_INVALID, "cps_mppi_step_host: null pointer");
+    if (h->shard)   // a sharded solve ends with the merged partial record, not with a control: there is no u to return
+        return fail(h, CPS_ERR_INVALID, "cps_mppi_step_host: the handle is in shard mode (cps_mppi_set_shard); use cps_mppi_step + cps_mppi_finalize");
     CUDA_TRY(h, cudaSetDevice(h->cfg.device));
-    if (h->cfg.integrator != CPS_PREDICTOR_NEURAL && h->h_pin_dev && !h->shard) {
+    if (h->cfg.integrator != CPS_PREDICTOR_NEURAL && h->h_pin_dev) {
         // ODE predictors: ONE operation on the stream.  The state rides in the kernel's parameter block and the block that
         // finishes the update writes u straight into mapped pinned host memory; no copy in either direction.
         h->inline_s = s_host;
@@ -632,16 +634,17 @@ extern "C" int cps_mppi_step_host(cps_handle *h, const float *s_host, const floa
     return CPS_OK;
 }
 
+__global__ void fill_kernel(float *p, int n, float v) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
 extern "C" int cps_mppi_reset(cps_handle *h, float v) {
     if (!h) return CPS_ERR_INVALID;
     CUDA_TRY(h, cudaSetDevice(h->cfg.device));
-    const int T = h->cfg.horizon;
-    float *tmp = new float[T];
-    for (int i = 0; i < T; ++i) tmp[i] = v;
-    cudaError_t e = cudaMemcpyAsync(h->d_unom, tmp, sizeof(float) * T, cudaMemcpyHostToDevice, h->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-    delete[] tmp;
-    CUDA_TRY(h, e);
+    fill_kernel<<<(h->cfg.horizon + 255) / 256, 256, 0, h->stream>>>(h->d_unom, h->cfg.horizon, v);   // stream-ordered, no allocation
+    h->launches += 1;
+    CUDA_TRY(h, cudaGetLastError());
     return CPS_OK;
 }
 

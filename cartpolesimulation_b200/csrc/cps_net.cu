@@ -191,6 +191,9 @@ __global__ void __launch_bounds__(R * 8 + 32, 1) net_kernel(const __grid_constan
     const bool row_warp = tid >= NC;
     const int T = a.T;
     const int row0 = blockIdx.x * R;
+    // differential networks: autoregression_loop.run takes the integrating helper only in its general loop; with
+    // horizon == 1 the "0th iteration" branch hands out the raw network output (autoregression.py:49-70)
+    const bool diff = N.differential && T > 1;
 
     // ---- shared-memory carve-up ------------------------------------------------------------------------------
     float *wsm = smem;                              // [n_weights]
@@ -308,14 +311,14 @@ __global__ void __launch_bounds__(R * 8 + 32, 1) net_kernel(const __grid_constan
                 if (row_lead) {
                     for (int i = 0; i < N.n_state_in; ++i)
                         xin[(1 + i) * R + r_row] = fmaf(N.norm_a[1 + i], a.s0[(long long)kc * a.ss_b + N.in_idx[i]], N.norm_b[1 + i]);
-                    if (N.differential)  // dmah.set_starting_point (autoregression.py:145-146)
+                    if (diff)  // dmah.set_starting_point (autoregression.py:145-146)
                         for (int o = 0; o < N.n_out; ++o)
                             snorm[o * R + r_row] = fmaf(N.on_a[o], a.s0[(long long)kc * a.ss_b + N.out_idx[o]], N.on_b[o]);
                 }
             } else {
                 out_layer_row<R>(N, wsm, hlast_base + (N.type == CPS_NET_GRU ? p * hstride : 0), lane, y);
                 if (row_lead) {
-                    if (N.differential) {  // autoregression.py:149-154
+                    if (diff) {  // autoregression.py:149-154
 #pragma unroll
                         for (int o = 0; o < 6; ++o) {
                             if (o < N.n_out) {
@@ -361,7 +364,7 @@ __global__ void __launch_bounds__(R * 8 + 32, 1) net_kernel(const __grid_constan
     float J = 0.0f;
     if (row_warp) {
         out_layer_row<R>(N, wsm, hlast_base + (N.type == CPS_NET_GRU ? p * hstride : 0), lane, y);
-        if (N.differential && row_lead) {
+        if (diff && row_lead) {
 #pragma unroll
             for (int o = 0; o < 6; ++o)
                 if (o < N.n_out) y[o] = snorm[o * R + r_row] + fmaf(N.p1[o], y[o], N.p2[o]);

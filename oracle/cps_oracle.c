@@ -694,6 +694,28 @@ static void net_step(const net_t *N, const float *x, float *hstate, float *y, fl
     }
 }
 
+/* Differential networks (outputs named D_*): SI_Toolkit/src/SI_Toolkit/Predictors/autoregression.py:118-158
+ * (differential_model_autoregression_helper) + Functions/General/Normalising.py:111-186
+ * (get_scaling_function_for_output_of_differential_network).  The network predicts normalised derivatives; the helper
+ * keeps the normalised state of the output features, starting_point <- starting_point + (p1 * y + p2) with
+ * p1 = a * C * dt, p2 = a * D * dt (a: normalisation of the integrated variables, C / D: de-normalisation of the
+ * derivatives), hands it out as the step's output and gathers the next network input from it.
+ * The configuration is a process-wide switch consulted by cps_oracle_net_rollout (and through it by
+ * cps_oracle_mppi_step_net): p1 == NULL turns it off.  Test infrastructure: not thread safe by design. */
+static struct {
+    int on;
+    float p1[8], p2[8], on_a[8], on_b[8];
+    int out_to_in[8];
+} g_diff = {0, {0}, {0}, {0}, {0}, {0}};
+
+void cps_oracle_net_differential(const float *p1, const float *p2, const float *on_a, const float *on_b,
+                                 const int *out_to_in, int n_out, int n_state_in) {
+    g_diff.on = (p1 != NULL);
+    if (!p1) return;
+    for (int o = 0; o < n_out && o < 8; ++o) { g_diff.p1[o] = p1[o]; g_diff.p2[o] = p2[o]; g_diff.on_a[o] = on_a[o]; g_diff.on_b[o] = on_b[o]; }
+    for (int i = 0; i < n_state_in && i < 8; ++i) g_diff.out_to_in[i] = out_to_in[i];
+}
+
 /* Flat-argument entry (ctypes friendly).
  * weights: concatenation, per hidden layer l: GRU: w_ih, w_hh, b_ih, b_hh ; Dense: w, b ; then w_out, b_out.
  * Net inputs are [Q, state features in_idx[0..n_state_in)] (state indices into the 6-vector);
@@ -744,14 +766,33 @@ void cps_oracle_net_rollout(int net_type, int n_state_in, int n_layers, const in
             if (net_type == 0) memcpy(h, h0 + (h0_batched ? (size_t)b * Htot : 0), sizeof(float) * Htot);
             /* normalise the initial state features (:271,279) */
             for (int i = 0; i < n_state_in; ++i) x[1 + i] = norm_a[1 + i] * s[in_idx[i]] + norm_b[1 + i];
+            /* autoregression_loop.run takes the helper only in its general loop: with horizon == 1 the "0th iteration"
+             * branch hands out the raw network output (autoregression.py:49-70) */
+            const int diff = g_diff.on && T > 1;
+            float sp[8];
+            if (diff) /* dmah.set_starting_point(normalize_state(s)) (predictor_autoregressive_neural.py:276-277) */
+                for (int j = 0; j < n_out; ++j) sp[j] = g_diff.on_a[j] * s[out_idx[j]] + g_diff.on_b[j];
+            int has_angle = 0, has_sin = 0, has_cos = 0;
+            for (int j = 0; j < n_out; ++j) {
+                if (out_idx[j] == IDX_ANGLE) has_angle = 1;
+                if (out_idx[j] == IDX_SIN) has_sin = 1;
+                if (out_idx[j] == IDX_COS) has_cos = 1;
+            }
             for (int t = 0; t < T; ++t) {
                 x[0] = norm_a[0] * Q[(size_t)b * T + t] + norm_b[0];
                 net_step(&N, x, h, y, scratch);
+                if (diff) { /* autoregression.py:149-154 */
+                    for (int j = 0; j < n_out; ++j) { sp[j] = sp[j] + (g_diff.p1[j] * y[j] + g_diff.p2[j]); y[j] = sp[j]; }
+                }
                 float *o = row + (size_t)(t + 1) * 6;
                 for (int j = 0; j < 6; ++j) o[j] = 0.0f;
                 for (int j = 0; j < n_out; ++j) o[out_idx[j]] = denorm_A[j] * y[j] + denorm_B[j];
-                o[IDX_ANGLE] = atan2f(o[IDX_SIN], o[IDX_COS]);
-                for (int i = 0; i < n_state_in && i < n_out; ++i) x[1 + i] = y[i]; /* feed back normalised output */
+                /* predictor_output_augmentation._augment (predictors_customization.py:120-139) */
+                if (!has_angle && has_sin && has_cos) o[IDX_ANGLE] = atan2f(o[IDX_SIN], o[IDX_COS]);
+                if (has_angle && !has_sin) o[IDX_SIN] = sinf(o[IDX_ANGLE]);
+                if (has_angle && !has_cos) o[IDX_COS] = cosf(o[IDX_ANGLE]);
+                if (diff) for (int i = 0; i < n_state_in; ++i) x[1 + i] = sp[g_diff.out_to_in[i]];
+                else for (int i = 0; i < n_state_in && i < n_out; ++i) x[1 + i] = y[i]; /* feed back normalised output */
             }
             if (h_final && net_type == 0) memcpy(h_final + (size_t)b * Htot, h, sizeof(float) * Htot);
         }

@@ -270,6 +270,7 @@ def main(which=None):
         from oracle import gen_golden_net
         todo["net"] = gen_golden_net.gen_net
         todo["mppi_net"] = gen_golden_net.gen_mppi_net
+        todo["net_diff"] = gen_golden_net.gen_net_diff
     except ImportError:
         pass
     for k, fn in todo.items():

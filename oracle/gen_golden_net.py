@@ -29,7 +29,12 @@ NORM = {"Q": (0, 0.5, 1.0, -1.0), "angle": (0, 1.8, np.pi, -np.pi), "angleD": (0
         "positionD": (0, 0.3, 1.125, -1.125)}
 
 
-def write_model_dir(root, full_name, net_type_name, seed, weight_scale=1.0):
+# differential networks (outputs D_*): value ranges of the derivatives for the normalisation table
+NORM_D = {"D_angle": (0, 4.0, 18.38, -18.38), "D_angleD": (0, 20.0, 90.0, -90.0), "D_angle_cos": (0, 3.0, 15.0, -15.0),
+          "D_angle_sin": (0, 3.0, 15.0, -15.0), "D_position": (0, 0.3, 1.125, -1.125), "D_positionD": (0, 2.0, 9.0, -9.0)}
+
+
+def write_model_dir(root, full_name, net_type_name, seed, weight_scale=1.0, INPUTS=INPUTS, OUTPUTS=OUTPUTS, NORM=NORM):
     import torch
     from SI_Toolkit.Functions.Pytorch.Network import Sequence
     d = os.path.join(root, full_name)
@@ -114,6 +119,80 @@ def gen_net():
         shutil.rmtree(root, ignore_errors=True)
 
 
+DIFF_NETS = (
+    # full name, type, seed, weight scale, inputs, outputs
+    ("GRU-6IN-32H1-32H2-5OUT-1", "GRU", 21, 1.5,
+     ["Q", "position", "positionD", "angle_cos", "angle_sin", "angleD"],            # permuted w.r.t. the outputs
+     ["D_angleD", "D_angle_cos", "D_angle_sin", "D_position", "D_positionD"]),
+    ("Dense-5IN-32H1-32H2-4OUT-1", "Dense", 22, 1.5,
+     ["Q", "angle", "angleD", "position", "positionD"],                            # angle output: sin/cos are augmented
+     ["D_angle", "D_angleD", "D_position", "D_positionD"]),
+    ("GRU-6IN-64H1-64H2-5OUT-1", "GRU", 23, 1.0, INPUTS, ["D_" + o for o in OUTPUTS]),
+)
+
+
+def gen_net_diff():
+    """Differential networks (outputs named D_*): predictor_autoregressive_neural with the
+    differential_model_autoregression_helper (Predictors/autoregression.py:118-158, Normalising.py:111-186), the
+    unmodified reference on synthetic seeded weights.  Also the horizon == 1 case, which the reference's loop routes
+    around the helper (autoregression.py:49-70)."""
+    import torch
+    R.load()
+    from SI_Toolkit.Predictors.predictor_autoregressive_neural import predictor_autoregressive_neural
+    rng = np.random.default_rng(123)
+    norm = dict(NORM)
+    norm.update(NORM_D)
+    root = tempfile.mkdtemp(prefix="cps_models_")
+    try:
+        for full_name, tname, seed, scale, inputs, outputs in DIFF_NETS:
+            sd = write_model_dir(root, full_name, tname, seed, scale, inputs, outputs, norm)
+            K, T = 64, 50
+            arrays = {"state_dict_keys": np.array(list(sd.keys()))}
+            for k, v in sd.items():
+                arrays["w__" + k] = v
+            with contextlib.redirect_stdout(io.StringIO()), torch.inference_mode():
+                pred = predictor_autoregressive_neural(model_name=full_name, path_to_model=root + os.sep, horizon=T,
+                                                       dt=0.02, batch_size=K, disable_individual_compilation=True,
+                                                       update_before_predicting=False)
+                assert pred.differential_network
+                s_single = hanging_state()
+                s0 = np.tile(s_single, (K, 1))
+                Q = np.clip(rng.normal(0, 0.3, (K, T, 1)), -1, 1).astype(np.float32)
+                out1 = pred.predict_core(torch.from_numpy(s0), torch.from_numpy(Q)).numpy().astype(np.float32)
+                s_cur = s0.copy()
+                s_seq, q_seq = [], []
+                for i in range(2):
+                    q0 = np.full((K, 1, 1), 0.25 * (i + 1) - 0.3, dtype=np.float32)
+                    pred.update_internal_state_tf(torch.from_numpy(q0), torch.from_numpy(s_cur))
+                    s_seq.append(s_cur[0].copy())
+                    q_seq.append(float(q0[0, 0, 0]))
+                    s_cur = s_cur.copy()
+                    s_cur[:, 1] += 0.05
+                s_rand = make_states(rng, K, "random")
+                out3 = pred.predict_core(torch.from_numpy(s_rand), torch.from_numpy(Q)).numpy().astype(np.float32)
+                h_after = None
+                if tname == "GRU":
+                    h_after = np.stack([h[0].numpy() for h in pred.memory_states_ref[0]], 0).astype(np.float32)
+                # horizon 1: a second predictor object (the horizon is fixed at construction)
+                pred1 = predictor_autoregressive_neural(model_name=full_name, path_to_model=root + os.sep, horizon=1,
+                                                        dt=0.02, batch_size=K, disable_individual_compilation=True,
+                                                        update_before_predicting=False)
+                out_h1 = pred1.predict_core(torch.from_numpy(s_rand), torch.from_numpy(Q[:, :1])).numpy().astype(np.float32)
+            arrays.update(s0=s_single, Q=Q[:, :, 0], traj_zero_h=out1, upd_s=np.stack(s_seq),
+                          upd_q=np.array(q_seq, dtype=np.float32), s_rand=s_rand, traj_rand=out3, traj_rand_T1=out_h1,
+                          norm_table=np.array([[norm[c][r] for c in norm] for r in range(4)], dtype=np.float64),
+                          norm_cols=np.array(list(norm.keys())))
+            if h_after is not None:
+                arrays["h_after_updates"] = h_after
+            meta = dict(ref="SI_Toolkit/Predictors/predictor_autoregressive_neural.py:266-313 + autoregression.py:118-158 + "
+                            "Functions/General/Normalising.py:111-186 (torch Sequence, synthetic seeded weights, differential)",
+                        net=full_name, type=tname, inputs=inputs, outputs=outputs, K=K, T=T, seed=seed, weight_scale=scale,
+                        dt=0.02, differential=True)
+            save("net_diff_" + full_name.replace("-", "_"), meta, **arrays)
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
+
+
 class NeuralCoreAdapter:
     """PredictorWrapper-shaped holder around the unmodified predictor_autoregressive_neural, with the wrapper's
     `update` (SI_Toolkit/src/SI_Toolkit/Predictors/predictor_wrapper.py:173-177)."""
@@ -148,11 +227,22 @@ def gen_mppi_net():
     from SI_Toolkit.Predictors.predictor_autoregressive_neural import predictor_autoregressive_neural
     root = tempfile.mkdtemp(prefix="cps_models_")
     try:
-        for (run, full_name, tname, seed, scale, cost, K, T, steps) in (
-                ("gru64_gradmin", "GRU-6IN-64H1-64H2-5OUT-0", "GRU", 7, 1.0, "quadratic_boundary_grad_minimal", 256, 50, 4),
-                ("gru32_grad", "GRU-6IN-32H1-32H2-5OUT-0", "GRU", 8, 2.0, "quadratic_boundary_grad", 128, 35, 3),
-                ("dense32_gradmin", "Dense-6IN-32H1-32H2-5OUT-0", "Dense", 9, 1.5, "quadratic_boundary_grad_minimal", 128, 50, 3)):
-            sd = write_model_dir(root, full_name, tname, seed, scale)
+        norm_d = dict(NORM)
+        norm_d.update(NORM_D)
+        only = [x for x in os.environ.get("CPS_GOLDEN_ONLY", "").split(",") if x]
+        for (run, full_name, tname, seed, scale, cost, K, T, steps, inputs, outputs, norm) in (
+                ("gru64_gradmin", "GRU-6IN-64H1-64H2-5OUT-0", "GRU", 7, 1.0, "quadratic_boundary_grad_minimal", 256, 50, 4, INPUTS, OUTPUTS, NORM),
+                ("gru32_grad", "GRU-6IN-32H1-32H2-5OUT-0", "GRU", 8, 2.0, "quadratic_boundary_grad", 128, 35, 3, INPUTS, OUTPUTS, NORM),
+                ("dense32_gradmin", "Dense-6IN-32H1-32H2-5OUT-0", "Dense", 9, 1.5, "quadratic_boundary_grad_minimal", 128, 50, 3, INPUTS, OUTPUTS, NORM),
+                # differential network (a15) under the optimizer, incl. the post-solve hidden-state update
+                ("diff_gru32_gradmin", DIFF_NETS[0][0], "GRU", DIFF_NETS[0][2], DIFF_NETS[0][3], "quadratic_boundary_grad_minimal",
+                 128, 50, 3, DIFF_NETS[0][4], DIFF_NETS[0][5], norm_d),
+                # the MAX_COST plugin with the neural predictor (backend-ordered cost mean in net_kernel)
+                ("gru32_qb", "GRU-6IN-32H1-32H2-5OUT-0", "GRU", 8, 2.0, "quadratic_boundary", 128, 50, 2, INPUTS, OUTPUTS, NORM)):
+            if only and run not in only:
+                continue
+            NORM_RUN = norm
+            sd = write_model_dir(root, full_name, tname, seed, scale, inputs, outputs, norm)
             lib = R.torch_lib()
             if cost == "quadratic_boundary_grad":
                 from oracle.gen_golden import _patch_torch_lib_for_grad
@@ -188,13 +278,14 @@ def gen_mppi_net():
                     arrays["traj0"] = opt.logging_values["rollout_trajectories_logged"][:32].astype(np.float32)
                 s = O.rollout("ODE", s, np.array([[u]], dtype=np.float32), n=10, dt=0.02)[0, 1]
             arrays.update(s=np.stack(S), u=np.array(U), u_nom=np.stack(UNOM), J=np.stack(JJ), u_prev=np.array(UPREV),
-                          norm_table=np.array([[NORM[c][r] for c in NORM] for r in range(4)], dtype=np.float64),
-                          norm_cols=np.array(list(NORM.keys())))
+                          norm_table=np.array([[NORM_RUN[c][r] for c in NORM_RUN] for r in range(4)], dtype=np.float64),
+                          norm_cols=np.array(list(NORM_RUN.keys())))
             if HH:
                 arrays["h_after"] = np.stack(HH)
             meta = dict(ref="Control_Toolkit/Optimizers/optimizer_mppi.py:180-224 + predictor_autoregressive_neural.py:266-352 "
                             "(torch lib, injected rng.normal draws, synthetic seeded weights)",
-                        net=full_name, type=tname, inputs=INPUTS, outputs=OUTPUTS, predictor="neural", cost=cost, K=K, T=T,
+                        net=full_name, type=tname, inputs=inputs, outputs=outputs, predictor="neural", cost=cost, K=K, T=T,
+                        differential=any(o.startswith("D_") for o in outputs),
                         steps=steps, target_position=0.0, target_equilibrium=1.0, dt=0.02, p=10, cc_weight=1.0, R=1.0,
                         LBD=100.0, NU=1000.0, SQRTRHOINV=0.03, seed=seed, weight_scale=scale)
             save("mppi_net_" + run, meta, **arrays)

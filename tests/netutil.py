@@ -39,11 +39,23 @@ def net_spec_from_golden(z):
     out_layer = (z[f"w__layers.{n_lay}.weight"], z[f"w__layers.{n_lay}.bias"])
     cols = [str(c) for c in z["norm_cols"]]
     a, b, _, _ = minmax_sym_coeffs(z["norm_table"], cols, inputs)
-    _, _, A, B = minmax_sym_coeffs(z["norm_table"], cols, outputs)
+    # differential networks (outputs D_*): the integrated variables carry the output names without the prefix
+    # (predictor_autoregressive_neural.py:184-190)
+    out_names = [(o[2:] if o[:2] == "D_" else o) for o in outputs]
+    _, _, A, B = minmax_sym_coeffs(z["norm_table"], cols, out_names)
+    diff = None
+    if any("D_" in o for o in outputs):
+        # Normalising.py:111-186: p1 = a * C * dt, p2 = a * D * dt with a of the integrated variables and C, D of the
+        # derivatives; autoregression.py:137-146: state -> output and output -> input index maps
+        on_a, on_b, _, _ = minmax_sym_coeffs(z["norm_table"], cols, out_names)
+        _, _, Cd, Dd = minmax_sym_coeffs(z["norm_table"], cols, outputs)
+        dt = np.float32(meta["dt"])
+        diff = dict(p1=(on_a * Cd * dt).astype(np.float32), p2=(on_a * Dd * dt).astype(np.float32), on_a=on_a, on_b=on_b,
+                    out_to_in=[out_names.index(n) for n in inputs[1:]])
     return dict(net_type=ntype, hsz=hsz, layers=layers, out_layer=out_layer,
                 in_idx=[STATE_VARIABLES.index(n) for n in inputs[1:]],
-                out_idx=[STATE_VARIABLES.index(n) for n in outputs],
-                norm_a=a, norm_b=b, denorm_A=A, denorm_B=B, meta=meta)
+                out_idx=[STATE_VARIABLES.index(n) for n in out_names],
+                norm_a=a, norm_b=b, denorm_A=A, denorm_B=B, diff=diff, meta=meta)
 
 
 def write_model_dir(root, z):

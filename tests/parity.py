@@ -70,6 +70,32 @@ def vec_err(a, b):
     return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
 
 
+def shifted_cost_stats(J, J_ref):
+    """Costs of the MAX_COST plugins (default / quadratic_boundary).  A rollout that stays clear of the 1e9 track-end
+    barrier ("quiet") has every cost entry at -6.00002e9 + O(1e4), quantised to 512, and the T+1 entries are summed in
+    the backend's order, so its J must agree BIT FOR BIT (up to the rare stage cost that straddles a rounding
+    boundary).  Rollouts that touch the barrier carry costs that are continuous (and steep) in the state, or -- with the
+    edge bounce of ODE_v0 -- discontinuous; they have zero weight in the update and are compared relatively.
+    Returns (fraction of quiet rollouts that are bit-equal, fraction of the others within 1e-3 relative)."""
+    J, J_ref = np.asarray(J), np.asarray(J_ref)
+    quiet = J_ref < -5.0e9   # ~ -(T / (T + 1)) MAX_COST; any real barrier contact lifts J far above this
+    if quiet.any():
+        quiet &= J_ref < J_ref[quiet].min() + 1e5
+    exact = float((J[quiet] == J_ref[quiet]).mean()) if quiet.any() else 1.0
+    loud_ok = 1.0
+    if (~quiet).any():
+        rel = np.abs(J[~quiet].astype(np.float64) - J_ref[~quiet]) / np.abs(J_ref[~quiet]).astype(np.float64)
+        loud_ok = float((rel < 1e-3).mean())
+    return exact, loud_ok
+
+
+def shifted_cost_ok(J, J_ref, min_exact=0.98):
+    exact, loud_ok = shifted_cost_stats(J, J_ref)
+    # barrier rollouts: the penalty is steep (6e11 (depth / 0.0099)^2), and ODE_v0's edge bounce forks a trajectory on a
+    # 1-ulp difference in the position, so a few per cent of them legitimately differ by more than 1e-3 (measured 1.05 %)
+    return exact >= min_exact and loud_ok >= 0.95
+
+
 # ---- measured-error record ---------------------------------------------------------------------------------------
 # GPU parity tests call record(...) with the errors they measured; the file travels back from the GPU box in
 # gpurun_out/ and is committed as profiles/parity_r02.json, so that every tolerance in the tests can be read next to

@@ -10,7 +10,7 @@ cases carry the looser, measured bound that two IEEE restatements of the same fo
 import numpy as np
 import pytest
 
-from tests.parity import golden_eps, load_golden, record, traj_err, vec_err
+from tests.parity import golden_eps, load_golden, record, shifted_cost_ok, shifted_cost_stats, traj_err, vec_err
 
 pytestmark = pytest.mark.gpu
 
@@ -119,13 +119,12 @@ def test_cost_kernels_vs_reference_golden(name):
             if big.any():
                 assert np.abs(un[big] - ref_un[big]).max() / np.abs(ref_un[big]).max() < 2e-6
             assert np.abs(un[~big] - ref_un[~big]).max() <= 512.0
-            assert vec_err(J, ref_J) < 1e-6
-            # the T+1 entries are summed in the backend's order (RowSumPlan), so the MAX_COST-shifted means agree bit
-            # for bit unless a stage cost straddles a 512-wide rounding boundary
-            exact = float((J == ref_J).mean())
-            record("cost_kernels_vs_reference_golden", f"{name}/{i}", J_bit_exact_fraction=exact,
-                   stage_bit_exact_fraction=float((st == ref_stage).mean()))
-            assert exact > 0.98, exact
+            # the T+1 entries are summed in the backend's order (RowSumPlan), so the MAX_COST-shifted means of
+            # rollouts clear of the barrier agree bit for bit unless a stage cost straddles a 512-wide rounding boundary
+            exact, loud = shifted_cost_stats(J, ref_J)
+            record("cost_kernels_vs_reference_golden", f"{name}/{i}", J_bit_exact_fraction_quiet=exact,
+                   J_barrier_within_1e3_fraction=loud, stage_bit_exact_fraction=float((st == ref_stage).mean()))
+            assert shifted_cost_ok(J, ref_J), (exact, loud)
         else:
             record("cost_kernels_vs_reference_golden", f"{name}/{i}", stage=vec_err(st, ref_stage), J=vec_err(J, ref_J))
             assert vec_err(st, ref_stage) < 2e-6
@@ -175,15 +174,16 @@ def test_mppi_step_vs_reference_golden(run, variant):
             assert max(traj_err(traj[:32].cpu().numpy(), z["traj0"]).values()) < 1e-5
         Jg = J.cpu().numpy()
         du, dn = abs(u - float(z["u"][i])), float(np.abs(u_nom - z["u_nom"][i]).max())
-        record("mppi_step_vs_reference_golden", f"{run}/{variant}/{i}", J=vec_err(Jg, z["J"][i]), u=du, u_nom=dn,
-               J_bit_exact_fraction=float((Jg == z["J"][i]).mean()))
         if m["cost"] in ("default", "quadratic_boundary"):
             # MAX_COST plugins: every cost entry is quantised to 512 at -6e9 and the row sum to 32768 at -3e11; the
             # kernel sums in the backend's order (RowSumPlan), so J agrees bit for bit except where a stage cost
-            # straddles a rounding boundary, and the control follows
-            assert vec_err(Jg, z["J"][i]) < 1e-6
-            assert (Jg == z["J"][i]).mean() > 0.98
+            # straddles a rounding boundary (or the rollout runs into the barrier), and the control follows
+            exact, loud = shifted_cost_stats(Jg, z["J"][i])
+            record("mppi_step_vs_reference_golden", f"{run}/{variant}/{i}", u=du, u_nom=dn, J_bit_exact_fraction_quiet=exact,
+                   J_barrier_within_1e3_fraction=loud)
+            assert shifted_cost_ok(Jg, z["J"][i]), (exact, loud)
         else:
+            record("mppi_step_vs_reference_golden", f"{run}/{variant}/{i}", J=vec_err(Jg, z["J"][i]), u=du, u_nom=dn)
             # J inherits the fp32 rounding noise of the trajectories (floor ~1e-5 of max|J|, see
             # test_fp32_noise_floor); the functional criterion is the control, 1e-4
             assert vec_err(Jg, z["J"][i]) < J_TOL
@@ -221,12 +221,15 @@ def test_mppi_step_vs_oracle(integ, cost, K, T, p):
     J = torch.empty(K, device="cuda")
     u = eng.mppi_step(cuda(s), cuda(eps.T), L.TIME_MAJOR, 0.1, None, J)
     Jg = J.cpu().numpy()
-    record("mppi_step_vs_oracle", f"{integ}/{cost}/K{K}/T{T}/p{p}", J=vec_err(Jg, ref["J"]),
-           u=abs(float(u.cpu()[0]) - float(ref["u"])), u_nom=float(np.abs(eng.get_u_nom() - ref["u_nom"]).max()),
-           J_bit_exact_fraction=float((Jg == ref["J"]).mean()))
-    assert vec_err(Jg, ref["J"]) < 1e-5
-    if cost in ("default", "quadratic_boundary"):
-        assert (Jg == ref["J"]).mean() > 0.98   # backend-ordered row sum: bit-equal means up to bucket-boundary cases
+    shifted = cost in ("default", "quadratic_boundary")
+    rec = dict(u=abs(float(u.cpu()[0]) - float(ref["u"])), u_nom=float(np.abs(eng.get_u_nom() - ref["u_nom"]).max()))
+    if shifted:   # backend-ordered row sum: bit-equal means up to bucket-boundary cases and barrier rollouts
+        rec["J_bit_exact_fraction_quiet"], rec["J_within_1e-3_fraction_barrier"] = shifted_cost_stats(Jg, ref["J"])
+        assert shifted_cost_ok(Jg, ref["J"]), rec
+    else:
+        rec["J"] = vec_err(Jg, ref["J"])
+        assert rec["J"] < 1e-5
+    record("mppi_step_vs_oracle", f"{integ}/{cost}/K{K}/T{T}/p{p}", **rec)
     assert abs(float(u.cpu()[0]) - float(ref["u"])) < 1e-4
     np.testing.assert_allclose(eng.get_u_nom(), ref["u_nom"], rtol=0, atol=1e-4)
     # DIRECT noise mode fed with the oracle's interpolated perturbations must agree with the INDUCING mode
@@ -235,7 +238,7 @@ def test_mppi_step_vs_oracle(integ, cost, K, T, p):
     eng_d.set_u_nom(u_nom0)
     J2 = torch.empty(K, device="cuda")
     u2 = eng_d.mppi_step(cuda(s), cuda(ref["delta_u"]), L.ROLLOUT_MAJOR, 0.1, None, J2)
-    assert vec_err(J2.cpu().numpy(), ref["J"]) < 1e-5
+    assert shifted_cost_ok(J2.cpu().numpy(), ref["J"]) if shifted else vec_err(J2.cpu().numpy(), ref["J"]) < 1e-5
     assert abs(float(u2.cpu()[0]) - float(ref["u"])) < 1e-4
     np.testing.assert_allclose(eng_d.get_u_nom(), ref["u_nom"], rtol=0, atol=1e-4)
 
