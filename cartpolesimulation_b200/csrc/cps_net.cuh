@@ -56,6 +56,7 @@ struct NetArgs {
     int *nonfinite;
     float *shard_out;
     float *h_ref;             // stored hidden state to advance after the solve (null: skip)
+    int tc_rows;              // net_tc_kernel: live rollouts per CTA (32 | 64 | 128 of the 128 tensor-memory lanes)
 };
 
 // ---- small device helpers ---------------------------------------------------------------------------------------

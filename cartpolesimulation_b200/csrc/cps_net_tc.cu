@@ -1,19 +1,28 @@
 // cps_net_tc.cu -- the GRU predictor on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a.
 //
-// net_tc_kernel<MPPI>: one CTA advances 128 rollouts (one per TMEM lane) of a 2 x 64 GRU through the horizon.
-//   * the gate GEMMs [128 rollouts] x [192 gates] x [K = 16 | 64] run as tcgen05.mma.kind::f16 with fp32 accumulators
-//     in tensor memory; weights (B operand) are resident in shared memory for the whole launch in the UMMA
-//     K-major core-matrix layout; activations (A operand) live in TENSOR MEMORY (".ts" form), written by the thread
-//     that owns the rollout with tcgen05.st -- no shared-memory round trip, no bank conflicts;
+// net_tc_kernel<MPPI>: one CTA advances 128 rollouts (one per TMEM lane) of a 2 x 64 GRU through the horizon as a
+// software pipeline of warp-specialised roles, so that the tensor pipe, the MUFU-bound gate epilogues and the per-rollout
+// bookkeeping overlap instead of taking turns:
+//   * warp 20 (converged, one elected lane executes): issues every tcgen05.mma.  Each layer is processed as two HALF-LAYER jobs of 32 hidden units
+//     ([r | z | n] gate columns of those units = 96 weight rows): per step the jobs 1a, 1b, 2a, 2b.  A job accumulates
+//     into one of THREE rotating 128-column tensor-memory regions {R, Z, NH, NI} (job j uses region j mod 3), which lets
+//     the recurrent products W_hh h of the NEXT jobs be issued into the two idle regions while the epilogue of the
+//     current job reads the third -- only the input products (W_ih1 x, W_ih2 h1) and the output layer stay on the
+//     step's critical path;
+//   * warps 0..15 (512 threads): gate epilogues.  Thread (rollout, quarter) reads its 8 units of the job's region with
+//     tcgen05.ld, applies the GRU non-linearities and writes h(t) back as the next A operand (tensor memory, ".ts"
+//     MMAs: no shared-memory round trip);
+//   * warps 16..19 (128 threads, one per rollout): the output layer's result -> next network input (shared memory A
+//     operand of the first layer), and off the critical path de-normalisation, angle augmentation, trajectory store,
+//     stage / terminal cost, MPPI perturbation interpolation;
+//   * hand-offs are mbarriers (tcgen05.commit towards the epilogue / row warps, per-warp arrivals towards the issuer).
 //   * fp32 accuracy from fp16 tensor cores: every operand is split x = hi + lo (two fp16 values after a power-of-two
 //     pre-scale that keeps lo out of the subnormal range: activations x 2^7, weight rows scaled to [64, 128)), and
 //     each product runs as three MMAs  hi*hi + lo*hi + hi*lo  into the same accumulator (the dropped lo*lo term is
 //     2^-22 relative).  The scales are undone, and the biases added, by one FMA in the epilogue;
-//   * 8 warps; thread (rollout, half) reads its 32 hidden units' accumulators with tcgen05.ld, applies the GRU
-//     non-linearities, and writes h(t) back as the next A operand; the "lead" half of the threads also carries the
-//     rollout's bookkeeping (feedback, de-normalisation, trajectory, cost, MPPI control) overlapped with the next
-//     step's first-layer MMAs;
 //   * MPPI = true: block partials, last-block merge and the stored-hidden-state update as in net_kernel.
+// Tensor memory (512 columns): 3 x 128 accumulator regions, h1 and h2 operands (hi + lo, 4 x 32); the output layer's 16
+// columns alias the NI columns of a region that is idle at that moment.
 // Reference: see cps_net.cu.  The tcgen05 building blocks were brought up with tools/tc/tc_test.cu.
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -26,14 +35,19 @@
 
 namespace {
 
-constexpr int TC_H = 64, TC_ROWS = 128, TC_NT = 256;
-// tensor-memory columns
-constexpr uint32_t C_ACC = 0, C_OUT = 256, C_AX_HI = 288, C_AX_LO = 296, C_AH1_HI = 304, C_AH1_LO = 336, C_AH2_HI = 368,
-                   C_AH2_LO = 400;
-// image offsets (bytes)
+constexpr int TC_H = 64, TC_ROWS = 128;
+constexpr int TC_EPI = 512, TC_ROWT = 128, TC_NT = TC_EPI + TC_ROWT + 32;   // epilogue warps 0-15, row warps 16-19, issuer warp 20
+constexpr int TC_EW = TC_EPI / 32, TC_EU = 32 / (TC_EW / 4);            // epilogue warps; units per epilogue thread and job (8)
+// tensor-memory columns: accumulator region r at 128 r = {NH [0,32), R [32,64), Z [64,96), NI [96,128)}: the recurrent
+// product of a job is ONE N = 96 MMA per k-step into {NH, R, Z}, the input product one N = 96 MMA into {R, Z, NI}
+constexpr uint32_t C_NH = 0, C_R = 32, C_Z = 64, C_NI = 96, C_AH1_HI = 384, C_AH1_LO = 416, C_AH2_HI = 448, C_AH2_LO = 480;
+// image offsets (bytes).  Weight rows are ordered by half-layer job jh (units 32 jh .. 32 jh + 31): 96 rows per job, gate
+// blocks [r | z | n] in the input matrices W_ih and [n | r | z] in the recurrent matrices W_hh (matching the columns above).
 constexpr uint32_t O_WIH1_HI = 0, O_WIH1_LO = 6144, O_WHH1_HI = 12288, O_WHH1_LO = 36864, O_WIH2_HI = 61440,
                    O_WIH2_LO = 86016, O_WHH2_HI = 110592, O_WHH2_LO = 135168, O_WOUT_HI = 159744, O_WOUT_LO = 161792,
-                   O_CST1 = 163840, O_CST2 = 165888, O_CSTO = 167936, TC_IMAGE_BYTES = 168064;
+                   O_CST1 = 163840, O_CST2 = 165888, O_CSTO = 167936, TC_IMAGE_BYTES = 168192;
+// after the image: the first layer's A operand x = [control, state features] (K = 16, hi and lo tiles), then float scratch
+constexpr uint32_t O_X_HI = TC_IMAGE_BYTES, O_X_LO = O_X_HI + 4096, O_FLOATS = O_X_LO + 4096;
 constexpr float A_SCALE = 128.0f, A_INV = 1.0f / 128.0f;
 
 __host__ __device__ inline uint32_t kmajor_off(int r, int k, int K) {  // UMMA K-major, no swizzle: 8 x 16 B core matrices
@@ -50,19 +64,39 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo) {
 __device__ __forceinline__ constexpr uint32_t idesc_f16(int N) {  // D fp32, A/B fp16 K-major, M = 128
     return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
+// The MMA-issuing code is executed by ALL lanes of the issuer warp, converged, on warp-uniform operands; one elected lane
+// executes the instruction.  (Issued from a divergent `if (lane == 0)` branch the compiler wraps every UTCHMMA into a
+// lane-uniformisation loop and the descriptor arithmetic leaves the uniform datapath: measured ~200 cycles per MMA
+// instead of N / 2 + 10, tools/tc/mma_cost.cu.)
+// A operand in tensor memory
 __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                 "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+    asm volatile("{\n\t.reg .pred p, e;\n\tsetp.ne.b32 p, %4, 0;\n\telect.sync _|e, 0xffffffff;\n\t"
+                 "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
                  ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+// A operand in shared memory
+__device__ __forceinline__ void tc_mma_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n\t.reg .pred p, e;\n\tsetp.ne.b32 p, %4, 0;\n\telect.sync _|e, 0xffffffff;\n\t"
+                 "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {   // whole warp, one elected lane arrives
+    asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+                 "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void bar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void bar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Waiting warps share their scheduler with working ones: the suspend-time hint parks the thread in hardware until the phase
+// completes (or the hint expires) instead of polling, which would take issue slots from the epilogue warps.
 __device__ __forceinline__ void bar_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok = 0;
     while (!ok)
-        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok) : "r"(bar), "r"(parity), "r"(20000u) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -72,6 +106,13 @@ __device__ __forceinline__ void tc_sync() {
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+}
+// one warp -> the issuer: this warp's tensor-memory stores / loads are done (count one arrival per warp)
+__device__ __forceinline__ void warp_signal(uint32_t bar, int lane) {
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) bar_arrive(bar);
 }
 __device__ __forceinline__ void ld16(uint32_t addr, uint32_t (&v)[16]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -86,6 +127,14 @@ __device__ __forceinline__ void ld8(uint32_t addr, uint32_t (&v)[8]) {
 __device__ __forceinline__ void st8(uint32_t addr, const uint32_t (&v)[8]) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
                  ::"r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+__device__ __forceinline__ void ld4(uint32_t addr, uint32_t (&v)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(addr));
+}
+__device__ __forceinline__ void st4(uint32_t addr, const uint32_t (&v)[4]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
+                 ::"r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
 }
 __device__ __forceinline__ void ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -115,116 +164,173 @@ __device__ __forceinline__ float2 unpack_h2(uint32_t v) {
     return __half22float2(*reinterpret_cast<const __half2 *>(&v));
 }
 
-// 16 consecutive values of one rollout -> A operand (8 hi + 8 lo columns at column offset c0 of the two regions)
-__device__ __forceinline__ void write_operand16(uint32_t tl, uint32_t c_hi, uint32_t c_lo, const float (&v)[16]) {
-    uint32_t ph[8], pl[8];
+// 8 consecutive values of one rollout -> A operand (4 hi + 4 lo columns at column offset c0 of the two regions)
+__device__ __forceinline__ void write_operand8(uint32_t tl, uint32_t c_hi, uint32_t c_lo, const float (&v)[8]) {
+    uint32_t ph[4], pl[4];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
+    for (int q = 0; q < 4; ++q) {
         __half h0, l0, h1, l1;
         split_h(v[2 * q] * A_SCALE, h0, l0);
         split_h(v[2 * q + 1] * A_SCALE, h1, l1);
         ph[q] = pack_h2(h0, h1);
         pl[q] = pack_h2(l0, l1);
     }
-    st8(tl + c_hi, ph);
-    st8(tl + c_lo, pl);
+    st4(tl + c_hi, ph);
+    st4(tl + c_lo, pl);
 }
 // ... and back: (hi + lo) / scale
-__device__ __forceinline__ void read_operand16(uint32_t tl, uint32_t c_hi, uint32_t c_lo, float (&v)[16]) {
-    uint32_t ph[8], pl[8];
-    ld8(tl + c_hi, ph);
-    ld8(tl + c_lo, pl);
+__device__ __forceinline__ void read_operand8(uint32_t tl, uint32_t c_hi, uint32_t c_lo, float (&v)[8]) {
+    uint32_t ph[4], pl[4];
+    ld4(tl + c_hi, ph);
+    ld4(tl + c_lo, pl);
     ld_wait();
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
+    for (int q = 0; q < 4; ++q) {
         const float2 h = unpack_h2(ph[q]), l = unpack_h2(pl[q]);
         v[2 * q] = (h.x + l.x) * A_INV;
         v[2 * q + 1] = (h.y + l.y) * A_INV;
     }
 }
 
-// One GRU layer's MMAs: x-part (A = ax, K = Kx, W_ih rows 0..191 -> ACC[0,192)) then h-part (A = ah, K = 64, W_hh rows
-// 0..127 -> ACC[0,128) accumulating, rows 128..191 -> ACC[192,256)); three split passes each.  One thread.
-__device__ __forceinline__ void issue_layer(uint32_t tmem, uint32_t ax_hi, uint32_t ax_lo, int Kx, uint32_t bx_hi,
-                                            uint32_t bx_lo, uint32_t ah_hi, uint32_t ah_lo, uint32_t bh_hi, uint32_t bh_lo,
-                                            uint32_t bar) {
-    uint32_t acc = 0;
-    const uint32_t sbo_x = (uint32_t)(Kx >> 3) * 128u;
-#pragma unroll 1
-    for (int pass = 0; pass < 3; ++pass) {
-        const uint32_t a = (pass == 1) ? ax_lo : ax_hi, b = (pass == 2) ? bx_lo : bx_hi;
-        for (int ks = 0; ks < (Kx >> 4); ++ks) {
-            tc_mma(tmem + C_ACC, tmem + a + 8 * ks, make_desc(b + 256 * ks, sbo_x), idesc_f16(192), acc);
-            acc = 1;
-        }
-    }
-    uint32_t accn = 0;
-#pragma unroll 1
-    for (int pass = 0; pass < 3; ++pass) {
-        const uint32_t a = (pass == 1) ? ah_lo : ah_hi, b = (pass == 2) ? bh_lo : bh_hi;
+// ---- MMA issue (issuer warp, converged).  Half-layer job jh of a layer: weight rows [96 jh, 96 jh + 96). ----------------
+// Recurrent part W_hh h: one N = 96 MMA per pass and k-step -> {NH, R, Z} of the region, overwriting it.
+__device__ __forceinline__ void issue_H(uint32_t region, uint32_t ah_hi, uint32_t ah_lo, uint32_t bh_hi, uint32_t bh_lo, int jh) {
+    const uint32_t row = (uint32_t)jh * 12288u;   // 96 rows x (64 / 8) x 128 B / 8
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-            tc_mma(tmem + C_ACC, tmem + a + 8 * ks, make_desc(b + 256 * ks, 1024), idesc_f16(128), 1);
-            tc_mma(tmem + C_ACC + 192, tmem + a + 8 * ks, make_desc(b + 16 * 1024 + 256 * ks, 1024), idesc_f16(64), accn);
-            accn = 1;
-        }
+    for (int pass = 0; pass < 3; ++pass) {
+        const uint32_t a = (pass == 1) ? ah_lo : ah_hi, b = ((pass == 2) ? bh_lo : bh_hi) + row;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+            tc_mma(region + C_NH, a + 8 * ks, make_desc(b + 256 * ks, 1024), idesc_f16(96), (pass | ks) != 0);
     }
-    tc_commit(bar);
 }
-__device__ __forceinline__ void issue_out(uint32_t tmem, uint32_t b_hi, uint32_t b_lo, uint32_t bar) {
-    uint32_t acc = 0;
-#pragma unroll 1
+// Input part of the second layer, W_ih2 h1 (K = 64): {R, Z} accumulate on top of the recurrent part, NI is written fresh
+// by the first MMA (split in two for that) and accumulated by the rest.
+__device__ __forceinline__ void issue_X2(uint32_t region, uint32_t ah_hi, uint32_t ah_lo, uint32_t bx_hi, uint32_t bx_lo, int jh) {
+    const uint32_t row = (uint32_t)jh * 12288u;
+#pragma unroll
     for (int pass = 0; pass < 3; ++pass) {
-        const uint32_t a = (pass == 1) ? C_AH2_LO : C_AH2_HI, b = (pass == 2) ? b_lo : b_hi;
+        const uint32_t a = (pass == 1) ? ah_lo : ah_hi, b = ((pass == 2) ? bx_lo : bx_hi) + row;
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
-            tc_mma(tmem + C_OUT, tmem + a + 8 * ks, make_desc(b + 256 * ks, 1024), idesc_f16(16), acc);
-            acc = 1;
+            if ((pass | ks) == 0) {
+                tc_mma(region + C_R, a, make_desc(b, 1024), idesc_f16(64), 1);
+                tc_mma(region + C_NI, a, make_desc(b + 8192, 1024), idesc_f16(32), 0);
+            } else {
+                tc_mma(region + C_R, a + 8 * ks, make_desc(b + 256 * ks, 1024), idesc_f16(96), 1);
+            }
         }
     }
-    tc_commit(bar);
+}
+// Input part of the first layer, W_ih1 x (K = 16, A operand x in shared memory).
+__device__ __forceinline__ void issue_X1(uint32_t region, uint32_t ax_hi, uint32_t ax_lo, uint32_t bx_hi, uint32_t bx_lo, int jh) {
+    const uint32_t row = (uint32_t)jh * 3072u;    // 96 rows x (16 / 8) x 128 B / 8
+#pragma unroll
+    for (int pass = 0; pass < 3; ++pass) {
+        const uint64_t a = make_desc((pass == 1) ? ax_lo : ax_hi, 256);
+        const uint32_t b = ((pass == 2) ? bx_lo : bx_hi) + row;
+        if (pass == 0) {
+            tc_mma_ss(region + C_R, a, make_desc(b, 256), idesc_f16(64), 1);
+            tc_mma_ss(region + C_NI, a, make_desc(b + 2048, 256), idesc_f16(32), 0);
+        } else {
+            tc_mma_ss(region + C_R, a, make_desc(b, 256), idesc_f16(96), 1);
+        }
+    }
+}
+// Linear output layer W_out h2 -> 16 columns at `dst`.
+__device__ __forceinline__ void issue_OUT(uint32_t dst, uint32_t ah_hi, uint32_t ah_lo, uint32_t b_hi, uint32_t b_lo) {
+#pragma unroll
+    for (int pass = 0; pass < 3; ++pass) {
+        const uint32_t a = (pass == 1) ? ah_lo : ah_hi, b = (pass == 2) ? b_lo : b_hi;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+            tc_mma(dst, a + 8 * ks, make_desc(b + 256 * ks, 1024), idesc_f16(16), (pass | ks) != 0);
+    }
 }
 
-// GRU non-linearities for this thread's 32 hidden units (torch GRUCell, gate order r, z, n):
-// reads ACC = {R, Z, NI, NH} and h(t-1) (the A operand itself), writes h(t) as the new A operand.
-__device__ __forceinline__ void gru_epilogue(uint32_t tl, const float *cst, uint32_t c_hi, uint32_t c_lo, int half) {
-#pragma unroll 1
-    for (int ch = 0; ch < 2; ++ch) {
-        const int u0 = 32 * half + 16 * ch;
-        uint32_t R[16], Z[16], NI[16], NH[16];
-        ld16(tl + C_ACC + u0, R);
-        ld16(tl + C_ACC + 64 + u0, Z);
-        ld16(tl + C_ACC + 128 + u0, NI);
-        ld16(tl + C_ACC + 192 + u0, NH);
-        float h[16];
-        read_operand16(tl, c_hi + (u0 >> 1), c_lo + (u0 >> 1), h);   // includes the tcgen05.wait::ld
-#pragma unroll
-        for (int i = 0; i < 16; i += 2) {
-            // two units at a time: 6 exponentials + 2 reciprocals (instead of 6 + 6): 1/a = (b c d) / (a b c d).
-            // Pre-activations are clamped to +-20 (sigmoid(-20) = 2e-9, tanh(10) = 1 - 4e-9), which bounds the products.
-            const float4 c0 = *reinterpret_cast<const float4 *>(cst + (u0 + i) * 8);
-            const float4 c1 = *reinterpret_cast<const float4 *>(cst + (u0 + i) * 8 + 4);
-            const float4 d0 = *reinterpret_cast<const float4 *>(cst + (u0 + i + 1) * 8);
-            const float4 d1 = *reinterpret_cast<const float4 *>(cst + (u0 + i + 1) * 8 + 4);
-            const float ar = 1.0f + ex2_neg(fmaf(__uint_as_float(R[i]), c0.x, c0.y));
-            const float az = 1.0f + ex2_neg(fmaf(__uint_as_float(Z[i]), c0.z, c0.w));
-            const float br = 1.0f + ex2_neg(fmaf(__uint_as_float(R[i + 1]), d0.x, d0.y));
-            const float bz = 1.0f + ex2_neg(fmaf(__uint_as_float(Z[i + 1]), d0.z, d0.w));
-            const float pa = ar * az, pb = br * bz;
-            const float inv = rcp_f(pa * pb);
-            const float ia = pb * inv, ib = pa * inv;           // 1/(ar az), 1/(br bz)
-            const float r0 = az * ia, z0 = ar * ia, r1 = bz * ib, z1 = br * ib;
-            const float n0p = fmaf(r0, fmaf(__uint_as_float(NH[i]), c1.z, c1.w), fmaf(__uint_as_float(NI[i]), c1.x, c1.y));
-            const float n1p = fmaf(r1, fmaf(__uint_as_float(NH[i + 1]), d1.z, d1.w), fmaf(__uint_as_float(NI[i + 1]), d1.x, d1.y));
-            const float e0 = 1.0f + ex2_neg(-2.0f * n0p), e1 = 1.0f + ex2_neg(-2.0f * n1p);   // 1 + e^{2 n}
-            const float inv2 = rcp_f(e0 * e1);
-            const float n0 = fmaf(-2.0f * e1, inv2, 1.0f), n1 = fmaf(-2.0f * e0, inv2, 1.0f);  // tanh = 1 - 2 / (1 + e^{2n})
-            h[i] = fmaf(h[i] - n0, z0, n0);
-            h[i + 1] = fmaf(h[i + 1] - n1, z1, n1);
-        }
-        write_operand16(tl, c_hi + (u0 >> 1), c_lo + (u0 >> 1), h);
-    }
+__device__ __forceinline__ F2 f2bits(uint32_t a, uint32_t b) {
+    F2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "r"(a), "r"(b));
+    return r;
 }
+__device__ __forceinline__ float ex2_f(float t) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t));
+    return r;
+}
+__device__ __forceinline__ uint32_t pack_f16x2(float lo_v, float hi_v) {   // two floats -> fp16x2, round to nearest
+    uint32_t d;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi_v), "f"(lo_v));
+    return d;
+}
+
+// GRU non-linearities for 8 hidden units of one rollout (torch GRUCell, gate order r, z, n): reads the job's region
+// {NH, R, Z, NI} at column offset `cu` (= unit index inside the half layer) and h(t-1) (the A operand itself), writes h(t)
+// as the new A operand.  u0 = index of the first unit inside the layer (constants, operand columns).
+// Two units per step in packed FP32 (FFMA2 / FMUL2 / FADD2: the FMA-pipe work of the epilogue halves, which leaves the 4
+// MUFU operations per unit -- 3 exponentials and, shared between two units, 2 reciprocals: 1/a = (b c d) / (a b c d) --
+// as its bound).  c = 1 / (128 S) undoes the operand scales (uniform per layer), cn = -c log2 e; per pair of units the
+// constants are {-log2e (b_ir + b_hr), -log2e (b_iz + b_hz), b_in, b_hn} x 2.  Exponents are capped at 2^30, which
+// bounds the shared-reciprocal products; everything stays in the operand scale (h is kept as 128 h).
+#ifdef CPS_TC_TRACE
+__device__ long long g_epi_t[4];
+#define EPI_TR(i) if (threadIdx.x == 0 && blockIdx.x == 0) g_epi_t[i] = clock64()
+#else
+#define EPI_TR(i)
+#endif
+__device__ __forceinline__ void gru_epilogue8(uint32_t tl, uint32_t region, uint32_t cu, const float *cst, float c, float cn,
+                                               uint32_t c_hi, uint32_t c_lo, int u0) {
+    uint32_t R[8], Z[8], NI[8], NH[8], PH[4], PL[4];
+    EPI_TR(0);
+    ld8(tl + region + C_R + cu, R);
+    ld8(tl + region + C_Z + cu, Z);
+    ld8(tl + region + C_NI + cu, NI);
+    ld8(tl + region + C_NH + cu, NH);
+    ld4(tl + c_hi + (u0 >> 1), PH);
+    ld4(tl + c_lo + (u0 >> 1), PL);
+    ld_wait();
+    EPI_TR(1);
+    const float *kp = cst + (u0 >> 1) * 8;
+    const F2 C2 = f2(c), CN2 = f2(cn), ONE = f2(1.0f);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float4 k0 = *reinterpret_cast<const float4 *>(kp + 8 * q);       // brn0, brn1, bzn0, bzn1
+        const float4 k1 = *reinterpret_cast<const float4 *>(kp + 8 * q + 4);   // bni0, bni1, bnh0, bnh1
+        const F2 tr = fma2(f2bits(R[2 * q], R[2 * q + 1]), CN2, f2(k0.x, k0.y));    // -log2e * pre-activation
+        const F2 tz = fma2(f2bits(Z[2 * q], Z[2 * q + 1]), CN2, f2(k0.z, k0.w));
+        const F2 AR = add2(f2(ex2_f(fminf(lo(tr), 30.0f)), ex2_f(fminf(hi(tr), 30.0f))), ONE);   // 1 + e^{-r}
+        const F2 AZ = add2(f2(ex2_f(fminf(lo(tz), 30.0f)), ex2_f(fminf(hi(tz), 30.0f))), ONE);
+        const F2 PA = mul2(AR, AZ);
+        const float inv = rcp_f(lo(PA) * hi(PA));
+        const F2 IAB = mul2(f2(hi(PA), lo(PA)), f2(inv));          // 1 / (ar az) of each unit
+        const F2 R2 = mul2(AZ, IAB), Z2 = mul2(AR, IAB);           // sigmoids
+        const F2 tnh = fma2(f2bits(NH[2 * q], NH[2 * q + 1]), C2, f2(k1.z, k1.w));
+        const F2 tni = fma2(f2bits(NI[2 * q], NI[2 * q + 1]), C2, f2(k1.x, k1.y));
+        const F2 ta = mul2(fma2(R2, tnh, tni), f2(2.885390081777927f));               // 2 log2e * n pre-activation
+        const F2 E = add2(f2(ex2_f(fminf(lo(ta), 30.0f)), ex2_f(fminf(hi(ta), 30.0f))), ONE);   // 1 + e^{2n}
+        const float m2 = -256.0f * rcp_f(lo(E) * hi(E));
+        const F2 N128 = fma2(f2(hi(E), lo(E)), f2(m2), f2(128.0f));   // 128 tanh = 128 - 256 / (1 + e^{2n})
+        const float2 hh = unpack_h2(PH[q]), hl = unpack_h2(PL[q]);
+        const F2 HS = add2(f2(hh.x, hh.y), f2(hl.x, hl.y));          // 128 h(t-1)
+        const F2 HN = fma2(HS, Z2, fma2(neg2(N128), Z2, N128));      // 128 h(t) = 128 ((h - n) z + n)
+        PH[q] = pack_f16x2(lo(HN), hi(HN));
+        const float2 hf = unpack_h2(PH[q]);
+        const F2 L = add2(HN, f2(-hf.x, -hf.y));
+        PL[q] = pack_f16x2(lo(L), hi(L));
+    }
+    EPI_TR(2);
+    st4(tl + c_hi + (u0 >> 1), PH);
+    st4(tl + c_lo + (u0 >> 1), PL);
+    EPI_TR(3);
+}
+
+// Optional pipeline trace (-DCPS_TC_TRACE): cycle stamps of one step of block 0, printed by the issuer / one epilogue
+// thread / one row thread.  Used to find what a step waits for.
+#ifdef CPS_TC_TRACE
+#define TC_TR(i) tr[i] = clock64()
+#else
+#define TC_TR(i)
+#endif
 
 }  // namespace
 
@@ -232,32 +338,49 @@ template <bool MPPI>
 __global__ void __launch_bounds__(TC_NT, 1) net_tc_kernel(const __grid_constant__ NetArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint32_t s_tmem;
-    __shared__ __align__(8) unsigned long long s_wbar, s_mbar;
+    // mbarriers: 0 weights landed; 1..3 region r complete (issuer -> epilogue); 4 output layer complete (issuer -> rows);
+    // 5..8 epilogue of job 1a / 1b / 2a / 2b done (8 epilogue warps -> issuer); 9 next input written (4 row warps ->
+    // issuer); 10 hidden-state update after the solve
+    __shared__ __align__(8) unsigned long long s_bars[11];
     __shared__ unsigned s_ticket;
     __shared__ float s_bmin[4];
     const NetDev &N = a.net;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int half = warp >> 2, row = 32 * (warp & 3) + lane;
-    const bool lead = half == 0;
+    const bool is_epi = warp < TC_EW, is_row = warp >= TC_EW && warp < TC_EW + 4, is_mma = warp == TC_EW + 4;
+    const int sub = (warp >> 2) & 3;           // epilogue warps: which 8 of a job's 32 units
+    const int row = 32 * (warp & 3) + lane;    // rollout inside the tile (epilogue and row warps)
     const int T = a.T;
-    const int row0 = blockIdx.x * TC_ROWS;
+    // Small batches are latency-bound by the step's dependence chain, not by throughput: spreading the rollouts over more
+    // SMs with only the first 32 / 64 tensor-memory lanes of each CTA live shortens the MUFU-bound epilogues (the MMAs
+    // cost the same for any number of live rows: M = 128 is the instruction's minimum).
+    const int row0 = blockIdx.x * a.tc_rows;
+    const bool live = row < a.tc_rows;         // warp-uniform (tc_rows is a multiple of 32)
     const int k = row0 + row;
-    const bool active = lead && k < a.B;
+    const bool active = is_row && live && k < a.B;
     const int kc = min(k, a.B - 1);
-    float *s_f = reinterpret_cast<float *>(smem + TC_IMAGE_BYTES);
+    float *s_f = reinterpret_cast<float *>(smem + O_FLOATS);
     float *s_unom = s_f;                                   // MPPI: [T] shifted nominal inputs, [p] w0, [p] w1, scratch
     float *s_w0 = s_unom + (MPPI ? a.mp.T : 0);
     float *s_w1 = s_w0 + (MPPI ? a.mp.p : 0);
-    float *s_red = s_w1 + (MPPI ? a.mp.p : 0);             // [4][n_red + 2] then [n_red + 2]
+    float *s_red = s_w1 + (MPPI ? a.mp.p : 0);             // [4][n_red + 2] then [n_red + 2 + warps]
+    float *s_rs = s_red + (MPPI ? 5 * (a.mp.n_red + 2) + 8 : 0);   // MAX_COST plugins: row-sum slots [32][128] (RowSumPlan)
     const float *cst1 = reinterpret_cast<const float *>(smem + O_CST1);
     const float *cst2 = reinterpret_cast<const float *>(smem + O_CST2);
-    const float *csto = reinterpret_cast<const float *>(smem + O_CSTO);
-    const uint32_t sm0 = smem_u32(smem), wbar = smem_u32(&s_wbar), mbar = smem_u32(&s_mbar);
+    const float *csto = reinterpret_cast<const float *>(smem + O_CSTO);   // [16][2] output layer, then {c, cn} of the two layers
+    const uint32_t sm0 = smem_u32(smem), bars = smem_u32(s_bars);
+    const uint32_t wbar = bars, outb = bars + 32, xrdy = bars + 72, tailb = bars + 80;
+    auto doneb = [&](int r) { return bars + 8u + 8u * (uint32_t)r; };
+    auto epib = [&](int job) { return bars + 40u + 8u * (uint32_t)job; };
 
     // ---- weights: bulk asynchronous copy; tensor memory; MPPI tables ------------------------------------------------
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(wbar));
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
+        bar_init(wbar, 1);
+        for (int r = 0; r < 3; ++r) bar_init(doneb(r), 1);
+        bar_init(outb, 1);
+        // arrivals come from the warps that carry live rollouts only; the others skip the horizon loop
+        for (int j = 0; j < 4; ++j) bar_init(epib(j), (uint32_t)(a.tc_rows / 32) * (TC_EW / 4));
+        bar_init(xrdy, (uint32_t)(a.tc_rows / 32));
+        bar_init(tailb, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(wbar), "r"(TC_IMAGE_BYTES) : "memory");
         for (uint32_t done = 0; done < TC_IMAGE_BYTES; done += 32768u) {
@@ -267,7 +390,7 @@ __global__ void __launch_bounds__(TC_NT, 1) net_tc_kernel(const __grid_constant_
         }
     }
     __syncwarp();
-    if (warp == 0) {
+    if (is_mma) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "n"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
@@ -278,24 +401,33 @@ __global__ void __launch_bounds__(TC_NT, 1) net_tc_kernel(const __grid_constant_
             s_w1[j] = (float)j / (float)a.mp.p;
         }
     }
+    for (int i = tid; i < 2048; i += TC_NT) reinterpret_cast<uint32_t *>(smem + O_X_HI)[i] = 0u;   // x tiles: k = 7..15 stay 0
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = s_tmem;
     const uint32_t tl = tmem + ((uint32_t)(32 * (warp & 3)) << 16);   // this warp's lane quarter
 
-    // ---- row bookkeeping (lead threads) ---------------------------------------------------------------------------------
+    // ---- row bookkeeping (row warps) ------------------------------------------------------------------------------------
     float Jacc = 0.0f, corr = 0.0f, up = a.u_prev, u_cur = 0.0f, du_cur = 0.0f, u_nxt = 0.0f, du_nxt = 0.0f;
     int seg = 0, jj = 0;
     float na = 0.0f, nb = 0.0f;
     const float *nz = nullptr, *qrow = nullptr;
     float *traj = (a.traj_out && active) ? a.traj_out + (long long)k * a.ts_k : nullptr;
-    if (MPPI) {
-        nz = a.noise + (long long)kc * a.ns_k;
-        na = nz[0] * a.mp.sigma;
-        nb = (a.mp.n_ind > 1) ? nz[a.ns_i] * a.mp.sigma : 0.0f;
-    } else {
-        qrow = a.Q + (long long)kc * a.qs_b;
+    // default / quadratic_boundary: the T+1 cost entries are summed in the reference backend's order (cps_device.cuh)
+    const bool rowsum = MPPI && (a.cost_id == CPS_COST_DEFAULT || a.cost_id == CPS_COST_QUADRATIC_BOUNDARY);
+    const RowSumPlan rsp = row_sum_plan(T + 1);
+    float *sl = s_rs + row;
+    float rs_tail = 0.0f;
+    if (is_row && live) {
+        if (MPPI) {
+            nz = a.noise + (long long)kc * a.ns_k;
+            na = nz[0] * a.mp.sigma;
+            nb = (a.mp.n_ind > 1) ? nz[a.ns_i] * a.mp.sigma : 0.0f;
+            if (rowsum) row_sum_init(rsp, sl, TC_ROWS);
+        } else {
+            qrow = a.Q + (long long)kc * a.qs_b;
+        }
     }
     auto next_control = [&](int t) {
         if (MPPI) {
@@ -310,36 +442,51 @@ __global__ void __launch_bounds__(TC_NT, 1) net_tc_kernel(const __grid_constant_
             u_nxt = qrow[(long long)t * a.qs_t];
         }
     };
-    // network input x = [control, state features] -> A operand (K padded to 16)
+    // network input x = [control, state features] -> shared-memory A operand of the first layer (K padded to 16; k >= 8 is
+    // zero for good).  Followed by the generic -> async proxy fence the tensor core's read needs.
     auto write_x = [&](float ctrl, const float (&feat)[6]) {
-        float x[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) x[i] = 0.0f;
+        float x[8];
         x[0] = fmaf(N.norm_a[0], ctrl, N.norm_b[0]);
 #pragma unroll
-        for (int i = 0; i < 6; ++i)
-            if (i < N.n_state_in) x[1 + i] = feat[i];
-        write_operand16(tl, C_AX_HI, C_AX_LO, x);
+        for (int i = 0; i < 6; ++i) x[1 + i] = (i < N.n_state_in) ? feat[i] : 0.0f;
+        x[7] = 0.0f;
+        uint32_t ph[4], pl[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            __half h0, l0, h1, l1;
+            split_h(x[2 * q] * A_SCALE, h0, l0);
+            split_h(x[2 * q + 1] * A_SCALE, h1, l1);
+            ph[q] = pack_h2(h0, h1);
+            pl[q] = pack_h2(l0, l1);
+        }
+        const uint32_t off = (uint32_t)(row >> 3) * 256u + (uint32_t)(row & 7) * 16u;
+        *reinterpret_cast<uint4 *>(smem + O_X_HI + off) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+        *reinterpret_cast<uint4 *>(smem + O_X_LO + off) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     };
+    // this thread's units of a layer, chunk ch = 0, 1: [32 ch + 8 sub, + 8) -- the units it handles in job (layer, ch)
+    auto chunk_u0 = [&](int ch) { return 32 * ch + TC_EU * sub; };
 
     // ---- initial operands -------------------------------------------------------------------------------------------------
-    {
-        float v[16];
+    float st[6], y[6], feat[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) { st[c] = 0.0f; y[c] = 0.0f; }
+    if (is_epi && live) {
+        float v[TC_EU];
 #pragma unroll 1
         for (int l = 0; l < 2; ++l) {
 #pragma unroll 1
             for (int ch = 0; ch < 2; ++ch) {
-                const int u0 = 32 * half + 16 * ch;
+                const int u0 = chunk_u0(ch);
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = a.h0[(long long)kc * a.hs_b + l * TC_H + u0 + i];
-                write_operand16(tl, (l ? C_AH2_HI : C_AH1_HI) + (u0 >> 1), (l ? C_AH2_LO : C_AH1_LO) + (u0 >> 1), v);
+                for (int i = 0; i < TC_EU; ++i) v[i] = a.h0[(long long)kc * a.hs_b + l * TC_H + u0 + i];
+                write_operand8(tl, (l ? C_AH2_HI : C_AH1_HI) + (u0 >> 1), (l ? C_AH2_LO : C_AH1_LO) + (u0 >> 1), v);
             }
         }
     }
-    float st[6], y[6], feat[6];
+    if (is_row && live) {
 #pragma unroll
-    for (int c = 0; c < 6; ++c) st[c] = a.s0[(long long)kc * a.ss_b + c];
-    if (lead) {
+        for (int c = 0; c < 6; ++c) st[c] = a.s0[(long long)kc * a.ss_b + c];
         next_control(0);
 #pragma unroll
         for (int i = 0; i < 6; ++i)
@@ -349,65 +496,173 @@ __global__ void __launch_bounds__(TC_NT, 1) net_tc_kernel(const __grid_constant_
     bar_wait(wbar, 0);   // weights have landed
     tc_sync();
 
+    const uint32_t AX_HI = sm0 + O_X_HI, AX_LO = sm0 + O_X_LO;
+    const float ec1 = csto[32], ecn1 = csto[33], ec2 = csto[34], ecn2 = csto[35];   // epilogue scale constants (see gru_epilogue16)
+    auto region = [&](int j) { return (uint32_t)(128 * (j % 3)); };   // column base of job j's accumulator region
+
     // ---- the horizon ------------------------------------------------------------------------------------------------------
-    uint32_t phase = 0;
+    if (is_mma) {
+        // warp-uniform operands (the compiler keeps them in uniform registers): tensor-memory base via a broadcast
+        const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
+        const uint32_t ah1_hi = tm + C_AH1_HI, ah1_lo = tm + C_AH1_LO, ah2_hi = tm + C_AH2_HI, ah2_lo = tm + C_AH2_LO;
+        // recurrent parts of the first two jobs (1a, 1b of step 0); job j accumulates in region j mod 3
+        issue_H(tm + 0, ah1_hi, ah1_lo, sm0 + O_WHH1_HI, sm0 + O_WHH1_LO, 0);
+        issue_H(tm + 128, ah1_hi, ah1_lo, sm0 + O_WHH1_HI, sm0 + O_WHH1_LO, 1);
+        int t3 = 0;   // t mod 3 = (4 t) mod 3: region index of job 1a of this step
 #pragma unroll 1
-    for (int t = 0; t < T; ++t) {
-        if (tid == 0)
-            issue_layer(tmem, C_AX_HI, C_AX_LO, 16, sm0 + O_WIH1_HI, sm0 + O_WIH1_LO, C_AH1_HI, C_AH1_LO, sm0 + O_WHH1_HI,
-                        sm0 + O_WHH1_LO, mbar);
-        if (lead) {  // under the first-layer MMAs: state s_t -> trajectory row, stage cost; next control
-            if (t > 0) compose_state(N, y, st);
-            if (traj) {
-#pragma unroll
-                for (int c = 0; c < 6; ++c) traj[(long long)t * a.ts_t + c * a.ts_c] = st[c];
-            }
-            u_cur = u_nxt; du_cur = du_nxt;
-            if (MPPI) {
-                Jacc += stage_cost_rt(a.cost_id, a.cost, cosf(st[IDX_ANGLE]), st[IDX_ANGLED], st[IDX_POS], u_cur, up);
-                corr = fmaf(a.mp.cc_half_nu * du_cur, du_cur,
-                            fmaf(a.mp.cc_R * u_cur, du_cur, fmaf(a.mp.cc_half_R * u_cur, u_cur, corr)));
-                if (a.u_run_out && active) a.u_run_out[(long long)k * T + t] = u_cur;
-                up = u_cur;
-            }
-            if (t + 1 < T) next_control(t + 1);
+        for (int t = 0; t < T; ++t) {
+            const uint32_t par = (uint32_t)(t & 1);
+            const bool more = t + 1 < T;
+            const int i1 = (t3 == 2) ? 0 : t3 + 1, i2 = (i1 == 2) ? 0 : i1 + 1;
+            const uint32_t q0 = tm + 128u * (uint32_t)t3, q1 = tm + 128u * (uint32_t)i1, q2 = tm + 128u * (uint32_t)i2;
+            // jobs of this step: 1a -> q0, 1b -> q1, 2a -> q2, 2b -> q0; next step: 1a -> q1, 1b -> q2, 2a -> q0
+#ifdef CPS_TC_TRACE
+            long long tr[12];
+#endif
+            TC_TR(0);
+            if (t > 0) { bar_wait(xrdy, (uint32_t)((t - 1) & 1)); tc_fence_after(); }   // x(t) is in shared memory
+            TC_TR(1);
+            issue_X1(q0, AX_HI, AX_LO, sm0 + O_WIH1_HI, sm0 + O_WIH1_LO, 0);
+            tc_commit(doneb(t3));
+            issue_X1(q1, AX_HI, AX_LO, sm0 + O_WIH1_HI, sm0 + O_WIH1_LO, 1);
+            tc_commit(doneb(i1));
+            // (after the critical input products) recurrent part of job 2a; its region was read by job 2b of step t - 1
+            issue_H(q2, ah2_hi, ah2_lo, sm0 + O_WHH2_HI, sm0 + O_WHH2_LO, 0);
+            TC_TR(2);
+            bar_wait(epib(0), par); tc_fence_after();      // job 1a read: its region takes job 2b's recurrent part
+            TC_TR(3);
+            issue_H(q0, ah2_hi, ah2_lo, sm0 + O_WHH2_HI, sm0 + O_WHH2_LO, 1);
+            TC_TR(4);
+            bar_wait(epib(1), par); tc_fence_after();      // h1(t) complete
+            TC_TR(5);
+            issue_X2(q2, ah1_hi, ah1_lo, sm0 + O_WIH2_HI, sm0 + O_WIH2_LO, 0);
+            tc_commit(doneb(i2));
+            issue_X2(q0, ah1_hi, ah1_lo, sm0 + O_WIH2_HI, sm0 + O_WIH2_LO, 1);
+            tc_commit(doneb(t3));
+            if (more) issue_H(q1, ah1_hi, ah1_lo, sm0 + O_WHH1_HI, sm0 + O_WHH1_LO, 0);
+            TC_TR(6);
+            bar_wait(epib(2), par); tc_fence_after();
+            TC_TR(7);
+            if (more) issue_H(q2, ah1_hi, ah1_lo, sm0 + O_WHH1_HI, sm0 + O_WHH1_LO, 1);
+            TC_TR(8);
+            bar_wait(epib(3), par); tc_fence_after();      // h2(t) complete; the region of job 2b is idle
+            TC_TR(9);
+            issue_OUT(q0 + C_NI, ah2_hi, ah2_lo, sm0 + O_WOUT_HI, sm0 + O_WOUT_LO);
+            tc_commit(outb);
+            TC_TR(10);
+#ifdef CPS_TC_TRACE
+            if (blockIdx.x == 0 && lane == 0 && t == 10)
+                printf("ISSUER t=%d: wait x %lld | X1a X1b H2a %lld | wait e1a %lld | H2b %lld | wait e1b %lld | X2a X2b H1a' %lld | wait e2a %lld | H1b' %lld | wait e2b %lld | OUT %lld | step %lld\n",
+                       t, tr[1] - tr[0], tr[2] - tr[1], tr[3] - tr[2], tr[4] - tr[3], tr[5] - tr[4], tr[6] - tr[5], tr[7] - tr[6],
+                       tr[8] - tr[7], tr[9] - tr[8], tr[10] - tr[9], tr[10] - tr[0]);
+#endif
+            t3 = i1;
         }
-        bar_wait(mbar, phase); phase ^= 1;
-        tc_fence_after();
-        gru_epilogue(tl, cst1, C_AH1_HI, C_AH1_LO, half);
-        tc_sync();
-        if (tid == 0)
-            issue_layer(tmem, C_AH1_HI, C_AH1_LO, 64, sm0 + O_WIH2_HI, sm0 + O_WIH2_LO, C_AH2_HI, C_AH2_LO, sm0 + O_WHH2_HI,
-                        sm0 + O_WHH2_LO, mbar);
-        bar_wait(mbar, phase); phase ^= 1;
-        tc_fence_after();
-        gru_epilogue(tl, cst2, C_AH2_HI, C_AH2_LO, half);
-        tc_sync();
-        if (tid == 0) issue_out(tmem, sm0 + O_WOUT_HI, sm0 + O_WOUT_LO, mbar);
-        bar_wait(mbar, phase); phase ^= 1;
-        tc_fence_after();
-        if (lead) {  // linear output layer -> feedback as the next input (autoregression.py:94-98)
-            uint32_t o[8];
-            ld8(tl + C_OUT, o);
-            ld_wait();
-#pragma unroll
-            for (int i = 0; i < 6; ++i) y[i] = (i < N.n_out) ? fmaf(__uint_as_float(o[i]), csto[2 * i], csto[2 * i + 1]) : 0.0f;
-            if (t + 1 < T) write_x(u_nxt, y);
+    } else if (is_epi && live) {
+#pragma unroll 1
+        for (int t = 0; t < T; ++t) {
+#pragma unroll 1
+#ifdef CPS_TC_TRACE
+            long long tr[12];
+#endif
+            for (int job = 0; job < 4; ++job) {
+                const int j = 4 * t + job, l = job >> 1, ch = job & 1;
+                TC_TR(3 * job);
+                bar_wait(doneb(j % 3), (uint32_t)((j / 3) & 1));
+                tc_fence_after();
+                TC_TR(3 * job + 1);
+                if (live)
+                    gru_epilogue8(tl, region(j), (uint32_t)(TC_EU * sub), l ? cst2 : cst1, l ? ec2 : ec1, l ? ecn2 : ecn1,
+                                  l ? C_AH2_HI : C_AH1_HI, l ? C_AH2_LO : C_AH1_LO, chunk_u0(ch));
+#ifdef CPS_TC_TRACE
+                const long long c_mid = clock64();
+#endif
+                warp_signal(epib(job), lane);
+                TC_TR(3 * job + 2);
+#ifdef CPS_TC_TRACE
+                if (blockIdx.x == 0 && tid == 0 && t == 10) {
+                    tr[3 * job] = tr[3 * job + 2] - c_mid;   // the signal part alone
+                    printf("  job %d: loads %lld math %lld stores %lld\n", job, g_epi_t[1] - g_epi_t[0], g_epi_t[2] - g_epi_t[1], g_epi_t[3] - g_epi_t[2]);
+                }
+#endif
+            }
+#ifdef CPS_TC_TRACE
+            if (blockIdx.x == 0 && tid == 0 && t == 10)
+                printf("EPILOGUE t=%d: work (of which st-wait + signal): 1a %lld (%lld) | 1b %lld (%lld) | 2a %lld (%lld) | 2b %lld (%lld)\n", t,
+                       tr[2] - tr[1], tr[0], tr[5] - tr[4], tr[3], tr[8] - tr[7], tr[6], tr[11] - tr[10], tr[9]);
+#endif
         }
-        tc_sync();
+    } else if (is_row && live) {
+#pragma unroll 1
+        for (int t = 0; t < T; ++t) {
+            // behind the tensor cores: state s_t -> trajectory row, stage cost; the control of step t + 1
+#ifdef CPS_TC_TRACE
+            long long tr[4];
+#endif
+            TC_TR(0);
+            if (live) {
+                u_cur = u_nxt; du_cur = du_nxt;
+                if (t > 0) compose_state(N, y, st);
+                if (traj) {
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) traj[(long long)t * a.ts_t + c * a.ts_c] = st[c];
+                }
+                if (MPPI) {
+                    const float stc = stage_cost_rt(a.cost_id, a.cost, cosf(st[IDX_ANGLE]), st[IDX_ANGLED], st[IDX_POS], u_cur, up);
+                    if (rowsum) row_sum_push(rsp, sl, TC_ROWS, rs_tail, t, stc);
+                    else Jacc += stc;
+                    corr = fmaf(a.mp.cc_half_nu * du_cur, du_cur,
+                                fmaf(a.mp.cc_R * u_cur, du_cur, fmaf(a.mp.cc_half_R * u_cur, u_cur, corr)));
+                    if (a.u_run_out && active) a.u_run_out[(long long)k * T + t] = u_cur;
+                    up = u_cur;
+                }
+                if (t + 1 < T) next_control(t + 1);
+            }
+            // linear output layer -> feedback as the next input (autoregression.py:94-98)
+            TC_TR(1);
+            bar_wait(outb, (uint32_t)(t & 1));
+            tc_fence_after();
+            TC_TR(2);
+            if (live) {
+                uint32_t o[8];
+                ld8(tl + region(4 * t + 6) + C_NI, o);
+                ld_wait();
+#pragma unroll
+                for (int i = 0; i < 6; ++i) y[i] = (i < N.n_out) ? fmaf(__uint_as_float(o[i]), csto[2 * i], csto[2 * i + 1]) : 0.0f;
+                if (t + 1 < T) write_x(u_nxt, y);
+            }
+            if (t + 1 < T) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) bar_arrive(xrdy);
+            }
+            TC_TR(3);
+#ifdef CPS_TC_TRACE
+            if (blockIdx.x == 0 && tid == TC_EPI && t == 10)
+                printf("ROW t=%d: bookkeeping %lld | wait out %lld | feedback %lld\n", t, tr[1] - tr[0], tr[2] - tr[1], tr[3] - tr[2]);
+#endif
+        }
     }
+    tc_sync();
 
     // ---- last state, costs, hidden state out ---------------------------------------------------------------------------
     float J = 0.0f;
-    if (lead) {
+    if (is_row && live) {
         compose_state(N, y, st);
         if (traj) {
 #pragma unroll
             for (int c = 0; c < 6; ++c) traj[(long long)T * a.ts_t + c * a.ts_c] = st[c];
         }
         if (MPPI) {
-            if (a.cost_id == CPS_COST_DEFAULT || a.cost_id == CPS_COST_QUADRATIC_BOUNDARY)
-                Jacc += terminal_cost<COST_DEFAULT>(a.cost, st[IDX_ANGLE], st[IDX_POS]);
+            if (a.cost_id == CPS_COST_DEFAULT || a.cost_id == CPS_COST_QUADRATIC_BOUNDARY) {
+                const float term = terminal_cost<COST_DEFAULT>(a.cost, st[IDX_ANGLE], st[IDX_POS]);
+                if (rowsum) {
+                    row_sum_push(rsp, sl, TC_ROWS, rs_tail, T, term);
+                    Jacc = row_sum_finish(rsp, sl, TC_ROWS, rs_tail);
+                } else {
+                    Jacc += term;
+                }
+            }
             J = __fdiv_rn(Jacc, a.mp.T1) + corr;   // mean over T+1 entries (true division, as torch.mean) + correction
             if (active) {
                 if (a.J_out) a.J_out[k] = J;
@@ -415,42 +670,43 @@ __global__ void __launch_bounds__(TC_NT, 1) net_tc_kernel(const __grid_constant_
             }
         }
     }
-    auto store_hidden = [&](float *dst) {  // this thread's 2 x 32 units of the current hidden state
-        float v[16];
+    auto store_hidden = [&](float *dst) {  // this epilogue thread's 2 x 2 x 8 units of the current hidden state
+        float v[TC_EU];
 #pragma unroll 1
         for (int l = 0; l < 2; ++l) {
 #pragma unroll 1
             for (int ch = 0; ch < 2; ++ch) {
-                const int u0 = 32 * half + 16 * ch;
-                read_operand16(tl, (l ? C_AH2_HI : C_AH1_HI) + (u0 >> 1), (l ? C_AH2_LO : C_AH1_LO) + (u0 >> 1), v);
+                const int u0 = chunk_u0(ch);
+                read_operand8(tl, (l ? C_AH2_HI : C_AH1_HI) + (u0 >> 1), (l ? C_AH2_LO : C_AH1_LO) + (u0 >> 1), v);
                 if (dst) {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) dst[l * TC_H + u0 + i] = v[i];
+                    for (int i = 0; i < TC_EU; ++i) dst[l * TC_H + u0 + i] = v[i];
                 }
             }
         }
     };
-    if (a.h_final) store_hidden((k < a.B) ? a.h_final + (long long)k * (2 * TC_H) : nullptr);
+    if (a.h_final && is_epi && live) store_hidden((k < a.B) ? a.h_final + (long long)k * (2 * TC_H) : nullptr);
 
     bool last = false;
     if (MPPI) {
-        // ---- block partial {min J, sum w, sum w*eps[.]} over the 128 rollouts (lead warps 0..3) ----------------------
+        // ---- block partial {min J, sum w, sum w*eps[.]} over the 128 rollouts (row warps) ------------------------------
         const MppiParams &mp = a.mp;
         const int rec = 2 + mp.n_red;
-        if (lead) {
+        const int rw = warp - TC_EW;
+        if (is_row) {
             const float m = warp_min(active ? J : INFINITY);
-            if (lane == 0) s_bmin[warp] = m;
+            if (lane == 0) s_bmin[rw] = m;
         }
         __syncthreads();
         const float m = fminf(fminf(s_bmin[0], s_bmin[1]), fminf(s_bmin[2], s_bmin[3]));
-        if (lead) {
+        if (is_row) {
             const float wgt = active ? expf(-(J - m) * mp.inv_lambda) : 0.0f;
             const float S = warp_sum(wgt);
-            if (lane == 0) s_red[warp * rec + 1] = S;
+            if (lane == 0) s_red[rw * rec + 1] = S;
             for (int i = 0; i < mp.n_red; ++i) {
                 const float e = active ? nz[(long long)i * a.ns_i] : 0.0f;
                 const float v = warp_sum(wgt * e);
-                if (lane == 0) s_red[warp * rec + 2 + i] = v;
+                if (lane == 0) s_red[rw * rec + 2 + i] = v;
             }
         }
         __syncthreads();
@@ -469,47 +725,66 @@ __global__ void __launch_bounds__(TC_NT, 1) net_tc_kernel(const __grid_constant_
             if (tid == 0) *a.ticket = 0u;
         }
         if (last && !a.shard_out && a.h_ref) {
-            // ---- advance the stored hidden state by one step on (u, s) (optimizer_mppi.py:191,194-196) ----------------
+            // ---- advance the stored hidden state by one step on (u, s) (optimizer_mppi.py:191,194-196): one more,
+            //      unpipelined, network step with every rollout carrying the stored state --------------------------------
             __syncthreads();
             const float u_sel = __ldcg(a.u_out);
-            float v[16];
+            const bool upd = row < 32;   // the stored state is one row: the first lane quarter carries it
+            if (is_epi && upd) {
+                float v[TC_EU];
 #pragma unroll 1
-            for (int l = 0; l < 2; ++l) {
+                for (int l = 0; l < 2; ++l) {
 #pragma unroll 1
-                for (int ch = 0; ch < 2; ++ch) {
-                    const int u0 = 32 * half + 16 * ch;
+                    for (int ch = 0; ch < 2; ++ch) {
+                        const int u0 = chunk_u0(ch);
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] = a.h_ref[l * TC_H + u0 + i];
-                    write_operand16(tl, (l ? C_AH2_HI : C_AH1_HI) + (u0 >> 1), (l ? C_AH2_LO : C_AH1_LO) + (u0 >> 1), v);
+                        for (int i = 0; i < TC_EU; ++i) v[i] = a.h_ref[l * TC_H + u0 + i];
+                        write_operand8(tl, (l ? C_AH2_HI : C_AH1_HI) + (u0 >> 1), (l ? C_AH2_LO : C_AH1_LO) + (u0 >> 1), v);
+                    }
                 }
             }
-            if (lead) {
+            if (is_row && upd) {
 #pragma unroll
                 for (int i = 0; i < 6; ++i)
                     feat[i] = (i < N.n_state_in) ? fmaf(N.norm_a[1 + i], a.s0[N.in_idx[i]], N.norm_b[1 + i]) : 0.0f;
                 write_x(u_sel, feat);
             }
             tc_sync();
-            if (tid == 0)
-                issue_layer(tmem, C_AX_HI, C_AX_LO, 16, sm0 + O_WIH1_HI, sm0 + O_WIH1_LO, C_AH1_HI, C_AH1_LO, sm0 + O_WHH1_HI,
-                            sm0 + O_WHH1_LO, mbar);
-            bar_wait(mbar, phase); phase ^= 1;
+            const uint32_t tmu = __shfl_sync(0xffffffffu, tmem, 0);   // warp-uniform for the issuer (see tc_mma)
+            if (is_mma) {
+                issue_H(tmu + 0, tmu + C_AH1_HI, tmu + C_AH1_LO, sm0 + O_WHH1_HI, sm0 + O_WHH1_LO, 0);
+                issue_X1(tmu + 0, AX_HI, AX_LO, sm0 + O_WIH1_HI, sm0 + O_WIH1_LO, 0);
+                issue_H(tmu + 128, tmu + C_AH1_HI, tmu + C_AH1_LO, sm0 + O_WHH1_HI, sm0 + O_WHH1_LO, 1);
+                issue_X1(tmu + 128, AX_HI, AX_LO, sm0 + O_WIH1_HI, sm0 + O_WIH1_LO, 1);
+                tc_commit(tailb);
+            }
+            bar_wait(tailb, 0);
             tc_fence_after();
-            gru_epilogue(tl, cst1, C_AH1_HI, C_AH1_LO, half);
+            if (is_epi && upd) {
+                gru_epilogue8(tl, 0, (uint32_t)(TC_EU * sub), cst1, ec1, ecn1, C_AH1_HI, C_AH1_LO, chunk_u0(0));
+                gru_epilogue8(tl, 128, (uint32_t)(TC_EU * sub), cst1, ec1, ecn1, C_AH1_HI, C_AH1_LO, chunk_u0(1));
+            }
             tc_sync();
-            if (tid == 0)
-                issue_layer(tmem, C_AH1_HI, C_AH1_LO, 64, sm0 + O_WIH2_HI, sm0 + O_WIH2_LO, C_AH2_HI, C_AH2_LO, sm0 + O_WHH2_HI,
-                            sm0 + O_WHH2_LO, mbar);
-            bar_wait(mbar, phase); phase ^= 1;
+            if (is_mma) {
+                issue_H(tmu + 256, tmu + C_AH2_HI, tmu + C_AH2_LO, sm0 + O_WHH2_HI, sm0 + O_WHH2_LO, 0);
+                issue_X2(tmu + 256, tmu + C_AH1_HI, tmu + C_AH1_LO, sm0 + O_WIH2_HI, sm0 + O_WIH2_LO, 0);
+                issue_H(tmu + 0, tmu + C_AH2_HI, tmu + C_AH2_LO, sm0 + O_WHH2_HI, sm0 + O_WHH2_LO, 1);
+                issue_X2(tmu + 0, tmu + C_AH1_HI, tmu + C_AH1_LO, sm0 + O_WIH2_HI, sm0 + O_WIH2_LO, 1);
+                tc_commit(tailb);
+            }
+            bar_wait(tailb, 1);
             tc_fence_after();
-            gru_epilogue(tl, cst2, C_AH2_HI, C_AH2_LO, half);
-            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-            store_hidden(row == 0 ? a.h_ref : nullptr);
+            if (is_epi && upd) {
+                gru_epilogue8(tl, 256, (uint32_t)(TC_EU * sub), cst2, ec2, ecn2, C_AH2_HI, C_AH2_LO, chunk_u0(0));
+                gru_epilogue8(tl, 0, (uint32_t)(TC_EU * sub), cst2, ec2, ecn2, C_AH2_HI, C_AH2_LO, chunk_u0(1));
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                store_hidden(row == 0 ? a.h_ref : nullptr);
+            }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
+    if (is_mma) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
 }
 
 // =====================================================================================================
@@ -522,8 +797,8 @@ bool cps_net_tc_eligible(const NetDev &N) {
 
 size_t cps_net_tc_smem(const MppiParams *mp, bool mppi) {
     size_t f = 0;
-    if (mppi) f = (size_t)mp->T + 2 * (size_t)mp->p + 5 * ((size_t)mp->n_red + 2) + 8;
-    return TC_IMAGE_BYTES + f * sizeof(float);
+    if (mppi) f = (size_t)mp->T + 2 * (size_t)mp->p + 5 * ((size_t)mp->n_red + 2) + 8 + 32 * TC_ROWS;   // + row-sum slots
+    return O_FLOATS + f * sizeof(float);
 }
 
 // Builds the kernel image from the torch-order weights: fp16 hi/lo parts of the row-scaled matrices in UMMA core-matrix
@@ -549,22 +824,33 @@ void cps_net_tc_build_image(const NetDev &N, const float *w, std::vector<unsigne
         memcpy(&img[o_hi + kmajor_off(r, kk, K)], &hi, 2);
         memcpy(&img[o_lo + kmajor_off(r, kk, K)], &lo, 2);
     };
-    auto layer = [&](const float *wih, int kin, int Kpad, const float *whh, const float *bih, const float *bhh, uint32_t oih_hi,
+    // one power-of-two scale per layer (the epilogue undoes it with one uniform constant): S max|w| in [64, 128).  Rows
+    // with small weights lose nothing that matters: their lo parts become fp16 subnormals with an absolute resolution of
+    // 2^-24 in scaled units, i.e. 2^-31 of the layer's largest weight.
+    auto layer = [&](int li, const float *wih, int kin, int Kpad, const float *whh, const float *bih, const float *bhh, uint32_t oih_hi,
                      uint32_t oih_lo, uint32_t ohh_hi, uint32_t ohh_lo, uint32_t ocst) {
         float *cst = reinterpret_cast<float *>(&img[ocst]);
+        const float s = row_scale(wih, 3 * H * kin, whh, 3 * H * H);
+        const float c = 1.0f / (A_SCALE * s);
+        const double L2E = 1.4426950408889634;
+        float *cu = reinterpret_cast<float *>(&img[O_CSTO]) + 32 + 2 * li;
+        cu[0] = c;
+        cu[1] = (float)(-(double)c * L2E);
         for (int n = 0; n < 3 * H; ++n) {
-            const float s = row_scale(wih + (size_t)n * kin, kin, whh + (size_t)n * H, H);
-            for (int kk = 0; kk < kin; ++kk) put(oih_hi, oih_lo, n, kk, Kpad, wih[(size_t)n * kin + kk] * s);
-            for (int kk = 0; kk < H; ++kk) put(ohh_hi, ohh_lo, n, kk, H, whh[(size_t)n * H + kk] * s);
-            const float c = 1.0f / (A_SCALE * s);
             const int u = n % H, g = n / H;   // gate 0 = r, 1 = z, 2 = n
-            if (g == 0) { cst[u * 8 + 0] = c; cst[u * 8 + 1] = bih[n] + bhh[n]; }
-            else if (g == 1) { cst[u * 8 + 2] = c; cst[u * 8 + 3] = bih[n] + bhh[n]; }
-            else { cst[u * 8 + 4] = c; cst[u * 8 + 5] = bih[n]; cst[u * 8 + 6] = c; cst[u * 8 + 7] = bhh[n]; }
+            const int nr = 96 * (u / 32) + 32 * g + (u % 32);               // input matrices: [r | z | n] per half-layer job
+            const int nh = 96 * (u / 32) + 32 * ((g + 1) % 3) + (u % 32);   // recurrent matrices: [n | r | z]
+            for (int kk = 0; kk < kin; ++kk) put(oih_hi, oih_lo, nr, kk, Kpad, wih[(size_t)n * kin + kk] * s);
+            for (int kk = 0; kk < H; ++kk) put(ohh_hi, ohh_lo, nh, kk, H, whh[(size_t)n * H + kk] * s);
+            // epilogue constants of the pair of units (u & ~1, u | 1): {brn x 2, bzn x 2, bni x 2, bnh x 2}
+            float *k = cst + (u >> 1) * 8 + (u & 1);
+            if (g == 0) k[0] = (float)(-L2E * ((double)bih[n] + (double)bhh[n]));
+            else if (g == 1) k[2] = (float)(-L2E * ((double)bih[n] + (double)bhh[n]));
+            else { k[4] = bih[n]; k[6] = bhh[n]; }
         }
     };
-    layer(w_ih1, n_in, 16, w_hh1, b_ih1, b_hh1, O_WIH1_HI, O_WIH1_LO, O_WHH1_HI, O_WHH1_LO, O_CST1);
-    layer(w_ih2, H, H, w_hh2, b_ih2, b_hh2, O_WIH2_HI, O_WIH2_LO, O_WHH2_HI, O_WHH2_LO, O_CST2);
+    layer(0, w_ih1, n_in, 16, w_hh1, b_ih1, b_hh1, O_WIH1_HI, O_WIH1_LO, O_WHH1_HI, O_WHH1_LO, O_CST1);
+    layer(1, w_ih2, H, H, w_hh2, b_ih2, b_hh2, O_WIH2_HI, O_WIH2_LO, O_WHH2_HI, O_WHH2_LO, O_CST2);
     float *co = reinterpret_cast<float *>(&img[O_CSTO]);
     for (int o = 0; o < 16; ++o) { co[2 * o] = 0.0f; co[2 * o + 1] = 0.0f; }
     for (int o = 0; o < N.n_out; ++o) {
@@ -581,7 +867,11 @@ int cps_net_tc_launch(cps_handle *h, NetArgs &a, bool mppi, int n_rows) {
     const size_t smem = cps_net_tc_smem(&h->mp, mppi);
     void (*fn)(const NetArgs) = mppi ? net_tc_kernel<true> : net_tc_kernel<false>;
     CUDA_TRY(h, cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int grid = (n_rows + TC_ROWS - 1) / TC_ROWS;
+    // live rollouts per CTA: the fewest that still give every CTA its own SM (see the kernel's comment on tc_rows)
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device);
+    a.tc_rows = (n_rows <= 32 * sms) ? 32 : ((n_rows <= 64 * sms) ? 64 : TC_ROWS);
+    const int grid = (n_rows + a.tc_rows - 1) / a.tc_rows;
     fn<<<grid, TC_NT, smem, h->stream>>>(a);
     h->launches += 1;
     CUDA_TRY(h, cudaGetLastError());

@@ -210,8 +210,8 @@ def test_net_mppi_vs_reference_golden(run):
             assert shifted_cost_ok(Jg, z["J"][i])
         else:
             assert vec_err(Jg, z["J"][i]) < 1e-5
-        assert du < 1e-4
-        np.testing.assert_allclose(eng.get_u_nom(), z["u_nom"][i], rtol=0, atol=1e-4)
+        assert du < 2e-5      # measured <= 9.1e-6 (gru32_grad); north_star: 1e-4
+        np.testing.assert_allclose(eng.get_u_nom(), z["u_nom"][i], rtol=0, atol=2e-5)
         if sp["net_type"] == "GRU":  # the solve advanced the stored hidden state on (u, s) (optimizer_mppi.py:191)
             assert np.abs(eng.net_get_state() - z["h_after"][i]).max() < 5e-6
             h = z["h_after"][i].copy()

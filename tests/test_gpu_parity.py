@@ -33,6 +33,9 @@ def cuda(x):
 
 ROLL_CASES = ["known", "random", "edge", "wrap", "upright", "tiled", "varL", "T100", "n1"]
 CHAOTIC = ("random", "edge", "wrap", "varL", "T100")
+# measured (max over integrators and kernel variants): random 2.7e-5, edge 2.5e-5, T100 2.8e-5, upright 1.8e-5,
+# varL 1.0e-5, wrap 5.5e-6, tiled 3.1e-6, n1 9.5e-7, known 4e-8
+ROLL_TOL = {"random": 6e-5, "edge": 5e-5, "T100": 6e-5, "upright": 3e-5, "varL": 2e-5, "wrap": 1.2e-5}
 
 
 # kernel variants: default = rotation substeps; the others evaluate sin/cos every substep like the reference text
@@ -62,7 +65,10 @@ def test_rollout_vs_reference_golden(integ, fname, case, variant):
     # 1e-5 on the MPPI operating point (hanging start, MPPI-sized perturbations); near the unstable upright
     # equilibrium the reference's own fp32 output is already ~6e-6 from an fp64 integration (test_fp32_noise_floor),
     # so two fp32 realisations can differ by ~2e-5 there; random high-energy states amplify further
-    tol = 3e-4 if case in CHAOTIC else (3e-5 if case == "upright" else 1e-5)
+    # per-case bounds = ~2x the errors measured on B200 (profiles/parity_r02.json): 1e-5 (north_star) wherever the dynamics
+    # do not amplify rounding noise; the high-energy / near-upright cases carry the amplified fp32 noise floor that the
+    # oracle-vs-reference comparison shows as well (tests/test_oracle_golden.py)
+    tol = ROLL_TOL.get(case, 1e-5)
     record("rollout_vs_reference_golden", f"{integ}/{case}/{variant}", first_step=max(e1.values()), horizon=max(e.values()),
            tol=tol, T=T)
     assert max(e.values()) < tol, e
@@ -131,7 +137,8 @@ def test_cost_kernels_vs_reference_golden(name):
             assert vec_err(J, ref_J) < 2e-6
 
 
-J_TOL = 3e-5
+J_TOL = 2e-5   # measured <= 1.03e-5 (ode_grad_down); everything else <= 2e-6
+U_TOL = 1e-5   # selected control and nominal sequence: measured <= 1.9e-6 / 3.7e-6 (north_star: 1e-4)
 
 MPPI_RUNS = ["ode_gradmin", "v0_gradmin", "ode_gradmin_K2000", "ode_grad", "ode_grad_down", "ode_qb", "ode_default",
              "ode_gradmin_T100", "ode_gradmin_T51",
@@ -187,8 +194,8 @@ def test_mppi_step_vs_reference_golden(run, variant):
             # J inherits the fp32 rounding noise of the trajectories (floor ~1e-5 of max|J|, see
             # test_fp32_noise_floor); the functional criterion is the control, 1e-4
             assert vec_err(Jg, z["J"][i]) < J_TOL
-        assert du < 1e-4
-        np.testing.assert_allclose(u_nom, z["u_nom"][i], rtol=0, atol=1e-4)
+        assert du < U_TOL
+        np.testing.assert_allclose(u_nom, z["u_nom"][i], rtol=0, atol=U_TOL)
         assert eng.nonfinite_costs() == 0
         u_nom_prev = z["u_nom"][i].copy()
 
@@ -230,8 +237,8 @@ def test_mppi_step_vs_oracle(integ, cost, K, T, p):
         rec["J"] = vec_err(Jg, ref["J"])
         assert rec["J"] < 1e-5
     record("mppi_step_vs_oracle", f"{integ}/{cost}/K{K}/T{T}/p{p}", **rec)
-    assert abs(float(u.cpu()[0]) - float(ref["u"])) < 1e-4
-    np.testing.assert_allclose(eng.get_u_nom(), ref["u_nom"], rtol=0, atol=1e-4)
+    assert abs(float(u.cpu()[0]) - float(ref["u"])) < U_TOL          # measured <= 2.1e-6
+    np.testing.assert_allclose(eng.get_u_nom(), ref["u_nom"], rtol=0, atol=U_TOL)   # measured <= 4.8e-6
     # DIRECT noise mode fed with the oracle's interpolated perturbations must agree with the INDUCING mode
     eng_d = _engine(K, T, integrator=integ, cost=cost, interp_period=p, noise_mode="direct")
     eng_d.set_variable_parameters(target_position=0.03)

@@ -251,8 +251,13 @@ def test_optimizer_neural_closed_loop_matches_reference(run, tmp_path):
     for i in range(m["steps"]):
         u = opt.step(z["s"][i].copy())
         assert isinstance(u, np.ndarray) and u.dtype == np.float32
-        assert abs(float(u) - float(z["u"][i])) < 2e-4, (i, float(u), float(z["u"][i]))
-        np.testing.assert_allclose(opt.u_nom.numpy().reshape(-1), z["u_nom"][i], rtol=0, atol=2e-4)
+        from tests.parity import record
+        du, dn = abs(float(u) - float(z["u"][i])), float(np.abs(opt.u_nom.numpy().reshape(-1) - z["u_nom"][i]).max())
+        record("optimizer_neural_closed_loop", f"{run}/{i}", u=du, u_nom=dn)
+        # closed loop: the solver carries ITS u_nom / hidden state forward, so differences accumulate over the steps
+        # (measured <= 3e-5 after 3-4 solves; north_star: 1e-4)
+        assert du < 1e-4, (i, float(u), float(z["u"][i]))
+        np.testing.assert_allclose(opt.u_nom.numpy().reshape(-1), z["u_nom"][i], rtol=0, atol=1e-4)
         if "h_after" in z.files:
             assert np.abs(opt.engine.net_get_state() - z["h_after"][i]).max() < 1e-5
         if opt.optimizer_logging:
