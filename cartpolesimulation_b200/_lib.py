@@ -113,6 +113,7 @@ SYMBOLS = {
     "cps_cem_set_distribution": (C.c_int, [_VP, _FP, _FP]),
     "cps_measure_peaks": (C.c_int, [_VP, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "cps_launch_count": (C.c_longlong, [_VP]),
+    "cps_net_last_kernel": (C.c_int, [_VP]),
     "cps_nonfinite_costs": (C.c_int, [_VP, C.POINTER(C.c_int)]),
 }
 

@@ -529,6 +529,10 @@ class Engine:
     def launch_count(self) -> int:
         return int(self.lib.cps_launch_count(self._h))
 
+    def net_last_kernel(self) -> str | None:
+        """'fp32' | 'tensor': the network kernel the last neural rollout / solve launched (None: none yet)."""
+        return {0: None, 1: "fp32", 2: "tensor"}[int(self.lib.cps_net_last_kernel(self._h))]
+
     def nonfinite_costs(self) -> int:
         n = C.c_int(0)
         self._chk(self.lib.cps_nonfinite_costs(self._h, C.byref(n)))

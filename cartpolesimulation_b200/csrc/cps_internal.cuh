@@ -95,6 +95,7 @@ struct cps_handle {
     cudaEvent_t ev_start, ev_in[16], ev_k[16];
     int pipe_ready;
     long long launches;
+    int net_last_kernel;       // 0 none, 1 net_kernel (FP32), 2 net_tc_kernel
     std::string err;
     NetState *net;      // neural predictor (cps_net_load), owned
     FleetState *fleet;  // closed-loop experiments (cps_fleet_create), owned

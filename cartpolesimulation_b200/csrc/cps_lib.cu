@@ -961,6 +961,7 @@ extern "C" int cps_measure_peaks(cps_handle *h, double *fp32_tflops, double *muf
 
 // ---- diagnostics ---------------------------------------------------------------------------------------
 extern "C" long long cps_launch_count(const cps_handle *h) { return h ? h->launches : -1; }
+extern "C" int cps_net_last_kernel(const cps_handle *h) { return h ? h->net_last_kernel : -1; }
 
 extern "C" int cps_nonfinite_costs(cps_handle *h, int *count_out) {
     if (!h || !count_out) return CPS_ERR_INVALID;

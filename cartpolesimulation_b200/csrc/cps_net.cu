@@ -468,6 +468,7 @@ static net_fn pick_net(int R, int ht, bool mppi) {
 bool cps_net_tc_eligible(const NetDev &N);
 void cps_net_tc_build_image(const NetDev &N, const float *w, std::vector<unsigned char> &img);
 int cps_net_tc_launch(cps_handle *h, NetArgs &a, bool mppi, int n_rows);
+size_t cps_net_tc_smem(const MppiParams *mp, bool mppi);
 
 void cps_net_free(cps_handle *h) {
     if (!h || !h->net) return;
@@ -595,17 +596,14 @@ static int net_launch(cps_handle *h, NetArgs &a, bool mppi, int n_rows) {
     a.net = S->dev;
     a.weights = S->d_weights;
     a.tc = S->d_tc;
-    // tensor cores (tcgen05, 128 rollouts per CTA): a solve takes ~0.42 ms of per-step latency whatever the batch (T = 50);
-    // the FP32 kernel's 16-row tiles take 0.38 ms while they fit one wave (148 x 16 rollouts) and 0.64 ms beyond
+    // 2 x 64 GRU: the tensor-core kernel (tcgen05; 64 or 128 rollouts per CTA) at every batch size -- a T = 50 solve takes
+    // 0.21 ms up to 64 x 148 rollouts (per-step latency bound) and 1.0 ms at 65536, against 0.39 ms / 8.0 ms of the FP32
+    // kernel (profiles/r02_net_timing.txt).  CPS_FLAG_NET_FP32 forces the CUDA-core kernel.
     const unsigned fl = h->cfg.flags;
-    const bool want_tc = (fl & CPS_FLAG_NET_TENSOR_CORES) || (!(fl & CPS_FLAG_NET_FP32) && n_rows > 148 * 16);
     if ((fl & CPS_FLAG_NET_TENSOR_CORES) && !S->d_tc)
         return fail(h, CPS_ERR_UNSUPPORTED, "CPS_FLAG_NET_TENSOR_CORES: the tensor-core kernel supports plain (not differential, D_*) 2 x 64 GRU networks only");
-    // the MAX_COST plugins need the backend-ordered row sum (RowSumPlan), which lives in the FP32 kernel
-    const bool shifted = mppi && (h->cfg.cost_id == CPS_COST_DEFAULT || h->cfg.cost_id == CPS_COST_QUADRATIC_BOUNDARY);
-    if ((fl & CPS_FLAG_NET_TENSOR_CORES) && shifted)
-        return fail(h, CPS_ERR_UNSUPPORTED, "CPS_FLAG_NET_TENSOR_CORES: default / quadratic_boundary run on the FP32 network kernel");
-    if (want_tc && S->d_tc && !shifted) return cps_net_tc_launch(h, a, mppi, n_rows);
+    if (S->d_tc && !(fl & CPS_FLAG_NET_FP32) && ((fl & CPS_FLAG_NET_TENSOR_CORES) || cps_net_tc_smem(&h->mp, mppi) <= 227 * 1024))
+        return cps_net_tc_launch(h, a, mppi, n_rows);
     // small batches: 16 rollouts per CTA spread the work over more SMs; large ones: 32 (two warps per scheduler)
     int R = (n_rows > 148 * 16) ? 32 : 16;
     if (net_smem_bytes(S->dev, R, mppi, &h->mp) > 227 * 1024) R = 16;
@@ -615,6 +613,7 @@ static int net_launch(cps_handle *h, NetArgs &a, bool mppi, int n_rows) {
     const int grid = (n_rows + R - 1) / R;
     fn<<<grid, R * 8 + 32, smem, h->stream>>>(a);
     h->launches += 1;
+    h->net_last_kernel = 1;
     CUDA_TRY(h, cudaGetLastError());
     return CPS_OK;
 }

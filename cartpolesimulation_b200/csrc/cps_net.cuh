@@ -56,7 +56,7 @@ struct NetArgs {
     int *nonfinite;
     float *shard_out;
     float *h_ref;             // stored hidden state to advance after the solve (null: skip)
-    int tc_rows;              // net_tc_kernel: live rollouts per CTA (32 | 64 | 128 of the 128 tensor-memory lanes)
+    int tc_rows;              // net_tc_kernel: live rollouts per CTA (64: the first 16 lanes of each tensor-memory lane quarter | 128)
 };
 
 // ---- small device helpers ---------------------------------------------------------------------------------------

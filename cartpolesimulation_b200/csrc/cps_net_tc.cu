@@ -137,6 +137,20 @@ __device__ __forceinline__ void st4(uint32_t addr, const uint32_t (&v)[4]) {
                  ::"r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
 }
 __device__ __forceinline__ void ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// 16-lane shapes (layouts verified with tools/tc/shape_probe.cu): the address names lane L = quarter base (+ 16) and column c.
+//   .16x256b.x1: thread t gets {(L + t/4, c + 2 (t%4)), (L + t/4, c + 2 (t%4) + 1), (L + 8 + t/4, same two columns)}
+//   .16x128b.x1: thread t gets {(L + t/4, c + t%4), (L + 8 + t/4, c + t%4)}
+// i.e. four threads share a rollout: the gate epilogue of 16 rollouts x 8 units is spread over the whole warp.
+__device__ __forceinline__ void ld16x256(uint32_t addr, uint32_t (&v)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.16x256b.x1.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ld16x128(uint32_t addr, uint32_t (&v)[2]) {
+    asm volatile("tcgen05.ld.sync.aligned.16x128b.x1.b32 {%0, %1}, [%2];" : "=r"(v[0]), "=r"(v[1]) : "r"(addr));
+}
+__device__ __forceinline__ void st16x128(uint32_t addr, const uint32_t (&v)[2]) {
+    asm volatile("tcgen05.st.sync.aligned.16x128b.x1.b32 [%0], {%1, %2};" ::"r"(addr), "r"(v[0]), "r"(v[1]) : "memory");
+}
 
 // e^{-x} for x clamped to [-20, 20]: one FMUL-free MUFU.EX2 (ex2.approx.ftz of x * -log2 e)
 __device__ __forceinline__ float ex2_neg(float x) {
@@ -264,70 +278,76 @@ __device__ __forceinline__ uint32_t pack_f16x2(float lo_v, float hi_v) {   // tw
     return d;
 }
 
-// GRU non-linearities for 8 hidden units of one rollout (torch GRUCell, gate order r, z, n): reads the job's region
-// {NH, R, Z, NI} at column offset `cu` (= unit index inside the half layer) and h(t-1) (the A operand itself), writes h(t)
-// as the new A operand.  u0 = index of the first unit inside the layer (constants, operand columns).
+// GRU non-linearities (torch GRUCell, gate order r, z, n) of 8 hidden units x 16 HALVES rollouts, by one warp: thread t
+// takes the pair of units 2 (t % 4), + 1 of the rollouts (tensor-memory lanes) t / 4 and 8 + t / 4 of each 16-lane half
+// (the .16x256b / .16x128b access shapes above).  Reads the job's region {NH, R, Z, NI} at column offset `cu` (= first
+// unit inside the half layer) and h(t-1) (the A operand itself), writes h(t) as the new A operand.  u0 = index of the
+// first of the 8 units inside the layer (constants, operand columns); tq = tensor-memory address of the warp's lane quarter.
 // Two units per step in packed FP32 (FFMA2 / FMUL2 / FADD2: the FMA-pipe work of the epilogue halves, which leaves the 4
 // MUFU operations per unit -- 3 exponentials and, shared between two units, 2 reciprocals: 1/a = (b c d) / (a b c d) --
-// as its bound).  c = 1 / (128 S) undoes the operand scales (uniform per layer), cn = -c log2 e; per pair of units the
-// constants are {-log2e (b_ir + b_hr), -log2e (b_iz + b_hz), b_in, b_hn} x 2.  Exponents are capped at 2^30, which
-// bounds the shared-reciprocal products; everything stays in the operand scale (h is kept as 128 h).
-#ifdef CPS_TC_TRACE
-__device__ long long g_epi_t[4];
-#define EPI_TR(i) if (threadIdx.x == 0 && blockIdx.x == 0) g_epi_t[i] = clock64()
-#else
-#define EPI_TR(i)
-#endif
-__device__ __forceinline__ void gru_epilogue8(uint32_t tl, uint32_t region, uint32_t cu, const float *cst, float c, float cn,
-                                               uint32_t c_hi, uint32_t c_lo, int u0) {
-    uint32_t R[8], Z[8], NI[8], NH[8], PH[4], PL[4];
-    EPI_TR(0);
-    ld8(tl + region + C_R + cu, R);
-    ld8(tl + region + C_Z + cu, Z);
-    ld8(tl + region + C_NI + cu, NI);
-    ld8(tl + region + C_NH + cu, NH);
-    ld4(tl + c_hi + (u0 >> 1), PH);
-    ld4(tl + c_lo + (u0 >> 1), PL);
-    ld_wait();
-    EPI_TR(1);
-    const float *kp = cst + (u0 >> 1) * 8;
-    const F2 C2 = f2(c), CN2 = f2(cn), ONE = f2(1.0f);
+// as its bound: 16 MUFU lanes per clock and SM).  c = 1 / (128 S) undoes the operand scales (uniform per layer),
+// cn = -c log2 e; per pair of units the constants are {-log2e (b_ir + b_hr), -log2e (b_iz + b_hz), b_in, b_hn} x 2.
+// Exponents are capped at 2^30, which bounds the shared-reciprocal products; everything stays in the operand scale (h is
+// kept as 128 h).
+template <int HALVES>
+__device__ __forceinline__ void gru_epilogue(uint32_t tq, uint32_t region, uint32_t cu, const float *cst, float c, float cn,
+                                              uint32_t c_hi, uint32_t c_lo, int u0, int lane) {
+    uint32_t R[HALVES][4], Z[HALVES][4], NI[HALVES][4], NH[HALVES][4], PH[HALVES][2], PL[HALVES][2];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const float4 k0 = *reinterpret_cast<const float4 *>(kp + 8 * q);       // brn0, brn1, bzn0, bzn1
-        const float4 k1 = *reinterpret_cast<const float4 *>(kp + 8 * q + 4);   // bni0, bni1, bnh0, bnh1
-        const F2 tr = fma2(f2bits(R[2 * q], R[2 * q + 1]), CN2, f2(k0.x, k0.y));    // -log2e * pre-activation
-        const F2 tz = fma2(f2bits(Z[2 * q], Z[2 * q + 1]), CN2, f2(k0.z, k0.w));
-        const F2 AR = add2(f2(ex2_f(fminf(lo(tr), 30.0f)), ex2_f(fminf(hi(tr), 30.0f))), ONE);   // 1 + e^{-r}
-        const F2 AZ = add2(f2(ex2_f(fminf(lo(tz), 30.0f)), ex2_f(fminf(hi(tz), 30.0f))), ONE);
-        const F2 PA = mul2(AR, AZ);
-        const float inv = rcp_f(lo(PA) * hi(PA));
-        const F2 IAB = mul2(f2(hi(PA), lo(PA)), f2(inv));          // 1 / (ar az) of each unit
-        const F2 R2 = mul2(AZ, IAB), Z2 = mul2(AR, IAB);           // sigmoids
-        const F2 tnh = fma2(f2bits(NH[2 * q], NH[2 * q + 1]), C2, f2(k1.z, k1.w));
-        const F2 tni = fma2(f2bits(NI[2 * q], NI[2 * q + 1]), C2, f2(k1.x, k1.y));
-        const F2 ta = mul2(fma2(R2, tnh, tni), f2(2.885390081777927f));               // 2 log2e * n pre-activation
-        const F2 E = add2(f2(ex2_f(fminf(lo(ta), 30.0f)), ex2_f(fminf(hi(ta), 30.0f))), ONE);   // 1 + e^{2n}
-        const float m2 = -256.0f * rcp_f(lo(E) * hi(E));
-        const F2 N128 = fma2(f2(hi(E), lo(E)), f2(m2), f2(128.0f));   // 128 tanh = 128 - 256 / (1 + e^{2n})
-        const float2 hh = unpack_h2(PH[q]), hl = unpack_h2(PL[q]);
-        const F2 HS = add2(f2(hh.x, hh.y), f2(hl.x, hl.y));          // 128 h(t-1)
-        const F2 HN = fma2(HS, Z2, fma2(neg2(N128), Z2, N128));      // 128 h(t) = 128 ((h - n) z + n)
-        PH[q] = pack_f16x2(lo(HN), hi(HN));
-        const float2 hf = unpack_h2(PH[q]);
-        const F2 L = add2(HN, f2(-hf.x, -hf.y));
-        PL[q] = pack_f16x2(lo(L), hi(L));
+    for (int hh = 0; hh < HALVES; ++hh) {
+        const uint32_t th = tq + ((uint32_t)(16 * hh) << 16);
+        ld16x256(th + region + C_R + cu, R[hh]);
+        ld16x256(th + region + C_Z + cu, Z[hh]);
+        ld16x256(th + region + C_NI + cu, NI[hh]);
+        ld16x256(th + region + C_NH + cu, NH[hh]);
+        ld16x128(th + c_hi + (u0 >> 1), PH[hh]);
+        ld16x128(th + c_lo + (u0 >> 1), PL[hh]);
     }
-    EPI_TR(2);
-    st4(tl + c_hi + (u0 >> 1), PH);
-    st4(tl + c_lo + (u0 >> 1), PL);
-    EPI_TR(3);
+    const float *kp = cst + ((u0 >> 1) + (lane & 3)) * 8;
+    const float4 k0 = *reinterpret_cast<const float4 *>(kp);       // brn0, brn1, bzn0, bzn1
+    const float4 k1 = *reinterpret_cast<const float4 *>(kp + 4);   // bni0, bni1, bnh0, bnh1
+    const F2 C2 = f2(c), CN2 = f2(cn), ONE = f2(1.0f);
+    ld_wait();
+#pragma unroll
+    for (int hh = 0; hh < HALVES; ++hh) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {   // the two rollouts of this thread in the half
+            const F2 tr = fma2(f2bits(R[hh][2 * q], R[hh][2 * q + 1]), CN2, f2(k0.x, k0.y));    // -log2e * pre-activation
+            const F2 tz = fma2(f2bits(Z[hh][2 * q], Z[hh][2 * q + 1]), CN2, f2(k0.z, k0.w));
+            const F2 AR = add2(f2(ex2_f(fminf(lo(tr), 30.0f)), ex2_f(fminf(hi(tr), 30.0f))), ONE);   // 1 + e^{-r}
+            const F2 AZ = add2(f2(ex2_f(fminf(lo(tz), 30.0f)), ex2_f(fminf(hi(tz), 30.0f))), ONE);
+            const F2 PA = mul2(AR, AZ);
+            const float inv = rcp_f(lo(PA) * hi(PA));
+            const F2 IAB = mul2(f2(hi(PA), lo(PA)), f2(inv));          // 1 / (ar az) of each unit
+            const F2 R2 = mul2(AZ, IAB), Z2 = mul2(AR, IAB);           // sigmoids
+            const F2 tnh = fma2(f2bits(NH[hh][2 * q], NH[hh][2 * q + 1]), C2, f2(k1.z, k1.w));
+            const F2 tni = fma2(f2bits(NI[hh][2 * q], NI[hh][2 * q + 1]), C2, f2(k1.x, k1.y));
+            const F2 ta = mul2(fma2(R2, tnh, tni), f2(2.885390081777927f));               // 2 log2e * n pre-activation
+            const F2 E = add2(f2(ex2_f(fminf(lo(ta), 30.0f)), ex2_f(fminf(hi(ta), 30.0f))), ONE);   // 1 + e^{2n}
+            const float m2 = -256.0f * rcp_f(lo(E) * hi(E));
+            const F2 N128 = fma2(f2(hi(E), lo(E)), f2(m2), f2(128.0f));   // 128 tanh = 128 - 256 / (1 + e^{2n})
+            const float2 hh_ = unpack_h2(PH[hh][q]), hl = unpack_h2(PL[hh][q]);
+            const F2 HS = add2(f2(hh_.x, hh_.y), f2(hl.x, hl.y));        // 128 h(t-1)
+            const F2 HN = fma2(HS, Z2, fma2(neg2(N128), Z2, N128));      // 128 h(t) = 128 ((h - n) z + n)
+            PH[hh][q] = pack_f16x2(lo(HN), hi(HN));
+            const float2 hf = unpack_h2(PH[hh][q]);
+            const F2 L = add2(HN, f2(-hf.x, -hf.y));
+            PL[hh][q] = pack_f16x2(lo(L), hi(L));
+        }
+    }
+#pragma unroll
+    for (int hh = 0; hh < HALVES; ++hh) {
+        const uint32_t th = tq + ((uint32_t)(16 * hh) << 16);
+        st16x128(th + c_hi + (u0 >> 1), PH[hh]);
+        st16x128(th + c_lo + (u0 >> 1), PL[hh]);
+    }
 }
 
 // Optional pipeline trace (-DCPS_TC_TRACE): cycle stamps of one step of block 0, printed by the issuer / one epilogue
 // thread / one row thread.  Used to find what a step waits for.
 #ifdef CPS_TC_TRACE
-#define TC_TR(i) tr[i] = clock64()
+#define TC_TRACE_STEP 10
+#define TC_TR(i) do { if (blockIdx.x == 0 && lane == 0 && t == TC_TRACE_STEP) s_tr[i] = clock64(); } while (0)
 #else
 #define TC_TR(i)
 #endif
@@ -344,18 +364,24 @@ __global__ void __launch_bounds__(TC_NT, 1) net_tc_kernel(const __grid_constant_
     __shared__ __align__(8) unsigned long long s_bars[11];
     __shared__ unsigned s_ticket;
     __shared__ float s_bmin[4];
+#ifdef CPS_TC_TRACE
+    __shared__ long long s_tr[48];
+#endif
     const NetDev &N = a.net;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool is_epi = warp < TC_EW, is_row = warp >= TC_EW && warp < TC_EW + 4, is_mma = warp == TC_EW + 4;
     const int sub = (warp >> 2) & 3;           // epilogue warps: which 8 of a job's 32 units
     const int row = 32 * (warp & 3) + lane;    // rollout inside the tile (epilogue and row warps)
     const int T = a.T;
-    // Small batches are latency-bound by the step's dependence chain, not by throughput: spreading the rollouts over more
-    // SMs with only the first 32 / 64 tensor-memory lanes of each CTA live shortens the MUFU-bound epilogues (the MMAs
-    // cost the same for any number of live rows: M = 128 is the instruction's minimum).
+    // Small batches are latency-bound by the step's dependence chain, not by throughput: with only the first 16 tensor-
+    // memory lanes of every lane quarter live (64 rollouts per CTA) the MUFU-bound epilogues take half the time, because the
+    // 16-lane access shapes spread those rollouts over all 32 threads of the epilogue warps -- and all four schedulers stay
+    // in use, a warp's lane quarter being tied to its scheduler.  (The MMAs cost the same for any number of live rows:
+    // M = 128 is the instruction's minimum.)
+    const int rpq = a.tc_rows >> 2;            // live rollouts per lane quarter: 16 | 32
     const int row0 = blockIdx.x * a.tc_rows;
-    const bool live = row < a.tc_rows;         // warp-uniform (tc_rows is a multiple of 32)
-    const int k = row0 + row;
+    const bool live = lane < rpq;              // per lane; dead lanes run along on clamped indices and store nothing
+    const int k = row0 + rpq * (warp & 3) + lane;
     const bool active = is_row && live && k < a.B;
     const int kc = min(k, a.B - 1);
     float *s_f = reinterpret_cast<float *>(smem + O_FLOATS);
@@ -377,9 +403,8 @@ __global__ void __launch_bounds__(TC_NT, 1) net_tc_kernel(const __grid_constant_
         bar_init(wbar, 1);
         for (int r = 0; r < 3; ++r) bar_init(doneb(r), 1);
         bar_init(outb, 1);
-        // arrivals come from the warps that carry live rollouts only; the others skip the horizon loop
-        for (int j = 0; j < 4; ++j) bar_init(epib(j), (uint32_t)(a.tc_rows / 32) * (TC_EW / 4));
-        bar_init(xrdy, (uint32_t)(a.tc_rows / 32));
+        for (int j = 0; j < 4; ++j) bar_init(epib(j), TC_EW / 2);   // a job is one group's: 8 warps
+        bar_init(xrdy, 4);
         bar_init(tailb, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(wbar), "r"(TC_IMAGE_BYTES) : "memory");
@@ -419,7 +444,7 @@ __global__ void __launch_bounds__(TC_NT, 1) net_tc_kernel(const __grid_constant_
     const RowSumPlan rsp = row_sum_plan(T + 1);
     float *sl = s_rs + row;
     float rs_tail = 0.0f;
-    if (is_row && live) {
+    if (is_row) {
         if (MPPI) {
             nz = a.noise + (long long)kc * a.ns_k;
             na = nz[0] * a.mp.sigma;
@@ -471,7 +496,7 @@ __global__ void __launch_bounds__(TC_NT, 1) net_tc_kernel(const __grid_constant_
     float st[6], y[6], feat[6];
 #pragma unroll
     for (int c = 0; c < 6; ++c) { st[c] = 0.0f; y[c] = 0.0f; }
-    if (is_epi && live) {
+    if (is_epi) {
         float v[TC_EU];
 #pragma unroll 1
         for (int l = 0; l < 2; ++l) {
@@ -484,7 +509,7 @@ __global__ void __launch_bounds__(TC_NT, 1) net_tc_kernel(const __grid_constant_
             }
         }
     }
-    if (is_row && live) {
+    if (is_row) {
 #pragma unroll
         for (int c = 0; c < 6; ++c) st[c] = a.s0[(long long)kc * a.ss_b + c];
         next_control(0);
@@ -516,9 +541,6 @@ __global__ void __launch_bounds__(TC_NT, 1) net_tc_kernel(const __grid_constant_
             const int i1 = (t3 == 2) ? 0 : t3 + 1, i2 = (i1 == 2) ? 0 : i1 + 1;
             const uint32_t q0 = tm + 128u * (uint32_t)t3, q1 = tm + 128u * (uint32_t)i1, q2 = tm + 128u * (uint32_t)i2;
             // jobs of this step: 1a -> q0, 1b -> q1, 2a -> q2, 2b -> q0; next step: 1a -> q1, 1b -> q2, 2a -> q0
-#ifdef CPS_TC_TRACE
-            long long tr[12];
-#endif
             TC_TR(0);
             if (t > 0) { bar_wait(xrdy, (uint32_t)((t - 1) & 1)); tc_fence_after(); }   // x(t) is in shared memory
             TC_TR(1);
@@ -550,57 +572,44 @@ __global__ void __launch_bounds__(TC_NT, 1) net_tc_kernel(const __grid_constant_
             issue_OUT(q0 + C_NI, ah2_hi, ah2_lo, sm0 + O_WOUT_HI, sm0 + O_WOUT_LO);
             tc_commit(outb);
             TC_TR(10);
-#ifdef CPS_TC_TRACE
-            if (blockIdx.x == 0 && lane == 0 && t == 10)
-                printf("ISSUER t=%d: wait x %lld | X1a X1b H2a %lld | wait e1a %lld | H2b %lld | wait e1b %lld | X2a X2b H1a' %lld | wait e2a %lld | H1b' %lld | wait e2b %lld | OUT %lld | step %lld\n",
-                       t, tr[1] - tr[0], tr[2] - tr[1], tr[3] - tr[2], tr[4] - tr[3], tr[5] - tr[4], tr[6] - tr[5], tr[7] - tr[6],
-                       tr[8] - tr[7], tr[9] - tr[8], tr[10] - tr[9], tr[10] - tr[0]);
-#endif
             t3 = i1;
         }
-    } else if (is_epi && live) {
+    } else if (is_epi) {
+        // Two groups of 8 warps (two per scheduler each): group g takes the half-layer jobs (layer 1, g) and (layer 2, g) of
+        // every step, a warp 16 of the job's 32 units.  The two jobs of a layer become ready almost together, so the groups
+        // run side by side and one group's tensor-memory latencies and hand-offs are filled with the other's MUFU work.
+        const bool two = rpq > 16;   // both 16-lane halves of the quarter carry rollouts
+        const int g = warp >> 3, hs = (warp >> 2) & 1;   // job group; which 16 of the job's 32 units
 #pragma unroll 1
         for (int t = 0; t < T; ++t) {
 #pragma unroll 1
-#ifdef CPS_TC_TRACE
-            long long tr[12];
-#endif
-            for (int job = 0; job < 4; ++job) {
-                const int j = 4 * t + job, l = job >> 1, ch = job & 1;
-                TC_TR(3 * job);
+            for (int l = 0; l < 2; ++l) {
+                const int job = 2 * l + g, j = 4 * t + job;
+                if (warp == 8 * g) TC_TR(16 + 4 * job);
                 bar_wait(doneb(j % 3), (uint32_t)((j / 3) & 1));
                 tc_fence_after();
-                TC_TR(3 * job + 1);
-                if (live)
-                    gru_epilogue8(tl, region(j), (uint32_t)(TC_EU * sub), l ? cst2 : cst1, l ? ec2 : ec1, l ? ecn2 : ecn1,
-                                  l ? C_AH2_HI : C_AH1_HI, l ? C_AH2_LO : C_AH1_LO, chunk_u0(ch));
-#ifdef CPS_TC_TRACE
-                const long long c_mid = clock64();
-#endif
-                warp_signal(epib(job), lane);
-                TC_TR(3 * job + 2);
-#ifdef CPS_TC_TRACE
-                if (blockIdx.x == 0 && tid == 0 && t == 10) {
-                    tr[3 * job] = tr[3 * job + 2] - c_mid;   // the signal part alone
-                    printf("  job %d: loads %lld math %lld stores %lld\n", job, g_epi_t[1] - g_epi_t[0], g_epi_t[2] - g_epi_t[1], g_epi_t[3] - g_epi_t[2]);
+                if (warp == 8 * g) TC_TR(16 + 4 * job + 1);
+#pragma unroll 1
+                for (int e = 0; e < 2; ++e) {
+                    const int cu = 16 * hs + 8 * e;   // first unit inside the job
+                    if (two)
+                        gru_epilogue<2>(tl, region(j), (uint32_t)cu, l ? cst2 : cst1, l ? ec2 : ec1, l ? ecn2 : ecn1,
+                                        l ? C_AH2_HI : C_AH1_HI, l ? C_AH2_LO : C_AH1_LO, 32 * g + cu, lane);
+                    else
+                        gru_epilogue<1>(tl, region(j), (uint32_t)cu, l ? cst2 : cst1, l ? ec2 : ec1, l ? ecn2 : ecn1,
+                                        l ? C_AH2_HI : C_AH1_HI, l ? C_AH2_LO : C_AH1_LO, 32 * g + cu, lane);
                 }
-#endif
+                if (warp == 8 * g) TC_TR(16 + 4 * job + 2);
+                warp_signal(epib(job), lane);
+                if (warp == 8 * g) TC_TR(16 + 4 * job + 3);
             }
-#ifdef CPS_TC_TRACE
-            if (blockIdx.x == 0 && tid == 0 && t == 10)
-                printf("EPILOGUE t=%d: work (of which st-wait + signal): 1a %lld (%lld) | 1b %lld (%lld) | 2a %lld (%lld) | 2b %lld (%lld)\n", t,
-                       tr[2] - tr[1], tr[0], tr[5] - tr[4], tr[3], tr[8] - tr[7], tr[6], tr[11] - tr[10], tr[9]);
-#endif
         }
-    } else if (is_row && live) {
+    } else if (is_row) {
 #pragma unroll 1
         for (int t = 0; t < T; ++t) {
             // behind the tensor cores: state s_t -> trajectory row, stage cost; the control of step t + 1
-#ifdef CPS_TC_TRACE
-            long long tr[4];
-#endif
-            TC_TR(0);
-            if (live) {
+            if (warp == TC_EW) TC_TR(40);
+            {
                 u_cur = u_nxt; du_cur = du_nxt;
                 if (t > 0) compose_state(N, y, st);
                 if (traj) {
@@ -619,11 +628,11 @@ __global__ void __launch_bounds__(TC_NT, 1) net_tc_kernel(const __grid_constant_
                 if (t + 1 < T) next_control(t + 1);
             }
             // linear output layer -> feedback as the next input (autoregression.py:94-98)
-            TC_TR(1);
+            if (warp == TC_EW) TC_TR(41);
             bar_wait(outb, (uint32_t)(t & 1));
             tc_fence_after();
-            TC_TR(2);
-            if (live) {
+            if (warp == TC_EW) TC_TR(42);
+            {
                 uint32_t o[8];
                 ld8(tl + region(4 * t + 6) + C_NI, o);
                 ld_wait();
@@ -636,18 +645,26 @@ __global__ void __launch_bounds__(TC_NT, 1) net_tc_kernel(const __grid_constant_
                 __syncwarp();
                 if (lane == 0) bar_arrive(xrdy);
             }
-            TC_TR(3);
-#ifdef CPS_TC_TRACE
-            if (blockIdx.x == 0 && tid == TC_EPI && t == 10)
-                printf("ROW t=%d: bookkeeping %lld | wait out %lld | feedback %lld\n", t, tr[1] - tr[0], tr[2] - tr[1], tr[3] - tr[2]);
-#endif
+            if (warp == TC_EW) TC_TR(43);
         }
     }
     tc_sync();
+#ifdef CPS_TC_TRACE
+    if (blockIdx.x == 0 && tid == 0) {
+        const long long b = s_tr[0];
+        printf("TRACE step %d (cycles after the issuer's step start)\n", TC_TRACE_STEP);
+        printf(" issuer: x ready %lld | X1a X1b H2a issued %lld | e1a seen %lld | H2b issued %lld | e1b seen %lld | X2a X2b H1a' issued %lld | e2a seen %lld | H1b' issued %lld | e2b seen %lld | OUT issued %lld\n",
+               s_tr[1] - b, s_tr[2] - b, s_tr[3] - b, s_tr[4] - b, s_tr[5] - b, s_tr[6] - b, s_tr[7] - b, s_tr[8] - b, s_tr[9] - b, s_tr[10] - b);
+        for (int j = 0; j < 4; ++j)
+            printf(" epilogue job %d: wait from %lld | region ready %lld | math done %lld | signalled %lld\n", j, s_tr[16 + 4 * j] - b,
+                   s_tr[17 + 4 * j] - b, s_tr[18 + 4 * j] - b, s_tr[19 + 4 * j] - b);
+        printf(" row: step start %lld | bookkeeping done %lld | out ready %lld | x written %lld\n", s_tr[40] - b, s_tr[41] - b, s_tr[42] - b, s_tr[43] - b);
+    }
+#endif
 
     // ---- last state, costs, hidden state out ---------------------------------------------------------------------------
     float J = 0.0f;
-    if (is_row && live) {
+    if (is_row) {
         compose_state(N, y, st);
         if (traj) {
 #pragma unroll
@@ -685,7 +702,7 @@ __global__ void __launch_bounds__(TC_NT, 1) net_tc_kernel(const __grid_constant_
             }
         }
     };
-    if (a.h_final && is_epi && live) store_hidden((k < a.B) ? a.h_final + (long long)k * (2 * TC_H) : nullptr);
+    if (a.h_final && is_epi) store_hidden((live && k < a.B) ? a.h_final + (long long)k * (2 * TC_H) : nullptr);
 
     bool last = false;
     if (MPPI) {
@@ -761,8 +778,8 @@ __global__ void __launch_bounds__(TC_NT, 1) net_tc_kernel(const __grid_constant_
             bar_wait(tailb, 0);
             tc_fence_after();
             if (is_epi && upd) {
-                gru_epilogue8(tl, 0, (uint32_t)(TC_EU * sub), cst1, ec1, ecn1, C_AH1_HI, C_AH1_LO, chunk_u0(0));
-                gru_epilogue8(tl, 128, (uint32_t)(TC_EU * sub), cst1, ec1, ecn1, C_AH1_HI, C_AH1_LO, chunk_u0(1));
+                gru_epilogue<1>(tl, 0, (uint32_t)(TC_EU * sub), cst1, ec1, ecn1, C_AH1_HI, C_AH1_LO, chunk_u0(0), lane);
+                gru_epilogue<1>(tl, 128, (uint32_t)(TC_EU * sub), cst1, ec1, ecn1, C_AH1_HI, C_AH1_LO, chunk_u0(1), lane);
             }
             tc_sync();
             if (is_mma) {
@@ -775,8 +792,8 @@ __global__ void __launch_bounds__(TC_NT, 1) net_tc_kernel(const __grid_constant_
             bar_wait(tailb, 1);
             tc_fence_after();
             if (is_epi && upd) {
-                gru_epilogue8(tl, 256, (uint32_t)(TC_EU * sub), cst2, ec2, ecn2, C_AH2_HI, C_AH2_LO, chunk_u0(0));
-                gru_epilogue8(tl, 0, (uint32_t)(TC_EU * sub), cst2, ec2, ecn2, C_AH2_HI, C_AH2_LO, chunk_u0(1));
+                gru_epilogue<1>(tl, 256, (uint32_t)(TC_EU * sub), cst2, ec2, ecn2, C_AH2_HI, C_AH2_LO, chunk_u0(0), lane);
+                gru_epilogue<1>(tl, 0, (uint32_t)(TC_EU * sub), cst2, ec2, ecn2, C_AH2_HI, C_AH2_LO, chunk_u0(1), lane);
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 store_hidden(row == 0 ? a.h_ref : nullptr);
             }
@@ -867,13 +884,14 @@ int cps_net_tc_launch(cps_handle *h, NetArgs &a, bool mppi, int n_rows) {
     const size_t smem = cps_net_tc_smem(&h->mp, mppi);
     void (*fn)(const NetArgs) = mppi ? net_tc_kernel<true> : net_tc_kernel<false>;
     CUDA_TRY(h, cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    // live rollouts per CTA: the fewest that still give every CTA its own SM (see the kernel's comment on tc_rows)
+    // live rollouts per CTA: 64 while that still gives every CTA its own SM (see the kernel's comment on rpq)
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device);
-    a.tc_rows = (n_rows <= 32 * sms) ? 32 : ((n_rows <= 64 * sms) ? 64 : TC_ROWS);
+    a.tc_rows = (n_rows <= 64 * sms) ? 64 : TC_ROWS;
     const int grid = (n_rows + a.tc_rows - 1) / a.tc_rows;
     fn<<<grid, TC_NT, smem, h->stream>>>(a);
     h->launches += 1;
+    h->net_last_kernel = 2;
     CUDA_TRY(h, cudaGetLastError());
     return CPS_OK;
 }

@@ -86,7 +86,7 @@ typedef enum cps_layout { CPS_ROLLOUT_MAJOR = 0, CPS_TIME_MAJOR = 1 } cps_layout
 #define CPS_MPPI_PAIR_MIN_ROLLOUTS 65536 /* cps_mppi_step: from this K on (even K, native noise order, no logging outputs)
                                            the solve runs two rollouts per thread in packed FP32 */
 #define CPS_FLAG_NET_TENSOR_CORES 0x10u /* neural predictor: force the tcgen05 tensor-core kernel (2 x 64 GRU only) */
-#define CPS_FLAG_NET_FP32 0x20u         /* neural predictor: force the FP32 CUDA-core kernel (default: by batch size) */
+#define CPS_FLAG_NET_FP32 0x20u         /* neural predictor: force the FP32 CUDA-core kernel (default: tensor cores for 2 x 64 GRU) */
 
 typedef struct cps_config {
     int struct_size;      /* = sizeof(cps_config), ABI check */
@@ -383,6 +383,10 @@ int cps_measure_peaks(cps_handle *h, double *fp32_tflops, double *mufu_gops);
 /* ---- diagnostics ------------------------------------------------------------------------------------- */
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches claim). */
 long long cps_launch_count(const cps_handle *h);
+/* Which network kernel the last cps_net_rollout / neural cps_mppi_step of this handle launched: 0 none yet, 1 the FP32
+ * CUDA-core kernel (net_kernel), 2 the tensor-core kernel (net_tc_kernel; the default for plain 2 x 64 GRU networks).
+ * The reference has no counterpart (its predictor is one torch module, SI_Toolkit/Predictors/predictor_autoregressive_neural.py:266-313). */
+int cps_net_last_kernel(const cps_handle *h);
 /* Cumulative count of non-finite trajectory costs seen by cps_mppi_step since cps_create (the reference propagates
  * NaN silently into exp(); this library does the same arithmetic but counts it).  Synchronises. */
 int cps_nonfinite_costs(cps_handle *h, int *count_out);

@@ -372,6 +372,44 @@ def test_tc_matches_fp32_kernel_K65536():
     np.testing.assert_allclose(out["tensor"][3], out["fp32"][3], rtol=0, atol=5e-6)
 
 
+@pytest.mark.parametrize("cost", ["quadratic_boundary", "default"])
+def test_tc_matches_fp32_kernel_shifted_costs(cost):
+    """MAX_COST plugins on the tensor-core kernel (backend-ordered row sum of the T+1 cost entries): same costs and control
+    as the FP32 kernel, which is pinned against the reference (mppi_net_gru32_qb)."""
+    import torch
+    from cartpolesimulation_b200 import _lib as L
+    z, m = load_golden("mppi_net_gru64_gradmin")
+    sp = net_spec_from_golden(z)
+    K, T = 4096, 50
+    out = {}
+    rng = np.random.default_rng(7)
+    noise_np = rng.standard_normal((K, 16)).astype(np.float32)
+    for kern in ("fp32", "tensor"):
+        eng = make_engine(sp, K, T, cost=cost, net_kernel=kern)
+        noise = torch.from_numpy(noise_np[:, :eng.n_ind].copy()).to(eng.device)
+        J = torch.empty(K, device=eng.device)
+        u = eng.mppi_step(torch.from_numpy(z["s"][1]).to(eng.device), noise, L.ROLLOUT_MAJOR, 0.0, None, J)
+        out[kern] = (float(u.cpu()[0]), J.cpu().numpy(), eng.get_u_nom())
+        assert eng.net_last_kernel() == kern
+        assert eng.nonfinite_costs() == 0
+    assert shifted_cost_ok(out["tensor"][1], out["fp32"][1])
+    record("tc_vs_fp32_shifted", cost, u=abs(out["tensor"][0] - out["fp32"][0]),
+           u_nom=float(np.abs(out["tensor"][2] - out["fp32"][2]).max()))
+    assert abs(out["tensor"][0] - out["fp32"][0]) < 2e-5
+    np.testing.assert_allclose(out["tensor"][2], out["fp32"][2], rtol=0, atol=2e-5)
+
+
+def test_default_kernel_choice():
+    """plain 2 x 64 GRU -> tensor cores at every batch size (BASELINE.json configs[2]: K = 2000); anything else -> FP32."""
+    import torch
+    for net, K, want in ((TC_NET, 2000, "tensor"), (TC_NET, 16, "tensor"), ("net_GRU_6IN_32H1_32H2_5OUT_0", 2000, "fp32"),
+                         ("net_diff_GRU_6IN_64H1_64H2_5OUT_1", 2000, "fp32")):
+        z, m = load_golden(net)
+        eng = make_engine(net_spec_from_golden(z), K, 5)
+        eng.net_rollout(torch.zeros(6, device=eng.device), torch.zeros((K, 5), device=eng.device))
+        assert eng.net_last_kernel() == want, (net, K)
+
+
 def test_tc_flag_rejected_for_other_networks():
     z, m = load_golden("net_GRU_6IN_32H1_32H2_5OUT_0")
     sp = net_spec_from_golden(z)
