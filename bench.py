@@ -486,23 +486,89 @@ def fleet_bench(device, E_total=8192, world=1, rank=0, periods=20, K=2000, T=50)
 
 
 def sharded_solve(local_rank, world, n=30):
-    """configs[3] with K sharded over the ranks: local rollouts + ONE all-gather of n_ind+2 floats per rank (NCCL) +
-    merge.  Device time of the slowest rank."""
+    """configs[3] with K sharded over the ranks, both transports of ShardedMPPI: "peer" = ONE launch per solve (local
+    rollouts, records pushed over NVLink into every rank's symmetric-memory buffer, update finished on every rank) and
+    "allgather" = kernel + NCCL all-gather of n_ind+2 floats + finalize kernel.  Device time of the slowest rank.
+    Self-check on every run: all ranks hold bit-identical u_nom, and they agree with a one-GPU solve of the same K
+    rollouts (same noise) on rank 0 to 2e-6 (different association order of the block sums only)."""
     import torch
     import torch.distributed as dist
+    from cartpolesimulation_b200.core import Engine
     from cartpolesimulation_b200.distributed import ShardedMPPI
     K, T = 65536, 100
-    sm = ShardedMPPI(K, T, integrator="ODE", cost="quadratic_boundary", device=local_rank)
+    dev = torch.device("cuda", local_rank)
+    rank = dist.get_rank() if world > 1 else 0
     a = np.pi - 1e-3
-    s = torch.tensor([a, 0.0, np.cos(a), np.sin(a), 0.0, 0.0], device=sm.device, dtype=torch.float32)
-    noise = torch.randn((sm.engine.n_ind, sm.K_local), device=sm.device)
-    ks = _event_times(lambda: sm.step(s, noise, 1, 0.0), n)
-    t = torch.tensor([float(np.median(ks))], device=sm.device, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    kms = float(t.item())
-    return {"K_total": K, "T": T, "ranks": world, "solve_ms_median_max_over_ranks": kms,
-            "state_steps_per_s": K * T * N_SUB / (kms * 1e-3), "exchange_bytes_per_rank": 4 * sm.rec}
+    s = torch.tensor([a, 0.0, np.cos(a), np.sin(a), 0.0, 0.0], device=dev, dtype=torch.float32)
+    out = {"K_total": K, "T": T, "ranks": world}
+    full = None
+    for exchange in ("peer", "allgather"):
+        rec = {}
+        try:
+            sm = ShardedMPPI(K, T, integrator="ODE", cost="quadratic_boundary", device=local_rank, exchange=exchange)
+            if full is None:   # the same draws on every rank (seeded device generator), each takes its slice
+                g = torch.Generator(device=dev)
+                g.manual_seed(7)
+                full = torch.randn((sm.engine.n_ind, K), device=dev, generator=g)
+            noise = sm.noise_slice(full)
+            # ---- parity --------------------------------------------------------------------------------------------
+            sm.reset(0.0)
+            u = sm.step(s, noise, 1, 0.0)
+            mine = torch.cat([torch.from_numpy(sm.get_u_nom()).to(dev), u.reshape(1).float()])
+            allr = torch.empty((world, mine.numel()), device=dev)
+            if world > 1:
+                dist.all_gather_into_tensor(allr, mine)
+            else:
+                allr[0] = mine
+            rec["ranks_bit_identical"] = bool((allr == allr[0]).all().item())
+            if rank == 0:
+                ref = Engine(K, T, integrator="ODE", cost="quadratic_boundary", device=local_rank)
+                ref.mppi_reset(0.0)
+                u1 = ref.mppi_step(s, full, 1, 0.0)
+                d_nom = float(np.abs(ref.get_u_nom() - sm.get_u_nom()).max())
+                d_u = abs(float(u1.cpu()[0]) - float(u.cpu()[0]))
+                rec["vs_one_gpu_solve"] = {"u_nom_max_abs_diff": d_nom, "u_abs_diff": d_u, "tol": 2e-6}
+                rec["parity_ok"] = bool(rec["ranks_bit_identical"] and d_nom <= 2e-6 and d_u <= 2e-6)
+                ref.close()
+            # ---- time ----------------------------------------------------------------------------------------------
+            ks = _event_times(lambda: sm.step(s, noise, 1, 0.0), n)
+            t = torch.tensor([float(np.median(ks))], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            rec["solve_ms_median_max_over_ranks"] = float(t.item())
+            rec["state_steps_per_s"] = K * T * N_SUB / (float(t.item()) * 1e-3)
+            rec["exchange_bytes_per_rank"] = 4 * sm.rec
+            rec["transport"] = sm.exchange
+            rec["launches_per_solve"] = 1 if sm.exchange == "peer" else 2
+            # ---- where the time goes (this rank; CUDA events around each stream operation) ----------------------------
+            if sm.exchange == "allgather":
+                eng = sm.engine
+                bd = {"local_kernel_us": 1e3 * float(np.median(_event_times(lambda: eng.mppi_step(s, noise, 1, 0.0), n))),
+                      "finalize_us": 1e3 * float(np.median(_event_times(lambda: eng.mppi_finalize(sm._gathered), n)))}
+                if world > 1:
+                    bd["allgather_us"] = 1e3 * float(np.median(_event_times(
+                        lambda: dist.all_gather_into_tensor(sm._gathered, sm._partial), n)))
+                rec["breakdown"] = bd
+            else:
+                solo = Engine(sm.K_local, T, integrator="ODE", cost="quadratic_boundary", device=local_rank)
+                lk = 1e3 * float(np.median(_event_times(lambda: solo.mppi_step(s, noise, 1, 0.0), n)))
+                solo.close()
+                rec["breakdown"] = {"local_kernel_us": lk, "exchange_and_wait_us": 1e3 * float(np.median(ks)) - lk,
+                                    "note": "local = the same K_local solve without the exchange; the rest is the push "
+                                            "over NVLink plus waiting for the slowest rank's record"}
+                rec["peer_timeouts"] = sm.engine.peer_timeouts()
+            sm.engine.close()
+        except Exception as ex:
+            rec["error"] = repr(ex)
+        out[exchange] = rec
+    best = min((out[k] for k in ("peer", "allgather") if "solve_ms_median_max_over_ranks" in out[k]),
+               key=lambda r: r["solve_ms_median_max_over_ranks"], default=None)
+    if best:
+        out["solve_ms_median_max_over_ranks"] = best["solve_ms_median_max_over_ranks"]
+        out["state_steps_per_s"] = best["state_steps_per_s"]
+        out["parity_ok"] = all(out[k].get("parity_ok", True) and out[k].get("ranks_bit_identical", False)
+                               for k in ("peer", "allgather") if "error" not in out[k])
+    return out
 
 
 def run_ours(args):
@@ -547,27 +613,62 @@ def run_ours(args):
     for _ in range(max(args.warmup, 3)):
         one_pass()
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    launches0 = eng.launch_count()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
-    t_all0 = torch.cuda.Event(enable_timing=True)
-    t_all1 = torch.cuda.Event(enable_timing=True)
-    t_all0.record()
+    # The K timed passes are replayed as ONE CUDA graph (captured before the timed region): the host issues a single
+    # launch, so Python / ctypes launch gaps and host-side jitter of N concurrent processes stay out of the device time.
+    graph = None
+    if not args.no_graph:
+        try:
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                one_pass()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=side):
+                    for _ in range(args.steps):
+                        one_pass()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize()
+            g.replay()          # one untimed replay (graph upload)
+            torch.cuda.synchronize()
+            graph = g
+        except Exception as ex:   # fall back to K separate launches
+            print(f"[bench] CUDA graph capture failed ({ex!r}); timing {args.steps} separate launches", file=sys.stderr)
+            graph = None
+            torch.cuda.synchronize()
+        eng.use_current_stream()
+    # per-launch kernel time (CUDA events around single launches on the launching stream) for the roofline
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(min(args.steps, 10))]
     for e0, e1 in evs:
         e0.record()
         one_pass()
         e1.record()
+    torch.cuda.synchronize()
+    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = eng.launch_count()
+    barrier()
+    t_all0 = torch.cuda.Event(enable_timing=True)
+    t_all1 = torch.cuda.Event(enable_timing=True)
+    t_all0.record()
+    if graph is not None:
+        graph.replay()
+    else:
+        for _ in range(args.steps):
+            one_pass()
     t_all1.record()
     barrier()
-    launches = eng.launch_count() - launches0
+    launches = (args.steps if graph is not None else eng.launch_count() - launches0)
     total_ms = t_all0.elapsed_time(t_all1)
-    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+    per_rank = None
     if world > 1:
-        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
+        # every rank's own device time and per-launch kernel time: with no communication in the timed region, the spread
+        # between ranks (GPU-to-GPU clock / power differences) is all there is to the weak-scaling loss
+        mine = torch.tensor([total_ms / args.steps, kern_ms], device=dev, dtype=torch.float64)
+        allr = torch.empty((world, 2), device=dev, dtype=torch.float64)
+        dist.all_gather_into_tensor(allr, mine)
+        per_rank = {"ms_per_step": [float(v) for v in allr[:, 0].cpu()], "kernel_ms": [float(v) for v in allr[:, 1].cpu()]}
+        total_ms = float(allr[:, 0].max().item()) * args.steps
     steps_per_pass = float(B) * T * N_SUB
     value = steps_per_pass * args.steps * world / (total_ms * 1e-3)
 
@@ -635,8 +736,9 @@ def run_ours(args):
         ncu_view = rt.get("ncu")   # pipe utilisation of the same kernel from the committed ncu capture (not measured live)
     except Exception:
         pass
-    roofline = {"bound": "fp32", "kernel": "rollout_kernel<ODE_v0>", "achieved": achieved_tflops, "peak": fp32_peak,
+    roofline = {"bound": "fp32", "kernel": "%s<ODE_v0>" % (eng.rollout_last_kernel() or "rollout_kernel"), "achieved": achieved_tflops, "peak": fp32_peak,
                 "unit": "TFLOP/s", "frac": achieved_tflops / fp32_peak if fp32_peak else None, "traffic": traffic,
+                "traffic_source": "committed ncu capture (profiles/roofline_traffic.json), not measured in this run",
                 "peak_source": "cps_measure_peaks FFMA microbenchmark, this run (not in MEASURED_PEAKS.json)",
                 "flop_per_state_step": FLOP_PER_STATE_STEP, "kernel_ms": kern_ms,
                 "fp32_pipe": {"lane_ops_per_state_step": FP32_LANE_OPS_PER_STATE_STEP,
@@ -674,12 +776,14 @@ def run_ours(args):
             "config": {"workload": workload_name(B, T), "per_gpu_batch": B, "l2": "inputs larger than L2 (Q = %d MB)" % (Q.numel() * 4 >> 20),
                        "sincos": ("MUFU every substep" if args.fast_sincos else "sincosf every substep")
                        if (args.fast_sincos or args.substep_sincos) else
-                       "rotation substeps + sincosf resync per control step (default)"},
+                       "rotation substeps + sincosf resync per control step (default)",
+                       "timed_region": ("one CUDA graph replay of the %d passes" % args.steps) if graph is not None
+                       else ("%d separate launches" % args.steps)},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * e2e_s / e2e_steps, "api": "cps_rollout_host (pinned host buffers)",
                     "numa_bound_cpus": len(numa_cpus) if numa_cpus else None},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
-            "clocks": sampler.summary(), "mppi_solve": mppi, "mppi_sharded": sharded, "fleet_sharded": fleet}
+            "clocks": sampler.summary(), "per_rank": per_rank, "mppi_solve": mppi, "mppi_sharded": sharded, "fleet_sharded": fleet}
     print(json.dumps(line))
     if world > 1:
         dist.barrier()
@@ -697,6 +801,7 @@ def main():
     ap.add_argument("--fast-sincos", action="store_true", help="MUFU sin/cos every substep (parity-checked separately)")
     ap.add_argument("--substep-sincos", action="store_true", help="sincosf every substep, literally as the reference")
     ap.add_argument("--no-mppi", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time K separate launches instead of one CUDA graph of K passes")
     ap.add_argument("--mppi-calls", type=int, default=1000)
     args = ap.parse_args()
     if args.impl == "reference":

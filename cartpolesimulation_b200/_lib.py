@@ -76,6 +76,9 @@ SYMBOLS = {
     "cps_mppi_set_shard": (C.c_int, [_VP, C.c_int, _VP]),
     "cps_mppi_partial_size": (C.c_int, [_VP]),
     "cps_mppi_finalize": (C.c_int, [_VP, _VP, C.c_int, _VP, _VP]),
+    "cps_mppi_peer_buffer_floats": (C.c_longlong, [_VP, C.c_int]),
+    "cps_mppi_set_peers": (C.c_int, [_VP, C.c_int, C.c_int, C.POINTER(_VP)]),
+    "cps_mppi_peer_timeouts": (C.c_int, [_VP, C.POINTER(C.c_int)]),
     "cps_legacy_step": (C.c_int, [_VP, _VP, _VP, C.c_int, _VP, _VP, _VP, C.c_int, _VP]),
     "cps_legacy_step_host": (C.c_int, [_VP, _FP, _VP, C.c_int, _FP]),
     "cps_legacy_advance": (C.c_int, [_VP, _FP]),
@@ -114,6 +117,7 @@ SYMBOLS = {
     "cps_measure_peaks": (C.c_int, [_VP, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "cps_launch_count": (C.c_longlong, [_VP]),
     "cps_net_last_kernel": (C.c_int, [_VP]),
+    "cps_rollout_last_kernel": (C.c_int, [_VP]),
     "cps_nonfinite_costs": (C.c_int, [_VP, C.POINTER(C.c_int)]),
 }
 

@@ -108,13 +108,20 @@ class Engine:
     def set_physics(self, **params):
         v = cfgmod.physics_vector(**params)
         self._chk(self.lib.cps_set_physics(self._h, v.ctypes.data_as(L._FP), len(v)))
+        u_max = float(v[cfgmod.PHYS_ORDER.index("u_max")])
+        if u_max != getattr(self, "_u_max", 1.77):
+            # MAX_COST of the shifted plugins contains u_max^2 (default.py:20, quadratic_boundary.py:23): keep it in step
+            self._u_max = u_max
+            if getattr(self, "_cost_cfg_set", False):
+                self.set_cost_config(self._cost_cfg)
 
     def set_cost_params(self, vec):
         v = np.ascontiguousarray(vec, dtype=np.float32)
         self._chk(self.lib.cps_set_cost_params(self._h, v.ctypes.data_as(L._FP), len(v)))
 
     def set_cost_config(self, cfg: dict | None = None):
-        self.set_cost_params(cfgmod.cost_vector(self.cost_name, cfg))
+        self._cost_cfg, self._cost_cfg_set = cfg, True
+        self.set_cost_params(cfgmod.cost_vector(self.cost_name, cfg, u_max=getattr(self, "_u_max", 1.77)))
 
     def set_mppi_params(self, cc_weight=1.0, R=1.0, LBD=100.0, NU=1000.0, SQRTRHOINV=0.03, lo=-1.0, hi=1.0):
         sigma = np.float32(np.array(SQRTRHOINV) * (1 / np.sqrt(self.dt)))  # optimizer_mppi.py:130
@@ -250,6 +257,24 @@ class Engine:
                 raise ValueError("partial_out too small")
             self._chk(self.lib.cps_mppi_set_shard(self._h, 1, _ptr(partial_out)))
         self._shard_buf = partial_out
+
+    def peer_buffer_floats(self, world: int) -> int:
+        return int(self.lib.cps_mppi_peer_buffer_floats(self._h, int(world)))
+
+    def set_peers(self, world: int, rank: int, peer_ptrs):
+        """K sharded over `world` GPUs with the exchange inside the solve launch (cps_mppi_set_peers): peer_ptrs[r] is the
+        device address, as mapped on this GPU, of rank r's zero-initialised exchange buffer of peer_buffer_floats(world)
+        floats.  None / world <= 1 switches it off."""
+        if peer_ptrs is None or world <= 1:
+            self._chk(self.lib.cps_mppi_set_peers(self._h, 0, 0, None))
+            return
+        arr = (C.c_void_p * int(world))(*[int(p) for p in peer_ptrs])
+        self._chk(self.lib.cps_mppi_set_peers(self._h, int(world), int(rank), arr))
+
+    def peer_timeouts(self) -> int:
+        n = C.c_int(0)
+        self._chk(self.lib.cps_mppi_peer_timeouts(self._h, C.byref(n)))
+        return int(n.value)
 
     def mppi_finalize(self, partials, u_nom=None):
         self.use_current_stream()
@@ -528,6 +553,10 @@ class Engine:
     # -- diagnostics ----------------------------------------------------------------------------------
     def launch_count(self) -> int:
         return int(self.lib.cps_launch_count(self._h))
+
+    def rollout_last_kernel(self) -> str | None:
+        """'rollout_kernel' | 'rollout_pair_kernel': what the last open-loop rollout call launched (None: none yet)."""
+        return {0: None, 1: "rollout_kernel", 2: "rollout_pair_kernel"}[int(self.lib.cps_rollout_last_kernel(self._h))]
 
     def net_last_kernel(self) -> str | None:
         """'fp32' | 'tensor': the network kernel the last neural rollout / solve launched (None: none yet)."""

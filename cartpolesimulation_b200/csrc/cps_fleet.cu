@@ -224,6 +224,7 @@ __global__ void __launch_bounds__(256, 4) fleet_kernel(const __grid_constant__ F
     io.ticket = a.tickets + e;
     io.nonfinite = a.nonfinite;
     io.shard_out = nullptr;
+    io.px.world = 0;
     OdeParams ode = a.ode;
     if (a.L_row || a.mp_row)
         fold_ode_device<INTEG>(a, a.L_row ? (double)a.L_row[e] : (double)a.L_default,

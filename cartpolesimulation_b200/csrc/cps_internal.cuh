@@ -96,6 +96,9 @@ struct cps_handle {
     int pipe_ready;
     long long launches;
     int net_last_kernel;       // 0 none, 1 net_kernel (FP32), 2 net_tc_kernel
+    int rollout_last_kernel;   // 0 none, 1 rollout_kernel, 2 rollout_pair_kernel
+    PeerExchange px;           // cps_mppi_set_peers (world <= 1: off); px.epoch = solves exchanged so far
+    int *d_px_timeouts;
     std::string err;
     NetState *net;      // neural predictor (cps_net_load), owned
     FleetState *fleet;  // closed-loop experiments (cps_fleet_create), owned

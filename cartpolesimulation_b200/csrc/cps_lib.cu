@@ -401,7 +401,7 @@ extern "C" void cps_destroy(cps_handle *h) {
     cps_net_free(h);
     cps_fleet_free(h);
     cps_plan_free(h);
-    cudaFree(h->d_partials); cudaFree(h->d_ticket); cudaFree(h->d_nonfinite);
+    cudaFree(h->d_partials); cudaFree(h->d_ticket); cudaFree(h->d_nonfinite); cudaFree(h->d_px_timeouts);
     cudaFree(h->d_s); cudaFree(h->d_unom); cudaFree(h->d_u); cudaFree(h->d_uprev); cudaFree(h->d_ldu);
     cudaFree(h->d_rs0); cudaFree(h->d_rQ); cudaFree(h->d_rtraj); cudaFree(h->d_rfinal);
     if (h->h_pin) cudaFreeHost(h->h_pin);
@@ -578,6 +578,8 @@ extern "C" int cps_mppi_step(cps_handle *h, const float *s_dev, const float *noi
     io.u_run_out = u_run_out_dev;
     io.partials = h->d_partials; io.ticket = h->d_ticket; io.nonfinite = h->d_nonfinite;
     io.shard_out = h->shard ? h->shard_out : nullptr;
+    io.px = h->px;
+    if (h->px.world > 1) io.px.epoch = ++h->px.epoch;
     // Large K is issue-bound, not latency-bound: two rollouts per thread in packed FP32 (same arithmetic per rollout; the
     // block sums associate pairs first).  Measured (tools/ab_pairs.py): 10 % faster at K = 65536, 10-15 % SLOWER at 16384
     // and 32768, where the solve is still bound by the latency of one rollout's dependence chain.  Needs the kernel's native noise order and no per-rollout logging outputs.
@@ -669,12 +671,49 @@ extern "C" float *cps_mppi_u_nom_dev(cps_handle *h) { return h ? h->d_unom : nul
 extern "C" int cps_mppi_set_shard(cps_handle *h, int enabled, float *partial_out_dev) {
     if (!h) return CPS_ERR_INVALID;
     if (enabled && !partial_out_dev) return fail(h, CPS_ERR_INVALID, "cps_mppi_set_shard: need an output buffer");
+    if (enabled && h->px.world > 1) return fail(h, CPS_ERR_INVALID, "cps_mppi_set_shard: the handle exchanges over peer memory (cps_mppi_set_peers)");
     h->shard = enabled ? 1 : 0;
     h->shard_out = enabled ? partial_out_dev : nullptr;
     return CPS_OK;
 }
 
 extern "C" int cps_mppi_partial_size(const cps_handle *h) { return h ? h->n_red + 2 : -1; }
+
+extern "C" long long cps_mppi_peer_buffer_floats(const cps_handle *h, int world) {
+    if (!h || world < 1 || world > CPS_MAX_PEERS) return -1;
+    return 2LL * world * (h->n_red + 2) + 2LL * world;   // 2 slots x world records, then 2 x world arrival flags
+}
+
+extern "C" int cps_mppi_set_peers(cps_handle *h, int world, int rank, float *const *peer_bufs_host) {
+    if (!h) return CPS_ERR_INVALID;
+    if (world <= 1 || !peer_bufs_host) {
+        h->px.world = 0;
+        return CPS_OK;
+    }
+    if (world > CPS_MAX_PEERS || rank < 0 || rank >= world)
+        return fail(h, CPS_ERR_INVALID, "cps_mppi_set_peers: need 2 <= world <= CPS_MAX_PEERS and 0 <= rank < world");
+    if (h->shard) return fail(h, CPS_ERR_INVALID, "cps_mppi_set_peers: the handle is in shard mode (cps_mppi_set_shard)");
+    for (int r = 0; r < world; ++r)
+        if (!peer_bufs_host[r]) return fail(h, CPS_ERR_INVALID, "cps_mppi_set_peers: null peer buffer");
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    if (!h->d_px_timeouts) {
+        CUDA_TRY(h, cudaMalloc(&h->d_px_timeouts, sizeof(int)));
+        CUDA_TRY(h, cudaMemset(h->d_px_timeouts, 0, sizeof(int)));
+    }
+    for (int r = 0; r < CPS_MAX_PEERS; ++r) h->px.buf[r] = r < world ? peer_bufs_host[r] : nullptr;
+    h->px.world = world; h->px.rank = rank; h->px.epoch = 0; h->px.timeouts = h->d_px_timeouts;
+    return CPS_OK;
+}
+
+extern "C" int cps_mppi_peer_timeouts(cps_handle *h, int *count_out) {
+    if (!h || !count_out) return CPS_ERR_INVALID;
+    *count_out = 0;
+    if (!h->d_px_timeouts) return CPS_OK;
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    CUDA_TRY(h, cudaMemcpyAsync(count_out, h->d_px_timeouts, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return CPS_OK;
+}
 
 extern "C" int cps_mppi_finalize(cps_handle *h, const float *partials_dev, int n_ranks, float *u_nom_dev,
                                  float *u_out_dev) {
@@ -723,7 +762,9 @@ static int rollout_launch(cps_handle *h, const float *s0, int s0_batched, const 
         else
             fn = (h->cfg.flags & CPS_FLAG_FAST_DIV) ? rollout_pair_kernel<1, true> : rollout_pair_kernel<1, false>;
         fn<<<(unsigned)grid, block, 0, h->stream>>>(a);
+        h->rollout_last_kernel = 2;
     } else {
+        h->rollout_last_kernel = 1;
         const int block = (B <= 148 * 32 * 4) ? 32 : 128;
         long long grid = ((long long)B + block - 1) / block;
         const long long max_grid = 148LL * 16 * 8;  // grid-stride beyond 8 full waves
@@ -962,6 +1003,7 @@ extern "C" int cps_measure_peaks(cps_handle *h, double *fp32_tflops, double *muf
 // ---- diagnostics ---------------------------------------------------------------------------------------
 extern "C" long long cps_launch_count(const cps_handle *h) { return h ? h->launches : -1; }
 extern "C" int cps_net_last_kernel(const cps_handle *h) { return h ? h->net_last_kernel : -1; }
+extern "C" int cps_rollout_last_kernel(const cps_handle *h) { return h ? h->rollout_last_kernel : -1; }
 
 extern "C" int cps_nonfinite_costs(cps_handle *h, int *count_out) {
     if (!h || !count_out) return CPS_ERR_INVALID;

@@ -417,7 +417,7 @@ __global__ void __launch_bounds__(R * 8 + 32, 1) net_kernel(const __grid_constan
     __syncthreads();
     if (s_ticket != gridDim.x - 1) return;
     __threadfence();
-    merge_and_finish(mp, a.partials, gridDim.x, s_red, s_unom, a.u_nom, a.u_out, a.shard_out, false);
+    merge_and_finish(mp, a.partials, gridDim.x, s_red, s_unom, a.u_nom, a.u_out, a.shard_out, false, &a.px);
     if (tid == 0) *a.ticket = 0u;
     if (a.shard_out || !a.h_ref || N.type != CPS_NET_GRU) return;
 
@@ -710,6 +710,8 @@ int cps_net_mppi_step(cps_handle *h, const float *s_dev, const float *noise_dev,
     a.u_nom = u_nom_dev; a.u_out = u_out_dev; a.J_out = J_out_dev; a.u_run_out = u_run_out_dev;
     a.partials = h->d_partials; a.ticket = h->d_ticket; a.nonfinite = h->d_nonfinite;
     a.shard_out = h->shard ? h->shard_out : nullptr;
+    a.px = h->px;
+    if (h->px.world > 1) a.px.epoch = ++h->px.epoch;
     a.h_ref = h->net->d_href;
     return net_launch(h, a, true, (int)K);
 }

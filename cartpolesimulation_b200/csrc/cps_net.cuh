@@ -55,6 +55,7 @@ struct NetArgs {
     unsigned *ticket;
     int *nonfinite;
     float *shard_out;
+    PeerExchange px;          // K sharded over GPUs, exchange inside the launch (cps_mppi_set_peers)
     float *h_ref;             // stored hidden state to advance after the solve (null: skip)
     int tc_rows;              // net_tc_kernel: live rollouts per CTA (64: the first 16 lanes of each tensor-memory lane quarter | 128)
 };

@@ -738,7 +738,7 @@ __global__ void __launch_bounds__(TC_NT, 1) net_tc_kernel(const __grid_constant_
         last = s_ticket == gridDim.x - 1;
         if (last) {
             __threadfence();
-            merge_and_finish(mp, a.partials, gridDim.x, s_red, s_unom, a.u_nom, a.u_out, a.shard_out, false);
+            merge_and_finish(mp, a.partials, gridDim.x, s_red, s_unom, a.u_nom, a.u_out, a.shard_out, false, &a.px);
             if (tid == 0) *a.ticket = 0u;
         }
         if (last && !a.shard_out && a.h_ref) {

@@ -2,10 +2,15 @@
 
   ShardedMPPI        ONE MPPI solve with its K rollouts partitioned over the ranks.  Every rank rolls out its
                      contiguous slice of rollouts (its own slice of the noise draws; s, u_nom and the scalars are
-                     replicated) and reduces it to a partial record (min J, sum w, sum w*eps[.]) = n_ind + 2 floats
-                     (cps_mppi_set_shard).  The only exchange is one all-gather of those records
-                     (32 B per rank at n_ind = 6; NCCL over NVLink on GPUs); every rank then merges them with
-                     the online-softmax rule (cps_mppi_finalize) and holds the identical u_nom / u.
+                     replicated) and reduces it to a partial record (min J, sum w, sum w*eps[.]) = n_ind + 2 floats.
+                     The only exchange is that record (32 B per rank at n_ind = 6), merged on every rank with the
+                     online-softmax rule, so that all ranks hold the identical u_nom / u.  Two transports:
+                       exchange="peer"       inside the solve launch: the last block pushes the record into every
+                                             rank's symmetric-memory buffer over NVLink, waits for the others' and
+                                             finishes the update itself (cps_mppi_set_peers) -- one launch per solve,
+                                             no collective call;
+                       exchange="allgather"  cps_mppi_set_shard + dist.all_gather_into_tensor + cps_mppi_finalize
+                                             (three stream operations; any backend, also gloo on CPU in the tests).
   replica_slice      independent experiments / open-loop batches: plain partition, no collective at all.
 
 The reference has no counterpart: it parallelises by running one process per experiment on a SLURM array
@@ -65,7 +70,10 @@ class ShardedMPPI:
     builds a cartpolesimulation_b200.core.Engine from **engine_kwargs.
     """
 
-    def __init__(self, num_rollouts: int, horizon: int, group=None, engine_factory=None, **engine_kwargs):
+    def __init__(self, num_rollouts: int, horizon: int, group=None, engine_factory=None, exchange: str = "auto",
+                 **engine_kwargs):
+        if exchange not in ("auto", "peer", "allgather"):
+            raise ValueError("exchange must be 'auto', 'peer' or 'allgather'")
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -80,10 +88,36 @@ class ShardedMPPI:
         self.engine = engine_factory(self.K_local)
         self.device = self.engine.device
         self.rec = int(self.engine.partial_size())
-        self._partial = torch.zeros(self.rec, device=self.device, dtype=torch.float32)
-        self._gathered = torch.zeros(self.world * self.rec, device=self.device, dtype=torch.float32)
-        self.engine.set_shard(self._partial)
         self.recurrent = bool(getattr(self.engine, "net_htot", 0))
+        self.exchange = "allgather"
+        self._symm = None
+        if exchange != "allgather" and self.world > 1:
+            try:
+                self._setup_peers()
+                self.exchange = "peer"
+            except Exception:
+                if exchange == "peer":
+                    raise
+        if self.exchange == "allgather":
+            self._partial = torch.zeros(self.rec, device=self.device, dtype=torch.float32)
+            self._gathered = torch.zeros(self.world * self.rec, device=self.device, dtype=torch.float32)
+            self.engine.set_shard(self._partial)
+
+    def _setup_peers(self):
+        """Symmetric-memory exchange buffers (torch.distributed._symmetric_memory: CUDA virtual-memory handles exchanged
+        over the process group's store) mapped into every rank; their device addresses go to cps_mppi_set_peers."""
+        if not hasattr(self.engine, "set_peers") or self.device.type != "cuda":
+            raise RuntimeError("peer exchange needs the CUDA engine")
+        import torch.distributed._symmetric_memory as symm_mem
+        n = int(self.engine.peer_buffer_floats(self.world))
+        buf = symm_mem.empty(n, dtype=torch.float32, device=self.device)
+        buf.zero_()
+        group = self.group if self.group is not None else dist.group.WORLD
+        hdl = symm_mem.rendezvous(buf, group)
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)   # every rank's buffer is zeroed before anybody's first solve pushes into it
+        self.engine.set_peers(self.world, self.rank, [int(p) for p in hdl.buffer_ptrs])
+        self._symm = (buf, hdl)
 
     def noise_slice(self, noise_full: torch.Tensor, time_major: bool = True) -> torch.Tensor:
         """This rank's rollouts of a full noise tensor ([n_ind, K_total] time-major, or [K_total, n_ind])."""
@@ -93,6 +127,8 @@ class ShardedMPPI:
     def step(self, s: torch.Tensor, noise_local: torch.Tensor, noise_layout: int = 1, u_prev: float = 0.0) -> torch.Tensor:
         """s: device tensor [6] (identical on all ranks); noise_local: this rank's draws.  Returns the device tensor
         [1] holding u -- identical on every rank.  No host synchronisation."""
+        if self.exchange == "peer":   # one launch: local rollouts, record exchange over peer memory, update (+ GRU state)
+            return self.engine.mppi_step(s, noise_local, noise_layout, u_prev)
         self.engine.mppi_step(s, noise_local, noise_layout, u_prev)   # -> self._partial (stream-ordered)
         if self.world > 1:
             dist.all_gather_into_tensor(self._gathered, self._partial, group=self.group)

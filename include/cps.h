@@ -114,7 +114,8 @@ enum {
  * optimizer + predictor + cost wrapper for one (K, T, n, integrator, cost) configuration.  Physics defaults to
  * cartpole_physical_parameters.yml:6-17,33-42, cost weights to config_cost_function.yml:5-58 and MPPI parameters
  * to config_optimizers.yml:87-97 until the cps_set_* calls override them.  The handle owns all scratch
- * (block partials, ticket, staging buffers); no allocation happens in the step / rollout calls. */
+ * (block partials, ticket, staging buffers); no allocation happens in the step / rollout calls on device buffers
+ * (cps_rollout_host is the exception: its staging buffers grow on first use / on a larger batch, see below). */
 int cps_create(const cps_config *cfg, cps_handle **out);
 void cps_destroy(cps_handle *h);
 /* Text of the last error on this handle (h == NULL: last cps_create failure on the calling thread). */
@@ -172,6 +173,21 @@ float *cps_mppi_u_nom_dev(cps_handle *h);
 int cps_mppi_set_shard(cps_handle *h, int enabled, float *partial_out_dev);
 int cps_mppi_partial_size(const cps_handle *h);
 int cps_mppi_finalize(cps_handle *h, const float *partials_dev, int n_ranks, float *u_nom_dev, float *u_out_dev);
+
+/* The same sharding with the exchange INSIDE the solve launch, over peer memory (NVLink / NVSwitch): every rank owns an
+ * exchange buffer of cps_mppi_peer_buffer_floats(h, world) zero-initialised floats that all ranks have mapped (CUDA IPC /
+ * virtual-memory handles, e.g. torch.distributed._symmetric_memory); peer_bufs_host[r] is rank r's buffer as mapped on
+ * THIS device.  After cps_mppi_set_peers every cps_mppi_step (one launch) pushes the rank's partial record into all
+ * ranks' buffers, waits for theirs and finishes the update itself: u_nom / u are bit-identical on all ranks, no
+ * collective call and no second launch.  All ranks must call cps_mppi_step the same number of times.  world <= 1 (or
+ * peer_bufs_host == NULL) switches the exchange off.  Excludes cps_mppi_set_shard.  The reference has no counterpart
+ * (one process per experiment, others/EulerClusterScripts/ParallelDataGeneration.sh). */
+#define CPS_MAX_PEERS 8
+long long cps_mppi_peer_buffer_floats(const cps_handle *h, int world);
+int cps_mppi_set_peers(cps_handle *h, int world, int rank, float *const *peer_bufs_host);
+/* Waits on a peer's record that were given up after 10 s (a rank that never called cps_mppi_step); 0 in a healthy run.
+ * Synchronises. */
+int cps_mppi_peer_timeouts(cps_handle *h, int *count_out);
 
 /* ---- legacy front-end: controller_mppi_cartpole ------------------------------------------------------------ */
 /* The repository's original MPPI controller (Control_Toolkit_ASF/Controllers/controller_mppi_cartpole.py), which
@@ -387,6 +403,9 @@ long long cps_launch_count(const cps_handle *h);
  * CUDA-core kernel (net_kernel), 2 the tensor-core kernel (net_tc_kernel; the default for plain 2 x 64 GRU networks).
  * The reference has no counterpart (its predictor is one torch module, SI_Toolkit/Predictors/predictor_autoregressive_neural.py:266-313). */
 int cps_net_last_kernel(const cps_handle *h);
+/* Which kernel the last cps_rollout / cps_rollout_host chunk of this handle launched: 0 none yet, 1 rollout_kernel (one
+ * cartpole per thread), 2 rollout_pair_kernel (two per thread, packed FP32; large time-major batches). */
+int cps_rollout_last_kernel(const cps_handle *h);
 /* Cumulative count of non-finite trajectory costs seen by cps_mppi_step since cps_create (the reference propagates
  * NaN silently into exp(); this library does the same arithmetic but counts it).  Synchronises. */
 int cps_nonfinite_costs(cps_handle *h, int *count_out);

@@ -1,5 +1,6 @@
-"""K sharded over 2 GPUs (NCCL all-gather of the partial records) must give the same u_nom / u as one GPU solving
-all K rollouts.  Needs 2 GPUs (gpurun --gpus 2); skipped otherwise."""
+"""K sharded over 2 GPUs -- records exchanged inside the solve launch over peer memory (cps_mppi_set_peers), or by an NCCL
+all-gather -- must give the same u_nom / u as one GPU solving all K rollouts.  Needs 2 GPUs (gpurun --gpus 2); skipped
+otherwise."""
 import os
 import socket
 
@@ -16,14 +17,15 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, K, T, integ, q):
+def _worker(rank, world, port, K, T, integ, exchange, q):
     import torch.distributed as dist
     from cartpolesimulation_b200.distributed import ShardedMPPI
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
-        sm = ShardedMPPI(K, T, integrator=integ, cost="quadratic_boundary_grad_minimal", device=rank)
+        sm = ShardedMPPI(K, T, integrator=integ, cost="quadratic_boundary_grad_minimal", device=rank, exchange=exchange)
+        assert sm.exchange == exchange
         rng = np.random.default_rng(3)
         eps = rng.standard_normal((sm.engine.n_ind, K)).astype(np.float32)
         a = np.pi - 1e-3
@@ -33,6 +35,8 @@ def _worker(rank, world, port, K, T, integ, q):
             full = torch.from_numpy(eps * (1.0 - 0.3 * step)).to(sm.device)
             u = sm.step(s, sm.noise_slice(full), 1, u_prev=0.05 * step)
             us.append(float(u.cpu()[0]))
+        if exchange == "peer":
+            assert sm.engine.peer_timeouts() == 0
         q.put((rank, us, sm.get_u_nom()))
     except Exception as ex:  # report instead of leaving the parent to time out
         q.put((rank, "error", repr(ex)))
@@ -41,8 +45,9 @@ def _worker(rank, world, port, K, T, integ, q):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("exchange", ["peer", "allgather"])
 @pytest.mark.parametrize("integ", ["ODE", "ODE_v0"])
-def test_sharded_mppi_two_gpus_matches_one_gpu(integ):
+def test_sharded_mppi_two_gpus_matches_one_gpu(integ, exchange):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
@@ -51,7 +56,7 @@ def test_sharded_mppi_two_gpus_matches_one_gpu(integ):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, K, T, integ, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, K, T, integ, exchange, q)) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
