@@ -189,9 +189,13 @@ def mppi_latency(device, n_calls=1000):
             if i >= 10:
                 ks.append(e0.elapsed_time(e1))
         out[pred] = {"latency_ms_median": float(np.median(lat) * 1e3), "latency_ms_p99": float(np.percentile(lat, 99) * 1e3),
-                     "kernel_ms_median": float(np.median(ks)), "calls": n_calls,
+                     "kernel_ms_median": float(np.median(ks)),
+                     "kernel_ms_in_stream": float(np.median(_stream_times(lambda: eng.mppi_step(s_dev, noise, 1, 0.0)))),
+                     "calls": n_calls,
                      "state_steps_per_solve": K * T * N_SUB}
-    out["config"] = "K=2000, T=50, n=10, cost quadratic_boundary_grad_minimal, optimizer_mppi_b200.step(numpy s) -> numpy u"
+    out["config"] = ("K=2000, T=50, n=10, cost quadratic_boundary_grad_minimal, optimizer_mppi_b200.step(numpy s) -> numpy u; "
+                     "kernel_ms_median = CUDA events around one launch on an idle GPU (includes the host's launch latency), "
+                     "kernel_ms_in_stream = device time per solve in a stream of 20 back-to-back solves")
     out["neural_GRU_2x64"] = neural_latency(device, n_calls=min(n_calls, 300))
     out["neural_GRU_2x64_K65536"] = neural_big(device)
     out["ODE_K65536_T100"] = big_solve(device)
@@ -352,6 +356,25 @@ def legacy_latency(device, n_calls=300):
     return out
 
 
+def _stream_times(fn, n_batches=5, per_batch=20, warm=5):
+    """Device time per call inside a stream of back-to-back calls (per_batch calls per CUDA-event pair): what a kernel
+    costs without the host's launch latency, which an event pair around ONE launch on an idle GPU includes."""
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(n_batches):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(per_batch):
+            fn()
+        e1.record()
+        e1.synchronize()
+        ts.append(e0.elapsed_time(e1) / per_batch)
+    return ts
+
+
 def _event_times(fn, n, warm=5):
     import torch
     for _ in range(warm):
@@ -445,7 +468,8 @@ def big_solve(device):
         noise = torch.randn((eng.n_ind, K), device=eng.device)
         ks = _event_times(lambda: eng.mppi_step(s, noise, 1, 0.0), 30)
         kms = float(np.median(ks))
-        out[cost] = {"kernel_ms_median": kms, "state_steps_per_s": K * T * N_SUB / (kms * 1e-3)}
+        out[cost] = {"kernel_ms_median": kms, "state_steps_per_s": K * T * N_SUB / (kms * 1e-3),
+                     "kernel_ms_in_stream": float(np.median(_stream_times(lambda: eng.mppi_step(s, noise, 1, 0.0))))}
         eng.close()
     return out
 

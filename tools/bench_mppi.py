@@ -36,8 +36,20 @@ def main():
         e1.synchronize()
         ts.append(e0.elapsed_time(e1))
     ms = float(np.median(ts))
-    print(f"MPPI solve K={args.K} T={args.T} {args.integrator} {args.cost}: kernel {ms * 1e3:.1f} us median, "
-          f"{args.K * args.T * 10 / ms * 1e3:.3e} state-steps/s")
+    # the same solve inside a stream of back-to-back solves (20 per event pair): the device time per solve without the
+    # host's launch latency, which an event pair around a single launch on an idle GPU includes
+    tb = []
+    for _ in range(max(3, args.iters // 10)):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            eng.mppi_step(s, noise, 1, 0.0)
+        e1.record()
+        e1.synchronize()
+        tb.append(e0.elapsed_time(e1) / 20)
+    mb = float(np.median(tb))
+    print(f"MPPI solve K={args.K} T={args.T} {args.integrator} {args.cost}: single launch {ms * 1e3:.1f} us median (events around one "
+          f"launch on an idle GPU), {mb * 1e3:.1f} us per solve in a stream of 20, {args.K * args.T * 10 / mb * 1e3:.3e} state-steps/s")
 
 
 if __name__ == "__main__":
