@@ -23,6 +23,12 @@ struct MppiArgs {
     int use_inline;
 };
 
+typedef void (*mppi_fn)(const MppiArgs);
+static inline int sc_mode(unsigned flags) {
+    if (flags & CPS_FLAG_SUBSTEP_SINCOS) return (flags & CPS_FLAG_FAST_SINCOS) ? SC_MUFU : SC_ACCURATE;
+    return SC_ROTATE;
+}
+
 struct RolloutArgs {
     OdeParams ode;
     const float *s0;

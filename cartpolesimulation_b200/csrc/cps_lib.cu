@@ -1,7 +1,7 @@
 // cps_lib.cu -- kernels and C ABI of libcps_b200.so (see include/cps.h).
 //
 // Kernels
-//   mppi_kernel      K1+K2: one MPPI solve in one launch (optimizer_mppi.py:180-192).  One thread = one rollout,
+//   mppi_kernel      (cps_mppi_inst.cuh, one translation unit per cost plugin) K1+K2: one MPPI solve in one launch (optimizer_mppi.py:180-192).  One thread = one rollout,
 //                    state in registers, stage/terminal/correction cost accumulated in the same pass, block
 //                    partials (min J, sum w, sum w*noise[i]) merged by the last block to finish (ticket) with the
 //                    online-softmax rule, which then writes the clipped u_nom and u.
@@ -22,23 +22,6 @@
 // =====================================================================================================
 // K1 + K2: the MPPI solve
 // =====================================================================================================
-template <int INTEG, int COST, int SC, int NOISE, bool FAST_DIV, bool EXACT_ATAN2>
-__global__ void __launch_bounds__(256, 4) mppi_kernel(const __grid_constant__ MppiArgs a) {
-    extern __shared__ float smem[];
-    SolveIO io = a.io;
-    if (a.use_inline) io.s = a.s_inline;   // constant-bank reads instead of a global load of the state
-    mppi_solve_block<INTEG, COST, SC, NOISE, FAST_DIV, EXACT_ATAN2>(a.ode, a.cost, a.mp, io, smem, blockIdx.x, gridDim.x);
-}
-
-// The throughput form: two rollouts per thread in packed FP32 (mppi_solve_block2); chosen by cps_mppi_step for large K.
-template <int INTEG, int COST>
-__global__ void __launch_bounds__(128, 4) mppi_pair_kernel(const __grid_constant__ MppiArgs a) {
-    extern __shared__ float smem[];
-    SolveIO io = a.io;
-    if (a.use_inline) io.s = a.s_inline;
-    mppi_solve_block2<INTEG, COST>(a.ode, a.cost, a.mp, io, smem, blockIdx.x, gridDim.x);
-}
-
 // Merge of gathered per-rank partials (K sharded over GPUs).
 __global__ void __launch_bounds__(128) finalize_kernel(const __grid_constant__ FinalizeArgs a, int direct_noise) {
     extern __shared__ float smem[];
@@ -86,6 +69,8 @@ __device__ __forceinline__ void store_state2(float *base, long long ts_c, const 
     *reinterpret_cast<unsigned long long *>(base + 5 * ts_c) = z.v.v;
 }
 
+// Occupancy A/B (1M x 500, B200): 56 registers / 9 blocks per SM (this) 812 us; 48 registers / 10 blocks 805 us; 64 / 8
+// 823 us; 40 / 12 (spills) 827 us; 80 / 6 878 us -- the kernel sits on a plateau, occupancy is not its limiter.
 template <int INTEG, bool FAST_DIV>
 __global__ void __launch_bounds__(128) rollout_pair_kernel(const __grid_constant__ RolloutArgs a) {
     const OdeParams ode = pin_params(a.ode, a.s0[0]);
@@ -462,60 +447,30 @@ extern "C" int cps_set_variable_parameters(cps_handle *h, float tp, float te, fl
 }
 
 // ---- kernel dispatch --------------------------------------------------------------------------------
-typedef void (*mppi_fn)(const MppiArgs);
 typedef void (*rollout_fn)(const RolloutArgs);
 typedef void (*cost_fn)(const CostArgs);
 
-template <int INTEG, int COST, int SC, int NOISE>
-static mppi_fn pick_mppi3(unsigned flags) {
-    const bool fd = flags & CPS_FLAG_FAST_DIV, ea = flags & CPS_FLAG_EXACT_ATAN2;
-    if (fd) return ea ? mppi_kernel<INTEG, COST, SC, NOISE, true, true> : mppi_kernel<INTEG, COST, SC, NOISE, true, false>;
-    return ea ? mppi_kernel<INTEG, COST, SC, NOISE, false, true> : mppi_kernel<INTEG, COST, SC, NOISE, false, false>;
-}
-static int sc_mode(unsigned flags) {
-    if (flags & CPS_FLAG_SUBSTEP_SINCOS) return (flags & CPS_FLAG_FAST_SINCOS) ? SC_MUFU : SC_ACCURATE;
-    return SC_ROTATE;
-}
-template <int INTEG, int COST, int NOISE>
-static mppi_fn pick_mppi2b(unsigned flags) {
-    switch (sc_mode(flags)) {
-    case SC_ACCURATE: return pick_mppi3<INTEG, COST, SC_ACCURATE, NOISE>(flags);
-    case SC_MUFU: return pick_mppi3<INTEG, COST, SC_MUFU, NOISE>(flags);
-    default: return (flags & CPS_FLAG_FAST_DIV) ? mppi_kernel<INTEG, COST, SC_ROTATE, NOISE, true, false>
-                                                : mppi_kernel<INTEG, COST, SC_ROTATE, NOISE, false, false>;
-    }
-}
-template <int INTEG, int COST>
-static mppi_fn pick_mppi2(int noise, unsigned flags) {
-    if (noise == CPS_NOISE_INDUCING) return pick_mppi2b<INTEG, COST, CPS_NOISE_INDUCING>(flags);
-    return pick_mppi2b<INTEG, COST, CPS_NOISE_DIRECT>(flags);
-}
-template <int INTEG>
-static mppi_fn pick_mppi1(int cost, int noise, unsigned flags) {
-    switch (cost) {
-    case CPS_COST_DEFAULT: return pick_mppi2<INTEG, COST_DEFAULT>(noise, flags);
-    case CPS_COST_QUADRATIC_BOUNDARY: return pick_mppi2<INTEG, COST_QB>(noise, flags);
-    case CPS_COST_QB_GRAD_MINIMAL: return pick_mppi2<INTEG, COST_GRADMIN>(noise, flags);
-    case CPS_COST_QB_GRAD: return pick_mppi2<INTEG, COST_GRAD>(noise, flags);
-    default: return pick_mppi2<INTEG, COST_NONE>(noise, flags);
-    }
-}
-template <int INTEG>
-static mppi_fn pick_mppi_pair1(int cost) {
-    switch (cost) {
-    case CPS_COST_DEFAULT: return mppi_pair_kernel<INTEG, COST_DEFAULT>;
-    case CPS_COST_QUADRATIC_BOUNDARY: return mppi_pair_kernel<INTEG, COST_QB>;
-    case CPS_COST_QB_GRAD_MINIMAL: return mppi_pair_kernel<INTEG, COST_GRADMIN>;
-    case CPS_COST_QB_GRAD: return mppi_pair_kernel<INTEG, COST_GRAD>;
-    default: return mppi_pair_kernel<INTEG, COST_NONE>;
-    }
-}
+// The MPPI solve kernels are instantiated in one translation unit per cost plugin (cps_mppi_*.cu, cps_mppi_inst.cuh).
+#define CPS_DECL_MPPI(name) mppi_fn cps_pick_mppi_##name(int integ, int noise, unsigned flags); mppi_fn cps_pick_mppi_pair_##name(int integ);
+CPS_DECL_MPPI(default) CPS_DECL_MPPI(qb) CPS_DECL_MPPI(gradmin) CPS_DECL_MPPI(grad) CPS_DECL_MPPI(none)
+#undef CPS_DECL_MPPI
 static mppi_fn pick_mppi_pair(const cps_config &c) {
-    return c.integrator == CPS_EULER_V0 ? pick_mppi_pair1<0>(c.cost_id) : pick_mppi_pair1<1>(c.cost_id);
+    switch (c.cost_id) {
+    case CPS_COST_DEFAULT: return cps_pick_mppi_pair_default(c.integrator);
+    case CPS_COST_QUADRATIC_BOUNDARY: return cps_pick_mppi_pair_qb(c.integrator);
+    case CPS_COST_QB_GRAD_MINIMAL: return cps_pick_mppi_pair_gradmin(c.integrator);
+    case CPS_COST_QB_GRAD: return cps_pick_mppi_pair_grad(c.integrator);
+    default: return cps_pick_mppi_pair_none(c.integrator);
+    }
 }
 static mppi_fn pick_mppi(const cps_config &c) {
-    return c.integrator == CPS_EULER_V0 ? pick_mppi1<0>(c.cost_id, c.noise_mode, c.flags)
-                                        : pick_mppi1<1>(c.cost_id, c.noise_mode, c.flags);
+    switch (c.cost_id) {
+    case CPS_COST_DEFAULT: return cps_pick_mppi_default(c.integrator, c.noise_mode, c.flags);
+    case CPS_COST_QUADRATIC_BOUNDARY: return cps_pick_mppi_qb(c.integrator, c.noise_mode, c.flags);
+    case CPS_COST_QB_GRAD_MINIMAL: return cps_pick_mppi_gradmin(c.integrator, c.noise_mode, c.flags);
+    case CPS_COST_QB_GRAD: return cps_pick_mppi_grad(c.integrator, c.noise_mode, c.flags);
+    default: return cps_pick_mppi_none(c.integrator, c.noise_mode, c.flags);
+    }
 }
 
 template <int INTEG, int SC>
