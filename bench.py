@@ -415,7 +415,8 @@ def neural_latency(device, n_calls=300):
     kms = float(np.median(ks))
     out = {"latency_ms_median": float(np.median(lat) * 1e3), "latency_ms_p99": float(np.percentile(lat, 99) * 1e3),
            "kernel_ms_median": kms, "net_steps_per_s": K * T / (kms * 1e-3), "fp32_tflops": flops / (kms * 1e-3) / 1e12,
-           "flop_per_solve": flops, "api": "cps_mppi_step_host (numpy s -> float u), net_kernel<16,64,MPPI>"}
+           "flop_per_solve": flops,
+           "api": "cps_mppi_step_host (numpy s -> float u); kernel: %s" % {"tensor": "net_tc_kernel<MPPI> (tcgen05)", "fp32": "net_kernel<16,64,MPPI> (FP32)"}.get(eng.net_last_kernel(), "?")}
     try:  # the same solve by the CPU oracle port (C, OpenMP), once, on the host cores
         from oracle import oracle as O
         eps = noise.t().contiguous().cpu().numpy()
@@ -683,6 +684,7 @@ def run_ours(args):
     t_all1.record()
     barrier()
     launches = (args.steps if graph is not None else eng.launch_count() - launches0)
+    kernel_label = eng.rollout_last_kernel() or "rollout_kernel"   # what the timed passes dispatched to
     total_ms = t_all0.elapsed_time(t_all1)
     per_rank = None
     if world > 1:
@@ -700,26 +702,66 @@ def run_ours(args):
     s0_pin = torch.from_numpy(s0_np).pin_memory()
     Q_pin = torch.from_numpy(Q_np).pin_memory()
     traj_pin = torch.empty((T + 1, 6, B), pin_memory=True)
+    final_pin = torch.empty((B, 6), pin_memory=True)
     e2e_steps = max(2, min(args.steps, 5))
-    for _ in range(2):
-        eng.rollout_host(s0_pin.numpy(), Q_pin.numpy(), L.TIME_MAJOR, L.TIME_MAJOR, traj_out=traj_pin.numpy())
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        eng.rollout_host(s0_pin.numpy(), Q_pin.numpy(), L.TIME_MAJOR, L.TIME_MAJOR, traj_out=traj_pin.numpy())
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
+
+    def timed_host(fn, n):
+        for _ in range(2):
+            fn()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            fn()
+        torch.cuda.synchronize()
+        dt_s = time.perf_counter() - t0
+        if world > 1:   # the slowest rank decides
+            t = torch.tensor([dt_s], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt_s = float(t.item())
+        return dt_s
+
+    # (1) the full trajectory comes back (what predictor.predict_core returns): PCIe-bound, 1.28 GB D2H per pass
+    e2e_s = timed_host(lambda: eng.rollout_host(s0_pin.numpy(), Q_pin.numpy(), L.TIME_MAJOR, L.TIME_MAJOR,
+                                                traj_out=traj_pin.numpy()), e2e_steps)
+    # (2) only the final states come back (what a cost-only / MPPI caller needs from the rollouts): 25 MB D2H per pass
+    e2e_final_s = timed_host(lambda: eng.rollout_host(s0_pin.numpy(), Q_pin.numpy(), L.TIME_MAJOR, L.TIME_MAJOR,
+                                                      traj_out=None, final_out=final_pin.numpy()), e2e_steps)
+    # (3) the bus itself: pinned device-to-host and host-to-device copies of the same buffers, all ranks at once -- the
+    #     ceiling the full-trajectory leg runs against (N ranks share one host memory system and the PCIe root complexes)
+    def copy_rate(dst, src, n=3):
+        dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize()
+        dt_s = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt_s], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt_s = float(t.item())
+        return src.numel() * 4 * n / dt_s / 1e9   # GB/s per rank, slowest rank
+    d2h_gbs = copy_rate(traj_pin, traj)
+    h2d_gbs = copy_rate(Q, Q_pin)
     if numa_cpus:
         os.sched_setaffinity(0, all_cpus)   # the CPU baseline below uses every host core again
     sampler.stop_flag = True   # the clock record covers both timed regions (device-resident and e2e)
     sampler.join(timeout=1.0)
     e2e_value = steps_per_pass * e2e_steps * world / e2e_s
+    e2e_final_value = steps_per_pass * e2e_steps * world / e2e_final_s
     h2d = s0_pin.numel() * 4 + Q_pin.numel() * 4
     d2h = traj_pin.numel() * 4
+    # time the two copies alone would take on this rank at the measured concurrent rates (they do not overlap each other
+    # much: the D2H of a chunk follows its kernel, the H2D of the next chunk runs beside it)
+    bus_floor_s = d2h / (d2h_gbs * 1e9)
+    e2e_bus = {"achieved_gbs_per_rank": (h2d + d2h) / (e2e_s / e2e_steps) / 1e9,
+               "d2h_gbs_per_rank_all_ranks_copying": d2h_gbs, "h2d_gbs_per_rank_all_ranks_copying": h2d_gbs,
+               "d2h_gbs_all_ranks": d2h_gbs * world,
+               "frac_of_d2h_copy_rate": (d2h / (e2e_s / e2e_steps) / 1e9) / d2h_gbs,
+               "d2h_floor_ms_per_step": 1e3 * bus_floor_s,
+               "note": "full-trajectory leg = 1.28 GB device-to-host per pass: bounded by the pinned D2H copy rate measured here "
+                       "with every rank copying at once, not by the 0.8 ms kernel"}
 
     sharded = None
     fleet = None
@@ -760,7 +802,7 @@ def run_ours(args):
         ncu_view = rt.get("ncu")   # pipe utilisation of the same kernel from the committed ncu capture (not measured live)
     except Exception:
         pass
-    roofline = {"bound": "fp32", "kernel": "%s<ODE_v0>" % (eng.rollout_last_kernel() or "rollout_kernel"), "achieved": achieved_tflops, "peak": fp32_peak,
+    roofline = {"bound": "fp32", "kernel": "%s<ODE_v0>" % kernel_label, "achieved": achieved_tflops, "peak": fp32_peak,
                 "unit": "TFLOP/s", "frac": achieved_tflops / fp32_peak if fp32_peak else None, "traffic": traffic,
                 "traffic_source": "committed ncu capture (profiles/roofline_traffic.json), not measured in this run",
                 "peak_source": "cps_measure_peaks FFMA microbenchmark, this run (not in MEASURED_PEAKS.json)",
@@ -804,8 +846,12 @@ def run_ours(args):
                        "timed_region": ("one CUDA graph replay of the %d passes" % args.steps) if graph is not None
                        else ("%d separate launches" % args.steps)},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": 1e3 * e2e_s / e2e_steps, "api": "cps_rollout_host (pinned host buffers)",
-                    "numa_bound_cpus": len(numa_cpus) if numa_cpus else None},
+                    "ms_per_step": 1e3 * e2e_s / e2e_steps, "api": "cps_rollout_host (pinned host buffers), full trajectory returned",
+                    "numa_bound_cpus": len(numa_cpus) if numa_cpus else None, "pcie": e2e_bus,
+                    "final_states_only": {"value": e2e_final_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                                          "d2h_bytes_per_step": int(final_pin.numel() * 4),
+                                          "ms_per_step": 1e3 * e2e_final_s / e2e_steps,
+                                          "api": "cps_rollout_host(traj_out=NULL, final_out): what a cost-only caller moves"}},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
             "clocks": sampler.summary(), "per_rank": per_rank, "mppi_solve": mppi, "mppi_sharded": sharded, "fleet_sharded": fleet}
     print(json.dumps(line))

@@ -31,6 +31,12 @@
 
 // acc[q][.] += sum_i Wt[i][q*H + j] * x[i][g*8 .. g*8+8), rows held as 4 packed pairs.
 // Wt points at column j already; ws = row stride of Wt (NG*H); x points at the thread's row group.
+// Block-wide barrier for the warp-specialised part of net_kernel, where the row warp and the compute warps reach their
+// matching barriers at DIFFERENT code locations: PTX's unaligned form (barrier.sync), which -- unlike __syncthreads()'s
+// barrier.sync.aligned -- does not require all threads of the block to execute the same instruction (compute-sanitizer
+// --tool synccheck flags the aligned form there; profiles/r02_sanitizer.txt).
+__device__ __forceinline__ void cta_sync() { asm volatile("barrier.sync 0;" ::: "memory"); }
+
 template <int R, int NG, int HT>
 __device__ __forceinline__ void matvec_acc2(const float *__restrict__ w, const float *__restrict__ xv, int in_len, int H,
                                             u64 (&acc)[NG][4]) {
@@ -131,7 +137,7 @@ __device__ __forceinline__ void compute_step(const NetDev &N, const float *W, fl
     const bool has0 = tid < (R / NET_RT) * H0;
     u64 acc[3][4];
     if (split && has0) gru_hh<R, HT>(N, W, 0, hb + p * hstride, j0, g0, acc);
-    __syncthreads();  // the row warp has written this step's network input
+    cta_sync();  // the row warp has written this step's network input
     const float *in = xin;
     int in_len = N.n_in;
     for (int l = 0; l < N.n_layers; ++l) {
@@ -154,7 +160,7 @@ __device__ __forceinline__ void compute_step(const NetDev &N, const float *W, fl
             in = hl;
         }
         in_len = H;
-        __syncthreads();
+        cta_sync();
     }
 }
 
@@ -336,7 +342,7 @@ __global__ void __launch_bounds__(R * 8 + 32, 1) net_kernel(const __grid_constan
             }
             u_cur = u_nxt; du_cur = du_nxt;
             if (row_lead) xin[r_row] = fmaf(N.norm_a[0], u_cur, N.norm_b[0]);
-            __syncthreads();
+            cta_sync();
             // (2) behind the compute warps: state s_t -> trajectory row, stage cost, next control
             if (t > 0) compose_state(N, y, st);
             if (traj) {
@@ -353,7 +359,7 @@ __global__ void __launch_bounds__(R * 8 + 32, 1) net_kernel(const __grid_constan
                 up = u_cur;
             }
             if (t + 1 < T) next_control(t + 1);
-            for (int l = 0; l < N.n_layers; ++l) __syncthreads();
+            for (int l = 0; l < N.n_layers; ++l) cta_sync();
         } else {
             compute_step<R, HT>(N, wsm, hb, hstride, p, xin, tid);
         }
@@ -432,7 +438,7 @@ __global__ void __launch_bounds__(R * 8 + 32, 1) net_kernel(const __grid_constan
     }
     __syncthreads();
     if (row_warp) {
-        for (int l = 0; l <= N.n_layers; ++l) __syncthreads();
+        for (int l = 0; l <= N.n_layers; ++l) cta_sync();
     } else {
         compute_step<R, HT>(N, wsm, hb, hstride, 0, xin, tid);
     }
