@@ -264,3 +264,62 @@ def test_optimizer_neural_closed_loop_matches_reference(run, tmp_path):
             assert vec_err(opt.logging_values["J_logged"], z["J"][i]) < 2e-5
             if i == 0:
                 assert max(traj_err(opt.logging_values["rollout_trajectories_logged"][:32], z["traj0"]).values()) < 1e-5
+
+
+def test_optimizer_with_reference_shaped_wrappers():
+    """The optimizer fed with objects shaped like the REFERENCE's wrappers (not this package's mirrors), real Engine on the
+    GPU: the cost plugin is an instance of a class called `quadratic_boundary` whose weights are module-level constants
+    (Control_Toolkit_ASF/Cost_Functions/CartPole/quadratic_boundary.py:10-21), the predictor wrapper carries
+    predictor_type and predictor_config['intermediate_steps'] (SI_Toolkit/Predictors/predictor_wrapper.py), and
+    variable_parameters holds 0-d tensors (Control_Toolkit/others/environment.py / General/variable_parameters.py).
+    Checked against the oracle with the same (non-default) weights, substeps, pole length and mass."""
+    import sys
+    import types
+    import torch
+    from cartpolesimulation_b200.optimizer_mppi_b200 import optimizer_mppi_b200
+    from oracle import oracle as O
+    from tests.parity import shifted_cost_ok
+
+    weights = dict(dd_weight=450.0, ep_weight=15000.0, cc_weight=1.5, ccrc_weight=0.5, R=1.0)
+    mod = types.ModuleType("Control_Toolkit_ASF.Cost_Functions.CartPole.quadratic_boundary")
+    for k, v in weights.items():
+        setattr(mod, k, v)
+
+    class quadratic_boundary:     # no .config dict: the weights live in the module, as in the reference
+        pass
+    quadratic_boundary.__module__ = mod.__name__
+    mod.quadratic_boundary = quadratic_boundary
+    sys.modules[mod.__name__] = mod
+    try:
+        vp = types.SimpleNamespace(target_position=torch.tensor(0.05), target_equilibrium=torch.tensor(1.0),
+                                   L=torch.tensor(0.3), m_pole=torch.tensor(0.1))
+        cost_wrapper = types.SimpleNamespace(cost_function=quadratic_boundary(), variable_parameters=vp)
+        cost_wrapper.cost_function.variable_parameters = vp
+        predictor_wrapper = types.SimpleNamespace(predictor_type="ODE", predictor_config={"intermediate_steps": 5},
+                                                  predictor=types.SimpleNamespace())
+        K, T = 1024, 30
+        opt = optimizer_mppi_b200(predictor=predictor_wrapper, cost_function=cost_wrapper, control_limits=([-1.0], [1.0]),
+                                  seed=3, mpc_horizon=T, num_rollouts=K, optimizer_logging=True)
+        opt.configure(num_states=6, num_control_inputs=1, dt=0.02, predictor_specification="ODE")
+        assert opt.cost_name == "quadratic_boundary" and opt.predictor_type == "ODE"
+        rng = np.random.default_rng(11)
+        eps = rng.standard_normal((K, opt.engine.n_ind)).astype(np.float32)
+
+        class Injected:   # the reference's call shape: rng.normal([K, n_ind, 1], dtype)
+            def normal(self, shape, dtype=None):
+                assert list(shape) == [K, opt.engine.n_ind, 1]
+                return torch.from_numpy(eps).reshape(shape)
+        opt.rng = Injected()
+        s = np.array([2.8, -0.4, np.cos(2.8), np.sin(2.8), 0.03, 0.1], dtype=np.float32)
+        u = opt.step(s)
+        ref = O.mppi_step("ODE", "quadratic_boundary", s, np.zeros(T, np.float32), eps=eps, u_prev=0.0, target_position=0.05,
+                          target_equilibrium=1.0, n=5, phys=O.physics_vector(L=0.3, m_pole=0.1), cost_cfg=weights)
+        assert shifted_cost_ok(opt.logging_values["J_logged"], ref["J"])
+        assert abs(float(u) - float(ref["u"])) < 1e-5
+        np.testing.assert_allclose(opt.u_nom.numpy().reshape(-1), ref["u_nom"], rtol=0, atol=1e-5)
+        # the same call with default weights must differ: the module constants really reached the kernel
+        ref_default = O.mppi_step("ODE", "quadratic_boundary", s, np.zeros(T, np.float32), eps=eps, u_prev=0.0,
+                                  target_position=0.05, n=5, phys=O.physics_vector(L=0.3, m_pole=0.1))
+        assert np.abs(ref_default["u_nom"] - ref["u_nom"]).max() > 1e-4
+    finally:
+        sys.modules.pop(mod.__name__, None)
