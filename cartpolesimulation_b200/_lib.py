@@ -114,6 +114,12 @@ SYMBOLS = {
     "cps_cem_step_host": (C.c_int, [_VP, _FP, _VP, C.c_int, C.c_int, C.c_float, _FP]),
     "cps_cem_get_distribution": (C.c_int, [_VP, _FP, _FP]),
     "cps_cem_set_distribution": (C.c_int, [_VP, _FP, _FP]),
+    "cps_cem_gmm_configure": (C.c_int, [_VP, C.c_int, C.c_float, C.c_float]),
+    "cps_cem_gmm_reset": (C.c_int, [_VP]),
+    "cps_cem_gmm_step": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.c_int, C.c_float, _VP, _VP, _VP]),
+    "cps_cem_gmm_step_host": (C.c_int, [_VP, _FP, _VP, _VP, C.c_int, C.c_int, C.c_float, _FP]),
+    "cps_cem_gmm_get_distribution": (C.c_int, [_VP, _FP, _FP, _FP]),
+    "cps_cem_gmm_set_distribution": (C.c_int, [_VP, _FP, _FP, _FP]),
     "cps_measure_peaks": (C.c_int, [_VP, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "cps_launch_count": (C.c_longlong, [_VP]),
     "cps_net_last_kernel": (C.c_int, [_VP]),

@@ -543,6 +543,65 @@ class Engine:
         s_, sp = arr(stdev)
         self._chk(self.lib.cps_cem_set_distribution(self._h, mp_, sp))
 
+    # -- CEM with a Gaussian-mixture sampling distribution (optimizer_cem_gmm_tf) -----------------------------
+    def cem_gmm_configure(self, best_k, initial_stdev, stdev_min):
+        self.use_current_stream()
+        self._chk(self.lib.cps_cem_gmm_configure(self._h, int(best_k), float(initial_stdev), float(stdev_min)))
+
+    def cem_gmm_reset(self):
+        self.use_current_stream()
+        self._chk(self.lib.cps_cem_gmm_reset(self._h))
+
+    def _gmm_draws(self, eps, u01, layout):
+        _check_dev(eps, "eps", self.device)
+        _check_dev(u01, "u01", self.device)
+        n_it = int(u01.shape[0])
+        want_e = (n_it, 2, self.T, self.K) if layout == L.TIME_MAJOR else (n_it, self.K, self.T, 2)
+        want_u = (n_it, self.T, self.K) if layout == L.TIME_MAJOR else (n_it, self.K, self.T)
+        if tuple(eps.shape) != want_e or tuple(u01.shape) != want_u:
+            raise ValueError(f"draws have shapes {tuple(eps.shape)} / {tuple(u01.shape)}, expected {want_e} / {want_u}")
+        return n_it
+
+    def cem_gmm_step(self, s, eps, u01, layout=L.ROLLOUT_MAJOR, u_prev=0.0, Q_out=None, J_out=None):
+        """cps_cem_gmm_step: u01.shape[0] outer iterations; returns the cuda tensor [1] holding u (no synchronisation)."""
+        self.use_current_stream()
+        _check_dev(s, "s", self.device)
+        n_it = self._gmm_draws(eps, u01, layout)
+        self._chk(self.lib.cps_cem_gmm_step(self._h, _ptr(s), _ptr(eps), _ptr(u01), layout, n_it, float(u_prev),
+                                            _ptr(self._u_dev), _ptr(Q_out), _ptr(J_out)))
+        return self._u_dev
+
+    def cem_gmm_step_host(self, s_np, eps, u01, layout=L.ROLLOUT_MAJOR, u_prev=0.0) -> float:
+        self.use_current_stream()
+        n_it = self._gmm_draws(eps, u01, layout)
+        for i in range(6):
+            self._s_host[i] = s_np[i]
+        self._chk(self.lib.cps_cem_gmm_step_host(self._h, self._s_host, _ptr(eps), _ptr(u01), layout, n_it, float(u_prev),
+                                                 self._u_host))
+        return self._u_host[0]
+
+    def cem_gmm_get_distribution(self):
+        """(loc [2, T], scale [2, T], p1): component-major copies of the device-resident mixture."""
+        self.use_current_stream()
+        loc, sc = np.zeros((2, self.T), dtype=np.float32), np.zeros((2, self.T), dtype=np.float32)
+        p1 = np.zeros(1, dtype=np.float32)
+        self._chk(self.lib.cps_cem_gmm_get_distribution(self._h, loc.ctypes.data_as(L._FP), sc.ctypes.data_as(L._FP),
+                                                        p1.ctypes.data_as(L._FP)))
+        return loc, sc, float(p1[0])
+
+    def cem_gmm_set_distribution(self, loc=None, scale=None, p1=None):
+        self.use_current_stream()
+        keep = []
+        def arr(v, n):
+            if v is None:
+                return None
+            a = np.ascontiguousarray(np.asarray(v, dtype=np.float32).reshape(-1))
+            if a.shape[0] != n:
+                raise ValueError(f"expected {n} values")
+            keep.append(a)
+            return a.ctypes.data_as(L._FP)
+        self._chk(self.lib.cps_cem_gmm_set_distribution(self._h, arr(loc, 2 * self.T), arr(scale, 2 * self.T), arr(p1, 1)))
+
     def measure_peaks(self):
         """(FP32 TFLOP/s, MUFU Gop/s) measured on this device by two microbenchmark kernels."""
         self.use_current_stream()

@@ -66,6 +66,7 @@ struct FinalizeArgs {
 struct NetState;    // cps_net.cu
 struct FleetState;  // cps_fleet.cu
 struct PlanState;   // cps_plan.cu
+struct GmmState;    // cps_gmm.cu
 
 struct cps_handle {
     cps_config cfg;
@@ -109,6 +110,7 @@ struct cps_handle {
     NetState *net;      // neural predictor (cps_net_load), owned
     FleetState *fleet;  // closed-loop experiments (cps_fleet_create), owned
     PlanState *plan;    // forward-only planners (cps_plan_*, cps_cem_*), owned
+    GmmState *gmm;      // CEM with a Gaussian-mixture sampling distribution (cps_cem_gmm_*), owned
 };
 
 extern thread_local std::string g_create_err;
@@ -130,6 +132,8 @@ static inline size_t mppi_smem_floats(MppiParams &mp, int cost_id, int block, in
 void cps_fleet_free(cps_handle *h);
 // cps_plan.cu
 void cps_plan_free(cps_handle *h);
+// cps_gmm.cu
+void cps_gmm_free(cps_handle *h);
 // cps_lib.cu: cost parameters folded for a given target equilibrium
 int cps_fold_cost_for(cps_handle *h, float target_equilibrium, CostParams *out);
 // cps_net.cu

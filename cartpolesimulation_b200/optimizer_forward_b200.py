@@ -1,5 +1,5 @@
-"""optimizer_random_action_b200 and optimizer_cem_b200 -- the reference's forward-only optimizers on the GPU
-(SURVEY.md 8f row f3).
+"""optimizer_random_action_b200, optimizer_cem_b200 and optimizer_cem_gmm_b200 -- the reference's forward-only optimizers
+on the GPU.
 
 Mirrors of Control_Toolkit/Optimizers/optimizer_random_action_tf.py:12-86 and optimizer_cem_tf.py:12-117: the same
 constructor keywords, `configure`, `step(s, time) -> np scalar`, `optimizer_reset`, and the attributes other code
@@ -248,3 +248,77 @@ class optimizer_cem_b200(_forward_optimizer):
         self.engine.cem_reset()
         self.count = 0
         self.u = 0.0
+
+
+class optimizer_cem_gmm_b200(_forward_optimizer):
+    """optimizer_cem_gmm_tf (Control_Toolkit/Optimizers/optimizer_cem_gmm_tf.py:14-140): CEM whose sampling distribution is
+    a two-component Gaussian mixture per horizon step; the elites are clustered around the two cheapest plans.  Same
+    constructor keywords; the mixture lives on the device (`engine.cem_gmm_get_distribution()`); `sampling_dist` exposes
+    it in the reference's shapes (loc / scale [T, 1, 2], probs [2]).  cps_cem_gmm_step: three launches per outer iteration,
+    no host round trip inside a solve.
+
+    Draws: every (iteration, rollout, step) consumes two standard normals (one per component, as
+    MixtureSameFamily.sample does) and one uniform that picks the component (index 0 iff u < probs[0]).  A caller-supplied
+    generator is asked for `normal([K, T, 1, 2])` and `uniform([K, T, 1])` once per outer iteration."""
+
+    def __init__(self, predictor, cost_function, control_limits, computation_library=None, seed=None,
+                 mpc_horizon: int = 35, cem_outer_it: int = 3, cem_initial_action_stdev: float = 0.5,
+                 num_rollouts: int = 200, cem_stdev_min: float = 0.01, cem_best_k: int = 40,
+                 optimizer_logging: bool = False, calculate_optimal_trajectory: bool = False, device=None, **kwargs):
+        super().__init__(predictor=predictor, cost_function=cost_function, control_limits=control_limits,
+                         computation_library=computation_library, seed=seed, mpc_horizon=mpc_horizon,
+                         num_rollouts=num_rollouts, optimizer_logging=optimizer_logging,
+                         calculate_optimal_trajectory=calculate_optimal_trajectory, device=device)
+        self.cem_outer_it = int(cem_outer_it)
+        self.cem_initial_action_stdev = float(cem_initial_action_stdev)
+        self.cem_stdev_min = float(cem_stdev_min)
+        self.cem_best_k = int(cem_best_k)
+
+    def _configure_engine(self):
+        self.engine.cem_gmm_configure(self.cem_best_k, self.cem_initial_action_stdev, self.cem_stdev_min)
+
+    @property
+    def sampling_dist(self):
+        loc, scale, p1 = self.engine.cem_gmm_get_distribution()
+        T = self.mpc_horizon
+        return dict(loc=torch.from_numpy(loc.T.copy()).reshape(T, 1, 2), scale=torch.from_numpy(scale.T.copy()).reshape(T, 1, 2),
+                    probs=torch.tensor([p1, 1.0 - p1]))
+
+    def _draw(self):
+        K, T, it = self.num_rollouts, self.mpc_horizon, self.cem_outer_it
+        if self.rng is self._own_rng:
+            eps = self._ring_draw((it, 2, T, K), self._own_rng.normal)
+            ring = getattr(self, "_uring", None)
+            if ring is None or self._uring_i >= ring.shape[0]:
+                n = max(1, min(self.NOISE_RING, (64 << 20) // (4 * it * T * K)))
+                self._uring = self._own_rng.uniform((n, it, T, K))
+                self._uring_i = 0
+            u01 = self._uring[self._uring_i]
+            self._uring_i += 1
+            return eps, u01, L.TIME_MAJOR
+        eps, u01 = [], []
+        for _ in range(it):
+            eps.append(torch.as_tensor(self.rng.normal(shape=(K, T, 1, 2), dtype=torch.float32)).reshape(K, T, 2))
+            u01.append(torch.as_tensor(self.rng.uniform(shape=(K, T, 1), minval=0.0, maxval=1.0, dtype=torch.float32)).reshape(K, T))
+        to = dict(device=self.device, dtype=torch.float32)
+        return torch.stack(eps).to(**to).contiguous(), torch.stack(u01).to(**to).contiguous(), L.ROLLOUT_MAJOR
+
+    def step(self, s: np.ndarray, time=None):
+        s = self._state(s)
+        eps, u01, layout = self._draw()
+        u_prev = float(np.asarray(self.u).reshape(-1)[0])
+        self._u_prev_logged = self.u
+        if self.optimizer_logging:
+            K, T = self.num_rollouts, self.mpc_horizon
+            Q = torch.empty((T, K) if layout == L.TIME_MAJOR else (K, T), device=self.device)
+            u_dev = self.engine.cem_gmm_step(torch.from_numpy(s).to(self.device), eps, u01, layout, u_prev, Q_out=Q)
+            u = float(u_dev.cpu()[0])
+        else:
+            u = self.engine.cem_gmm_step_host(s, eps, u01, layout, u_prev)
+        self.u = np.array(u, dtype=np.float32)
+        if self.optimizer_logging:
+            self._log_rollouts(s, Q.t() if layout == L.TIME_MAJOR else Q)
+        return self.u
+
+    def optimizer_reset(self):
+        self.engine.cem_gmm_reset()

@@ -392,6 +392,28 @@ int cps_cem_step_host(cps_handle *h, const float *s_host, const float *eps_dev, 
 int cps_cem_get_distribution(cps_handle *h, float *mean_host, float *stdev_host);
 int cps_cem_set_distribution(cps_handle *h, const float *mean_host, const float *stdev_host);
 
+/* optimizer_cem_gmm_tf (Control_Toolkit/Optimizers/optimizer_cem_gmm_tf.py:58-140): CEM whose sampling distribution is a
+ * two-component Gaussian mixture per horizon step.  Per outer iteration (three launches, nothing returns to the host):
+ * Q = clip(loc[t, c] + scale[t, c] * eps_c) with the component c of every (rollout, step) chosen independently
+ * (c = 0 iff u01 < p1; MixtureSameFamily over the [T, 1] batch, :60-61); predict_and_cost (plan_kernel); the cem_best_k
+ * cheapest plans (ties to the lowest index); every elite but the two cheapest joins the nearer of those two in the
+ * Euclidean norm over the horizon (:72-77); the clusters' per-step mean and population stdev clipped to
+ * [cem_stdev_min, 1e4] become the components, the first cluster's share of the elites its weight p1 (:79-93).  After the
+ * last iteration u_out_dev[0] = elite_Q[0, 0] and loc / scale are shifted by one step with the last entry repeated
+ * (:108-118).  cps_cem_gmm_reset: both components at mid-range with the initial stdev, p1 = 0.5 (:133-139).
+ * Draws: eps_dev standard normals for BOTH components, [n_iterations][K][T][2] (the reference's sample shape) or
+ * [n_iterations][2][T][K] with CPS_TIME_MAJOR; u01_dev uniforms in [0, 1), [n_iterations][K][T] or [n_iterations][T][K].
+ * Q_out_dev ([K][T] or [T][K]) receives the last iteration's plans, J_out_dev [K] its costs; both may be NULL.
+ * Distribution: loc[2][T], scale[2][T] (component-major), p1. */
+int cps_cem_gmm_configure(cps_handle *h, int best_k, float initial_stdev, float stdev_min);
+int cps_cem_gmm_reset(cps_handle *h);
+int cps_cem_gmm_step(cps_handle *h, const float *s_dev, const float *eps_dev, const float *u01_dev, int layout,
+                     int n_iterations, float u_prev, float *u_out_dev, float *Q_out_dev, float *J_out_dev);
+int cps_cem_gmm_step_host(cps_handle *h, const float *s_host, const float *eps_dev, const float *u01_dev, int layout,
+                          int n_iterations, float u_prev, float *u_out_host);
+int cps_cem_gmm_get_distribution(cps_handle *h, float *loc_host, float *scale_host, float *p1_host);
+int cps_cem_gmm_set_distribution(cps_handle *h, const float *loc_host, const float *scale_host, const float *p1_host);
+
 /* Roofline denominators for the compute-bound rollout kernels, measured on this device with two microbenchmarks
  * (dense FFMA chains; MUFU.EX2 chains): FP32 TFLOP/s (FMA = 2 flops) and MUFU Gop/s.  Synchronises. */
 int cps_measure_peaks(cps_handle *h, double *fp32_tflops, double *mufu_gops);

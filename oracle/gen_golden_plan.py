@@ -6,7 +6,7 @@ installed here, so the handful of tf.* ops these two files call is supplied by o
 the optimizers' own Python runs as is, on the reference's torch predictor_ODE (or numba predictor_ODE_v0) and the
 reference's cost plugins, with the generator's draws injected so that the CUDA path can be fed the same numbers.
 
-    python oracle/gen_golden_plan.py
+    python oracle/gen_golden_plan.py [ra] [cem] [gmm]      (default: gmm)
 """
 from __future__ import annotations
 
@@ -104,11 +104,55 @@ def gen_cem():
              mean=np.stack(MU), stdev=np.stack(SD))
 
 
+def gen_cem_gmm():
+    import zlib
+    from oracle import oracle as O
+    runs = [  # name, predictor, cost, K, T, steps, outer iterations, best_k, tp, te
+        ("gmm_ode_gradmin", "ODE", "quadratic_boundary_grad_minimal", 200, 35, 4, 3, 40, 0.0, 1.0),
+        ("gmm_v0_gradmin", "ODE_v0", "quadratic_boundary_grad_minimal", 200, 35, 3, 3, 40, 0.0, 1.0),
+        ("gmm_ode_K512", "ODE", "quadratic_boundary_grad_minimal", 512, 25, 3, 2, 33, 0.05, 1.0),
+    ]
+    for (name, pred, cost, K, T, steps, iters, best_k, tp, te) in runs:
+        rng = np.random.default_rng(zlib.crc32(name.encode()))   # reproducible (str hashes are salted per process)
+        opt = _make("optimizer_cem_gmm_tf", pred, cost, K, T, tp, te, cem_outer_it=iters, cem_initial_action_stdev=0.5,
+                    cem_stdev_min=0.01, cem_best_k=best_k)
+        eps = rng.standard_normal((steps, iters, K, T, 2)).astype(np.float32)
+        u01 = rng.uniform(0, 1, (steps, iters, K, T)).astype(np.float32)
+        draws = []
+        for i in range(steps):
+            for j in range(iters):
+                draws += [eps[i, j][:, :, None, :], u01[i, j][:, :, None]]
+        tf_shim.GMM_DRAWS = tf_shim.InjectedDraws(draws)
+        s = hanging_state()
+        S, U, JJ, QQ, UP, LOC, SC, P1 = [], [], [], [], [], [], [], []
+        for i in range(steps):
+            UP.append(np.float32(opt.u))
+            u = opt.step(s.copy())
+            S.append(s.copy()); U.append(np.float32(u))
+            JJ.append(opt.logging_values["J_logged"].astype(np.float32))
+            QQ.append(opt.logging_values["Q_logged"][:, :, 0].astype(np.float32))
+            cd = opt.sampling_dist.components_distribution
+            LOC.append(cd.mean().numpy().reshape(T, 2).astype(np.float32))
+            SC.append(cd.stddev().numpy().reshape(T, 2).astype(np.float32))
+            P1.append(np.float32(opt.sampling_dist.mixture_distribution.probs[0]))
+            s = O.rollout("ODE", s, np.array([[u]], dtype=np.float32))[0, 1]
+        save("plan_" + name, dict(ref="Control_Toolkit/Optimizers/optimizer_cem_gmm_tf.py:58-131 (tf / tfpd ops from "
+                                      "oracle/tf_shim.py, injected normal and uniform draws)", predictor=pred, cost=cost, K=K,
+                                  T=T, steps=steps, iterations=iters, best_k=best_k, initial_stdev=0.5, stdev_min=0.01,
+                                  target_position=tp, target_equilibrium=te),
+             eps=eps, u01=u01, s=np.stack(S), u=np.array(U), J=np.stack(JJ), Q=np.stack(QQ), u_prev=np.array(UP),
+             loc=np.stack(LOC), scale=np.stack(SC), p1=np.array(P1))
+
+
 def main():
     if not R.available():
         raise SystemExit("reference tree not available; fixtures can only be regenerated in the build container")
     R.load()
-    for fn in (gen_random_action, gen_cem):
+    # the ra_* / cem_* fixtures were drawn with per-process seeds (salted str hash): they carry their own inputs and stay
+    # valid recordings, but regenerating them gives different draws -- pass their names to regenerate deliberately
+    which = set(sys.argv[1:]) or {"gmm"}
+    fns = [f for f, tag in ((gen_random_action, "ra"), (gen_cem, "cem"), (gen_cem_gmm, "gmm")) if tag in which]
+    for fn in fns:
         with contextlib.redirect_stdout(io.StringIO()) as buf:
             try:
                 fn()

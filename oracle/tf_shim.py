@@ -9,6 +9,8 @@ only the ~15 `tf.*` ops it calls are supplied here, on torch CPU float32 tensors
   tf.math.reduce_std    population standard deviation: sqrt(mean(|x - mean(x)|^2)) (tf.math.reduce_variance)
   tf.clip_by_value, tf.tile, tf.gather, tf.concat, tf.reduce_mean, tf.squeeze, tf.multiply, tf.zeros, tf.ones,
   tf.convert_to_tensor, tf.constant, tf.ensure_shape: their numpy namesakes.
+  optimizer_cem_gmm_tf additionally: tf.norm, tf.transpose, tf.argmin (first of equal minima), tf.cast, tf.shape, tf.stack,
+  and tensorflow_probability's Normal / Categorical / MixtureSameFamily (sample, mean, stddev) with injected draws.
 Everything else resolves to an inert stub so that `TensorFlowLibrary()` (SI_Toolkit/computation_library.py:306-...) can
 be constructed; none of those attributes is called on this path.  What this pins is the optimizer LOGIC of the
 reference, not TensorFlow's kernels (the summation order inside reduce_mean / reduce_std is TF's own; the parity
@@ -102,12 +104,73 @@ def install():
     tf.concat = lambda xs, axis=0: torch.cat([_t(x, torch.float32) for x in xs], dim=axis)
     tf.squeeze = lambda x, axis=None: torch.squeeze(_t(x)) if axis is None else torch.squeeze(_t(x), axis)
     tf.ensure_shape = lambda x, shape: x
+    # optimizer_cem_gmm_tf (:72-93)
+    tf.newaxis = None
+    tf.transpose = lambda x, perm=None: _t(x).permute(*perm) if perm is not None else _t(x).t()
+    tf.norm = lambda x, axis=None: torch.sqrt(torch.sum(_t(x) * _t(x), dim=tuple(axis) if isinstance(axis, (list, tuple)) else axis))
+    tf.argmin = lambda x, axis=None: torch.argmin(_t(x), dim=axis)   # the first of equal minima, like TF
+    tf.cast = lambda x, dtype=None: _t(x).to(dtype) if isinstance(x, torch.Tensor) else torch.as_tensor(x, dtype=dtype)
+    tf.shape = lambda x: torch.as_tensor(list(_t(x).shape))
+    tf.stack = lambda xs, axis=0: torch.stack([_t(x, torch.float32) for x in xs], dim=axis)
     math = _Mod("tensorflow.math")
     math.reduce_std = _reduce_std
     tf.math = math
     sys.modules["tensorflow"] = tf
     sys.modules["tensorflow.math"] = math
+    _install_tfp()
     return tf
+
+
+# ---- tensorflow_probability.python.distributions: the three classes optimizer_cem_gmm_tf builds -----------------------
+GMM_DRAWS = None   # an InjectedDraws: MixtureSameFamily.sample takes one normal [n, *batch, k] and one uniform [n, *batch]
+
+
+class _Normal:
+    def __init__(self, loc, scale):
+        self.loc, self.scale = _t(loc, torch.float32), _t(scale, torch.float32)
+
+    def mean(self):
+        return self.loc
+
+    def stddev(self):
+        return self.scale
+
+
+class _Categorical:
+    def __init__(self, probs):
+        self.probs = torch.stack([_t(p, torch.float32).reshape(()) for p in probs]) if isinstance(probs, (list, tuple)) else _t(probs, torch.float32)
+
+
+class _MixtureSameFamily:
+    """Two components.  sample(): every batch member of every sample picks its component independently (index 0 iff the
+    uniform draw is below probs[0]) from component draws loc + scale * eps, as tfpd.MixtureSameFamily.sample does (it
+    draws all components and masks with the one-hot mixture sample)."""
+
+    def __init__(self, mixture_distribution, components_distribution):
+        self.mixture_distribution, self.components_distribution = mixture_distribution, components_distribution
+
+    def sample(self, sample_shape):
+        n = int(sample_shape[0])
+        cd = self.components_distribution
+        batch = list(cd.loc.shape[:-1])
+        eps = GMM_DRAWS.normal([n] + batch + [int(cd.loc.shape[-1])])
+        u = GMM_DRAWS.uniform([n] + batch)
+        x = cd.loc[None] + cd.scale[None] * eps
+        c = (u >= self.mixture_distribution.probs[0]).long()
+        return torch.gather(x, -1, c[..., None])[..., 0]
+
+
+def _install_tfp():
+    tfp = _Mod("tensorflow_probability")
+    tfp.__path__ = []
+    py = _Mod("tensorflow_probability.python")
+    py.__path__ = []
+    d = _Mod("tensorflow_probability.python.distributions")
+    d.Normal, d.Categorical, d.MixtureSameFamily, d.Distribution = _Normal, _Categorical, _MixtureSameFamily, object
+    tfp.python, py.distributions = py, d
+    sys.modules["tensorflow_probability"] = tfp
+    sys.modules["tensorflow_probability.python"] = py
+    sys.modules["tensorflow_probability.python.distributions"] = d
 
 
 class InjectedDraws:
