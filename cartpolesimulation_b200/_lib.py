@@ -103,6 +103,7 @@ SYMBOLS = {
     "cps_fleet_period": (C.c_longlong, [_VP]),
     "cps_fleet_step": (C.c_int, [_VP, C.c_int, _VP, _VP, _VP, _VP, _VP]),
     "cps_fleet_relabel": (C.c_int, [_VP, C.c_int, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "cps_fleet_relabel_masked": (C.c_int, [_VP, C.c_int, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "cps_fleet_reset": (C.c_int, [_VP, C.c_longlong]),
     "cps_fleet_noise": (C.c_int, [_VP, C.c_longlong, _VP]),
     "cps_plan_cost": (C.c_int, [_VP, _VP, _VP, C.c_int, C.c_int, C.c_int, C.c_float, _VP, _VP, C.c_int]),

@@ -52,6 +52,7 @@ struct FleetArgs {
     const float *replay_s;      // [E][6] recorded states of this row, or null (closed loop)
     const float *L_row, *mp_row;  // [E] controller-model pole length / mass of this row, or null (handle's values)
     float *Q_out;               // [E] controls computed for this row
+    const int *active;          // [E] or null: files with 0 sit this row out (controller state untouched, no output)
     float k, m_cart, g, J_fric, M_fric, u_max;  // physical constants for the device-side fold of (L, m_pole)
     float m_pole_fixed;         // ODE_v0 takes only L from the variable parameters
     float L_default, mp_default;  // the handle's L / m_pole "for controller" when only one of the arrays is given
@@ -184,6 +185,7 @@ __global__ void __launch_bounds__(256, 4) fleet_kernel(const __grid_constant__ F
     __shared__ CostParams s_cost;
     const MppiParams &mp = a.mp;
     const int e = blockIdx.y, tid = threadIdx.x;
+    if (a.active && a.active[e] == 0) return;   // whole experiment (all its blocks): warm start, last control and ticket stay
     const float tp = a.tp ? a.tp[e] : 0.0f, te = a.te ? a.te[e] : 1.0f;
     if (tid == 0) {
         s_cost = (te == 1.0f) ? a.cost_up : a.cost_dn;
@@ -420,7 +422,7 @@ int cps_fold_cost_for(cps_handle *h, float target_equilibrium, CostParams *out);
 // Shared by cps_fleet_step (closed loop: replay_dev == nullptr) and cps_fleet_relabel (states from a recording).
 static int fleet_launch(cps_handle *h, const char *who, int n_periods, const float *tp_dev, const float *te_dev,
                         const float *noise_dev, float *record_dev, float *J_out_dev, const float *replay_dev,
-                        const float *L_dev, const float *mp_dev, float *Q_out_dev) {
+                        const float *L_dev, const float *mp_dev, float *Q_out_dev, const int *active_dev = nullptr) {
     FleetState *F = h->fleet;
     if (!F) return fail(h, CPS_ERR_NOT_CONFIGURED, "%s: no fleet (cps_fleet_create)", who);
     if (n_periods < 0) return fail(h, CPS_ERR_INVALID, "%s: negative number of periods / rows", who);
@@ -465,6 +467,7 @@ static int fleet_launch(cps_handle *h, const char *who, int n_periods, const flo
         a.L_row = L_dev ? L_dev + (size_t)j * E : nullptr;
         a.mp_row = mp_dev ? mp_dev + (size_t)j * E : nullptr;
         a.Q_out = Q_out_dev ? Q_out_dev + (size_t)j * E : nullptr;
+        a.active = active_dev ? active_dev + (size_t)j * E : nullptr;
         a.period = (unsigned)F->period;
         a.time = (double)F->period * dt_control;
         fn<<<grid, F->block, F->smem, h->stream>>>(a);
@@ -487,6 +490,15 @@ extern "C" int cps_fleet_relabel(cps_handle *h, int n_rows, const float *states_
     if (!h) return CPS_ERR_INVALID;
     if (!states_dev || !Q_out_dev) return fail(h, CPS_ERR_INVALID, "cps_fleet_relabel: null pointer");
     return fleet_launch(h, "cps_fleet_relabel", n_rows, tp_dev, te_dev, noise_dev, nullptr, J_out_dev, states_dev, L_dev, m_pole_dev, Q_out_dev);
+}
+
+extern "C" int cps_fleet_relabel_masked(cps_handle *h, int n_rows, const float *states_dev, const float *tp_dev, const float *te_dev,
+                                        const float *L_dev, const float *m_pole_dev, const float *noise_dev, float *Q_out_dev,
+                                        float *J_out_dev, const int *active_dev) {
+    if (!h) return CPS_ERR_INVALID;
+    if (!states_dev || !Q_out_dev) return fail(h, CPS_ERR_INVALID, "cps_fleet_relabel_masked: null pointer");
+    return fleet_launch(h, "cps_fleet_relabel_masked", n_rows, tp_dev, te_dev, noise_dev, nullptr, J_out_dev, states_dev, L_dev,
+                        m_pole_dev, Q_out_dev, active_dev);
 }
 
 extern "C" int cps_fleet_noise(cps_handle *h, long long period, float *out_dev) {

@@ -12,12 +12,18 @@ Attribute-name conventions of the reference are kept (:166-263): `<col>_random_u
 attribute per row, `<col>_integrate_<lo>_<hi>_` averages the control over a scrambled-Sobol sample of the attribute
 (`integration_num_evals` consecutive controller steps per row, :318-345), `<col>_differentiate_` labels the derivative of
 the control with respect to the attribute (five controller steps per row and feature at value + {-2..2} * 0.5e-3, then a
-Savitzky-Golay first derivative, :348-470).  integration_method='nquad' (adaptive quadrature: the next query point
-depends on the controller's answers) and method='nd' are not offered (NotImplementedError).  No CPU fallback.
+Savitzky-Golay first derivative, :348-470).  integration_method='nquad' (:346-362, the reference's default): the
+quadrature is adaptive -- the next query point depends on the controller's answers, and every answer advances the
+controller's warm start -- so it cannot be laid out as a fixed table of rows.  Here scipy's own `nquad` (QUADPACK, as in
+the reference) drives every file on a host thread of its own, and the integrand evaluations of all files are collected
+into lockstep rounds: one masked fleet launch (cps_fleet_relabel_masked) evaluates the pending query of every file that
+still has one, files that are done with the row sit the launch out.  method='nd' is not offered.  No CPU fallback.
 """
 from __future__ import annotations
 
 import re
+import threading
+from math import ceil
 
 import numpy as np
 import torch
@@ -57,9 +63,10 @@ class Relabeller:
         self.engine._chk(self.engine.lib.cps_fleet_reset(self.engine._h, int(period)))
 
     def relabel_device(self, states, target_position=None, target_equilibrium=None, pole_length=None, m_pole=None,
-                       noise=None, Q_out=None, J_out=None):
+                       noise=None, Q_out=None, J_out=None, active=None):
         """cps_fleet_relabel on cuda tensors: states [R, E, 6]; attributes [R, E] or None; noise [R, E, n_ind, K] for a
-        'supplied' fleet.  Returns Q_out [R, E] (no synchronisation)."""
+        'supplied' fleet; active [R, E] int32 or None: files with 0 sit the row out (cps_fleet_relabel_masked).
+        Returns Q_out [R, E] (no synchronisation)."""
         eng = self.engine
         eng.use_current_stream()
         _check_dev(states, "states", self.device)
@@ -77,6 +84,14 @@ class Relabeller:
         if Q_out is None:
             Q_out = torch.empty((R, self.E), device=self.device, dtype=torch.float32)
         _check_dev(Q_out, "Q_out", self.device)
+        if active is not None:
+            _check_dev(active, "active", self.device, dtype=torch.int32)
+            if active.dtype != torch.int32 or active.numel() != R * self.E:
+                raise ValueError("active must be an int32 tensor of shape [rows, files]")
+            eng._chk(eng.lib.cps_fleet_relabel_masked(eng._h, R, _ptr(states), _ptr(target_position), _ptr(target_equilibrium),
+                                                      _ptr(pole_length), _ptr(m_pole), _ptr(noise), _ptr(Q_out), _ptr(J_out),
+                                                      _ptr(active)))
+            return Q_out
         eng._chk(eng.lib.cps_fleet_relabel(eng._h, R, _ptr(states), _ptr(target_position), _ptr(target_equilibrium),
                                            _ptr(pole_length), _ptr(m_pole), _ptr(noise), _ptr(Q_out), _ptr(J_out)))
         return Q_out
@@ -182,6 +197,111 @@ def sobol_samples(features, ranges, num_evals, n_rows, seed=None):
     return out
 
 
+class _Lockstep:
+    """Rendezvous between the per-file quadrature threads and the launching thread: workers post one query each and
+    block; once every live worker has posted (or finished) the coordinator evaluates the batch and hands the answers back."""
+
+    def __init__(self, n_live):
+        self.cv = threading.Condition()
+        self.req, self.res, self.done, self.n_live, self.err = {}, {}, set(), n_live, None
+
+    def ask(self, e, vals):
+        with self.cv:
+            self.req[e] = vals
+            self.cv.notify_all()
+            while e not in self.res and self.err is None:
+                self.cv.wait()
+            if self.err is not None:
+                raise RuntimeError("relabelling launch failed") from self.err
+            return self.res.pop(e)
+
+    def finish(self, e):
+        with self.cv:
+            self.done.add(e)
+            self.cv.notify_all()
+
+    def serve(self, evaluate):
+        while True:
+            with self.cv:
+                while len(self.req) + len(self.done) < self.n_live:
+                    self.cv.wait()
+                if not self.req:
+                    return
+                batch = dict(self.req)
+                self.req.clear()
+            try:
+                out = evaluate(batch)
+            except Exception as ex:   # wake the workers up, then re-raise in the launching thread
+                with self.cv:
+                    self.err = ex
+                    self.cv.notify_all()
+                raise
+            with self.cv:
+                self.res.update(out)
+                self.cv.notify_all()
+
+
+def nquad_rows(relabeller: Relabeller, states, attrs, features, ranges, num_evals, rows, noise=None):
+    """integration(method='nquad') (:346-362) for every row of every file: states [R, E, 6]; attrs {name: [R, E] or None}
+    (the row's attribute values; swept features are overridden by the quadrature's query points); rows[e] = number of
+    rows of file e.  noise: for a 'supplied' fleet a list, per file, of cuda tensors [n_calls_e, n_ind, K] consumed one per
+    controller step of that file.  Returns (labels [R, E] float64 = integral / volume, calls [E] controller steps taken)."""
+    from scipy.integrate import nquad
+    E, R = relabeller.E, states.shape[0]
+    d = len(features)
+    limits = [ranges[f] for f in features]
+    volume = float(np.prod([hi - lo for lo, hi in limits]))
+    opts = {"limit": ceil(num_evals ** (1 / d)), "epsabs": 1e-2, "epsrel": 1e-2}   # :355-357
+    dev = relabeller.device
+    names = [k for k in _CONTROLLER_ATTRIBUTES if attrs.get(k) is not None or k in features]
+    labels = np.full((R, E), np.nan)
+    calls = np.zeros(E, dtype=np.int64)
+    Q_dev = torch.zeros((1, E), device=dev)
+    nz_dev = torch.zeros((1, E, relabeller.n_ind, relabeller.K), device=dev) if noise is not None else None
+    for r in range(R):
+        live = [e for e in range(E) if r < rows[e]]
+        if not live:
+            break
+        sync = _Lockstep(len(live))
+        s_dev = torch.from_numpy(np.ascontiguousarray(states[r:r + 1])).to(dev)
+        base = {k: (np.zeros(E, np.float32) if attrs.get(k) is None else np.asarray(attrs[k][r], np.float32).copy()) for k in names}
+
+        def worker(e):
+            try:
+                integral, _ = nquad(lambda *x: float(sync.ask(e, x)), limits, opts=[opts] * d)
+                labels[r, e] = integral / volume
+            except Exception:
+                labels[r, e] = np.nan   # the reference prints the exception and leaves the row unlabelled
+            finally:
+                sync.finish(e)
+
+        def evaluate(batch):
+            vals = {k: v.copy() for k, v in base.items()}
+            act = np.zeros((1, E), dtype=np.int32)
+            for e, x in batch.items():
+                act[0, e] = 1
+                for f, v in zip(features, x):
+                    vals[f][e] = np.float32(v)
+                if nz_dev is not None:
+                    nz_dev[0, e].copy_(noise[e][calls[e]])
+                calls[e] += 1
+            t = {k: torch.from_numpy(v.reshape(1, E)).to(dev) for k, v in vals.items()}
+            relabeller.relabel_device(s_dev, t.get("target_position"), t.get("target_equilibrium"), t.get("L"), t.get("m_pole"),
+                                      noise=nz_dev, Q_out=Q_dev, active=torch.from_numpy(act).to(dev))
+            q = Q_dev.cpu().numpy()[0]
+            return {e: float(q[e]) for e in batch}
+
+        threads = [threading.Thread(target=worker, args=(e,), daemon=True) for e in live]
+        for t in threads:
+            t.start()
+        try:
+            sync.serve(evaluate)
+        finally:
+            for t in threads:
+                t.join(timeout=60)
+    return labels, calls
+
+
 def add_control_along_trajectories(dfs, controller_config, controller_output_variable_name="Q_calculated",
                                    integration_method="monte_carlo", integration_num_evals=64, save_output_only=False,
                                    df_modifier=lambda df: df, relabeller: Relabeller | None = None, seed=None,
@@ -212,13 +332,14 @@ def add_control_along_trajectories(dfs, controller_config, controller_output_var
                                                                  else controller_output_variable_name)
     if features and diff_features:
         raise ValueError("Cannot integrate and differentiate at the same time.")
-    if features and integration_method != "monte_carlo":
-        raise NotImplementedError("integration_method='nquad' is adaptive (sequential on the host); use 'monte_carlo'")
+    if features and integration_method not in ("monte_carlo", "nquad"):
+        raise ValueError("Invalid integration method. Choose 'nquad' or 'monte_carlo'.")
+    nquad_mode = bool(features) and integration_method == "nquad"
     unknown = [k for k in features + diff_features if k not in _CONTROLLER_ATTRIBUTES]
     if unknown:
         raise ValueError(f"cannot sweep {unknown}: the controller's attributes are {_CONTROLLER_ATTRIBUTES}")
     ev = 1
-    if features:
+    if features and not nquad_mode:
         m = int(np.ceil(np.log2(integration_num_evals)))
         ev = 2 ** m
     elif diff_features:
@@ -240,7 +361,7 @@ def add_control_along_trajectories(dfs, controller_config, controller_output_var
         for k in _CONTROLLER_ATTRIBUTES:
             if attrs[k] is not None and k in env and env[k] in t.columns:
                 attrs[k][:, e] = np.repeat(t[env[k]].to_numpy(dtype=np.float32)[idx], ev)
-        if features:
+        if features and not nquad_mode:
             smp = sobol_samples(features, ranges, ev, R, seed=None if seed is None else [int(seed), e])
             for j, f in enumerate(features):
                 attrs[f][:, e] = smp[:, :, j].reshape(-1).astype(np.float32)
@@ -257,13 +378,19 @@ def add_control_along_trajectories(dfs, controller_config, controller_output_var
         raise ValueError(f"the relabeller was built for {relabeller.E} files, got {E}")
     try:
         relabeller.reset()
-        Q = relabeller.relabel(states, attrs["target_position"], attrs["target_equilibrium"], attrs["L"], attrs["m_pole"],
-                               noise=noise)
+        if nquad_mode:
+            labels_nq, _ = nquad_rows(relabeller, states, attrs, features, ranges, integration_num_evals, rows, noise=noise)
+            Q = np.zeros((R, E), dtype=np.float32)
+        else:
+            Q = relabeller.relabel(states, attrs["target_position"], attrs["target_equilibrium"], attrs["L"], attrs["m_pole"],
+                                   noise=noise)
     finally:
         if own:
             relabeller.close()
     Q = Q.reshape(R, ev, E).astype(np.float64)
-    if diff_features:
+    if nquad_mode:
+        labels = labels_nq[:, None, :]
+    elif diff_features:
         from scipy.signal import savgol_filter
         half = (DIFF_WINDOW - 1) // 2
         u = Q.reshape(R, len(diff_features), DIFF_WINDOW, E)

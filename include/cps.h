@@ -349,6 +349,12 @@ int cps_fleet_step(cps_handle *h, int n_periods, const float *tp_dev, const floa
 int cps_fleet_relabel(cps_handle *h, int n_rows, const float *states_dev, const float *tp_dev, const float *te_dev,
                       const float *L_dev, const float *m_pole_dev, const float *noise_dev, float *Q_out_dev,
                       float *J_out_dev);
+/* The same with a per-row, per-file mask active_dev [n_rows][E] (int; NULL: all active): a file whose entry is 0 sits
+ * the row out -- its warm start, last control and Q_out entry stay untouched.  Used by the adaptive quadrature of
+ * integration(method='nquad') (:346-362), where every file asks for a different number of controller steps per row. */
+int cps_fleet_relabel_masked(cps_handle *h, int n_rows, const float *states_dev, const float *tp_dev, const float *te_dev,
+                             const float *L_dev, const float *m_pole_dev, const float *noise_dev, float *Q_out_dev,
+                             float *J_out_dev, const int *active_dev);
 int cps_fleet_reset(cps_handle *h, long long period);
 /* The draws CPS_FLEET_NOISE_PHILOX uses in controller period `period`: out_dev [E][n_ind][K]. */
 int cps_fleet_noise(cps_handle *h, long long period, float *out_dev);

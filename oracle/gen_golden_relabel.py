@@ -66,7 +66,7 @@ def make_file(rng, n_rows):
     return df
 
 
-def gen(name, pred, cost, K, T, n_files, n_rows, env_attrs, n_evals):
+def gen(name, pred, cost, K, T, n_files, n_rows, env_attrs, n_evals, method="monte_carlo"):
     import torch
     if "numdifftools" not in sys.modules:
         try:
@@ -74,7 +74,9 @@ def gen(name, pred, cost, K, T, n_files, n_rows, env_attrs, n_evals):
         except Exception:
             sys.modules["numdifftools"] = types.ModuleType("numdifftools")
     from SI_Toolkit.General.preprocess_data_add_control_along_trajectories import add_control_along_trajectories
-    rng = np.random.default_rng(abs(hash(name)) % (2 ** 31))
+    import zlib
+    # (the fixtures before nquad_* were drawn with a per-process salted str hash; they carry their own inputs)
+    rng = np.random.default_rng(zlib.crc32(name.encode()) if method == "nquad" else abs(hash(name)) % (2 ** 31))
     arrays, n_calls = {}, None
     for f in range(n_files):
         df = make_file(rng, n_rows)
@@ -95,17 +97,23 @@ def gen(name, pred, cost, K, T, n_files, n_rows, env_attrs, n_evals):
         n_ind = opt.Interpolator.number_of_interpolation_inducing_points
         gen_ = torch.Generator().manual_seed(100 + f)
         draws = [torch.normal(0.0, 1.0, size=(K, n_ind, 1), generator=gen_, dtype=torch.float32)
-                 for _ in range(n_rows * max(n_evals, 1, 5))]
+                 for _ in range(n_rows * (21 * 2 * max(n_evals, 1) if method == "nquad" else max(n_evals, 1, 5)))]
         opt.rng = R.InjectedNormal(draws)
         ctrl = RecordingController(opt, vp, draws, vp_np)
         cfg = dict(state_components=STATE_COLUMNS, environment_attributes_dict=dict(env_attrs))
         out = add_control_along_trajectories(df.copy(), cfg, controller_creator=lambda c, a: ctrl,
                                              controller_output_variable_name="Q_calculated_offline",
-                                             integration_method="monte_carlo", integration_num_evals=n_evals)
+                                             integration_method=method, integration_num_evals=n_evals)
         n_diff = sum(1 for v in env_attrs.values() if v.endswith("_differentiate_"))
         per_row = 5 * n_diff if n_diff else max(n_evals, 1)   # savgol window 5 per differentiated feature (:365-372)
-        assert len(ctrl.calls) == n_rows * per_row, "the reference swallowed an exception (it prints and goes on)"
-        n_calls = len(ctrl.calls)
+        if method == "nquad":   # adaptive: at least one 21-point Gauss-Kronrod rule per row
+            assert len(ctrl.calls) >= 21 * n_rows and len(ctrl.calls) % 21 == 0
+            assert not np.isnan(out["Q_calculated_offline"].to_numpy(dtype=np.float64)).any()
+            n_calls = max(n_calls or 0, len(ctrl.calls))
+            arrays[f"f{f}__n_calls"] = np.array(len(ctrl.calls))
+        else:
+            assert len(ctrl.calls) == n_rows * per_row, "the reference swallowed an exception (it prints and goes on)"
+            n_calls = len(ctrl.calls)
         arrays[f"f{f}__s"] = np.stack([c["s"] for c in ctrl.calls])
         arrays[f"f{f}__tp"] = np.array([c["tp"] for c in ctrl.calls], dtype=np.float64)
         arrays[f"f{f}__te"] = np.array([c["te"] for c in ctrl.calls], dtype=np.float64)
@@ -119,7 +127,7 @@ def gen(name, pred, cost, K, T, n_files, n_rows, env_attrs, n_evals):
     save("relabel_" + name, dict(ref="SI_Toolkit/General/preprocess_data_add_control_along_trajectories.py:53-140 driving "
                                      "optimizer_mppi (torch lib, injected draws) through a controller_mpc.step-shaped hook",
                                  predictor=pred, cost=cost, K=K, T=T, files=n_files, rows=n_rows, calls=n_calls,
-                                 evals=n_evals, environment_attributes_dict=env_attrs,
+                                 evals=n_evals, method=method, environment_attributes_dict=env_attrs,
                                  columns=["time"] + STATE_COLUMNS + ["target_position", "target_equilibrium", "L"]),
          **arrays)
 
@@ -128,6 +136,16 @@ def main():
     if not R.available():
         raise SystemExit("reference tree not available; fixtures can only be regenerated in the build container")
     R.load()
+    if "nquad" in sys.argv[1:]:   # only the adaptive-quadrature fixture (the others carry per-process random inputs)
+        integ = {"target_position": "target_position", "target_equilibrium": "target_equilibrium",
+                 "L": "L_integrate_0.25_0.55_", "Q_ccrc": "Q_applied_-1"}
+        with contextlib.redirect_stdout(io.StringIO()) as buf, contextlib.redirect_stderr(io.StringIO()):
+            try:
+                gen("nquad_ode", "ODE", "quadratic_boundary_grad_minimal", 128, 20, 2, 3, integ, 3, method="nquad")
+            finally:
+                txt = buf.getvalue()
+        print("\n".join(l for l in txt.splitlines() if l.startswith("wrote") or "Error" in l))
+        return
     plain = {"target_position": "target_position", "target_equilibrium": "target_equilibrium", "L": "L"}
     integ = {"target_position": "target_position", "target_equilibrium": "target_equilibrium",
              "L": "L_integrate_0.25_0.55_", "Q_ccrc": "Q_applied_-1"}

@@ -122,3 +122,39 @@ def test_relabel_errors():
         rl.relabel(np.zeros((3, 2, 6), np.float32))            # a 'supplied' fleet needs its noise
     with pytest.raises(ValueError):
         rl.relabel_device(torch.zeros((3, 5, 6), device="cuda"))   # wrong number of files
+
+
+def test_nquad_relabelling_matches_reference():
+    """integration_method='nquad' (the reference's default, adaptive quadrature): scipy's nquad drives every file, the
+    integrand evaluations of all files run as masked fleet launches.  Against a recording of the UNMODIFIED reference
+    (integration(), preprocess_data_add_control_along_trajectories.py:346-362, around optimizer_mppi with injected draws):
+    the same number of controller steps per file -- i.e. the same adaptive subdivisions -- and the same labels."""
+    import pandas as pd
+    from cartpolesimulation_b200.relabel import Relabeller, add_control_along_trajectories, nquad_rows
+    z, m = load_golden("relabel_nquad_ode")
+    E = m["files"]
+    dfs = [pd.DataFrame(z[f"f{f}__table"], columns=m["columns"]) for f in range(E)]
+    for f in range(E):
+        dfs[f]["Q_applied_-1"] = 0.0
+    noise = [torch.from_numpy(np.ascontiguousarray(z[f"f{f}__eps"].transpose(0, 2, 1))).cuda() for f in range(E)]   # [calls, n_ind, K]
+    steps = []
+
+    class Counting(Relabeller):   # records which files stepped in which launch and what they answered
+        def relabel_device(self, *a, **k):
+            q = super().relabel_device(*a, **k)
+            steps.append((k["active"].cpu().numpy()[0].copy(), q.cpu().numpy()[0].copy()))
+            return q
+
+    rl = Counting(E, m["K"], m["T"], integrator=m["predictor"], cost=m["cost"], noise="supplied", device=0)
+    cfg = dict(state_components=STATE, environment_attributes_dict=m["environment_attributes_dict"])
+    out = add_control_along_trajectories(dfs, cfg, "Q_calculated_offline", integration_method="nquad",
+                                         integration_num_evals=m["evals"], relabeller=rl, noise=noise)
+    for f in range(E):
+        calls = sum(int(a[f]) for a, _ in steps)
+        assert calls == int(z[f"f{f}__n_calls"]), (f, calls)            # the same adaptive path as the reference took
+        u = np.array([q[f] for a, q in steps if a[f]])
+        np.testing.assert_allclose(u, z[f"f{f}__u"], rtol=0, atol=1e-4)  # every controller step along the way
+        np.testing.assert_allclose(out[f]["Q_calculated_offline"].to_numpy(), z[f"f{f}__Q_calculated_offline"], rtol=0,
+                                   atol=1e-4)
+    assert any(a.sum() < E for a, _ in steps)   # the files did take different numbers of steps: some launches were masked
+    rl.close()

@@ -68,10 +68,58 @@ def test_attribute_name_conventions():
     assert set(np.round(d3["L_random_uniform"], 6)) <= {0.2, 0.3, 0.4, 0.5}
     f, r, env = RL.get_integration_features({"L": "L_integrate_0.25_0.55_", "target_position": "target_position"})
     assert f == ["L"] and r == {"L": (0.25, 0.55)} and env["L"] == "L"
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ValueError):
         RL.add_control_along_trajectories([df.assign(**{c: 0.0 for c in STATE})],
                                           dict(environment_attributes_dict={"L": "L_integrate_0.25_0.55_"}),
-                                          integration_method="nquad", relabeller=Recorder(1))
+                                          integration_method="simpson", relabeller=Recorder(1))
+
+
+class LockstepFake:
+    """Stands in for Relabeller in nquad mode: the 'controller' of file e answers u = a_e + b_e * L,
+    so the quadrature answer is known and the per-file step counters show who was masked out of which launch."""
+
+    def __init__(self, E):
+        import torch
+        self.E, self.K, self.n_ind, self.device = E, 4, 2, torch.device("cpu")
+        self.steps = np.zeros(E, dtype=np.int64)
+        self.launches, self.resets = [], 0
+        self.a, self.b = np.linspace(-0.2, 0.3, E), np.linspace(1.0, -2.0, E)
+
+    def reset(self, period=0):
+        self.resets += 1
+
+    def close(self):
+        pass
+
+    def relabel_device(self, states, target_position=None, target_equilibrium=None, pole_length=None, m_pole=None,
+                       noise=None, Q_out=None, J_out=None, active=None):
+        act = active.numpy()[0].astype(bool)
+        self.launches.append(act.copy())
+        L = pole_length.numpy()[0]
+        for e in np.nonzero(act)[0]:
+            Q_out[0, e] = float(self.a[e] + self.b[e] * L[e])
+            self.steps[e] += 1
+        return Q_out
+
+
+def test_nquad_runs_the_files_in_lockstep_rounds():
+    """integration_method='nquad': scipy's adaptive quadrature per file and row, evaluations of all files gathered into
+    masked launches; files that have no rows left (or are done with the row) sit launches out."""
+    E = 3
+    rows = [4, 2, 3]
+    dfs = [pd.DataFrame({**{c: np.full(n, 0.1 * (e + 1)) for c in STATE}, "time": np.arange(n) * 0.02, "L": np.full(n, 0.4),
+                         "target_position": np.zeros(n)}) for e, n in enumerate(rows)]
+    fake = LockstepFake(E)
+    cfg = dict(state_components=STATE, environment_attributes_dict={"L": "L_integrate_0.25_0.55_",
+                                                                   "target_position": "target_position"})
+    out = RL.add_control_along_trajectories(dfs, cfg, "Q", integration_method="nquad", integration_num_evals=64,
+                                            relabeller=fake, save_output_only=True)
+    assert fake.resets == 1 and [len(o) for o in out] == rows
+    for e in range(E):   # a linear integrand: the 21-point Gauss-Kronrod rule is exact, one interval per row
+        np.testing.assert_allclose(out[e]["Q"].to_numpy(), fake.a[e] + fake.b[e] * 0.4, rtol=0, atol=1e-6)
+        assert fake.steps[e] == 21 * rows[e]
+    assert len(fake.launches) == 21 * max(rows)                      # lockstep: one launch per round, not per file
+    assert [int(l.sum()) for l in fake.launches[::21]] == [3, 3, 2, 1]   # the short files drop out row by row
 
 
 def test_differentiation_expansion_and_labels_match_the_reference():
