@@ -289,57 +289,63 @@ __device__ __forceinline__ uint32_t pack_f16x2(float lo_v, float hi_v) {   // tw
 // cn = -c log2 e; per pair of units the constants are {-log2e (b_ir + b_hr), -log2e (b_iz + b_hz), b_in, b_hn} x 2.
 // Exponents are capped at 2^30, which bounds the shared-reciprocal products; everything stays in the operand scale (h is
 // kept as 128 h).
-template <int HALVES>
+// N chunks of 16 rollouts x 8 units per call, interleaved for instruction-level parallelism (2 N independent dependence
+// chains per thread): UNITS -> the chunks are consecutive 8-unit groups of the same 16 rollouts (64 live rollouts per CTA),
+// else -> the same 8 units of the two 16-lane halves of the quarter (128 live rollouts).
+template <int N, bool UNITS>
 __device__ __forceinline__ void gru_epilogue(uint32_t tq, uint32_t region, uint32_t cu, const float *cst, float c, float cn,
                                               uint32_t c_hi, uint32_t c_lo, int u0, int lane) {
-    uint32_t R[HALVES][4], Z[HALVES][4], NI[HALVES][4], NH[HALVES][4], PH[HALVES][2], PL[HALVES][2];
+    uint32_t R[N][4], Z[N][4], NI[N][4], NH[N][4], PH[N][2], PL[N][2];
+    float4 k0[N], k1[N];
 #pragma unroll
-    for (int hh = 0; hh < HALVES; ++hh) {
-        const uint32_t th = tq + ((uint32_t)(16 * hh) << 16);
-        ld16x256(th + region + C_R + cu, R[hh]);
-        ld16x256(th + region + C_Z + cu, Z[hh]);
-        ld16x256(th + region + C_NI + cu, NI[hh]);
-        ld16x256(th + region + C_NH + cu, NH[hh]);
-        ld16x128(th + c_hi + (u0 >> 1), PH[hh]);
-        ld16x128(th + c_lo + (u0 >> 1), PL[hh]);
+    for (int j = 0; j < N; ++j) {
+        const uint32_t th = tq + ((uint32_t)(UNITS ? 0 : 16 * j) << 16), cj = cu + (UNITS ? 8 * j : 0);
+        const int uj = u0 + (UNITS ? 8 * j : 0);
+        ld16x256(th + region + C_R + cj, R[j]);
+        ld16x256(th + region + C_Z + cj, Z[j]);
+        ld16x256(th + region + C_NI + cj, NI[j]);
+        ld16x256(th + region + C_NH + cj, NH[j]);
+        ld16x128(th + c_hi + (uj >> 1), PH[j]);
+        ld16x128(th + c_lo + (uj >> 1), PL[j]);
+        const float *kp = cst + ((uj >> 1) + (lane & 3)) * 8;
+        k0[j] = *reinterpret_cast<const float4 *>(kp);       // brn0, brn1, bzn0, bzn1
+        k1[j] = *reinterpret_cast<const float4 *>(kp + 4);   // bni0, bni1, bnh0, bnh1
     }
-    const float *kp = cst + ((u0 >> 1) + (lane & 3)) * 8;
-    const float4 k0 = *reinterpret_cast<const float4 *>(kp);       // brn0, brn1, bzn0, bzn1
-    const float4 k1 = *reinterpret_cast<const float4 *>(kp + 4);   // bni0, bni1, bnh0, bnh1
     const F2 C2 = f2(c), CN2 = f2(cn), ONE = f2(1.0f);
     ld_wait();
 #pragma unroll
-    for (int hh = 0; hh < HALVES; ++hh) {
+    for (int j = 0; j < N; ++j) {
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {   // the two rollouts of this thread in the half
-            const F2 tr = fma2(f2bits(R[hh][2 * q], R[hh][2 * q + 1]), CN2, f2(k0.x, k0.y));    // -log2e * pre-activation
-            const F2 tz = fma2(f2bits(Z[hh][2 * q], Z[hh][2 * q + 1]), CN2, f2(k0.z, k0.w));
+        for (int q = 0; q < 2; ++q) {   // the two rollouts of this thread in the chunk
+            const F2 tr = fma2(f2bits(R[j][2 * q], R[j][2 * q + 1]), CN2, f2(k0[j].x, k0[j].y));    // -log2e * pre-activation
+            const F2 tz = fma2(f2bits(Z[j][2 * q], Z[j][2 * q + 1]), CN2, f2(k0[j].z, k0[j].w));
             const F2 AR = add2(f2(ex2_f(fminf(lo(tr), 30.0f)), ex2_f(fminf(hi(tr), 30.0f))), ONE);   // 1 + e^{-r}
             const F2 AZ = add2(f2(ex2_f(fminf(lo(tz), 30.0f)), ex2_f(fminf(hi(tz), 30.0f))), ONE);
             const F2 PA = mul2(AR, AZ);
             const float inv = rcp_f(lo(PA) * hi(PA));
             const F2 IAB = mul2(f2(hi(PA), lo(PA)), f2(inv));          // 1 / (ar az) of each unit
             const F2 R2 = mul2(AZ, IAB), Z2 = mul2(AR, IAB);           // sigmoids
-            const F2 tnh = fma2(f2bits(NH[hh][2 * q], NH[hh][2 * q + 1]), C2, f2(k1.z, k1.w));
-            const F2 tni = fma2(f2bits(NI[hh][2 * q], NI[hh][2 * q + 1]), C2, f2(k1.x, k1.y));
+            const F2 tnh = fma2(f2bits(NH[j][2 * q], NH[j][2 * q + 1]), C2, f2(k1[j].z, k1[j].w));
+            const F2 tni = fma2(f2bits(NI[j][2 * q], NI[j][2 * q + 1]), C2, f2(k1[j].x, k1[j].y));
             const F2 ta = mul2(fma2(R2, tnh, tni), f2(2.885390081777927f));               // 2 log2e * n pre-activation
             const F2 E = add2(f2(ex2_f(fminf(lo(ta), 30.0f)), ex2_f(fminf(hi(ta), 30.0f))), ONE);   // 1 + e^{2n}
             const float m2 = -256.0f * rcp_f(lo(E) * hi(E));
             const F2 N128 = fma2(f2(hi(E), lo(E)), f2(m2), f2(128.0f));   // 128 tanh = 128 - 256 / (1 + e^{2n})
-            const float2 hh_ = unpack_h2(PH[hh][q]), hl = unpack_h2(PL[hh][q]);
+            const float2 hh_ = unpack_h2(PH[j][q]), hl = unpack_h2(PL[j][q]);
             const F2 HS = add2(f2(hh_.x, hh_.y), f2(hl.x, hl.y));        // 128 h(t-1)
             const F2 HN = fma2(HS, Z2, fma2(neg2(N128), Z2, N128));      // 128 h(t) = 128 ((h - n) z + n)
-            PH[hh][q] = pack_f16x2(lo(HN), hi(HN));
-            const float2 hf = unpack_h2(PH[hh][q]);
+            PH[j][q] = pack_f16x2(lo(HN), hi(HN));
+            const float2 hf = unpack_h2(PH[j][q]);
             const F2 L = add2(HN, f2(-hf.x, -hf.y));
-            PL[hh][q] = pack_f16x2(lo(L), hi(L));
+            PL[j][q] = pack_f16x2(lo(L), hi(L));
         }
     }
 #pragma unroll
-    for (int hh = 0; hh < HALVES; ++hh) {
-        const uint32_t th = tq + ((uint32_t)(16 * hh) << 16);
-        st16x128(th + c_hi + (u0 >> 1), PH[hh]);
-        st16x128(th + c_lo + (u0 >> 1), PL[hh]);
+    for (int j = 0; j < N; ++j) {
+        const uint32_t th = tq + ((uint32_t)(UNITS ? 0 : 16 * j) << 16);
+        const int uj = u0 + (UNITS ? 8 * j : 0);
+        st16x128(th + c_hi + (uj >> 1), PH[j]);
+        st16x128(th + c_lo + (uj >> 1), PL[j]);
     }
 }
 
@@ -589,15 +595,16 @@ __global__ void __launch_bounds__(TC_NT, 1) net_tc_kernel(const __grid_constant_
                 bar_wait(doneb(j % 3), (uint32_t)((j / 3) & 1));
                 tc_fence_after();
                 if (warp == 8 * g) TC_TR(16 + 4 * job + 1);
+                if (two) {
 #pragma unroll 1
-                for (int e = 0; e < 2; ++e) {
-                    const int cu = 16 * hs + 8 * e;   // first unit inside the job
-                    if (two)
-                        gru_epilogue<2>(tl, region(j), (uint32_t)cu, l ? cst2 : cst1, l ? ec2 : ec1, l ? ecn2 : ecn1,
-                                        l ? C_AH2_HI : C_AH1_HI, l ? C_AH2_LO : C_AH1_LO, 32 * g + cu, lane);
-                    else
-                        gru_epilogue<1>(tl, region(j), (uint32_t)cu, l ? cst2 : cst1, l ? ec2 : ec1, l ? ecn2 : ecn1,
-                                        l ? C_AH2_HI : C_AH1_HI, l ? C_AH2_LO : C_AH1_LO, 32 * g + cu, lane);
+                    for (int e = 0; e < 2; ++e) {   // both 16-lane halves of 8 units at a time
+                        const int cu = 16 * hs + 8 * e;   // first unit inside the job
+                        gru_epilogue<2, false>(tl, region(j), (uint32_t)cu, l ? cst2 : cst1, l ? ec2 : ec1, l ? ecn2 : ecn1,
+                                               l ? C_AH2_HI : C_AH1_HI, l ? C_AH2_LO : C_AH1_LO, 32 * g + cu, lane);
+                    }
+                } else {   // 16 rollouts x this warp's 16 units in one interleaved pass
+                    gru_epilogue<2, true>(tl, region(j), (uint32_t)(16 * hs), l ? cst2 : cst1, l ? ec2 : ec1, l ? ecn2 : ecn1,
+                                          l ? C_AH2_HI : C_AH1_HI, l ? C_AH2_LO : C_AH1_LO, 32 * g + 16 * hs, lane);
                 }
                 if (warp == 8 * g) TC_TR(16 + 4 * job + 2);
                 warp_signal(epib(job), lane);
@@ -778,8 +785,8 @@ __global__ void __launch_bounds__(TC_NT, 1) net_tc_kernel(const __grid_constant_
             bar_wait(tailb, 0);
             tc_fence_after();
             if (is_epi && upd) {
-                gru_epilogue<1>(tl, 0, (uint32_t)(TC_EU * sub), cst1, ec1, ecn1, C_AH1_HI, C_AH1_LO, chunk_u0(0), lane);
-                gru_epilogue<1>(tl, 128, (uint32_t)(TC_EU * sub), cst1, ec1, ecn1, C_AH1_HI, C_AH1_LO, chunk_u0(1), lane);
+                gru_epilogue<1, true>(tl, 0, (uint32_t)(TC_EU * sub), cst1, ec1, ecn1, C_AH1_HI, C_AH1_LO, chunk_u0(0), lane);
+                gru_epilogue<1, true>(tl, 128, (uint32_t)(TC_EU * sub), cst1, ec1, ecn1, C_AH1_HI, C_AH1_LO, chunk_u0(1), lane);
             }
             tc_sync();
             if (is_mma) {
@@ -792,8 +799,8 @@ __global__ void __launch_bounds__(TC_NT, 1) net_tc_kernel(const __grid_constant_
             bar_wait(tailb, 1);
             tc_fence_after();
             if (is_epi && upd) {
-                gru_epilogue<1>(tl, 256, (uint32_t)(TC_EU * sub), cst2, ec2, ecn2, C_AH2_HI, C_AH2_LO, chunk_u0(0), lane);
-                gru_epilogue<1>(tl, 0, (uint32_t)(TC_EU * sub), cst2, ec2, ecn2, C_AH2_HI, C_AH2_LO, chunk_u0(1), lane);
+                gru_epilogue<1, true>(tl, 256, (uint32_t)(TC_EU * sub), cst2, ec2, ecn2, C_AH2_HI, C_AH2_LO, chunk_u0(0), lane);
+                gru_epilogue<1, true>(tl, 0, (uint32_t)(TC_EU * sub), cst2, ec2, ecn2, C_AH2_HI, C_AH2_LO, chunk_u0(1), lane);
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 store_hidden(row == 0 ? a.h_ref : nullptr);
             }
