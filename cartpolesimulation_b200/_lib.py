@@ -53,6 +53,13 @@ class cps_fleet_config(C.Structure):
                 ("experiment_offset", C.c_longlong)]
 
 
+class cps_fleet_plant_models(C.Structure):
+    _fields_ = [("struct_size", C.c_int), ("control_noise_mode", C.c_int), ("control_noise_mult", C.c_float),
+                ("control_noise_add", C.c_float), ("measurement_noise", C.c_int), ("sigma_angle", C.c_float),
+                ("sigma_position", C.c_float), ("sigma_angleD", C.c_float), ("sigma_positionD", C.c_float),
+                ("latency", C.c_double)]
+
+
 # name -> (restype, argtypes); every symbol include/cps.h declares
 _FP = C.POINTER(C.c_float)
 _VP = C.c_void_p
@@ -102,6 +109,9 @@ SYMBOLS = {
     "cps_fleet_get_states": (C.c_int, [_VP, _FP, _FP, _FP]),
     "cps_fleet_period": (C.c_longlong, [_VP]),
     "cps_fleet_step": (C.c_int, [_VP, C.c_int, _VP, _VP, _VP, _VP, _VP]),
+    "cps_fleet_set_plant_models": (C.c_int, [_VP, C.POINTER(cps_fleet_plant_models)]),
+    "cps_fleet_get_observed": (C.c_int, [_VP, _FP]),
+    "cps_fleet_step_noisy": (C.c_int, [_VP, C.c_int, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "cps_fleet_relabel": (C.c_int, [_VP, C.c_int, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "cps_fleet_relabel_masked": (C.c_int, [_VP, C.c_int, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "cps_fleet_reset": (C.c_int, [_VP, C.c_longlong]),

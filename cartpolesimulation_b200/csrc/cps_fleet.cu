@@ -28,7 +28,30 @@ struct PlantParams {
     int n_sim;
 };
 
+// Plant-side models between the plant and the controller (all OFF in the shipped configuration,
+// cartpole_physical_parameters.yml:13-24): control disturbance (CartPole/noise_control_signal.py:5-26), measurement
+// noise (CartPole/noise_adder.py:69-84), latency (CartPole/latency_adder.py:10-74).  Per plant tick the reference pushes
+// the true state into a ring buffer, reads it back `latency` seconds late (linear interpolation between the two
+// neighbouring ticks, all six components), adds the measurement noise and recomputes cos / sin; the controller is handed
+// that observation, the plant keeps integrating the true state.
+struct PlantModels {
+    int on;                    // any of the three enabled: the solve reads `obs`, the plant stage maintains ring / obs
+    int ctrl_mode;             // 0 OFF, 1 additive, 2 truncnorm
+    float ctrl_mult, ctrl_add;
+    int meas_on;
+    float sig_a, sig_p, sig_aD, sig_pD;
+    int lat_int;               // int(latency / dt_simulation)
+    double lat_frac;           // latency / dt_simulation - lat_int
+    int ring_len;              // lat_int + 2 slots of 6 floats per experiment
+    float *obs;                // [E][8] the controller's view of the state for the next solve
+    float *ring;               // [E][ring_len][6]
+    long long pushed;          // states pushed per experiment before this launch
+    const float *ctrl_draws;   // [E] standard normal (additive) / uniform (truncnorm) draw of this period, or null: Philox
+    const float *meas_draws;   // [n_sim][E][4] standard normals of this period (angle, position, angleD, positionD), or null
+};
+
 struct FleetArgs {
+    PlantModels pm;
     OdeParams ode;              // the controller's model (L, m_pole "for controller")
     CostParams cost_up, cost_dn;  // folded for target_equilibrium = +1 / -1 (quadratic_boundary_grad selects its set)
     MppiParams mp;
@@ -179,6 +202,50 @@ __device__ __forceinline__ void plant_tick(const PlantParams &P, float *s, doubl
     s[IDX_ANGLE] = (float)plant_wrap((double)s[IDX_ANGLE]);
 }
 
+// The controller's view after `pushed` ring pushes: delayed + interpolated state (latency_adder.py:67-71), measurement
+// noise (noise_adder.py:69-84, draws n[0..3] = angle, position, angleD, positionD; null: none) and the cos / sin refresh of
+// update_vertical_angle_offset with a zero offset (CartPole/__init__.py:348-358).  float64 like the reference's buffer.
+__device__ __forceinline__ void plant_observe(const PlantModels &M, const float *ring, long long pushed, const float *n,
+                                              float *obs) {
+    const int RL = M.ring_len;
+    const int i1 = (int)(((pushed - 1 - M.lat_int) % RL + RL) % RL), i2 = (int)(((pushed - 2 - M.lat_int) % RL + RL) % RL);
+    double v[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+        const double s1 = (double)ring[i1 * 6 + c], s2 = (double)ring[i2 * 6 + c];
+        v[c] = __dadd_rn(s1, __dmul_rn(M.lat_frac, __dsub_rn(s2, s1)));
+    }
+    if (M.meas_on && n) {
+        v[IDX_ANGLE] = plant_wrap(__dadd_rn(v[IDX_ANGLE], (double)__fmul_rn(M.sig_a, n[0])));
+        v[IDX_POS] = __dadd_rn(v[IDX_POS], (double)__fmul_rn(M.sig_p, n[1]));
+        v[IDX_ANGLED] = __dadd_rn(v[IDX_ANGLED], (double)__fmul_rn(M.sig_aD, n[2]));
+        v[IDX_POSD] = __dadd_rn(v[IDX_POSD], (double)__fmul_rn(M.sig_pD, n[3]));
+    }
+    v[IDX_ANGLE] = plant_wrap(v[IDX_ANGLE]);
+    v[IDX_COS] = cos(v[IDX_ANGLE]);
+    v[IDX_SIN] = sin(v[IDX_ANGLE]);
+#pragma unroll
+    for (int c = 0; c < 6; ++c) obs[c] = (float)v[c];
+}
+
+// Philox draws of the plant-side models: counter (0xFFFFFF00 + j, 0xFFFFFFFF, period, experiment) -- disjoint from the
+// rollout draws, whose first word is a rollout index < K.  j = tick inside the period (measurement) or 0xFF (control).
+__device__ __forceinline__ uint4 plant_philox(unsigned long long seed, unsigned period, unsigned e_global, unsigned j) {
+    return philox4x32_10(make_uint4(0xFFFFFF00u + j, 0xFFFFFFFFu, period, e_global), make_uint2((unsigned)seed, (unsigned)(seed >> 32)));
+}
+
+// add_control_noise (CartPole/noise_control_signal.py:5-26): d = a standard normal (additive) or a uniform (truncnorm)
+__device__ __forceinline__ float plant_control_noise(const PlantModels &M, float Q, float d) {
+    if (M.ctrl_mode == 1) return __fadd_rn(__fadd_rn(Q, __fmul_rn(M.ctrl_mult, d)), M.ctrl_add);
+    if (M.ctrl_mode == 2) {   // truncnorm.rvs((-1 - loc) / scale, (1 - loc) / scale, loc, scale): inverse-CDF of the draw
+        const double scale = (double)M.ctrl_mult, loc = (double)Q + (double)M.ctrl_add;
+        const double ca = normcdf((-1.0 - loc) / scale), cb = normcdf((1.0 - loc) / scale);
+        const double z = normcdfinv(ca + (double)d * (cb - ca));
+        return (float)fmin(fmax(loc + scale * z, -1.0), 1.0);
+    }
+    return Q;
+}
+
 template <int INTEG, int COST, bool PHILOX, bool PAIR>
 __global__ void __launch_bounds__(256, 4) fleet_kernel(const __grid_constant__ FleetArgs a) {
     extern __shared__ float smem[];
@@ -209,7 +276,7 @@ __global__ void __launch_bounds__(256, 4) fleet_kernel(const __grid_constant__ F
     __syncthreads();
 
     SolveIO io;
-    io.s = a.replay_s ? a.replay_s + (size_t)e * 6 : a.s + (size_t)e * 8;
+    io.s = a.replay_s ? a.replay_s + (size_t)e * 6 : ((a.pm.on ? a.pm.obs : a.s) + (size_t)e * 8);
     if (PHILOX) {  // rollout k of the experiment sits at s_eps[i * per_block + (k - first rollout of this block)]
         io.noise = s_eps - (long long)blockIdx.x * per_block;
         io.ns_i = per_block; io.ns_k = 1;
@@ -244,10 +311,23 @@ __global__ void __launch_bounds__(256, 4) fleet_kernel(const __grid_constant__ F
 
     // ---- the plant: one controller period with Q held (CartPole/__init__.py:283-324, 475-527) -------------------------
     const PlantParams &P = a.plant;
+    const PlantModels &M = a.pm;
     float s[6];
 #pragma unroll
-    for (int c = 0; c < 6; ++c) s[c] = io.s[c];
-    const float Q = *io.u_out;   // written by this thread in merge_and_finish
+    for (int c = 0; c < 6; ++c) s[c] = a.s[(size_t)e * 8 + c];   // the TRUE state (io.s is the controller's view when M.on)
+    const float Qc = *io.u_out;   // written by this thread in merge_and_finish
+    float Q = Qc;
+    if (M.on && M.ctrl_mode) {
+        float d;
+        if (M.ctrl_draws) d = M.ctrl_draws[e];
+        else {
+            const uint4 r = plant_philox(a.seed, a.period, a.e_offset + (unsigned)e, 0xFFu);
+            float n0, n1;
+            box_muller(r.x, r.y, n0, n1);
+            d = (M.ctrl_mode == 1) ? n0 : ((float)(r.z >> 8) + 0.5f) * 5.9604644775390625e-8f;
+        }
+        Q = plant_control_noise(M, Qc, d);
+    }
     const float u = __fmul_rn(P.u_max, Q);
     double aDD, pDD;
     plant_ode(P, s[IDX_COS], s[IDX_SIN], s[IDX_ANGLED], s[IDX_POSD], u, aDD, pDD);
@@ -256,15 +336,49 @@ __global__ void __launch_bounds__(256, 4) fleet_kernel(const __grid_constant__ F
         r[0] = (float)a.time;
         r[1] = s[IDX_ANGLE]; r[2] = s[IDX_ANGLED]; r[3] = (float)aDD; r[4] = s[IDX_COS]; r[5] = s[IDX_SIN];
         r[6] = s[IDX_POS]; r[7] = s[IDX_POSD]; r[8] = (float)pDD;
-        r[9] = Q; r[10] = Q; r[11] = u; r[12] = tp; r[13] = te; r[14] = 0.0f; r[15] = 0.0f;
+        r[9] = Qc; r[10] = Q; r[11] = u; r[12] = tp; r[13] = te; r[14] = 0.0f; r[15] = 0.0f;
     }
+    float *ring = M.on ? M.ring + (size_t)e * M.ring_len * 6 : nullptr;
     for (int i = 0; i < P.n_sim; ++i) {
         plant_tick(P, s, aDD, pDD);
         plant_ode(P, s[IDX_COS], s[IDX_SIN], s[IDX_ANGLED], s[IDX_POSD], u, aDD, pDD);
+        if (M.on) {   // add_current_state_to_latency_buffer (latency_adder.py:36-47)
+            float *slot = ring + (size_t)((M.pushed + i) % M.ring_len) * 6;
+#pragma unroll
+            for (int c = 0; c < 6; ++c) slot[c] = s[c];
+        }
     }
     float *so = a.s + (size_t)e * 8;
 #pragma unroll
     for (int c = 0; c < 6; ++c) so[c] = s[c];
+    if (M.on) {   // what the controller will see at the start of the next period: the observation made on the last tick
+        float n[4];
+        const float *np_ = nullptr;
+        if (M.meas_on) {
+            if (M.meas_draws) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) n[q] = M.meas_draws[((size_t)(P.n_sim - 1) * gridDim.y + e) * 4 + q];
+            } else {
+                const uint4 r = plant_philox(a.seed, a.period, a.e_offset + (unsigned)e, (unsigned)(P.n_sim - 1));
+                box_muller(r.x, r.y, n[0], n[1]);
+                box_muller(r.z, r.w, n[2], n[3]);
+            }
+            np_ = n;
+        }
+        plant_observe(M, ring, M.pushed + P.n_sim, np_, M.obs + (size_t)e * 8);
+    }
+}
+
+// (Re)start of the observation chain: ring = the reference's initial buffer (zeros, cos = 1, latency_adder.py:26-28), nothing
+// pushed yet; the first solve sees the TRUE state, as the controller call of set_cartpole_state_at_t0 does
+// (CartPole/__init__.py:869-880: self.s, no noise, no latency).
+__global__ void fleet_observe_reset_kernel(PlantModels M, const float *s, int E) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    float *ring = M.ring + (size_t)e * M.ring_len * 6;
+    for (int j = 0; j < M.ring_len; ++j)
+        for (int c = 0; c < 6; ++c) ring[j * 6 + c] = (c == IDX_COS) ? 1.0f : 0.0f;
+    for (int c = 0; c < 8; ++c) M.obs[(size_t)e * 8 + c] = s[(size_t)e * 8 + c];
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------------------
@@ -277,12 +391,14 @@ struct FleetState {
     unsigned *d_tickets;
     long long period;
     CostParams cost_up, cost_dn;
+    PlantModels pm;            // plant-side models (cps_fleet_set_plant_models); pm.pushed counts the ring pushes
 };
 
 void cps_fleet_free(cps_handle *h) {
     FleetState *F = h->fleet;
     if (!F) return;
     cudaFree(F->d_s); cudaFree(F->d_unom); cudaFree(F->d_uprev); cudaFree(F->d_partials); cudaFree(F->d_tickets);
+    cudaFree(F->pm.obs); cudaFree(F->pm.ring);
     delete F;
     h->fleet = nullptr;
 }
@@ -375,6 +491,61 @@ extern "C" int cps_fleet_set_states(cps_handle *h, const float *s_host, long lon
     delete[] tmp;
     CUDA_TRY(h, er);
     F->period = period;
+    if (F->pm.on) {   // ring = the reference's initial buffer; the first solve sees the true state
+        F->pm.pushed = 0;
+        fleet_observe_reset_kernel<<<(F->E + 127) / 128, 128, 0, h->stream>>>(F->pm, F->d_s, F->E);
+        h->launches += 1;
+        CUDA_TRY(h, cudaGetLastError());
+    }
+    return CPS_OK;
+}
+
+extern "C" int cps_fleet_set_plant_models(cps_handle *h, const cps_fleet_plant_models *m) {
+    if (!h) return CPS_ERR_INVALID;
+    FleetState *F = h->fleet;
+    if (!F) return fail(h, CPS_ERR_NOT_CONFIGURED, "cps_fleet_set_plant_models: no fleet (cps_fleet_create)");
+    if (!m || m->struct_size != (int)sizeof(cps_fleet_plant_models))
+        return fail(h, CPS_ERR_INVALID, "cps_fleet_set_plant_models: cps_fleet_plant_models size mismatch");
+    if (m->control_noise_mode < 0 || m->control_noise_mode > 2) return fail(h, CPS_ERR_INVALID, "cps_fleet_set_plant_models: control_noise_mode must be 0 (OFF), 1 (additive) or 2 (truncnorm)");
+    if (m->control_noise_mode == 2 && !(m->control_noise_mult > 0.0f)) return fail(h, CPS_ERR_INVALID, "cps_fleet_set_plant_models: truncnorm needs a positive scale");
+    const double lat_len = m->latency / F->cfg.dt_simulation;
+    if (!(m->latency >= 0.0) || lat_len > 200.0)   // MAX_LATENCY_LEN (latency_adder.py:8,74-75)
+        return fail(h, CPS_ERR_INVALID, "cps_fleet_set_plant_models: latency must lie in [0, 200 plant ticks]");
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    PlantModels &M = F->pm;
+    cudaFree(M.obs); cudaFree(M.ring);
+    memset(&M, 0, sizeof(M));
+    M.ctrl_mode = m->control_noise_mode; M.ctrl_mult = m->control_noise_mult; M.ctrl_add = m->control_noise_add;
+    M.meas_on = m->measurement_noise ? 1 : 0;
+    M.sig_a = m->sigma_angle; M.sig_p = m->sigma_position; M.sig_aD = m->sigma_angleD; M.sig_pD = m->sigma_positionD;
+    M.lat_int = (int)lat_len; M.lat_frac = lat_len - (double)M.lat_int;
+    M.ring_len = M.lat_int + 2;
+    M.on = (M.ctrl_mode || M.meas_on || m->latency > 0.0) ? 1 : 0;
+    if (!M.on) return CPS_OK;
+    CUDA_TRY(h, cudaMalloc(&M.obs, sizeof(float) * (size_t)F->E * 8));
+    CUDA_TRY(h, cudaMalloc(&M.ring, sizeof(float) * (size_t)F->E * M.ring_len * 6));
+    M.pushed = 0;
+    fleet_observe_reset_kernel<<<(F->E + 127) / 128, 128, 0, h->stream>>>(M, F->d_s, F->E);
+    h->launches += 1;
+    CUDA_TRY(h, cudaGetLastError());
+    return CPS_OK;
+}
+
+extern "C" int cps_fleet_get_observed(cps_handle *h, float *obs_host) {
+    if (!h) return CPS_ERR_INVALID;
+    FleetState *F = h->fleet;
+    if (!F || !F->pm.on) return fail(h, CPS_ERR_NOT_CONFIGURED, "cps_fleet_get_observed: no plant-side models (cps_fleet_set_plant_models)");
+    if (!obs_host) return fail(h, CPS_ERR_INVALID, "cps_fleet_get_observed: null pointer");
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    float *tmp = new (std::nothrow) float[(size_t)F->E * 8];
+    if (!tmp) return fail(h, CPS_ERR_INVALID, "cps_fleet_get_observed: out of host memory");
+    cudaError_t er = cudaMemcpyAsync(tmp, F->pm.obs, sizeof(float) * (size_t)F->E * 8, cudaMemcpyDeviceToHost, h->stream);
+    if (er == cudaSuccess) er = cudaStreamSynchronize(h->stream);
+    if (er == cudaSuccess)
+        for (int e = 0; e < F->E; ++e)
+            for (int c = 0; c < 6; ++c) obs_host[(size_t)e * 6 + c] = tmp[(size_t)e * 8 + c];
+    delete[] tmp;
+    CUDA_TRY(h, er);
     return CPS_OK;
 }
 
@@ -422,7 +593,8 @@ int cps_fold_cost_for(cps_handle *h, float target_equilibrium, CostParams *out);
 // Shared by cps_fleet_step (closed loop: replay_dev == nullptr) and cps_fleet_relabel (states from a recording).
 static int fleet_launch(cps_handle *h, const char *who, int n_periods, const float *tp_dev, const float *te_dev,
                         const float *noise_dev, float *record_dev, float *J_out_dev, const float *replay_dev,
-                        const float *L_dev, const float *mp_dev, float *Q_out_dev, const int *active_dev = nullptr) {
+                        const float *L_dev, const float *mp_dev, float *Q_out_dev, const int *active_dev = nullptr,
+                        const float *ctrl_draws_dev = nullptr, const float *meas_draws_dev = nullptr) {
     FleetState *F = h->fleet;
     if (!F) return fail(h, CPS_ERR_NOT_CONFIGURED, "%s: no fleet (cps_fleet_create)", who);
     if (n_periods < 0) return fail(h, CPS_ERR_INVALID, "%s: negative number of periods / rows", who);
@@ -433,6 +605,10 @@ static int fleet_launch(cps_handle *h, const char *who, int n_periods, const flo
     FleetArgs a;
     a.ode = h->ode; a.mp = h->mp;
     a.mp.rs_off = F->rs_off;
+    a.pm = F->pm;
+    if (replay_dev) a.pm.on = 0;   // relabelling feeds recorded states: no plant, no observation chain
+    if (a.pm.on && !philox && ((a.pm.ctrl_mode && !ctrl_draws_dev) || (a.pm.meas_on && !meas_draws_dev)))
+        return fail(h, CPS_ERR_INVALID, "%s: a fleet with supplied noise needs the plant-side draws as well (cps_fleet_step_noisy)", who);
     int rc;
     if ((rc = cps_fold_cost_for(h, 1.0f, &a.cost_up)) != CPS_OK) return rc;
     if ((rc = cps_fold_cost_for(h, -1.0f, &a.cost_dn)) != CPS_OK) return rc;
@@ -468,6 +644,12 @@ static int fleet_launch(cps_handle *h, const char *who, int n_periods, const flo
         a.mp_row = mp_dev ? mp_dev + (size_t)j * E : nullptr;
         a.Q_out = Q_out_dev ? Q_out_dev + (size_t)j * E : nullptr;
         a.active = active_dev ? active_dev + (size_t)j * E : nullptr;
+        if (a.pm.on) {
+            a.pm.pushed = F->pm.pushed;
+            a.pm.ctrl_draws = ctrl_draws_dev ? ctrl_draws_dev + (size_t)j * E : nullptr;
+            a.pm.meas_draws = meas_draws_dev ? meas_draws_dev + (size_t)j * F->cfg.sim_substeps * E * 4 : nullptr;
+            F->pm.pushed += F->cfg.sim_substeps;
+        }
         a.period = (unsigned)F->period;
         a.time = (double)F->period * dt_control;
         fn<<<grid, F->block, F->smem, h->stream>>>(a);
@@ -482,6 +664,15 @@ extern "C" int cps_fleet_step(cps_handle *h, int n_periods, const float *tp_dev,
                               float *record_dev, float *J_out_dev) {
     if (!h) return CPS_ERR_INVALID;
     return fleet_launch(h, "cps_fleet_step", n_periods, tp_dev, te_dev, noise_dev, record_dev, J_out_dev, nullptr, nullptr, nullptr, nullptr);
+}
+
+extern "C" int cps_fleet_step_noisy(cps_handle *h, int n_periods, const float *tp_dev, const float *te_dev, const float *noise_dev,
+                                    float *record_dev, float *J_out_dev, const float *ctrl_draws_dev, const float *meas_draws_dev) {
+    if (!h) return CPS_ERR_INVALID;
+    if (!h->fleet || !h->fleet->pm.on)
+        return fail(h, CPS_ERR_NOT_CONFIGURED, "cps_fleet_step_noisy: no plant-side models (cps_fleet_set_plant_models)");
+    return fleet_launch(h, "cps_fleet_step_noisy", n_periods, tp_dev, te_dev, noise_dev, record_dev, J_out_dev, nullptr, nullptr, nullptr,
+                        nullptr, nullptr, ctrl_draws_dev, meas_draws_dev);
 }
 
 extern "C" int cps_fleet_relabel(cps_handle *h, int n_rows, const float *states_dev, const float *tp_dev, const float *te_dev,

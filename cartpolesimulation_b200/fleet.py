@@ -214,10 +214,38 @@ class Fleet:
         self.engine._chk(self.engine.lib.cps_fleet_noise(self.engine._h, int(period), _ptr(out)))
         return out
 
-    def run(self, n_periods: int, target_position=None, target_equilibrium=None, noise=None, record=None, J_out=None):
+    _CONTROL_NOISE = {"OFF": 0, "additive": 1, "truncnorm": 2}
+
+    def set_plant_models(self, control_noise_mode: str = "OFF", control_noise: float = 0.0, control_bias: float = 0.0,
+                         noise_mode: str = "OFF", sigma_angle: float = 0.0, sigma_position: float = 0.0,
+                         sigma_angleD: float = 0.0, sigma_positionD: float = 0.0, latency: float = 0.0):
+        """cps_fleet_set_plant_models with the reference's configuration keys (cartpole_physical_parameters.yml:13-24:
+        controlDisturbance_mode / controlDisturbance / controlBias, latency, noise.noise_mode / sigma_*).  Call before
+        reset(); the first solve after reset() sees the true state (the reference's controller call at t = 0)."""
+        if control_noise_mode not in self._CONTROL_NOISE:
+            raise ValueError(f"controlDisturbance_mode with value {control_noise_mode} not valid")
+        m = L.cps_fleet_plant_models(C.sizeof(L.cps_fleet_plant_models), self._CONTROL_NOISE[control_noise_mode],
+                                     float(control_noise), float(control_bias), 0 if noise_mode == "OFF" else 1,
+                                     float(sigma_angle), float(sigma_position), float(sigma_angleD), float(sigma_positionD),
+                                     float(latency))
+        self.engine.use_current_stream()
+        self.engine._chk(self.engine.lib.cps_fleet_set_plant_models(self.engine._h, C.byref(m)))
+        self.plant_models = bool(m.control_noise_mode or m.measurement_noise or m.latency > 0.0)
+
+    def observed(self) -> np.ndarray:
+        """[E, 6]: the states as the controller will see them at the next solve (delayed, noisy)."""
+        o = np.zeros((self.E, 6), dtype=np.float32)
+        self.engine.use_current_stream()
+        self.engine._chk(self.engine.lib.cps_fleet_get_observed(self.engine._h, o.ctypes.data_as(L._FP)))
+        return o
+
+    def run(self, n_periods: int, target_position=None, target_equilibrium=None, noise=None, record=None, J_out=None,
+            ctrl_draws=None, meas_draws=None):
         """cps_fleet_step: n_periods launches, no synchronisation.  target_position / target_equilibrium: cuda tensors
         [n_periods, E] or None; noise: cuda tensor [n_periods, E, n_ind, K] for a 'supplied' fleet;
-        record: cuda tensor [n_periods, E, 16] or None; J_out: [n_periods, E, K] or None."""
+        record: cuda tensor [n_periods, E, 16] or None; J_out: [n_periods, E, K] or None.  With plant-side models
+        (set_plant_models): ctrl_draws [n_periods, E] and meas_draws [n_periods, sim_substeps, E, 4] supply their draws
+        (cps_fleet_step_noisy); a 'philox' fleet draws them itself when they are None."""
         eng = self.engine
         eng.use_current_stream()
         for t, name, numel in ((target_position, "target_position", n_periods * self.E),
@@ -229,6 +257,13 @@ class Fleet:
                 _check_dev(t, name, self.device)
                 if t.numel() != numel:
                     raise ValueError(f"{name} has {t.numel()} elements, expected {numel}")
+        if getattr(self, "plant_models", False):
+            for t, name in ((ctrl_draws, "ctrl_draws"), (meas_draws, "meas_draws")):
+                if t is not None:
+                    _check_dev(t, name, self.device)
+            eng._chk(eng.lib.cps_fleet_step_noisy(eng._h, int(n_periods), _ptr(target_position), _ptr(target_equilibrium),
+                                                  _ptr(noise), _ptr(record), _ptr(J_out), _ptr(ctrl_draws), _ptr(meas_draws)))
+            return record
         eng._chk(eng.lib.cps_fleet_step(eng._h, int(n_periods), _ptr(target_position), _ptr(target_equilibrium),
                                         _ptr(noise), _ptr(record), _ptr(J_out)))
         return record

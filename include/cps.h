@@ -304,7 +304,7 @@ int cps_terminal_cost(cps_handle *h, const float *states_dev, int K, float *out_
  * stream; the handle's (K, T, n, integrator, cost, MPPI parameters) are shared.  The plant uses the handle's physical
  * parameters (cps_set_physics); the controller's model uses L / m_pole from cps_set_variable_parameters.
  * Control disturbance, measurement noise and latency (all off in the shipped configuration,
- * cartpole_physical_parameters.yml:13-18) are not modelled. */
+ * cartpole_physical_parameters.yml:13-24): cps_fleet_set_plant_models below. */
 #define CPS_FLEET_NOISE_SUPPLIED 0  /* caller passes standard-normal draws [period][E][n_ind][K] */
 #define CPS_FLEET_NOISE_PHILOX 1    /* drawn in the kernel: Philox4x32-10 + Box-Muller, counter = (rollout, draw group,
                                        period, experiment_offset + e), key = seed; cps_fleet_noise materialises them */
@@ -335,6 +335,35 @@ long long cps_fleet_period(const cps_handle *h);
  * it, what save_csv_routine logs at dt_save = dt_controller) or NULL; J_out_dev: [n_periods][E][K] or NULL. */
 int cps_fleet_step(cps_handle *h, int n_periods, const float *tp_dev, const float *te_dev, const float *noise_dev,
                    float *record_dev, float *J_out_dev);
+/* Plant-side models between plant and controller (CartPole/__init__.py:336-340, 523-524):
+ *   control disturbance  add_control_noise (CartPole/noise_control_signal.py:5-26): the plant is driven by
+ *                        Q_applied = Q + mult * n + add (additive, n standard normal, float32, not clipped) or by a draw of
+ *                        truncnorm(loc = Q + add, scale = mult) on [-1, 1]; the optimizer's own last control stays Q;
+ *   measurement noise    NoiseAdder.add_noise_to_measurement (CartPole/noise_adder.py:69-84): sigma * standard normal on
+ *                        angle (then wrapped), position, angleD, positionD of the state handed to the controller;
+ *   latency              LatencyAdder (CartPole/latency_adder.py:10-74): the controller sees the state `latency` seconds
+ *                        late, linearly interpolated between the two neighbouring plant ticks (ring buffer that starts as
+ *                        zeros with cos = 1); cos / sin of the observation are recomputed from its angle.
+ * The record rows keep the TRUE state (what the reference's CSV logs) with Q_calculated and Q_applied side by side.
+ * Call after cps_fleet_create; cps_fleet_set_states restarts the observation chain: empty latency buffer, and the first
+ * solve sees the true state, as the controller call at t = 0 does (CartPole/__init__.py:869-880).  Draws: a Philox fleet generates them in the
+ * kernel (counters disjoint from the rollout draws); cps_fleet_step_noisy takes them from the caller -- ctrl_draws_dev
+ * [n_periods][E] (standard normal for additive, uniform in (0, 1) for truncnorm), meas_draws_dev
+ * [n_periods][sim_substeps][E][4] standard normals per plant tick in the reference's call order (angle, position, angleD,
+ * positionD; the draws of the last tick of a period reach the controller); either may be NULL on a Philox fleet. */
+typedef struct cps_fleet_plant_models {
+    int struct_size;                 /* = sizeof(cps_fleet_plant_models) */
+    int control_noise_mode;          /* 0 OFF, 1 additive, 2 truncnorm (controlDisturbance_mode) */
+    float control_noise_mult;        /* controlDisturbance */
+    float control_noise_add;         /* controlBias */
+    int measurement_noise;           /* noise_mode != 'OFF' */
+    float sigma_angle, sigma_position, sigma_angleD, sigma_positionD;
+    double latency;                  /* seconds */
+} cps_fleet_plant_models;
+int cps_fleet_set_plant_models(cps_handle *h, const cps_fleet_plant_models *m);
+int cps_fleet_get_observed(cps_handle *h, float *obs_host /* [E][6] */);
+int cps_fleet_step_noisy(cps_handle *h, int n_periods, const float *tp_dev, const float *te_dev, const float *noise_dev,
+                         float *record_dev, float *J_out_dev, const float *ctrl_draws_dev, const float *meas_draws_dev);
 /* Offline relabelling: add_control_along_trajectories
  * (SI_Toolkit/src/SI_Toolkit/General/preprocess_data_add_control_along_trajectories.py:53-140) calls controller.step once
  * per recorded row -- `updated_attributes` first, then one solve from the recorded state -- sequentially within a file

@@ -174,6 +174,77 @@ def gen_closed_loop():
         print(f"closed_loop_{name}: {len(ctrl.calls)} solves, final state {states[-1]}")
 
 
+class SeqRng:
+    """Stands in for a numpy Generator: hands out prepared float32 standard normals in call order."""
+
+    def __init__(self, values):
+        self.v, self.i = np.asarray(values, dtype=np.float32), 0
+
+    def standard_normal(self, size=None, dtype=np.float32):
+        x = self.v[self.i]
+        self.i += 1
+        return np.float32(x) if size is None or size == () else np.full(size, x, dtype=np.float32)
+
+
+def gen_closed_loop_noisy():
+    """Closed loop with the plant-side models ON: additive control disturbance, measurement noise, 5 ms latency (2.5 plant
+    ticks) -- CartPole/noise_control_signal.py, noise_adder.py, latency_adder.py driven by the unmodified CartPole."""
+    import torch
+    import CartPole as CPmod
+    import CartPole.noise_adder as NA
+    K, T, n_ctrl = 256, 30, 20
+    n_ind = int(np.ceil((T - 1) / 10)) + 1
+    sig = dict(sigma_angle=0.01, sigma_position=0.002, sigma_angleD=0.075, sigma_positionD=0.02)
+    cases = (("noisy", 0.005, "additive", 0.1, 0.02, True), ("latency", 0.013, "OFF", 0.0, 0.0, False))
+    for name, latency, cmode, cmult, cadd, meas in cases:
+        g = torch.Generator().manual_seed(21)
+        draws = [torch.randn((K, n_ind, 1), generator=g, dtype=torch.float32) for _ in range(n_ctrl + 1)]
+        rng = np.random.default_rng(5)
+        meas_draws = rng.standard_normal((n_ctrl * 10, 4)).astype(np.float32)
+        ctrl_draws = rng.standard_normal(n_ctrl + 8).astype(np.float32)
+        ctrl = MppiController(K, T, "quadratic_boundary_grad_minimal", draws)
+        tp_f = lambda t: 0.04 * np.sin(2.0 * t)  # noqa: E731
+        saved = (CPmod.rng, CPmod.controlDisturbance_mode, float(CPmod.controlDisturbance), float(CPmod.controlBias),
+                 NA.sigma_angle, NA.sigma_position, NA.sigma_angleD, NA.sigma_positionD)
+        try:
+            CPmod.rng = SeqRng(ctrl_draws)
+            CPmod.controlDisturbance_mode = cmode
+            CPmod.controlDisturbance[...] = cmult
+            CPmod.controlBias[...] = cadd
+            NA.sigma_angle, NA.sigma_position = sig["sigma_angle"], sig["sigma_position"]
+            NA.sigma_angleD, NA.sigma_positionD = sig["sigma_angleD"], sig["sigma_positionD"]
+            cp = make_cartpole(ctrl, [np.pi - 1e-3, 0.0, 0, 0, 0.0, 0.0], tp_f, 1.0, np.inf, np.inf, length=n_ctrl * 0.02 + 1.0)
+            # make_cartpole made the controller call of t = 0 (true state); its control-noise draw is the last one consumed
+            i0 = CPmod.rng.i - 1
+            cp.NoiseAdderInstance.noise_mode = "ON" if meas else "OFF"
+            cp.NoiseAdderInstance.rng_noise_adder = SeqRng(meas_draws.reshape(-1))
+            cp.LatencyAdderInstance.dt_sampling = 0.002
+            cp.LatencyAdderInstance.set_latency(latency)
+            states, q_applied = [cp.s.copy()], [float(cp.Q_applied)]
+            for _ in range(n_ctrl * 10):
+                cp.update_state()
+                states.append(cp.s.copy())
+                q_applied.append(float(cp.Q_applied))
+        finally:
+            (CPmod.rng, CPmod.controlDisturbance_mode) = saved[0], saved[1]
+            CPmod.controlDisturbance[...] = saved[2]
+            CPmod.controlBias[...] = saved[3]
+            NA.sigma_angle, NA.sigma_position, NA.sigma_angleD, NA.sigma_positionD = saved[4:]
+        meta = dict(entry="CartPole.update_state + optimizer_mppi.step with add_control_noise / NoiseAdder / LatencyAdder "
+                          "(CartPole/__init__.py:336-340,523-524)", K=K, T=T, cost="quadratic_boundary_grad_minimal",
+                    latency=latency, control_noise_mode=cmode, control_noise=cmult, control_bias=cadd,
+                    measurement_noise=bool(meas), **sig)
+        np.savez_compressed(
+            os.path.join(GOLDEN, f"closed_loop_{name}.npz"), eps=np.stack([d.numpy()[:, :, 0] for d in draws]).astype(np.float32),
+            states=np.array(states, np.float32), ctrl_s=np.array([c[0] for c in ctrl.calls], np.float32),
+            ctrl_time=np.array([c[1] for c in ctrl.calls]), ctrl_tp=np.array([c[2] for c in ctrl.calls]),
+            ctrl_te=np.array([c[3] for c in ctrl.calls], np.float32), Q=np.array(ctrl.us, np.float32),
+            Q_applied_tick=np.array(q_applied, np.float32), u_nom=np.array(ctrl.u_noms, np.float32),
+            meas_draws=meas_draws, ctrl_draws=ctrl_draws[i0:i0 + n_ctrl + 1], meta=json.dumps(meta))
+        print(f"closed_loop_{name}: {len(ctrl.calls)} solves, max |observed - true| = "
+              f"{np.abs(np.array([c[0] for c in ctrl.calls])[1:] - np.array(states)[10::10][:len(ctrl.calls) - 1]).max():.4f}")
+
+
 def gen_datagen():
     """Host-side pieces of the data generator: generate_random_initial_state (CartPole/data_generator.py:238-275) and
     Generate_Random_Trace_Function (CartPole/random_target_generator.py:9-87) with seeded numpy Generators."""
@@ -205,6 +276,9 @@ def gen_datagen():
 if __name__ == "__main__":
     R.load()
     os.makedirs(GOLDEN, exist_ok=True)
+    if "noisy" in sys.argv[1:]:   # only the plant-side-model fixtures
+        gen_closed_loop_noisy()
+        raise SystemExit(0)
     gen_plant()
     gen_datagen()
     if "--no-closed-loop" not in sys.argv:

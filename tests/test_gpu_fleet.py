@@ -286,3 +286,70 @@ def test_fleet_full_size_is_independent_of_the_sharding():
         fl.run(P, tp_d[:, lo:hi].contiguous(), te_d[:, lo:hi].contiguous(), record=r)
         np.testing.assert_array_equal(r.cpu().numpy(), rec[:, lo:hi])
         fl.close()
+
+
+@pytest.mark.parametrize("case", ["noisy", "latency"])
+def test_fleet_plant_side_models_reproduce_reference(case):
+    """Control disturbance, measurement noise and latency (CartPole/noise_control_signal.py, noise_adder.py,
+    latency_adder.py; all OFF in the shipped configuration) against the unmodified CartPole + optimizer_mppi in closed loop
+    with the models ON and every draw injected: what the controller saw in every period (delayed, interpolated, noisy),
+    the control it chose, the control the plant received, and the true state."""
+    from cartpolesimulation_b200.fleet import Fleet
+    z, m = load_golden(f"closed_loop_{case}")
+    K, T = m["K"], m["T"]
+    P = len(z["Q"]) - 1
+    fl = Fleet(1, K, T, integrator="ODE", cost=m["cost"], noise="supplied")
+    fl.set_plant_models(control_noise_mode=m["control_noise_mode"], control_noise=m["control_noise"], control_bias=m["control_bias"],
+                        noise_mode="ON" if m["measurement_noise"] else "OFF", sigma_angle=m["sigma_angle"],
+                        sigma_position=m["sigma_position"], sigma_angleD=m["sigma_angleD"], sigma_positionD=m["sigma_positionD"],
+                        latency=m["latency"])
+    fl.reset(z["states"][0:1].copy())
+    np.testing.assert_array_equal(fl.observed()[0], z["states"][0])     # t = 0: the controller sees the true state
+    eps = torch.from_numpy(np.ascontiguousarray(z["eps"][:P].transpose(0, 2, 1))[:, None]).cuda().contiguous()  # [P,1,n_ind,K]
+    tp = torch.from_numpy(z["ctrl_tp"][:P].astype(np.float32)[:, None].copy()).cuda()
+    te = torch.from_numpy(z["ctrl_te"][:P].astype(np.float32)[:, None].copy()).cuda()
+    meas = torch.from_numpy(z["meas_draws"].reshape(P, 10, 1, 4).copy()).cuda()
+    cd = torch.from_numpy(z["ctrl_draws"][:P].reshape(P, 1).copy()).cuda()
+    rec = torch.zeros((P, 1, 16), device="cuda")
+    obs = []
+    for j in range(P):
+        fl.run(1, tp[j:j + 1], te[j:j + 1], eps[j:j + 1], rec[j:j + 1], ctrl_draws=cd[j:j + 1], meas_draws=meas[j:j + 1])
+        obs.append(fl.observed()[0])
+    rec = rec.cpu().numpy()[:, 0]
+    assert state_err(np.array(obs), z["ctrl_s"][1:P + 1]) < 2e-5               # the controller's view, period by period
+    np.testing.assert_allclose(rec[:, 9], z["Q"][:P], rtol=0, atol=1e-4)       # Q_calculated (north_star: 1e-4)
+    np.testing.assert_allclose(rec[:, 10], z["Q_applied_tick"][0:10 * P:10], rtol=0, atol=1e-4)   # what drove the plant
+    assert state_err(rec[:, [1, 2, 4, 5, 6, 7]], z["states"][0:10 * P:10]) < 2e-5   # the TRUE state stays in the record
+    assert state_err(fl.states()[0], z["states"][10 * P]) < 2e-5
+    if case == "noisy":
+        assert np.abs(np.array(obs) - z["states"][10:10 * P + 1:10]).max() > 1e-2   # the view really differs from the truth
+    fl.close()
+
+
+def test_fleet_plant_side_models_philox_and_errors():
+    """A Philox fleet draws the plant-side noise itself, reproducibly and independently of the sharding; truncnorm keeps
+    the applied control inside [-1, 1]; a supplied-noise fleet refuses to run without the plant-side draws."""
+    from cartpolesimulation_b200.fleet import Fleet
+    E, K, T, P = 4, 128, 20, 6
+    ang = np.array([3.0, 0.2, -1.0, 2.0])
+    s0 = np.stack([ang, np.zeros(E), np.cos(ang), np.sin(ang), np.zeros(E), np.zeros(E)], 1).astype(np.float32)
+    kw = dict(control_noise_mode="truncnorm", control_noise=0.5, control_bias=0.0, noise_mode="ON", sigma_angle=0.01,
+              sigma_position=0.002, sigma_angleD=0.05, sigma_positionD=0.02, latency=0.004)
+    recs = []
+    for off, sl in ((0, slice(0, 4)), (0, slice(0, 4)), (2, slice(2, 4))):
+        fl = Fleet(sl.stop - sl.start, K, T, noise="philox", seed=3, experiment_offset=off)
+        fl.set_plant_models(**kw)
+        fl.reset(s0[sl])
+        rec = torch.zeros((P, sl.stop - sl.start, 16), device="cuda")
+        fl.run(P, record=rec)
+        recs.append(rec.cpu().numpy())
+        fl.close()
+    np.testing.assert_array_equal(recs[0], recs[1])            # reproducible
+    np.testing.assert_array_equal(recs[0][:, 2:4], recs[2])    # streams keyed by the global experiment index
+    assert np.abs(recs[0][:, :, 10]).max() <= 1.0 and np.abs(recs[0][:, :, 10] - recs[0][:, :, 9]).max() > 0.05
+    fl = Fleet(1, K, T, noise="supplied")
+    fl.set_plant_models(**kw)
+    fl.reset(s0[:1])
+    with pytest.raises(Exception):
+        fl.run(1, noise=torch.zeros((1, 1, fl.n_ind, K), device="cuda"))
+    fl.close()
