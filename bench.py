@@ -414,7 +414,9 @@ def neural_latency(device, n_calls=300):
     flops = net_flops_per_step(spec) * K * T
     kms = float(np.median(ks))
     out = {"latency_ms_median": float(np.median(lat) * 1e3), "latency_ms_p99": float(np.percentile(lat, 99) * 1e3),
-           "kernel_ms_median": kms, "net_steps_per_s": K * T / (kms * 1e-3), "fp32_tflops": flops / (kms * 1e-3) / 1e12,
+           "kernel_ms_median": kms,
+           "kernel_ms_in_stream": float(np.median(_stream_times(lambda: eng.mppi_step(s, noise, 1, 0.0)))),
+           "net_steps_per_s": K * T / (kms * 1e-3), "fp32_tflops": flops / (kms * 1e-3) / 1e12,
            "flop_per_solve": flops,
            "api": "cps_mppi_step_host (numpy s -> float u); kernel: %s" % {"tensor": "net_tc_kernel<MPPI> (tcgen05)", "fp32": "net_kernel<16,64,MPPI> (FP32)"}.get(eng.net_last_kernel(), "?")}
     try:  # the same solve by the CPU oracle port (C, OpenMP), once, on the host cores

@@ -132,6 +132,11 @@ SYMBOLS = {
     "cps_cem_gmm_get_distribution": (C.c_int, [_VP, _FP, _FP, _FP]),
     "cps_cem_gmm_set_distribution": (C.c_int, [_VP, _FP, _FP, _FP]),
     "cps_measure_peaks": (C.c_int, [_VP, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "cps_plan_cost_grad": (C.c_int, [_VP, _VP, _VP, C.c_int, C.c_float, _VP, _VP]),
+    "cps_rpgd_reset": (C.c_int, [_VP]),
+    "cps_rpgd_grad_step": (C.c_int, [_VP, _VP, _VP] + [C.c_float] * 6 + [_VP]),
+    "cps_rpgd_adam_state": (C.c_int, [_VP, C.POINTER(_VP), C.POINTER(_VP), C.POINTER(C.c_longlong)]),
+    "cps_rpgd_set_iterations": (C.c_int, [_VP, C.c_longlong]),
     "cps_launch_count": (C.c_longlong, [_VP]),
     "cps_net_last_kernel": (C.c_int, [_VP]),
     "cps_rollout_last_kernel": (C.c_int, [_VP]),

@@ -602,6 +602,53 @@ class Engine:
             return a.ctypes.data_as(L._FP)
         self._chk(self.lib.cps_cem_gmm_set_distribution(self._h, arr(loc, 2 * self.T), arr(scale, 2 * self.T), arr(p1, 1)))
 
+    # -- gradient of predict_and_cost, RPGD --------------------------------------------------------------------
+    def plan_cost_grad(self, s, Q, q_layout=L.ROLLOUT_MAJOR, u_prev=0.0, want_J=True):
+        """cps_plan_cost_grad: (J [K] or None, dJ/dQ in the layout of Q) as cuda tensors (no synchronisation)."""
+        self.use_current_stream()
+        _check_dev(s, "s", self.device)
+        _check_dev(Q, "Q", self.device)
+        if self._q_dims(Q, q_layout) != (self.K, self.T):
+            raise ValueError(f"Q has shape {tuple(Q.shape)}, expected K = {self.K}, T = {self.T}")
+        G = torch.empty_like(Q)
+        J = torch.empty(self.K, device=self.device) if want_J else None
+        self._chk(self.lib.cps_plan_cost_grad(self._h, _ptr(s), _ptr(Q), q_layout, float(u_prev), _ptr(J), _ptr(G)))
+        return J, G
+
+    def rpgd_reset(self):
+        self.use_current_stream()
+        self._chk(self.lib.cps_rpgd_reset(self._h))
+
+    def rpgd_grad_step(self, s, Q, u_prev=0.0, learning_rate=0.05, beta_1=0.9, beta_2=0.999, epsilon=1e-8, gradmax_clip=5.0,
+                       J_out=None):
+        """cps_rpgd_grad_step: gradient, clip_by_norm, Adam, clip to the limits -- in place on Q [K, T] (rollout-major)."""
+        self.use_current_stream()
+        _check_dev(s, "s", self.device)
+        _check_dev(Q, "Q", self.device)
+        if tuple(Q.shape[:2]) != (self.K, self.T) or not Q.is_contiguous():
+            raise ValueError(f"Q must be a contiguous [{self.K}, {self.T}] tensor")
+        self._chk(self.lib.cps_rpgd_grad_step(self._h, _ptr(s), _ptr(Q), float(u_prev), float(learning_rate), float(beta_1),
+                                              float(beta_2), float(epsilon), float(gradmax_clip), _ptr(J_out)))
+
+    def rpgd_adam_state(self):
+        """(m, v, iterations): the Adam moments as cuda tensors [K, T] aliasing the handle's buffers."""
+        m, v, it = C.c_void_p(), C.c_void_p(), C.c_longlong()
+        self._chk(self.lib.cps_rpgd_adam_state(self._h, C.byref(m), C.byref(v), C.byref(it)))
+        if not hasattr(self, "_adam_views") or self._adam_views[2] != (m.value, v.value):
+            import ctypes
+
+            def view(ptr):
+                n = self.K * self.T
+                # a non-owning tensor over the handle's buffer (CUDA array interface)
+                class _Buf:
+                    __cuda_array_interface__ = {"shape": (self.K, self.T), "typestr": "<f4", "data": (ptr, False), "version": 2}
+                return torch.as_tensor(_Buf(), device=self.device)
+            self._adam_views = (view(m.value), view(v.value), (m.value, v.value))
+        return self._adam_views[0], self._adam_views[1], int(it.value)
+
+    def rpgd_set_iterations(self, n: int):
+        self._chk(self.lib.cps_rpgd_set_iterations(self._h, int(n)))
+
     def measure_peaks(self):
         """(FP32 TFLOP/s, MUFU Gop/s) measured on this device by two microbenchmark kernels."""
         self.use_current_stream()

@@ -1,0 +1,320 @@
+// cps_grad.cu -- the gradient of predict_and_cost with respect to the input plans, and the RPGD update built on it.
+//
+// The reference's gradient-based optimizers (RPGD is its shipped default, Control_Toolkit_ASF/config_controllers.yml:2;
+// Control_Toolkit/Optimizers/optimizer_rpgd_tf.py:167-180) wrap
+//     rollout_trajectory = predictor.predict_core(s, Q);  traj_cost = cost_function.get_trajectory_cost(traj, Q, u)
+// in a tf.GradientTape and take d(traj_cost)/dQ [K][T]: reverse-mode differentiation through T x n Euler-Cromer substeps
+// (SI_Toolkit/Predictors/predictor_ODE.py, CartPole/cartpole_equations.py:71-99, 245-262) and the cost plugin, with the
+// [K][T+1][6] trajectory and the tape in between.  Here it is ONE launch: every thread owns a plan,
+//   forward   integrates it (cos / sin from the angle every substep, as the reference's graph does), accumulates the cost
+//             and leaves a checkpoint (angle, angleD, position, positionD) per control step in a [T][4][K] workspace
+//             (coalesced: consecutive plans are consecutive addresses);
+//   backward  walks the control steps in reverse: re-integrates the n substeps of the step from its checkpoint keeping
+//             their inputs in local memory, then sweeps them backwards with the hand-derived adjoint of the substep
+//             (oracle/oracle.py:plan_cost_grad is the same derivation in numpy, checked against torch autograd through the
+//             unmodified reference modules, tests/golden/grad_*.npz), adding the cost plugin's partial derivatives at the
+//             control-step boundaries.
+// rpgd_update_kernel is the rest of grad_step (:176-180): tf.clip_by_norm per plan, the Adam step (Keras legacy Adam =
+// ResourceApplyAdam) and the clip to the control limits.
+// Cost plugin: quadratic_boundary_grad_minimal (the plugin the shipped RPGD configuration uses); predictor "ODE".
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstring>
+#include <new>
+
+#include "cps_internal.cuh"
+
+#define CPS_GRAD_MAX_SUBSTEPS 32
+
+struct GradState {
+    float *d_ck;        // [T][4][K] checkpoints
+    float *d_J;         // [K]
+    float *d_G;         // [K][T]
+    float *d_m, *d_v;   // Adam moments [K][T]
+    long long adam_iterations;
+};
+
+struct GradArgs {
+    OdeParams ode;
+    CostParams cost;
+    const float *s;
+    float s_inline[6];
+    int use_inline;
+    const float *Q;
+    long long qs_k, qs_t;
+    int K, T;
+    float inv_T1;
+    float *ck, *J, *G;
+    long long gs_k, gs_t;
+    int *nonfinite;
+};
+
+namespace {
+
+struct Sub { float th, w, v; };
+
+// One Euler-Cromer substep of predictor_ODE with cos / sin taken from the angle (cartpole_equations.py:71-99, 245-262).
+__device__ __forceinline__ void grad_substep(const OdeParams &P, float &th, float &w, float &x, float &v, float uk) {
+    float sn, c;
+    sincosf(th, &sn, &c);
+    const float rA = rcp_pos<false>(fmaf(-P.m_p, c * c, P.KM));
+    const float t1 = fmaf(-P.c2, w * w, P.c1 * c);
+    const float num = fmaf(sn, t1, fmaf(-(P.c3 * w), c, fmaf(-P.c5, v, uk)));
+    const float xDD = num * rA;
+    const float thDD = fmaf(P.d1, sn, fmaf(P.d2 * xDD, c, -P.d3 * w));
+    w = fmaf(thDD, P.h, w);
+    v = fmaf(xDD, P.h, v);
+    th = fold_angle(fmaf(w, P.h, th));
+    x = fmaf(v, P.h, x);
+}
+
+// quadratic_boundary_grad_minimal (Control_Toolkit_ASF/Cost_Functions/CartPole/quadratic_boundary_grad_minimal.py:62-130);
+// w: [dd_q, db, ep, ekp, cc*R, bf = f thl, 1/((1-f) thl)] as in stage_cost<COST_GRADMIN>.
+__device__ __forceinline__ void gradmin_partials(const CostParams &C, float th, float w, float x, float &d_th, float &d_w,
+                                                 float &d_x) {
+    float sn, c;
+    sincosf(th, &sn, &c);
+    const float dist = (x - C.target_position) * C.inv_2thl;
+    const float apos = fabsf(x);
+    const float over = (apos > C.w[5]) ? (apos - C.w[5]) * C.w[6] : 0.0f;
+    d_x = fmaf(C.w[0] * 2.0f * dist, C.inv_2thl, C.w[1] * 2.0f * over * C.w[6] * copysignf(1.0f, x));
+    d_th = C.w[2] * 2.0f * (1.0f - C.target_equilibrium * c) * (C.target_equilibrium * sn);
+    d_w = 2.0f * C.w[3] * w;
+}
+
+__global__ void __launch_bounds__(128) plan_grad_kernel(const __grid_constant__ GradArgs a) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= a.K) return;
+    const OdeParams &P = a.ode;
+    const CostParams &C = a.cost;
+    const int T = a.T, n = P.n, K = a.K;
+    const float *s0 = a.use_inline ? a.s_inline : a.s;
+    float th = s0[IDX_ANGLE], w = s0[IDX_ANGLED], x = s0[IDX_POS], v = s0[IDX_POSD];
+    const float *q = a.Q + (long long)k * a.qs_k;
+    float *ck = a.ck + k;
+
+    // ---- forward: cost and checkpoints ---------------------------------------------------------------------------------------
+    float Jacc = 0.0f;
+#pragma unroll 1
+    for (int t = 0; t < T; ++t) {
+        const float u = q[(long long)t * a.qs_t];
+        ck[((long long)t * 4 + 0) * K] = th; ck[((long long)t * 4 + 1) * K] = w;
+        ck[((long long)t * 4 + 2) * K] = x;  ck[((long long)t * 4 + 3) * K] = v;
+        Jacc += stage_cost<COST_GRADMIN>(C, cosf(th), w, x, u, 0.0f);
+        const float uk = P.u_scale * u;
+#pragma unroll 1
+        for (int i = 0; i < n; ++i) grad_substep(P, th, w, x, v, uk);
+    }
+    const float J = __fdiv_rn(Jacc, (float)(T + 1));   // the plugin's terminal cost is zero
+    if (a.J) a.J[k] = J;
+    if (!isfinite(J)) atomicAdd(a.nonfinite, 1);
+
+    // ---- backward ----------------------------------------------------------------------------------------------------------------
+    float a_th = 0.0f, a_w = 0.0f, a_x = 0.0f, a_v = 0.0f;
+    float *g = a.G + (long long)k * a.gs_k;
+    Sub sub[CPS_GRAD_MAX_SUBSTEPS];
+#pragma unroll 1
+    for (int t = T - 1; t >= 0; --t) {
+        th = ck[((long long)t * 4 + 0) * K]; w = ck[((long long)t * 4 + 1) * K];
+        x = ck[((long long)t * 4 + 2) * K];  v = ck[((long long)t * 4 + 3) * K];
+        const float th0 = th, w0 = w, x0 = x;
+        const float u = q[(long long)t * a.qs_t];
+        const float uk = P.u_scale * u;
+#pragma unroll 1
+        for (int i = 0; i < n; ++i) {
+            sub[i].th = th; sub[i].w = w; sub[i].v = v;
+            grad_substep(P, th, w, x, v, uk);
+        }
+        float a_uk = 0.0f;
+#pragma unroll 1
+        for (int i = n - 1; i >= 0; --i) {
+            const float thi = sub[i].th, wi = sub[i].w, vi = sub[i].v;
+            float sn, c;
+            sincosf(thi, &sn, &c);
+            const float rA = rcp_pos<false>(fmaf(-P.m_p, c * c, P.KM));
+            const float t1 = fmaf(-P.c2, wi * wi, P.c1 * c), t4 = P.c3 * wi;
+            const float num = fmaf(sn, t1, fmaf(-t4, c, fmaf(-P.c5, vi, uk)));
+            const float xDD = num * rA;
+            const float a_v2 = fmaf(P.h, a_x, a_v);            // x' = x + h v'
+            const float a_w2 = fmaf(P.h, a_th, a_w);           // th' = th + h w'
+            const float a_thDD = P.h * a_w2;                   // w' = w + h thDD
+            float a_xDD = fmaf(P.d2 * c, a_thDD, P.h * a_v2);  // v' = v + h xDD; thDD = d1 s + d2 xDD c - d3 w
+            float a_s = P.d1 * a_thDD;
+            float a_c = P.d2 * xDD * a_thDD;
+            float a_win = fmaf(-P.d3, a_thDD, a_w2);
+            const float a_num = rA * a_xDD, a_rA = num * a_xDD;          // xDD = num rA
+            a_c = fmaf(2.0f * P.m_p * c * rA * rA, a_rA, a_c);             // rA = 1 / (KM - m_p c^2)
+            a_s = fmaf(t1, a_num, a_s);                                    // num = s t1 - t4 c + (uk - c5 v)
+            const float a_t1 = sn * a_num, a_t4 = -c * a_num;
+            a_c = fmaf(-t4, a_num, a_c);
+            a_c = fmaf(P.c1, a_t1, a_c);                                   // t1 = c1 c - c2 w^2
+            a_win = fmaf(-2.0f * P.c2 * wi, a_t1, fmaf(P.c3, a_t4, a_win));
+            a_uk += a_num;
+            a_v = fmaf(-P.c5, a_num, a_v2);
+            a_th = fmaf(c, a_s, fmaf(-sn, a_c, a_th));                     // c = cos th, s = sin th
+            a_w = a_win;
+        }
+        g[(long long)t * a.gs_t] = fmaf(P.u_scale, a_uk, a.inv_T1 * 2.0f * C.w[4] * u);
+        float d_th, d_w, d_x;
+        gradmin_partials(C, th0, w0, x0, d_th, d_w, d_x);
+        a_th = fmaf(a.inv_T1, d_th, a_th);
+        a_w = fmaf(a.inv_T1, d_w, a_w);
+        a_x = fmaf(a.inv_T1, d_x, a_x);
+    }
+}
+
+// grad_step after the tape (optimizer_rpgd_tf.py:176-180): clip_by_norm over the plan, Adam, clip to the limits.
+// One warp per plan.
+struct RpgdArgs {
+    float *Q; const float *G; float *m, *v;
+    int K, T;
+    float clip_norm, lr_t, beta1, beta2, eps, lo, hi;
+};
+__global__ void __launch_bounds__(128) rpgd_update_kernel(const __grid_constant__ RpgdArgs a) {
+    const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (k >= a.K) return;
+    const float *g = a.G + (long long)k * a.T;
+    float ss = 0.0f;
+    for (int t = lane; t < a.T; t += 32) ss = fmaf(g[t], g[t], ss);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float l2 = sqrtf(ss);
+    const float scale = a.clip_norm / fmaxf(l2, a.clip_norm);   // tf.clip_by_norm: t * clip_norm / max(l2norm, clip_norm)
+    for (int t = lane; t < a.T; t += 32) {
+        const long long i = (long long)k * a.T + t;
+        const float gi = g[t] * scale;
+        const float m = fmaf(a.beta1, a.m[i], (1.0f - a.beta1) * gi);
+        const float v = fmaf(a.beta2, a.v[i], (1.0f - a.beta2) * gi * gi);
+        a.m[i] = m; a.v[i] = v;
+        const float qn = a.Q[i] - a.lr_t * m / (sqrtf(v) + a.eps);
+        a.Q[i] = fminf(fmaxf(qn, a.lo), a.hi);
+    }
+}
+
+}  // namespace
+
+void cps_grad_free(cps_handle *h) {
+    GradState *G = h->grad;
+    if (!G) return;
+    cudaFree(G->d_ck); cudaFree(G->d_J); cudaFree(G->d_G); cudaFree(G->d_m); cudaFree(G->d_v);
+    delete G;
+    h->grad = nullptr;
+}
+
+static int grad_state(cps_handle *h, GradState **out) {
+    if (h->grad) { *out = h->grad; return CPS_OK; }
+    if (h->cfg.integrator != CPS_EULER_CROMER)
+        return fail(h, CPS_ERR_UNSUPPORTED, "cps_plan_cost_grad: the adjoint is built for predictor \"ODE\" (Euler-Cromer)");
+    if (h->cfg.cost_id != CPS_COST_QB_GRAD_MINIMAL)
+        return fail(h, CPS_ERR_UNSUPPORTED, "cps_plan_cost_grad: the adjoint is built for the quadratic_boundary_grad_minimal plugin");
+    if (h->cfg.substeps > CPS_GRAD_MAX_SUBSTEPS)
+        return fail(h, CPS_ERR_UNSUPPORTED, "cps_plan_cost_grad: at most 32 substeps per control step");
+    GradState *G = new (std::nothrow) GradState();
+    if (!G) return fail(h, CPS_ERR_INVALID, "cps_plan_cost_grad: out of host memory");
+    memset(G, 0, sizeof(*G));
+    const size_t K = h->cfg.num_rollouts, T = h->cfg.horizon;
+    cudaError_t e = cudaMalloc(&G->d_ck, sizeof(float) * 4 * K * T);
+    if (e == cudaSuccess) e = cudaMalloc(&G->d_J, sizeof(float) * K);
+    if (e == cudaSuccess) e = cudaMalloc(&G->d_G, sizeof(float) * K * T);
+    if (e == cudaSuccess) e = cudaMalloc(&G->d_m, sizeof(float) * K * T);
+    if (e == cudaSuccess) e = cudaMalloc(&G->d_v, sizeof(float) * K * T);
+    if (e == cudaSuccess) e = cudaMemset(G->d_m, 0, sizeof(float) * K * T);
+    if (e == cudaSuccess) e = cudaMemset(G->d_v, 0, sizeof(float) * K * T);
+    if (e != cudaSuccess) {
+        cudaFree(G->d_ck); cudaFree(G->d_J); cudaFree(G->d_G); cudaFree(G->d_m); cudaFree(G->d_v);
+        delete G;
+        return fail(h, CPS_ERR_CUDA, "cps_plan_cost_grad: allocating the workspace: %s", cudaGetErrorString(e));
+    }
+    h->grad = G;
+    *out = G;
+    return CPS_OK;
+}
+
+extern "C" int cps_plan_cost_grad(cps_handle *h, const float *s_dev, const float *Q_dev, int q_layout, float u_prev,
+                                  float *J_out_dev, float *G_out_dev) {
+    if (!h) return CPS_ERR_INVALID;
+    if (!s_dev || !Q_dev || !G_out_dev) return fail(h, CPS_ERR_INVALID, "cps_plan_cost_grad: null pointer");
+    (void)u_prev;   // quadratic_boundary_grad_minimal has no control-change term
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    GradState *G;
+    int rc = grad_state(h, &G);
+    if (rc != CPS_OK) return rc;
+    const int K = h->cfg.num_rollouts, T = h->cfg.horizon;
+    GradArgs a;
+    memset(&a, 0, sizeof(a));
+    a.ode = h->ode; a.cost = h->cost;
+    a.s = s_dev;
+    a.use_inline = h->inline_s ? 1 : 0;
+    for (int c = 0; c < 6; ++c) a.s_inline[c] = h->inline_s ? h->inline_s[c] : 0.0f;
+    a.Q = Q_dev;
+    if (q_layout == CPS_TIME_MAJOR) { a.qs_k = 1; a.qs_t = K; a.gs_k = 1; a.gs_t = K; }
+    else { a.qs_k = T; a.qs_t = 1; a.gs_k = T; a.gs_t = 1; }
+    a.K = K; a.T = T;
+    a.inv_T1 = 1.0f / (float)(T + 1);
+    a.ck = G->d_ck; a.J = J_out_dev ? J_out_dev : G->d_J; a.G = G_out_dev;
+    a.nonfinite = h->d_nonfinite;
+    const int block = (K <= 148 * 32) ? 32 : 128;   // small K: one warp per block spreads the plans over the SMs
+    plan_grad_kernel<<<(K + block - 1) / block, block, 0, h->stream>>>(a);
+    h->launches += 1;
+    CUDA_TRY(h, cudaGetLastError());
+    return CPS_OK;
+}
+
+extern "C" int cps_rpgd_reset(cps_handle *h) {
+    if (!h) return CPS_ERR_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    GradState *G;
+    int rc = grad_state(h, &G);
+    if (rc != CPS_OK) return rc;
+    const size_t n = (size_t)h->cfg.num_rollouts * h->cfg.horizon;
+    CUDA_TRY(h, cudaMemsetAsync(G->d_m, 0, sizeof(float) * n, h->stream));
+    CUDA_TRY(h, cudaMemsetAsync(G->d_v, 0, sizeof(float) * n, h->stream));
+    G->adam_iterations = 0;
+    return CPS_OK;
+}
+
+extern "C" int cps_rpgd_grad_step(cps_handle *h, const float *s_dev, float *Q_dev, float u_prev, float learning_rate, float beta_1,
+                                  float beta_2, float epsilon, float gradmax_clip, float *J_out_dev) {
+    if (!h) return CPS_ERR_INVALID;
+    if (!s_dev || !Q_dev) return fail(h, CPS_ERR_INVALID, "cps_rpgd_grad_step: null pointer");
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    GradState *G;
+    int rc = grad_state(h, &G);
+    if (rc != CPS_OK) return rc;
+    if ((rc = cps_plan_cost_grad(h, s_dev, Q_dev, CPS_ROLLOUT_MAJOR, u_prev, J_out_dev, G->d_G)) != CPS_OK) return rc;
+    G->adam_iterations += 1;
+    const double t = (double)G->adam_iterations;
+    RpgdArgs a;
+    a.Q = Q_dev; a.G = G->d_G; a.m = G->d_m; a.v = G->d_v;
+    a.K = h->cfg.num_rollouts; a.T = h->cfg.horizon;
+    a.clip_norm = gradmax_clip;
+    a.lr_t = (float)((double)learning_rate * sqrt(1.0 - pow((double)beta_2, t)) / (1.0 - pow((double)beta_1, t)));   // ResourceApplyAdam
+    a.beta1 = beta_1; a.beta2 = beta_2; a.eps = epsilon;
+    a.lo = h->mppi_in[5]; a.hi = h->mppi_in[6];
+    rpgd_update_kernel<<<(a.K + 3) / 4, 128, 0, h->stream>>>(a);
+    h->launches += 1;
+    CUDA_TRY(h, cudaGetLastError());
+    return CPS_OK;
+}
+
+extern "C" int cps_rpgd_adam_state(cps_handle *h, float **m_dev, float **v_dev, long long *iterations) {
+    if (!h) return CPS_ERR_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    GradState *G;
+    int rc = grad_state(h, &G);
+    if (rc != CPS_OK) return rc;
+    if (m_dev) *m_dev = G->d_m;
+    if (v_dev) *v_dev = G->d_v;
+    if (iterations) *iterations = G->adam_iterations;
+    return CPS_OK;
+}
+
+extern "C" int cps_rpgd_set_iterations(cps_handle *h, long long iterations) {
+    if (!h || iterations < 0) return CPS_ERR_INVALID;
+    GradState *G;
+    int rc = grad_state(h, &G);
+    if (rc != CPS_OK) return rc;
+    G->adam_iterations = iterations;
+    return CPS_OK;
+}

@@ -67,6 +67,7 @@ struct NetState;    // cps_net.cu
 struct FleetState;  // cps_fleet.cu
 struct PlanState;   // cps_plan.cu
 struct GmmState;    // cps_gmm.cu
+struct GradState;   // cps_grad.cu
 
 struct cps_handle {
     cps_config cfg;
@@ -111,6 +112,7 @@ struct cps_handle {
     FleetState *fleet;  // closed-loop experiments (cps_fleet_create), owned
     PlanState *plan;    // forward-only planners (cps_plan_*, cps_cem_*), owned
     GmmState *gmm;      // CEM with a Gaussian-mixture sampling distribution (cps_cem_gmm_*), owned
+    GradState *grad;    // adjoint workspace and Adam moments (cps_plan_cost_grad, cps_rpgd_*), owned
 };
 
 extern thread_local std::string g_create_err;
@@ -134,6 +136,8 @@ void cps_fleet_free(cps_handle *h);
 void cps_plan_free(cps_handle *h);
 // cps_gmm.cu
 void cps_gmm_free(cps_handle *h);
+// cps_grad.cu
+void cps_grad_free(cps_handle *h);
 // cps_lib.cu: cost parameters folded for a given target equilibrium
 int cps_fold_cost_for(cps_handle *h, float target_equilibrium, CostParams *out);
 // cps_net.cu

@@ -453,6 +453,27 @@ int cps_cem_gmm_set_distribution(cps_handle *h, const float *loc_host, const flo
  * (dense FFMA chains; MUFU.EX2 chains): FP32 TFLOP/s (FMA = 2 flops) and MUFU Gop/s.  Synchronises. */
 int cps_measure_peaks(cps_handle *h, double *fp32_tflops, double *mufu_gops);
 
+/* ---- gradient of predict_and_cost; RPGD ----------------------------------------------------------------- */
+/* The reference's gradient-based optimizers take d(traj_cost)/dQ with a tf.GradientTape around predict_and_cost
+ * (Control_Toolkit/Optimizers/optimizer_rpgd_tf.py:167-175; RPGD is the shipped default optimizer,
+ * Control_Toolkit_ASF/config_controllers.yml:2).  cps_plan_cost_grad is that derivative in one launch: forward rollout with a
+ * checkpoint per control step, backward sweep with the hand-derived adjoint of the Euler-Cromer substep and of the cost
+ * plugin.  Q_dev [K][T] (or [T][K] with CPS_TIME_MAJOR) for the handle's K and T; J_out_dev [K] (or NULL) the costs,
+ * G_out_dev the gradient in the layout of Q.  Predictor "ODE" with cos / sin from the angle every substep (the arithmetic
+ * the reference differentiates), cost quadratic_boundary_grad_minimal (the shipped RPGD configuration); anything else:
+ * CPS_ERR_UNSUPPORTED.
+ * cps_rpgd_grad_step is grad_step (:166-180) on the device: the gradient, tf.clip_by_norm over each plan (gradmax_clip), one
+ * Adam step (Keras legacy Adam: lr_t = lr sqrt(1 - b2^t) / (1 - b1^t), m, v per element, handle-owned, t = iterations since
+ * cps_rpgd_reset) and the clip to the control limits, in place on Q_dev [K][T].  cps_rpgd_adam_state exposes the device
+ * buffers of m and v ([K][T]) and the iteration count for the warm-start bookkeeping of step() (:297-356). */
+int cps_plan_cost_grad(cps_handle *h, const float *s_dev, const float *Q_dev, int q_layout, float u_prev, float *J_out_dev,
+                       float *G_out_dev);
+int cps_rpgd_reset(cps_handle *h);
+int cps_rpgd_grad_step(cps_handle *h, const float *s_dev, float *Q_dev, float u_prev, float learning_rate, float beta_1,
+                       float beta_2, float epsilon, float gradmax_clip, float *J_out_dev);
+int cps_rpgd_adam_state(cps_handle *h, float **m_dev, float **v_dev, long long *iterations);
+int cps_rpgd_set_iterations(cps_handle *h, long long iterations);
+
 /* ---- diagnostics ------------------------------------------------------------------------------------- */
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches claim). */
 long long cps_launch_count(const cps_handle *h);
