@@ -274,7 +274,43 @@ def planner_latency(device, n_calls=300):
         rec["cpu_port_threads"] = O.lib().cps_oracle_num_threads()
         out[name] = rec
         opt.engine.close()
-    out["api"] = "optimizer_cem_b200 / optimizer_random_action_b200 .step(numpy s) -> numpy u (cps_cem_step_host, cps_plan_random_action_host; plan_kernel)"
+    # the reference's shipped default optimizer: RPGD at its shipped configuration (config_optimizers.yml:63-85: 16 plans x 35
+    # steps, 4 Adam steps on the adjoint's gradient per solve), and CEM-GMM at its shipped 200 x 35 x 3
+    from cartpolesimulation_b200.optimizer_forward_b200 import optimizer_cem_gmm_b200, optimizer_rpgd_b200
+    for name, cls, K, T, kw in (("rpgd_16x35_it4", optimizer_rpgd_b200, 16, 35, dict(outer_its=4)),
+                                ("rpgd_2000x50_it4", optimizer_rpgd_b200, 2000, 50, dict(outer_its=4)),
+                                ("cem_gmm_200x35_it3", optimizer_cem_gmm_b200, 200, 35, dict(cem_outer_it=3, cem_best_k=40))):
+        try:
+            vp = cps.VariableParameters(target_position=0.0, target_equilibrium=1.0, L=0.395, m_pole=0.087)
+            cost, pred = cps.CostFunctionWrapper(), cps.PredictorWrapper()
+            opt = cls(predictor=pred, cost_function=cost, control_limits=lim, seed=1, mpc_horizon=T, num_rollouts=K, device=device, **kw)
+            pred.configure(batch_size=K, horizon=T, dt=0.02, variable_parameters=vp, predictor_specification="ODE")
+            cost.configure(batch_size=K, horizon=T, variable_parameters=vp, environment_name="CartPole",
+                           computation_library=None, cost_function_specification="quadratic_boundary_grad_minimal")
+            opt.configure(num_states=6, num_control_inputs=1, dt=0.02, predictor_specification="ODE")
+            for _ in range(20):
+                opt.step(s)
+            lat = []
+            for _ in range(n_calls):
+                t0 = time.perf_counter()
+                opt.step(s)
+                lat.append((time.perf_counter() - t0) * 1e3)
+            n0 = opt.engine.launch_count()
+            opt.step(s)
+            rec = {"latency_ms_median": float(np.median(lat)), "latency_ms_p99": float(np.percentile(lat, 99)),
+                   "launches_per_solve": opt.engine.launch_count() - n0, "calls": n_calls}
+            if cls is optimizer_rpgd_b200:   # the adjoint kernel alone
+                import torch
+                Q = torch.zeros((K, T), device=opt.device).uniform_(-0.5, 0.5)
+                s_dev = torch.from_numpy(s).to(opt.device)
+                rec["grad_kernel_ms_in_stream"] = float(np.median(_stream_times(lambda: opt.engine.plan_cost_grad(s_dev, Q))))
+                rec["state_steps_per_grad"] = K * T * N_SUB
+            out[name] = rec
+            opt.engine.close()
+        except Exception as ex:
+            out[name] = {"error": repr(ex)}
+    out["api"] = ("optimizer_cem_b200 / optimizer_cem_gmm_b200 / optimizer_random_action_b200 / optimizer_rpgd_b200 .step(numpy s) -> numpy u "
+                  "(cps_cem_step_host, cps_cem_gmm_step_host, cps_plan_random_action_host, cps_rpgd_grad_step; plan_kernel, plan_grad_kernel)")
     return out
 
 

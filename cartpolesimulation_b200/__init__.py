@@ -8,7 +8,7 @@ from . import _lib
 from ._lib import CpsError, build, library_path
 from .config import DEFAULT_COST_CONFIG, DEFAULT_MPPI_CONFIG, DEFAULT_PHYSICS, cost_vector, physics_vector
 
-__all__ = ["Engine", "optimizer_mppi_b200", "optimizer_cem_b200", "optimizer_cem_gmm_b200", "optimizer_random_action_b200", "PredictorWrapper", "predictor_ODE", "predictor_ODE_v0",
+__all__ = ["Engine", "optimizer_mppi_b200", "optimizer_cem_b200", "optimizer_cem_gmm_b200", "optimizer_rpgd_b200", "optimizer_random_action_b200", "PredictorWrapper", "predictor_ODE", "predictor_ODE_v0",
            "CostFunctionWrapper", "CpsError", "build", "library_path", "VariableParameters"]
 
 
@@ -34,7 +34,7 @@ def __getattr__(name):  # lazy: importing the package must not need torch.cuda o
     if name == "optimizer_mppi_b200":
         from .optimizer_mppi_b200 import optimizer_mppi_b200
         return optimizer_mppi_b200
-    if name in ("optimizer_cem_b200", "optimizer_cem_gmm_b200", "optimizer_random_action_b200"):
+    if name in ("optimizer_cem_b200", "optimizer_cem_gmm_b200", "optimizer_rpgd_b200", "optimizer_random_action_b200"):
         from . import optimizer_forward_b200
         return getattr(optimizer_forward_b200, name)
     if name in ("PredictorWrapper", "predictor_ODE", "predictor_ODE_v0"):

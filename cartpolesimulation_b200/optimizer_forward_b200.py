@@ -322,3 +322,125 @@ class optimizer_cem_gmm_b200(_forward_optimizer):
 
     def optimizer_reset(self):
         self.engine.cem_gmm_reset()
+
+
+class optimizer_rpgd_b200(_forward_optimizer):
+    """optimizer_rpgd_tf (Control_Toolkit/Optimizers/optimizer_rpgd_tf.py:15-420; `rpgd` is the reference's shipped
+    default optimizer, Control_Toolkit_ASF/config_controllers.yml:2): resampling parallel gradient descent.  K input plans
+    are improved by `outer_its` Adam steps on d(traj_cost)/dQ, the cheapest plan's first input is applied, all plans are
+    shifted by `shift_previous` as the next warm start, and every `resamp_per` solves the worst K - opt_keep_k plans are
+    replaced by fresh samples (their Adam moments zeroed, the kept ones' shifted).
+
+    The gradient -- a GradientTape around predict_and_cost in the reference -- is one adjoint kernel launch
+    (cps_rpgd_grad_step: gradient, clip_by_norm, Adam, clip to the limits); the plans and the Adam moments stay on the
+    device, the per-solve bookkeeping of step() (:297-356: argsort of K costs, gather, shift) is a handful of torch index
+    operations on those device tensors.  Predictor "ODE", cost quadratic_boundary_grad_minimal (the shipped configuration);
+    no CPU fallback."""
+
+    def __init__(self, predictor, cost_function, control_limits, computation_library=None, seed=None,
+                 mpc_horizon: int = 35, num_rollouts: int = 16, outer_its: int = 4, sample_stdev: float = 0.5,
+                 sample_mean: float = 0.0, sample_whole_control_space: bool = False, uniform_dist_min: float = -0.8,
+                 uniform_dist_max: float = 0.8, resamp_per: int = 10, period_interpolation_inducing_points: int = 4,
+                 SAMPLING_DISTRIBUTION: str = "normal", shift_previous: int = 1, warmup: bool = False,
+                 warmup_iterations: int = 250, learning_rate: float = 0.05, opt_keep_k_ratio: float = 0.75,
+                 gradmax_clip: float = 5.0, rtol: float = 1e-3, adam_beta_1: float = 0.9, adam_beta_2: float = 0.999,
+                 adam_epsilon: float = 1e-8, optimizer_logging: bool = False, calculate_optimal_trajectory: bool = False,
+                 device=None, **kwargs):
+        super().__init__(predictor=predictor, cost_function=cost_function, control_limits=control_limits,
+                         computation_library=computation_library, seed=seed, mpc_horizon=mpc_horizon,
+                         num_rollouts=num_rollouts, optimizer_logging=optimizer_logging,
+                         calculate_optimal_trajectory=calculate_optimal_trajectory, device=device)
+        if SAMPLING_DISTRIBUTION not in ("normal", "uniform"):
+            raise ValueError(f"RPGD cannot interpret sampling type {SAMPLING_DISTRIBUTION}")
+        self.outer_its, self.sample_stdev, self.sample_mean = int(outer_its), float(sample_stdev), float(sample_mean)
+        if sample_whole_control_space:
+            self.sample_min, self.sample_max = float(self.action_low[0]), float(self.action_high[0])
+        else:
+            self.sample_min, self.sample_max = float(uniform_dist_min), float(uniform_dist_max)
+        self.resamp_per, self.shift_previous = int(resamp_per), int(shift_previous)
+        self.period_interpolation_inducing_points = int(period_interpolation_inducing_points)
+        self.SAMPLING_DISTRIBUTION = SAMPLING_DISTRIBUTION
+        self.first_iter_count = int(warmup_iterations) if warmup else self.outer_its
+        self.opt_keep_k = int(max(int(self.num_rollouts * opt_keep_k_ratio), 1))
+        self.learning_rate, self.gradmax_clip, self.rtol = float(learning_rate), float(gradmax_clip), float(rtol)
+        self.adam_beta_1, self.adam_beta_2, self.adam_epsilon = float(adam_beta_1), float(adam_beta_2), float(adam_epsilon)
+        self.calculate_optimal_trajectory = bool(calculate_optimal_trajectory)
+        self.optimal_trajectory = self.optimal_control_sequence = self.u_nom = None
+        self.count = 0
+
+    def _configure_engine(self):
+        K, T, p = self.num_rollouts, self.mpc_horizon, self.period_interpolation_inducing_points
+        n_ind = int(self.engine.lib.cps_num_inducing_points(T, p))
+        # Interpolator.calculate_interpolation_matrix (Control_Toolkit/others/Interpolator.py:54-78): tent weights, the last
+        # inducing point enters its own step with weight 1 / p
+        W = np.zeros(((n_ind - 1) * p + 1, n_ind), dtype=np.float32)
+        for i in range(n_ind - 1):
+            for j in range(p):
+                W[i * p + j, i], W[i * p + j, i + 1] = p - j, j
+        W[-1, -1] = 1
+        self._W = torch.from_numpy((W[:T] / np.float32(p)).T.copy()).to(self.device)   # [n_ind, T]
+        self.number_of_interpolation_inducing_points = n_ind
+        self.Q_tf = torch.zeros((K, T), device=self.device)
+        self.trajectory_ages = torch.zeros(K, dtype=torch.int32, device=self.device)
+
+    def sample_actions(self, batch_size: int):
+        """:149-171: draws at the inducing points, clipped, then interpolated over the horizon."""
+        n_ind = self.number_of_interpolation_inducing_points
+        if self.SAMPLING_DISTRIBUTION == "normal":
+            if self.rng is self._own_rng:
+                Qn = self.rng.normal((batch_size, n_ind)) * self.sample_stdev + self.sample_mean
+            else:
+                Qn = torch.as_tensor(self.rng.normal([batch_size, n_ind, 1], mean=self.sample_mean, stddev=self.sample_stdev,
+                                                     dtype=torch.float32)).reshape(batch_size, n_ind)
+        else:
+            Qn = torch.as_tensor(self.rng.uniform([batch_size, n_ind, 1], minval=self.sample_min, maxval=self.sample_max,
+                                                  dtype=torch.float32)).reshape(batch_size, n_ind)
+        Qn = Qn.to(device=self.device, dtype=torch.float32).clamp(float(self.action_low[0]), float(self.action_high[0]))
+        return Qn @ self._W
+
+    def step(self, s: np.ndarray, time=None):
+        s = self._state(s)
+        K, T, keep = self.num_rollouts, self.mpc_horizon, self.opt_keep_k
+        s_dev = torch.from_numpy(s).to(self.device)
+        u_prev = float(np.asarray(self.u).reshape(-1)[0])
+        for _ in range(self.first_iter_count if self.count == 0 else self.outer_its):   # grad_step (:166-180)
+            self.engine.rpgd_grad_step(s_dev, self.Q_tf, u_prev, self.learning_rate, self.adam_beta_1, self.adam_beta_2,
+                                       self.adam_epsilon, self.gradmax_clip)
+        # get_action (:182-224): costs of the improved plans, the best opt_keep_k of them, the shifted warm start
+        J = self.engine.plan_cost(s_dev, self.Q_tf, L.ROLLOUT_MAJOR, u_prev)[0]
+        best_idx = torch.sort(J, stable=True).indices[:keep]
+        self.u_nom = self.Q_tf[best_idx[0]].clone().reshape(1, T, 1)
+        sp = self.shift_previous
+        Qn = torch.cat([self.Q_tf[:, sp:], self.Q_tf[:, -1:].repeat(1, sp)], dim=1)
+        if self.optimizer_logging:
+            self._u_prev_logged = self.u
+            self._log_rollouts(s, self.Q_tf)
+            self.logging_values["trajectory_ages_logged"] = self.trajectory_ages.cpu().numpy()
+        self.optimal_control_sequence = self.u_nom.cpu().numpy()
+        m, v, _ = self.engine.rpgd_adam_state()
+        zeros = torch.zeros((K, 1), device=self.device)
+        if self.count % self.resamp_per == 0:   # :299-343: the worst plans are redrawn, the kept ones sorted by cost
+            Qn = torch.cat([self.sample_actions(K - keep), Qn[best_idx]], dim=0)
+            self.trajectory_ages = torch.cat([torch.zeros(K - keep, dtype=torch.int32, device=self.device),
+                                              self.trajectory_ages[best_idx]])
+            fresh = torch.zeros((K - keep, T), device=self.device)
+            m.copy_(torch.cat([fresh, torch.cat([m[best_idx][:, 1:], zeros[:keep]], dim=1)], dim=0))
+            v.copy_(torch.cat([fresh, torch.cat([v[best_idx][:, 1:], zeros[:keep]], dim=1)], dim=0))
+        else:                                   # :344-356: every plan keeps its moments, shifted by one step
+            m.copy_(torch.cat([m[:, 1:], zeros], dim=1))
+            v.copy_(torch.cat([v[:, 1:], zeros], dim=1))
+        self.trajectory_ages += 1
+        self.Q_tf.copy_(Qn)
+        self.count += 1
+        if self.calculate_optimal_trajectory:
+            traj, _ = self.engine.rollout(s_dev, self.u_nom.reshape(1, T))
+            self.optimal_trajectory = traj.cpu().numpy()
+        self.u = np.array(float(self.u_nom[0, 0, 0]), dtype=np.float32)
+        return self.u
+
+    def optimizer_reset(self):
+        """:379-408: fresh plans, Adam moments and iteration count zeroed."""
+        self.Q_tf.copy_(self.sample_actions(self.num_rollouts))
+        self.count = 0
+        self.engine.rpgd_reset()
+        self.trajectory_ages.zero_()

@@ -6,7 +6,7 @@ installed here, so the handful of tf.* ops these two files call is supplied by o
 the optimizers' own Python runs as is, on the reference's torch predictor_ODE (or numba predictor_ODE_v0) and the
 reference's cost plugins, with the generator's draws injected so that the CUDA path can be fed the same numbers.
 
-    python oracle/gen_golden_plan.py [ra] [cem] [gmm]      (default: gmm)
+    python oracle/gen_golden_plan.py [ra] [cem] [gmm] [rpgd]      (default: gmm)
 """
 from __future__ import annotations
 
@@ -28,7 +28,7 @@ from oracle import ref_loader as R  # noqa: E402
 from oracle.gen_golden import hanging_state, make_states, save  # noqa: E402
 
 
-def _make(cls_name, pred, cost, K, T, tp, te, **params):
+def _make(cls_name, pred, cost, K, T, tp, te, rng=None, configure_kw=None, **params):
     import importlib
     import torch
     from SI_Toolkit.computation_library import TensorFlowLibrary
@@ -43,8 +43,8 @@ def _make(cls_name, pred, cost, K, T, tp, te, **params):
               control_limits=(np.array([-1.0], dtype=np.float32), np.array([1.0], dtype=np.float32)),
               computation_library=TensorFlowLibrary(), seed=1, mpc_horizon=T, num_rollouts=K,
               optimizer_logging=True, calculate_optimal_trajectory=False, **params)
-    opt.rng = tf_shim.InjectedDraws([torch.zeros(K, T, 1)])  # optimizer_reset of random-action draws once
-    opt.configure(num_states=6, num_control_inputs=1)
+    opt.rng = rng if rng is not None else tf_shim.InjectedDraws([torch.zeros(K, T, 1)])  # optimizer_reset of random-action draws once
+    opt.configure(num_states=6, num_control_inputs=1, **(configure_kw or {}))
     return opt
 
 
@@ -144,6 +144,51 @@ def gen_cem_gmm():
              loc=np.stack(LOC), scale=np.stack(SC), p1=np.array(P1))
 
 
+def gen_rpgd():
+    """optimizer_rpgd_tf (:15-420) on the shim: torch autograd stands in for the GradientTape, _LegacyAdam for Keras' Adam."""
+    import zlib
+    import torch
+    from oracle import oracle as O
+    runs = [  # name, K, T, steps, outer_its, resamp_per, keep ratio, period of the inducing points, tp, te
+        ("rpgd_default", 16, 35, 12, 4, 10, 0.75, 4, 0.0, 1.0),      # the shipped configuration (config_optimizers.yml:63-85)
+        ("rpgd_resamp3", 24, 20, 8, 2, 3, 0.5, 5, 0.05, 1.0),
+    ]
+    for (name, K, T, steps, its, resamp, ratio, p, tp, te) in runs:
+        rng = np.random.default_rng(zlib.crc32(name.encode()))
+        n_ind = int(np.ceil((T - 1) / p)) + 1
+        keep = int(max(int(K * ratio), 1))
+        n_resamp = sum(1 for c in range(steps) if c % resamp == 0)
+        draws = [rng.standard_normal((K, n_ind, 1)).astype(np.float32)] + \
+                [rng.standard_normal((K - keep, n_ind, 1)).astype(np.float32) for _ in range(n_resamp)]
+        opt = _make("optimizer_rpgd_tf", "ODE", "quadratic_boundary_grad_minimal", K, T, tp, te,
+                    rng=tf_shim.InjectedDraws(draws), configure_kw=dict(dt=0.02, predictor_specification="ODE"),   # optimizer_reset: first draw
+                    outer_its=its, sample_stdev=0.5,
+                    sample_mean=0.0, sample_whole_control_space=False, uniform_dist_min=-0.8, uniform_dist_max=0.8,
+                    resamp_per=resamp, period_interpolation_inducing_points=p, SAMPLING_DISTRIBUTION="normal",
+                    shift_previous=1, warmup=False, warmup_iterations=250, learning_rate=0.05, opt_keep_k_ratio=ratio,
+                    gradmax_clip=5, rtol=1e-3, adam_beta_1=0.9, adam_beta_2=0.999, adam_epsilon=1e-8)
+        s = hanging_state()
+        S, U, JJ, QQ, UP, QN, M1, V1, IT = [], [], [], [], [], [], [], [], []
+        for i in range(steps):
+            UP.append(np.float32(np.asarray(opt.u).reshape(-1)[0]))
+            u = opt.step(s.copy())
+            S.append(s.copy()); U.append(np.float32(np.asarray(u).reshape(-1)[0]))
+            JJ.append(opt.logging_values["J_logged"].astype(np.float32))
+            QQ.append(opt.logging_values["Q_logged"][:, :, 0].astype(np.float32))      # plans after the gradient steps
+            QN.append(opt.Q_tf.detach().numpy()[:, :, 0].astype(np.float32).copy())      # warm start for the next solve
+            w = opt.opt.get_weights()
+            IT.append(int(w[0])); M1.append(w[1].numpy()[:, :, 0].copy()); V1.append(w[2].numpy()[:, :, 0].copy())
+            s = O.rollout("ODE", s, np.array([[float(np.asarray(u).reshape(-1)[0])]], dtype=np.float32))[0, 1]
+        save("plan_" + name, dict(ref="Control_Toolkit/Optimizers/optimizer_rpgd_tf.py:149-408 (tf ops, GradientTape and Keras "
+                                      "legacy Adam from oracle/tf_shim.py; injected normal draws)", predictor="ODE",
+                                  cost="quadratic_boundary_grad_minimal", K=K, T=T, steps=steps, outer_its=its, resamp_per=resamp,
+                                  opt_keep_k_ratio=ratio, period_interpolation_inducing_points=p, learning_rate=0.05,
+                                  gradmax_clip=5.0, sample_stdev=0.5, target_position=tp, target_equilibrium=te),
+             draw0=draws[0][:, :, 0], resamp_draws=np.stack([d[:, :, 0] for d in draws[1:]]), s=np.stack(S), u=np.array(U),
+             J=np.stack(JJ), Q=np.stack(QQ), Q_next=np.stack(QN), u_prev=np.array(UP), adam_m=np.stack(M1), adam_v=np.stack(V1),
+             adam_iterations=np.array(IT))
+
+
 def main():
     if not R.available():
         raise SystemExit("reference tree not available; fixtures can only be regenerated in the build container")
@@ -151,7 +196,7 @@ def main():
     # the ra_* / cem_* fixtures were drawn with per-process seeds (salted str hash): they carry their own inputs and stay
     # valid recordings, but regenerating them gives different draws -- pass their names to regenerate deliberately
     which = set(sys.argv[1:]) or {"gmm"}
-    fns = [f for f, tag in ((gen_random_action, "ra"), (gen_cem, "cem"), (gen_cem_gmm, "gmm")) if tag in which]
+    fns = [f for f, tag in ((gen_random_action, "ra"), (gen_cem, "cem"), (gen_cem_gmm, "gmm"), (gen_rpgd, "rpgd")) if tag in which]
     for fn in fns:
         with contextlib.redirect_stdout(io.StringIO()) as buf:
             try:

@@ -11,6 +11,9 @@ only the ~15 `tf.*` ops it calls are supplied here, on torch CPU float32 tensors
   tf.convert_to_tensor, tf.constant, tf.ensure_shape: their numpy namesakes.
   optimizer_cem_gmm_tf additionally: tf.norm, tf.transpose, tf.argmin (first of equal minima), tf.cast, tf.shape, tf.stack,
   and tensorflow_probability's Normal / Categorical / MixtureSameFamily (sample, mean, stddev) with injected draws.
+  optimizer_rpgd_tf additionally: tf.Variable (a torch leaf tensor with .assign), tf.GradientTape (torch autograd),
+  tf.clip_by_norm, tf.keras.optimizers.legacy.Adam (ResourceApplyAdam's update rule), tf.range / tf.linalg.matmul /
+  tf.math.ceil for the Interpolator.
 Everything else resolves to an inert stub so that `TensorFlowLibrary()` (SI_Toolkit/computation_library.py:306-...) can
 be constructed; none of those attributes is called on this path.  What this pins is the optimizer LOGIC of the
 reference, not TensorFlow's kernels (the summation order inside reduce_mean / reduce_std is TF's own; the parity
@@ -81,6 +84,80 @@ def _reduce_std(x, axis=None, keepdims=False):
     return torch.sqrt(v)
 
 
+def _variable(x, **kw):
+    """tf.Variable: a leaf tensor that records gradients and can be assigned in place."""
+    v = _t(x, torch.float32).detach().clone().requires_grad_(True)
+    v.assign = lambda val: _assign(v, val)
+    return v
+
+
+def _assign(v, val):
+    # a NEW storage: slices taken from the variable earlier (torch views; copies in TF) keep the values they were taken with
+    v.data = _t(val).detach().clone()
+    return v
+
+
+class _GradientTape:
+    """d(sum(target)) / d(source) by torch autograd: what tape.gradient returns for a vector target, each entry of which
+    depends on one row of the source (optimizer_rpgd_tf.py:169-175)."""
+
+    def __init__(self, **kw):
+        pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+    def watch(self, x):
+        pass
+
+    def gradient(self, target, source):
+        return torch.autograd.grad(target.sum(), source)[0]
+
+
+def _clip_by_norm(t, clip_norm, axes=None):
+    """tf.clip_by_norm: t * clip_norm / max(l2norm(t, axes), clip_norm)."""
+    t = _t(t)
+    l2 = torch.sqrt(torch.sum(t * t, dim=tuple(axes), keepdim=True))
+    c = _t(clip_norm, torch.float32)
+    return t * c / torch.maximum(l2, c)
+
+
+class _LegacyAdam:
+    """tf.keras.optimizers.legacy.Adam for ONE variable (ResourceApplyAdam): weights = [iterations, m, v];
+    lr_t = lr sqrt(1 - b2^t) / (1 - b1^t), m = b1 m + (1 - b1) g, v = b2 v + (1 - b2) g^2, var -= lr_t m / (sqrt(v) + eps)."""
+
+    def __init__(self, learning_rate=0.001, beta_1=0.9, beta_2=0.999, epsilon=1e-7, **kw):
+        self.lr, self.b1, self.b2, self.eps = float(learning_rate), float(beta_1), float(beta_2), float(epsilon)
+        self.iterations, self.m, self.v = 0, None, None
+
+    def get_weights(self):
+        if self.m is None:
+            return []
+        return [np.int64(self.iterations), self.m.clone(), self.v.clone()]
+
+    def set_weights(self, w):
+        if not w:
+            return
+        self.iterations = int(w[0])
+        self.m, self.v = _t(w[1], torch.float32).clone(), _t(w[2], torch.float32).clone()
+
+    def apply_gradients(self, grads_and_vars):
+        for g, var in grads_and_vars:
+            g = _t(g).detach()
+            if self.m is None:
+                self.m, self.v = torch.zeros_like(g), torch.zeros_like(g)
+            self.iterations += 1
+            t = float(self.iterations)
+            lr_t = np.float32(self.lr * np.sqrt(1.0 - self.b2 ** t) / (1.0 - self.b1 ** t))
+            self.m = self.b1 * self.m + (1.0 - self.b1) * g
+            self.v = self.b2 * self.v + (1.0 - self.b2) * g * g
+            with torch.no_grad():
+                var.sub_(lr_t * self.m / (torch.sqrt(self.v) + self.eps))
+
+
 def install():
     """Put the shim into sys.modules as `tensorflow` (before oracle.ref_loader.load()).  Idempotent."""
     cur = sys.modules.get("tensorflow")
@@ -112,8 +189,35 @@ def install():
     tf.cast = lambda x, dtype=None: _t(x).to(dtype) if isinstance(x, torch.Tensor) else torch.as_tensor(x, dtype=dtype)
     tf.shape = lambda x: torch.as_tensor(list(_t(x).shape))
     tf.stack = lambda xs, axis=0: torch.stack([_t(x, torch.float32) for x in xs], dim=axis)
+    # tf tensors hand out numpy copies whether or not a tape watches them
+    if not getattr(torch.Tensor.numpy, "_cps_detaching", False):
+        _orig_numpy = torch.Tensor.numpy
+
+        def _numpy(self, *a, **k):
+            return _orig_numpy(self.detach(), *a, **k).copy()   # tf hands out copies; torch would alias the variable
+        _numpy._cps_detaching = True
+        torch.Tensor.numpy = _numpy
+    # optimizer_rpgd_tf: variables, the gradient tape, clip_by_norm, Keras' legacy Adam; Interpolator through TensorFlowLibrary
+    tf.__version__ = "2.11.0"
+    tf.Variable = _variable
+    tf.GradientTape = _GradientTape
+    tf.clip_by_norm = _clip_by_norm
+    tf.zeros_like = lambda x, dtype=None: torch.zeros_like(_t(x))
+    tf.range = lambda *a, **k: torch.arange(*[int(v) for v in a])
+    tf.function = lambda f=None, **k: (f if f is not None else (lambda g: g))
+    linalg = _Mod("tensorflow.linalg")
+    linalg.matmul = lambda a, b: torch.matmul(_t(a), _t(b))
+    tf.linalg = linalg
+    keras = _Mod("tensorflow.keras")
+    opts = _Mod("tensorflow.keras.optimizers")
+    legacy = _Mod("tensorflow.keras.optimizers.legacy")
+    legacy.Adam = opts.Adam = _LegacyAdam
+    opts.legacy = legacy
+    keras.optimizers = opts
+    tf.keras = keras
     math = _Mod("tensorflow.math")
     math.reduce_std = _reduce_std
+    math.ceil = lambda x: float(np.ceil(x))
     tf.math = math
     sys.modules["tensorflow"] = tf
     sys.modules["tensorflow.math"] = math
@@ -186,8 +290,11 @@ class InjectedDraws:
         assert [int(v) for v in shape] == list(d.shape), (list(shape), d.shape)
         return d
 
-    def normal(self, shape, dtype=None, **kw):
-        return self._next(shape)
+    def normal(self, shape, mean=0.0, stddev=1.0, dtype=None, **kw):
+        d = self._next(shape)
+        if float(stddev) != 1.0 or float(mean) != 0.0:   # tf.random.Generator.normal(shape, mean, stddev)
+            d = d * _t(stddev, torch.float32) + _t(mean, torch.float32)
+        return d
 
     def uniform(self, shape, minval=None, maxval=None, dtype=None, **kw):
         return self._next(shape)

@@ -94,3 +94,99 @@ def test_gradient_rejects_other_configurations():
         eng = _engine(8, 5, integ=integ, cost=cost)
         with pytest.raises(NotImplementedError):
             eng.plan_cost_grad(torch.zeros(6, device="cuda"), torch.zeros((8, 5), device="cuda"), L.ROLLOUT_MAJOR, 0.0)
+
+
+RPGD = ["plan_rpgd_default", "plan_rpgd_resamp3"]
+
+
+class _Draws:
+    def __init__(self, draws):
+        self.draws, self.i = list(draws), 0
+
+    def normal(self, shape, mean=0.0, stddev=1.0, dtype=None):
+        d = self.draws[self.i]
+        self.i += 1
+        assert list(d.shape) == list(shape)
+        return d * stddev + mean
+
+
+def _make_rpgd(m, draws, logging=False):
+    import cartpolesimulation_b200 as cps
+    from cartpolesimulation_b200.optimizer_forward_b200 import optimizer_rpgd_b200
+    vp = cps.VariableParameters(target_position=m["target_position"], target_equilibrium=m["target_equilibrium"], L=0.395,
+                                m_pole=0.087)
+    cost, predictor = cps.CostFunctionWrapper(), cps.PredictorWrapper()
+    opt = optimizer_rpgd_b200(predictor=predictor, cost_function=cost,
+                              control_limits=(np.array([-1.0], np.float32), np.array([1.0], np.float32)), seed=1,
+                              mpc_horizon=m["T"], num_rollouts=m["K"], outer_its=m["outer_its"], resamp_per=m["resamp_per"],
+                              opt_keep_k_ratio=m["opt_keep_k_ratio"], optimizer_logging=logging,
+                              period_interpolation_inducing_points=m["period_interpolation_inducing_points"],
+                              learning_rate=m["learning_rate"], gradmax_clip=m["gradmax_clip"], sample_stdev=m["sample_stdev"])
+    predictor.configure(batch_size=m["K"], horizon=m["T"], dt=0.02, variable_parameters=vp, predictor_specification="ODE")
+    cost.configure(batch_size=m["K"], horizon=m["T"], variable_parameters=vp, environment_name="CartPole",
+                   computation_library=None, cost_function_specification=m["cost"])
+    opt.configure(num_states=6, num_control_inputs=1, default_configure=False, dt=0.02, predictor_specification="ODE")
+    opt.rng = _Draws(draws)
+    opt.optimizer_reset()
+    return opt
+
+
+@pytest.mark.parametrize("name", RPGD)
+def test_optimizer_rpgd_b200_matches_reference(name):
+    """optimizer_rpgd_b200.step against recordings of the UNMODIFIED optimizer_rpgd_tf (tests/golden/plan_rpgd_*.npz): every
+    solve starts from the reference's recorded state (plans, Adam moments, counters), so a near-tie in the cost order cannot
+    compound; compared: the plans after the gradient steps, the control, the warm start with its resampled rows, the
+    re-sorted and shifted Adam moments."""
+    z, m = load_golden(name)
+    K, T = m["K"], m["T"]
+    draws = [torch.from_numpy(z["draw0"][:, :, None].copy())] + [torch.from_numpy(d[:, :, None].copy()) for d in z["resamp_draws"]]
+    opt = _make_rpgd(m, draws, logging=True)
+    W = opt._W.cpu().numpy()
+    np.testing.assert_allclose(opt.Q_tf.cpu().numpy(), np.clip(z["draw0"] * m["sample_stdev"], -1, 1) @ W, rtol=0, atol=1e-6)
+    for i in range(m["steps"]):
+        u = opt.step(z["s"][i].copy())
+        assert isinstance(u, np.ndarray) and u.dtype == np.float32
+        Q_opt = opt.logging_values["Q_logged"][:, :, 0]
+        eQ, eu = float(np.abs(Q_opt - z["Q"][i]).max()), abs(float(u) - float(z["u"][i]))
+        record("optimizer_rpgd", f"{name}/{i}", Q=eQ, u=eu)
+        assert eQ < 2e-4
+        assert eu < 1e-4                                              # north_star: selected control within 1e-4
+        np.testing.assert_allclose(opt.Q_tf.cpu().numpy(), z["Q_next"][i], rtol=0, atol=2e-4)
+        mm, vv, it = opt.engine.rpgd_adam_state()
+        assert it == int(z["adam_iterations"][i])
+        np.testing.assert_allclose(mm.cpu().numpy(), z["adam_m"][i], rtol=0, atol=2e-4 * max(1.0, np.abs(z["adam_m"][i]).max()))
+        np.testing.assert_allclose(vv.cpu().numpy(), z["adam_v"][i], rtol=0, atol=2e-4 * max(1.0, np.abs(z["adam_v"][i]).max()))
+        # restart the next solve from the reference's own state
+        opt.Q_tf.copy_(torch.from_numpy(z["Q_next"][i]).cuda())
+        mm.copy_(torch.from_numpy(z["adam_m"][i]).cuda())
+        vv.copy_(torch.from_numpy(z["adam_v"][i]).cuda())
+    assert opt.optimizer_name == "rpgd-b200" and opt.count == m["steps"]
+
+
+def test_optimizer_rpgd_b200_free_running_and_own_rng():
+    """Free running (its own state from solve to solve) the control follows the reference over the first solves, and with
+    its own seeded generator two instances agree; a solve lowers the cost of the plans it starts from."""
+    z, m = load_golden("plan_rpgd_default")
+    draws = [torch.from_numpy(z["draw0"][:, :, None].copy())] + [torch.from_numpy(d[:, :, None].copy()) for d in z["resamp_draws"]]
+    opt = _make_rpgd(m, draws)
+    for i in range(4):
+        assert abs(float(opt.step(z["s"][i].copy())) - float(z["u"][i])) < 2e-3
+    import cartpolesimulation_b200 as cps
+    from cartpolesimulation_b200 import _lib as L
+    a, b = _make_rpgd(m, draws), _make_rpgd(m, draws)
+    for o in (a, b):
+        o.rng = o._own_rng
+        o.optimizer_reset()
+    s = z["s"][0]
+    J0 = a.engine.plan_cost(torch.from_numpy(s).cuda(), a.Q_tf, L.ROLLOUT_MAJOR, 0.0)[0].cpu().numpy()
+    ua, ub = [float(a.step(s)) for _ in range(3)], [float(b.step(s)) for _ in range(3)]
+    assert ua == ub and all(abs(v) <= 1.0 for v in ua)
+    b2 = _make_rpgd(m, draws)
+    b2.rng = b2._own_rng
+    b2.optimizer_reset()
+    Q_start = b2.Q_tf.clone()
+    for _ in range(m["outer_its"]):
+        b2.engine.rpgd_grad_step(torch.from_numpy(s).cuda(), b2.Q_tf)
+    J1 = b2.engine.plan_cost(torch.from_numpy(s).cuda(), b2.Q_tf, L.ROLLOUT_MAJOR, 0.0)[0].cpu().numpy()
+    J0 = b2.engine.plan_cost(torch.from_numpy(s).cuda(), Q_start, L.ROLLOUT_MAJOR, 0.0)[0].cpu().numpy()
+    assert (J1 < J0).mean() > 0.8
