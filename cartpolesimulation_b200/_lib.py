@@ -10,7 +10,8 @@ import os
 import subprocess
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_PKG, "libcps_b200.so")
+# CPS_B200_LIB: another build of the same library (kernel A/B measurements, tools/); the product is the in-tree file
+_SO = os.environ.get("CPS_B200_LIB") or os.path.join(_PKG, "libcps_b200.so")
 _CSRC = os.path.join(_PKG, "csrc")
 
 CPS_OK = 0
@@ -132,6 +133,7 @@ SYMBOLS = {
     "cps_cem_gmm_get_distribution": (C.c_int, [_VP, _FP, _FP, _FP]),
     "cps_cem_gmm_set_distribution": (C.c_int, [_VP, _FP, _FP, _FP]),
     "cps_measure_peaks": (C.c_int, [_VP, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "cps_selftest_sincos": (C.c_int, [_VP, C.POINTER(C.c_longlong)]),
     "cps_plan_cost_grad": (C.c_int, [_VP, _VP, _VP, C.c_int, C.c_float, _VP, _VP]),
     "cps_rpgd_reset": (C.c_int, [_VP]),
     "cps_rpgd_grad_step": (C.c_int, [_VP, _VP, _VP] + [C.c_float] * 6 + [_VP]),
@@ -172,6 +174,8 @@ def lib():
                 "cartpolesimulation_b200 has no CPU fallback.")
         L = C.CDLL(_SO)
         for name, (res, args) in SYMBOLS.items():
+            if os.environ.get("CPS_B200_LIB") and not hasattr(L, name):
+                continue  # an older build under A/B measurement may lack the newest entry points
             fn = getattr(L, name)  # AttributeError if the library does not export a declared symbol
             fn.restype = res
             fn.argtypes = args

@@ -656,6 +656,13 @@ class Engine:
         self._chk(self.lib.cps_measure_peaks(self._h, C.byref(f), C.byref(m)))
         return f.value, m.value
 
+    def selftest_sincos(self) -> int:
+        """Number of floats in [-pi, pi] on which the kernels' folded sincos differs from sincosf / cosf (0 expected)."""
+        self.use_current_stream()
+        n = C.c_longlong(-1)
+        self._chk(self.lib.cps_selftest_sincos(self._h, C.byref(n)))
+        return int(n.value)
+
     # -- diagnostics ----------------------------------------------------------------------------------
     def launch_count(self) -> int:
         return int(self.lib.cps_launch_count(self._h))

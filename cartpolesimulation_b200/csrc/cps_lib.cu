@@ -57,22 +57,30 @@ __global__ void __launch_bounds__(256, 4) rollout_kernel(const __grid_constant__
     }
 }
 
+#ifndef CPS_PAIR_MIN_BLOCKS
+#define CPS_PAIR_MIN_BLOCKS 8
+#endif
 // Two cartpoles per thread (packed FP32, see cps_device.cuh "two cartpoles per thread"): thread p owns cartpoles
 // 2p and 2p+1 of a time-major batch, so controls arrive as one 8-byte load and every state channel leaves as one
 // 8-byte store per control step (256 B per warp and channel).  Bit-identical to rollout_kernel<INTEG, SC_ROTATE>.
-__device__ __forceinline__ void store_state2(float *base, long long ts_c, const State2 &z) {
-    *reinterpret_cast<unsigned long long *>(base + 0 * ts_c) = z.th.v;
-    *reinterpret_cast<unsigned long long *>(base + 1 * ts_c) = z.w.v;
-    *reinterpret_cast<unsigned long long *>(base + 2 * ts_c) = z.c.v;
-    *reinterpret_cast<unsigned long long *>(base + 3 * ts_c) = z.s.v;
-    *reinterpret_cast<unsigned long long *>(base + 4 * ts_c) = z.x.v;
-    *reinterpret_cast<unsigned long long *>(base + 5 * ts_c) = z.v.v;
+// Stores the six channels at *tp and advances it to the same cartpoles one control step on: one 64-bit pointer walked
+// channel by channel (cb = channel stride, tb = step stride minus five channel strides, both in bytes).
+__device__ __forceinline__ void store_state2_walk(char *&tp, long long cb, long long tb, const State2 &z) {
+    *reinterpret_cast<unsigned long long *>(tp) = z.th.v; tp += cb;
+    *reinterpret_cast<unsigned long long *>(tp) = z.w.v; tp += cb;
+    *reinterpret_cast<unsigned long long *>(tp) = z.c.v; tp += cb;
+    *reinterpret_cast<unsigned long long *>(tp) = z.s.v; tp += cb;
+    *reinterpret_cast<unsigned long long *>(tp) = z.x.v; tp += cb;
+    *reinterpret_cast<unsigned long long *>(tp) = z.v.v; tp += tb;
 }
 
-// Occupancy A/B (1M x 500, B200): 56 registers / 9 blocks per SM (this) 812 us; 48 registers / 10 blocks 805 us; 64 / 8
-// 823 us; 40 / 12 (spills) 827 us; 80 / 6 878 us -- the kernel sits on a plateau, occupancy is not its limiter.
-template <int INTEG, bool FAST_DIV>
-__global__ void __launch_bounds__(128) rollout_pair_kernel(const __grid_constant__ RolloutArgs a) {
+// Occupancy A/B (1M x 500, B200, round 1): 56 registers / 9 blocks per SM 812 us; 48 / 10 805 us; 64 / 8 823 us; 40 / 12
+// (spills) 827 us; 80 / 6 878 us -- a plateau.  Per control step (round 2): the angle resync of both halves in packed
+// arithmetic (resync_angle2), the redo copy of the state in shared memory, the trajectory pointer advanced instead of
+// recomputed.
+template <int INTEG, bool FAST_DIV, int NSUB, bool TRAJ>
+__global__ void __launch_bounds__(128, CPS_PAIR_MIN_BLOCKS) rollout_pair_kernel(const __grid_constant__ RolloutArgs a) {
+    __shared__ unsigned long long s_save[5 * 128];
     const OdeParams ode = pin_params(a.ode, a.s0[0]);
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long n_pairs = (long long)a.B >> 1;
@@ -80,17 +88,19 @@ __global__ void __launch_bounds__(128) rollout_pair_kernel(const __grid_constant
         const long long b = 2 * p;
         State2 z = join_states(load_state(a.s0 + b * a.ss_b), load_state(a.s0 + (b + 1) * a.ss_b));
         const float *q = a.Q + b;
-        float *traj = a.traj_out ? a.traj_out + b : nullptr;
+        char *tp = TRAJ ? reinterpret_cast<char *>(a.traj_out + b) : nullptr;
+        const long long cb = a.ts_c * 4, tb = (a.ts_t - 5 * a.ts_c) * 4;
         unsigned long long qn = *reinterpret_cast<const unsigned long long *>(q);
 #pragma unroll 1
         for (int t = 0; t < a.T; ++t) {
             F2 Q;
             Q.v = qn;
-            if (t + 1 < a.T) qn = *reinterpret_cast<const unsigned long long *>(q + (long long)(t + 1) * a.qs_t);
-            if (traj) store_state2(traj + (long long)t * a.ts_t, a.ts_c, z);
-            control_step2<INTEG, FAST_DIV>(ode, z, Q);
+            q += a.qs_t;
+            if (t + 1 < a.T) qn = *reinterpret_cast<const unsigned long long *>(q);
+            if (TRAJ) store_state2_walk(tp, cb, tb, z);
+            control_step2<INTEG, FAST_DIV, NSUB>(ode, z, Q, s_save + threadIdx.x, 128);
         }
-        if (traj) store_state2(traj + (long long)a.T * a.ts_t, a.ts_c, z);
+        if (TRAJ) store_state2_walk(tp, cb, tb, z);
         if (a.final_out) {
             store_state(a.final_out + b * 6, 1, half_state(z, 0));
             store_state(a.final_out + (b + 1) * 6, 1, half_state(z, 1));
@@ -690,6 +700,16 @@ extern "C" int cps_mppi_finalize(cps_handle *h, const float *partials_dev, int n
 // ---- open-loop rollouts -------------------------------------------------------------------------------
 // B cartpoles starting at the given pointers; B_full is the batch size the time-major strides refer to (a chunk of a
 // larger batch keeps the full batch's row pitch).
+template <int INTEG, bool FAST>
+static rollout_fn pick_pair2(bool n10, bool tr) {
+    if (n10) return tr ? rollout_pair_kernel<INTEG, FAST, 10, true> : rollout_pair_kernel<INTEG, FAST, 10, false>;
+    return tr ? rollout_pair_kernel<INTEG, FAST, 0, true> : rollout_pair_kernel<INTEG, FAST, 0, false>;
+}
+static rollout_fn pick_pair(bool v0, bool fast, bool n10, bool tr) {
+    if (v0) return fast ? pick_pair2<0, true>(n10, tr) : pick_pair2<0, false>(n10, tr);
+    return fast ? pick_pair2<1, true>(n10, tr) : pick_pair2<1, false>(n10, tr);
+}
+
 static int rollout_launch(cps_handle *h, const float *s0, int s0_batched, const float *Q, int q_layout, int B, int T,
                           float *traj, int traj_layout, float *fin, long long B_full = -1) {
     if (B_full < 0) B_full = B;
@@ -713,11 +733,9 @@ static int rollout_launch(cps_handle *h, const float *s0, int s0_batched, const 
         long long grid = ((long long)(B / 2) + block - 1) / block;
         const long long max_grid = 148LL * 16 * 8;
         if (grid > max_grid) grid = max_grid;
-        rollout_fn fn;
-        if (h->cfg.integrator == CPS_EULER_V0)
-            fn = (h->cfg.flags & CPS_FLAG_FAST_DIV) ? rollout_pair_kernel<0, true> : rollout_pair_kernel<0, false>;
-        else
-            fn = (h->cfg.flags & CPS_FLAG_FAST_DIV) ? rollout_pair_kernel<1, true> : rollout_pair_kernel<1, false>;
+        const bool v0 = h->cfg.integrator == CPS_EULER_V0, fast = (h->cfg.flags & CPS_FLAG_FAST_DIV) != 0;
+        const bool n10 = a.ode.n == 10, tr = a.traj_out != nullptr;   // n = 10: the predictors' operating point
+        rollout_fn fn = pick_pair(v0, fast, n10, tr);
         fn<<<(unsigned)grid, block, 0, h->stream>>>(a);
         h->rollout_last_kernel = 2;
     } else {
@@ -954,6 +972,42 @@ extern "C" int cps_measure_peaks(cps_handle *h, double *fp32_tflops, double *muf
     CUDA_TRY(h, cudaGetLastError());
     *fp32_tflops = best_f;
     *mufu_gops = best_m;
+    return CPS_OK;
+}
+
+// ---- self-test of sincos_folded ---------------------------------------------------------------------------
+// Every float of [-pi, pi] (both signs of every bit pattern up to fl32(pi)): sincos_folded against the math library's
+// sincosf and cosf, bit for bit.
+__global__ void __launch_bounds__(256) sincos_selftest_kernel(unsigned long long *mismatches) {
+    const unsigned last = 0x40490fdbu;   // fl32(pi)
+    unsigned long long bad = 0;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i <= last;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        for (unsigned sign = 0; sign < 2; ++sign) {
+            const float x = __uint_as_float((unsigned)i | (sign << 31));
+            float s0, c0, s1, c1;
+            sincosf(x, &s0, &c0);
+            sincos_folded(x, s1, c1);
+            bad += (__float_as_uint(s0) != __float_as_uint(s1)) + (__float_as_uint(c0) != __float_as_uint(c1)) +
+                   (__float_as_uint(cosf(x)) != __float_as_uint(c1));
+        }
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
+extern "C" int cps_selftest_sincos(cps_handle *h, long long *mismatches_out) {
+    if (!h || !mismatches_out) return CPS_ERR_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    unsigned long long *d = nullptr, host = 0;
+    CUDA_TRY(h, cudaMalloc(&d, sizeof(*d)));
+    cudaMemsetAsync(d, 0, sizeof(*d), h->stream);
+    sincos_selftest_kernel<<<148 * 8, 256, 0, h->stream>>>(d);
+    h->launches += 1;
+    cudaError_t e = cudaMemcpyAsync(&host, d, sizeof(host), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(d);
+    CUDA_TRY(h, e);
+    *mismatches_out = (long long)host;
     return CPS_OK;
 }
 

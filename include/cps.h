@@ -453,6 +453,12 @@ int cps_cem_gmm_set_distribution(cps_handle *h, const float *loc_host, const flo
  * (dense FFMA chains; MUFU.EX2 chains): FP32 TFLOP/s (FMA = 2 flops) and MUFU Gop/s.  Synchronises. */
 int cps_measure_peaks(cps_handle *h, double *fp32_tflops, double *mufu_gops);
 
+/* Self-test of the rotation kernels' once-per-control-step sin / cos (the math library's small-argument path without its
+ * large-argument branch; the reference takes np.sin / np.cos of the wrapped angle, CartPole/cartpole_equations.py:297-299):
+ * compares it bit for bit with sincosf and cosf on every float of [-pi, pi]; *mismatches_out = number of differing
+ * results (0 expected).  One launch, ~2e9 evaluations; synchronises. */
+int cps_selftest_sincos(cps_handle *h, long long *mismatches_out);
+
 /* ---- gradient of predict_and_cost; RPGD ----------------------------------------------------------------- */
 /* The reference's gradient-based optimizers take d(traj_cost)/dQ with a tf.GradientTape around predict_and_cost
  * (Control_Toolkit/Optimizers/optimizer_rpgd_tf.py:167-175; RPGD is the shipped default optimizer,

@@ -408,9 +408,10 @@ def test_rollout_host_pipelined_chunks_bit_identical(layout, B):
     eng.close()
 
 
+@pytest.mark.parametrize("substeps", [10, 7])   # 10: the unrolled instantiation; 7: the runtime loop with an odd remainder
 @pytest.mark.parametrize("shared_s0", [False, True])
 @pytest.mark.parametrize("integ", ["ODE_v0", "ODE"])
-def test_rollout_pair_kernel_bit_identical(integ, shared_s0):
+def test_rollout_pair_kernel_bit_identical(integ, shared_s0, substeps):
     """Large time-major batches run two cartpoles per thread with packed FP32 (rollout_pair_kernel: FFMA2/FMUL2/FADD2).
     Each half performs the arithmetic of the one-per-thread kernel, so trajectories and final states must be
     bit-identical -- including pairs in which one or both cartpoles hit the track end (edge_bounce) or spin fast
@@ -430,7 +431,7 @@ def test_rollout_pair_kernel_bit_identical(integ, shared_s0):
     Qd = cuda(Q)
     outs = []
     for no_pairs in (False, True):
-        eng = _engine(B, T, integrator=integ, cost=None, no_pairs=no_pairs)
+        eng = _engine(B, T, integrator=integ, cost=None, no_pairs=no_pairs, substeps=substeps)
         traj, fin = eng.rollout(s_in, Qd, q_layout=L.TIME_MAJOR, traj_layout=L.TIME_MAJOR, want_final=True)
         torch.cuda.synchronize()
         outs.append((traj, fin))
@@ -438,13 +439,13 @@ def test_rollout_pair_kernel_bit_identical(integ, shared_s0):
     assert torch.equal(outs[0][0], outs[1][0])
     assert torch.equal(outs[0][1], outs[1][1])
     # final-state-only launch takes the same path
-    eng = _engine(B, T, integrator=integ, cost=None)
+    eng = _engine(B, T, integrator=integ, cost=None, substeps=substeps)
     _, fin2 = eng.rollout(s_in, Qd, q_layout=L.TIME_MAJOR, want_traj=False, want_final=True)
     assert torch.equal(fin2, outs[0][1])
     eng.close()
     if not shared_s0:
         rows = np.r_[0:256, 5:B:1001][:512]
-        ref = O.rollout(integ, s0[rows], np.ascontiguousarray(Q[:, rows].T), want_traj=False)
+        ref = O.rollout(integ, s0[rows], np.ascontiguousarray(Q[:, rows].T), n=substeps, want_traj=False)
         calm = np.abs(s0[rows, 1]) < 50
         e = traj_err(outs[0][1][rows].cpu().numpy()[calm], ref[calm])
         assert max(e.values()) < 5e-5, e

@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--integrator", default="ODE_v0")
     ap.add_argument("--no-pairs", action="store_true")
     ap.add_argument("--no-traj", action="store_true")
+    ap.add_argument("--no-pairs-skip", action="store_true", help="packed-pair kernel only")
     args = ap.parse_args()
     import bench
     from cartpolesimulation_b200 import _lib as L
@@ -28,7 +29,7 @@ def main():
     s0, Q = torch.from_numpy(s0_np).cuda(), torch.from_numpy(Q_np).cuda()
     traj = None if args.no_traj else torch.empty((args.T + 1, 6, args.B), device="cuda")
     fin = torch.empty((args.B, 6), device="cuda") if args.no_traj else None
-    for no_pairs in ([True] if args.no_pairs else [False, True]):
+    for no_pairs in ([True] if args.no_pairs else [False] if args.no_pairs_skip else [False, True]):
         eng = Engine(args.B, args.T, integrator=args.integrator, cost=None, device=0, no_pairs=no_pairs)
         run = lambda: eng.rollout(s0, Q, q_layout=L.TIME_MAJOR, traj_layout=L.TIME_MAJOR, want_traj=not args.no_traj,
                                   want_final=args.no_traj, traj_out=traj, final_out=fin)
