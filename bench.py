@@ -33,8 +33,8 @@ if REPO not in sys.path:
 
 FLOP_PER_STATE_STEP = 32.0   # 24 (ODE rhs) + 8 (integrator), FMA = 2
 # FMA-pipe lane operations the pair kernel executes per state-step (ncu instruction mix): 29 packed in the
-# substep loop + ~2.6 scalar per-control-step work (sincosf resync, compensated angle) + ~2 IMAD.MOV
-FP32_LANE_OPS_PER_STATE_STEP = 33.5
+# substep + ~2.7 amortised per-control-step work (packed angle resync: 25 packed + 4 scalar per pair and control step)
+FP32_LANE_OPS_PER_STATE_STEP = 31.7
 MUFU_PER_STATE_STEP = 3.0    # rcp + sin + cos when the MUFU path is used; 1 (rcp) otherwise
 B_DEFAULT, T_DEFAULT, N_SUB, DT = 1 << 20, 50, 10, 0.02
 METRIC = "rollout_state_steps_per_sec"
@@ -849,8 +849,10 @@ def run_ours(args):
                               "achieved_frac_of_lanes": rate_1gpu * FP32_LANE_OPS_PER_STATE_STEP / (fp32_peak * 1e12 / 2.0)
                               if fp32_peak else None,
                               "note": "FMA-pipe lane operations executed per state-step (FMUL/FADD occupy a lane like an FMA): "
-                                      "29 in the substep loop + ~4.5 amortised per-control-step work and moves; peak = measured FFMA "
+                                      "29 in the substep + ~2.7 amortised per-control-step work; peak = measured FFMA "
                                       "lane rate (roofline.peak / 2)"},
+                "frac_of_theoretical": achieved_tflops / (148 * 128 * 2 * 1.965e-3),
+                "theoretical_note": "148 SMs x 128 lanes x 2 flops x 1965 MHz = 74.5 TFLOP/s",
                 "ncu": ncu_view,
                 "mufu": {"achieved_gops": rate_1gpu * (MUFU_PER_STATE_STEP if args.fast_sincos else 1.0) / 1e9,
                          "peak_gops": mufu_peak},

@@ -1,7 +1,7 @@
 // ffma2_forms.cu -- what a packed FP32 instruction costs on this device, by operand form.  The rollout kernels are bound by
 // the FMA pipe ("math pipe throttle" is their top stall), yet the pipe reports 70-75 % active: this probe measures the
-// issue-to-issue cost per warp instruction and scheduler (SM sub-partition) of each form the substep uses, at 8 warps per
-// scheduler with 6 independent chains per thread, from per-warp clock64() stamps.
+// issue-to-issue cost per warp instruction and scheduler (SM sub-partition) of each form the substep uses, with 6 independent chains per thread,
+// from CUDA-event times of long launches (the per-warp clock64() stamps are kept for inspection only).
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/ffma2_forms tools/ffma2_forms.cu
 #include <cuda_runtime.h>
 #include <cstdio>
@@ -25,7 +25,7 @@ const char *NAMES[N_FORMS] = {
     "FFMA2 x = x*y_i + z_i    (three distinct pairs)", "FFMA2 x = x*U + z_i      (uniform scalar, two pairs)",
     "FFMA2 x = x*y_i + 1.0    (immediate, two pairs)", "FMUL2 x = x*y_i", "FMUL2 x = x*U", "FADD2 x = x + y_i",
     "FFMA2 a = b*c + d ring   (three distinct pairs, fourth written)", "FFMA  x = x*y_i + z_i    (scalar, three registers)",
-    "FFMA  x = x*U + z_i      (scalar, uniform operand)", "FFMA2 x*U + z_i  and one FMNMX per FFMA2 (ALU pipe beside it)",
+    "FFMA  x = x*U + z_i      (scalar, uniform operand)", "FFMA2 x*U + z_i  with 1.5 ALU instructions per FFMA2 beside it",
     "FFMA2 x = y_i*y_i + x    (one pair read twice)"};
 
 template <int F>
@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(256) probe(float *out, long long *stamps, int 
             }
             if (F == F_S_FMA_3U) sx[i] = fmaf(sx[i], sy[i], sz[i]);
             if (F == F_S_FMA_UR) sx[i] = fmaf(sx[i], U, sz[i]);
-            if (F == F_MIX_ALU) { x[i] = fma2(x[i], Uu, z[i]); m = fmaxf(m, fabsf(sx[i])); sx[i] = __int_as_float(__float_as_int(sx[i]) ^ it); }
+            if (F == F_MIX_ALU) { x[i] = fma2(x[i], Uu, z[i]); m = fmaxf(m, fabsf(sx[i])); sx[i] = __int_as_float(__float_as_int(sx[i]) + 12345); }
             if (F == F_FMA_SQ) x[i] = fma2(y[i], y[i], x[i]);
         }
     }
@@ -91,22 +91,27 @@ int main() {
     cudaMalloc(&dout, 4); cudaMalloc(&dst, sizeof(long long) * 2 * warps);
     kern tab[N_FORMS];
     Tab<0>::fill(tab);
-    std::vector<long long> st(2 * warps);
-    printf("%d SMs, %d warps per scheduler, %d chains per thread; cycles per warp instruction and scheduler (1.0 = one issue slot)\n",
-           sms, bps * block / 32 / 4, CH);
+    // Event-timed (robust against how many blocks are co-resident): cycles = elapsed x SM clock x schedulers / warp
+    // instructions, with the SM clock read through the attribute (boost clock; the rollout bench holds it under load).
+    int khz = 0;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, 0);
+    printf("%d SMs at %d MHz, %d chains per thread; cycles per warp instruction and scheduler (1.0 = one issue slot per cycle)\n",
+           sms, khz / 1000, CH);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const int long_iters = 1 << 16;
     for (int f = 0; f < N_FORMS; ++f) {
         double best = 1e30;
-        for (int rep = 0; rep < 3; ++rep) {
-            tab[f]<<<grid, block>>>(dout, dst, iters, dp, 0.99999f);
-            cudaDeviceSynchronize();
-            cudaMemcpy(st.data(), dst, sizeof(long long) * 2 * warps, cudaMemcpyDeviceToHost);
-            // per SM: (latest end - earliest start) over its warps is not recoverable without smid; every warp runs the whole
-            // time (one wave), so the mean per-warp elapsed is the scheduler's busy time
-            double mean = 0;
-            for (int w = 0; w < warps; ++w) mean += (double)(st[2 * w + 1] - st[2 * w]);
-            mean /= warps;
-            const double per = mean / ((double)iters * CH * (bps * block / 32 / 4)) / (f == F_FMA_RING ? 4.0 : 1.0);
-            best = std::min(best, per);
+        for (int rep = 0; rep < 4; ++rep) {
+            cudaEventRecord(e0);
+            tab[f]<<<grid, block>>>(dout, dst, long_iters, dp, 0.99999f);
+            cudaEventRecord(e1);
+            cudaEventSynchronize(e1);
+            float ms = 0;
+            cudaEventElapsedTime(&ms, e0, e1);
+            const double instr = (double)long_iters * CH * warps * (f == F_FMA_RING ? 4.0 : 1.0);
+            const double per = ms * 1e-3 * khz * 1e3 * (sms * 4.0) / instr;
+            if (rep > 0) best = std::min(best, per);
         }
         printf("  %-68s %6.3f\n", NAMES[f], best);
     }
