@@ -463,25 +463,25 @@ typedef void (*rollout_fn)(const RolloutArgs);
 typedef void (*cost_fn)(const CostArgs);
 
 // The MPPI solve kernels are instantiated in one translation unit per cost plugin (cps_mppi_*.cu, cps_mppi_inst.cuh).
-#define CPS_DECL_MPPI(name) mppi_fn cps_pick_mppi_##name(int integ, int noise, unsigned flags); mppi_fn cps_pick_mppi_pair_##name(int integ);
+#define CPS_DECL_MPPI(name) mppi_fn cps_pick_mppi_##name(int integ, int noise, unsigned flags, int n_sub); mppi_fn cps_pick_mppi_pair_##name(int integ, int n_sub);
 CPS_DECL_MPPI(default) CPS_DECL_MPPI(qb) CPS_DECL_MPPI(gradmin) CPS_DECL_MPPI(grad) CPS_DECL_MPPI(none)
 #undef CPS_DECL_MPPI
-static mppi_fn pick_mppi_pair(const cps_config &c) {
+static mppi_fn pick_mppi_pair(const cps_config &c, int n_sub) {
     switch (c.cost_id) {
-    case CPS_COST_DEFAULT: return cps_pick_mppi_pair_default(c.integrator);
-    case CPS_COST_QUADRATIC_BOUNDARY: return cps_pick_mppi_pair_qb(c.integrator);
-    case CPS_COST_QB_GRAD_MINIMAL: return cps_pick_mppi_pair_gradmin(c.integrator);
-    case CPS_COST_QB_GRAD: return cps_pick_mppi_pair_grad(c.integrator);
-    default: return cps_pick_mppi_pair_none(c.integrator);
+    case CPS_COST_DEFAULT: return cps_pick_mppi_pair_default(c.integrator, n_sub);
+    case CPS_COST_QUADRATIC_BOUNDARY: return cps_pick_mppi_pair_qb(c.integrator, n_sub);
+    case CPS_COST_QB_GRAD_MINIMAL: return cps_pick_mppi_pair_gradmin(c.integrator, n_sub);
+    case CPS_COST_QB_GRAD: return cps_pick_mppi_pair_grad(c.integrator, n_sub);
+    default: return cps_pick_mppi_pair_none(c.integrator, n_sub);
     }
 }
-static mppi_fn pick_mppi(const cps_config &c) {
+static mppi_fn pick_mppi(const cps_config &c, int n_sub) {
     switch (c.cost_id) {
-    case CPS_COST_DEFAULT: return cps_pick_mppi_default(c.integrator, c.noise_mode, c.flags);
-    case CPS_COST_QUADRATIC_BOUNDARY: return cps_pick_mppi_qb(c.integrator, c.noise_mode, c.flags);
-    case CPS_COST_QB_GRAD_MINIMAL: return cps_pick_mppi_gradmin(c.integrator, c.noise_mode, c.flags);
-    case CPS_COST_QB_GRAD: return cps_pick_mppi_grad(c.integrator, c.noise_mode, c.flags);
-    default: return cps_pick_mppi_none(c.integrator, c.noise_mode, c.flags);
+    case CPS_COST_DEFAULT: return cps_pick_mppi_default(c.integrator, c.noise_mode, c.flags, n_sub);
+    case CPS_COST_QUADRATIC_BOUNDARY: return cps_pick_mppi_qb(c.integrator, c.noise_mode, c.flags, n_sub);
+    case CPS_COST_QB_GRAD_MINIMAL: return cps_pick_mppi_gradmin(c.integrator, c.noise_mode, c.flags, n_sub);
+    case CPS_COST_QB_GRAD: return cps_pick_mppi_grad(c.integrator, c.noise_mode, c.flags, n_sub);
+    default: return cps_pick_mppi_none(c.integrator, c.noise_mode, c.flags, n_sub);
     }
 }
 
@@ -559,12 +559,12 @@ extern "C" int cps_mppi_step(cps_handle *h, const float *s_dev, const float *noi
         const int grid = (int)((threads + block - 1) / block);   // grid <= h->grid: the partial records fit
         const size_t smem = sizeof(float) * mppi_smem_floats(a.mp, h->cfg.cost_id, block, 2);
         if (smem > 200 * 1024) return fail(h, CPS_ERR_UNSUPPORTED, "cps_mppi_step: horizon too large for the shared-memory staging of this build");
-        mppi_fn fn = pick_mppi_pair(h->cfg);
+        mppi_fn fn = pick_mppi_pair(h->cfg, a.ode.n);
         if (smem > 48 * 1024) CUDA_TRY(h, cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         fn<<<grid, block, smem, h->stream>>>(a);
     } else {
         mppi_smem_floats(a.mp, h->cfg.cost_id, h->block, 1);   // a.mp.rs_off for this geometry
-        mppi_fn fn = pick_mppi(h->cfg);
+        mppi_fn fn = pick_mppi(h->cfg, a.ode.n);
         if (h->smem > 48 * 1024) CUDA_TRY(h, cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
         fn<<<h->grid, h->block, h->smem, h->stream>>>(a);
     }
