@@ -246,7 +246,8 @@ __device__ __forceinline__ float plant_control_noise(const PlantModels &M, float
     return Q;
 }
 
-template <int INTEG, int COST, bool PHILOX, bool PAIR>
+// NSUB = 10 (packed solve only): the substeps of the predictors' operating point unrolled; 0: ode.n substeps in a loop.
+template <int INTEG, int COST, bool PHILOX, bool PAIR, int NSUB = 0>
 __global__ void __launch_bounds__(256, 4) fleet_kernel(const __grid_constant__ FleetArgs a) {
     extern __shared__ float smem[];
     __shared__ CostParams s_cost;
@@ -298,8 +299,8 @@ __global__ void __launch_bounds__(256, 4) fleet_kernel(const __grid_constant__ F
     if (a.L_row || a.mp_row)
         fold_ode_device<INTEG>(a, a.L_row ? (double)a.L_row[e] : (double)a.L_default,
                                a.mp_row ? (double)a.mp_row[e] : (double)a.mp_default, ode);
-    const bool last = PAIR ? mppi_solve_block2<INTEG, COST>(ode, s_cost, mp, io, smem, blockIdx.x, a.bpe)
-                           : mppi_solve_block<INTEG, COST, SC_ROTATE, CPS_NOISE_INDUCING, false, false>(ode, s_cost, mp, io, smem,
+    const bool last = PAIR ? mppi_solve_block2<INTEG, COST, NSUB, false>(ode, s_cost, mp, io, smem, blockIdx.x, a.bpe)
+                           : mppi_solve_block<INTEG, COST, SC_ROTATE, CPS_NOISE_INDUCING, false, false, 0, false>(ode, s_cost, mp, io, smem,
                                                                                                        blockIdx.x, a.bpe);
     if (!last) return;
     __syncthreads();
@@ -404,23 +405,24 @@ void cps_fleet_free(cps_handle *h) {
 }
 
 typedef void (*fleet_fn)(const FleetArgs);
-template <int INTEG, bool PHILOX, bool PAIR>
+template <int INTEG, bool PHILOX, bool PAIR, int NSUB>
 static fleet_fn pick_fleet2(int cost) {
     switch (cost) {
-    case CPS_COST_DEFAULT: return fleet_kernel<INTEG, COST_DEFAULT, PHILOX, PAIR>;
-    case CPS_COST_QUADRATIC_BOUNDARY: return fleet_kernel<INTEG, COST_QB, PHILOX, PAIR>;
-    case CPS_COST_QB_GRAD_MINIMAL: return fleet_kernel<INTEG, COST_GRADMIN, PHILOX, PAIR>;
-    case CPS_COST_QB_GRAD: return fleet_kernel<INTEG, COST_GRAD, PHILOX, PAIR>;
+    case CPS_COST_DEFAULT: return fleet_kernel<INTEG, COST_DEFAULT, PHILOX, PAIR, NSUB>;
+    case CPS_COST_QUADRATIC_BOUNDARY: return fleet_kernel<INTEG, COST_QB, PHILOX, PAIR, NSUB>;
+    case CPS_COST_QB_GRAD_MINIMAL: return fleet_kernel<INTEG, COST_GRADMIN, PHILOX, PAIR, NSUB>;
+    case CPS_COST_QB_GRAD: return fleet_kernel<INTEG, COST_GRAD, PHILOX, PAIR, NSUB>;
     default: return nullptr;
     }
 }
 template <int INTEG>
-static fleet_fn pick_fleet1(int cost, bool philox, bool pair) {
-    if (pair) return philox ? pick_fleet2<INTEG, true, true>(cost) : pick_fleet2<INTEG, false, true>(cost);
-    return philox ? pick_fleet2<INTEG, true, false>(cost) : pick_fleet2<INTEG, false, false>(cost);
+static fleet_fn pick_fleet1(int cost, bool philox, bool pair, bool n10) {
+    if (pair && n10) return philox ? pick_fleet2<INTEG, true, true, 10>(cost) : pick_fleet2<INTEG, false, true, 10>(cost);
+    if (pair) return philox ? pick_fleet2<INTEG, true, true, 0>(cost) : pick_fleet2<INTEG, false, true, 0>(cost);
+    return philox ? pick_fleet2<INTEG, true, false, 0>(cost) : pick_fleet2<INTEG, false, false, 0>(cost);
 }
-static fleet_fn pick_fleet(int integ, int cost, bool philox, bool pair) {
-    return integ == CPS_EULER_V0 ? pick_fleet1<0>(cost, philox, pair) : pick_fleet1<1>(cost, philox, pair);
+static fleet_fn pick_fleet(int integ, int cost, bool philox, bool pair, bool n10) {
+    return integ == CPS_EULER_V0 ? pick_fleet1<0>(cost, philox, pair, n10) : pick_fleet1<1>(cost, philox, pair, n10);
 }
 
 extern "C" int cps_fleet_create(cps_handle *h, const cps_fleet_config *cfg) {
@@ -627,7 +629,7 @@ static int fleet_launch(cps_handle *h, const char *who, int n_periods, const flo
     a.h_step = (double)h->cfg.dt / (double)h->cfg.substeps;
     if (F->pair && noise_dev && ((uintptr_t)noise_dev % 8) != 0)
         return fail(h, CPS_ERR_INVALID, "%s: supplied noise must be 8-byte aligned", who);
-    fleet_fn fn = pick_fleet(h->cfg.integrator, h->cfg.cost_id, philox, F->pair != 0);
+    fleet_fn fn = pick_fleet(h->cfg.integrator, h->cfg.cost_id, philox, F->pair != 0, h->ode.n == 10);
     if (!fn) return fail(h, CPS_ERR_NOT_CONFIGURED, "%s: no kernel for this configuration", who);
     if (F->smem > 48 * 1024) CUDA_TRY(h, cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F->smem));
     const size_t E = F->E, K = h->cfg.num_rollouts;

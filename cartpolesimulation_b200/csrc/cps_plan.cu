@@ -517,7 +517,8 @@ __global__ void __launch_bounds__(256) cem_update_kernel(const __grid_constant__
     }
 }
 
-template <int INTEG, int COST, int MODE>
+// NSUB = 10: the substeps of the predictors' operating point unrolled (control_step); 0: a.ode.n substeps in a loop.
+template <int INTEG, int COST, int MODE, int NSUB = 0>
 __global__ void __launch_bounds__(256, 4) plan_kernel(const __grid_constant__ PlanArgs a) {
     extern __shared__ float smem[];   // PLAN_CEM: mu[T], sd[T], mu2[T], sd2[T], elite list [elite_smem]
     __shared__ unsigned s_ticket;
@@ -560,7 +561,7 @@ __global__ void __launch_bounds__(256, 4) plan_kernel(const __grid_constant__ Pl
             else Jacc += st;
         }
         if (active && traj) store_state(traj + (long long)t * a.ts_t, a.ts_c, z);
-        control_step<INTEG, SC_ROTATE, false, false>(ode, z, u);
+        control_step<INTEG, SC_ROTATE, false, false, false, NSUB>(ode, z, u);
         c_cost = z.c;
         up = u;
     }
@@ -695,19 +696,23 @@ static void plan_pair_launch(cps_handle *h, PlanArgs &a, int mode) {
 
 // ---- host side ---------------------------------------------------------------------------------------------------------
 typedef void (*plan_fn)(const PlanArgs);
-template <int INTEG, int MODE>
+template <int INTEG, int MODE, int NSUB>
 static plan_fn pick_plan2(int cost) {
     switch (cost) {
-    case CPS_COST_DEFAULT: return plan_kernel<INTEG, COST_DEFAULT, MODE>;
-    case CPS_COST_QUADRATIC_BOUNDARY: return plan_kernel<INTEG, COST_QB, MODE>;
-    case CPS_COST_QB_GRAD_MINIMAL: return plan_kernel<INTEG, COST_GRADMIN, MODE>;
-    case CPS_COST_QB_GRAD: return plan_kernel<INTEG, COST_GRAD, MODE>;
+    case CPS_COST_DEFAULT: return plan_kernel<INTEG, COST_DEFAULT, MODE, NSUB>;
+    case CPS_COST_QUADRATIC_BOUNDARY: return plan_kernel<INTEG, COST_QB, MODE, NSUB>;
+    case CPS_COST_QB_GRAD_MINIMAL: return plan_kernel<INTEG, COST_GRADMIN, MODE, NSUB>;
+    case CPS_COST_QB_GRAD: return plan_kernel<INTEG, COST_GRAD, MODE, NSUB>;
     default: return nullptr;
     }
 }
-static plan_fn pick_plan(int integ, int cost, int mode) {
-    if (integ == CPS_EULER_V0) return mode == PLAN_CEM ? pick_plan2<0, PLAN_CEM>(cost) : pick_plan2<0, PLAN_Q>(cost);
-    return mode == PLAN_CEM ? pick_plan2<1, PLAN_CEM>(cost) : pick_plan2<1, PLAN_Q>(cost);
+template <int INTEG, int MODE>
+static plan_fn pick_plan1(int cost, int n_sub) {
+    return n_sub == 10 ? pick_plan2<INTEG, MODE, 10>(cost) : pick_plan2<INTEG, MODE, 0>(cost);
+}
+static plan_fn pick_plan(int integ, int cost, int mode, int n_sub) {
+    if (integ == CPS_EULER_V0) return mode == PLAN_CEM ? pick_plan1<0, PLAN_CEM>(cost, n_sub) : pick_plan1<0, PLAN_Q>(cost, n_sub);
+    return mode == PLAN_CEM ? pick_plan1<1, PLAN_CEM>(cost, n_sub) : pick_plan1<1, PLAN_Q>(cost, n_sub);
 }
 
 void cps_plan_free(cps_handle *h) {
@@ -806,7 +811,7 @@ extern "C" int cps_plan_cost(cps_handle *h, const float *s_dev, const float *Q_d
     } else {
         int grid, block;
         plan_geometry(K, false, grid, block);
-        plan_fn fn = pick_plan(h->cfg.integrator, h->cfg.cost_id, PLAN_Q);
+        plan_fn fn = pick_plan(h->cfg.integrator, h->cfg.cost_id, PLAN_Q, h->ode.n);
         const size_t smem = plan_smem(h, a, 0, block, 1);
         if (smem > 48 * 1024) CUDA_TRY(h, cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         fn<<<grid, block, smem, h->stream>>>(a);
@@ -837,7 +842,7 @@ extern "C" int cps_plan_random_action(cps_handle *h, const float *s_dev, const f
     a.best_out = best_out_dev ? best_out_dev : P->d_best;
     int grid, block;
     plan_geometry(K, true, grid, block);
-    plan_fn fn = pick_plan(h->cfg.integrator, h->cfg.cost_id, PLAN_Q);
+    plan_fn fn = pick_plan(h->cfg.integrator, h->cfg.cost_id, PLAN_Q, h->ode.n);
     const size_t smem = plan_smem(h, a, 0, block, 1);
     if (smem > 48 * 1024) CUDA_TRY(h, cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     fn<<<grid, block, smem, h->stream>>>(a);
@@ -921,7 +926,7 @@ extern "C" int cps_cem_step(cps_handle *h, const float *s_dev, const float *eps_
     plan_geometry(K, true, grid, block);
     a.elite_smem = 0;   // set below once defer_stats is known
     const size_t smem = sizeof(float) * 4 * (size_t)T + sizeof(int) * (size_t)(((long long)P->best_k * T > 2048) ? 0 : P->best_k);
-    plan_fn fn = pick_plan(h->cfg.integrator, h->cfg.cost_id, PLAN_CEM);
+    plan_fn fn = pick_plan(h->cfg.integrator, h->cfg.cost_id, PLAN_CEM, h->ode.n);
     // small elite sets: the selecting block also computes the T x best_k statistics; large ones: a second launch with
     // one block per horizon step
     a.defer_stats = ((long long)P->best_k * T > 2048) ? 1 : 0;
