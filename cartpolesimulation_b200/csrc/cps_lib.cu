@@ -74,12 +74,14 @@ __device__ __forceinline__ void store_state2_walk(char *&tp, long long cb, long 
     *reinterpret_cast<unsigned long long *>(tp) = z.v.v; tp += tb;
 }
 
+// Without the trajectory stores the 9-block / 56-register allocation is the faster one (606 vs 641 us), with them the
+// 8-block / 64-register one (636 vs 644 us): ptxas' schedule, not occupancy, decides at this point.
 // Occupancy A/B (1M x 500, B200, round 1): 56 registers / 9 blocks per SM 812 us; 48 / 10 805 us; 64 / 8 823 us; 40 / 12
 // (spills) 827 us; 80 / 6 878 us -- a plateau.  Per control step (round 2): the angle resync of both halves in packed
 // arithmetic (resync_angle2), the redo copy of the state in shared memory, the trajectory pointer advanced instead of
 // recomputed.
 template <int INTEG, bool FAST_DIV, int NSUB, bool TRAJ>
-__global__ void __launch_bounds__(128, CPS_PAIR_MIN_BLOCKS) rollout_pair_kernel(const __grid_constant__ RolloutArgs a) {
+__global__ void __launch_bounds__(128, TRAJ ? CPS_PAIR_MIN_BLOCKS : CPS_PAIR_MIN_BLOCKS + 1) rollout_pair_kernel(const __grid_constant__ RolloutArgs a) {
     __shared__ unsigned long long s_save[5 * 128];
     const OdeParams ode = pin_params(a.ode, a.s0[0]);
     const long long stride = (long long)gridDim.x * blockDim.x;
