@@ -18,9 +18,10 @@ def main():
     ap.add_argument("--iters", type=int, default=50)
     ap.add_argument("--integrator", default="ODE")
     ap.add_argument("--cost", default="quadratic_boundary_grad_minimal")
+    ap.add_argument("--no-pairs", action="store_true", help="one rollout per thread at every K (A/B of the packed solve)")
     args = ap.parse_args()
     from cartpolesimulation_b200.core import Engine
-    eng = Engine(args.K, args.T, integrator=args.integrator, cost=args.cost, device=0)
+    eng = Engine(args.K, args.T, integrator=args.integrator, cost=args.cost, device=0, no_pairs=args.no_pairs)
     a = np.pi - 1e-3
     s = torch.tensor([a, 0.0, np.cos(a), np.sin(a), 0.0, 0.0], device=eng.device, dtype=torch.float32)
     noise = torch.randn((eng.n_ind, args.K), device=eng.device)
@@ -48,7 +49,7 @@ def main():
         e1.synchronize()
         tb.append(e0.elapsed_time(e1) / 20)
     mb = float(np.median(tb))
-    print(f"MPPI solve K={args.K} T={args.T} {args.integrator} {args.cost}: single launch {ms * 1e3:.1f} us median (events around one "
+    print(f"MPPI solve K={args.K} T={args.T} {args.integrator} {args.cost}{' one-per-thread' if args.no_pairs else ''}: single launch {ms * 1e3:.1f} us median (events around one "
           f"launch on an idle GPU), {mb * 1e3:.1f} us per solve in a stream of 20, {args.K * args.T * 10 / mb * 1e3:.3e} state-steps/s")
 
 
