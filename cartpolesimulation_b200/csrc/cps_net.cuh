@@ -57,7 +57,7 @@ struct NetArgs {
     float *shard_out;
     PeerExchange px;          // K sharded over GPUs, exchange inside the launch (cps_mppi_set_peers)
     float *h_ref;             // stored hidden state to advance after the solve (null: skip)
-    int tc_rows;              // net_tc_kernel: live rollouts per CTA (64: the first 16 lanes of each tensor-memory lane quarter | 128)
+    int tc_rows;              // net_tc_kernel: live rollouts per CTA (32 | 64: the first 8 | 16 lanes of each tensor-memory lane quarter | 128)
 };
 
 // ---- small device helpers ---------------------------------------------------------------------------------------

@@ -28,6 +28,7 @@
 #include <cuda_runtime.h>
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -56,12 +57,12 @@ __global__ void __launch_bounds__(TC_NT, 1) net_tc_kernel(const __grid_constant_
     const int sub = (warp >> 2) & 3;           // epilogue warps: which 8 of a job's 32 units
     const int row = 32 * (warp & 3) + lane;    // rollout inside the tile (epilogue and row warps)
     const int T = a.T;
-    // Small batches are latency-bound by the step's dependence chain, not by throughput: with only the first 16 tensor-
-    // memory lanes of every lane quarter live (64 rollouts per CTA) the MUFU-bound epilogues take half the time, because the
+    // Small batches are latency-bound by the step's dependence chain, not by throughput: with only the first 16 (or 8) tensor-
+    // memory lanes of every lane quarter live (64 / 32 rollouts per CTA) the epilogues take half the time (12 % less again), because the
     // 16-lane access shapes spread those rollouts over all 32 threads of the epilogue warps -- and all four schedulers stay
     // in use, a warp's lane quarter being tied to its scheduler.  (The MMAs cost the same for any number of live rows:
     // M = 128 is the instruction's minimum.)
-    const int rpq = a.tc_rows >> 2;            // live rollouts per lane quarter: 16 | 32
+    const int rpq = a.tc_rows >> 2;            // live rollouts per lane quarter: 8 | 16 | 32
     const int row0 = blockIdx.x * a.tc_rows;
     const bool live = lane < rpq;              // per lane; dead lanes run along on clamped indices and store nothing
     const int k = row0 + rpq * (warp & 3) + lane;
@@ -248,13 +249,15 @@ __global__ void __launch_bounds__(TC_NT, 1) net_tc_kernel(const __grid_constant_
             TC_TR(6);
             bar_wait(epib(2), par); tc_fence_after();
             TC_TR(7);
-            if (more) issue_H(q2, ah1_hi, ah1_lo, sm0 + O_WHH1_HI, sm0 + O_WHH1_LO, 1);
             TC_TR(8);
             bar_wait(epib(3), par); tc_fence_after();      // h2(t) complete; the region of job 2b is idle
             TC_TR(9);
             issue_OUT(q0 + C_NI, ah2_hi, ah2_lo, sm0 + O_WOUT_HI, sm0 + O_WOUT_LO);
             tc_commit(outb);
             TC_TR(10);
+            // recurrent part of job 1b of the next step, behind the output layer: the tensor pipe executes in order, and in
+            // front of it these 12 MMAs would sit between h2(t) and x(t + 1); here they run under the row warps' feedback
+            if (more) issue_H(q2, ah1_hi, ah1_lo, sm0 + O_WHH1_HI, sm0 + O_WHH1_LO, 1);
             t3 = i1;
         }
     } else if (is_epi) {
@@ -279,9 +282,12 @@ __global__ void __launch_bounds__(TC_NT, 1) net_tc_kernel(const __grid_constant_
                         gru_epilogue<2, false>(tl, region(j), (uint32_t)cu, l ? cst2 : cst1, l ? ec2 : ec1, l ? ecn2 : ecn1,
                                                l ? C_AH2_HI : C_AH1_HI, l ? C_AH2_LO : C_AH1_LO, 32 * g + cu, lane);
                     }
-                } else {   // 16 rollouts x this warp's 16 units in one interleaved pass
+                } else if (rpq > 8) {   // 16 rollouts x this warp's 16 units in one interleaved pass
                     gru_epilogue<2, true>(tl, region(j), (uint32_t)(16 * hs), l ? cst2 : cst1, l ? ec2 : ec1, l ? ecn2 : ecn1,
                                           l ? C_AH2_HI : C_AH1_HI, l ? C_AH2_LO : C_AH1_LO, 32 * g + 16 * hs, lane);
+                } else {   // 8 rollouts: one per thread and chunk
+                    gru_epilogue<2, true, true>(tl, region(j), (uint32_t)(16 * hs), l ? cst2 : cst1, l ? ec2 : ec1, l ? ecn2 : ecn1,
+                                                l ? C_AH2_HI : C_AH1_HI, l ? C_AH2_LO : C_AH1_LO, 32 * g + 16 * hs, lane);
                 }
                 if (warp == 8 * g) TC_TR(16 + 4 * job + 2);
                 warp_signal(epib(job), lane);
@@ -568,10 +574,14 @@ int cps_net_tc_launch(cps_handle *h, NetArgs &a, bool mppi, int n_rows) {
     const size_t smem = cps_net_tc_smem(&h->mp, mppi);
     void (*fn)(const NetArgs) = mppi ? net_tc_kernel<true> : net_tc_kernel<false>;
     CUDA_TRY(h, cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    // live rollouts per CTA: 64 while that still gives every CTA its own SM (see the kernel's comment on rpq)
+    // live rollouts per CTA: 32 or 64 while that still gives every CTA its own SM (see the kernel's comment on rpq)
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->cfg.device);
-    a.tc_rows = (n_rows <= 64 * sms) ? 64 : TC_ROWS;
+    a.tc_rows = (n_rows <= 32 * sms) ? 32 : (n_rows <= 64 * sms) ? 64 : TC_ROWS;
+    if (const char *e = getenv("CPS_TC_ROWS")) {   // A/B switch (tools/bench_net.py)
+        const int r = atoi(e);
+        if (r == 32 || r == 64 || r == 128) a.tc_rows = r;
+    }
     const int grid = (n_rows + a.tc_rows - 1) / a.tc_rows;
     fn<<<grid, TC_NT, smem, h->stream>>>(a);
     h->launches += 1;

@@ -259,7 +259,9 @@ __device__ __forceinline__ uint32_t pack_f16x2(float lo_v, float hi_v) {   // tw
 // N chunks of 16 rollouts x 8 units per call, interleaved for instruction-level parallelism (2 N independent dependence
 // chains per thread): UNITS -> the chunks are consecutive 8-unit groups of the same 16 rollouts (64 live rollouts per CTA),
 // else -> the same 8 units of the two 16-lane halves of the quarter (128 live rollouts).
-template <int N, bool UNITS>
+// HALF: only the rollouts t / 4 are live (32 live rollouts per CTA, 8 per lane quarter): the second rollout of every thread is
+// skipped, its operand columns are written back as read.
+template <int N, bool UNITS, bool HALF = false>
 __device__ __forceinline__ void gru_epilogue(uint32_t tq, uint32_t region, uint32_t cu, const float *cst, float c, float cn,
                                               uint32_t c_hi, uint32_t c_lo, int u0, int lane) {
     uint32_t R[N][4], Z[N][4], NI[N][4], NH[N][4], PH[N][2], PL[N][2];
@@ -283,7 +285,7 @@ __device__ __forceinline__ void gru_epilogue(uint32_t tq, uint32_t region, uint3
 #pragma unroll
     for (int j = 0; j < N; ++j) {
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {   // the two rollouts of this thread in the chunk
+        for (int q = 0; q < (HALF ? 1 : 2); ++q) {   // the two rollouts of this thread in the chunk
             const F2 tr = fma2(f2bits(R[j][2 * q], R[j][2 * q + 1]), CN2, f2(k0[j].x, k0[j].y));    // -log2e * pre-activation
             const F2 tz = fma2(f2bits(Z[j][2 * q], Z[j][2 * q + 1]), CN2, f2(k0[j].z, k0[j].w));
             const F2 AR = add2(f2(ex2_f(fminf(lo(tr), 30.0f)), ex2_f(fminf(hi(tr), 30.0f))), ONE);   // 1 + e^{-r}
