@@ -44,8 +44,8 @@ __global__ void __launch_bounds__(TC_NT, 1) net_tc_kernel(const __grid_constant_
     __shared__ uint32_t s_tmem;
     // mbarriers: 0 weights landed; 1..3 region r complete (issuer -> epilogue); 4 output layer complete (issuer -> rows);
     // 5..8 epilogue of job 1a / 1b / 2a / 2b done (8 epilogue warps -> issuer); 9 next input written (4 row warps ->
-    // issuer); 10 hidden-state update after the solve
-    __shared__ __align__(8) unsigned long long s_bars[11];
+    // issuer); 10 hidden-state update after the solve; 11 region of job 1a loaded into registers (8 epilogue warps -> issuer)
+    __shared__ __align__(8) unsigned long long s_bars[12];
     __shared__ unsigned s_ticket;
     __shared__ float s_bmin[4];
 #ifdef CPS_TC_TRACE
@@ -65,7 +65,10 @@ __global__ void __launch_bounds__(TC_NT, 1) net_tc_kernel(const __grid_constant_
     const int rpq = a.tc_rows >> 2;            // live rollouts per lane quarter: 8 | 16 | 32
     const int row0 = blockIdx.x * a.tc_rows;
     const bool live = lane < rpq;              // per lane; dead lanes run along on clamped indices and store nothing
-    const int k = row0 + rpq * (warp & 3) + lane;
+    // 32 live rollouts: the hi / lo parts of a rollout's operands are stacked in rows r and r + 8 (gru_epilogue<.., STACK>);
+    // the epilogue warps' lanes r + 8 then work on the rollout of lane r
+    const bool stk = rpq == 8;
+    const int k = row0 + rpq * (warp & 3) + ((stk && is_epi) ? (lane & 7) : lane);
     const bool active = is_row && live && k < a.B;
     const int kc = min(k, a.B - 1);
     float *s_f = reinterpret_cast<float *>(smem + O_FLOATS);
@@ -78,7 +81,7 @@ __global__ void __launch_bounds__(TC_NT, 1) net_tc_kernel(const __grid_constant_
     const float *cst2 = reinterpret_cast<const float *>(smem + O_CST2);
     const float *csto = reinterpret_cast<const float *>(smem + O_CSTO);   // [16][2] output layer, then {c, cn} of the two layers
     const uint32_t sm0 = smem_u32(smem), bars = smem_u32(s_bars);
-    const uint32_t wbar = bars, outb = bars + 32, xrdy = bars + 72, tailb = bars + 80;
+    const uint32_t wbar = bars, outb = bars + 32, xrdy = bars + 72, tailb = bars + 80, ldb = bars + 88;
     auto doneb = [&](int r) { return bars + 8u + 8u * (uint32_t)r; };
     auto epib = [&](int job) { return bars + 40u + 8u * (uint32_t)job; };
 
@@ -90,6 +93,7 @@ __global__ void __launch_bounds__(TC_NT, 1) net_tc_kernel(const __grid_constant_
         for (int j = 0; j < 4; ++j) bar_init(epib(j), TC_EW / 2);   // a job is one group's: 8 warps
         bar_init(xrdy, 4);
         bar_init(tailb, 1);
+        bar_init(ldb, TC_EW / 2);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(wbar), "r"(TC_IMAGE_BYTES) : "memory");
         for (uint32_t done = 0; done < TC_IMAGE_BYTES; done += 32768u) {
@@ -153,7 +157,7 @@ __global__ void __launch_bounds__(TC_NT, 1) net_tc_kernel(const __grid_constant_
     };
     // network input x = [control, state features] -> shared-memory A operand of the first layer (K padded to 16; k >= 8 is
     // zero for good).  Followed by the generic -> async proxy fence the tensor core's read needs.
-    auto write_x = [&](float ctrl, const float (&feat)[6]) {
+    auto write_x = [&](float ctrl, const float (&feat)[6], bool stacked) {
         float x[8];
         x[0] = fmaf(N.norm_a[0], ctrl, N.norm_b[0]);
 #pragma unroll
@@ -169,8 +173,13 @@ __global__ void __launch_bounds__(TC_NT, 1) net_tc_kernel(const __grid_constant_
             pl[q] = pack_h2(l0, l1);
         }
         const uint32_t off = (uint32_t)(row >> 3) * 256u + (uint32_t)(row & 7) * 16u;
-        *reinterpret_cast<uint4 *>(smem + O_X_HI + off) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-        *reinterpret_cast<uint4 *>(smem + O_X_LO + off) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+        if (!stacked) {
+            *reinterpret_cast<uint4 *>(smem + O_X_HI + off) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+            *reinterpret_cast<uint4 *>(smem + O_X_LO + off) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+        } else if (live) {   // rows r and r + 8 of the hi tile (the next 8-row core matrix); lanes 8.. own no row
+            *reinterpret_cast<uint4 *>(smem + O_X_HI + off) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+            *reinterpret_cast<uint4 *>(smem + O_X_HI + off + 256u) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+        }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     };
     // this thread's units of a layer, chunk ch = 0, 1: [32 ch + 8 sub, + 8) -- the units it handles in job (layer, ch)
@@ -189,7 +198,8 @@ __global__ void __launch_bounds__(TC_NT, 1) net_tc_kernel(const __grid_constant_
                 const int u0 = chunk_u0(ch);
 #pragma unroll
                 for (int i = 0; i < TC_EU; ++i) v[i] = a.h0[(long long)kc * a.hs_b + l * TC_H + u0 + i];
-                write_operand8(tl, (l ? C_AH2_HI : C_AH1_HI) + (u0 >> 1), (l ? C_AH2_LO : C_AH1_LO) + (u0 >> 1), v);
+                if (stk) write_operand8_stacked(tl, (l ? C_AH2_HI : C_AH1_HI) + (u0 >> 1), v, lane);
+                else write_operand8(tl, (l ? C_AH2_HI : C_AH1_HI) + (u0 >> 1), (l ? C_AH2_LO : C_AH1_LO) + (u0 >> 1), v);
             }
         }
     }
@@ -200,7 +210,7 @@ __global__ void __launch_bounds__(TC_NT, 1) net_tc_kernel(const __grid_constant_
 #pragma unroll
         for (int i = 0; i < 6; ++i)
             feat[i] = (i < N.n_state_in) ? fmaf(N.norm_a[1 + i], a.s0[(long long)kc * a.ss_b + N.in_idx[i]], N.norm_b[1 + i]) : 0.0f;
-        write_x(u_nxt, feat);
+        write_x(u_nxt, feat, stk);
     }
     bar_wait(wbar, 0);   // weights have landed
     tc_sync();
@@ -215,8 +225,8 @@ __global__ void __launch_bounds__(TC_NT, 1) net_tc_kernel(const __grid_constant_
         const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
         const uint32_t ah1_hi = tm + C_AH1_HI, ah1_lo = tm + C_AH1_LO, ah2_hi = tm + C_AH2_HI, ah2_lo = tm + C_AH2_LO;
         // recurrent parts of the first two jobs (1a, 1b of step 0); job j accumulates in region j mod 3
-        issue_H(tm + 0, ah1_hi, ah1_lo, sm0 + O_WHH1_HI, sm0 + O_WHH1_LO, 0);
-        issue_H(tm + 128, ah1_hi, ah1_lo, sm0 + O_WHH1_HI, sm0 + O_WHH1_LO, 1);
+        issue_H(tm + 0, ah1_hi, ah1_lo, sm0 + O_WHH1_HI, sm0 + O_WHH1_LO, 0, stk);
+        issue_H(tm + 128, ah1_hi, ah1_lo, sm0 + O_WHH1_HI, sm0 + O_WHH1_LO, 1, stk);
         int t3 = 0;   // t mod 3 = (4 t) mod 3: region index of job 1a of this step
 #pragma unroll 1
         for (int t = 0; t < T; ++t) {
@@ -228,36 +238,41 @@ __global__ void __launch_bounds__(TC_NT, 1) net_tc_kernel(const __grid_constant_
             TC_TR(0);
             if (t > 0) { bar_wait(xrdy, (uint32_t)((t - 1) & 1)); tc_fence_after(); }   // x(t) is in shared memory
             TC_TR(1);
-            issue_X1(q0, AX_HI, AX_LO, sm0 + O_WIH1_HI, sm0 + O_WIH1_LO, 0);
+            issue_X1(q0, AX_HI, AX_LO, sm0 + O_WIH1_HI, sm0 + O_WIH1_LO, 0, stk);
             tc_commit(doneb(t3));
-            issue_X1(q1, AX_HI, AX_LO, sm0 + O_WIH1_HI, sm0 + O_WIH1_LO, 1);
+            issue_X1(q1, AX_HI, AX_LO, sm0 + O_WIH1_HI, sm0 + O_WIH1_LO, 1, stk);
             tc_commit(doneb(i1));
             // (after the critical input products) recurrent part of job 2a; its region was read by job 2b of step t - 1
-            issue_H(q2, ah2_hi, ah2_lo, sm0 + O_WHH2_HI, sm0 + O_WHH2_LO, 0);
+            issue_H(q2, ah2_hi, ah2_lo, sm0 + O_WHH2_HI, sm0 + O_WHH2_LO, 0, stk);
             TC_TR(2);
-            bar_wait(epib(0), par); tc_fence_after();      // job 1a read: its region takes job 2b's recurrent part
+            // job 1a's region is consumed as soon as its epilogue warps hold it in registers (stacked mode): the recurrent part
+            // of job 2b goes there right away and runs under the gate arithmetic instead of between h1(t) and the second layer
+            if (stk) bar_wait(ldb, par);
+            else bar_wait(epib(0), par);
+            tc_fence_after();
             TC_TR(3);
-            issue_H(q0, ah2_hi, ah2_lo, sm0 + O_WHH2_HI, sm0 + O_WHH2_LO, 1);
+            issue_H(q0, ah2_hi, ah2_lo, sm0 + O_WHH2_HI, sm0 + O_WHH2_LO, 1, stk);
             TC_TR(4);
+            if (stk) bar_wait(epib(0), par);
             bar_wait(epib(1), par); tc_fence_after();      // h1(t) complete
             TC_TR(5);
-            issue_X2(q2, ah1_hi, ah1_lo, sm0 + O_WIH2_HI, sm0 + O_WIH2_LO, 0);
+            issue_X2(q2, ah1_hi, ah1_lo, sm0 + O_WIH2_HI, sm0 + O_WIH2_LO, 0, stk);
             tc_commit(doneb(i2));
-            issue_X2(q0, ah1_hi, ah1_lo, sm0 + O_WIH2_HI, sm0 + O_WIH2_LO, 1);
+            issue_X2(q0, ah1_hi, ah1_lo, sm0 + O_WIH2_HI, sm0 + O_WIH2_LO, 1, stk);
             tc_commit(doneb(t3));
-            if (more) issue_H(q1, ah1_hi, ah1_lo, sm0 + O_WHH1_HI, sm0 + O_WHH1_LO, 0);
+            if (more) issue_H(q1, ah1_hi, ah1_lo, sm0 + O_WHH1_HI, sm0 + O_WHH1_LO, 0, stk);
             TC_TR(6);
             bar_wait(epib(2), par); tc_fence_after();
             TC_TR(7);
             TC_TR(8);
             bar_wait(epib(3), par); tc_fence_after();      // h2(t) complete; the region of job 2b is idle
             TC_TR(9);
-            issue_OUT(q0 + C_NI, ah2_hi, ah2_lo, sm0 + O_WOUT_HI, sm0 + O_WOUT_LO);
+            issue_OUT(q0 + C_NI, ah2_hi, ah2_lo, sm0 + O_WOUT_HI, sm0 + O_WOUT_LO, stk);
             tc_commit(outb);
             TC_TR(10);
             // recurrent part of job 1b of the next step, behind the output layer: the tensor pipe executes in order, and in
             // front of it these 12 MMAs would sit between h2(t) and x(t + 1); here they run under the row warps' feedback
-            if (more) issue_H(q2, ah1_hi, ah1_lo, sm0 + O_WHH1_HI, sm0 + O_WHH1_LO, 1);
+            if (more) issue_H(q2, ah1_hi, ah1_lo, sm0 + O_WHH1_HI, sm0 + O_WHH1_LO, 1, stk);
             t3 = i1;
         }
     } else if (is_epi) {
@@ -285,9 +300,10 @@ __global__ void __launch_bounds__(TC_NT, 1) net_tc_kernel(const __grid_constant_
                 } else if (rpq > 8) {   // 16 rollouts x this warp's 16 units in one interleaved pass
                     gru_epilogue<2, true>(tl, region(j), (uint32_t)(16 * hs), l ? cst2 : cst1, l ? ec2 : ec1, l ? ecn2 : ecn1,
                                           l ? C_AH2_HI : C_AH1_HI, l ? C_AH2_LO : C_AH1_LO, 32 * g + 16 * hs, lane);
-                } else {   // 8 rollouts: one per thread and chunk
+                } else {   // 8 rollouts, hi / lo rows stacked: one rollout per thread and chunk, two-pass MMAs
                     gru_epilogue<2, true, true>(tl, region(j), (uint32_t)(16 * hs), l ? cst2 : cst1, l ? ec2 : ec1, l ? ecn2 : ecn1,
-                                                l ? C_AH2_HI : C_AH1_HI, l ? C_AH2_LO : C_AH1_LO, 32 * g + 16 * hs, lane);
+                                                l ? C_AH2_HI : C_AH1_HI, l ? C_AH2_LO : C_AH1_LO, 32 * g + 16 * hs, lane,
+                                                job == 0 ? ldb : 0u);   // job 1a tells the issuer when its region is in registers
                 }
                 if (warp == 8 * g) TC_TR(16 + 4 * job + 2);
                 warp_signal(epib(job), lane);
@@ -326,9 +342,14 @@ __global__ void __launch_bounds__(TC_NT, 1) net_tc_kernel(const __grid_constant_
                 uint32_t o[8];
                 ld8(tl + region(4 * t + 6) + C_NI, o);
                 ld_wait();
+                if (stk) {   // row r + 8 holds the product with the lo parts of h2
+#pragma unroll
+                    for (int i = 0; i < 6; ++i)
+                        o[i] = __float_as_uint(__uint_as_float(o[i]) + __shfl_down_sync(0xffffffffu, __uint_as_float(o[i]), 8));
+                }
 #pragma unroll
                 for (int i = 0; i < 6; ++i) y[i] = (i < N.n_out) ? fmaf(__uint_as_float(o[i]), csto[2 * i], csto[2 * i + 1]) : 0.0f;
-                if (t + 1 < T) write_x(u_nxt, y);
+                if (t + 1 < T) write_x(u_nxt, y, stk);
             }
             if (t + 1 < T) {
                 tc_fence_before();
@@ -377,14 +398,15 @@ __global__ void __launch_bounds__(TC_NT, 1) net_tc_kernel(const __grid_constant_
             }
         }
     }
-    auto store_hidden = [&](float *dst) {  // this epilogue thread's 2 x 2 x 8 units of the current hidden state
+    auto store_hidden = [&](float *dst, bool stacked) {  // this epilogue thread's 2 x 2 x 8 units of the current hidden state
         float v[TC_EU];
 #pragma unroll 1
         for (int l = 0; l < 2; ++l) {
 #pragma unroll 1
             for (int ch = 0; ch < 2; ++ch) {
                 const int u0 = chunk_u0(ch);
-                read_operand8(tl, (l ? C_AH2_HI : C_AH1_HI) + (u0 >> 1), (l ? C_AH2_LO : C_AH1_LO) + (u0 >> 1), v);
+                if (stacked) read_operand8_stacked(tl, (l ? C_AH2_HI : C_AH1_HI) + (u0 >> 1), v);
+                else read_operand8(tl, (l ? C_AH2_HI : C_AH1_HI) + (u0 >> 1), (l ? C_AH2_LO : C_AH1_LO) + (u0 >> 1), v);
                 if (dst) {
 #pragma unroll
                     for (int i = 0; i < TC_EU; ++i) dst[l * TC_H + u0 + i] = v[i];
@@ -392,7 +414,7 @@ __global__ void __launch_bounds__(TC_NT, 1) net_tc_kernel(const __grid_constant_
             }
         }
     };
-    if (a.h_final && is_epi) store_hidden((live && k < a.B) ? a.h_final + (long long)k * (2 * TC_H) : nullptr);
+    if (a.h_final && is_epi) store_hidden((live && k < a.B) ? a.h_final + (long long)k * (2 * TC_H) : nullptr, stk);
 
     bool last = false;
     if (MPPI) {
@@ -454,15 +476,15 @@ __global__ void __launch_bounds__(TC_NT, 1) net_tc_kernel(const __grid_constant_
 #pragma unroll
                 for (int i = 0; i < 6; ++i)
                     feat[i] = (i < N.n_state_in) ? fmaf(N.norm_a[1 + i], a.s0[N.in_idx[i]], N.norm_b[1 + i]) : 0.0f;
-                write_x(u_sel, feat);
+                write_x(u_sel, feat, false);
             }
             tc_sync();
             const uint32_t tmu = __shfl_sync(0xffffffffu, tmem, 0);   // warp-uniform for the issuer (see tc_mma)
             if (is_mma) {
-                issue_H(tmu + 0, tmu + C_AH1_HI, tmu + C_AH1_LO, sm0 + O_WHH1_HI, sm0 + O_WHH1_LO, 0);
-                issue_X1(tmu + 0, AX_HI, AX_LO, sm0 + O_WIH1_HI, sm0 + O_WIH1_LO, 0);
-                issue_H(tmu + 128, tmu + C_AH1_HI, tmu + C_AH1_LO, sm0 + O_WHH1_HI, sm0 + O_WHH1_LO, 1);
-                issue_X1(tmu + 128, AX_HI, AX_LO, sm0 + O_WIH1_HI, sm0 + O_WIH1_LO, 1);
+                issue_H(tmu + 0, tmu + C_AH1_HI, tmu + C_AH1_LO, sm0 + O_WHH1_HI, sm0 + O_WHH1_LO, 0, false);
+                issue_X1(tmu + 0, AX_HI, AX_LO, sm0 + O_WIH1_HI, sm0 + O_WIH1_LO, 0, false);
+                issue_H(tmu + 128, tmu + C_AH1_HI, tmu + C_AH1_LO, sm0 + O_WHH1_HI, sm0 + O_WHH1_LO, 1, false);
+                issue_X1(tmu + 128, AX_HI, AX_LO, sm0 + O_WIH1_HI, sm0 + O_WIH1_LO, 1, false);
                 tc_commit(tailb);
             }
             bar_wait(tailb, 0);
@@ -473,10 +495,10 @@ __global__ void __launch_bounds__(TC_NT, 1) net_tc_kernel(const __grid_constant_
             }
             tc_sync();
             if (is_mma) {
-                issue_H(tmu + 256, tmu + C_AH2_HI, tmu + C_AH2_LO, sm0 + O_WHH2_HI, sm0 + O_WHH2_LO, 0);
-                issue_X2(tmu + 256, tmu + C_AH1_HI, tmu + C_AH1_LO, sm0 + O_WIH2_HI, sm0 + O_WIH2_LO, 0);
-                issue_H(tmu + 0, tmu + C_AH2_HI, tmu + C_AH2_LO, sm0 + O_WHH2_HI, sm0 + O_WHH2_LO, 1);
-                issue_X2(tmu + 0, tmu + C_AH1_HI, tmu + C_AH1_LO, sm0 + O_WIH2_HI, sm0 + O_WIH2_LO, 1);
+                issue_H(tmu + 256, tmu + C_AH2_HI, tmu + C_AH2_LO, sm0 + O_WHH2_HI, sm0 + O_WHH2_LO, 0, false);
+                issue_X2(tmu + 256, tmu + C_AH1_HI, tmu + C_AH1_LO, sm0 + O_WIH2_HI, sm0 + O_WIH2_LO, 0, false);
+                issue_H(tmu + 0, tmu + C_AH2_HI, tmu + C_AH2_LO, sm0 + O_WHH2_HI, sm0 + O_WHH2_LO, 1, false);
+                issue_X2(tmu + 0, tmu + C_AH1_HI, tmu + C_AH1_LO, sm0 + O_WIH2_HI, sm0 + O_WIH2_LO, 1, false);
                 tc_commit(tailb);
             }
             bar_wait(tailb, 1);
@@ -485,7 +507,7 @@ __global__ void __launch_bounds__(TC_NT, 1) net_tc_kernel(const __grid_constant_
                 gru_epilogue<1, true>(tl, 256, (uint32_t)(TC_EU * sub), cst2, ec2, ecn2, C_AH2_HI, C_AH2_LO, chunk_u0(0), lane);
                 gru_epilogue<1, true>(tl, 0, (uint32_t)(TC_EU * sub), cst2, ec2, ecn2, C_AH2_HI, C_AH2_LO, chunk_u0(1), lane);
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-                store_hidden(row == 0 ? a.h_ref : nullptr);
+                store_hidden(row == 0 ? a.h_ref : nullptr, false);
             }
         }
     }

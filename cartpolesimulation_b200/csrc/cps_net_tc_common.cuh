@@ -173,12 +173,41 @@ __device__ __forceinline__ void read_operand8(uint32_t tl, uint32_t c_hi, uint32
     }
 }
 
+// Stacked layout (see gru_epilogue): row r of a 16-row group holds the hi parts, row r + 8 the lo parts, both in the HI region.
+// v: the values of rollout (lane & 7) of the quarter; lanes with bit 3 set write the lo parts.
+__device__ __forceinline__ void write_operand8_stacked(uint32_t tl, uint32_t c_hi, const float (&v)[8], int lane) {
+    uint32_t p[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        __half h0, l0, h1, l1;
+        split_h(v[2 * q] * A_SCALE, h0, l0);
+        split_h(v[2 * q + 1] * A_SCALE, h1, l1);
+        p[q] = (lane & 8) ? pack_h2(l0, l1) : pack_h2(h0, h1);
+    }
+    st4(tl + c_hi, p);
+}
+// ... and back: valid in the lanes r < 8 of every 16-row group (whole warp calls)
+__device__ __forceinline__ void read_operand8_stacked(uint32_t tl, uint32_t c_hi, float (&v)[8]) {
+    uint32_t p[4];
+    ld4(tl + c_hi, p);
+    ld_wait();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float2 h = unpack_h2(p[q]);
+        v[2 * q] = (h.x + __shfl_down_sync(0xffffffffu, h.x, 8)) * A_INV;
+        v[2 * q + 1] = (h.y + __shfl_down_sync(0xffffffffu, h.y, 8)) * A_INV;
+    }
+}
+
 // ---- MMA issue (issuer warp, converged).  Half-layer job jh of a layer: weight rows [96 jh, 96 jh + 96). ----------------
 // Recurrent part W_hh h: one N = 96 MMA per pass and k-step -> {NH, R, Z} of the region, overwriting it.
-__device__ __forceinline__ void issue_H(uint32_t region, uint32_t ah_hi, uint32_t ah_lo, uint32_t bh_hi, uint32_t bh_lo, int jh) {
+// stk (warp-uniform): the A operand carries the hi parts in rows r and the lo parts in rows r + 8 of every 16-row group
+// ("stacked", see gru_epilogue): the a_lo pass is skipped, rows r + 8 accumulate it beside rows r in the SAME two MMAs.
+__device__ __forceinline__ void issue_H(uint32_t region, uint32_t ah_hi, uint32_t ah_lo, uint32_t bh_hi, uint32_t bh_lo, int jh, bool stk) {
     const uint32_t row = (uint32_t)jh * 12288u;   // 96 rows x (64 / 8) x 128 B / 8
 #pragma unroll
     for (int pass = 0; pass < 3; ++pass) {
+        if (stk && pass == 1) continue;
         const uint32_t a = (pass == 1) ? ah_lo : ah_hi, b = ((pass == 2) ? bh_lo : bh_hi) + row;
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks)
@@ -187,10 +216,11 @@ __device__ __forceinline__ void issue_H(uint32_t region, uint32_t ah_hi, uint32_
 }
 // Input part of the second layer, W_ih2 h1 (K = 64): {R, Z} accumulate on top of the recurrent part, NI is written fresh
 // by the first MMA (split in two for that) and accumulated by the rest.
-__device__ __forceinline__ void issue_X2(uint32_t region, uint32_t ah_hi, uint32_t ah_lo, uint32_t bx_hi, uint32_t bx_lo, int jh) {
+__device__ __forceinline__ void issue_X2(uint32_t region, uint32_t ah_hi, uint32_t ah_lo, uint32_t bx_hi, uint32_t bx_lo, int jh, bool stk) {
     const uint32_t row = (uint32_t)jh * 12288u;
 #pragma unroll
     for (int pass = 0; pass < 3; ++pass) {
+        if (stk && pass == 1) continue;
         const uint32_t a = (pass == 1) ? ah_lo : ah_hi, b = ((pass == 2) ? bx_lo : bx_hi) + row;
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
@@ -204,10 +234,11 @@ __device__ __forceinline__ void issue_X2(uint32_t region, uint32_t ah_hi, uint32
     }
 }
 // Input part of the first layer, W_ih1 x (K = 16, A operand x in shared memory).
-__device__ __forceinline__ void issue_X1(uint32_t region, uint32_t ax_hi, uint32_t ax_lo, uint32_t bx_hi, uint32_t bx_lo, int jh) {
+__device__ __forceinline__ void issue_X1(uint32_t region, uint32_t ax_hi, uint32_t ax_lo, uint32_t bx_hi, uint32_t bx_lo, int jh, bool stk) {
     const uint32_t row = (uint32_t)jh * 3072u;    // 96 rows x (16 / 8) x 128 B / 8
 #pragma unroll
     for (int pass = 0; pass < 3; ++pass) {
+        if (stk && pass == 1) continue;
         const uint64_t a = make_desc((pass == 1) ? ax_lo : ax_hi, 256);
         const uint32_t b = ((pass == 2) ? bx_lo : bx_hi) + row;
         if (pass == 0) {
@@ -219,9 +250,10 @@ __device__ __forceinline__ void issue_X1(uint32_t region, uint32_t ax_hi, uint32
     }
 }
 // Linear output layer W_out h2 -> 16 columns at `dst`.
-__device__ __forceinline__ void issue_OUT(uint32_t dst, uint32_t ah_hi, uint32_t ah_lo, uint32_t b_hi, uint32_t b_lo) {
+__device__ __forceinline__ void issue_OUT(uint32_t dst, uint32_t ah_hi, uint32_t ah_lo, uint32_t b_hi, uint32_t b_lo, bool stk) {
 #pragma unroll
     for (int pass = 0; pass < 3; ++pass) {
+        if (stk && pass == 1) continue;
         const uint32_t a = (pass == 1) ? ah_lo : ah_hi, b = (pass == 2) ? b_lo : b_hi;
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks)
@@ -259,11 +291,15 @@ __device__ __forceinline__ uint32_t pack_f16x2(float lo_v, float hi_v) {   // tw
 // N chunks of 16 rollouts x 8 units per call, interleaved for instruction-level parallelism (2 N independent dependence
 // chains per thread): UNITS -> the chunks are consecutive 8-unit groups of the same 16 rollouts (64 live rollouts per CTA),
 // else -> the same 8 units of the two 16-lane halves of the quarter (128 live rollouts).
-// HALF: only the rollouts t / 4 are live (32 live rollouts per CTA, 8 per lane quarter): the second rollout of every thread is
-// skipped, its operand columns are written back as read.
-template <int N, bool UNITS, bool HALF = false>
+// ldbar != 0: mbarrier that counts this warp once its tensor-memory loads have completed, i.e. before the arithmetic.
+// STACK: 32 live rollouts per CTA, 8 per lane quarter (rows t / 4), and the dead rows 8 + t / 4 put to work: the A operand
+// holds the fp16 hi part of a rollout's hidden state in row r and the lo part in row r + 8, so ONE MMA per weight part
+// computes hi * W in row r and lo * W in row r + 8 -- two passes (W_hi, W_lo) instead of three, and the dropped lo * lo term
+// comes for free.  The 16-lane access shapes hand a thread exactly that pair of rows: the two accumulator rows are added
+// here, and one 16x128b access moves the {hi, lo} operand pair (no separate lo region).
+template <int N, bool UNITS, bool STACK = false>
 __device__ __forceinline__ void gru_epilogue(uint32_t tq, uint32_t region, uint32_t cu, const float *cst, float c, float cn,
-                                              uint32_t c_hi, uint32_t c_lo, int u0, int lane) {
+                                              uint32_t c_hi, uint32_t c_lo, int u0, int lane, uint32_t ldbar = 0) {
     uint32_t R[N][4], Z[N][4], NI[N][4], NH[N][4], PH[N][2], PL[N][2];
     float4 k0[N], k1[N];
 #pragma unroll
@@ -275,38 +311,49 @@ __device__ __forceinline__ void gru_epilogue(uint32_t tq, uint32_t region, uint3
         ld16x256(th + region + C_NI + cj, NI[j]);
         ld16x256(th + region + C_NH + cj, NH[j]);
         ld16x128(th + c_hi + (uj >> 1), PH[j]);
-        ld16x128(th + c_lo + (uj >> 1), PL[j]);
+        if (!STACK) ld16x128(th + c_lo + (uj >> 1), PL[j]);
         const float *kp = cst + ((uj >> 1) + (lane & 3)) * 8;
         k0[j] = *reinterpret_cast<const float4 *>(kp);       // brn0, brn1, bzn0, bzn1
         k1[j] = *reinterpret_cast<const float4 *>(kp + 4);   // bni0, bni1, bnh0, bnh1
     }
     const F2 C2 = f2(c), CN2 = f2(cn), ONE = f2(1.0f);
     ld_wait();
+    if (ldbar) {   // the region is in registers: the issuer may overwrite it (one arrival per warp)
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) bar_arrive(ldbar);
+    }
 #pragma unroll
     for (int j = 0; j < N; ++j) {
 #pragma unroll
-        for (int q = 0; q < (HALF ? 1 : 2); ++q) {   // the two rollouts of this thread in the chunk
-            const F2 tr = fma2(f2bits(R[j][2 * q], R[j][2 * q + 1]), CN2, f2(k0[j].x, k0[j].y));    // -log2e * pre-activation
-            const F2 tz = fma2(f2bits(Z[j][2 * q], Z[j][2 * q + 1]), CN2, f2(k0[j].z, k0[j].w));
+        for (int q = 0; q < (STACK ? 1 : 2); ++q) {   // the two rollouts of this thread in the chunk (STACK: one, in two rows)
+            const F2 aR = STACK ? add2(f2bits(R[j][0], R[j][1]), f2bits(R[j][2], R[j][3])) : f2bits(R[j][2 * q], R[j][2 * q + 1]);
+            const F2 aZ = STACK ? add2(f2bits(Z[j][0], Z[j][1]), f2bits(Z[j][2], Z[j][3])) : f2bits(Z[j][2 * q], Z[j][2 * q + 1]);
+            const F2 aNH = STACK ? add2(f2bits(NH[j][0], NH[j][1]), f2bits(NH[j][2], NH[j][3])) : f2bits(NH[j][2 * q], NH[j][2 * q + 1]);
+            const F2 aNI = STACK ? add2(f2bits(NI[j][0], NI[j][1]), f2bits(NI[j][2], NI[j][3])) : f2bits(NI[j][2 * q], NI[j][2 * q + 1]);
+            const F2 tr = fma2(aR, CN2, f2(k0[j].x, k0[j].y));    // -log2e * pre-activation
+            const F2 tz = fma2(aZ, CN2, f2(k0[j].z, k0[j].w));
             const F2 AR = add2(f2(ex2_f(fminf(lo(tr), 30.0f)), ex2_f(fminf(hi(tr), 30.0f))), ONE);   // 1 + e^{-r}
             const F2 AZ = add2(f2(ex2_f(fminf(lo(tz), 30.0f)), ex2_f(fminf(hi(tz), 30.0f))), ONE);
             const F2 PA = mul2(AR, AZ);
             const float inv = rcp_f(lo(PA) * hi(PA));
             const F2 IAB = mul2(f2(hi(PA), lo(PA)), f2(inv));          // 1 / (ar az) of each unit
             const F2 R2 = mul2(AZ, IAB), Z2 = mul2(AR, IAB);           // sigmoids
-            const F2 tnh = fma2(f2bits(NH[j][2 * q], NH[j][2 * q + 1]), C2, f2(k1[j].z, k1[j].w));
-            const F2 tni = fma2(f2bits(NI[j][2 * q], NI[j][2 * q + 1]), C2, f2(k1[j].x, k1[j].y));
+            const F2 tnh = fma2(aNH, C2, f2(k1[j].z, k1[j].w));
+            const F2 tni = fma2(aNI, C2, f2(k1[j].x, k1[j].y));
             const F2 ta = mul2(fma2(R2, tnh, tni), f2(2.885390081777927f));               // 2 log2e * n pre-activation
             const F2 E = add2(f2(ex2_f(fminf(lo(ta), 30.0f)), ex2_f(fminf(hi(ta), 30.0f))), ONE);   // 1 + e^{2n}
             const float m2 = -256.0f * rcp_f(lo(E) * hi(E));
             const F2 N128 = fma2(f2(hi(E), lo(E)), f2(m2), f2(128.0f));   // 128 tanh = 128 - 256 / (1 + e^{2n})
-            const float2 hh_ = unpack_h2(PH[j][q]), hl = unpack_h2(PL[j][q]);
+            const float2 hh_ = unpack_h2(PH[j][STACK ? 0 : q]), hl = unpack_h2(STACK ? PH[j][1] : PL[j][q]);
             const F2 HS = add2(f2(hh_.x, hh_.y), f2(hl.x, hl.y));        // 128 h(t-1)
             const F2 HN = fma2(HS, Z2, fma2(neg2(N128), Z2, N128));      // 128 h(t) = 128 ((h - n) z + n)
-            PH[j][q] = pack_f16x2(lo(HN), hi(HN));
-            const float2 hf = unpack_h2(PH[j][q]);
+            const uint32_t p_hi = pack_f16x2(lo(HN), hi(HN));
+            const float2 hf = unpack_h2(p_hi);
             const F2 L = add2(HN, f2(-hf.x, -hf.y));
-            PL[j][q] = pack_f16x2(lo(L), hi(L));
+            const uint32_t p_lo = pack_f16x2(lo(L), hi(L));
+            if (STACK) { PH[j][0] = p_hi; PH[j][1] = p_lo; }
+            else { PH[j][q] = p_hi; PL[j][q] = p_lo; }
         }
     }
 #pragma unroll
@@ -314,7 +361,7 @@ __device__ __forceinline__ void gru_epilogue(uint32_t tq, uint32_t region, uint3
         const uint32_t th = tq + ((uint32_t)(UNITS ? 0 : 16 * j) << 16);
         const int uj = u0 + (UNITS ? 8 * j : 0);
         st16x128(th + c_hi + (uj >> 1), PH[j]);
-        st16x128(th + c_lo + (uj >> 1), PL[j]);
+        if (!STACK) st16x128(th + c_lo + (uj >> 1), PL[j]);
     }
 }
 

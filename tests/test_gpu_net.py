@@ -294,7 +294,7 @@ def test_tc_rollout_vs_reference_golden():
     assert max(traj_err(traj3.permute(2, 0, 1).cpu().numpy(), z["traj_rand"]).values()) < 1e-5
 
 
-@pytest.mark.parametrize("B,T", [(1, 1), (129, 3), (2000, 50), (20000, 10)])
+@pytest.mark.parametrize("B,T", [(1, 1), (129, 3), (2000, 50), (4736, 4), (4737, 4), (6000, 10), (20000, 10)])
 def test_tc_rollout_vs_oracle_sizes(B, T):
     import torch
     from oracle import oracle as O
@@ -315,6 +315,41 @@ def test_tc_rollout_vs_oracle_sizes(B, T):
     assert e.pop("angle") < 1e-4     # atan2 of small-norm outputs, see test_net_rollout_vs_oracle_sizes
     assert max(e.values()) < 3e-6, e
     assert np.abs(hf.cpu().numpy() - href).max() < 5e-6
+
+
+def test_tc_live_rollouts_per_cta_modes(monkeypatch):
+    """the three tile occupancies of net_tc_kernel (32 / 64 / 128 live rollouts per CTA; chosen by batch size, forced here).
+    64 and 128: every rollout's arithmetic is the same -> bit-identical trajectories and costs, the control differs only by
+    the order of the block partials.  32: the hi / lo operand parts are stacked in two tensor-memory rows (two MMA passes,
+    lo * lo term included) -> equal to rounding."""
+    import torch
+    from cartpolesimulation_b200 import _lib as L
+    z, m = load_golden("mppi_net_gru64_gradmin")
+    sp = net_spec_from_golden(z)
+    K, T = 1000, 20
+    rng = np.random.default_rng(5)
+    noise_np = rng.standard_normal((K, 16)).astype(np.float32)
+    out = {}
+    for r in (32, 64, 128):
+        monkeypatch.setenv("CPS_TC_ROWS", str(r))
+        eng = make_engine(sp, K, T, cost="quadratic_boundary_grad_minimal", net_kernel="tensor")
+        noise = torch.from_numpy(noise_np[:, :eng.n_ind].copy()).to(eng.device)
+        J = torch.empty(K, device=eng.device)
+        traj = torch.empty((K, T + 1, 6), device=eng.device)
+        u = eng.mppi_step(torch.from_numpy(z["s"][1]).to(eng.device), noise, L.ROLLOUT_MAJOR, 0.0, None, J, traj, L.ROLLOUT_MAJOR)
+        torch.cuda.synchronize()
+        out[r] = (float(u.cpu()[0]), J.cpu().numpy(), traj.cpu().numpy(), eng.get_u_nom(), eng.net_get_state())
+        assert eng.nonfinite_costs() == 0
+    a, b, c = out[64], out[128], out[32]
+    assert np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    for x in (b, c):
+        assert abs(a[0] - x[0]) < 1e-6
+        np.testing.assert_allclose(a[3], x[3], rtol=0, atol=1e-6)
+        np.testing.assert_allclose(a[4], x[4], rtol=0, atol=1e-6)
+    assert vec_err(c[1], a[1]) < 2e-6
+    e = traj_err(c[2], a[2])
+    record("tc_stacked_vs_three_pass", "K1000_T20", J=vec_err(c[1], a[1]), **e)
+    assert max(e.values()) < 1e-5, e
 
 
 def test_tc_mppi_vs_reference_golden():
