@@ -245,15 +245,14 @@ __global__ void __launch_bounds__(TC_NT, 1) net_tc_kernel(const __grid_constant_
             // (after the critical input products) recurrent part of job 2a; its region was read by job 2b of step t - 1
             issue_H(q2, ah2_hi, ah2_lo, sm0 + O_WHH2_HI, sm0 + O_WHH2_LO, 0, stk);
             TC_TR(2);
-            // job 1a's region is consumed as soon as its epilogue warps hold it in registers (stacked mode): the recurrent part
+            // job 1a's region is consumed as soon as its epilogue warps hold it in registers: the recurrent part
             // of job 2b goes there right away and runs under the gate arithmetic instead of between h1(t) and the second layer
-            if (stk) bar_wait(ldb, par);
-            else bar_wait(epib(0), par);
+            bar_wait(ldb, par);
             tc_fence_after();
             TC_TR(3);
             issue_H(q0, ah2_hi, ah2_lo, sm0 + O_WHH2_HI, sm0 + O_WHH2_LO, 1, stk);
             TC_TR(4);
-            if (stk) bar_wait(epib(0), par);
+            bar_wait(epib(0), par);
             bar_wait(epib(1), par); tc_fence_after();      // h1(t) complete
             TC_TR(5);
             issue_X2(q2, ah1_hi, ah1_lo, sm0 + O_WIH2_HI, sm0 + O_WIH2_LO, 0, stk);
@@ -295,11 +294,13 @@ __global__ void __launch_bounds__(TC_NT, 1) net_tc_kernel(const __grid_constant_
                     for (int e = 0; e < 2; ++e) {   // both 16-lane halves of 8 units at a time
                         const int cu = 16 * hs + 8 * e;   // first unit inside the job
                         gru_epilogue<2, false>(tl, region(j), (uint32_t)cu, l ? cst2 : cst1, l ? ec2 : ec1, l ? ecn2 : ecn1,
-                                               l ? C_AH2_HI : C_AH1_HI, l ? C_AH2_LO : C_AH1_LO, 32 * g + cu, lane);
+                                               l ? C_AH2_HI : C_AH1_HI, l ? C_AH2_LO : C_AH1_LO, 32 * g + cu, lane,
+                                               (job == 0 && e == 1) ? ldb : 0u);
                     }
                 } else if (rpq > 8) {   // 16 rollouts x this warp's 16 units in one interleaved pass
                     gru_epilogue<2, true>(tl, region(j), (uint32_t)(16 * hs), l ? cst2 : cst1, l ? ec2 : ec1, l ? ecn2 : ecn1,
-                                          l ? C_AH2_HI : C_AH1_HI, l ? C_AH2_LO : C_AH1_LO, 32 * g + 16 * hs, lane);
+                                          l ? C_AH2_HI : C_AH1_HI, l ? C_AH2_LO : C_AH1_LO, 32 * g + 16 * hs, lane,
+                                          job == 0 ? ldb : 0u);
                 } else {   // 8 rollouts, hi / lo rows stacked: one rollout per thread and chunk, two-pass MMAs
                     gru_epilogue<2, true, true>(tl, region(j), (uint32_t)(16 * hs), l ? cst2 : cst1, l ? ec2 : ec1, l ? ecn2 : ecn1,
                                                 l ? C_AH2_HI : C_AH1_HI, l ? C_AH2_LO : C_AH1_LO, 32 * g + 16 * hs, lane,
