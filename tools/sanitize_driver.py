@@ -46,7 +46,7 @@ def main(which):
             done.append(f"cem K={K}")
     if "net" in which:
         spec = synthetic_net_spec((64, 64), "GRU", seed=0)
-        for kern, K in (("tensor", 200), ("tensor", 9600), ("fp32", 200)):
+        for kern, K in (("tensor", 200), ("tensor", 4800), ("tensor", 9600), ("fp32", 200)):   # 32 / 64 / 128 live rollouts per CTA
             T = 4
             eng = Engine(K, T, integrator="neural", cost="quadratic_boundary_grad_minimal", device=0, net_kernel=kern)
             eng.net_load(spec)

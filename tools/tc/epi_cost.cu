@@ -1,4 +1,4 @@
-// Micro-benchmark of the tensor-core GRU kernel's gate epilogue (gru_epilogue8) in isolation: cycles per call for one
+// Micro-benchmark of the tensor-core GRU kernel's gate epilogue (gru_epilogue) in isolation: cycles per call for one
 // warp per scheduler, and how it splits into tensor-memory loads, arithmetic and stores.
 #include "../../cartpolesimulation_b200/csrc/cps_net_tc.cu"
 thread_local std::string g_create_err;   // cps_lib.cu's (this TU links alone)
@@ -48,8 +48,16 @@ __global__ void __launch_bounds__(544, 1) epi_bench(int warps_active, int reps, 
         long long best = 1LL << 60, tot = 0;
         for (int r = 0; r < reps; ++r) {
             const long long t0 = clock64();
-            if (mode == 0) {
-                gru_epilogue8(tl, 0, (uint32_t)(8 * sub), s_cst, 1e-3f, -1.4e-3f, C_AH1_HI, C_AH1_LO, 8 * sub);
+            const int lane = tid & 31, hs = (warp >> 2) & 1;
+            if (mode == 0) {          // 32 live rollouts per CTA: stacked hi / lo rows, one job of a warp
+                gru_epilogue<2, true, true>(tl, 0, (uint32_t)(16 * hs), s_cst, 1e-3f, -1.4e-3f, C_AH1_HI, C_AH1_LO, 16 * hs, lane);
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            } else if (mode == 3) {   // 64 live rollouts per CTA
+                gru_epilogue<2, true>(tl, 0, (uint32_t)(16 * hs), s_cst, 1e-3f, -1.4e-3f, C_AH1_HI, C_AH1_LO, 16 * hs, lane);
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            } else if (mode == 4) {   // 128 live rollouts per CTA: two calls per job
+                for (int e = 0; e < 2; ++e)
+                    gru_epilogue<2, false>(tl, 0, (uint32_t)(16 * hs + 8 * e), s_cst, 1e-3f, -1.4e-3f, C_AH1_HI, C_AH1_LO, 16 * hs + 8 * e, lane);
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             } else if (mode == 1) {   // loads only
                 uint32_t R[8], Z[8], NI[8], NH[8], PH[4], PL[4];
@@ -80,12 +88,12 @@ int main() {
     cudaMalloc(&d, 32);
     cudaFuncSetAttribute((const void *)epi_bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
     for (int bg = 0; bg < 3; ++bg)
-    for (int mode = 0; mode < 3; ++mode)
-        for (int w : {1, 4, 16}) {
+    for (int mode = 0; mode < 5; ++mode)
+        for (int w : {1, 4, 8, 16}) {
             epi_bench<<<1, 544, 65536>>>(w, 50, mode, d, bg);
             cudaDeviceSynchronize();
             cudaMemcpy(h, d, 32, cudaMemcpyDeviceToHost);
-            printf("bg MMAs %d: %s, %2d warps: best %lld mean %lld cycles per call (50 calls)\n", bg, mode == 0 ? "gru_epilogue8" : (mode == 1 ? "6 loads + wait " : "2 stores + wait"), w, h[0], h[2]);
+            printf("bg MMAs %d: %s, %2d warps: best %lld mean %lld cycles per call (50 calls)\n", bg, mode == 0 ? "job, 32 rollouts (stacked)" : mode == 3 ? "job, 64 rollouts" : mode == 4 ? "job, 128 rollouts" : (mode == 1 ? "6 loads + wait " : "2 stores + wait"), w, h[0], h[2]);
         }
     printf("status: %s\n", cudaGetErrorString(cudaGetLastError()));
     return 0;
