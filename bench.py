@@ -310,7 +310,7 @@ def planner_latency(device, n_calls=300):
         except Exception as ex:
             out[name] = {"error": repr(ex)}
     out["api"] = ("optimizer_cem_b200 / optimizer_cem_gmm_b200 / optimizer_random_action_b200 / optimizer_rpgd_b200 .step(numpy s) -> numpy u "
-                  "(cps_cem_step_host, cps_cem_gmm_step_host, cps_plan_random_action_host, cps_rpgd_grad_step; plan_kernel, plan_grad_kernel)")
+                  "(cps_cem_step_host, cps_cem_gmm_step_host, cps_plan_random_action_host, cps_rpgd_grad_step; plan_kernel, plan_grad_fwd_kernel + plan_grad_jacrev_kernel)")
     return out
 
 

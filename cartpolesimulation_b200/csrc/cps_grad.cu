@@ -5,15 +5,18 @@
 //     rollout_trajectory = predictor.predict_core(s, Q);  traj_cost = cost_function.get_trajectory_cost(traj, Q, u)
 // in a tf.GradientTape and take d(traj_cost)/dQ [K][T]: reverse-mode differentiation through T x n Euler-Cromer substeps
 // (SI_Toolkit/Predictors/predictor_ODE.py, CartPole/cartpole_equations.py:71-99, 245-262) and the cost plugin, with the
-// [K][T+1][6] trajectory and the tape in between.  Here it is ONE launch: every thread owns a plan,
-//   forward   integrates it (cos / sin from the angle every substep, as the reference's graph does), accumulates the cost
-//             and leaves a checkpoint (angle, angleD, position, positionD) per control step in a [T][4][K] workspace
-//             (coalesced: consecutive plans are consecutive addresses);
-//   backward  walks the control steps in reverse: re-integrates the n substeps of the step from its checkpoint keeping
-//             their inputs in local memory, then sweeps them backwards with the hand-derived adjoint of the substep
-//             (oracle/oracle.py:plan_cost_grad is the same derivation in numpy, checked against torch autograd through the
-//             unmodified reference modules, tests/golden/grad_*.npz), adding the cost plugin's partial derivatives at the
-//             control-step boundaries.
+// [K][T+1][6] trajectory and the tape in between.  Here it is three launches, and only the first and the cheap last one are
+// sequential in time:
+//   forward   (thread per plan) integrates it (cos / sin from the angle every substep, as the reference's graph does),
+//             accumulates the cost and leaves a checkpoint (angle, angleD, position, positionD) per control step in a
+//             [T][4][K] workspace (coalesced: consecutive plans are consecutive addresses);
+//   jacobians (thread per (control step, plan), T times the parallelism): re-integrates the n substeps of the step from its
+//             checkpoint and sweeps the four unit adjoints backwards through them with the hand-derived adjoint of the
+//             substep (oracle/oracle.py:plan_cost_grad is the same derivation in numpy, checked against torch autograd
+//             through the unmodified reference modules, tests/golden/grad_*.npz): the step's transposed Jacobian;
+//   reverse   (thread per plan) walks the control steps backwards: one 4 x 4 matrix-vector product per step plus the cost
+//             plugin's partial derivatives at the control-step boundaries.
+// (The first version did all of it in one thread per plan: 3 T n sequential substep evaluations, 0.124 ms for 16 plans.)
 // rpgd_update_kernel is the rest of grad_step (:176-180): tf.clip_by_norm per plan, the Adam step (Keras legacy Adam =
 // ResourceApplyAdam) and the clip to the control limits.
 // Cost plugin: quadratic_boundary_grad_minimal (the plugin the shipped RPGD configuration uses); predictor "ODE".
@@ -26,9 +29,11 @@
 #include "cps_internal.cuh"
 
 #define CPS_GRAD_MAX_SUBSTEPS 32
+#define CPS_GRAD_REC 20   /* floats per (control step, plan) record: M[3][4], r[4], cost partials (3), control term */
 
 struct GradState {
     float *d_ck;        // [T][4][K] checkpoints
+    float *d_jac;       // [T][CPS_GRAD_REC][K] transposed Jacobians of the control steps + boundary terms
     float *d_J;         // [K]
     float *d_G;         // [K][T]
     float *d_m, *d_v;   // Adam moments [K][T]
@@ -45,19 +50,31 @@ struct GradArgs {
     long long qs_k, qs_t;
     int K, T;
     float inv_T1;
-    float *ck, *J, *G;
+    float *ck, *jac, *J, *G;
     long long gs_k, gs_t;
     int *nonfinite;
 };
 
 namespace {
 
-struct Sub { float th, w, v; };
+// sincosf / cosf for the angles a rollout produces: fold_angle leaves every angle after the first substep in [-pi, pi], where
+// sincos_folded is bit-identical to the math library (cps_selftest_sincos); anything else (a caller-supplied unwrapped
+// initial angle) takes the library call, out of line.
+static __device__ __noinline__ void sincos_library(float a, float *s, float *c) { sincosf(a, s, c); }
+__device__ __forceinline__ void sincos_th(float th, float &s, float &c) {
+    if (__builtin_expect(fabsf(th) <= CPS_PI_F, 1)) sincos_folded(th, s, c);
+    else sincos_library(th, &s, &c);
+}
+
+struct Sub { float th, w, v, sn, c; };
 
 // One Euler-Cromer substep of predictor_ODE with cos / sin taken from the angle (cartpole_equations.py:71-99, 245-262).
-__device__ __forceinline__ void grad_substep(const OdeParams &P, float &th, float &w, float &x, float &v, float uk) {
-    float sn, c;
-    sincosf(th, &sn, &c);
+// Returns the substep's inputs (angle, angleD, positionD, sin, cos) for the reverse sweep.
+__device__ __forceinline__ Sub grad_substep(const OdeParams &P, float &th, float &w, float &x, float &v, float uk) {
+    Sub in;
+    in.th = th; in.w = w; in.v = v;
+    sincos_th(th, in.sn, in.c);
+    const float sn = in.sn, c = in.c;
     const float rA = rcp_pos<false>(fmaf(-P.m_p, c * c, P.KM));
     const float t1 = fmaf(-P.c2, w * w, P.c1 * c);
     const float num = fmaf(sn, t1, fmaf(-(P.c3 * w), c, fmaf(-P.c5, v, uk)));
@@ -67,6 +84,7 @@ __device__ __forceinline__ void grad_substep(const OdeParams &P, float &th, floa
     v = fmaf(xDD, P.h, v);
     th = fold_angle(fmaf(w, P.h, th));
     x = fmaf(v, P.h, x);
+    return in;
 }
 
 // quadratic_boundary_grad_minimal (Control_Toolkit_ASF/Cost_Functions/CartPole/quadratic_boundary_grad_minimal.py:62-130);
@@ -74,7 +92,7 @@ __device__ __forceinline__ void grad_substep(const OdeParams &P, float &th, floa
 __device__ __forceinline__ void gradmin_partials(const CostParams &C, float th, float w, float x, float &d_th, float &d_w,
                                                  float &d_x) {
     float sn, c;
-    sincosf(th, &sn, &c);
+    sincos_th(th, sn, c);
     const float dist = (x - C.target_position) * C.inv_2thl;
     const float apos = fabsf(x);
     const float over = (apos > C.w[5]) ? (apos - C.w[5]) * C.w[6] : 0.0f;
@@ -83,84 +101,173 @@ __device__ __forceinline__ void gradmin_partials(const CostParams &C, float th, 
     d_w = 2.0f * C.w[3] * w;
 }
 
-__global__ void __launch_bounds__(128) plan_grad_kernel(const __grid_constant__ GradArgs a) {
+// ---- forward: one thread per plan; cost and a checkpoint per control step ---------------------------------------------------
+// The integration and the cost are plan_kernel's (control_step with the rotation substeps, stage_cost): J is bit-identical
+// to cps_plan_cost's, and the sequential part of the gradient runs at the solve kernels' speed.
+template <int NSUB>
+__global__ void __launch_bounds__(128) plan_grad_fwd_kernel(const __grid_constant__ GradArgs a) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= a.K) return;
-    const OdeParams &P = a.ode;
     const CostParams &C = a.cost;
-    const int T = a.T, n = P.n, K = a.K;
-    const float *s0 = a.use_inline ? a.s_inline : a.s;
-    float th = s0[IDX_ANGLE], w = s0[IDX_ANGLED], x = s0[IDX_POS], v = s0[IDX_POSD];
+    const int T = a.T, K = a.K;
+    State z = load_state(a.use_inline ? a.s_inline : a.s);
+    const OdeParams ode = pin_params(a.ode, z.th);
+    float c_cost = cosf(z.th);
     const float *q = a.Q + (long long)k * a.qs_k;
     float *ck = a.ck + k;
-
-    // ---- forward: cost and checkpoints ---------------------------------------------------------------------------------------
     float Jacc = 0.0f;
+    float qn = q[0];
 #pragma unroll 1
     for (int t = 0; t < T; ++t) {
-        const float u = q[(long long)t * a.qs_t];
-        ck[((long long)t * 4 + 0) * K] = th; ck[((long long)t * 4 + 1) * K] = w;
-        ck[((long long)t * 4 + 2) * K] = x;  ck[((long long)t * 4 + 3) * K] = v;
-        Jacc += stage_cost<COST_GRADMIN>(C, cosf(th), w, x, u, 0.0f);
-        const float uk = P.u_scale * u;
-#pragma unroll 1
-        for (int i = 0; i < n; ++i) grad_substep(P, th, w, x, v, uk);
+        const float u = qn;
+        if (t + 1 < T) qn = q[(long long)(t + 1) * a.qs_t];   // prefetch under the integration
+        ck[((long long)t * 4 + 0) * K] = z.th; ck[((long long)t * 4 + 1) * K] = z.w;
+        ck[((long long)t * 4 + 2) * K] = z.x;  ck[((long long)t * 4 + 3) * K] = z.v;
+        Jacc += stage_cost<COST_GRADMIN>(C, c_cost, z.w, z.x, u, 0.0f);
+        control_step<1, SC_ROTATE, false, false, false, NSUB>(ode, z, u);
+        c_cost = z.c;
     }
     const float J = __fdiv_rn(Jacc, (float)(T + 1));   // the plugin's terminal cost is zero
     if (a.J) a.J[k] = J;
     if (!isfinite(J)) atomicAdd(a.nonfinite, 1);
+}
 
-    // ---- backward ----------------------------------------------------------------------------------------------------------------
-    float a_th = 0.0f, a_w = 0.0f, a_x = 0.0f, a_v = 0.0f;
-    float *g = a.G + (long long)k * a.gs_k;
-    Sub sub[CPS_GRAD_MAX_SUBSTEPS];
-#pragma unroll 1
-    for (int t = T - 1; t >= 0; --t) {
-        th = ck[((long long)t * 4 + 0) * K]; w = ck[((long long)t * 4 + 1) * K];
-        x = ck[((long long)t * 4 + 2) * K];  v = ck[((long long)t * 4 + 3) * K];
-        const float th0 = th, w0 = w, x0 = x;
-        const float u = q[(long long)t * a.qs_t];
-        const float uk = P.u_scale * u;
-#pragma unroll 1
-        for (int i = 0; i < n; ++i) {
-            sub[i].th = th; sub[i].w = w; sub[i].v = v;
-            grad_substep(P, th, w, x, v, uk);
-        }
-        float a_uk = 0.0f;
-#pragma unroll 1
-        for (int i = n - 1; i >= 0; --i) {
-            const float thi = sub[i].th, wi = sub[i].w, vi = sub[i].v;
-            float sn, c;
-            sincosf(thi, &sn, &c);
-            const float rA = rcp_pos<false>(fmaf(-P.m_p, c * c, P.KM));
-            const float t1 = fmaf(-P.c2, wi * wi, P.c1 * c), t4 = P.c3 * wi;
-            const float num = fmaf(sn, t1, fmaf(-t4, c, fmaf(-P.c5, vi, uk)));
-            const float xDD = num * rA;
-            const float a_v2 = fmaf(P.h, a_x, a_v);            // x' = x + h v'
-            const float a_w2 = fmaf(P.h, a_th, a_w);           // th' = th + h w'
-            const float a_thDD = P.h * a_w2;                   // w' = w + h thDD
-            float a_xDD = fmaf(P.d2 * c, a_thDD, P.h * a_v2);  // v' = v + h xDD; thDD = d1 s + d2 xDD c - d3 w
+// ---- transposed Jacobian of every control step, in parallel over (control step, plan) ------------------------------------
+// The reverse sweep is linear in the adjoint (a_th, a_w, a_x, a_v), so a control step acts on it as a 4 x 4 matrix that
+// depends only on the step's forward states: thread (t, k) re-integrates the n substeps of step t from its checkpoint and
+// pushes the four unit adjoints back through them together (the coefficients of a substep are computed once for the four).
+// Output per (t, k): M[3][4] -- rows (a_th, a_w, a_v) at the start of the step as combinations of the adjoint at its end
+// (a_x passes through unchanged: the position enters no right-hand side) --, r[4], the row that gives d/d(uk), and the
+// terms the cost adds at the step's boundary.
+// Sequential work per plan shrinks from T x n reverse substeps to T small matrix-vector products (plan_grad_rev_kernel).
+template <int NSUB>
+__device__ __forceinline__ void step_record(const GradArgs &a, int t, int k, float *o, long long stride) {
+    const int K = a.K;
+    const OdeParams &P = a.ode;
+    const int n = NSUB ? NSUB : P.n;
+    const float *ck = a.ck + k;
+    float th = ck[((long long)t * 4 + 0) * K], w = ck[((long long)t * 4 + 1) * K];
+    float x = ck[((long long)t * 4 + 2) * K], v = ck[((long long)t * 4 + 3) * K];
+    const float th0 = th, w0 = w, x0 = x;
+    const float u = a.Q[(long long)k * a.qs_k + (long long)t * a.qs_t];
+    const float uk = P.u_scale * u;
+    Sub sub[NSUB ? NSUB : CPS_GRAD_MAX_SUBSTEPS];
+#pragma unroll
+    for (int i = 0; i < (NSUB ? NSUB : CPS_GRAD_MAX_SUBSTEPS); ++i)
+        if (i < n) sub[i] = grad_substep(P, th, w, x, v, uk);
+    // seed j = unit adjoint in component j (th, w, x, v) at the end of the step
+    float A_th[4] = {1.0f, 0.0f, 0.0f, 0.0f}, A_w[4] = {0.0f, 1.0f, 0.0f, 0.0f}, A_v[4] = {0.0f, 0.0f, 0.0f, 1.0f};
+    float A_uk[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+    for (int ii = 0; ii < (NSUB ? NSUB : CPS_GRAD_MAX_SUBSTEPS); ++ii) {
+        const int i = n - 1 - ii;
+        if (i < 0) continue;
+        const float wi = sub[i].w, vi = sub[i].v, sn = sub[i].sn, c = sub[i].c;
+        const float rA = rcp_pos<false>(fmaf(-P.m_p, c * c, P.KM));
+        const float t1 = fmaf(-P.c2, wi * wi, P.c1 * c), t4 = P.c3 * wi;
+        const float num = fmaf(sn, t1, fmaf(-t4, c, fmaf(-P.c5, vi, uk)));
+        const float xDD = num * rA;
+        const float d2c = P.d2 * c, d2x = P.d2 * xDD, krA = 2.0f * P.m_p * c * rA * rA, kw = -2.0f * P.c2 * wi;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float a_x = (j == 2) ? 1.0f : 0.0f;
+            const float a_v2 = fmaf(P.h, a_x, A_v[j]);             // x' = x + h v'
+            const float a_w2 = fmaf(P.h, A_th[j], A_w[j]);         // th' = th + h w'
+            const float a_thDD = P.h * a_w2;                       // w' = w + h thDD
+            const float a_xDD = fmaf(d2c, a_thDD, P.h * a_v2);     // v' = v + h xDD; thDD = d1 s + d2 xDD c - d3 w
             float a_s = P.d1 * a_thDD;
-            float a_c = P.d2 * xDD * a_thDD;
+            float a_c = d2x * a_thDD;
             float a_win = fmaf(-P.d3, a_thDD, a_w2);
-            const float a_num = rA * a_xDD, a_rA = num * a_xDD;          // xDD = num rA
-            a_c = fmaf(2.0f * P.m_p * c * rA * rA, a_rA, a_c);             // rA = 1 / (KM - m_p c^2)
-            a_s = fmaf(t1, a_num, a_s);                                    // num = s t1 - t4 c + (uk - c5 v)
+            const float a_num = rA * a_xDD, a_rA = num * a_xDD;    // xDD = num rA
+            a_c = fmaf(krA, a_rA, a_c);                            // rA = 1 / (KM - m_p c^2)
+            a_s = fmaf(t1, a_num, a_s);                            // num = s t1 - t4 c + (uk - c5 v)
             const float a_t1 = sn * a_num, a_t4 = -c * a_num;
             a_c = fmaf(-t4, a_num, a_c);
-            a_c = fmaf(P.c1, a_t1, a_c);                                   // t1 = c1 c - c2 w^2
-            a_win = fmaf(-2.0f * P.c2 * wi, a_t1, fmaf(P.c3, a_t4, a_win));
-            a_uk += a_num;
-            a_v = fmaf(-P.c5, a_num, a_v2);
-            a_th = fmaf(c, a_s, fmaf(-sn, a_c, a_th));                     // c = cos th, s = sin th
-            a_w = a_win;
+            a_c = fmaf(P.c1, a_t1, a_c);                           // t1 = c1 c - c2 w^2
+            a_win = fmaf(kw, a_t1, fmaf(P.c3, a_t4, a_win));
+            A_uk[j] += a_num;
+            A_v[j] = fmaf(-P.c5, a_num, a_v2);
+            A_th[j] = fmaf(c, a_s, fmaf(-sn, a_c, A_th[j]));       // c = cos th, s = sin th
+            A_w[j] = a_win;
         }
-        g[(long long)t * a.gs_t] = fmaf(P.u_scale, a_uk, a.inv_T1 * 2.0f * C.w[4] * u);
-        float d_th, d_w, d_x;
-        gradmin_partials(C, th0, w0, x0, d_th, d_w, d_x);
-        a_th = fmaf(a.inv_T1, d_th, a_th);
-        a_w = fmaf(a.inv_T1, d_w, a_w);
-        a_x = fmaf(a.inv_T1, d_x, a_x);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        o[(0 + j) * stride] = A_th[j];
+        o[(4 + j) * stride] = A_w[j];
+        o[(8 + j) * stride] = A_v[j];
+        o[(12 + j) * stride] = A_uk[j];
+    }
+    // what the reverse sweep adds at this control-step boundary: the cost plugin's partial derivatives at the step's first
+    // state and its control term, with the 1 / (T + 1) of the mean
+    float d_th, d_w, d_x;
+    gradmin_partials(a.cost, th0, w0, x0, d_th, d_w, d_x);
+    o[16 * stride] = a.inv_T1 * d_th;
+    o[17 * stride] = a.inv_T1 * d_w;
+    o[18 * stride] = a.inv_T1 * d_x;
+    o[19 * stride] = a.inv_T1 * 2.0f * a.cost.w[4] * u;
+}
+
+// records to global memory (horizons too long for the fused kernel below)
+template <int NSUB>
+__global__ void __launch_bounds__(128) plan_grad_jac_kernel(const __grid_constant__ GradArgs a) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int K = a.K;
+    if (gid >= (long long)K * a.T) return;
+    const int k = (int)(gid % K), t = (int)(gid / K);
+    step_record<NSUB>(a, t, k, a.jac + (long long)t * CPS_GRAD_REC * K + k, K);
+}
+
+// One control step of the reverse sweep from its record m (element stride `stride`).
+__device__ __forceinline__ void reverse_step(const float *m, long long stride, float us, float &a_th, float &a_w, float &a_x,
+                                             float &a_v, float &g_out) {
+    float r[CPS_GRAD_REC];
+#pragma unroll
+    for (int j = 0; j < CPS_GRAD_REC; ++j) r[j] = m[j * stride];
+    const float a_uk = fmaf(r[12], a_th, fmaf(r[13], a_w, fmaf(r[14], a_x, r[15] * a_v)));
+    const float n_th = fmaf(r[0], a_th, fmaf(r[1], a_w, fmaf(r[2], a_x, r[3] * a_v)));
+    const float n_w = fmaf(r[4], a_th, fmaf(r[5], a_w, fmaf(r[6], a_x, r[7] * a_v)));
+    const float n_v = fmaf(r[8], a_th, fmaf(r[9], a_w, fmaf(r[10], a_x, r[11] * a_v)));
+    g_out = fmaf(us, a_uk, r[19]);
+    a_th = n_th + r[16];
+    a_w = n_w + r[17];
+    a_x = a_x + r[18];
+    a_v = n_v;
+}
+
+// Fused: a block takes P plans, thread (t, plan) leaves its record in shared memory ([T][CPS_GRAD_REC][P]), then the first P
+// threads walk the control steps backwards from there -- no round trip through global memory under the sequential part.
+template <int NSUB>
+__global__ void __launch_bounds__(512) plan_grad_jacrev_kernel(const __grid_constant__ GradArgs a, int P) {
+    extern __shared__ float s_rec[];
+    const int tid = threadIdx.x, kk = tid % P, t = tid / P;
+    const int k = blockIdx.x * P + kk;
+    if (t < a.T && k < a.K) step_record<NSUB>(a, t, k, s_rec + (long long)t * CPS_GRAD_REC * P + kk, P);
+    __syncthreads();
+    if (tid < P && k < a.K) {
+        float *g = a.G + (long long)k * a.gs_k;
+        float a_th = 0.0f, a_w = 0.0f, a_x = 0.0f, a_v = 0.0f;
+#pragma unroll 2
+        for (int tt = a.T - 1; tt >= 0; --tt) {
+            float go;
+            reverse_step(s_rec + (long long)tt * CPS_GRAD_REC * P + kk, P, a.ode.u_scale, a_th, a_w, a_x, a_v, go);
+            g[(long long)tt * a.gs_t] = go;
+        }
+    }
+}
+
+// ---- reverse from global records (horizons too long for the fused kernel): one thread per plan -----------------------------
+__global__ void __launch_bounds__(128) plan_grad_rev_kernel(const __grid_constant__ GradArgs a) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= a.K) return;
+    const int T = a.T, K = a.K;
+    float *g = a.G + (long long)k * a.gs_k;
+    float a_th = 0.0f, a_w = 0.0f, a_x = 0.0f, a_v = 0.0f;
+#pragma unroll 4
+    for (int t = T - 1; t >= 0; --t) {
+        float go;
+        reverse_step(a.jac + (long long)t * CPS_GRAD_REC * K + k, K, a.ode.u_scale, a_th, a_w, a_x, a_v, go);
+        g[(long long)t * a.gs_t] = go;
     }
 }
 
@@ -197,7 +304,7 @@ __global__ void __launch_bounds__(128) rpgd_update_kernel(const __grid_constant_
 void cps_grad_free(cps_handle *h) {
     GradState *G = h->grad;
     if (!G) return;
-    cudaFree(G->d_ck); cudaFree(G->d_J); cudaFree(G->d_G); cudaFree(G->d_m); cudaFree(G->d_v);
+    cudaFree(G->d_ck); cudaFree(G->d_jac); cudaFree(G->d_J); cudaFree(G->d_G); cudaFree(G->d_m); cudaFree(G->d_v);
     delete G;
     h->grad = nullptr;
 }
@@ -215,6 +322,7 @@ static int grad_state(cps_handle *h, GradState **out) {
     memset(G, 0, sizeof(*G));
     const size_t K = h->cfg.num_rollouts, T = h->cfg.horizon;
     cudaError_t e = cudaMalloc(&G->d_ck, sizeof(float) * 4 * K * T);
+    if (e == cudaSuccess) e = cudaMalloc(&G->d_jac, sizeof(float) * CPS_GRAD_REC * K * T);
     if (e == cudaSuccess) e = cudaMalloc(&G->d_J, sizeof(float) * K);
     if (e == cudaSuccess) e = cudaMalloc(&G->d_G, sizeof(float) * K * T);
     if (e == cudaSuccess) e = cudaMalloc(&G->d_m, sizeof(float) * K * T);
@@ -222,7 +330,7 @@ static int grad_state(cps_handle *h, GradState **out) {
     if (e == cudaSuccess) e = cudaMemset(G->d_m, 0, sizeof(float) * K * T);
     if (e == cudaSuccess) e = cudaMemset(G->d_v, 0, sizeof(float) * K * T);
     if (e != cudaSuccess) {
-        cudaFree(G->d_ck); cudaFree(G->d_J); cudaFree(G->d_G); cudaFree(G->d_m); cudaFree(G->d_v);
+        cudaFree(G->d_ck); cudaFree(G->d_jac); cudaFree(G->d_J); cudaFree(G->d_G); cudaFree(G->d_m); cudaFree(G->d_v);
         delete G;
         return fail(h, CPS_ERR_CUDA, "cps_plan_cost_grad: allocating the workspace: %s", cudaGetErrorString(e));
     }
@@ -252,11 +360,30 @@ extern "C" int cps_plan_cost_grad(cps_handle *h, const float *s_dev, const float
     else { a.qs_k = T; a.qs_t = 1; a.gs_k = T; a.gs_t = 1; }
     a.K = K; a.T = T;
     a.inv_T1 = 1.0f / (float)(T + 1);
-    a.ck = G->d_ck; a.J = J_out_dev ? J_out_dev : G->d_J; a.G = G_out_dev;
+    a.ck = G->d_ck; a.jac = G->d_jac; a.J = J_out_dev ? J_out_dev : G->d_J; a.G = G_out_dev;
     a.nonfinite = h->d_nonfinite;
     const int block = (K <= 148 * 32) ? 32 : 128;   // small K: one warp per block spreads the plans over the SMs
-    plan_grad_kernel<<<(K + block - 1) / block, block, 0, h->stream>>>(a);
-    h->launches += 1;
+    const int grid = (K + block - 1) / block;
+    const long long pairs = (long long)K * T;
+    const int jblock = (pairs <= 148 * 32 * 4) ? 32 : 128;
+    if (a.ode.n == 10) plan_grad_fwd_kernel<10><<<grid, block, 0, h->stream>>>(a);
+    else plan_grad_fwd_kernel<0><<<grid, block, 0, h->stream>>>(a);
+    if (T <= 512 && pairs <= 148LL * 1024) {   // beyond about one resident wave the 128-thread Jacobian kernel's occupancy wins
+        // plans per block: as many as fit 512 threads, but keep ~100 blocks for the Jacobians of small batches
+        int P = 1;
+        while (2 * P * T <= 512 && 2 * P <= 32 && K / (2 * P) >= 96) P *= 2;
+        const int threads = ((P * T + 31) / 32) * 32;
+        const size_t smem = sizeof(float) * CPS_GRAD_REC * (size_t)P * T;
+        void (*fn)(const GradArgs, int) = (a.ode.n == 10) ? plan_grad_jacrev_kernel<10> : plan_grad_jacrev_kernel<0>;
+        if (smem > 48 * 1024) CUDA_TRY(h, cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        fn<<<(K + P - 1) / P, threads, smem, h->stream>>>(a, P);
+        h->launches += 2;
+    } else {
+        if (a.ode.n == 10) plan_grad_jac_kernel<10><<<(unsigned)((pairs + jblock - 1) / jblock), jblock, 0, h->stream>>>(a);
+        else plan_grad_jac_kernel<0><<<(unsigned)((pairs + jblock - 1) / jblock), jblock, 0, h->stream>>>(a);
+        plan_grad_rev_kernel<<<grid, block, 0, h->stream>>>(a);
+        h->launches += 3;
+    }
     CUDA_TRY(h, cudaGetLastError());
     return CPS_OK;
 }

@@ -435,7 +435,7 @@ class optimizer_rpgd_b200(_forward_optimizer):
         if self.calculate_optimal_trajectory:
             traj, _ = self.engine.rollout(s_dev, self.u_nom.reshape(1, T))
             self.optimal_trajectory = traj.cpu().numpy()
-        self.u = np.array(float(self.u_nom[0, 0, 0]), dtype=np.float32)
+        self.u = np.array(self.optimal_control_sequence[0, 0, 0], dtype=np.float32)   # already on the host: no second sync
         return self.u
 
     def optimizer_reset(self):

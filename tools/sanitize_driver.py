@@ -79,6 +79,17 @@ def main(which):
         torch.cuda.synchronize()
         fl.close()
         done.append("fleet E=4")
+    if "grad" in which:
+        # fused Jacobian + reverse kernel (records in shared memory, block barrier), small and multi-plan blocks, and the
+        # global-record path of large batches
+        for K, T in ((16, 35), (2000, 12), (20000, 10)):
+            eng = Engine(K, T, integrator="ODE", cost="quadratic_boundary_grad_minimal", device=0)
+            Q = torch.empty((K, T), device=eng.device).uniform_(-0.5, 0.5)
+            J, G = eng.plan_cost_grad(state(eng.device), Q)
+            torch.cuda.synchronize()
+            assert bool(torch.isfinite(G).all())
+            eng.close()
+            done.append(f"grad K={K} T={T}")
     print("sanitize_driver finished:", "; ".join(done))
 
 
