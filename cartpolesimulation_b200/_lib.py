@@ -139,6 +139,7 @@ SYMBOLS = {
     "cps_rpgd_grad_step": (C.c_int, [_VP, _VP, _VP] + [C.c_float] * 6 + [_VP]),
     "cps_rpgd_adam_state": (C.c_int, [_VP, C.POINTER(_VP), C.POINTER(_VP), C.POINTER(C.c_longlong)]),
     "cps_rpgd_set_iterations": (C.c_int, [_VP, C.c_longlong]),
+    "cps_rpgd_finish": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.c_int, _VP, _VP]),
     "cps_launch_count": (C.c_longlong, [_VP]),
     "cps_net_last_kernel": (C.c_int, [_VP]),
     "cps_rollout_last_kernel": (C.c_int, [_VP]),

@@ -646,6 +646,25 @@ class Engine:
             self._adam_views = (view(m.value), view(v.value), (m.value, v.value))
         return self._adam_views[0], self._adam_views[1], int(it.value)
 
+    def rpgd_finish(self, J, Q, fresh, keep: int, shift_previous: int, ages=None) -> np.ndarray:
+        """cps_rpgd_finish: get_action and the per-solve bookkeeping of RPGD's step() in place on Q [K, T] (and on the
+        handle's Adam moments, `ages` int32 [K]); returns the cheapest plan [T] on the host (synchronises)."""
+        self.use_current_stream()
+        for t, name in ((J, "J"), (Q, "Q")):
+            _check_dev(t, name, self.device)
+        if tuple(Q.shape[:2]) != (self.K, self.T) or not Q.is_contiguous() or J.numel() != self.K:
+            raise ValueError("rpgd_finish: Q must be a contiguous [K, T] tensor and J [K]")
+        if fresh is not None:
+            _check_dev(fresh, "fresh", self.device)
+            if tuple(fresh.shape) != (self.K - keep, self.T) or not fresh.is_contiguous():
+                raise ValueError(f"rpgd_finish: fresh has shape {tuple(fresh.shape)}, expected {(self.K - keep, self.T)}")
+        if ages is not None and (ages.dtype != torch.int32 or ages.numel() != self.K):
+            raise ValueError("rpgd_finish: ages must be int32 [K]")
+        out = np.empty(self.T, dtype=np.float32)
+        self._chk(self.lib.cps_rpgd_finish(self._h, _ptr(J), _ptr(Q), _ptr(fresh), int(keep), int(shift_previous), _ptr(ages),
+                                           out.ctypes.data_as(C.c_void_p)))
+        return out
+
     def rpgd_set_iterations(self, n: int):
         self._chk(self.lib.cps_rpgd_set_iterations(self._h, int(n)))
 

@@ -37,6 +37,9 @@ struct GradState {
     float *d_J;         // [K]
     float *d_G;         // [K][T]
     float *d_m, *d_v;   // Adam moments [K][T]
+    float *d_Q2, *d_m2, *d_v2, *d_unom;   // cps_rpgd_finish: permuted copies [K][T], the cheapest plan [T]
+    int *d_ages2;
+    float *h_unom;      // pinned [T]
     long long adam_iterations;
 };
 
@@ -299,12 +302,69 @@ __global__ void __launch_bounds__(128) rpgd_update_kernel(const __grid_constant_
     }
 }
 
+// get_action + the bookkeeping of step(): one block per plan.
+struct FinishArgs {
+    const float *J, *Q, *m, *v, *fresh;
+    const int *ages;
+    float *Q2, *m2, *v2, *u_nom;
+    int *ages2;
+    int K, T, keep, sp;
+};
+__global__ void __launch_bounds__(64) rpgd_finish_kernel(const __grid_constant__ FinishArgs a) {
+    __shared__ int s_cnt[2];
+    const int i = blockIdx.x, tid = threadIdx.x, K = a.K, T = a.T;
+    const float Ji = a.J[i];
+    int cnt = 0;   // plans in front of plan i in the stable ascending order (torch.sort(J, stable=True), :186)
+    for (int j = tid; j < K; j += 64) {
+        const float Jj = a.J[j];
+        cnt += (Jj < Ji || (Jj == Ji && j < i)) ? 1 : 0;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if ((tid & 31) == 0) s_cnt[tid >> 5] = cnt;
+    __syncthreads();
+    const int rank = s_cnt[0] + s_cnt[1];
+    const bool resample = a.fresh != nullptr;
+    const int dest = resample ? (rank < a.keep ? (K - a.keep) + rank : -1) : i;
+    const float *q = a.Q + (long long)i * T, *m = a.m + (long long)i * T, *v = a.v + (long long)i * T;
+    if (rank == 0)
+        for (int t = tid; t < T; t += 64) a.u_nom[t] = q[t];
+    if (dest >= 0) {
+        for (int t = tid; t < T; t += 64) {
+            const long long o = (long long)dest * T + t;
+            a.Q2[o] = q[min(t + a.sp, T - 1)];
+            a.m2[o] = (t + 1 < T) ? m[t + 1] : 0.0f;
+            a.v2[o] = (t + 1 < T) ? v[t + 1] : 0.0f;
+        }
+        if (a.ages && tid == 0) a.ages2[dest] = a.ages[i] + 1;
+    }
+    if (resample && i < K - a.keep) {
+        for (int t = tid; t < T; t += 64) {
+            const long long o = (long long)i * T + t;
+            a.Q2[o] = a.fresh[o];
+            a.m2[o] = 0.0f;
+            a.v2[o] = 0.0f;
+        }
+        if (a.ages && tid == 0) a.ages2[i] = 1;
+    }
+}
+__global__ void __launch_bounds__(256) rpgd_copyback_kernel(float *Q, float *m, float *v, int *ages, const float *Q2, const float *m2,
+                                                            const float *v2, const int *ages2, int K, int T) {
+    const int n = K * T;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        Q[i] = Q2[i]; m[i] = m2[i]; v[i] = v2[i];
+        if (ages && i < K) ages[i] = ages2[i];
+    }
+}
+
 }  // namespace
 
 void cps_grad_free(cps_handle *h) {
     GradState *G = h->grad;
     if (!G) return;
     cudaFree(G->d_ck); cudaFree(G->d_jac); cudaFree(G->d_J); cudaFree(G->d_G); cudaFree(G->d_m); cudaFree(G->d_v);
+    cudaFree(G->d_Q2); cudaFree(G->d_m2); cudaFree(G->d_v2); cudaFree(G->d_unom); cudaFree(G->d_ages2);
+    if (G->h_unom) cudaFreeHost(G->h_unom);
     delete G;
     h->grad = nullptr;
 }
@@ -422,6 +482,43 @@ extern "C" int cps_rpgd_grad_step(cps_handle *h, const float *s_dev, float *Q_de
     rpgd_update_kernel<<<(a.K + 3) / 4, 128, 0, h->stream>>>(a);
     h->launches += 1;
     CUDA_TRY(h, cudaGetLastError());
+    return CPS_OK;
+}
+
+extern "C" int cps_rpgd_finish(cps_handle *h, const float *J_dev, float *Q_dev, const float *fresh_dev, int keep, int shift_previous,
+                               int *ages_dev, float *u_nom_host) {
+    if (!h) return CPS_ERR_INVALID;
+    if (!J_dev || !Q_dev || !u_nom_host) return fail(h, CPS_ERR_INVALID, "cps_rpgd_finish: null pointer");
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    GradState *G;
+    int rc = grad_state(h, &G);
+    if (rc != CPS_OK) return rc;
+    const int K = h->cfg.num_rollouts, T = h->cfg.horizon;
+    if (K > 4096) return fail(h, CPS_ERR_UNSUPPORTED, "cps_rpgd_finish: at most 4096 plans (ranks by counting)");
+    if (keep < 1 || keep > K || shift_previous < 0) return fail(h, CPS_ERR_INVALID, "cps_rpgd_finish: bad keep / shift_previous");
+    if (!G->d_Q2) {   // first use
+        const size_t n = (size_t)K * T;
+        cudaError_t e = cudaMalloc(&G->d_Q2, sizeof(float) * n);
+        if (e == cudaSuccess) e = cudaMalloc(&G->d_m2, sizeof(float) * n);
+        if (e == cudaSuccess) e = cudaMalloc(&G->d_v2, sizeof(float) * n);
+        if (e == cudaSuccess) e = cudaMalloc(&G->d_unom, sizeof(float) * T);
+        if (e == cudaSuccess) e = cudaMalloc(&G->d_ages2, sizeof(int) * K);
+        if (e == cudaSuccess) e = cudaHostAlloc(&G->h_unom, sizeof(float) * T, cudaHostAllocDefault);
+        if (e != cudaSuccess) return fail(h, CPS_ERR_CUDA, "cps_rpgd_finish: allocating the workspace: %s", cudaGetErrorString(e));
+    }
+    FinishArgs a;
+    a.J = J_dev; a.Q = Q_dev; a.m = G->d_m; a.v = G->d_v; a.fresh = fresh_dev; a.ages = ages_dev;
+    a.Q2 = G->d_Q2; a.m2 = G->d_m2; a.v2 = G->d_v2; a.u_nom = G->d_unom; a.ages2 = G->d_ages2;
+    a.K = K; a.T = T; a.keep = keep; a.sp = shift_previous;
+    rpgd_finish_kernel<<<K, 64, 0, h->stream>>>(a);
+    const int n = K * T;
+    rpgd_copyback_kernel<<<(n + 255) / 256 < 592 ? (n + 255) / 256 : 592, 256, 0, h->stream>>>(Q_dev, G->d_m, G->d_v, ages_dev, G->d_Q2, G->d_m2,
+                                                                                                G->d_v2, G->d_ages2, K, T);
+    h->launches += 2;
+    CUDA_TRY(h, cudaGetLastError());
+    CUDA_TRY(h, cudaMemcpyAsync(G->h_unom, G->d_unom, sizeof(float) * T, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    memcpy(u_nom_host, G->h_unom, sizeof(float) * T);
     return CPS_OK;
 }
 

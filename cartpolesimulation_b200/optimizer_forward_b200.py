@@ -408,32 +408,40 @@ class optimizer_rpgd_b200(_forward_optimizer):
                                        self.adam_epsilon, self.gradmax_clip)
         # get_action (:182-224): costs of the improved plans, the best opt_keep_k of them, the shifted warm start
         J = self.engine.plan_cost(s_dev, self.Q_tf, L.ROLLOUT_MAJOR, u_prev)[0]
-        best_idx = torch.sort(J, stable=True).indices[:keep]
-        self.u_nom = self.Q_tf[best_idx[0]].clone().reshape(1, T, 1)
-        sp = self.shift_previous
-        Qn = torch.cat([self.Q_tf[:, sp:], self.Q_tf[:, -1:].repeat(1, sp)], dim=1)
         if self.optimizer_logging:
             self._u_prev_logged = self.u
             self._log_rollouts(s, self.Q_tf)
             self.logging_values["trajectory_ages_logged"] = self.trajectory_ages.cpu().numpy()
-        self.optimal_control_sequence = self.u_nom.cpu().numpy()
-        m, v, _ = self.engine.rpgd_adam_state()
-        zeros = torch.zeros((K, 1), device=self.device)
-        if self.count % self.resamp_per == 0:   # :299-343: the worst plans are redrawn, the kept ones sorted by cost
-            Qn = torch.cat([self.sample_actions(K - keep), Qn[best_idx]], dim=0)
-            self.trajectory_ages = torch.cat([torch.zeros(K - keep, dtype=torch.int32, device=self.device),
-                                              self.trajectory_ages[best_idx]])
-            fresh = torch.zeros((K - keep, T), device=self.device)
-            m.copy_(torch.cat([fresh, torch.cat([m[best_idx][:, 1:], zeros[:keep]], dim=1)], dim=0))
-            v.copy_(torch.cat([fresh, torch.cat([v[best_idx][:, 1:], zeros[:keep]], dim=1)], dim=0))
-        else:                                   # :344-356: every plan keeps its moments, shifted by one step
-            m.copy_(torch.cat([m[:, 1:], zeros], dim=1))
-            v.copy_(torch.cat([v[:, 1:], zeros], dim=1))
-        self.trajectory_ages += 1
-        self.Q_tf.copy_(Qn)
+        resample = self.count % self.resamp_per == 0
+        if K <= 4096 and not (resample and keep == K):
+            # one launch: stable order of the costs, the cheapest plan, shift, resampling permutation of plans / moments / ages
+            fresh = self.sample_actions(K - keep).contiguous() if resample else None
+            u_nom = self.engine.rpgd_finish(J, self.Q_tf, fresh, keep, self.shift_previous, self.trajectory_ages)
+            self.optimal_control_sequence = u_nom.reshape(1, T, 1)
+            self.u_nom = torch.from_numpy(self.optimal_control_sequence)   # host view; moved to the device only where needed
+        else:
+            best_idx = torch.sort(J, stable=True).indices[:keep]
+            self.u_nom = self.Q_tf[best_idx[0]].clone().reshape(1, T, 1)
+            sp = self.shift_previous
+            Qn = torch.cat([self.Q_tf[:, sp:], self.Q_tf[:, -1:].repeat(1, sp)], dim=1)
+            self.optimal_control_sequence = self.u_nom.cpu().numpy()
+            m, v, _ = self.engine.rpgd_adam_state()
+            zeros = torch.zeros((K, 1), device=self.device)
+            if resample:   # :299-343: the worst plans are redrawn, the kept ones sorted by cost
+                Qn = torch.cat([self.sample_actions(K - keep), Qn[best_idx]], dim=0)
+                self.trajectory_ages = torch.cat([torch.zeros(K - keep, dtype=torch.int32, device=self.device),
+                                                  self.trajectory_ages[best_idx]])
+                fresh = torch.zeros((K - keep, T), device=self.device)
+                m.copy_(torch.cat([fresh, torch.cat([m[best_idx][:, 1:], zeros[:keep]], dim=1)], dim=0))
+                v.copy_(torch.cat([fresh, torch.cat([v[best_idx][:, 1:], zeros[:keep]], dim=1)], dim=0))
+            else:                                   # :344-356: every plan keeps its moments, shifted by one step
+                m.copy_(torch.cat([m[:, 1:], zeros], dim=1))
+                v.copy_(torch.cat([v[:, 1:], zeros], dim=1))
+            self.trajectory_ages += 1
+            self.Q_tf.copy_(Qn)
         self.count += 1
         if self.calculate_optimal_trajectory:
-            traj, _ = self.engine.rollout(s_dev, self.u_nom.reshape(1, T))
+            traj, _ = self.engine.rollout(s_dev, self.u_nom.reshape(1, T).to(self.device))
             self.optimal_trajectory = traj.cpu().numpy()
         self.u = np.array(self.optimal_control_sequence[0, 0, 0], dtype=np.float32)   # already on the host: no second sync
         return self.u

@@ -462,9 +462,9 @@ int cps_selftest_sincos(cps_handle *h, long long *mismatches_out);
 /* ---- gradient of predict_and_cost; RPGD ----------------------------------------------------------------- */
 /* The reference's gradient-based optimizers take d(traj_cost)/dQ with a tf.GradientTape around predict_and_cost
  * (Control_Toolkit/Optimizers/optimizer_rpgd_tf.py:167-175; RPGD is the shipped default optimizer,
- * Control_Toolkit_ASF/config_controllers.yml:2).  cps_plan_cost_grad is that derivative in one launch: forward rollout with a
- * checkpoint per control step, backward sweep with the hand-derived adjoint of the Euler-Cromer substep and of the cost
- * plugin.  Q_dev [K][T] (or [T][K] with CPS_TIME_MAJOR) for the handle's K and T; J_out_dev [K] (or NULL) the costs,
+ * Control_Toolkit_ASF/config_controllers.yml:2).  cps_plan_cost_grad is that derivative on the device: forward rollout with a
+ * checkpoint per control step, the control steps' transposed Jacobians (hand-derived adjoint of the Euler-Cromer substep) in
+ * parallel over (step, plan), reverse sweep over the steps with the cost plugin's partial derivatives (two launches).  Q_dev [K][T] (or [T][K] with CPS_TIME_MAJOR) for the handle's K and T; J_out_dev [K] (or NULL) the costs,
  * G_out_dev the gradient in the layout of Q.  Predictor "ODE" with cos / sin from the angle every substep (the arithmetic
  * the reference differentiates), cost quadratic_boundary_grad_minimal (the shipped RPGD configuration); anything else:
  * CPS_ERR_UNSUPPORTED.
@@ -479,6 +479,14 @@ int cps_rpgd_grad_step(cps_handle *h, const float *s_dev, float *Q_dev, float u_
                        float beta_2, float epsilon, float gradmax_clip, float *J_out_dev);
 int cps_rpgd_adam_state(cps_handle *h, float **m_dev, float **v_dev, long long *iterations);
 int cps_rpgd_set_iterations(cps_handle *h, long long iterations);
+/* get_action and the per-solve bookkeeping of optimizer_rpgd_tf.step (:182-224, :297-356) on the device: the stable order of
+ * the K costs J_dev, u_nom = the cheapest plan (copied to u_nom_host [T]; synchronises), every plan shifted by
+ * shift_previous (last input repeated), the Adam moments shifted by one step, ages_dev [K] (int32, or NULL) + 1.  With
+ * fresh_dev != NULL ([K - keep][T], a resampling solve) the `keep` cheapest plans move to the rows K - keep.. in cost order
+ * with their moments and ages, rows 0..K - keep - 1 take the fresh plans with zero moments and age.  In place on Q_dev
+ * [K][T]; K <= 4096 (ranks by counting), else CPS_ERR_UNSUPPORTED and the caller does it with tensor operations. */
+int cps_rpgd_finish(cps_handle *h, const float *J_dev, float *Q_dev, const float *fresh_dev, int keep, int shift_previous,
+                    int *ages_dev, float *u_nom_host);
 
 /* ---- diagnostics ------------------------------------------------------------------------------------- */
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches claim). */

@@ -88,6 +88,13 @@ def main(which):
             J, G = eng.plan_cost_grad(state(eng.device), Q)
             torch.cuda.synchronize()
             assert bool(torch.isfinite(G).all())
+            if K <= 4096:   # get_action + bookkeeping kernel, resampling and plain solves
+                keep = max(1, (3 * K) // 4)
+                ages = torch.zeros(K, dtype=torch.int32, device=eng.device)
+                eng.rpgd_reset()
+                for fresh in (torch.zeros((K - keep, T), device=eng.device), None):
+                    u_nom = eng.rpgd_finish(J, Q, fresh, keep, 1, ages)
+                    assert np.isfinite(u_nom).all()
             eng.close()
             done.append(f"grad K={K} T={T}")
     print("sanitize_driver finished:", "; ".join(done))
