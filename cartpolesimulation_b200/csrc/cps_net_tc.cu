@@ -20,6 +20,9 @@
 //     pre-scale that keeps lo out of the subnormal range: activations x 2^7, weight rows scaled to [64, 128)), and
 //     each product runs as three MMAs  hi*hi + lo*hi + hi*lo  into the same accumulator (the dropped lo*lo term is
 //     2^-22 relative).  The scales are undone, and the biases added, by one FMA in the epilogue;
+//   * small batches (<= 32 rollouts per SM's worth: config 3, K = 2000) run with 8 live rollouts per lane quarter and put the
+//     idle rows to work: row r + 8 of every 16-row group carries the lo parts of the rollout in row r ("stacked", see
+//     gru_epilogue), so a product is two MMAs (W_hi, W_lo) instead of three and includes the lo * lo term;
 //   * MPPI = true: block partials, last-block merge and the stored-hidden-state update as in net_kernel.
 // Tensor memory (512 columns): 3 x 128 accumulator regions, h1 and h2 operands (hi + lo, 4 x 32); the output layer's 16
 // columns alias the NI columns of a region that is idle at that moment.
