@@ -38,7 +38,9 @@ def test_gradient_matches_autograd_through_the_reference(name, layout):
     assert eng.nonfinite_costs() == 0
 
 
-@pytest.mark.parametrize("K,T", [(1, 1), (33, 7), (2000, 50), (5000, 20)])
+# (8192, 20): more (step, plan) pairs than the fused Jacobian + reverse kernel takes -> records in global memory; (8, 600): a
+# horizon beyond its 512 steps
+@pytest.mark.parametrize("K,T", [(1, 1), (33, 7), (2000, 50), (5000, 20), (8192, 20), (8, 600)])
 def test_gradient_vs_oracle_sizes(K, T):
     from cartpolesimulation_b200 import _lib as L
     from oracle import oracle as O
@@ -190,3 +192,45 @@ def test_optimizer_rpgd_b200_free_running_and_own_rng():
     J1 = b2.engine.plan_cost(torch.from_numpy(s).cuda(), b2.Q_tf, L.ROLLOUT_MAJOR, 0.0)[0].cpu().numpy()
     J0 = b2.engine.plan_cost(torch.from_numpy(s).cuda(), Q_start, L.ROLLOUT_MAJOR, 0.0)[0].cpu().numpy()
     assert (J1 < J0).mean() > 0.8
+
+
+@pytest.mark.parametrize("K,T,resample", [(16, 35, True), (16, 35, False), (37, 9, True), (2000, 50, True), (4096, 5, False)])
+def test_rpgd_finish_matches_the_tensor_restatement(K, T, resample):
+    """cps_rpgd_finish = get_action + the bookkeeping of optimizer_rpgd_tf.step (:182-224, :297-356), here against the same
+    steps written with torch operations (stable sort, gather, shift, concatenation); costs with ties."""
+    eng = _engine(K, T)
+    eng.rpgd_reset()
+    g = torch.Generator(device="cuda").manual_seed(K * 100 + T)
+    J = torch.randint(0, max(2, K // 3), (K,), generator=g, device="cuda").float()   # many equal costs: the order must be stable
+    Q = torch.rand((K, T), generator=g, device="cuda") * 2 - 1
+    m, v, _ = eng.rpgd_adam_state()
+    m.copy_(torch.rand((K, T), generator=g, device="cuda"))
+    v.copy_(torch.rand((K, T), generator=g, device="cuda"))
+    ages = torch.randint(0, 50, (K,), generator=g, device="cuda", dtype=torch.int32)
+    keep, sp = max(1, (3 * K) // 4), 1
+    fresh = (torch.rand((K - keep, T), generator=g, device="cuda") - 0.5) if resample else None
+    # restatement
+    best = torch.sort(J, stable=True).indices[:keep]
+    u_nom_ref = Q[best[0]].clone()
+    Qn = torch.cat([Q[:, sp:], Q[:, -1:].repeat(1, sp)], dim=1)
+    zeros = torch.zeros((K, 1), device="cuda")
+    if resample:
+        Qn = torch.cat([fresh, Qn[best]], dim=0)
+        ages_ref = torch.cat([torch.zeros(K - keep, dtype=torch.int32, device="cuda"), ages[best]]) + 1
+        z = torch.zeros((K - keep, T), device="cuda")
+        m_ref = torch.cat([z, torch.cat([m[best][:, 1:], zeros[:keep]], dim=1)], dim=0)
+        v_ref = torch.cat([z, torch.cat([v[best][:, 1:], zeros[:keep]], dim=1)], dim=0)
+    else:
+        ages_ref = ages + 1
+        m_ref = torch.cat([m[:, 1:], zeros], dim=1)
+        v_ref = torch.cat([v[:, 1:], zeros], dim=1)
+    u_nom = eng.rpgd_finish(J, Q, fresh, keep, sp, ages)
+    m2, v2, _ = eng.rpgd_adam_state()
+    assert np.array_equal(u_nom, u_nom_ref.cpu().numpy())
+    assert torch.equal(Q, Qn) and torch.equal(m2, m_ref) and torch.equal(v2, v_ref) and torch.equal(ages, ages_ref)
+
+
+def test_rpgd_finish_rejects_large_batches():
+    eng = _engine(5000, 4)
+    with pytest.raises(NotImplementedError):
+        eng.rpgd_finish(torch.zeros(5000, device="cuda"), torch.zeros((5000, 4), device="cuda"), None, 3750, 1, None)
