@@ -401,7 +401,12 @@ class optimizer_rpgd_b200(_forward_optimizer):
     def step(self, s: np.ndarray, time=None):
         s = self._state(s)
         K, T, keep = self.num_rollouts, self.mpc_horizon, self.opt_keep_k
-        s_dev = torch.from_numpy(s).to(self.device)
+        if getattr(self, "_s_pin", None) is None:   # pinned staging: the state's copy is stream-ordered, no synchronisation
+            self._s_pin = torch.empty(6, dtype=torch.float32).pin_memory()
+            self._s_dev = torch.empty(6, dtype=torch.float32, device=self.device)
+        self._s_pin.copy_(torch.from_numpy(s))
+        self._s_dev.copy_(self._s_pin, non_blocking=True)
+        s_dev = self._s_dev
         u_prev = float(np.asarray(self.u).reshape(-1)[0])
         for _ in range(self.first_iter_count if self.count == 0 else self.outer_its):   # grad_step (:166-180)
             self.engine.rpgd_grad_step(s_dev, self.Q_tf, u_prev, self.learning_rate, self.adam_beta_1, self.adam_beta_2,
