@@ -6,9 +6,11 @@ mkdir -p gpurun_out
 rm -f gpurun_out/parity_measured.json
 CS=/usr/local/cuda/bin/compute-sanitizer
 for tool in memcheck racecheck synccheck; do
-  log=gpurun_out/sanitizer_${tool}_net.log
-  timeout 600 $CS --tool $tool --print-limit 20 python tools/sanitize_driver.py net > $log 2>&1
-  echo "$tool net rc=$? : $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY|sanitize_driver finished' $log | tr '\n' ' ')"
+  for part in net grad; do
+    log=gpurun_out/sanitizer_${tool}_${part}.log
+    timeout 600 $CS --tool $tool --print-limit 20 python tools/sanitize_driver.py $part > $log 2>&1
+    echo "$tool $part rc=$? : $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY|sanitize_driver finished' $log | tr '\n' ' ')"
+  done
 done
 timeout 2400 python -m pytest tests -m gpu -q -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"
 tail -2 gpurun_out/pytest_gpu.log
@@ -26,6 +28,7 @@ print("ODE_v0", m["ODE_v0"]); print("ODE", m["ODE"]); print("K65536", m["ODE_K65
 r=json.loads(open("gpurun_out/bench_ref.json").read().strip().splitlines()[-1]); print("ref", r["value"], r["cpu_baseline"]["cores"])
 PY
 for K in 2000 4096 6000 8192 65536; do timeout 200 python tools/bench_net.py --K $K --kernel tensor 2>&1 | tail -2; done > gpurun_out/net_tc_timing.txt 2>&1
+timeout 300 python tools/bench_rpgd.py > gpurun_out/rpgd_timing.txt 2>&1
 NCU="ncu --set full --clock-control none --import-source on -f"
 timeout 600 $NCU -k regex:net_tc_kernel -s 3 -c 1 -o gpurun_out/r02_net_tc_K2000_v2 python tools/bench_net.py --K 2000 --kernel tensor --iters 3 > gpurun_out/ncu_net_tc.log 2>&1; echo "ncu net rc=$?"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02_launches.csv python bench.py --steps 2 --warmup 1 --no-mppi > gpurun_out/ncu_bench.log 2>&1; echo "launch list rc=$?"
