@@ -348,9 +348,10 @@ def relabel_bench(device, E=256, rows=50, K=2000, T=50):
 
 def legacy_latency(device, n_calls=300):
     """the legacy controller_mppi_cartpole at its shipped configuration (config_controllers.yml:9-30:
-    K=3500, T=35, 'interpolated' sampling, predictor ODE): controller.step(numpy s) -> numpy Q, host-drawn perturbations
-    (numpy SFC64 + scipy interp1d, as in the reference) included; kernel-only time from CUDA events; the CPU port of the
-    same iteration beside it."""
+    K=3500, T=35, 'interpolated' sampling, predictor ODE): controller.step(numpy s) -> numpy Q, the host-drawn knot
+    perturbations (numpy SFC64, the reference's generator call) included -- the interpolation between the knots, scipy
+    interp1d in the reference, runs on the device; kernel-only time from CUDA events; the CPU port of the same iteration
+    beside it.  reference_sampler_ms = what the reference's whole host sampler (draws + interp1d) costs on this host."""
     import torch
     from cartpolesimulation_b200.controller_mppi_cartpole_b200 import controller_mppi_cartpole_b200
     ctrl = controller_mppi_cartpole_b200(dict(seed=1), dt=DT, device=device)
@@ -359,7 +360,7 @@ def legacy_latency(device, n_calls=300):
     s = np.array([a, 0.0, np.cos(a), np.sin(a), 0.0, 0.0], dtype=np.float32)
     for _ in range(20):
         ctrl.step(s)
-    lat, samp = np.empty(n_calls), np.empty(n_calls)
+    lat, samp, knot = np.empty(n_calls), np.empty(n_calls), np.empty(n_calls)
     for i in range(n_calls):
         t0 = time.perf_counter()
         ctrl.step(s)
@@ -368,14 +369,19 @@ def legacy_latency(device, n_calls=300):
         t0 = time.perf_counter()
         ctrl.initialize_perturbations(stdev=ctrl.SQRTRHODTINV, sampling_type=ctrl.SAMPLING_TYPE)
         samp[i] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        ctrl._interpolated_knots(stdev=ctrl.SQRTRHODTINV)
+        knot[i] = time.perf_counter() - t0
     eng = ctrl.engine
     du = torch.from_numpy(np.ascontiguousarray(ctrl.delta_u.T, dtype=np.float32)).to(eng.device)
     s_dev = torch.from_numpy(s).to(eng.device)
     ks = _event_times(lambda: eng.legacy_step(s_dev, du, 1), 50, warm=10)
     out = {"latency_ms_median": float(np.median(lat) * 1e3), "latency_ms_p99": float(np.percentile(lat, 99) * 1e3),
-           "host_sampler_ms_median": float(np.median(samp) * 1e3), "kernel_ms_median": float(np.median(ks)),
+           "host_sampler_ms_median": float(np.median(knot) * 1e3), "reference_sampler_ms_median": float(np.median(samp) * 1e3),
+           "kernel_ms_median": float(np.median(ks)),
            "calls": n_calls, "K": K, "T": T, "state_steps_per_solve": K * T * N_SUB,
-           "api": "controller_mppi_cartpole_b200.step(numpy s) -> numpy Q (cps_legacy_step_host, legacy_mppi_kernel<ODE>)"}
+           "api": "controller_mppi_cartpole_b200.step(numpy s) -> numpy Q (cps_legacy_step_host_knots: legacy_interp_kernel + "
+                  "legacy_mppi_kernel<ODE>)"}
     try:
         from oracle import legacy as OL
         from oracle import oracle as O

@@ -89,6 +89,8 @@ SYMBOLS = {
     "cps_mppi_peer_timeouts": (C.c_int, [_VP, C.POINTER(C.c_int)]),
     "cps_legacy_step": (C.c_int, [_VP, _VP, _VP, C.c_int, _VP, _VP, _VP, C.c_int, _VP]),
     "cps_legacy_step_host": (C.c_int, [_VP, _FP, _VP, C.c_int, _FP]),
+    "cps_legacy_step_host_knots": (C.c_int, [_VP, _FP, _VP, C.c_int, C.c_int, _FP]),
+    "cps_legacy_get_perturbations": (C.c_int, [_VP, _VP]),
     "cps_legacy_advance": (C.c_int, [_VP, _FP]),
     "cps_legacy_reset": (C.c_int, [_VP]),
     "cps_legacy_get_inputs": (C.c_int, [_VP, _FP, _FP]),

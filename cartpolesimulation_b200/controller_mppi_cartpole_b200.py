@@ -106,6 +106,26 @@ class controller_mppi_cartpole_b200:
         e.set_variable_parameters(target_position=float(self.target_position))
         self._folded = key
 
+    INTERPOLATION_STEP = 10   # `step` of the interpolated sampler (:431)
+
+    @property
+    def delta_u(self) -> np.ndarray:
+        """The perturbations of the last solve [K, T]; after a device-interpolated solve they are read back on first use."""
+        if self._delta_u is None:
+            self._delta_u = self.engine.legacy_get_perturbations()
+        return self._delta_u
+
+    @delta_u.setter
+    def delta_u(self, value):
+        self._delta_u = value
+
+    def _interpolated_knots(self, stdev: float = 1.0) -> np.ndarray:
+        """The draws of the "interpolated" sampler (:430-441) at the knots 0, 10, 20, ...: the reference assigns
+        `stdev * rng.standard_normal(size=(K, n_knots), dtype=float32)` into its float32 array, i.e. rounds to float32."""
+        K, T, step = self.num_rollouts, self.mpc_horizon, self.INTERPOLATION_STEP
+        n_knots = int(np.ceil(T / step)) + 1
+        return np.ascontiguousarray((stdev * self.rng_mppi.standard_normal(size=(K, n_knots), dtype=np.float32)).astype(np.float32))
+
     def initialize_perturbations(self, stdev: float = 1.0, sampling_type: str = None) -> np.ndarray:
         """The reference's five samplers (:392-457), same generator calls in the same order.  `stdev` is a numpy float64
         scalar in the reference; under NEP 50 `stdev * float32 array` is then float64, which the iid / repeated types
@@ -150,10 +170,19 @@ class controller_mppi_cartpole_b200:
         if (self.num_rollouts, self.mpc_horizon) != self._engine_shape:  # changed in the GUI while running (:474-479)
             self.update_control_vector()
         if self.iteration % self.update_every == 0:
-            self.delta_u = self.initialize_perturbations(stdev=self.SQRTRHODTINV, sampling_type=self.SAMPLING_TYPE)
-            self._sync_parameters()
-            np.copyto(self._du32, self.delta_u, casting="same_kind")
-            Q = self.engine.legacy_step_host(np.asarray(s, dtype=np.float32), self._du32, L.ROLLOUT_MAJOR)
+            if self.SAMPLING_TYPE == "interpolated":
+                # the shipped sampler: only the knot draws are made here (the same generator call as the reference's); the
+                # linear interpolation between them -- scipy's interp1d in the reference, three quarters of this controller's
+                # host time -- runs on the device, bit-identical (cps_legacy_step_host_knots)
+                knots = self._interpolated_knots(stdev=self.SQRTRHODTINV)
+                self._sync_parameters()
+                Q = self.engine.legacy_step_host_knots(np.asarray(s, dtype=np.float32), knots, self.INTERPOLATION_STEP)
+                self._delta_u = None   # on the device; `delta_u` fetches it on demand
+            else:
+                self.delta_u = self.initialize_perturbations(stdev=self.SQRTRHODTINV, sampling_type=self.SAMPLING_TYPE)
+                self._sync_parameters()
+                np.copyto(self._du32, self.delta_u, casting="same_kind")
+                Q = self.engine.legacy_step_host(np.asarray(s, dtype=np.float32), self._du32, L.ROLLOUT_MAJOR)
         else:
             Q = self.engine.legacy_advance()
         if self.LOGGING:

@@ -217,6 +217,25 @@ class Engine:
                                                 self._u_host))
         return self._u_host[0]
 
+    def legacy_step_host_knots(self, s_np, knots_np, knot_step: int) -> float:
+        """cps_legacy_step_host_knots: the "interpolated" sampler's knot draws [K, n_knots] (float32) in, python float out;
+        the perturbations between the knots are interpolated on the device."""
+        self.use_current_stream()
+        if knots_np.dtype != np.float32 or not knots_np.flags.c_contiguous or knots_np.ndim != 2 or knots_np.shape[0] != self.K:
+            raise ValueError(f"knots must be a C-contiguous float32 array [K = {self.K}, n_knots]")
+        for i in range(6):
+            self._s_host[i] = s_np[i]
+        self._chk(self.lib.cps_legacy_step_host_knots(self._h, self._s_host, C.c_void_p(knots_np.ctypes.data),
+                                                      int(knots_np.shape[1]), int(knot_step), self._u_host))
+        return self._u_host[0]
+
+    def legacy_get_perturbations(self) -> np.ndarray:
+        """delta_u [K, T] of the last host-form legacy step (cps_legacy_get_perturbations)."""
+        self.use_current_stream()
+        out = np.empty((self.K, self.T), dtype=np.float32)
+        self._chk(self.lib.cps_legacy_get_perturbations(self._h, C.c_void_p(out.ctypes.data)))
+        return out
+
     def legacy_advance(self) -> float:
         self.use_current_stream()
         self._chk(self.lib.cps_legacy_advance(self._h, self._u_host))

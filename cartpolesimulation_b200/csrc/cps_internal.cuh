@@ -88,6 +88,8 @@ struct cps_handle {
     float *d_s, *d_unom, *d_u;
     float *d_uprev;   // legacy front-end: previous nominal sequence [T]
     float *d_ldu;     // legacy front-end: staging of delta_u for cps_legacy_step_host [K][T]
+    float *d_lknots;  // legacy front-end: knot draws of the interpolated sampler [K][n_knots]
+    size_t n_lknots;  // bytes allocated at d_lknots
     float *h_pin;  // pinned: [0..6) s, [8] u
     float *h_pin_dev;        // device view of h_pin (mapped): the solve writes u straight into host memory
     const float *inline_s;   // set by cps_mppi_step_host around its cps_mppi_step call

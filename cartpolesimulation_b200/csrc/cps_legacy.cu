@@ -178,6 +178,71 @@ extern "C" int cps_legacy_step_host(cps_handle *h, const float *s_host, const fl
     return CPS_OK;
 }
 
+// SAMPLING_TYPE "interpolated" (controller_mppi_cartpole.py:430-451) on the device: the reference draws the perturbation at
+// every `step`-th horizon index and fills the rest with scipy's linear interp1d, i.e. (scipy 1.18, _call_linear) in float64
+//   y = ((x - x_lo) / (x_hi - x_lo)) * y_hi + ((x_hi - x) / (x_hi - x_lo)) * y_lo
+// -- two products and a sum, each rounded, no contraction -- assigned into a float32 array.  Restated with the same
+// operations so that the perturbations are bit-identical to the host path (tested against the recorded delta_u).
+__global__ void __launch_bounds__(256) legacy_interp_kernel(const float *__restrict__ knots, float *__restrict__ du, int K, int T,
+                                                            int n_knots, int step) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)K * T) return;
+    const int k = (int)(i / T), t = (int)(i % T);
+    const int lo = t / step, j = t - lo * step;
+    const float *kn = knots + (long long)k * n_knots;
+    float y = kn[lo];
+    if (j != 0) {
+        const double w_hi = __ddiv_rn((double)j, (double)step), w_lo = __ddiv_rn((double)(step - j), (double)step);
+        y = __double2float_rn(__dadd_rn(__dmul_rn(w_hi, (double)kn[lo + 1]), __dmul_rn(w_lo, (double)kn[lo])));
+    }
+    du[i] = y;
+}
+
+extern "C" int cps_legacy_step_host_knots(cps_handle *h, const float *s_host, const float *knots_host, int n_knots, int knot_step,
+                                          float *u_out_host) {
+    if (!h) return CPS_ERR_INVALID;
+    int rc = legacy_check(h, "cps_legacy_step_host_knots");
+    if (rc != CPS_OK) return rc;
+    if (!s_host || !knots_host || !u_out_host) return fail(h, CPS_ERR_INVALID, "cps_legacy_step_host_knots: null pointer");
+    const int K = h->cfg.num_rollouts, T = h->cfg.horizon;
+    if (knot_step < 1 || n_knots < 1 || (long long)(n_knots - 1) * knot_step < T - 1)
+        return fail(h, CPS_ERR_INVALID, "cps_legacy_step_host_knots: the knots do not cover the horizon");
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    const size_t n_du = sizeof(float) * (size_t)K * T, n_kn = sizeof(float) * (size_t)K * n_knots;
+    if (!h->d_ldu) CUDA_TRY(h, cudaMalloc(&h->d_ldu, n_du));
+    if (h->n_lknots < n_kn) {
+        if (h->d_lknots) cudaFree(h->d_lknots);
+        h->d_lknots = nullptr; h->n_lknots = 0;
+        CUDA_TRY(h, cudaMalloc(&h->d_lknots, n_kn));
+        h->n_lknots = n_kn;
+    }
+    memcpy(h->h_pin, s_host, sizeof(float) * 6);
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_s, h->h_pin, sizeof(float) * 6, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_lknots, knots_host, n_kn, cudaMemcpyHostToDevice, h->stream));
+    const long long n = (long long)K * T;
+    legacy_interp_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->d_lknots, h->d_ldu, K, T, n_knots, knot_step);
+    h->launches += 1;
+    rc = cps_legacy_step(h, h->d_s, h->d_ldu, CPS_ROLLOUT_MAJOR, h->d_u, nullptr, nullptr, CPS_ROLLOUT_MAJOR, nullptr);
+    if (rc != CPS_OK) return rc;
+    CUDA_TRY(h, cudaMemcpyAsync(h->h_pin + 8, h->d_u, sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    *u_out_host = h->h_pin[8];
+    return CPS_OK;
+}
+
+extern "C" int cps_legacy_get_perturbations(cps_handle *h, float *delta_u_host) {
+    if (!h) return CPS_ERR_INVALID;
+    int rc = legacy_check(h, "cps_legacy_get_perturbations");
+    if (rc != CPS_OK) return rc;
+    if (!delta_u_host) return fail(h, CPS_ERR_INVALID, "cps_legacy_get_perturbations: null pointer");
+    if (!h->d_ldu) return fail(h, CPS_ERR_NOT_CONFIGURED, "cps_legacy_get_perturbations: no host-form step has run yet");
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    CUDA_TRY(h, cudaMemcpyAsync(delta_u_host, h->d_ldu, sizeof(float) * (size_t)h->cfg.num_rollouts * h->cfg.horizon,
+                                cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return CPS_OK;
+}
+
 extern "C" int cps_legacy_advance(cps_handle *h, float *u_out_host) {
     if (!h) return CPS_ERR_INVALID;
     int rc = legacy_check(h, "cps_legacy_advance");

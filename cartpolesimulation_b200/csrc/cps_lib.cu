@@ -401,7 +401,7 @@ extern "C" void cps_destroy(cps_handle *h) {
     cps_gmm_free(h);
     cps_grad_free(h);
     cudaFree(h->d_partials); cudaFree(h->d_ticket); cudaFree(h->d_nonfinite); cudaFree(h->d_px_timeouts);
-    cudaFree(h->d_s); cudaFree(h->d_unom); cudaFree(h->d_u); cudaFree(h->d_uprev); cudaFree(h->d_ldu);
+    cudaFree(h->d_s); cudaFree(h->d_unom); cudaFree(h->d_u); cudaFree(h->d_uprev); cudaFree(h->d_ldu); cudaFree(h->d_lknots);
     cudaFree(h->d_rs0); cudaFree(h->d_rQ); cudaFree(h->d_rtraj); cudaFree(h->d_rfinal);
     if (h->h_pin) cudaFreeHost(h->h_pin);
     if (h->pipe_ready) {

@@ -213,6 +213,14 @@ int cps_legacy_step(cps_handle *h, const float *s_dev, const float *delta_u_dev,
 /* Host-buffer form, what controller_mppi_cartpole.step makes per call: s_host [6] and delta_u_host (K x T, `layout`
  * order; pinned memory makes the copy asynchronous) are copied up, *u_out_host = u[0].  Synchronises. */
 int cps_legacy_step_host(cps_handle *h, const float *s_host, const float *delta_u_host, int layout, float *u_out_host);
+/* The same solve with SAMPLING_TYPE "interpolated" (controller_mppi_cartpole.py:430-451) expanded on the device: knots_host
+ * [K][n_knots] are the draws at the horizon indices 0, knot_step, 2 knot_step, ... (already scaled and rounded to float32
+ * as the reference's assignment into its float32 array does); the steps between are filled with scipy interp1d's linear
+ * formula in float64, bit-identical to the host path.  Moves K n_knots floats instead of K T and takes scipy off the
+ * controller's critical path.  cps_legacy_get_perturbations: the [K][T] perturbations of the last host-form step. */
+int cps_legacy_step_host_knots(cps_handle *h, const float *s_host, const float *knots_host, int n_knots, int knot_step,
+                               float *u_out_host);
+int cps_legacy_get_perturbations(cps_handle *h, float *delta_u_host);
 /* An iteration that is not a multiple of update_every (:481): no solve; u_out = u[0], u_prev <- u, shift.  u_out_host
  * may be NULL.  Synchronises only if u_out_host is given. */
 int cps_legacy_advance(cps_handle *h, float *u_out_host);
