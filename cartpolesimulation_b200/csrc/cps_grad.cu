@@ -221,12 +221,13 @@ __global__ void __launch_bounds__(128) plan_grad_jac_kernel(const __grid_constan
     step_record<NSUB>(a, t, k, a.jac + (long long)t * CPS_GRAD_REC * K + k, K);
 }
 
-// One control step of the reverse sweep from its record m (element stride `stride`).
-__device__ __forceinline__ void reverse_step(const float *m, long long stride, float us, float &a_th, float &a_w, float &a_x,
-                                             float &a_v, float &g_out) {
-    float r[CPS_GRAD_REC];
+// One control step of the reverse sweep from its record r.
+__device__ __forceinline__ void load_record(const float *m, long long stride, float (&r)[CPS_GRAD_REC]) {
 #pragma unroll
     for (int j = 0; j < CPS_GRAD_REC; ++j) r[j] = m[j * stride];
+}
+__device__ __forceinline__ void apply_record(const float (&r)[CPS_GRAD_REC], float us, float &a_th, float &a_w, float &a_x, float &a_v,
+                                             float &g_out) {
     const float a_uk = fmaf(r[12], a_th, fmaf(r[13], a_w, fmaf(r[14], a_x, r[15] * a_v)));
     const float n_th = fmaf(r[0], a_th, fmaf(r[1], a_w, fmaf(r[2], a_x, r[3] * a_v)));
     const float n_w = fmaf(r[4], a_th, fmaf(r[5], a_w, fmaf(r[6], a_x, r[7] * a_v)));
@@ -236,6 +237,12 @@ __device__ __forceinline__ void reverse_step(const float *m, long long stride, f
     a_w = n_w + r[17];
     a_x = a_x + r[18];
     a_v = n_v;
+}
+__device__ __forceinline__ void reverse_step(const float *m, long long stride, float us, float &a_th, float &a_w, float &a_x,
+                                             float &a_v, float &g_out) {
+    float r[CPS_GRAD_REC];
+    load_record(m, stride, r);
+    apply_record(r, us, a_th, a_w, a_x, a_v, g_out);
 }
 
 // Fused: a block takes P plans, thread (t, plan) leaves its record in shared memory ([T][CPS_GRAD_REC][P]), then the first P
@@ -266,11 +273,17 @@ __global__ void __launch_bounds__(128) plan_grad_rev_kernel(const __grid_constan
     const int T = a.T, K = a.K;
     float *g = a.G + (long long)k * a.gs_k;
     float a_th = 0.0f, a_w = 0.0f, a_x = 0.0f, a_v = 0.0f;
-#pragma unroll 4
+    // the records do not depend on the adjoint: the next one is read while this one is applied
+    float r[CPS_GRAD_REC], rn[CPS_GRAD_REC];
+    load_record(a.jac + (long long)(T - 1) * CPS_GRAD_REC * K + k, K, r);
+#pragma unroll 1
     for (int t = T - 1; t >= 0; --t) {
+        if (t > 0) load_record(a.jac + (long long)(t - 1) * CPS_GRAD_REC * K + k, K, rn);
         float go;
-        reverse_step(a.jac + (long long)t * CPS_GRAD_REC * K + k, K, a.ode.u_scale, a_th, a_w, a_x, a_v, go);
+        apply_record(r, a.ode.u_scale, a_th, a_w, a_x, a_v, go);
         g[(long long)t * a.gs_t] = go;
+#pragma unroll
+        for (int j = 0; j < CPS_GRAD_REC; ++j) r[j] = rn[j];
     }
 }
 
