@@ -19,7 +19,8 @@
 // (The first version did all of it in one thread per plan: 3 T n sequential substep evaluations, 0.124 ms for 16 plans.)
 // rpgd_update_kernel is the rest of grad_step (:176-180): tf.clip_by_norm per plan, the Adam step (Keras legacy Adam =
 // ResourceApplyAdam) and the clip to the control limits.
-// Cost plugin: quadratic_boundary_grad_minimal (the plugin the shipped RPGD configuration uses); predictor "ODE".
+// Cost plugins: quadratic_boundary_grad_minimal (the plugin the shipped RPGD configuration uses) and quadratic_boundary_grad;
+// predictor "ODE".
 #include <cuda_runtime.h>
 
 #include <cmath>
@@ -52,6 +53,8 @@ struct GradArgs {
     const float *Q;
     long long qs_k, qs_t;
     int K, T;
+    int full;        // cost plugin: 0 quadratic_boundary_grad_minimal, 1 quadratic_boundary_grad
+    float u_prev;    // the input applied before the plan (quadratic_boundary_grad's control-change term)
     float inv_T1;
     float *ck, *jac, *J, *G;
     long long gs_k, gs_t;
@@ -90,6 +93,7 @@ __device__ __forceinline__ Sub grad_substep(const OdeParams &P, float &th, float
     return in;
 }
 
+// Partial derivatives of the stage cost with respect to (angle, angleD, position).
 // quadratic_boundary_grad_minimal (Control_Toolkit_ASF/Cost_Functions/CartPole/quadratic_boundary_grad_minimal.py:62-130);
 // w: [dd_q, db, ep, ekp, cc*R, bf = f thl, 1/((1-f) thl)] as in stage_cost<COST_GRADMIN>.
 __device__ __forceinline__ void gradmin_partials(const CostParams &C, float th, float w, float x, float &d_th, float &d_w,
@@ -102,6 +106,23 @@ __device__ __forceinline__ void gradmin_partials(const CostParams &C, float th, 
     d_x = fmaf(C.w[0] * 2.0f * dist, C.inv_2thl, C.w[1] * 2.0f * over * C.w[6] * copysignf(1.0f, x));
     d_th = C.w[2] * 2.0f * (1.0f - C.target_equilibrium * c) * (C.target_equilibrium * sn);
     d_w = 2.0f * C.w[3] * w;
+}
+// quadratic_boundary_grad (quadratic_boundary_grad.py:62-142, 202-240); w as in stage_cost<COST_GRAD>:
+// [dd_q, dd_lin, db, ep, ekp, cc*R, ccrc, bf, 1/((1-f) thl), tmax, cos(admissible angle)].  The kinetic term is
+// |angleD^2 - tmax scaling(angle)| with the target under stop_gradient (:133-139): no derivative with respect to the angle.
+__device__ __forceinline__ float sgnf(float x) { return (float)(x > 0.0f) - (float)(x < 0.0f); }   // d|x|/dx with 0 at 0, as autograd
+__device__ __forceinline__ void grad_partials(const CostParams &C, float th, float w, float x, float &d_th, float &d_w,
+                                              float &d_x) {
+    float sn, c;
+    sincos_th(th, sn, c);
+    const float e = C.target_equilibrium;
+    const float dist = (x - C.target_position) * C.inv_2thl;
+    const float apos = fabsf(x);
+    const float over = (apos > C.w[7]) ? (apos - C.w[7]) * C.w[8] : 0.0f;
+    d_x = fmaf(C.w[0] * 2.0f * dist, C.inv_2thl, C.w[2] * 2.0f * over * C.w[8] * copysignf(1.0f, x)) + C.w[1] * sgnf(dist) * C.inv_2thl;
+    d_th = C.w[3] * 2.0f * (2.0f - e * c) * (e * sn);
+    const float scaling = (e * (c - C.w[10]) > 0.0f) ? 0.0f : 0.5f * (1.0f - e * c);
+    d_w = C.w[4] * sgnf(fmaf(w, w, -C.w[9] * scaling)) * 2.0f * w;
 }
 
 // ---- forward: one thread per plan; cost and a checkpoint per control step ---------------------------------------------------
@@ -118,7 +139,7 @@ __global__ void __launch_bounds__(128) plan_grad_fwd_kernel(const __grid_constan
     float c_cost = cosf(z.th);
     const float *q = a.Q + (long long)k * a.qs_k;
     float *ck = a.ck + k;
-    float Jacc = 0.0f;
+    float Jacc = 0.0f, up = a.u_prev;
     float qn = q[0];
 #pragma unroll 1
     for (int t = 0; t < T; ++t) {
@@ -126,9 +147,10 @@ __global__ void __launch_bounds__(128) plan_grad_fwd_kernel(const __grid_constan
         if (t + 1 < T) qn = q[(long long)(t + 1) * a.qs_t];   // prefetch under the integration
         ck[((long long)t * 4 + 0) * K] = z.th; ck[((long long)t * 4 + 1) * K] = z.w;
         ck[((long long)t * 4 + 2) * K] = z.x;  ck[((long long)t * 4 + 3) * K] = z.v;
-        Jacc += stage_cost<COST_GRADMIN>(C, c_cost, z.w, z.x, u, 0.0f);
+        Jacc += a.full ? stage_cost<COST_GRAD>(C, c_cost, z.w, z.x, u, up) : stage_cost<COST_GRADMIN>(C, c_cost, z.w, z.x, u, 0.0f);
         control_step<1, SC_ROTATE, false, false, false, NSUB>(ode, z, u);
         c_cost = z.c;
+        up = u;
     }
     const float J = __fdiv_rn(Jacc, (float)(T + 1));   // the plugin's terminal cost is zero
     if (a.J) a.J[k] = J;
@@ -203,12 +225,22 @@ __device__ __forceinline__ void step_record(const GradArgs &a, int t, int k, flo
     }
     // what the reverse sweep adds at this control-step boundary: the cost plugin's partial derivatives at the step's first
     // state and its control term, with the 1 / (T + 1) of the mean
-    float d_th, d_w, d_x;
-    gradmin_partials(a.cost, th0, w0, x0, d_th, d_w, d_x);
+    float d_th, d_w, d_x, d_u;
+    if (a.full) {
+        grad_partials(a.cost, th0, w0, x0, d_th, d_w, d_x);
+        // cc u_t^2 + ccrc (u_t - u_{t-1})^2 of this stage and ccrc (u_{t+1} - u_t)^2 of the next (_control_change_rate_cost, :174-180)
+        const float *q = a.Q + (long long)k * a.qs_k;
+        const float up = (t > 0) ? q[(long long)(t - 1) * a.qs_t] : a.u_prev;
+        d_u = 2.0f * a.cost.w[5] * u + 2.0f * a.cost.w[6] * (u - up);
+        if (t + 1 < a.T) d_u -= 2.0f * a.cost.w[6] * (q[(long long)(t + 1) * a.qs_t] - u);
+    } else {
+        gradmin_partials(a.cost, th0, w0, x0, d_th, d_w, d_x);
+        d_u = 2.0f * a.cost.w[4] * u;
+    }
     o[16 * stride] = a.inv_T1 * d_th;
     o[17 * stride] = a.inv_T1 * d_w;
     o[18 * stride] = a.inv_T1 * d_x;
-    o[19 * stride] = a.inv_T1 * 2.0f * a.cost.w[4] * u;
+    o[19 * stride] = a.inv_T1 * d_u;
 }
 
 // records to global memory (horizons too long for the fused kernel below)
@@ -386,8 +418,8 @@ static int grad_state(cps_handle *h, GradState **out) {
     if (h->grad) { *out = h->grad; return CPS_OK; }
     if (h->cfg.integrator != CPS_EULER_CROMER)
         return fail(h, CPS_ERR_UNSUPPORTED, "cps_plan_cost_grad: the adjoint is built for predictor \"ODE\" (Euler-Cromer)");
-    if (h->cfg.cost_id != CPS_COST_QB_GRAD_MINIMAL)
-        return fail(h, CPS_ERR_UNSUPPORTED, "cps_plan_cost_grad: the adjoint is built for the quadratic_boundary_grad_minimal plugin");
+    if (h->cfg.cost_id != CPS_COST_QB_GRAD_MINIMAL && h->cfg.cost_id != CPS_COST_QB_GRAD)
+        return fail(h, CPS_ERR_UNSUPPORTED, "cps_plan_cost_grad: the adjoint is built for the quadratic_boundary_grad_minimal and quadratic_boundary_grad plugins");
     if (h->cfg.substeps > CPS_GRAD_MAX_SUBSTEPS)
         return fail(h, CPS_ERR_UNSUPPORTED, "cps_plan_cost_grad: at most 32 substeps per control step");
     GradState *G = new (std::nothrow) GradState();
@@ -416,7 +448,6 @@ extern "C" int cps_plan_cost_grad(cps_handle *h, const float *s_dev, const float
                                   float *J_out_dev, float *G_out_dev) {
     if (!h) return CPS_ERR_INVALID;
     if (!s_dev || !Q_dev || !G_out_dev) return fail(h, CPS_ERR_INVALID, "cps_plan_cost_grad: null pointer");
-    (void)u_prev;   // quadratic_boundary_grad_minimal has no control-change term
     CUDA_TRY(h, cudaSetDevice(h->cfg.device));
     GradState *G;
     int rc = grad_state(h, &G);
@@ -432,6 +463,8 @@ extern "C" int cps_plan_cost_grad(cps_handle *h, const float *s_dev, const float
     if (q_layout == CPS_TIME_MAJOR) { a.qs_k = 1; a.qs_t = K; a.gs_k = 1; a.gs_t = K; }
     else { a.qs_k = T; a.qs_t = 1; a.gs_k = T; a.gs_t = 1; }
     a.K = K; a.T = T;
+    a.full = h->cfg.cost_id == CPS_COST_QB_GRAD ? 1 : 0;
+    a.u_prev = u_prev;   // enters quadratic_boundary_grad's control-change term only
     a.inv_T1 = 1.0f / (float)(T + 1);
     a.ck = G->d_ck; a.jac = G->d_jac; a.J = J_out_dev ? J_out_dev : G->d_J; a.G = G_out_dev;
     a.nonfinite = h->d_nonfinite;

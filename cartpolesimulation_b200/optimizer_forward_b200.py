@@ -334,8 +334,8 @@ class optimizer_rpgd_b200(_forward_optimizer):
     The gradient -- a GradientTape around predict_and_cost in the reference -- is one adjoint kernel launch
     (cps_rpgd_grad_step: gradient, clip_by_norm, Adam, clip to the limits); the plans and the Adam moments stay on the
     device, the per-solve bookkeeping of step() (:297-356: argsort of K costs, gather, shift) is a handful of torch index
-    operations on those device tensors.  Predictor "ODE", cost quadratic_boundary_grad_minimal (the shipped configuration);
-    no CPU fallback."""
+    operations on those device tensors.  Predictor "ODE"; cost quadratic_boundary_grad_minimal (the shipped configuration) or
+    quadratic_boundary_grad; no CPU fallback."""
 
     def __init__(self, predictor, cost_function, control_limits, computation_library=None, seed=None,
                  mpc_horizon: int = 35, num_rollouts: int = 16, outer_its: int = 4, sample_stdev: float = 0.5,

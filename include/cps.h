@@ -474,8 +474,9 @@ int cps_selftest_sincos(cps_handle *h, long long *mismatches_out);
  * checkpoint per control step, the control steps' transposed Jacobians (hand-derived adjoint of the Euler-Cromer substep) in
  * parallel over (step, plan), reverse sweep over the steps with the cost plugin's partial derivatives (two launches).  Q_dev [K][T] (or [T][K] with CPS_TIME_MAJOR) for the handle's K and T; J_out_dev [K] (or NULL) the costs,
  * G_out_dev the gradient in the layout of Q.  Predictor "ODE" with cos / sin from the angle every substep (the arithmetic
- * the reference differentiates), cost quadratic_boundary_grad_minimal (the shipped RPGD configuration); anything else:
- * CPS_ERR_UNSUPPORTED.
+ * the reference differentiates), cost quadratic_boundary_grad_minimal (the shipped RPGD configuration) or
+ * quadratic_boundary_grad (u_prev enters its control-change term; its kinetic term's target is under stop_gradient, as in
+ * the plugin); anything else: CPS_ERR_UNSUPPORTED.
  * cps_rpgd_grad_step is grad_step (:166-180) on the device: the gradient, tf.clip_by_norm over each plan (gradmax_clip), one
  * Adam step (Keras legacy Adam: lr_t = lr sqrt(1 - b2^t) / (1 - b1^t), m, v per element, handle-owned, t = iterations since
  * cps_rpgd_reset) and the clip to the control limits, in place on Q_dev [K][T].  cps_rpgd_adam_state exposes the device

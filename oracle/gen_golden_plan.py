@@ -33,6 +33,11 @@ def _make(cls_name, pred, cost, K, T, tp, te, rng=None, configure_kw=None, **par
     import torch
     from SI_Toolkit.computation_library import TensorFlowLibrary
     lib = R.torch_lib()
+    if cost == "quadratic_boundary_grad":
+        # TF-only plugin in the reference (PyTorchLibrary has no stop_gradient / cond, computation_library.py:501): their torch
+        # counterparts -- detach() is what tf.stop_gradient does to the tape
+        lib.stop_gradient = lambda x: x.detach() if hasattr(x, "detach") else x
+        lib.cond = lambda c, true_fn, false_fn: true_fn() if bool(c) else false_fn()
     vp = R.variable_parameters(lib, tp, te)
     cw = R.cost_function(cost, lib, vp, K, T)
     Pred = R.ODEv0CoreAdapter if pred == "ODE_v0" else R.ODECoreAdapter
@@ -149,18 +154,23 @@ def gen_rpgd():
     import zlib
     import torch
     from oracle import oracle as O
-    runs = [  # name, K, T, steps, outer_its, resamp_per, keep ratio, period of the inducing points, tp, te
-        ("rpgd_default", 16, 35, 12, 4, 10, 0.75, 4, 0.0, 1.0),      # the shipped configuration (config_optimizers.yml:63-85)
-        ("rpgd_resamp3", 24, 20, 8, 2, 3, 0.5, 5, 0.05, 1.0),
+    GM, GR = "quadratic_boundary_grad_minimal", "quadratic_boundary_grad"
+    runs = [  # name, K, T, steps, outer_its, resamp_per, keep ratio, period of the inducing points, tp, te, cost plugin
+        ("rpgd_default", 16, 35, 12, 4, 10, 0.75, 4, 0.0, 1.0, GM),      # the shipped configuration (config_optimizers.yml:63-85)
+        ("rpgd_resamp3", 24, 20, 8, 2, 3, 0.5, 5, 0.05, 1.0, GM),
+        ("rpgd_qbgrad", 16, 35, 6, 4, 4, 0.75, 4, 0.0, 1.0, GR),         # the same optimizer on the other gradient cost plugin
     ]
-    for (name, K, T, steps, its, resamp, ratio, p, tp, te) in runs:
+    only = os.environ.get("CPS_GOLDEN_ONLY")   # regenerate one fixture without touching the others
+    for (name, K, T, steps, its, resamp, ratio, p, tp, te, cost) in runs:
+        if only and name != only:
+            continue
         rng = np.random.default_rng(zlib.crc32(name.encode()))
         n_ind = int(np.ceil((T - 1) / p)) + 1
         keep = int(max(int(K * ratio), 1))
         n_resamp = sum(1 for c in range(steps) if c % resamp == 0)
         draws = [rng.standard_normal((K, n_ind, 1)).astype(np.float32)] + \
                 [rng.standard_normal((K - keep, n_ind, 1)).astype(np.float32) for _ in range(n_resamp)]
-        opt = _make("optimizer_rpgd_tf", "ODE", "quadratic_boundary_grad_minimal", K, T, tp, te,
+        opt = _make("optimizer_rpgd_tf", "ODE", cost, K, T, tp, te,
                     rng=tf_shim.InjectedDraws(draws), configure_kw=dict(dt=0.02, predictor_specification="ODE"),   # optimizer_reset: first draw
                     outer_its=its, sample_stdev=0.5,
                     sample_mean=0.0, sample_whole_control_space=False, uniform_dist_min=-0.8, uniform_dist_max=0.8,
@@ -181,7 +191,7 @@ def gen_rpgd():
             s = O.rollout("ODE", s, np.array([[float(np.asarray(u).reshape(-1)[0])]], dtype=np.float32))[0, 1]
         save("plan_" + name, dict(ref="Control_Toolkit/Optimizers/optimizer_rpgd_tf.py:149-408 (tf ops, GradientTape and Keras "
                                       "legacy Adam from oracle/tf_shim.py; injected normal draws)", predictor="ODE",
-                                  cost="quadratic_boundary_grad_minimal", K=K, T=T, steps=steps, outer_its=its, resamp_per=resamp,
+                                  cost=cost, K=K, T=T, steps=steps, outer_its=its, resamp_per=resamp,
                                   opt_keep_k_ratio=ratio, period_interpolation_inducing_points=p, learning_rate=0.05,
                                   gradmax_clip=5.0, sample_stdev=0.5, target_position=tp, target_equilibrium=te),
              draw0=draws[0][:, :, 0], resamp_draws=np.stack([d[:, :, 0] for d in draws[1:]]), s=np.stack(S), u=np.array(U),

@@ -4,18 +4,24 @@ numpy restatement (oracle.plan_cost_grad)."""
 import numpy as np
 import pytest
 
-from tests.parity import load_golden, record
+from tests.parity import close_except_few, load_golden, record
 
 pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")
 
-GRAD = ["grad_gradmin_K16_T35", "grad_gradmin_K64_T20", "grad_gradmin_down_K32_T50"]
+GRAD = ["grad_gradmin_K16_T35", "grad_gradmin_K64_T20", "grad_gradmin_down_K32_T50",
+        "grad_qbgrad_K16_T35", "grad_qbgrad_terms_K64_T20", "grad_qbgrad_down_K32_T50"]
 
 
-def _engine(K, T, tp=0.0, te=1.0, integ="ODE", cost="quadratic_boundary_grad_minimal"):
+def _engine(K, T, tp=0.0, te=1.0, integ="ODE", cost="quadratic_boundary_grad_minimal", cost_config=None):
+    from cartpolesimulation_b200 import config as cfgmod
     from cartpolesimulation_b200.core import Engine
     eng = Engine(K, T, integrator=integ, cost=cost, device=0)
     eng.set_variable_parameters(tp, te)
+    if cost_config:   # non-default plugin weights (config_cost_function.yml values), folded as the plugin folds them
+        cfg = dict(cfgmod.DEFAULT_COST_CONFIG[cost])
+        cfg.update(cost_config)
+        eng.set_cost_params(cfgmod.cost_vector(cost, cfg))
     return eng
 
 
@@ -25,7 +31,7 @@ def test_gradient_matches_autograd_through_the_reference(name, layout):
     from cartpolesimulation_b200 import _lib as L
     z, m = load_golden(name)
     K, T = m["K"], m["T"]
-    eng = _engine(K, T, m["target_position"], m["target_equilibrium"])
+    eng = _engine(K, T, m["target_position"], m["target_equilibrium"], cost=m["cost"], cost_config=m.get("cost_config_overrides"))
     Q = z["Q"] if layout == "rollout_major" else np.ascontiguousarray(z["Q"].T)
     J, G = eng.plan_cost_grad(torch.from_numpy(z["s"]).cuda(), torch.from_numpy(Q.copy()).cuda(),
                               L.ROLLOUT_MAJOR if layout == "rollout_major" else L.TIME_MAJOR, m["u_prev"])
@@ -33,8 +39,8 @@ def test_gradient_matches_autograd_through_the_reference(name, layout):
     eJ = float(np.abs(J.cpu().numpy() - z["J"]).max() / np.abs(z["J"]).max())
     eG = float(np.abs(G - z["G"]).max() / np.abs(z["G"]).max())
     record("gradient_vs_reference_autograd", f"{name}/{layout}", J=eJ, G=eG)
-    assert eJ < 1e-5
-    assert eG < 5e-5      # measured <= 1.5e-5 of the largest entry: two float32 realisations of a 350..500-substep adjoint
+    assert eJ < (2e-5 if name == "grad_qbgrad_down_K32_T50" else 1e-5)   # that golden's own float32 noise is 1.1e-5 (test_oracle_grad.py)
+    assert eG < 5e-5      # measured <= 2.5e-5 of the largest entry: two float32 realisations of a 350..500-substep adjoint
     assert eng.nonfinite_costs() == 0
 
 
@@ -56,6 +62,29 @@ def test_gradient_vs_oracle_sizes(K, T):
     # the costs are those of the forward-only planner kernel (rotation substeps) to float32 noise
     Jp = eng.plan_cost(torch.from_numpy(s).cuda(), torch.from_numpy(Q).cuda(), L.ROLLOUT_MAJOR, 0.0)[0].cpu().numpy()
     assert np.abs(J.cpu().numpy() - Jp).max() <= 1e-5 * np.abs(Jp).max()
+
+
+@pytest.mark.parametrize("te", [1.0, -1.0])
+def test_gradient_quadratic_boundary_grad_vs_oracle(te):
+    """quadratic_boundary_grad with its linear-distance and control-change terms on, both target equilibria, u_prev != 0."""
+    from cartpolesimulation_b200 import _lib as L
+    from oracle import oracle as O
+    K, T = 300, 25
+    rng = np.random.default_rng(11)
+    a = 2.2
+    s = np.array([a, -0.4, np.cos(a), np.sin(a), 0.16, 0.2], dtype=np.float32)
+    Q = np.clip(rng.normal(0, 0.6, (K, T)), -1, 1).astype(np.float32)
+    sfx = "_up" if te == 1.0 else "_down"
+    over = {"dd_linear_weight" + sfx: 25.0, "ccrc_weight" + sfx: 1.5}
+    eng = _engine(K, T, -0.02, te, cost="quadratic_boundary_grad", cost_config=over)
+    J, G = eng.plan_cost_grad(torch.from_numpy(s).cuda(), torch.from_numpy(Q).cuda(), L.ROLLOUT_MAJOR, -0.3)
+    cfg = dict(O.DEFAULT_COST_CONFIG["quadratic_boundary_grad"])
+    cfg.update(over)
+    Jr, Gr = O.plan_cost_grad("quadratic_boundary_grad", s, Q, -0.3, -0.02, te, cost_cfg=cfg)
+    eJ = float(np.abs(J.cpu().numpy() - Jr).max() / np.abs(Jr).max())
+    eG = float(np.abs(G.cpu().numpy() - Gr).max() / np.abs(Gr).max())
+    record("gradient_qb_grad_vs_oracle", f"te{te:+.0f}", J=eJ, G=eG)
+    assert eJ < 1e-5 and eG < 5e-5
 
 
 def test_rpgd_grad_step_is_clip_adam_clip():
@@ -98,7 +127,7 @@ def test_gradient_rejects_other_configurations():
             eng.plan_cost_grad(torch.zeros(6, device="cuda"), torch.zeros((8, 5), device="cuda"), L.ROLLOUT_MAJOR, 0.0)
 
 
-RPGD = ["plan_rpgd_default", "plan_rpgd_resamp3"]
+RPGD = ["plan_rpgd_default", "plan_rpgd_resamp3", "plan_rpgd_qbgrad"]
 
 
 class _Draws:
@@ -150,10 +179,13 @@ def test_optimizer_rpgd_b200_matches_reference(name):
         assert isinstance(u, np.ndarray) and u.dtype == np.float32
         Q_opt = opt.logging_values["Q_logged"][:, :, 0]
         eQ, eu = float(np.abs(Q_opt - z["Q"][i]).max()), abs(float(u) - float(z["u"][i]))
-        record("optimizer_rpgd", f"{name}/{i}", Q=eQ, u=eu)
-        assert eQ < 2e-4
+        record("optimizer_rpgd", f"{name}/{i}", Q=eQ, u=eu, Q_entries_over_2e_4=int((np.abs(Q_opt - z["Q"][i]) > 2e-4).sum()))
+        # quadratic_boundary_grad: a plan entry whose gradient is at rounding level takes an ill-conditioned Adam step
+        # (g / (|g| + eps)); the float64 restatement shows the same single entry (tests/test_oracle_plan.py)
+        few = dict(max_outliers=2, outlier_atol=2e-3) if name == "plan_rpgd_qbgrad" else {}
+        assert close_except_few(Q_opt, z["Q"][i], 2e-4, **few), eQ
         assert eu < 1e-4                                              # north_star: selected control within 1e-4
-        np.testing.assert_allclose(opt.Q_tf.cpu().numpy(), z["Q_next"][i], rtol=0, atol=2e-4)
+        assert close_except_few(opt.Q_tf.cpu().numpy(), z["Q_next"][i], 2e-4, **few)
         mm, vv, it = opt.engine.rpgd_adam_state()
         assert it == int(z["adam_iterations"][i])
         np.testing.assert_allclose(mm.cpu().numpy(), z["adam_m"][i], rtol=0, atol=2e-4 * max(1.0, np.abs(z["adam_m"][i]).max()))
