@@ -1,6 +1,7 @@
 // cps_net_tc.cu -- the GRU predictor on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a.
 //
-// net_tc_kernel<MPPI>: one CTA advances 128 rollouts (one per TMEM lane) of a 2 x 64 GRU through the horizon as a
+// net_tc_kernel<MPPI>: one CTA advances 128 rollouts (one per TMEM lane) of a 2 x 64 GRU (narrower layers: zero-padded to 64
+// units by cps_net_tc_build_image) through the horizon as a
 // software pipeline of warp-specialised roles, so that the tensor pipe, the MUFU-bound gate epilogues and the per-rollout
 // bookkeeping overlap instead of taking turns:
 //   * warp 20 (converged, one elected lane executes): issues every tcgen05.mma.  Each layer is processed as two HALF-LAYER jobs of 32 hidden units
@@ -200,7 +201,8 @@ __global__ void __launch_bounds__(TC_NT, 1) net_tc_kernel(const __grid_constant_
             for (int ch = 0; ch < 2; ++ch) {
                 const int u0 = chunk_u0(ch);
 #pragma unroll
-                for (int i = 0; i < TC_EU; ++i) v[i] = a.h0[(long long)kc * a.hs_b + l * TC_H + u0 + i];
+                for (int i = 0; i < TC_EU; ++i)   // layers narrower than 64 units: the padding units carry (and keep) zero
+                    v[i] = (u0 + i < N.hsz[l]) ? a.h0[(long long)kc * a.hs_b + N.hoff[l] + u0 + i] : 0.0f;
                 if (stk) write_operand8_stacked(tl, (l ? C_AH2_HI : C_AH1_HI) + (u0 >> 1), v, lane);
                 else write_operand8(tl, (l ? C_AH2_HI : C_AH1_HI) + (u0 >> 1), (l ? C_AH2_LO : C_AH1_LO) + (u0 >> 1), v);
             }
@@ -413,12 +415,13 @@ __global__ void __launch_bounds__(TC_NT, 1) net_tc_kernel(const __grid_constant_
                 else read_operand8(tl, (l ? C_AH2_HI : C_AH1_HI) + (u0 >> 1), (l ? C_AH2_LO : C_AH1_LO) + (u0 >> 1), v);
                 if (dst) {
 #pragma unroll
-                    for (int i = 0; i < TC_EU; ++i) dst[l * TC_H + u0 + i] = v[i];
+                    for (int i = 0; i < TC_EU; ++i)
+                        if (u0 + i < N.hsz[l]) dst[N.hoff[l] + u0 + i] = v[i];
                 }
             }
         }
     };
-    if (a.h_final && is_epi) store_hidden((live && k < a.B) ? a.h_final + (long long)k * (2 * TC_H) : nullptr, stk);
+    if (a.h_final && is_epi) store_hidden((live && k < a.B) ? a.h_final + (long long)k * N.htot : nullptr, stk);
 
     bool last = false;
     if (MPPI) {
@@ -471,7 +474,7 @@ __global__ void __launch_bounds__(TC_NT, 1) net_tc_kernel(const __grid_constant_
                     for (int ch = 0; ch < 2; ++ch) {
                         const int u0 = chunk_u0(ch);
 #pragma unroll
-                        for (int i = 0; i < TC_EU; ++i) v[i] = a.h_ref[l * TC_H + u0 + i];
+                        for (int i = 0; i < TC_EU; ++i) v[i] = (u0 + i < N.hsz[l]) ? a.h_ref[N.hoff[l] + u0 + i] : 0.0f;
                         write_operand8(tl, (l ? C_AH2_HI : C_AH1_HI) + (u0 >> 1), (l ? C_AH2_LO : C_AH1_LO) + (u0 >> 1), v);
                     }
                 }
@@ -524,7 +527,9 @@ __global__ void __launch_bounds__(TC_NT, 1) net_tc_kernel(const __grid_constant_
 // host side
 // =====================================================================================================
 bool cps_net_tc_eligible(const NetDev &N) {
-    return N.type == CPS_NET_GRU && N.n_layers == 2 && N.hsz[0] == TC_H && N.hsz[1] == TC_H && N.n_in <= 7 && N.n_out <= 6
+    // layers of up to 64 units: narrower ones are padded with units whose weights and biases are zero (their gates give
+    // h' = h / 2 from h = 0, and nothing reads them)
+    return N.type == CPS_NET_GRU && N.n_layers == 2 && N.hsz[0] >= 1 && N.hsz[0] <= TC_H && N.hsz[1] >= 1 && N.hsz[1] <= TC_H && N.n_in <= 7 && N.n_out <= 6
            && !N.differential;
 }
 
@@ -538,7 +543,36 @@ size_t cps_net_tc_smem(const MppiParams *mp, bool mppi) {
 // order + the per-column epilogue constants {c = 1 / (128 s_n), b = bias}.
 void cps_net_tc_build_image(const NetDev &N, const float *w, std::vector<unsigned char> &img) {
     img.assign(TC_IMAGE_BYTES, 0);
-    const int H = TC_H, n_in = N.n_in;
+    const int H = TC_H, n_in = N.n_in, H1 = N.hsz[0], H2 = N.hsz[1];
+    // torch-order weights of the H1 / H2-unit layers -> the same order for two 64-unit layers, zero in the padding units
+    std::vector<float> wp((size_t)3 * H * n_in + 3 * H * H + 6 * H + 6 * H * H + 6 * H + (size_t)N.n_out * H + N.n_out, 0.0f);
+    {
+        const float *s_ih1 = w, *s_hh1 = s_ih1 + 3 * H1 * n_in, *s_bi1 = s_hh1 + 3 * H1 * H1, *s_bh1 = s_bi1 + 3 * H1;
+        const float *s_ih2 = s_bh1 + 3 * H1, *s_hh2 = s_ih2 + 3 * H2 * H1, *s_bi2 = s_hh2 + 3 * H2 * H2, *s_bh2 = s_bi2 + 3 * H2;
+        const float *s_out = s_bh2 + 3 * H2, *s_bo = s_out + N.n_out * H2;
+        float *d_ih1 = wp.data(), *d_hh1 = d_ih1 + 3 * H * n_in, *d_bi1 = d_hh1 + 3 * H * H, *d_bh1 = d_bi1 + 3 * H;
+        float *d_ih2 = d_bh1 + 3 * H, *d_hh2 = d_ih2 + 3 * H * H, *d_bi2 = d_hh2 + 3 * H * H, *d_bh2 = d_bi2 + 3 * H;
+        float *d_out = d_bh2 + 3 * H, *d_bo = d_out + N.n_out * H;
+        for (int g = 0; g < 3; ++g) {
+            for (int u = 0; u < H1; ++u) {
+                for (int kk = 0; kk < n_in; ++kk) d_ih1[(size_t)(g * H + u) * n_in + kk] = s_ih1[(size_t)(g * H1 + u) * n_in + kk];
+                for (int kk = 0; kk < H1; ++kk) d_hh1[(size_t)(g * H + u) * H + kk] = s_hh1[(size_t)(g * H1 + u) * H1 + kk];
+                d_bi1[g * H + u] = s_bi1[g * H1 + u];
+                d_bh1[g * H + u] = s_bh1[g * H1 + u];
+            }
+            for (int u = 0; u < H2; ++u) {
+                for (int kk = 0; kk < H1; ++kk) d_ih2[(size_t)(g * H + u) * H + kk] = s_ih2[(size_t)(g * H2 + u) * H1 + kk];
+                for (int kk = 0; kk < H2; ++kk) d_hh2[(size_t)(g * H + u) * H + kk] = s_hh2[(size_t)(g * H2 + u) * H2 + kk];
+                d_bi2[g * H + u] = s_bi2[g * H2 + u];
+                d_bh2[g * H + u] = s_bh2[g * H2 + u];
+            }
+        }
+        for (int o = 0; o < N.n_out; ++o) {
+            for (int kk = 0; kk < H2; ++kk) d_out[(size_t)o * H + kk] = s_out[(size_t)o * H2 + kk];
+            d_bo[o] = s_bo[o];
+        }
+    }
+    w = wp.data();
     const float *w_ih1 = w, *w_hh1 = w_ih1 + 3 * H * n_in, *b_ih1 = w_hh1 + 3 * H * H, *b_hh1 = b_ih1 + 3 * H;
     const float *w_ih2 = b_hh1 + 3 * H, *w_hh2 = w_ih2 + 3 * H * H, *b_ih2 = w_hh2 + 3 * H * H, *b_hh2 = b_ih2 + 3 * H;
     const float *w_out = b_hh2 + 3 * H, *b_out = w_out + N.n_out * H;

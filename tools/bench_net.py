@@ -21,9 +21,10 @@ def main():
     ap.add_argument("--T", type=int, default=50)
     ap.add_argument("--iters", type=int, default=50)
     ap.add_argument("--kernel", default=None, choices=[None, "tensor", "fp32"])
+    ap.add_argument("--hidden", type=int, default=64, help="units per GRU layer (64: tensor-core kernel; else FP32 kernel)")
     args = ap.parse_args()
     from cartpolesimulation_b200.core import Engine
-    spec = synthetic_net_spec()
+    spec = synthetic_net_spec((args.hidden, args.hidden))
     K, T = args.K, args.T
     eng = Engine(K, T, integrator="neural", cost="quadratic_boundary_grad_minimal", device=0, net_kernel=args.kernel)
     eng.net_load(spec)
@@ -44,7 +45,7 @@ def main():
         ts.append(e0.elapsed_time(e1))
     ms = float(np.median(ts))
     fl = net_flops_per_step(spec) * K * T
-    print(f"neural MPPI solve K={K} T={T} GRU 2x64: kernel {ms * 1e3:.1f} us median, {K * T / ms * 1e3:.3e} net-steps/s, "
+    print(f"neural MPPI solve K={K} T={T} GRU 2x{args.hidden}: kernel {ms * 1e3:.1f} us median, {K * T / ms * 1e3:.3e} net-steps/s, "
           f"{fl / ms / 1e9:.2f} TFLOP/s fp32 ({fl / 1e9:.2f} GFLOP per solve)")
     # host-to-host latency through step_host
     s_np = s.cpu().numpy()
