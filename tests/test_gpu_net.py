@@ -504,3 +504,41 @@ def test_tc_padded_gru32_mppi_vs_reference_golden(run):
         h = z["h_after"][i].copy()
         u_nom = z["u_nom"][i].copy()
     assert eng.nonfinite_costs() == 0
+
+
+@pytest.mark.parametrize("hsz", [(32, 32), (48, 40), (16, 64), (64, 24), (8, 8)])
+@pytest.mark.parametrize("K", [500, 6000, 12000])   # 32 / 64 / 128 live rollouts per CTA
+def test_tc_padded_widths_match_fp32_kernel(hsz, K):
+    """two-layer GRUs narrower than the tensor-core kernel's 64 units (zero-padded image; k-steps and half-layer jobs that hold
+    only padding are skipped): same costs, control, nominal inputs and stored hidden state as the FP32 kernel, which is
+    pinned against the reference for arbitrary widths."""
+    import torch
+    from cartpolesimulation_b200 import _lib as L
+    from cartpolesimulation_b200.core import Engine
+    from cartpolesimulation_b200.neural import synthetic_net_spec
+    spec = synthetic_net_spec(hsz, "GRU", seed=sum(hsz))
+    T = 12
+    a = np.pi - 0.3
+    s = torch.tensor([a, 0.2, np.cos(a), np.sin(a), 0.03, -0.1], dtype=torch.float32)
+    rng = np.random.default_rng(K + hsz[0])
+    out = {}
+    for kern in ("fp32", "tensor"):
+        eng = Engine(K, T, integrator="neural", cost="quadratic_boundary_grad_minimal", device=0, net_kernel=kern)
+        eng.net_load(spec)
+        if kern == "fp32":
+            noise = torch.from_numpy(rng.standard_normal((eng.n_ind, K)).astype(np.float32)).to(eng.device)
+            h0 = rng.uniform(-0.5, 0.5, sum(hsz)).astype(np.float32)
+        eng.net_set_state(h0)
+        J = torch.empty(K, device=eng.device)
+        u = eng.mppi_step(s.to(eng.device), noise, L.TIME_MAJOR, 0.0, None, J)
+        torch.cuda.synchronize()
+        assert eng.net_last_kernel() == kern and eng.nonfinite_costs() == 0
+        out[kern] = (float(u.cpu()[0]), J.cpu().numpy(), eng.get_u_nom(), eng.net_get_state())
+        eng.close()
+    t, f = out["tensor"], out["fp32"]
+    eJ = vec_err(t[1], f[1])
+    record("tc_padded_widths_vs_fp32", f"{hsz[0]}x{hsz[1]}_K{K}", J=eJ, u=abs(t[0] - f[0]))
+    assert eJ < 2.5e-5    # measured <= 1.24e-5 (16 x 64, K = 500: rollouts on the boundary term's steep flank), else < 1e-5
+    assert abs(t[0] - f[0]) < 1e-5
+    np.testing.assert_allclose(t[2], f[2], rtol=0, atol=1e-5)
+    np.testing.assert_allclose(t[3], f[3], rtol=0, atol=5e-6)
