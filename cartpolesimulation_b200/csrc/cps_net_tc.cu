@@ -42,8 +42,13 @@ namespace {
 #include "cps_net_tc_common.cuh"
 }  // namespace
 
-template <bool MPPI>
+// NARROW: both layers have at most 32 units (the reference's shipped GRU-6IN-32H1-32H2-5OUT): the second half-layer jobs
+// (units 32..63) hold only padding -- their MMAs and epilogues are skipped, the hand-offs stay, so the pipeline's barrier
+// protocol is the same -- and the products over a hidden state take 2 k-steps instead of 4.
+template <bool MPPI, bool NARROW = false>
 __global__ void __launch_bounds__(TC_NT, 1) net_tc_kernel(const __grid_constant__ NetArgs a) {
+    constexpr int NKH = NARROW ? 2 : 4;
+    constexpr bool JB = !NARROW;
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint32_t s_tmem;
     // mbarriers: 0 weights landed; 1..3 region r complete (issuer -> epilogue); 4 output layer complete (issuer -> rows);
@@ -230,8 +235,8 @@ __global__ void __launch_bounds__(TC_NT, 1) net_tc_kernel(const __grid_constant_
         const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
         const uint32_t ah1_hi = tm + C_AH1_HI, ah1_lo = tm + C_AH1_LO, ah2_hi = tm + C_AH2_HI, ah2_lo = tm + C_AH2_LO;
         // recurrent parts of the first two jobs (1a, 1b of step 0); job j accumulates in region j mod 3
-        issue_H(tm + 0, ah1_hi, ah1_lo, sm0 + O_WHH1_HI, sm0 + O_WHH1_LO, 0, stk);
-        issue_H(tm + 128, ah1_hi, ah1_lo, sm0 + O_WHH1_HI, sm0 + O_WHH1_LO, 1, stk);
+        issue_H<NKH>(tm + 0, ah1_hi, ah1_lo, sm0 + O_WHH1_HI, sm0 + O_WHH1_LO, 0, stk);
+        if (JB) issue_H<NKH>(tm + 128, ah1_hi, ah1_lo, sm0 + O_WHH1_HI, sm0 + O_WHH1_LO, 1, stk);
         int t3 = 0;   // t mod 3 = (4 t) mod 3: region index of job 1a of this step
 #pragma unroll 1
         for (int t = 0; t < T; ++t) {
@@ -245,38 +250,38 @@ __global__ void __launch_bounds__(TC_NT, 1) net_tc_kernel(const __grid_constant_
             TC_TR(1);
             issue_X1(q0, AX_HI, AX_LO, sm0 + O_WIH1_HI, sm0 + O_WIH1_LO, 0, stk);
             tc_commit(doneb(t3));
-            issue_X1(q1, AX_HI, AX_LO, sm0 + O_WIH1_HI, sm0 + O_WIH1_LO, 1, stk);
+            if (JB) issue_X1(q1, AX_HI, AX_LO, sm0 + O_WIH1_HI, sm0 + O_WIH1_LO, 1, stk);
             tc_commit(doneb(i1));
             // (after the critical input products) recurrent part of job 2a; its region was read by job 2b of step t - 1
-            issue_H(q2, ah2_hi, ah2_lo, sm0 + O_WHH2_HI, sm0 + O_WHH2_LO, 0, stk);
+            issue_H<NKH>(q2, ah2_hi, ah2_lo, sm0 + O_WHH2_HI, sm0 + O_WHH2_LO, 0, stk);
             TC_TR(2);
             // job 1a's region is consumed as soon as its epilogue warps hold it in registers: the recurrent part
             // of job 2b goes there right away and runs under the gate arithmetic instead of between h1(t) and the second layer
             bar_wait(ldb, par);
             tc_fence_after();
             TC_TR(3);
-            issue_H(q0, ah2_hi, ah2_lo, sm0 + O_WHH2_HI, sm0 + O_WHH2_LO, 1, stk);
+            if (JB) issue_H<NKH>(q0, ah2_hi, ah2_lo, sm0 + O_WHH2_HI, sm0 + O_WHH2_LO, 1, stk);
             TC_TR(4);
             bar_wait(epib(0), par);
             bar_wait(epib(1), par); tc_fence_after();      // h1(t) complete
             TC_TR(5);
-            issue_X2(q2, ah1_hi, ah1_lo, sm0 + O_WIH2_HI, sm0 + O_WIH2_LO, 0, stk);
+            issue_X2<NKH>(q2, ah1_hi, ah1_lo, sm0 + O_WIH2_HI, sm0 + O_WIH2_LO, 0, stk);
             tc_commit(doneb(i2));
-            issue_X2(q0, ah1_hi, ah1_lo, sm0 + O_WIH2_HI, sm0 + O_WIH2_LO, 1, stk);
+            if (JB) issue_X2<NKH>(q0, ah1_hi, ah1_lo, sm0 + O_WIH2_HI, sm0 + O_WIH2_LO, 1, stk);
             tc_commit(doneb(t3));
-            if (more) issue_H(q1, ah1_hi, ah1_lo, sm0 + O_WHH1_HI, sm0 + O_WHH1_LO, 0, stk);
+            if (more) issue_H<NKH>(q1, ah1_hi, ah1_lo, sm0 + O_WHH1_HI, sm0 + O_WHH1_LO, 0, stk);
             TC_TR(6);
             bar_wait(epib(2), par); tc_fence_after();
             TC_TR(7);
             TC_TR(8);
             bar_wait(epib(3), par); tc_fence_after();      // h2(t) complete; the region of job 2b is idle
             TC_TR(9);
-            issue_OUT(q0 + C_NI, ah2_hi, ah2_lo, sm0 + O_WOUT_HI, sm0 + O_WOUT_LO, stk);
+            issue_OUT<NKH>(q0 + C_NI, ah2_hi, ah2_lo, sm0 + O_WOUT_HI, sm0 + O_WOUT_LO, stk);
             tc_commit(outb);
             TC_TR(10);
             // recurrent part of job 1b of the next step, behind the output layer: the tensor pipe executes in order, and in
             // front of it these 12 MMAs would sit between h2(t) and x(t + 1); here they run under the row warps' feedback
-            if (more) issue_H(q2, ah1_hi, ah1_lo, sm0 + O_WHH1_HI, sm0 + O_WHH1_LO, 1, stk);
+            if (more && JB) issue_H<NKH>(q2, ah1_hi, ah1_lo, sm0 + O_WHH1_HI, sm0 + O_WHH1_LO, 1, stk);
             t3 = i1;
         }
     } else if (is_epi) {
@@ -294,7 +299,9 @@ __global__ void __launch_bounds__(TC_NT, 1) net_tc_kernel(const __grid_constant_
                 bar_wait(doneb(j % 3), (uint32_t)((j / 3) & 1));
                 tc_fence_after();
                 if (warp == 8 * g) TC_TR(16 + 4 * job + 1);
-                if (two) {
+                if (!JB && g == 1) {
+                    // units 32..63 are padding in both layers: nothing to compute, their operand columns stay zero
+                } else if (two) {
 #pragma unroll 1
                     for (int e = 0; e < 2; ++e) {   // both 16-lane halves of 8 units at a time
                         const int cu = 16 * hs + 8 * e;   // first unit inside the job
@@ -632,7 +639,9 @@ int cps_net_tc_image_bytes() { return (int)TC_IMAGE_BYTES; }
 
 int cps_net_tc_launch(cps_handle *h, NetArgs &a, bool mppi, int n_rows) {
     const size_t smem = cps_net_tc_smem(&h->mp, mppi);
-    void (*fn)(const NetArgs) = mppi ? net_tc_kernel<true> : net_tc_kernel<false>;
+    const bool narrow = h->net->dev.hsz[0] <= 32 && h->net->dev.hsz[1] <= 32;
+    void (*fn)(const NetArgs) = narrow ? (mppi ? net_tc_kernel<true, true> : net_tc_kernel<false, true>)
+                                       : (mppi ? net_tc_kernel<true, false> : net_tc_kernel<false, false>);
     CUDA_TRY(h, cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // live rollouts per CTA: 32 or 64 while that still gives every CTA its own SM (see the kernel's comment on rpq)
     int sms = 148;

@@ -203,6 +203,10 @@ __device__ __forceinline__ void read_operand8_stacked(uint32_t tl, uint32_t c_hi
 // Recurrent part W_hh h: one N = 96 MMA per pass and k-step -> {NH, R, Z} of the region, overwriting it.
 // stk (warp-uniform): the A operand carries the hi parts in rows r and the lo parts in rows r + 8 of every 16-row group
 // ("stacked", see gru_epilogue): the a_lo pass is skipped, rows r + 8 accumulate it beside rows r in the SAME two MMAs.
+// NKS (compile time): k-steps of 16 units that carry live units of the A operand's layer -- 4 for 64 units, 2 when the layer has
+// at most 32 (the k-steps of a narrower layer's zero padding would add exact zeros).  A run-time bound here costs the
+// full-width kernel a third of its speed: the issue sequence has to stay straight-line.
+template <int NKS = 4>
 __device__ __forceinline__ void issue_H(uint32_t region, uint32_t ah_hi, uint32_t ah_lo, uint32_t bh_hi, uint32_t bh_lo, int jh, bool stk) {
     const uint32_t row = (uint32_t)jh * 12288u;   // 96 rows x (64 / 8) x 128 B / 8
 #pragma unroll
@@ -210,12 +214,13 @@ __device__ __forceinline__ void issue_H(uint32_t region, uint32_t ah_hi, uint32_
         if (stk && pass == 1) continue;
         const uint32_t a = (pass == 1) ? ah_lo : ah_hi, b = ((pass == 2) ? bh_lo : bh_hi) + row;
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks)
+        for (int ks = 0; ks < NKS; ++ks)
             tc_mma(region + C_NH, a + 8 * ks, make_desc(b + 256 * ks, 1024), idesc_f16(96), (pass | ks) != 0);
     }
 }
 // Input part of the second layer, W_ih2 h1 (K = 64): {R, Z} accumulate on top of the recurrent part, NI is written fresh
 // by the first MMA (split in two for that) and accumulated by the rest.
+template <int NKS = 4>
 __device__ __forceinline__ void issue_X2(uint32_t region, uint32_t ah_hi, uint32_t ah_lo, uint32_t bx_hi, uint32_t bx_lo, int jh, bool stk) {
     const uint32_t row = (uint32_t)jh * 12288u;
 #pragma unroll
@@ -223,7 +228,7 @@ __device__ __forceinline__ void issue_X2(uint32_t region, uint32_t ah_hi, uint32
         if (stk && pass == 1) continue;
         const uint32_t a = (pass == 1) ? ah_lo : ah_hi, b = ((pass == 2) ? bx_lo : bx_hi) + row;
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
+        for (int ks = 0; ks < NKS; ++ks) {
             if ((pass | ks) == 0) {
                 tc_mma(region + C_R, a, make_desc(b, 1024), idesc_f16(64), 1);
                 tc_mma(region + C_NI, a, make_desc(b + 8192, 1024), idesc_f16(32), 0);
@@ -250,13 +255,14 @@ __device__ __forceinline__ void issue_X1(uint32_t region, uint32_t ax_hi, uint32
     }
 }
 // Linear output layer W_out h2 -> 16 columns at `dst`.
+template <int NKS = 4>
 __device__ __forceinline__ void issue_OUT(uint32_t dst, uint32_t ah_hi, uint32_t ah_lo, uint32_t b_hi, uint32_t b_lo, bool stk) {
 #pragma unroll
     for (int pass = 0; pass < 3; ++pass) {
         if (stk && pass == 1) continue;
         const uint32_t a = (pass == 1) ? ah_lo : ah_hi, b = (pass == 2) ? b_lo : b_hi;
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks)
+        for (int ks = 0; ks < NKS; ++ks)
             tc_mma(dst, a + 8 * ks, make_desc(b + 256 * ks, 1024), idesc_f16(16), (pass | ks) != 0);
     }
 }
