@@ -45,8 +45,9 @@ def main(which):
             eng.close()
             done.append(f"cem K={K}")
     if "net" in which:
-        spec = synthetic_net_spec((64, 64), "GRU", seed=0)
-        for kern, K in (("tensor", 200), ("tensor", 4800), ("tensor", 9600), ("fp32", 200)):   # 32 / 64 / 128 live rollouts per CTA
+        for kern, K, hid in (("tensor", 200, 64), ("tensor", 4800, 64), ("tensor", 9600, 64), ("fp32", 200, 64),
+                             ("tensor", 200, 32), ("tensor", 9600, 32), ("tensor", 200, 48)):   # 32 / 64 / 128 live rollouts per CTA; narrow / padded nets
+            spec = synthetic_net_spec((hid, hid), "GRU", seed=0)
             T = 4
             eng = Engine(K, T, integrator="neural", cost="quadratic_boundary_grad_minimal", device=0, net_kernel=kern)
             eng.net_load(spec)
@@ -56,7 +57,7 @@ def main(which):
             torch.cuda.synchronize()
             assert np.isfinite(float(u.cpu()[0])) and eng.net_last_kernel() == kern
             eng.close()
-            done.append(f"net {kern} K={K}")
+            done.append(f"net {kern} K={K} H={hid}")
     if "rollout" in which:
         for B in (4096, 1 << 18):
             T = 4

@@ -28,6 +28,7 @@ print("ODE_v0", m["ODE_v0"]); print("ODE", m["ODE"]); print("K65536", m["ODE_K65
 r=json.loads(open("gpurun_out/bench_ref.json").read().strip().splitlines()[-1]); print("ref", r["value"], r["cpu_baseline"]["cores"])
 PY
 for K in 2000 4096 6000 8192 65536; do timeout 200 python tools/bench_net.py --K $K --kernel tensor 2>&1 | tail -2; done > gpurun_out/net_tc_timing.txt 2>&1
+for hk in "32 tensor" "32 fp32" "48 tensor"; do set -- $hk; timeout 200 python tools/bench_net.py --K 2000 --hidden $1 --kernel $2 2>&1 | tail -2; done >> gpurun_out/net_tc_timing.txt 2>&1
 timeout 300 python tools/bench_rpgd.py > gpurun_out/rpgd_timing.txt 2>&1
 NCU="ncu --set full --clock-control none --import-source on -f"
 timeout 600 $NCU -k regex:net_tc_kernel -s 3 -c 1 -o gpurun_out/r02_net_tc_K2000_v2 python tools/bench_net.py --K 2000 --kernel tensor --iters 3 > gpurun_out/ncu_net_tc.log 2>&1; echo "ncu net rc=$?"
