@@ -197,6 +197,10 @@ def mppi_latency(device, n_calls=1000):
                      "kernel_ms_median = CUDA events around one launch on an idle GPU (includes the host's launch latency), "
                      "kernel_ms_in_stream = device time per solve in a stream of 20 back-to-back solves")
     out["neural_GRU_2x64"] = neural_latency(device, n_calls=min(n_calls, 300))
+    try:
+        out["neural_GRU_2x32"] = neural_latency(device, n_calls=min(n_calls, 300), hidden=32)
+    except Exception as ex:
+        out["neural_GRU_2x32"] = {"error": repr(ex)}
     out["neural_GRU_2x64_K65536"] = neural_big(device)
     out["ODE_K65536_T100"] = big_solve(device)
     try:
@@ -433,14 +437,15 @@ def _event_times(fn, n, warm=5):
     return ts
 
 
-def neural_latency(device, n_calls=300):
+def neural_latency(device, n_calls=300, hidden=64):
     """BASELINE.json configs[2]: MPPI + autoregressive GRU (2x64 hidden), K=2000, T=50; synthetic seeded weights (no
-    dynamics model ships with the reference).  One launch per solve: rollout + cost + update + hidden-state step."""
+    dynamics model ships with the reference).  One launch per solve: rollout + cost + update + hidden-state step.
+    hidden = 32: the size of the network the reference's configuration names (GRU-6IN-32H1-32H2-5OUT-0)."""
     import torch
     from cartpolesimulation_b200.core import Engine
     from cartpolesimulation_b200.neural import net_flops_per_step, synthetic_net_spec
     K, T = 2000, 50
-    spec = synthetic_net_spec((64, 64), "GRU", seed=0)
+    spec = synthetic_net_spec((hidden, hidden), "GRU", seed=0)
     eng = Engine(K, T, integrator="neural", cost="quadratic_boundary_grad_minimal", device=device)
     eng.net_load(spec)
     a = np.pi - 1e-3
@@ -460,7 +465,7 @@ def neural_latency(device, n_calls=300):
            "kernel_ms_in_stream": float(np.median(_stream_times(lambda: eng.mppi_step(s, noise, 1, 0.0)))),
            "net_steps_per_s": K * T / (kms * 1e-3), "fp32_tflops": flops / (kms * 1e-3) / 1e12,
            "flop_per_solve": flops,
-           "api": "cps_mppi_step_host (numpy s -> float u); kernel: %s" % {"tensor": "net_tc_kernel<MPPI> (tcgen05)", "fp32": "net_kernel<16,64,MPPI> (FP32)"}.get(eng.net_last_kernel(), "?")}
+           "api": "cps_mppi_step_host (numpy s -> float u); kernel: %s" % {"tensor": "net_tc_kernel<MPPI> (tcgen05)", "fp32": "net_kernel<16,%d,MPPI> (FP32)" % hidden}.get(eng.net_last_kernel(), "?")}
     try:  # the same solve by the CPU oracle port (C, OpenMP), once, on the host cores
         from oracle import oracle as O
         eps = noise.t().contiguous().cpu().numpy()
