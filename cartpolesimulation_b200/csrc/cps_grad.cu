@@ -475,9 +475,10 @@ extern "C" int cps_plan_cost_grad(cps_handle *h, const float *s_dev, const float
     if (a.ode.n == 10) plan_grad_fwd_kernel<10><<<grid, block, 0, h->stream>>>(a);
     else plan_grad_fwd_kernel<0><<<grid, block, 0, h->stream>>>(a);
     if (T <= 512 && pairs <= 148LL * 1024) {   // beyond about one resident wave the 128-thread Jacobian kernel's occupancy wins
-        // plans per block: as many as fit 512 threads, but keep ~100 blocks for the Jacobians of small batches
+        // plans per block: small blocks (the Jacobian threads hold ~100 registers: 20 warps per SM whatever the block size, and
+        // finer blocks leave a shorter tail) as long as there are at least four blocks per SM
         int P = 1;
-        while (2 * P * T <= 512 && 2 * P <= 32 && K / (2 * P) >= 96) P *= 2;
+        while (2 * P * T <= 512 && 2 * P <= 32 && K / (2 * P) >= 592) P *= 2;
         const int threads = ((P * T + 31) / 32) * 32;
         const size_t smem = sizeof(float) * CPS_GRAD_REC * (size_t)P * T;
         void (*fn)(const GradArgs, int) = (a.ode.n == 10) ? plan_grad_jacrev_kernel<10> : plan_grad_jacrev_kernel<0>;
